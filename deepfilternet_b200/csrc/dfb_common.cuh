@@ -1,0 +1,118 @@
+// dfb_common.cuh -- shared host-side plumbing of libdfb200.so (error reporting, launch counter,
+// grow-only device arena) and the device tables of the DSP state.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/dfb200.h"
+
+namespace dfb {
+
+extern thread_local std::string g_err;
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define DFB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return dfb::fail(DFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                               \
+    } while (0)
+
+#define DFB_LAUNCH_CHECK()                                                                      \
+    do {                                                                                        \
+        dfb::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess)                                                                 \
+            return dfb::fail(DFB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                  \
+                             cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+
+// Selects `device` and verifies it is a Blackwell part; no CPU fallback exists.
+int use_device(int device);
+
+// Grow-only device arena: one cudaMalloc'd slab, bump allocated per call, reset between calls.
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, off = 0;
+    int reserve(size_t bytes);  // ensure capacity (may reallocate; invalidates old pointers)
+    void reset() { off = 0; }
+    template <typename T>
+    T *take(size_t n) {
+        size_t b = (n * sizeof(T) + 255) & ~size_t(255);
+        if (off + b > cap) return nullptr;
+        T *p = reinterpret_cast<T *>(base + off);
+        off += b;
+        return p;
+    }
+    void release();
+};
+
+constexpr int kMaxErb = 64;
+
+// Device-resident tables of one DSP state (fft 960 / hop 480 kernels).
+struct DspTables {
+    const float *window;     // [fft]
+    const float2 *tw_a_fwd;  // [24][20]  w480^{-lane k1}
+    const float2 *tw_a_inv;  // [24][20]  conj
+    const float2 *tw960;     // [241]     e^{-2 pi i k / 960}
+    const int *erb_off;      // [E + 1]
+    const float *erb_kinv;   // [E]  1 / width
+    const unsigned char *band_of_bin;  // [F]
+    float wnorm;
+    int fft, hop, F, E;
+};
+
+// Parameters of the fused apply + synthesis kernel (dfb_dsp.cu).
+// mode 0: plain ISTFT; 1: DeepFilterNet3 (DF on the noisy spectrum); 2: DeepFilterNet2 (DF on the
+// masked spectrum).
+struct ApplyParams {
+    const float2 *spec;   // [B,Tf,F]
+    const float *m;       // [B,Tf,E] or null
+    const float *coefs;   // [B,Tf,nb_df,2*order] or null
+    float *audio;         // [B, out_stride] or null
+    float2 *spec_out;     // optional [B,Tf,F]: enhanced spectrum (dfb_apply) or null
+    int64_t out_stride;
+    int64_t out_offset;   // first synthesised sample that is written (n_fft - hop when pad)
+    int64_t out_len;
+    int Tf, mode, nb_df, order, lookahead;
+    float atten_lim;      // 0 = off
+};
+
+}  // namespace dfb
+
+struct dfb_state;
+namespace dfb {
+int launch_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, float *d_erb_db,
+                    cudaStream_t s);
+int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float *d_spec, int Fd, int64_t spec_stride,
+                     int64_t C, int64_t Tf, float alpha, const float *d_erb_state, const float *d_unit_state,
+                     float *d_feat_erb, float *d_feat_spec, cudaStream_t s);
+int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaStream_t s);
+}  // namespace dfb
+
+struct dfb_state {
+    int device, sr, fft, hop, nb_erb, min_nb_erb_freqs;
+    std::vector<int64_t> erb;
+    std::vector<float> window;
+    void *d_tables = nullptr;  // one slab holding every table
+    dfb::DspTables tb{};
+    dfb::Arena arena;          // scratch of the *_host entry points
+    cudaStream_t stream = nullptr;
+};

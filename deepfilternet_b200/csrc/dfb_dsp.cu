@@ -1,0 +1,755 @@
+// dfb_dsp.cu -- analysis (windowed real FFT + ERB band energies), feature normalisation scans,
+// and the fused apply (ERB gain x spectrum + deep filter) + synthesis (irFFT + window + OLA)
+// kernels, plus the C-ABI entry points of the DSP state.
+//
+// Reference semantics (paths relative to /root/reference):
+//   frame_analysis        libDF/src/lib.rs:356-394     (pyDF/src/lib.rs:41-72 batches it)
+//   compute_band_corr     libDF/src/lib.rs:280-295, dB at :207-210
+//   band_mean_norm_erb    libDF/src/lib.rs:244-251
+//   band_unit_norm        libDF/src/lib.rs:253-259
+//   apply_interp_band_gain libDF/src/lib.rs:314-326 == Mask.forward DeepFilterNet/df/modules.py:266-269
+//   MF.DF                 DeepFilterNet/df/multiframe.py:72-74,126-136,169-180
+//   frame_synthesis       libDF/src/lib.rs:396-427     (pyDF/src/lib.rs:74-107)
+//
+// HBM layout: audio f32[B,T]; spec c64[B,Tf,481] (frame-major, 3848 B rows); features
+// f32[B,Tf,32] and c64[B,Tf,96]; every kernel reads/writes whole rows with consecutive lanes on
+// consecutive addresses.
+#include <cmath>
+#include <cstring>
+
+#include "dfb_common.cuh"
+#include "dfb_fft.cuh"
+
+namespace dfb {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(DFB_ERR_CUDA, "no CUDA device available (%s); libdfb200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(DFB_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    DFB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    DFB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        return fail(DFB_ERR_CUDA, "device %d is sm_%d%d; libdfb200 is built for sm_100a only", device, p.major,
+                    p.minor);
+    return DFB_OK;
+}
+
+int Arena::reserve(size_t bytes) {
+    if (bytes <= cap) return DFB_OK;
+    if (base) {
+        DFB_CUDA(cudaDeviceSynchronize());
+        DFB_CUDA(cudaFree(base));
+        base = nullptr;
+        cap = 0;
+    }
+    size_t want = (bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMalloc(&base, want);
+    if (e != cudaSuccess) {
+        base = nullptr;
+        return fail(DFB_ERR_OOM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return DFB_OK;
+}
+void Arena::release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = off = 0;
+}
+
+// ============================================================================ kernels =====
+
+constexpr int kFft = 960, kHop = 480, kF = 481;
+constexpr int kAnaWarps = 8;           // frames per CTA in the analysis kernel (one per warp)
+constexpr int kSynWarps = 4;           // warps per CTA in the synthesis kernel
+constexpr int kSynChunk = 16;          // consecutive frames per warp in the synthesis kernel
+constexpr int kAnaSmem = sizeof(float) * ((kAnaWarps + 1) * 480 + 960) + sizeof(float2) * (242 + kAnaWarps * kTileFloat2);
+
+// One warp: 480-point complex FFT of the values gathered by `load(n)` (n = 24 n1 + lane), result
+// in natural order in buf[0..480).  `buf` is a per-warp shared buffer of kTileFloat2 float2 that
+// serves as the pass-A/B transpose tile and then as the natural-order output; `load` may read it.
+template <bool INV, typename LoadF>
+__device__ __forceinline__ void warp_fft480(LoadF load, const float2 (&tw)[kN1], float2 *buf, int lane) {
+    float2 a[kN1];
+    if (lane < kN2) {
+#pragma unroll
+        for (int n1 = 0; n1 < kN1; n1++) a[n1] = load(kN2 * n1 + lane);
+    }
+    __syncwarp();
+    if (lane < kN2) fft480_pass_a<INV>(a, tw, buf, lane);
+    __syncwarp();
+    float2 b[kN2];
+    if (lane < kN1) fft480_pass_b<INV>(b, buf, lane);
+    __syncwarp();
+    if (lane < kN1) fft480_store_natural(b, buf, lane);
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------- analysis ----
+// grid (ceil(Tf / kAnaWarps), B), block 32 * kAnaWarps.  Warp w transforms frame t0 + w.
+// Algorithmic HBM bytes per frame: 1920 R (audio hop) + 3848 W (spec) + 128 W (erb dB).
+__global__ void __launch_bounds__(32 * kAnaWarps)
+k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restrict__ spec,
+           float *__restrict__ erb_db, DspTables tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_stage = reinterpret_cast<float *>(smem_raw);                    // (W + 1) * hop
+    float *s_win = s_stage + (kAnaWarps + 1) * kHop;                         // fft
+    float2 *s_tw960 = reinterpret_cast<float2 *>(s_win + kFft);              // 241 (+1 pad)
+    float2 *s_buf = s_tw960 + 242;                                           // W * kTileFloat2
+    const int b = blockIdx.y, t0 = blockIdx.x * kAnaWarps;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *x = audio + (int64_t)b * T;
+    // stage samples [(t0-1)*hop, (t0+W)*hop); zeros before the stream start (analysis_mem = 0)
+    const int64_t s0 = (int64_t)(t0 - 1) * kHop;
+    const int64_t s_end = (int64_t)Tf * kHop;
+    for (int i = tid; i < (kAnaWarps + 1) * kHop; i += blockDim.x) {
+        int64_t s = s0 + i;
+        s_stage[i] = (s >= 0 && s < s_end) ? __ldg(x + s) : 0.f;
+    }
+    for (int i = tid; i < kFft; i += blockDim.x) s_win[i] = tb.window[i];
+    for (int i = tid; i < 241; i += blockDim.x) s_tw960[i] = tb.tw960[i];
+    float2 tw[kN1];
+#pragma unroll
+    for (int k1 = 0; k1 < kN1; k1++) tw[k1] = lane < kN2 ? tb.tw_a_fwd[lane * kN1 + k1] : make_float2(0.f, 0.f);
+    __syncthreads();
+    const int t = t0 + warp;
+    if (t >= Tf) return;
+    const float *fr = s_stage + warp * kHop;  // frame t = samples [(t-1) hop, (t+1) hop)
+    float2 *nat = s_buf + warp * kTileFloat2;
+    warp_fft480<false>(
+        [&](int n) {
+            float2 v = *reinterpret_cast<const float2 *>(fr + 2 * n);
+            float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * n);
+            return make_float2(v.x * w.x, v.y * w.y);
+        },
+        tw, nat, lane);
+    // split step + wnorm, write spec row, keep |X|^2 for the band energies
+    float2 *row = spec + ((int64_t)b * Tf + t) * kF;
+    float pk[8], pnk[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int k = lane + 32 * j;
+        pk[j] = pnk[j] = 0.f;
+        if (k <= 240) {
+            float2 zk = nat[k], znk = nat[(kC - k) % kC];
+            float2 xk, xnk;
+            rfft_split(zk, znk, s_tw960[k], xk, xnk);
+            xk.x *= tb.wnorm; xk.y *= tb.wnorm;
+            xnk.x *= tb.wnorm; xnk.y *= tb.wnorm;
+            row[k] = xk;
+            if (k != 240) row[kC - k] = xnk;
+            pk[j] = __fadd_rn(__fmul_rn(xk.x, xk.x), __fmul_rn(xk.y, xk.y));
+            pnk[j] = __fadd_rn(__fmul_rn(xnk.x, xnk.x), __fmul_rn(xnk.y, xnk.y));
+        }
+    }
+    if (erb_db == nullptr) return;
+    __syncwarp();
+    float *P = reinterpret_cast<float *>(nat);  // 481 floats, reuses the natural-order buffer
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int k = lane + 32 * j;
+        if (k <= 240) {
+            P[k] = pk[j];
+            if (k != 240) P[kC - k] = pnk[j];
+        }
+    }
+    __syncwarp();
+    // band energies: sequential sum inside each band, factor 1/width inside the sum (lib.rs:288-292)
+    for (int band = lane; band < tb.E; band += 32) {
+        int o = tb.erb_off[band], n = tb.erb_off[band + 1] - o;
+        float kinv = tb.erb_kinv[band];
+        float acc = 0.f;
+        for (int j = 0; j < n; j++) acc = __fadd_rn(acc, __fmul_rn(P[o + j], kinv));
+        erb_db[((int64_t)b * Tf + t) * tb.E + band] = __fmul_rn(log10f(__fadd_rn(acc, 1e-10f)), 10.f);
+    }
+}
+
+// ----------------------------------------------------------- generic ERB (libdf.erb) ----
+// one warp per frame, arbitrary F / E (API parity path, not the hot path)
+__global__ void k_erb(const float2 *__restrict__ spec, int64_t n_frames, int F, const int *__restrict__ off,
+                      int E, int db, float *__restrict__ out) {
+    int64_t fr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (fr >= n_frames) return;
+    const float2 *x = spec + fr * F;
+    for (int band = lane; band < E; band += 32) {
+        int o = off[band], n = off[band + 1] - o;
+        float kinv = __fdiv_rn(1.f, (float)n);
+        float acc = 0.f;
+        for (int j = 0; j < n; j++) {
+            float2 v = x[o + j];
+            acc = __fadd_rn(acc, __fmul_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), kinv));
+        }
+        out[fr * E + band] = db ? __fmul_rn(log10f(__fadd_rn(acc, 1e-10f)), 10.f) : acc;
+    }
+}
+
+__global__ void k_erb_inv(const float *__restrict__ gains, int64_t n_frames, int F, int E,
+                          const unsigned char *__restrict__ band_of_bin, float *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frames * F) return;
+    int64_t fr = i / F;
+    int k = (int)(i - fr * F);
+    out[i] = gains[fr * E + band_of_bin[k]];
+}
+
+// ------------------------------------------------------------- feature norm scans ----
+// Exponential mean norm of the ERB dB features and exponential unit norm of the first Fd bins,
+// sequential in t per (stream, band | bin) exactly like the reference loops.
+// grid B, block E + Fd threads (thread j < E: band j; else bin j - E).  Loads are batched kPf
+// frames ahead so the dependent chain is arithmetic only.
+constexpr int kPf = 8;
+__global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
+                            const float2 *__restrict__ spec_in, int Fd, int64_t spec_stride_t, int Tf,
+                            float alpha, const float *__restrict__ erb_state, const float *__restrict__ unit_state,
+                            float *feat_erb, float2 *__restrict__ feat_spec) {
+    const int b = blockIdx.x, j = threadIdx.x;
+    const float one_m_alpha = __fsub_rn(1.f, alpha);
+    if (j < E) {
+        const float *src = erb_in + (int64_t)b * Tf * erb_stride_t + j;
+        float *dst = feat_erb + (int64_t)b * Tf * E + j;
+        float s;
+        if (erb_state) s = erb_state[(int64_t)b * E + j];
+        else s = (E == 1) ? -60.f : __fadd_rn(-60.f, __fmul_rn((float)j, __fdiv_rn(-30.f, (float)(E - 1))));
+        for (int t = 0; t < Tf; t += kPf) {
+            float v[kPf];
+#pragma unroll
+            for (int u = 0; u < kPf; u++) v[u] = (t + u < Tf) ? src[(int64_t)(t + u) * erb_stride_t] : 0.f;
+#pragma unroll
+            for (int u = 0; u < kPf; u++) {
+                if (t + u < Tf) {
+                    s = __fadd_rn(__fmul_rn(v[u], one_m_alpha), __fmul_rn(s, alpha));
+                    dst[(int64_t)(t + u) * E] = __fdiv_rn(__fsub_rn(v[u], s), 40.f);
+                }
+            }
+        }
+    } else if (j < E + Fd) {
+        const int k = j - E;
+        const float2 *src = spec_in + (int64_t)b * Tf * spec_stride_t + k;
+        float2 *dst = feat_spec + (int64_t)b * Tf * Fd + k;
+        float s;
+        if (unit_state) s = unit_state[(int64_t)b * Fd + k];
+        else s = (Fd == 1) ? 0.001f : __fadd_rn(0.001f, __fmul_rn((float)k, __fdiv_rn(__fsub_rn(0.0001f, 0.001f), (float)(Fd - 1))));
+        for (int t = 0; t < Tf; t += kPf) {
+            float2 v[kPf];
+#pragma unroll
+            for (int u = 0; u < kPf; u++)
+                v[u] = (t + u < Tf) ? src[(int64_t)(t + u) * spec_stride_t] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kPf; u++) {
+                if (t + u < Tf) {
+                    float nrm = hypotf(v[u].x, v[u].y);
+                    s = __fadd_rn(__fmul_rn(nrm, one_m_alpha), __fmul_rn(s, alpha));
+                    float d = __fsqrt_rn(s);
+                    dst[(int64_t)(t + u) * Fd] = make_float2(__fdiv_rn(v[u].x, d), __fdiv_rn(v[u].y, d));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------ fused apply + synthesis ----
+// mode 0: plain ISTFT of `spec` (pyDF DF.synthesis)
+// mode 1: DeepFilterNet3: bins < nb_df <- deep filter of the NOISY spectrum, bins >= nb_df <- spec * gain
+// mode 2: DeepFilterNet2: spectrum masked first (all bins), deep filter applied to the masked spectrum
+// Optional attenuation limit: X <- noisy * lim + X * (1 - lim)   (enhance.py:238-240)
+// One warp owns kSynChunk consecutive frames of one stream and keeps the overlap tail in registers;
+// it re-synthesises frame t0-1 to obtain the tail of its first frame.
+// Algorithmic HBM bytes per frame (mode 1/2): 3848 R spec + 128 R m + 3840 R coefs + 1920 W audio.
+
+__device__ __forceinline__ float2 apply_bin(const ApplyParams &p, const DspTables &tb, const float2 *srow0,
+                                            const float *mrow0, const float *crow, int t, int k) {
+    // srow0 / mrow0: row pointers of frame 0 of this stream
+    float2 x = srow0[(int64_t)t * kF + k];
+    float2 y;
+    if (p.mode == 0) return x;
+    const int band = tb.band_of_bin[k];
+    if (k >= p.nb_df) {
+        float g = mrow0[(int64_t)t * tb.E + band];
+        y = make_float2(x.x * g, x.y * g);
+    } else {
+        // Y[t,k] = sum_o S[t + o - (O-1-L), k] * W[o,t,k]   (multiframe.py:72-74,126-136)
+        const float *c = crow + (int64_t)k * (2 * p.order);
+        float yr = 0.f, yi = 0.f;
+        for (int o = 0; o < p.order; o++) {
+            int tt = t + o - (p.order - 1 - p.lookahead);
+            if (tt < 0 || tt >= p.Tf) continue;
+            float2 s = srow0[(int64_t)tt * kF + k];
+            if (p.mode == 2) {
+                float g = mrow0[(int64_t)tt * tb.E + band];
+                s.x *= g; s.y *= g;
+            }
+            float wr = c[2 * o], wi = c[2 * o + 1];
+            yr += s.x * wr - s.y * wi;
+            yi += s.x * wi + s.y * wr;
+        }
+        y = make_float2(yr, yi);
+    }
+    if (p.atten_lim > 0.f) {
+        y.x = x.x * p.atten_lim + y.x * (1.f - p.atten_lim);
+        y.y = x.y * p.atten_lim + y.y * (1.f - p.atten_lim);
+    }
+    return y;
+}
+
+__global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis(ApplyParams p, DspTables tb) {
+    __shared__ __align__(16) float s_win[kFft];
+    __shared__ __align__(16) float2 s_tw960[241];
+    __shared__ __align__(16) float2 s_buf[kSynWarps][kTileFloat2];
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kFft; i += blockDim.x) s_win[i] = tb.window[i];
+    for (int i = tid; i < 241; i += blockDim.x) s_tw960[i] = tb.tw960[i];
+    float2 tw[kN1];
+#pragma unroll
+    for (int k1 = 0; k1 < kN1; k1++) tw[k1] = lane < kN2 ? tb.tw_a_inv[lane * kN1 + k1] : make_float2(0.f, 0.f);
+    __syncthreads();
+    const int t0 = (blockIdx.x * kSynWarps + warp) * kSynChunk;
+    if (t0 >= p.Tf) return;
+    const int t1 = min(t0 + kSynChunk, p.Tf);
+    const float2 *srow0 = p.spec + (int64_t)b * p.Tf * kF;
+    const float *mrow0 = p.m ? p.m + (int64_t)b * p.Tf * tb.E : nullptr;
+    float2 *nat = s_buf[warp];
+    float *yb = reinterpret_cast<float *>(nat);  // 960 windowed samples of the current frame
+    float tail[15];
+#pragma unroll
+    for (int j = 0; j < 15; j++) tail[j] = 0.f;
+    for (int t = (t0 > 0 ? t0 - 1 : 0); t < t1; t++) {
+        const float *crow = p.coefs ? p.coefs + ((int64_t)b * p.Tf + t) * p.nb_df * (2 * p.order) : nullptr;
+        // gather X[k], X[480-k], merge into Z (natural order in `nat`)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int k = lane + 32 * j;
+            if (k <= 240) {
+                float2 xk = apply_bin(p, tb, srow0, mrow0, crow, t, k);
+                float2 xnk = apply_bin(p, tb, srow0, mrow0, crow, t, kC - k);
+                if (p.spec_out && t >= t0) {
+                    float2 *orow = p.spec_out + ((int64_t)b * p.Tf + t) * kF;
+                    orow[k] = xk;
+                    orow[kC - k] = xnk;
+                }
+                if (k == 0) { xk.y = 0.f; xnk.y = 0.f; }  // imag of DC / Nyquist ignored (lib.rs:402)
+                float2 w = s_tw960[k];
+                float2 zk, znk;
+                irfft_merge(xk, xnk, make_float2(w.x, -w.y), zk, znk);
+                nat[k] = zk;
+                if (k > 0 && k < 240) nat[kC - k] = znk;
+            }
+        }
+        __syncwarp();
+        if (p.audio) {
+            // reads of nat complete inside pass A before pass B overwrites it (warp syncs inside)
+            warp_fft480<true>([&](int n) { return nat[n]; }, tw, nat, lane);
+            // nat[n] = (x[2n], x[2n+1]); window in place
+#pragma unroll
+            for (int j = 0; j < 15; j++) {
+                int n = lane + 32 * j;
+                float2 v = nat[n];
+                float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * n);
+                nat[n] = make_float2(v.x * w.x, v.y * w.y);
+            }
+            __syncwarp();
+            float *orow = p.audio + (int64_t)b * p.out_stride;
+#pragma unroll
+            for (int j = 0; j < 15; j++) {
+                int i = lane + 32 * j;
+                float o = yb[i] + tail[j];      // lib.rs:407-411
+                tail[j] = yb[kHop + i];         // lib.rs:423-426 (hop == fft/2)
+                int64_t g = (int64_t)t * kHop + i - p.out_offset;
+                if (t >= t0 && g >= 0 && g < p.out_len) orow[g] = o;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace dfb
+
+// ====================================================================== host side / C ABI ==
+using namespace dfb;
+
+extern "C" const char *dfb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *dfb_version(void) { return "dfb200 0.1.0 sm_100a"; }
+extern "C" int64_t dfb_kernel_launches(void) { return g_launches.load(); }
+
+// libDF/src/lib.rs:42-47,68-100 (f32 arithmetic, integer result)
+extern "C" int dfb_erb_widths(int sr, int fft_size, int nb_erb, int min_nb_freqs, int64_t *out) {
+    if (!out || nb_erb <= 0 || nb_erb > kMaxErb || fft_size <= 0) return fail(DFB_ERR_INVALID, "bad erb parameters");
+    auto freq2erb = [](float f) { return 9.265f * log1pf(f / (24.7f * 9.265f)); };
+    auto erb2freq = [](float e) { return 24.7f * 9.265f * (expf(e / 9.265f) - 1.f); };
+    int nyq = sr / 2;
+    float freq_width = (float)sr / (float)fft_size;
+    float erb_low = freq2erb(0.f), erb_high = freq2erb((float)nyq);
+    float step = (erb_high - erb_low) / (float)nb_erb;
+    int prev_freq = 0, freq_over = 0;
+    for (int i = 1; i <= nb_erb; i++) {
+        float f = erb2freq(erb_low + (float)i * step);
+        int fb = (int)roundf(f / freq_width);
+        int nb = fb - prev_freq - freq_over;
+        if (nb < min_nb_freqs) {
+            freq_over = min_nb_freqs - nb;
+            nb = min_nb_freqs;
+        } else {
+            freq_over = 0;
+        }
+        out[i - 1] = nb;
+        prev_freq = fb;
+    }
+    out[nb_erb - 1] += 1;
+    int64_t sum = 0;
+    for (int i = 0; i < nb_erb; i++) sum += out[i];
+    int64_t too_large = sum - (fft_size / 2 + 1);
+    if (too_large > 0) out[nb_erb - 1] -= too_large;
+    return DFB_OK;
+}
+
+extern "C" int dfb_state_create(dfb_state **out, int device, int sr, int fft_size, int hop_size, int nb_erb,
+                                int min_nb_erb_freqs) {
+    if (!out) return fail(DFB_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (hop_size * 2 > fft_size) return fail(DFB_ERR_INVALID, "assertion failed: hop_size * 2 <= fft_size");
+    if (fft_size != kFft || hop_size != kHop)
+        return fail(DFB_ERR_UNSUPPORTED, "built kernels cover fft_size=960, hop_size=480 (got %d, %d)", fft_size,
+                    hop_size);
+    if (nb_erb <= 0 || nb_erb > kMaxErb) return fail(DFB_ERR_INVALID, "nb_erb out of range");
+    int rc = use_device(device);
+    if (rc) return rc;
+    dfb_state *st = new dfb_state();
+    st->device = device; st->sr = sr; st->fft = fft_size; st->hop = hop_size; st->nb_erb = nb_erb;
+    st->min_nb_erb_freqs = min_nb_erb_freqs;
+    st->erb.resize(nb_erb);
+    dfb_erb_widths(sr, fft_size, nb_erb, min_nb_erb_freqs, st->erb.data());
+    const int F = fft_size / 2 + 1;
+    // vorbis window, f64 -> f32 (lib.rs:126-132)
+    st->window.resize(fft_size);
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < fft_size; i++) {
+        double s = sin(0.5 * pi * ((double)i + 0.5) / (double)(fft_size / 2));
+        st->window[i] = (float)sin(0.5 * pi * s * s);
+    }
+    // one slab: window | tw_a_fwd | tw_a_inv | tw960 | erb_off | erb_kinv | band_of_bin
+    std::vector<float2> twf(kN2 * kN1), twi(kN2 * kN1), tw960(241);
+    for (int l = 0; l < kN2; l++)
+        for (int k1 = 0; k1 < kN1; k1++) {
+            double a = 2.0 * pi * (double)((l * k1) % kC) / (double)kC;
+            twf[l * kN1 + k1] = make_float2((float)cos(a), (float)-sin(a));
+            twi[l * kN1 + k1] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int k = 0; k <= 240; k++) {
+        double a = 2.0 * pi * (double)k / (double)kFft;
+        tw960[k] = make_float2((float)cos(a), (float)-sin(a));
+    }
+    std::vector<int> off(nb_erb + 1, 0);
+    std::vector<float> kinv(nb_erb);
+    std::vector<unsigned char> bob(F);
+    for (int b = 0; b < nb_erb; b++) {
+        off[b + 1] = off[b] + (int)st->erb[b];
+        kinv[b] = 1.f / (float)st->erb[b];
+        for (int k = off[b]; k < off[b + 1] && k < F; k++) bob[k] = (unsigned char)b;
+    }
+    if (off[nb_erb] != F) {
+        delete st;
+        return fail(DFB_ERR_INVALID, "erb widths sum to %d, expected %d", off[nb_erb], F);
+    }
+    size_t o_win = 0, o_twf = o_win + sizeof(float) * fft_size, o_twi = o_twf + sizeof(float2) * twf.size(),
+           o_960 = o_twi + sizeof(float2) * twi.size(), o_off = o_960 + sizeof(float2) * 256,
+           o_kinv = o_off + sizeof(int) * (kMaxErb + 1 + 3), o_bob = o_kinv + sizeof(float) * kMaxErb,
+           total = o_bob + ((F + 255) & ~255);
+    std::vector<char> slab(total, 0);
+    memcpy(slab.data() + o_win, st->window.data(), sizeof(float) * fft_size);
+    memcpy(slab.data() + o_twf, twf.data(), sizeof(float2) * twf.size());
+    memcpy(slab.data() + o_twi, twi.data(), sizeof(float2) * twi.size());
+    memcpy(slab.data() + o_960, tw960.data(), sizeof(float2) * tw960.size());
+    memcpy(slab.data() + o_off, off.data(), sizeof(int) * off.size());
+    memcpy(slab.data() + o_kinv, kinv.data(), sizeof(float) * kinv.size());
+    memcpy(slab.data() + o_bob, bob.data(), bob.size());
+    char *d = nullptr;
+    if (cudaMalloc(&d, total) != cudaSuccess || cudaMemcpy(d, slab.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete st;
+        return fail(DFB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    st->d_tables = d;
+    st->tb.window = (const float *)(d + o_win);
+    st->tb.tw_a_fwd = (const float2 *)(d + o_twf);
+    st->tb.tw_a_inv = (const float2 *)(d + o_twi);
+    st->tb.tw960 = (const float2 *)(d + o_960);
+    st->tb.erb_off = (const int *)(d + o_off);
+    st->tb.erb_kinv = (const float *)(d + o_kinv);
+    st->tb.band_of_bin = (const unsigned char *)(d + o_bob);
+    st->tb.wnorm = 1.f / ((float)((int64_t)fft_size * fft_size) / (float)(2 * hop_size));  // lib.rs:133
+    st->tb.fft = fft_size; st->tb.hop = hop_size; st->tb.F = F; st->tb.E = nb_erb;
+    cudaFuncSetAttribute(k_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, kAnaSmem);
+    if (cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaFree(d);
+        delete st;
+        return fail(DFB_ERR_CUDA, "stream creation failed");
+    }
+    *out = st;
+    return DFB_OK;
+}
+
+extern "C" void dfb_state_free(dfb_state *st) {
+    if (!st) return;
+    cudaSetDevice(st->device);
+    st->arena.release();
+    if (st->d_tables) cudaFree(st->d_tables);
+    if (st->stream) cudaStreamDestroy(st->stream);
+    delete st;
+}
+
+extern "C" int dfb_state_erb_widths(const dfb_state *st, int64_t *w) {
+    if (!st || !w) return fail(DFB_ERR_INVALID, "null argument");
+    memcpy(w, st->erb.data(), sizeof(int64_t) * st->nb_erb);
+    return DFB_OK;
+}
+extern "C" int dfb_state_fft_window(const dfb_state *st, float *w) {
+    if (!st || !w) return fail(DFB_ERR_INVALID, "null argument");
+    memcpy(w, st->window.data(), sizeof(float) * st->fft);
+    return DFB_OK;
+}
+extern "C" int dfb_state_params(const dfb_state *st, int *sr, int *fft, int *hop, int *nb_erb) {
+    if (!st) return fail(DFB_ERR_INVALID, "null state");
+    if (sr) *sr = st->sr;
+    if (fft) *fft = st->fft;
+    if (hop) *hop = st->hop;
+    if (nb_erb) *nb_erb = st->nb_erb;
+    return DFB_OK;
+}
+
+namespace dfb {
+
+int launch_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, float *d_erb_db,
+                    cudaStream_t s) {
+    int64_t Tf = T / st->hop;
+    if (C <= 0 || Tf <= 0) return DFB_OK;
+    if (C > 65535) return fail(DFB_ERR_INVALID, "more than 65535 channels per call");
+    dim3 grid((unsigned)((Tf + kAnaWarps - 1) / kAnaWarps), (unsigned)C);
+    k_analysis<<<grid, 32 * kAnaWarps, kAnaSmem, s>>>(d_audio, T, (int)Tf, (float2 *)d_spec, d_erb_db, st->tb);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+}
+
+int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float *d_spec, int Fd, int64_t spec_stride,
+                     int64_t C, int64_t Tf, float alpha, const float *d_erb_state, const float *d_unit_state,
+                     float *d_feat_erb, float *d_feat_spec, cudaStream_t s) {
+    if (C <= 0 || Tf <= 0 || E + Fd == 0) return DFB_OK;
+    if (E + Fd > 1024) return fail(DFB_ERR_INVALID, "E + F > 1024 in norm scan");
+    int threads = ((E + Fd + 31) / 32) * 32;
+    k_feat_norm<<<(unsigned)C, threads, 0, s>>>(d_erb, E, erb_stride, (const float2 *)d_spec, Fd, spec_stride, (int)Tf,
+                                               alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+}
+
+int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaStream_t s) {
+    if (B <= 0 || p.Tf <= 0) return DFB_OK;
+    if (B > 65535) return fail(DFB_ERR_INVALID, "more than 65535 channels per call");
+    if (p.mode != 0 && (p.nb_df > 240 || p.order > 8)) return fail(DFB_ERR_UNSUPPORTED, "nb_df > 240 or df_order > 8");
+    int per_cta = kSynWarps * kSynChunk;
+    dim3 grid((unsigned)((p.Tf + per_cta - 1) / per_cta), (unsigned)B);
+    k_apply_synthesis<<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+}
+
+}  // namespace dfb
+
+extern "C" int dfb_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, void *stream) {
+    if (!st || !d_audio || !d_spec) return fail(DFB_ERR_INVALID, "null argument");
+    DFB_CUDA(cudaSetDevice(st->device));
+    return launch_analysis(st, d_audio, C, T, d_spec, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int dfb_analysis_host(dfb_state *st, const float *h_audio, int64_t C, int64_t T, float *h_spec) {
+    if (!st || !h_audio || !h_spec) return fail(DFB_ERR_INVALID, "null argument");
+    if (C <= 0 || T <= 0) return fail(DFB_ERR_INVALID, "[df] Input array empty or not contiguous.");
+    DFB_CUDA(cudaSetDevice(st->device));
+    int64_t Tf = T / st->hop;
+    size_t nb_in = sizeof(float) * C * T, nb_out = sizeof(float) * 2 * C * Tf * st->tb.F;
+    int rc = st->arena.reserve(nb_in + nb_out + 1024);
+    if (rc) return rc;
+    st->arena.reset();
+    float *d_in = st->arena.take<float>(C * T), *d_out = st->arena.take<float>(2 * C * Tf * st->tb.F + 2);
+    DFB_CUDA(cudaMemcpyAsync(d_in, h_audio, nb_in, cudaMemcpyHostToDevice, st->stream));
+    rc = launch_analysis(st, d_in, C, T, d_out, nullptr, st->stream);
+    if (rc) return rc;
+    if (nb_out) DFB_CUDA(cudaMemcpyAsync(h_spec, d_out, nb_out, cudaMemcpyDeviceToHost, st->stream));
+    DFB_CUDA(cudaStreamSynchronize(st->stream));
+    return DFB_OK;
+}
+
+extern "C" int dfb_synthesis(dfb_state *st, const float *d_spec, int64_t C, int64_t Tf, float *d_audio, void *stream) {
+    if (!st || !d_spec || !d_audio) return fail(DFB_ERR_INVALID, "null argument");
+    DFB_CUDA(cudaSetDevice(st->device));
+    ApplyParams p{};
+    p.spec = (const float2 *)d_spec; p.audio = d_audio; p.out_stride = Tf * st->hop; p.out_offset = 0;
+    p.out_len = Tf * st->hop; p.Tf = (int)Tf; p.mode = 0;
+    return launch_apply_synthesis(st, p, C, (cudaStream_t)stream);
+}
+
+extern "C" int dfb_synthesis_host(dfb_state *st, const float *h_spec, int64_t C, int64_t Tf, float *h_audio) {
+    if (!st || !h_spec || !h_audio) return fail(DFB_ERR_INVALID, "null argument");
+    if (C <= 0 || Tf <= 0) return fail(DFB_ERR_INVALID, "[df] Input array empty or not contiguous.");
+    DFB_CUDA(cudaSetDevice(st->device));
+    size_t nb_in = sizeof(float) * 2 * C * Tf * st->tb.F, nb_out = sizeof(float) * C * Tf * st->hop;
+    int rc = st->arena.reserve(nb_in + nb_out + 1024);
+    if (rc) return rc;
+    st->arena.reset();
+    float *d_in = st->arena.take<float>(2 * C * Tf * st->tb.F), *d_out = st->arena.take<float>(C * Tf * st->hop);
+    DFB_CUDA(cudaMemcpyAsync(d_in, h_spec, nb_in, cudaMemcpyHostToDevice, st->stream));
+    rc = dfb_synthesis(st, d_in, C, Tf, d_out, st->stream);
+    if (rc) return rc;
+    DFB_CUDA(cudaMemcpyAsync(h_audio, d_out, nb_out, cudaMemcpyDeviceToHost, st->stream));
+    DFB_CUDA(cudaStreamSynchronize(st->stream));
+    return DFB_OK;
+}
+
+namespace {
+// tiny RAII scratch for the stateless *_host helpers
+struct Scratch {
+    std::vector<void *> ptrs;
+    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T>
+    T *alloc(size_t n) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return (T *)p;
+    }
+};
+}  // namespace
+
+extern "C" int dfb_erb_host(int device, const float *h_spec, int64_t n_frames, int64_t F, const int64_t *widths, int E,
+                            int db, float *h_out) {
+    if (!h_spec || !widths || !h_out || n_frames <= 0 || F <= 0 || E <= 0) return fail(DFB_ERR_INVALID, "bad argument");
+    std::vector<int> off(E + 1, 0);
+    for (int b = 0; b < E; b++) off[b + 1] = off[b] + (int)widths[b];
+    if (off[E] != F) return fail(DFB_ERR_INVALID, "DF shape error: erb widths sum to %d but input has %lld bins", off[E], (long long)F);
+    int rc = use_device(device);
+    if (rc) return rc;
+    Scratch s;
+    float2 *d_in = s.alloc<float2>(n_frames * F);
+    float *d_out = s.alloc<float>(n_frames * E);
+    int *d_off = s.alloc<int>(E + 1);
+    if (!d_in || !d_out || !d_off) return fail(DFB_ERR_OOM, "cudaMalloc failed");
+    DFB_CUDA(cudaMemcpy(d_in, h_spec, sizeof(float2) * n_frames * F, cudaMemcpyHostToDevice));
+    DFB_CUDA(cudaMemcpy(d_off, off.data(), sizeof(int) * (E + 1), cudaMemcpyHostToDevice));
+    k_erb<<<(unsigned)((n_frames + 7) / 8), 256>>>(d_in, n_frames, (int)F, d_off, E, db, d_out);
+    DFB_LAUNCH_CHECK();
+    DFB_CUDA(cudaMemcpy(h_out, d_out, sizeof(float) * n_frames * E, cudaMemcpyDeviceToHost));
+    return DFB_OK;
+}
+
+extern "C" int dfb_erb_inv_host(int device, const float *h_gains, int64_t n_frames, const int64_t *widths, int E,
+                                float *h_out) {
+    if (!h_gains || !widths || !h_out || n_frames <= 0 || E <= 0 || E > 255) return fail(DFB_ERR_INVALID, "bad argument");
+    int64_t F = 0;
+    for (int b = 0; b < E; b++) F += widths[b];
+    std::vector<unsigned char> bob(F);
+    int64_t o = 0;
+    for (int b = 0; b < E; b++) { for (int64_t j = 0; j < widths[b]; j++) bob[o + j] = (unsigned char)b; o += widths[b]; }
+    int rc = use_device(device);
+    if (rc) return rc;
+    Scratch s;
+    float *d_in = s.alloc<float>(n_frames * E), *d_out = s.alloc<float>(n_frames * F);
+    unsigned char *d_bob = s.alloc<unsigned char>(F);
+    if (!d_in || !d_out || !d_bob) return fail(DFB_ERR_OOM, "cudaMalloc failed");
+    DFB_CUDA(cudaMemcpy(d_in, h_gains, sizeof(float) * n_frames * E, cudaMemcpyHostToDevice));
+    DFB_CUDA(cudaMemcpy(d_bob, bob.data(), F, cudaMemcpyHostToDevice));
+    int64_t n = n_frames * F;
+    k_erb_inv<<<(unsigned)((n + 255) / 256), 256>>>(d_in, n_frames, (int)F, E, d_bob, d_out);
+    DFB_LAUNCH_CHECK();
+    DFB_CUDA(cudaMemcpy(h_out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return DFB_OK;
+}
+
+extern "C" int dfb_erb_norm_host(int device, const float *h_erb, int64_t C, int64_t T, int64_t E, float alpha,
+                                 const float *h_state, float *h_out) {
+    if (!h_erb || !h_out || C <= 0 || T <= 0 || E <= 0) return fail(DFB_ERR_INVALID, "bad argument");
+    int rc = use_device(device);
+    if (rc) return rc;
+    Scratch s;
+    float *d_in = s.alloc<float>(C * T * E), *d_out = s.alloc<float>(C * T * E), *d_st = nullptr;
+    if (!d_in || !d_out) return fail(DFB_ERR_OOM, "cudaMalloc failed");
+    DFB_CUDA(cudaMemcpy(d_in, h_erb, sizeof(float) * C * T * E, cudaMemcpyHostToDevice));
+    if (h_state) {
+        d_st = s.alloc<float>(C * E);
+        DFB_CUDA(cudaMemcpy(d_st, h_state, sizeof(float) * C * E, cudaMemcpyHostToDevice));
+    }
+    rc = launch_feat_norm(d_in, (int)E, E, nullptr, 0, 0, C, T, alpha, d_st, nullptr, d_out, nullptr, 0);
+    if (rc) return rc;
+    DFB_CUDA(cudaMemcpy(h_out, d_out, sizeof(float) * C * T * E, cudaMemcpyDeviceToHost));
+    return DFB_OK;
+}
+
+extern "C" int dfb_unit_norm_host(int device, const float *h_spec, int64_t C, int64_t T, int64_t F, float alpha,
+                                  const float *h_state, float *h_out) {
+    if (!h_spec || !h_out || C <= 0 || T <= 0 || F <= 0) return fail(DFB_ERR_INVALID, "bad argument");
+    int rc = use_device(device);
+    if (rc) return rc;
+    Scratch s;
+    float *d_in = s.alloc<float>(2 * C * T * F), *d_out = s.alloc<float>(2 * C * T * F), *d_st = nullptr;
+    if (!d_in || !d_out) return fail(DFB_ERR_OOM, "cudaMalloc failed");
+    DFB_CUDA(cudaMemcpy(d_in, h_spec, sizeof(float) * 2 * C * T * F, cudaMemcpyHostToDevice));
+    if (h_state) {
+        d_st = s.alloc<float>(C * F);
+        DFB_CUDA(cudaMemcpy(d_st, h_state, sizeof(float) * C * F, cudaMemcpyHostToDevice));
+    }
+    rc = launch_feat_norm(nullptr, 0, 0, d_in, (int)F, F, C, T, alpha, nullptr, d_st, nullptr, d_out, 0);
+    if (rc) return rc;
+    DFB_CUDA(cudaMemcpy(h_out, d_out, sizeof(float) * 2 * C * T * F, cudaMemcpyDeviceToHost));
+    return DFB_OK;
+}
+
+extern "C" int dfb_unit_norm_init(int64_t n, float *h_out) {
+    if (!h_out || n <= 0) return fail(DFB_ERR_INVALID, "bad argument");
+    if (n == 1) { h_out[0] = 0.001f; return DFB_OK; }
+    float step = (0.0001f - 0.001f) / (float)(n - 1);
+    for (int64_t i = 0; i < n; i++) h_out[i] = 0.001f + (float)i * step;
+    return DFB_OK;
+}
+
+extern "C" int dfb_features(dfb_state *st, const float *d_audio, int64_t C, int64_t T, int nb_df, float alpha,
+                            float *d_spec, float *d_feat_erb, float *d_feat_spec, void *stream) {
+    if (!st || !d_audio || !d_spec || !d_feat_erb || !d_feat_spec) return fail(DFB_ERR_INVALID, "null argument");
+    if (nb_df <= 0 || nb_df > st->tb.F) return fail(DFB_ERR_INVALID, "nb_df out of range");
+    DFB_CUDA(cudaSetDevice(st->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t Tf = T / st->hop;
+    // raw ERB dB goes to feat_erb and is normalised in place by the scan kernel
+    int rc = launch_analysis(st, d_audio, C, T, d_spec, d_feat_erb, s);
+    if (rc) return rc;
+    return launch_feat_norm(d_feat_erb, st->tb.E, st->tb.E, d_spec, nb_df, st->tb.F, C, Tf, alpha, nullptr, nullptr,
+                            d_feat_erb, d_feat_spec, s);
+}
+
+extern "C" int dfb_features_host(dfb_state *st, const float *h_audio, int64_t C, int64_t T, int nb_df, float alpha,
+                                 float *h_spec, float *h_feat_erb, float *h_feat_spec) {
+    if (!st || !h_audio || !h_spec || !h_feat_erb || !h_feat_spec) return fail(DFB_ERR_INVALID, "null argument");
+    if (C <= 0 || T <= 0) return fail(DFB_ERR_INVALID, "[df] Input array empty or not contiguous.");
+    DFB_CUDA(cudaSetDevice(st->device));
+    int64_t Tf = T / st->hop, F = st->tb.F, E = st->tb.E;
+    size_t n_spec = 2 * C * Tf * F, n_fe = C * Tf * E, n_fs = 2 * C * Tf * nb_df;
+    int rc = st->arena.reserve(sizeof(float) * (C * T + n_spec + n_fe + n_fs) + 4096);
+    if (rc) return rc;
+    st->arena.reset();
+    float *d_in = st->arena.take<float>(C * T), *d_spec = st->arena.take<float>(n_spec + 2),
+          *d_fe = st->arena.take<float>(n_fe + 1), *d_fs = st->arena.take<float>(n_fs + 2);
+    DFB_CUDA(cudaMemcpyAsync(d_in, h_audio, sizeof(float) * C * T, cudaMemcpyHostToDevice, st->stream));
+    rc = dfb_features(st, d_in, C, T, nb_df, alpha, d_spec, d_fe, d_fs, st->stream);
+    if (rc) return rc;
+    if (Tf > 0) {
+        DFB_CUDA(cudaMemcpyAsync(h_spec, d_spec, sizeof(float) * n_spec, cudaMemcpyDeviceToHost, st->stream));
+        DFB_CUDA(cudaMemcpyAsync(h_feat_erb, d_fe, sizeof(float) * n_fe, cudaMemcpyDeviceToHost, st->stream));
+        DFB_CUDA(cudaMemcpyAsync(h_feat_spec, d_fs, sizeof(float) * n_fs, cudaMemcpyDeviceToHost, st->stream));
+    }
+    DFB_CUDA(cudaStreamSynchronize(st->stream));
+    return DFB_OK;
+}

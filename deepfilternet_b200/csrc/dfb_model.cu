@@ -1,0 +1,1057 @@
+// dfb_model.cu -- the DNN of the enhancement path (encoder convs, grouped linears, GRUs, ERB and
+// DF decoders) as hand-written sm_100a kernels plus the executor behind dfb_model_* / dfb_enhance.
+//
+// Reference semantics (paths relative to /root/reference/DeepFilterNet/df):
+//   Conv2dNormAct / ConvTranspose2dNormAct   modules.py:18-72, 75-126
+//   GroupedLinearEinsum                       modules.py:741-780
+//   SqueezedGRU_S / SqueezedGRU               modules.py:702-738 / 663-699  (torch.nn.GRU inside)
+//   Encoder / ErbDecoder / DfDecoder          deepfilternet3.py:100-331, deepfilternet2.py:98-371
+//   DfNet.forward                             deepfilternet3.py:389-456,   deepfilternet2.py:481-505
+//
+// HBM layout: every activation is channel-last [B, T, F, C=64] (C fastest) so a 1x1 conv is a
+// row-major [rows, 64] x [64, 64] product and depthwise taps are +-64-float neighbours;
+// embeddings are [B*T, D] row-major.  BatchNorm is folded on the host (weights.py).
+// Arithmetic: IEEE fp32 (FFMA) everywhere; accumulation order differs from ATen's, which is
+// inside the 1e-4 RMS parity bound (tests/test_gpu_parity.py).
+#include <cooperative_groups.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "dfb_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace dfb {
+
+constexpr int kCh = 64;  // conv_ch of every shipped model
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3 };
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(x, 0.f);
+        case ACT_TANH: return tanhf(x);
+        case ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+        default: return x;
+    }
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ------------------------------------------------------------------- erb_conv0 ----
+// Dense 1 -> 64 conv, kernel (kt,3), causal in time, BN folded, ReLU.  modules.py:18-72 with
+// in_ch = 1 (groups = 1, not separable); feature look-ahead: deepfilternet3.py:359,409-410.
+// in  fe [B,T,E]; out e0 [B,T,E,64].  One CTA = kE0Frames frames; thread = (f, channel quad).
+constexpr int kE0Frames = 8;
+__global__ void __launch_bounds__(256)
+k_erb_conv0(const float *__restrict__ fe, const float *__restrict__ w /*[kt][3][64]*/,
+            const float *__restrict__ bias, float *__restrict__ out, int T, int E, int kt, int lookahead) {
+    extern __shared__ float s_in[];  // [(kE0Frames + kt - 1)][E + 2]
+    const int b = blockIdx.y, t0 = blockIdx.x * kE0Frames;
+    const int rows = kE0Frames + kt - 1, ld = E + 2;
+    for (int i = threadIdx.x; i < rows * ld; i += blockDim.x) {
+        int r = i / ld, f = i - r * ld - 1;
+        int tp = t0 - (kt - 1) + r;  // time index in the look-ahead shifted feature sequence
+        float v = 0.f;
+        if (f >= 0 && f < E && tp >= 0 && tp + lookahead < T) v = fe[((int64_t)b * T + tp + lookahead) * E + f];
+        s_in[i] = v;
+    }
+    const int cq = threadIdx.x & 15, fl = threadIdx.x >> 4;  // 16 channel quads x 16 f per pass
+    float4 wr[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) wr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < kt * 3; i++) wr[i + (3 - kt) * 3] = *reinterpret_cast<const float4 *>(w + i * kCh + cq * 4);
+    const float4 bv = *reinterpret_cast<const float4 *>(bias + cq * 4);
+    __syncthreads();
+    for (int fr = 0; fr < kE0Frames; fr++) {
+        int t = t0 + fr;
+        if (t >= T) break;
+        for (int f = fl; f < E; f += 16) {
+            float4 acc = bv;
+#pragma unroll
+            for (int dt = 0; dt < 3; dt++) {
+                if (dt < 3 - kt) continue;
+                const float *row = s_in + (fr + dt - (3 - kt)) * ld + f;  // f-1 .. f+1 -> +0..+2
+#pragma unroll
+                for (int df = 0; df < 3; df++) {
+                    float x = row[df];
+                    float4 ww = wr[dt * 3 + df];
+                    acc.x += x * ww.x; acc.y += x * ww.y; acc.z += x * ww.z; acc.w += x * ww.w;
+                }
+            }
+            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+            *reinterpret_cast<float4 *>(out + (((int64_t)b * T + t) * E + f) * kCh + cq * 4) = acc;
+        }
+    }
+}
+
+// ------------------------------------------------- depthwise (+pathway) -> 1x1 -> ReLU ----
+// One fused kernel for every "separable" block of the reference (modules.py:49-71, 104-125):
+//   prologue  A[r][c] = sum_{dt,df} dw[dt][df][c] * X[t-(kt-1)+dt][fi(fo,df)][c]
+//             with X = in (+ relu(path * ps + pb) when a pathway tensor is given; that is
+//             `convNp(eN) + prev`, deepfilternet3.py:250-253)
+//   GEMM      out[r][n] = relu(sum_c A[r][c] * pw[c][n] + b[n])
+// Modes: S1 stride 1, S2 stride 2 (fi = 2 fo + df - 1), T2 transposed stride 2
+// (out[2j] = w1 x[j]; out[2j+1] = w2 x[j] + w0 x[j+1]; ConvTranspose2d padding 1, output_padding 1),
+// DF0 the grouped 2 -> 64 input conv on the complex features (with look-ahead shift).
+// Tile: NF frames x Fout rows (R = NF * Fout <= 128, multiple of 4); thread tile 4 rows x 8 cols.
+enum DwMode { DW_S1 = 0, DW_S2 = 1, DW_T2 = 2, DW_DF0 = 3 };
+constexpr int kLdA = kCh + 4;  // padded row stride of the A tile (floats)
+
+struct DwPwParams {
+    const float *in;      // [B,T,Fin,64]  (DF0: feat_spec [B,T,Fin,2])
+    const float *path;    // optional [B,T,Fin,64]
+    const float *ps, *pb; // pathway scale / bias [64]
+    const float *dw;      // [kt][3][64]
+    const float *pw;      // [64][64]
+    const float *bias;    // [64]
+    float *out;           // [B,T,Fout,64]
+    int64_t in_fs, path_fs, out_fs;  // frame strides (floats)
+    int T, Fin, Fout, kt, NF, lookahead;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dwpw(DwPwParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float *Ws = smem;                 // [64][64]
+    float *As = smem + kCh * kCh;     // [R][kLdA]
+    const int b = blockIdx.y, t0 = blockIdx.x * p.NF;
+    const int tid = threadIdx.x;
+    const int nf = min(p.NF, p.T - t0);
+    const int R = nf * p.Fout;        // rows actually present
+    const int Rfull = p.NF * p.Fout;
+    for (int i = tid; i < kCh * kCh / 4; i += 256)
+        reinterpret_cast<float4 *>(Ws)[i] = reinterpret_cast<const float4 *>(p.pw)[i];
+    // ---- prologue: thread = (row slot, channel quad)
+    {
+        const int cq = tid & 15;
+        float4 wd[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) wd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < p.kt * 3; i++)
+            wd[i + (3 - p.kt) * 3] = *reinterpret_cast<const float4 *>(p.dw + i * kCh + cq * 4);
+        float4 ps4 = make_float4(0.f, 0.f, 0.f, 0.f), pb4 = ps4;
+        if (p.path) {
+            ps4 = *reinterpret_cast<const float4 *>(p.ps + cq * 4);
+            pb4 = *reinterpret_cast<const float4 *>(p.pb + cq * 4);
+        }
+        for (int r = tid >> 4; r < Rfull; r += 16) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < R) {
+                const int fr = r / p.Fout, fo = r - fr * p.Fout;
+                const int t = t0 + fr;
+#pragma unroll
+                for (int dt = 0; dt < 3; dt++) {
+                    if (dt < 3 - p.kt) continue;
+                    const int tp = t - (2 - dt);  // causal: taps at t-(kt-1) .. t
+                    if (tp < 0) continue;
+#pragma unroll
+                    for (int df = 0; df < 3; df++) {
+                        int fi;
+                        float4 wv;
+                        if (MODE == DW_S1 || MODE == DW_DF0) { fi = fo + df - 1; wv = wd[dt * 3 + df]; }
+                        else if (MODE == DW_S2) { fi = 2 * fo + df - 1; wv = wd[dt * 3 + df]; }
+                        else {  // DW_T2: df enumerates the (at most two) contributing taps
+                            if (df == 2) continue;
+                            if ((fo & 1) == 0) { if (df == 1) continue; fi = fo >> 1; wv = wd[dt * 3 + 1]; }
+                            else if (df == 0) { fi = fo >> 1; wv = wd[dt * 3 + 2]; }
+                            else { fi = (fo >> 1) + 1; wv = wd[dt * 3 + 0]; }
+                        }
+                        if (fi < 0 || fi >= p.Fin) continue;
+                        float4 x;
+                        if (MODE == DW_DF0) {
+                            // channels [0,32) read re, [32,64) read im (groups = 2); look-ahead shifted
+                            if (tp + p.lookahead >= p.T) continue;
+                            const float *src = p.in + ((int64_t)b * p.T + tp + p.lookahead) * p.in_fs + fi * 2;
+                            float v = (cq < 8) ? src[0] : src[1];
+                            x = make_float4(v, v, v, v);
+                        } else {
+                            const int64_t o = ((int64_t)b * p.T + tp);
+                            x = *reinterpret_cast<const float4 *>(p.in + o * p.in_fs + fi * kCh + cq * 4);
+                            if (p.path) {
+                                float4 e = *reinterpret_cast<const float4 *>(p.path + o * p.path_fs + fi * kCh + cq * 4);
+                                x.x += fmaxf(e.x * ps4.x + pb4.x, 0.f);
+                                x.y += fmaxf(e.y * ps4.y + pb4.y, 0.f);
+                                x.z += fmaxf(e.z * ps4.z + pb4.z, 0.f);
+                                x.w += fmaxf(e.w * ps4.w + pb4.w, 0.f);
+                            }
+                        }
+                        acc.x += x.x * wv.x; acc.y += x.y * wv.y; acc.z += x.z * wv.z; acc.w += x.w * wv.w;
+                    }
+                }
+            }
+            *reinterpret_cast<float4 *>(As + r * kLdA + cq * 4) = acc;
+        }
+    }
+    __syncthreads();
+    // ---- GEMM: thread (rg, cg): rows rg + RG * i (i < 4), cols 8 cg .. 8 cg + 7
+    const int RG = Rfull >> 2;
+    const int cgid = tid & 7, rg = tid >> 3;
+    if (rg >= RG) return;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < kCh; k += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(As + (rg + RG * i) * kLdA + k);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            float4 w0 = *reinterpret_cast<const float4 *>(Ws + (k + kk) * kCh + cgid * 8);
+            float4 w1 = *reinterpret_cast<const float4 *>(Ws + (k + kk) * kCh + cgid * 8 + 4);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                acc[i][0] += av * w0.x; acc[i][1] += av * w0.y; acc[i][2] += av * w0.z; acc[i][3] += av * w0.w;
+                acc[i][4] += av * w1.x; acc[i][5] += av * w1.y; acc[i][6] += av * w1.z; acc[i][7] += av * w1.w;
+            }
+        }
+    }
+    const float4 b0 = *reinterpret_cast<const float4 *>(p.bias + cgid * 8);
+    const float4 b1 = *reinterpret_cast<const float4 *>(p.bias + cgid * 8 + 4);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int r = rg + RG * i;
+        if (r >= R) continue;
+        int fr = r / p.Fout, fo = r - fr * p.Fout;
+        float *dst = p.out + ((int64_t)b * p.T + t0 + fr) * p.out_fs + fo * kCh + cgid * 8;
+        float4 o0 = make_float4(fmaxf(acc[i][0] + b0.x, 0.f), fmaxf(acc[i][1] + b0.y, 0.f),
+                                fmaxf(acc[i][2] + b0.z, 0.f), fmaxf(acc[i][3] + b0.w, 0.f));
+        float4 o1 = make_float4(fmaxf(acc[i][4] + b1.x, 0.f), fmaxf(acc[i][5] + b1.y, 0.f),
+                                fmaxf(acc[i][6] + b1.z, 0.f), fmaxf(acc[i][7] + b1.w, 0.f));
+        *reinterpret_cast<float4 *>(dst) = o0;
+        *reinterpret_cast<float4 *>(dst + 4) = o1;
+    }
+}
+
+// ------------------------------------------------------------------ grouped linear ----
+// Y[m, g*Hg + n] = act( sum_i X[m, g*Ig + i] * W[g][i][n] + bias ) * oscale + ooffset + R[m, ...]
+// (GroupedLinearEinsum, modules.py:766-776; G = 1 with bias = GRU input projection W_ih x + b_ih
+// with W given as [I][H] i.e. already transposed on upload.)
+// CTA tile 64 rows x 64 cols (one group, or a 64-wide slice of a wide group); K chunks of 32.
+struct GlParams {
+    const float *x; int64_t ldx;
+    const float *w;          // [G][Ig][Hg]
+    const float *bias;       // [G*Hg] or null
+    const float *res; int64_t ldr;  // optional residual, added after the activation
+    float *y; int64_t ldy;
+    int64_t M;
+    int G, Ig, Hg, act;
+    float oscale, ooffset;
+};
+constexpr int kGlBM = 64, kGlBN = 64, kGlBK = 32;
+
+__global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
+    __shared__ __align__(16) float As[kGlBM][kGlBK + 4];
+    __shared__ __align__(16) float Ws[kGlBK][kGlBN];
+    const int tiles_per_group = (p.Hg + kGlBN - 1) / kGlBN;
+    const int g = blockIdx.y / tiles_per_group, nt = blockIdx.y - g * tiles_per_group;
+    const int n0 = nt * kGlBN;
+    const int ncols = min(kGlBN, p.Hg - n0);
+    const int64_t m0 = (int64_t)blockIdx.x * kGlBM;
+    const int tid = threadIdx.x;
+    const int tc = tid & 15, tr = tid >> 4;  // thread tile: rows tr + 16 i, cols 4 tc .. 4 tc + 3
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    const float *xg = p.x + (int64_t)g * p.Ig;
+    const float *wg = p.w + (int64_t)g * p.Ig * p.Hg;
+    for (int k0 = 0; k0 < p.Ig; k0 += kGlBK) {
+        const int kc = min(kGlBK, p.Ig - k0);
+        // A tile: 64 rows x 32 k  (8 threads x float4 per row)
+        for (int i = tid; i < kGlBM * (kGlBK / 4); i += 256) {
+            int r = i >> 3, kq = (i & 7) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            int64_t m = m0 + r;
+            if (m < p.M && kq < kc) v = *reinterpret_cast<const float4 *>(xg + m * p.ldx + k0 + kq);
+            *reinterpret_cast<float4 *>(&As[r][kq]) = v;
+        }
+        // W tile: 32 k x 64 n
+        for (int i = tid; i < kGlBK * kGlBN; i += 256) {
+            int k = i >> 6, n = i & 63;
+            Ws[k][n] = (k < kc && n < ncols) ? wg[(int64_t)(k0 + k) * p.Hg + n0 + n] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kGlBK; k += 4) {
+            float4 a[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(&As[tr + 16 * i][k]);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                float4 w = *reinterpret_cast<const float4 *>(&Ws[k + kk][tc * 4]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                    acc[i][0] += av * w.x; acc[i][1] += av * w.y; acc[i][2] += av * w.z; acc[i][3] += av * w.w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int64_t m = m0 + tr + 16 * i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int n = tc * 4 + j;
+            if (n >= ncols) continue;
+            int col = g * p.Hg + n0 + n;
+            float v = acc[i][j];
+            if (p.bias) v += p.bias[col];
+            v = act_apply(v, p.act) * p.oscale + p.ooffset;
+            if (p.res) v += p.res[m * p.ldr + col];
+            p.y[m * p.ldy + col] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------- GRU recurrence ----
+// torch.nn.GRU cell (gate order r, z, n; modules.py:684,723):
+//   r = s(xr + Whr h + bhr), z = s(xz + Whz h + bhz), n = tanh(xn + r (Whn h + bhn)), h' = (1-z) n + z h
+// xproj = W_ih x + b_ih comes from k_grouped_linear.  One thread-block CLUSTER owns a group of Bc
+// streams for the whole sequence: CTA `rank` keeps the W_hh rows of its U = H / C hidden units
+// (3U rows x H) in REGISTERS (384 threads x 128 weights), the hidden state of the group lives in
+// shared memory of every CTA and the new slice is broadcast through DSMEM each step; one cluster
+// barrier per time step.  H = 256: C = 4, U = 64, 2 lanes per row;  H = 512: C = 16, U = 32, 4 lanes.
+constexpr int kGruThreads = 384, kGruWPerThread = 128, kGruSB = 4, kGruMaxBc = 16;
+
+struct GruParams {
+    const float *xproj;  // [B,T,3H]
+    const float *whh;    // [3H][H]
+    const float *bhh;    // [3H]
+    const float *res;    // optional [B,T,H] added to the OUTPUT only (identity skip, modules.py:696)
+    float *hout;         // [B,T,H]
+    int B, T, Bc;
+};
+
+template <int H, int C>
+__global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
+    constexpr int U = H / C;                       // hidden units per CTA
+    constexpr int KS = kGruThreads / (3 * U);      // lanes per weight row
+    constexpr int KR = H / KS;                     // k-range per lane (= 128)
+    static_assert(KR == kGruWPerThread, "layout");
+    constexpr int HP = H + 4 * KS;                 // padded h row (bank spread between k-parts)
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int group = blockIdx.x / C;
+    const int b0 = group * p.Bc;
+    const int nb = min(p.Bc, p.B - b0);
+    extern __shared__ __align__(16) float gru_smem[];
+    float (*s_h)[kGruMaxBc][HP] = reinterpret_cast<float (*)[kGruMaxBc][HP]>(gru_smem);            // [2][Bc][HP]
+    float (*s_pre)[kGruMaxBc + 1] = reinterpret_cast<float (*)[kGruMaxBc + 1]>(gru_smem + 2 * kGruMaxBc * HP);  // [3U]
+    const int tid = threadIdx.x;
+    const int row = tid / KS, kp = tid % KS;       // row in [0, 3U): gate = row / U, unit = row % U
+    const int gate = row / U, unit = row % U;
+    // weights -> registers
+    float w[kGruWPerThread];
+    {
+        const float *src = p.whh + ((int64_t)gate * H + rank * U + unit) * H + kp * KR;
+#pragma unroll
+        for (int i = 0; i < kGruWPerThread; i += 4) {
+            float4 v = *reinterpret_cast<const float4 *>(src + i);
+            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+        }
+    }
+    for (int i = tid; i < 2 * kGruMaxBc * HP; i += kGruThreads) gru_smem[i] = 0.f;  // h0 = 0
+    cluster.sync();
+    int cur = 0;
+    for (int t = 0; t < p.T; t++) {
+        // prefetch the input projections of this step for the gate phase (independent of h)
+        float xr[(kGruMaxBc * 64 + kGruThreads - 1) / kGruThreads][3];
+        {
+            int it = 0;
+            for (int item = tid; item < nb * U; item += kGruThreads, it++) {
+                int s = item / U, u = item - s * U;
+                const float *xp = p.xproj + ((int64_t)(b0 + s) * p.T + t) * (3 * H) + rank * U + u;
+                xr[it][0] = xp[0]; xr[it][1] = xp[H]; xr[it][2] = xp[2 * H];
+            }
+        }
+        // matvec: pre[row][s] = sum_k W[row][k] h[s][k]
+        for (int sc = 0; sc < nb; sc += kGruSB) {
+            float acc[kGruSB];
+#pragma unroll
+            for (int s = 0; s < kGruSB; s++) acc[s] = 0.f;
+            const float *hb = &s_h[cur][sc][kp * (KR + 4)];
+#pragma unroll
+            for (int k = 0; k < KR; k += 4) {
+#pragma unroll
+                for (int s = 0; s < kGruSB; s++) {
+                    float4 hv = *reinterpret_cast<const float4 *>(hb + s * HP + k);
+                    acc[s] += w[k] * hv.x; acc[s] += w[k + 1] * hv.y; acc[s] += w[k + 2] * hv.z; acc[s] += w[k + 3] * hv.w;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < kGruSB; s++) {
+#pragma unroll
+                for (int o = 1; o < KS; o <<= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+                if (kp == 0 && sc + s < nb) s_pre[row][sc + s] = acc[s];
+            }
+        }
+        __syncthreads();
+        // gates
+        {
+            int it = 0;
+            for (int item = tid; item < nb * U; item += kGruThreads, it++) {
+                int s = item / U, u = item - s * U;
+                int gu = rank * U + u;
+                float br = p.bhh[gu], bz = p.bhh[H + gu], bn = p.bhh[2 * H + gu];
+                float r = sigmoidf_(xr[it][0] + s_pre[u][s] + br);
+                float z = sigmoidf_(xr[it][1] + s_pre[U + u][s] + bz);
+                float n = tanhf(xr[it][2] + r * (s_pre[2 * U + u][s] + bn));
+                float hprev = s_h[cur][s][(gu / KR) * (KR + 4) + (gu % KR)];
+                float hn = (1.f - z) * n + z * hprev;
+                int64_t o = ((int64_t)(b0 + s) * p.T + t) * H + gu;
+                p.hout[o] = p.res ? hn + p.res[o] : hn;
+                // broadcast the new value to every CTA of the cluster (DSMEM)
+                float *dst_local = &s_h[cur ^ 1][s][(gu / KR) * (KR + 4) + (gu % KR)];
+#pragma unroll
+                for (int c = 0; c < C; c++) *cluster.map_shared_rank(dst_local, c) = hn;
+            }
+        }
+        cluster.sync();
+        cur ^= 1;
+    }
+}
+
+// --------------------------------------------------------------- ERB mask output conv ----
+// m[b,t,f] = sigmoid( sum_{dt,df,c} w[dt][df][c] * X[t-(kt-1)+dt][f+df-1][c] + bias ),
+// X = relu(e0 * ps + pb) + d1   (conv0_out(conv0p(e0) + e1), deepfilternet3.py:253).
+// One warp walks kMaskChunk consecutive frames of one stream; X rows of the current and the
+// previous frame are staged in shared memory ([E+2][65] floats, zero rows at f = -1, E).
+constexpr int kMaskWarps = 4, kMaskChunk = 8, kMaskLd = kCh + 1;
+__global__ void __launch_bounds__(32 * kMaskWarps)
+k_mask_out(const float *__restrict__ e0, const float *__restrict__ d1, const float *__restrict__ ps,
+           const float *__restrict__ pb, const float *__restrict__ w /*[kt][3][64]*/,
+           const float *__restrict__ bias_p, float *__restrict__ m, int T, int E, int kt) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int t0 = (blockIdx.x * kMaskWarps + warp) * kMaskChunk;
+    float *buf = smem + warp * 2 * (E + 2) * kMaskLd;  // two frames
+    float *ws = smem + kMaskWarps * 2 * (E + 2) * kMaskLd;  // [kt*3*64] shared by all warps
+    for (int i = threadIdx.x; i < kt * 3 * kCh; i += blockDim.x) ws[i] = w[i];
+    for (int i = lane; i < 2 * (E + 2) * kMaskLd; i += 32) buf[i] = 0.f;
+    __syncthreads();
+    if (t0 >= T) return;
+    const int t1 = min(t0 + kMaskChunk, T);
+    const float2 ps2 = *reinterpret_cast<const float2 *>(ps + lane * 2);
+    const float2 pb2 = *reinterpret_cast<const float2 *>(pb + lane * 2);
+    const float bias = bias_p[0];
+    for (int t = (kt > 1 && t0 > 0) ? t0 - 1 : t0; t < t1; t++) {
+        float *cur = buf + (t & 1) * (E + 2) * kMaskLd;
+        const float *prv = buf + ((t & 1) ^ 1) * (E + 2) * kMaskLd;
+        const int64_t base = ((int64_t)b * T + t) * E * kCh;
+        for (int f = 0; f < E; f++) {
+            float2 e = *reinterpret_cast<const float2 *>(e0 + base + f * kCh + lane * 2);
+            float2 d = *reinterpret_cast<const float2 *>(d1 + base + f * kCh + lane * 2);
+            cur[(f + 1) * kMaskLd + lane * 2] = fmaxf(e.x * ps2.x + pb2.x, 0.f) + d.x;
+            cur[(f + 1) * kMaskLd + lane * 2 + 1] = fmaxf(e.y * ps2.y + pb2.y, 0.f) + d.y;
+        }
+        __syncwarp();
+        if (t >= t0) {
+            for (int f = lane; f < E; f += 32) {
+                float acc = bias;
+                for (int dt = 0; dt < kt; dt++) {
+                    // dt = kt-1 is the current frame; dt = kt-2 the previous one (kt <= 2)
+                    const float *src = (dt == kt - 1) ? cur : prv;
+                    if (dt != kt - 1 && t == 0) continue;
+                    for (int df = 0; df < 3; df++) {
+                        const float *xr = src + (f + df) * kMaskLd;
+                        const float *wr = ws + (dt * 3 + df) * kCh;
+#pragma unroll 16
+                        for (int c = 0; c < kCh; c++) acc += xr[c] * wr[c];
+                    }
+                }
+                m[((int64_t)b * T + t) * E + f] = sigmoidf_(acc);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------- DF pathway conv + coefficient sum ----
+// coefs[b,t,f,:] (already holding tanh(df_out(c))) += relu( pw( conv_t(c0) ) + b ):
+// df_convp = grouped (2) temporal conv C -> 2*O with kernel (ktp,1), 1x1 conv, BN, ReLU
+// (deepfilternet3.py:293-295, 328-330).  One thread per (b,t,f) row.
+constexpr int kMaxO2 = 16;
+template <int ORDER>
+__global__ void __launch_bounds__(128)
+k_df_convp(const float *__restrict__ c0 /*[B,T,Fd,64]*/, const float *__restrict__ w1 /*[ktp][O2][32]*/,
+           const float *__restrict__ w2 /*[O2][O2]*/, const float *__restrict__ bias, float *__restrict__ coefs,
+           int64_t rows, int T, int Fd, int ktp) {
+    constexpr int O2 = 2 * ORDER;
+    extern __shared__ __align__(16) float sw[];  // w1 | w2 | bias
+    const int n1 = ktp * O2 * (kCh / 2);
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) sw[i] = w1[i];
+    for (int i = threadIdx.x; i < O2 * O2; i += blockDim.x) sw[n1 + i] = w2[i];
+    for (int i = threadIdx.x; i < O2; i += blockDim.x) sw[n1 + O2 * O2 + i] = bias[i];
+    __syncthreads();
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int f = (int)(row % Fd);
+    const int64_t bt = row / Fd;
+    const int t = (int)(bt % T);
+    float acc[O2];
+#pragma unroll
+    for (int o = 0; o < O2; o++) acc[o] = 0.f;
+    for (int dt = 0; dt < ktp; dt++) {
+        int tp = t - (ktp - 1) + dt;
+        if (tp < 0) continue;
+        const float *src = c0 + ((bt - t + tp) * Fd + f) * kCh;
+        const float *wdt = sw + dt * O2 * (kCh / 2);
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+#pragma unroll
+            for (int c4 = 0; c4 < kCh / 2; c4 += 4) {
+                float4 x = *reinterpret_cast<const float4 *>(src + g * (kCh / 2) + c4);
+#pragma unroll
+                for (int o = 0; o < ORDER; o++) {
+                    float4 ww = *reinterpret_cast<const float4 *>(wdt + (g * ORDER + o) * (kCh / 2) + c4);
+                    acc[g * ORDER + o] += x.x * ww.x + x.y * ww.y + x.z * ww.z + x.w * ww.w;
+                }
+            }
+        }
+    }
+    const float *s2 = sw + n1, *sb = sw + n1 + O2 * O2;
+    float *dst = coefs + row * O2;
+#pragma unroll
+    for (int n = 0; n < O2; n++) {
+        float v = sb[n];
+#pragma unroll
+        for (int k = 0; k < O2; k++) v += acc[k] * s2[k * O2 + n];
+        dst[n] += fmaxf(v, 0.f);
+    }
+}
+
+}  // namespace dfb
+
+// =========================================================================== executor =====
+using namespace dfb;
+
+
+struct GruLayerW { const float *w_ih_t, *w_hh, *b_ih, *b_hh; int in_dim; };
+
+struct dfb_model {
+    int device;
+    dfb_model_config cfg;
+    std::map<std::string, std::pair<float *, int64_t>> t;  // device tensors
+    std::map<std::string, std::pair<const float *, int64_t>> dbg;  // activations of the last forward
+    std::vector<GruLayerW> enc_gru, erb_gru, df_gru;
+    float *slab = nullptr;
+    Arena arena;
+    cudaStream_t stream = nullptr;
+    const float *get(const std::string &n) const {
+        auto it = t.find(n);
+        return it == t.end() ? nullptr : it->second.first;
+    }
+};
+
+static int need(const dfb_model *m, const char *name, int64_t numel, const float **out) {
+    auto it = m->t.find(name);
+    if (it == m->t.end()) return fail(DFB_ERR_INVALID, "missing weight tensor '%s'", name);
+    if (numel >= 0 && it->second.second != numel)
+        return fail(DFB_ERR_INVALID, "weight tensor '%s' has %lld elements, expected %lld", name,
+                    (long long)it->second.second, (long long)numel);
+    *out = it->second.first;
+    return DFB_OK;
+}
+
+extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_config *cfg, const dfb_tensor *tensors,
+                                int n_tensors, const int64_t *erb_widths) {
+    (void)erb_widths;
+    if (!out || !cfg || !tensors) return fail(DFB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->conv_ch != kCh) return fail(DFB_ERR_UNSUPPORTED, "conv_ch = %d (built kernels: 64)", cfg->conv_ch);
+    if (cfg->model_kind != 2 && cfg->model_kind != 3) return fail(DFB_ERR_UNSUPPORTED, "model_kind %d", cfg->model_kind);
+    if (cfg->conv_kt < 1 || cfg->conv_kt > 2 || cfg->inp_kt < 1 || cfg->inp_kt > 3)
+        return fail(DFB_ERR_UNSUPPORTED, "conv kernel time taps (%d, %d) unsupported", cfg->conv_kt, cfg->inp_kt);
+    if ((cfg->emb_hidden != 256 && cfg->emb_hidden != 512) || (cfg->df_hidden != 256 && cfg->df_hidden != 512))
+        return fail(DFB_ERR_UNSUPPORTED, "GRU hidden sizes (%d, %d): built kernels cover 256 and 512", cfg->emb_hidden,
+                    cfg->df_hidden);
+    if (cfg->nb_erb % 8 || cfg->nb_erb > 64 || cfg->nb_df % 8 || cfg->nb_df > 128 || 2 * cfg->df_order > kMaxO2)
+        return fail(DFB_ERR_UNSUPPORTED, "nb_erb / nb_df / df_order outside the built kernels");
+    int rc = use_device(device);
+    if (rc) return rc;
+    dfb_model *m = new dfb_model();
+    m->device = device;
+    m->cfg = *cfg;
+    // upload: one slab; GRU w_ih is stored transposed ([I][3H]) for the projection GEMM
+    size_t total = 0;
+    for (int i = 0; i < n_tensors; i++) total += ((size_t)tensors[i].numel * 4 + 255) & ~size_t(255);
+    if (cudaMalloc(&m->slab, total + 256) != cudaSuccess) {
+        delete m;
+        return fail(DFB_ERR_OOM, "cudaMalloc(%zu) for weights failed", total);
+    }
+    size_t off = 0;
+    std::vector<float> tmp;
+    for (int i = 0; i < n_tensors; i++) {
+        const dfb_tensor &tt = tensors[i];
+        if (!tt.name || !tt.data || tt.numel <= 0) { dfb_model_free(m); return fail(DFB_ERR_INVALID, "bad tensor %d", i); }
+        float *dst = (float *)((char *)m->slab + off);
+        if (cudaMemcpy(dst, tt.data, (size_t)tt.numel * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            dfb_model_free(m);
+            return fail(DFB_ERR_CUDA, "weight upload failed");
+        }
+        m->t[tt.name] = {dst, tt.numel};
+        off += ((size_t)tt.numel * 4 + 255) & ~size_t(255);
+    }
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        dfb_model_free(m);
+        return fail(DFB_ERR_CUDA, "stream creation failed");
+    }
+    *out = m;
+    return DFB_OK;
+}
+
+extern "C" void dfb_model_free(dfb_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    m->arena.release();
+    if (m->slab) cudaFree(m->slab);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" int64_t dfb_model_debug_fetch(dfb_model *m, const char *name, float *h_out, int64_t max_numel) {
+    if (!m || !name || !h_out) return fail(DFB_ERR_INVALID, "null argument");
+    auto it = m->dbg.find(name);
+    if (it == m->dbg.end()) return fail(DFB_ERR_INVALID, "no activation named '%s'", name);
+    int64_t n = it->second.second < max_numel ? it->second.second : max_numel;
+    cudaSetDevice(m->device);
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(h_out, it->second.first, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(DFB_ERR_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return n;
+}
+
+extern "C" int64_t dfb_model_workspace_bytes(const dfb_model *m) { return m ? (int64_t)m->arena.cap : 0; }
+
+namespace {
+
+int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const float *bias, const float *res,
+           int64_t ldr, float *y, int64_t ldy, int64_t M, int G, int I, int Hh, int act, float oscale = 1.f,
+           float ooffset = 0.f) {
+    GlParams p{x, ldx, w, bias, res, ldr, y, ldy, M, G, I / G, Hh / G, act, oscale, ooffset};
+    if ((p.Ig % 4) || (ldx % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: K not a multiple of 4");
+    int tiles = (p.Hg + kGlBN - 1) / kGlBN;
+    dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(G * tiles));
+    k_grouped_linear<<<grid, 256, 0, s>>>(p);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+}
+
+template <int H, int C>
+int launch_gru_t(cudaStream_t s, const GruParams &p, int ngroups) {
+    constexpr int KS = kGruThreads / (3 * (H / C));
+    constexpr int smem = (2 * kGruMaxBc * (H + 4 * KS) + 3 * (H / C) * (kGruMaxBc + 1)) * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (C > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru<H, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        DFB_CUDA(cudaFuncSetAttribute(k_gru<H, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(ngroups * C));
+    cfg.blockDim = dim3(kGruThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GruParams pp = p;
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru<H, C>, pp));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return DFB_OK;
+}
+
+int pick_bc(int B, int max_clusters) {
+    int bc = (B + max_clusters - 1) / max_clusters;
+    bc = ((bc + kGruSB - 1) / kGruSB) * kGruSB;
+    if (bc < kGruSB) bc = kGruSB;
+    if (bc > kGruMaxBc) bc = kGruMaxBc;
+    return bc;
+}
+
+// x [M, in_dim] -> multi-layer GRU -> y [M, H]  (uses xproj scratch [M,3H] and h ping-pong buffers)
+int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, const float *x, int in_dim,
+            const float *res_last, float *y, float *xproj, float *tmp_h, int B, int T) {
+    const int64_t M = (int64_t)B * T;
+    const float *cur_in = x;
+    int cur_dim = in_dim;
+    for (int l = 0; l < layers; l++) {
+        std::string base = std::string(name) + ".l" + std::to_string(l);
+        const float *w_ih_t, *w_hh, *b_ih, *b_hh;
+        int rc;
+        if ((rc = need(m, (base + ".w_ih_t").c_str(), (int64_t)3 * H * cur_dim, &w_ih_t))) return rc;
+        if ((rc = need(m, (base + ".w_hh").c_str(), (int64_t)3 * H * H, &w_hh))) return rc;
+        if ((rc = need(m, (base + ".b_ih").c_str(), 3 * H, &b_ih))) return rc;
+        if ((rc = need(m, (base + ".b_hh").c_str(), 3 * H, &b_hh))) return rc;
+        rc = run_gl(s, cur_in, cur_dim, w_ih_t, b_ih, nullptr, 0, xproj, 3 * H, M, 1, cur_dim, 3 * H, ACT_NONE);
+        if (rc) return rc;
+        float *dst = (l == layers - 1) ? y : tmp_h;
+        GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, 0};
+        if (H == 256) {
+            p.Bc = pick_bc(B, 148 / 4);
+            rc = launch_gru_t<256, 4>(s, p, (B + p.Bc - 1) / p.Bc);
+        } else {
+            p.Bc = pick_bc(B, 8);
+            rc = launch_gru_t<512, 16>(s, p, (B + p.Bc - 1) / p.Bc);
+        }
+        if (rc) return rc;
+        cur_in = dst;
+        cur_dim = H;
+        // middle layers may write tmp_h in place: the recurrence only reads xproj, which the
+        // projection GEMM above has already produced from the previous contents of tmp_h.
+    }
+    return DFB_OK;
+}
+
+template <int MODE>
+int run_dwpw(cudaStream_t s, DwPwParams p, int B) {
+    static bool attr_done = false;
+    const int smem = (kCh * kCh + 128 * kLdA) * 4;
+    if (!attr_done) {
+        DFB_CUDA(cudaFuncSetAttribute(k_dwpw<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    p.NF = 128 / p.Fout;
+    if (p.NF < 1) p.NF = 1;
+    if (p.NF * p.Fout > 128 || (p.NF * p.Fout) % 4) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile: Fout = %d", p.Fout);
+    dim3 grid((unsigned)((p.T + p.NF - 1) / p.NF), (unsigned)B);
+    k_dwpw<MODE><<<grid, 256, smem, s>>>(p);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+}
+
+}  // namespace
+
+// Buffers of one forward pass (all from the model arena).
+struct FwdBufs {
+    float *e0, *e1, *e2, *e3, *c0, *c1, *emb_in, *emb, *g_a, *g_b, *g_h, *xproj, *dec_emb, *d3, *d2, *d1, *dfc;
+};
+
+// Carves the activations of `M` frames out of `a` (or only counts bytes when a == nullptr).
+static size_t fwd_plan(const dfb_model_config &c, size_t M, Arena *a, FwdBufs *f) {
+    const int E = c.nb_erb, Fd = c.nb_df, H = c.emb_hidden, Hd = c.df_hidden;
+    const int ED = E / 4 * kCh;
+    const int emb_in_dim = c.enc_concat ? 2 * ED : ED;
+    const int emb_dim = c.model_kind == 2 ? H : ED;
+    const int Hmax = H > Hd ? H : Hd;
+    size_t bytes = 0;
+    auto take = [&](size_t n) -> float * {
+        bytes += (n * 4 + 255) & ~size_t(255);
+        return a ? a->take<float>(n) : nullptr;
+    };
+    FwdBufs t{};
+    t.e0 = take(M * E * kCh); t.e1 = take(M * (E / 2) * kCh); t.e2 = take(M * (E / 4) * kCh);
+    t.emb_in = take(M * emb_in_dim);
+    t.e3 = c.enc_concat ? t.emb_in : take(M * ED);  // DFN2: e3 lives inside the concat buffer
+    t.c0 = take(M * Fd * kCh); t.c1 = take(M * (Fd / 2) * kCh);
+    t.emb = take(M * emb_dim);
+    t.g_a = take(M * Hmax); t.g_b = take(M * Hmax); t.g_h = take(M * Hmax);
+    t.xproj = take(M * 3 * Hmax);
+    t.dec_emb = take(M * ED); t.d3 = take(M * ED); t.d2 = take(M * (E / 2) * kCh);
+    t.d1 = take(M * E * kCh); t.dfc = take(M * Hmax);
+    if (f) *f = t;
+    return bytes + 4096;
+}
+
+static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s);
+
+extern "C" int dfb_model_forward(dfb_model *m, const float *d_feat_erb, const float *d_feat_spec, int64_t B64,
+                                 int64_t T64, float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha,
+                                 void *stream) {
+    if (!m || !d_feat_erb || !d_feat_spec || !d_m || !d_coefs) return fail(DFB_ERR_INVALID, "null argument");
+    if (B64 <= 0 || T64 <= 0) return DFB_OK;
+    if (B64 > 65535) return fail(DFB_ERR_INVALID, "more than 65535 streams per call");
+    DFB_CUDA(cudaSetDevice(m->device));
+    int rc = m->arena.reserve(fwd_plan(m->cfg, (size_t)B64 * T64, nullptr, nullptr));
+    if (rc) return rc;
+    m->arena.reset();
+    rc = forward_impl(m, m->arena, d_feat_erb, d_feat_spec, (int)B64, (int)T64, d_m, d_coefs, d_lsnr, d_alpha,
+                      (cudaStream_t)stream);
+    m->arena.reset();
+    return rc;
+}
+
+static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s) {
+    const dfb_model_config &c = m->cfg;
+    const int64_t M = (int64_t)B * T;
+    const int E = c.nb_erb, Fd = c.nb_df, H = c.emb_hidden, Hd = c.df_hidden;
+    const int ED = E / 4 * kCh;  // embedding width (512)
+    const int emb_in_dim = c.enc_concat ? 2 * ED : ED;
+    const int emb_dim = c.model_kind == 2 ? H : ED;  // encoder output width
+    int rc;
+    FwdBufs f{};
+    fwd_plan(c, (size_t)M, &arena, &f);
+    if (!f.dfc) return fail(DFB_ERR_OOM, "forward workspace exhausted for %lld frames", (long long)M);
+    m->dbg.clear();
+    m->dbg["e0"] = {f.e0, M * E * kCh}; m->dbg["e1"] = {f.e1, M * (E / 2) * kCh}; m->dbg["e2"] = {f.e2, M * (E / 4) * kCh};
+    m->dbg["e3"] = {f.e3, c.enc_concat ? M * emb_in_dim : M * ED}; m->dbg["c0"] = {f.c0, M * Fd * kCh};
+    m->dbg["c1"] = {f.c1, M * (Fd / 2) * kCh}; m->dbg["emb_in"] = {f.emb_in, M * emb_in_dim};
+    m->dbg["emb"] = {f.emb, M * emb_dim}; m->dbg["dec_emb"] = {f.dec_emb, M * ED}; m->dbg["d3"] = {f.d3, M * ED};
+    m->dbg["d2"] = {f.d2, M * (E / 2) * kCh}; m->dbg["d1"] = {f.d1, M * E * kCh}; m->dbg["dfc"] = {f.dfc, M * Hd};
+    m->dbg["g_a"] = {f.g_a, M * (H > Hd ? H : Hd)}; m->dbg["g_b"] = {f.g_b, M * (H > Hd ? H : Hd)};
+    m->dbg["xproj"] = {f.xproj, M * 3 * (H > Hd ? H : Hd)};
+    const int64_t e3_fs = c.enc_concat ? 2 * ED : ED;
+
+    // ---- encoder (deepfilternet3.py:166-185)
+    {
+        const float *w, *bb;
+        if ((rc = need(m, "enc.erb_conv0.w", c.inp_kt * 3 * kCh, &w)) || (rc = need(m, "enc.erb_conv0.b", kCh, &bb))) return rc;
+        dim3 grid((unsigned)((T + kE0Frames - 1) / kE0Frames), (unsigned)B);
+        int smem = (kE0Frames + c.inp_kt - 1) * (E + 2) * 4;
+        k_erb_conv0<<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead);
+        DFB_LAUNCH_CHECK();
+    }
+    auto blk = [&](const char *name, DwPwParams &p) -> int {
+        std::string n(name);
+        int r;
+        if ((r = need(m, (n + ".dw").c_str(), -1, &p.dw)) || (r = need(m, (n + ".pw").c_str(), kCh * kCh, &p.pw)) ||
+            (r = need(m, (n + ".b").c_str(), kCh, &p.bias)))
+            return r;
+        return DFB_OK;
+    };
+    auto mk = [&](const float *in, int Fin, int64_t in_fs, float *out, int Fout, int64_t out_fs, int kt) {
+        DwPwParams p{};
+        p.in = in; p.Fin = Fin; p.in_fs = in_fs; p.out = out; p.Fout = Fout; p.out_fs = out_fs; p.kt = kt; p.T = T;
+        p.lookahead = 0;
+        return p;
+    };
+    {
+        DwPwParams p = mk(f.e0, E, (int64_t)E * kCh, f.e1, E / 2, (int64_t)E / 2 * kCh, c.conv_kt);
+        if ((rc = blk("enc.erb_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B))) return rc;
+        p = mk(f.e1, E / 2, (int64_t)E / 2 * kCh, f.e2, E / 4, (int64_t)E / 4 * kCh, c.conv_kt);
+        if ((rc = blk("enc.erb_conv2", p)) || (rc = run_dwpw<DW_S2>(s, p, B))) return rc;
+        p = mk(f.e2, E / 4, (int64_t)E / 4 * kCh, f.e3, E / 4, e3_fs, c.conv_kt);
+        if ((rc = blk("enc.erb_conv3", p)) || (rc = run_dwpw<DW_S1>(s, p, B))) return rc;
+        p = mk(d_feat_spec, Fd, (int64_t)Fd * 2, f.c0, Fd, (int64_t)Fd * kCh, c.inp_kt);
+        p.lookahead = c.conv_lookahead;
+        if ((rc = blk("enc.df_conv0", p)) || (rc = run_dwpw<DW_DF0>(s, p, B))) return rc;
+        p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
+        if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B))) return rc;
+    }
+    {
+        // cemb = relu(df_fc_emb(c1 flat)); emb_in = e3 flat + cemb  (DFN2: concat)
+        const float *w;
+        const int I = Fd / 2 * kCh;
+        if ((rc = need(m, "enc.df_fc_emb.gl", (int64_t)I * ED / c.g_df_fc_emb, &w))) return rc;
+        if (c.enc_concat)
+            rc = run_gl(s, f.c1, I, w, nullptr, nullptr, 0, f.emb_in + ED, emb_in_dim, M, c.g_df_fc_emb, I, ED, ACT_RELU);
+        else
+            rc = run_gl(s, f.c1, I, w, nullptr, f.e3, ED, f.emb_in, emb_in_dim, M, c.g_df_fc_emb, I, ED, ACT_RELU);
+        if (rc) return rc;
+    }
+    {
+        // enc.emb_gru: linear_in + ReLU -> GRU -> [linear_out + ReLU]
+        const float *w_in, *w_out = nullptr;
+        if ((rc = need(m, "enc.emb_gru.in.gl", (int64_t)emb_in_dim * H / c.g_enc_in, &w_in))) return rc;
+        if ((rc = run_gl(s, f.emb_in, emb_in_dim, w_in, nullptr, nullptr, 0, f.g_a, H, M, c.g_enc_in, emb_in_dim, H, ACT_RELU))) return rc;
+        float *gout = c.g_enc_out ? f.g_b : f.emb;
+        if ((rc = run_gru(m, s, "enc.emb_gru", c.enc_gru_layers, H, f.g_a, H, nullptr, gout, f.xproj, f.g_h, B, T))) return rc;
+        if (c.g_enc_out) {
+            if ((rc = need(m, "enc.emb_gru.out.gl", (int64_t)H * ED / c.g_enc_out, &w_out))) return rc;
+            if ((rc = run_gl(s, f.g_b, H, w_out, nullptr, nullptr, 0, f.emb, emb_dim, M, c.g_enc_out, H, ED, ACT_RELU))) return rc;
+        }
+        if (d_lsnr) {
+            const float *lw, *lb;
+            if ((rc = need(m, "enc.lsnr.w", emb_dim, &lw)) || (rc = need(m, "enc.lsnr.b", 1, &lb))) return rc;
+            if ((rc = run_gl(s, f.emb, emb_dim, lw, lb, nullptr, 0, d_lsnr, 1, M, 1, emb_dim, 1, ACT_SIGMOID, c.lsnr_scale, c.lsnr_offset))) return rc;
+        }
+    }
+    // ---- ERB decoder (deepfilternet3.py:245-254)
+    {
+        const float *w_in, *w_out;
+        if ((rc = need(m, "erb_dec.emb_gru.in.gl", (int64_t)emb_dim * H / c.g_erb_in, &w_in))) return rc;
+        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a, H, M, c.g_erb_in, emb_dim, H, ACT_RELU))) return rc;
+        // DFN2 (SqueezedGRU): identity skip around the GRU, y = GRU(x) + x  (modules.py:695-697)
+        const float *res = c.model_kind == 2 ? f.g_a : nullptr;
+        if ((rc = run_gru(m, s, "erb_dec.emb_gru", c.erb_gru_layers, H, f.g_a, H, res, f.g_b, f.xproj, f.g_h, B, T))) return rc;
+        if ((rc = need(m, "erb_dec.emb_gru.out.gl", (int64_t)H * ED / c.g_erb_out, &w_out))) return rc;
+        if ((rc = run_gl(s, f.g_b, H, w_out, nullptr, nullptr, 0, f.dec_emb, ED, M, c.g_erb_out, H, ED, ACT_RELU))) return rc;
+        auto path = [&](DwPwParams &p, const char *pn, const float *pt, int64_t pfs) -> int {
+            std::string n(pn);
+            p.path = pt; p.path_fs = pfs;
+            int r;
+            if ((r = need(m, (n + ".s").c_str(), kCh, &p.ps)) || (r = need(m, (n + ".b").c_str(), kCh, &p.pb))) return r;
+            return DFB_OK;
+        };
+        DwPwParams p = mk(f.dec_emb, E / 4, ED, f.d3, E / 4, ED, c.conv_kt);
+        if ((rc = blk("erb_dec.convt3", p)) || (rc = path(p, "erb_dec.conv3p", f.e3, e3_fs)) || (rc = run_dwpw<DW_S1>(s, p, B))) return rc;
+        p = mk(f.d3, E / 4, ED, f.d2, E / 2, (int64_t)E / 2 * kCh, 1);
+        if ((rc = blk("erb_dec.convt2", p)) || (rc = path(p, "erb_dec.conv2p", f.e2, (int64_t)E / 4 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B))) return rc;
+        p = mk(f.d2, E / 2, (int64_t)E / 2 * kCh, f.d1, E, (int64_t)E * kCh, 1);
+        if ((rc = blk("erb_dec.convt1", p)) || (rc = path(p, "erb_dec.conv1p", f.e1, (int64_t)E / 2 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B))) return rc;
+        const float *ps, *pb, *w, *bb;
+        if ((rc = need(m, "erb_dec.conv0p.s", kCh, &ps)) || (rc = need(m, "erb_dec.conv0p.b", kCh, &pb)) ||
+            (rc = need(m, "erb_dec.conv0_out.w", c.conv_kt * 3 * kCh, &w)) || (rc = need(m, "erb_dec.conv0_out.b", 1, &bb)))
+            return rc;
+        static bool attr_done = false;
+        int smem = (kMaskWarps * 2 * (E + 2) * kMaskLd + c.conv_kt * 3 * kCh) * 4;
+        if (!attr_done) {
+            DFB_CUDA(cudaFuncSetAttribute(k_mask_out, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_done = true;
+        }
+        int per_cta = kMaskWarps * kMaskChunk;
+        dim3 grid((unsigned)((T + per_cta - 1) / per_cta), (unsigned)B);
+        k_mask_out<<<grid, 32 * kMaskWarps, smem, s>>>(f.e0, f.d1, ps, pb, w, bb, d_m, T, E, c.conv_kt);
+        DFB_LAUNCH_CHECK();
+    }
+    // ---- DF decoder (deepfilternet3.py:323-331)
+    {
+        const float *w_in, *w_out;
+        if ((rc = need(m, "df_dec.df_gru.in.gl", (int64_t)emb_dim * Hd / c.g_df_in, &w_in))) return rc;
+        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a, Hd, M, c.g_df_in, emb_dim, Hd, ACT_RELU))) return rc;
+        const float *res = c.model_kind == 2 ? f.g_a : nullptr;
+        if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a, Hd, res, f.dfc, f.xproj, f.g_h, B, T))) return rc;
+        if (c.g_df_skip) {
+            const float *w_skip;
+            if ((rc = need(m, "df_dec.df_skip.gl", (int64_t)emb_dim * Hd / c.g_df_skip, &w_skip))) return rc;
+            if ((rc = run_gl(s, f.emb, emb_dim, w_skip, nullptr, f.dfc, Hd, f.dfc, Hd, M, c.g_df_skip, emb_dim, Hd, ACT_NONE))) return rc;
+        }
+        if (d_alpha && c.model_kind == 2) {  // alpha = sigmoid(df_fc_a(c)), deepfilternet2.py:368
+            const float *aw, *ab;
+            if ((rc = need(m, "df_dec.df_fc_a.w", Hd, &aw)) || (rc = need(m, "df_dec.df_fc_a.b", 1, &ab))) return rc;
+            if ((rc = run_gl(s, f.dfc, Hd, aw, ab, nullptr, 0, d_alpha, 1, M, 1, Hd, 1, ACT_SIGMOID))) return rc;
+        }
+        const int O2 = 2 * c.df_order;
+        if ((rc = need(m, "df_dec.df_out.gl", (int64_t)Hd * Fd * O2 / c.g_df_out, &w_out))) return rc;
+        if ((rc = run_gl(s, f.dfc, Hd, w_out, nullptr, nullptr, 0, d_coefs, (int64_t)Fd * O2, M, c.g_df_out, Hd, Fd * O2, ACT_TANH))) return rc;
+        const float *w1, *w2, *bb;
+        if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
+            (rc = need(m, "df_dec.df_convp.w2", O2 * O2, &w2)) || (rc = need(m, "df_dec.df_convp.b", O2, &bb)))
+            return rc;
+        int64_t rows = M * Fd;
+        int smem = (c.df_pathway_kt * O2 * (kCh / 2) + O2 * O2 + O2) * 4;
+        if (c.df_order != 5) return fail(DFB_ERR_UNSUPPORTED, "df_order %d (built kernels: 5)", c.df_order);
+        k_df_convp<5><<<(unsigned)((rows + 127) / 128), 128, smem, s>>>(f.c0, w1, w2, bb, d_coefs, rows, T, Fd, c.df_pathway_kt);
+        DFB_LAUNCH_CHECK();
+    }
+    return DFB_OK;
+}
+
+static int apply_mode(const dfb_model *m) { return m->cfg.model_kind == 2 ? 2 : 1; }
+
+extern "C" int dfb_apply(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_m, const float *d_coefs,
+                         int64_t B, int64_t T, float *d_spec_e, void *stream) {
+    if (!m || !st || !d_spec || !d_m || !d_coefs || !d_spec_e) return fail(DFB_ERR_INVALID, "null argument");
+    DFB_CUDA(cudaSetDevice(m->device));
+    dfb::ApplyParams p{};
+    p.spec = (const float2 *)d_spec; p.m = d_m; p.coefs = d_coefs; p.audio = nullptr; p.spec_out = (float2 *)d_spec_e;
+    p.Tf = (int)T; p.mode = apply_mode(m); p.nb_df = m->cfg.nb_df; p.order = m->cfg.df_order; p.lookahead = m->cfg.df_lookahead;
+    return launch_apply_synthesis(st, p, B, (cudaStream_t)stream);
+}
+
+extern "C" int dfb_model_forward_full(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_feat_erb,
+                                      const float *d_feat_spec, int64_t B, int64_t T, float *d_spec_e, float *d_m,
+                                      float *d_lsnr, float *d_coefs, float *d_alpha, void *stream) {
+    if (!m || !st || !d_spec || !d_feat_erb || !d_feat_spec || !d_spec_e) return fail(DFB_ERR_INVALID, "null argument");
+    DFB_CUDA(cudaSetDevice(m->device));
+    const int64_t M = B * T;
+    const int O2 = 2 * m->cfg.df_order;
+    if (B <= 0 || T <= 0) return DFB_OK;
+    if (B > 65535) return fail(DFB_ERR_INVALID, "more than 65535 streams per call");
+    size_t extra = ((size_t)M * m->cfg.nb_erb + (size_t)M * m->cfg.nb_df * O2) * 4 + 4096;
+    int rc = m->arena.reserve(fwd_plan(m->cfg, (size_t)M, nullptr, nullptr) + extra);
+    if (rc) return rc;
+    m->arena.reset();
+    float *mm = d_m ? d_m : m->arena.take<float>((size_t)M * m->cfg.nb_erb);
+    float *cc = d_coefs ? d_coefs : m->arena.take<float>((size_t)M * m->cfg.nb_df * O2);
+    rc = forward_impl(m, m->arena, d_feat_erb, d_feat_spec, (int)B, (int)T, mm, cc, d_lsnr, d_alpha, (cudaStream_t)stream);
+    if (rc) { m->arena.reset(); return rc; }
+    rc = dfb_apply(m, st, d_spec, mm, cc, B, T, d_spec_e, stream);
+    m->arena.reset();
+    return rc;
+}
+
+extern "C" int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad) {
+    if (!st) return -1;
+    return pad ? T : (T / st->hop) * st->hop;
+}
+
+// enhance(): df/enhance.py:206-250.  Streams are processed in groups so that the workspace stays
+// below kMaxWorkspace; streams are independent (per-channel state reset, pyDF/src/lib.rs:56-58).
+constexpr size_t kMaxWorkspace = size_t(24) << 30;
+
+extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, int64_t B, int64_t T, int pad,
+                           float atten_lim_db, float *d_out, void *stream) {
+    if (!m || !st || !d_audio || !d_out) return fail(DFB_ERR_INVALID, "null argument");
+    if (B <= 0 || T <= 0) return fail(DFB_ERR_INVALID, "empty input");
+    if (m->device != st->device) return fail(DFB_ERR_INVALID, "model and state live on different devices");
+    DFB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const dfb_model_config &c = m->cfg;
+    const int hop = st->hop, fft = st->fft, F = st->tb.F, E = c.nb_erb, Fd = c.nb_df, O2 = 2 * c.df_order;
+    // pad = True appends fft zeros (enhance.py:230-233): Tf = (T + fft) / hop
+    const int64_t Tp = pad ? T + fft : T;
+    const int64_t Tf = Tp / hop;
+    if (Tf <= 0) return fail(DFB_ERR_INVALID, "input shorter than one hop");
+    const int64_t out_len = dfb_enhance_out_len(st, T, pad);
+    const size_t per_stream = ((size_t)Tp + (size_t)Tf * (2 * F + E + 2 * Fd + E + (size_t)Fd * O2)) * 4 +
+                              fwd_plan(c, (size_t)Tf, nullptr, nullptr) + 8192;
+    int64_t group = (int64_t)(kMaxWorkspace / per_stream);
+    if (group < 1) group = 1;
+    if (group > B) group = B;
+    if (group > 65535) group = 65535;
+    int rc = m->arena.reserve(per_stream * (size_t)group + (2 << 20));
+    if (rc) return rc;
+    const float lim = (atten_lim_db > 0.f) ? powf(10.f, -atten_lim_db / 20.f) : 0.f;
+    for (int64_t b0 = 0; b0 < B; b0 += group) {
+        const int64_t nb = (B - b0 < group) ? B - b0 : group;
+        m->arena.reset();
+        const float *x = d_audio + b0 * T;
+        float *xp = nullptr;
+        if (pad) {
+            xp = m->arena.take<float>((size_t)nb * Tp);
+            DFB_CUDA(cudaMemsetAsync(xp, 0, sizeof(float) * nb * Tp, s));
+            DFB_CUDA(cudaMemcpy2DAsync(xp, sizeof(float) * Tp, x, sizeof(float) * T, sizeof(float) * T, nb,
+                                       cudaMemcpyDeviceToDevice, s));
+            x = xp;
+        }
+        float *spec = m->arena.take<float>((size_t)nb * Tf * F * 2 + 2);
+        float *fe = m->arena.take<float>((size_t)nb * Tf * E);
+        float *fs = m->arena.take<float>((size_t)nb * Tf * Fd * 2);
+        float *mm = m->arena.take<float>((size_t)nb * Tf * E);
+        float *cc = m->arena.take<float>((size_t)nb * Tf * Fd * O2);
+        if (!cc) return fail(DFB_ERR_OOM, "enhance workspace exhausted");
+        if ((rc = dfb_features(st, x, nb, Tp, Fd, c.norm_alpha, spec, fe, fs, s))) return rc;
+        if ((rc = forward_impl(m, m->arena, fe, fs, (int)nb, (int)Tf, mm, cc, nullptr, nullptr, s))) return rc;
+        dfb::ApplyParams p{};
+        p.spec = (const float2 *)spec; p.m = mm; p.coefs = cc; p.audio = d_out + b0 * out_len; p.spec_out = nullptr;
+        p.out_stride = out_len; p.out_offset = pad ? (fft - hop) : 0; p.out_len = out_len;
+        p.Tf = (int)Tf; p.mode = apply_mode(m); p.nb_df = Fd; p.order = c.df_order; p.lookahead = c.df_lookahead;
+        p.atten_lim = lim;
+        if ((rc = launch_apply_synthesis(st, p, nb, s))) return rc;
+    }
+    m->arena.reset();
+    return DFB_OK;
+}
+
+extern "C" int dfb_enhance_host(dfb_model *m, dfb_state *st, const float *h_audio, int64_t B, int64_t T, int pad,
+                                float atten_lim_db, float *h_out) {
+    if (!m || !st || !h_audio || !h_out) return fail(DFB_ERR_INVALID, "null argument");
+    if (B <= 0 || T <= 0) return fail(DFB_ERR_INVALID, "empty input");
+    DFB_CUDA(cudaSetDevice(m->device));
+    const int64_t out_len = dfb_enhance_out_len(st, T, pad);
+    int rc = st->arena.reserve(sizeof(float) * (size_t)B * (T + out_len) + 4096);
+    if (rc) return rc;
+    st->arena.reset();
+    float *d_in = st->arena.take<float>((size_t)B * T), *d_out = st->arena.take<float>((size_t)B * out_len);
+    DFB_CUDA(cudaMemcpyAsync(d_in, h_audio, sizeof(float) * B * T, cudaMemcpyHostToDevice, m->stream));
+    if ((rc = dfb_enhance(m, st, d_in, B, T, pad, atten_lim_db, d_out, m->stream))) return rc;
+    DFB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(float) * B * out_len, cudaMemcpyDeviceToHost, m->stream));
+    DFB_CUDA(cudaStreamSynchronize(m->stream));
+    return DFB_OK;
+}

@@ -1,0 +1,172 @@
+/*
+ * dfb200.h -- C ABI of libdfb200.so: the B200 (sm_100a) implementation of DeepFilterNet's
+ * per-frame enhancement path (STFT -> ERB / complex features -> encoder / GRUs / decoders ->
+ * gain mask + deep filter -> ISTFT).
+ *
+ * The reference has NO C ABI for this batched path: its boundary is the PyO3 module `libdf`
+ * (pyDF/src/lib.rs) plus the Python functions in DeepFilterNet/df/enhance.py.  Each entry point
+ * below names the reference interface it replaces; INTEGRATION.md shows the binding a reference
+ * maintainer would add (ctypes stubs that stand in for pyDF's #[pymethods]).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types cross this boundary.
+ *   - every function returns 0 on success or a negative dfb_status; dfb_last_error() returns a
+ *     thread-local human readable message for the last failure.
+ *   - "_host" entry points take HOST pointers and do the host<->device copies themselves (on the
+ *     handle's stream, synchronised before returning); the others take DEVICE pointers valid on
+ *     the handle's device and are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - complex data are interleaved (re, im) float pairs, exactly numpy complex64 / Rust Complex32.
+ *   - there is no CPU fallback: every function fails with DFB_ERR_CUDA when no sm_100 device is
+ *     usable.
+ */
+#ifndef DFB200_H
+#define DFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DFB_OK = 0,
+    DFB_ERR_INVALID = -1,     /* bad argument (shape, null pointer, unsupported size) */
+    DFB_ERR_CUDA = -2,        /* CUDA runtime / launch failure, or no usable device    */
+    DFB_ERR_UNSUPPORTED = -3, /* configuration outside the built kernels               */
+    DFB_ERR_OOM = -4
+} dfb_status;
+
+const char *dfb_last_error(void);
+/* ABI / build info: "dfb200 <version> sm_100a" */
+const char *dfb_version(void);
+/* number of CUDA kernels this library has launched in the calling process (all handles) */
+int64_t dfb_kernel_launches(void);
+
+/* ------------------------------------------------------------------ DSP state ------------
+ * Replaces libDF `DFState` as exposed by pyDF `DF` (pyDF/src/lib.rs:14-136,
+ * libDF/src/lib.rs:104-154).  Holds the vorbis window, FFT twiddles and ERB tables on the device.
+ * Unlike the reference there are no per-object analysis / synthesis memories: every call below
+ * starts each channel from the reset state, which is what pyDF does with its default
+ * `reset=True` (pyDF/src/lib.rs:56-58, 91-93). */
+typedef struct dfb_state dfb_state;
+
+/* pyDF DF.__new__ (pyDF/src/lib.rs:22-39) -> DFState::new (libDF/src/lib.rs:104-154).
+ * device: CUDA ordinal.  Built kernels: fft_size 960 / hop_size 480 (all shipped models). */
+int dfb_state_create(dfb_state **out, int device, int sr, int fft_size, int hop_size, int nb_erb,
+                     int min_nb_erb_freqs);
+void dfb_state_free(dfb_state *st);
+/* pyDF erb_widths / fft_window / sr / fft_size / hop_size / nb_erb (pyDF/src/lib.rs:109-131) */
+int dfb_state_erb_widths(const dfb_state *st, int64_t *widths /* [nb_erb] host */);
+int dfb_state_fft_window(const dfb_state *st, float *window /* [fft_size] host */);
+int dfb_state_params(const dfb_state *st, int *sr, int *fft_size, int *hop_size, int *nb_erb);
+/* ERB band widths only, no device needed: libDF erb_fb (libDF/src/lib.rs:68-100) */
+int dfb_erb_widths(int sr, int fft_size, int nb_erb, int min_nb_freqs, int64_t *widths);
+
+/* pyDF DF.analysis (pyDF/src/lib.rs:41-72) -> frame_analysis (libDF/src/lib.rs:356-394).
+ * audio f32[C, T] (row stride T) -> spec c64[C, T / hop, F].  Trailing partial frame dropped. */
+int dfb_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, void *stream);
+int dfb_analysis_host(dfb_state *st, const float *h_audio, int64_t C, int64_t T, float *h_spec);
+
+/* pyDF DF.synthesis (pyDF/src/lib.rs:74-107) -> frame_synthesis (libDF/src/lib.rs:396-427).
+ * spec c64[C, Tf, F] -> audio f32[C, Tf * hop].  Does NOT clobber its input (the reference does). */
+int dfb_synthesis(dfb_state *st, const float *d_spec, int64_t C, int64_t Tf, float *d_audio, void *stream);
+int dfb_synthesis_host(dfb_state *st, const float *h_spec, int64_t C, int64_t Tf, float *h_audio);
+
+/* libdf.erb (pyDF/src/lib.rs:142-192) -> compute_band_corr (+dB) (libDF/src/lib.rs:280-295,
+ * transforms.rs:236-253).  spec c64[n_frames, F] -> f32[n_frames, E]; widths host int64[E]. */
+int dfb_erb_host(int device, const float *h_spec, int64_t n_frames, int64_t F, const int64_t *widths, int E,
+                 int db, float *h_out);
+/* libdf.erb_inv (pyDF/src/lib.rs:194-250) -> interp_band_gain (libDF/src/lib.rs:328-337). */
+int dfb_erb_inv_host(int device, const float *h_gains, int64_t n_frames, const int64_t *widths, int E,
+                     float *h_out /* [n_frames, sum(widths)] */);
+/* libdf.erb_norm (pyDF/src/lib.rs:252-274) -> band_mean_norm_erb (libDF/src/lib.rs:244-251).
+ * erb f32[C, T, E] -> out f32[C, T, E]; state f32[C, E] or NULL (linspace(-60,-90,E)). */
+int dfb_erb_norm_host(int device, const float *h_erb, int64_t C, int64_t T, int64_t E, float alpha,
+                      const float *h_state, float *h_out);
+/* libdf.unit_norm (pyDF/src/lib.rs:276-298) -> band_unit_norm (libDF/src/lib.rs:253-259).
+ * spec c64[C, T, F] -> out c64[C, T, F]; state f32[C, F] or NULL (linspace(1e-3,1e-4,F)). */
+int dfb_unit_norm_host(int device, const float *h_spec, int64_t C, int64_t T, int64_t F, float alpha,
+                       const float *h_state, float *h_out);
+/* libdf.unit_norm_init (pyDF/src/lib.rs:300-307) */
+int dfb_unit_norm_init(int64_t n, float *h_out);
+
+/* df.enhance.df_features (DeepFilterNet/df/enhance.py:190-203) as ONE fused device pass:
+ * audio f32[C,T] -> spec c64[C,Tf,F], feat_erb f32[C,Tf,E], feat_spec c64[C,Tf,nb_df]. */
+int dfb_features(dfb_state *st, const float *d_audio, int64_t C, int64_t T, int nb_df, float alpha,
+                 float *d_spec, float *d_feat_erb, float *d_feat_spec, void *stream);
+int dfb_features_host(dfb_state *st, const float *h_audio, int64_t C, int64_t T, int nb_df, float alpha,
+                      float *h_spec, float *h_feat_erb, float *h_feat_spec);
+
+/* ------------------------------------------------------------------ model ------------------
+ * Replaces the forward pass of DeepFilterNet/df/deepfilternet3.py (DfNet :334-456) and
+ * deepfilternet2.py (DfNet :374-505) for the shipped DeepFilterNet2 / 3 / 3_ll topologies. */
+typedef struct dfb_model dfb_model;
+
+typedef struct {
+    int32_t model_kind;      /* 2 = DeepFilterNet2, 3 = DeepFilterNet3 (incl. _ll)          */
+    int32_t nb_erb, nb_df, df_order, df_lookahead, conv_lookahead;
+    int32_t conv_ch;         /* 64                                                           */
+    int32_t conv_kt;         /* time taps of the `conv_kernel` layers (1; _ll: 2)            */
+    int32_t inp_kt;          /* time taps of conv_kernel_inp (3)                             */
+    int32_t emb_hidden, df_hidden;
+    int32_t enc_gru_layers, erb_gru_layers, df_gru_layers;
+    int32_t df_pathway_kt;   /* 5 */
+    int32_t enc_concat;      /* DFN2: 1 */
+    int32_t g_df_fc_emb, g_enc_in, g_enc_out, g_erb_in, g_erb_out, g_df_in, g_df_skip, g_df_out;
+    float lsnr_scale, lsnr_offset;
+    float norm_alpha;        /* feature normalisation decay, df/utils.py:108-124 (0.99) */
+} dfb_model_config;
+
+/* One named fp32 tensor of the packed weight set (BatchNorm already folded, layouts as documented
+ * in deepfilternet_b200/weights.py).  `data` is a HOST pointer; it is copied to the device. */
+typedef struct {
+    const char *name;
+    const float *data;
+    int64_t numel;
+} dfb_tensor;
+
+/* Replaces init_model + load_state_dict (deepfilternet3.py:80-87, checkpoint.py:46-104). */
+int dfb_model_create(dfb_model **out, int device, const dfb_model_config *cfg, const dfb_tensor *tensors,
+                     int n_tensors, const int64_t *erb_widths);
+void dfb_model_free(dfb_model *m);
+
+/* DfNet.forward without the spectral apply (deepfilternet3.py:407-441): features -> ERB mask m,
+ * DF coefficients and local SNR.  feat_erb f32[B,T,E], feat_spec c64[B,T,nb_df]
+ * -> m f32[B,T,E], coefs f32[B,T,nb_df,2*order], lsnr f32[B,T] (may be NULL), alpha f32[B,T]
+ * (DeepFilterNet2's df_fc_a output, deepfilternet2.py:368; may be NULL, ignored for kind 3). */
+int dfb_model_forward(dfb_model *m, const float *d_feat_erb, const float *d_feat_spec, int64_t B, int64_t T,
+                      float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, void *stream);
+
+/* Mask.forward + MF.DF.forward (modules.py:248-269, multiframe.py:169-180,
+ * deepfilternet3.py:431-443 / deepfilternet2.py:494-503): spec c64[B,T,F], m, coefs -> spec_e. */
+int dfb_apply(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_m, const float *d_coefs,
+              int64_t B, int64_t T, float *d_spec_e, void *stream);
+
+/* DfNet.forward (deepfilternet3.py:389-456): (spec, feat_erb, feat_spec) -> (spec_e, m, lsnr, coefs);
+ * any of d_m / d_lsnr / d_coefs / d_alpha may be NULL. */
+int dfb_model_forward_full(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_feat_erb,
+                           const float *d_feat_spec, int64_t B, int64_t T, float *d_spec_e, float *d_m,
+                           float *d_lsnr, float *d_coefs, float *d_alpha, void *stream);
+
+/* df.enhance.enhance (DeepFilterNet/df/enhance.py:206-250), the whole path in one call:
+ * audio f32[B,T] -> enhanced f32[B,T_out].  pad != 0: zero-pad fft_size samples at the end and
+ * crop the STFT delay (T_out = T); pad == 0: T_out = (T / hop) * hop, delayed by fft - hop.
+ * atten_lim_db <= 0 disables the attenuation limit (enhance.py:238-240).
+ * The apply + ISTFT stage is one fused kernel (gain x spectrum + deep filter + irFFT + OLA). */
+int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, int64_t B, int64_t T, int pad,
+                float atten_lim_db, float *d_out, void *stream);
+int dfb_enhance_host(dfb_model *m, dfb_state *st, const float *h_audio, int64_t B, int64_t T, int pad,
+                     float atten_lim_db, float *h_out);
+/* output length of dfb_enhance for a given input length */
+int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad);
+/* Debug aid for parity tests: copies the named activation of the LAST forward pass on this handle
+ * (e0,e1,e2,e3,c0,c1,emb_in,emb,dec_emb,d3,d2,d1,dfc) to the host; returns the element count
+ * (or a negative dfb_status).  Valid until the next call on the handle. */
+int64_t dfb_model_debug_fetch(dfb_model *m, const char *name, float *h_out, int64_t max_numel);
+/* bytes of device workspace the model handle currently owns (grow-only arena) */
+int64_t dfb_model_workspace_bytes(const dfb_model *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFB200_H */
