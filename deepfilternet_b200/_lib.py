@@ -53,6 +53,8 @@ SIGNATURES = {
     "dfb_last_error": (C.c_char_p, []),
     "dfb_version": (C.c_char_p, []),
     "dfb_kernel_launches": (_I64, []),
+    "dfb_profile_enable": (_I, [_I, C.c_char_p]),
+    "dfb_profile_report": (_I64, [C.c_char_p, _I64]),
     "dfb_state_create": (_I, [C.POINTER(_VP), _I, _I, _I, _I, _I, _I]),
     "dfb_state_free": (None, [_VP]),
     "dfb_state_erb_widths": (_I, [_VP, _I64P]),

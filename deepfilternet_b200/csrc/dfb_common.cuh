@@ -44,6 +44,16 @@ inline int fail(int code, const char *fmt, ...) {
                              cudaGetErrorString(e__), __FILE__, __LINE__);                      \
     } while (0)
 
+// Optional per-kernel timing with CUDA events on the launching stream (dfb_profile_* in the C ABI).
+// Off by default; when on, every launch site brackets its kernel with two events.
+struct ProfScope {
+    int slot = -1;
+    cudaStream_t s;
+    ProfScope(const char *name, cudaStream_t stream);
+    ~ProfScope();
+};
+#define DFB_PROF(name, stream) dfb::ProfScope prof_scope__(name, stream)
+
 // Selects `device` and verifies it is a Blackwell part; no CPU fallback exists.
 int use_device(int device);
 

@@ -25,6 +25,34 @@ namespace dfb {
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
 
+// ---- per-kernel event profiler -------------------------------------------------------------
+namespace {
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+bool g_prof_on = false;
+std::string g_prof_only;
+}  // namespace
+
+ProfScope::ProfScope(const char *name, cudaStream_t stream) : s(stream) {
+    if (!g_prof_on) return;
+    if (!g_prof_only.empty() && g_prof_only != name) return;
+    ProfRec r;
+    r.name = name;
+    if (!g_prof_pool.empty()) {
+        r.a = g_prof_pool.back().first; r.b = g_prof_pool.back().second;
+        g_prof_pool.pop_back();
+    } else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+        return;
+    }
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, s);
+}
+
 int use_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -379,6 +407,40 @@ extern "C" const char *dfb_last_error(void) { return g_err.c_str(); }
 extern "C" const char *dfb_version(void) { return "dfb200 0.1.0 sm_100a"; }
 extern "C" int64_t dfb_kernel_launches(void) { return g_launches.load(); }
 
+extern "C" int dfb_profile_enable(int on, const char *only_kernel) {
+    g_prof_on = on != 0;
+    g_prof_only = only_kernel ? only_kernel : "";
+    return DFB_OK;
+}
+
+// Writes "name count total_ms\n" lines for everything recorded since the last report and clears.
+extern "C" int64_t dfb_profile_report(char *buf, int64_t buflen) {
+    if (!buf || buflen <= 0) return fail(DFB_ERR_INVALID, "bad buffer");
+    cudaDeviceSynchronize();
+    std::vector<std::string> names;
+    std::vector<double> ms;
+    std::vector<int64_t> cnt;
+    for (auto &r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) t = 0.f;
+        size_t i = 0;
+        for (; i < names.size(); i++) if (names[i] == r.name) break;
+        if (i == names.size()) { names.push_back(r.name); ms.push_back(0); cnt.push_back(0); }
+        ms[i] += t; cnt[i] += 1;
+        g_prof_pool.push_back({r.a, r.b});
+    }
+    g_prof.clear();
+    std::string out;
+    char line[256];
+    for (size_t i = 0; i < names.size(); i++) {
+        snprintf(line, sizeof line, "%s %lld %.6f\n", names[i].c_str(), (long long)cnt[i], ms[i]);
+        out += line;
+    }
+    if ((int64_t)out.size() + 1 > buflen) return fail(DFB_ERR_INVALID, "profile buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int64_t)out.size();
+}
+
 // libDF/src/lib.rs:42-47,68-100 (f32 arithmetic, integer result)
 extern "C" int dfb_erb_widths(int sr, int fft_size, int nb_erb, int min_nb_freqs, int64_t *out) {
     if (!out || nb_erb <= 0 || nb_erb > kMaxErb || fft_size <= 0) return fail(DFB_ERR_INVALID, "bad erb parameters");
@@ -531,6 +593,7 @@ int launch_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, f
     if (C <= 0 || Tf <= 0) return DFB_OK;
     if (C > 65535) return fail(DFB_ERR_INVALID, "more than 65535 channels per call");
     dim3 grid((unsigned)((Tf + kAnaWarps - 1) / kAnaWarps), (unsigned)C);
+    DFB_PROF("k_analysis", s);
     k_analysis<<<grid, 32 * kAnaWarps, kAnaSmem, s>>>(d_audio, T, (int)Tf, (float2 *)d_spec, d_erb_db, st->tb);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
@@ -542,6 +605,7 @@ int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float 
     if (C <= 0 || Tf <= 0 || E + Fd == 0) return DFB_OK;
     if (E + Fd > 1024) return fail(DFB_ERR_INVALID, "E + F > 1024 in norm scan");
     int threads = ((E + Fd + 31) / 32) * 32;
+    DFB_PROF("k_feat_norm", s);
     k_feat_norm<<<(unsigned)C, threads, 0, s>>>(d_erb, E, erb_stride, (const float2 *)d_spec, Fd, spec_stride, (int)Tf,
                                                alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec);
     DFB_LAUNCH_CHECK();
@@ -554,6 +618,7 @@ int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaS
     if (p.mode != 0 && (p.nb_df > 240 || p.order > 8)) return fail(DFB_ERR_UNSUPPORTED, "nb_df > 240 or df_order > 8");
     int per_cta = kSynWarps * kSynChunk;
     dim3 grid((unsigned)((p.Tf + per_cta - 1) / per_cta), (unsigned)B);
+    DFB_PROF("k_apply_synthesis", s);
     k_apply_synthesis<<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
     DFB_LAUNCH_CHECK();
     return DFB_OK;

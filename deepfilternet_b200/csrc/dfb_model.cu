@@ -644,6 +644,7 @@ int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const fl
     if ((p.Ig % 4) || (ldx % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: K not a multiple of 4");
     int tiles = (p.Hg + kGlBN - 1) / kGlBN;
     dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(G * tiles));
+    DFB_PROF(p.G == 1 && p.bias && p.Hg >= 512 ? "k_grouped_linear[gru_proj]" : "k_grouped_linear", s);
     k_grouped_linear<<<grid, 256, 0, s>>>(p);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
@@ -669,6 +670,7 @@ int launch_gru_t(cudaStream_t s, const GruParams &p, int ngroups) {
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     GruParams pp = p;
+    DFB_PROF("k_gru", s);
     DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru<H, C>, pp));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return DFB_OK;
@@ -728,6 +730,7 @@ int run_dwpw(cudaStream_t s, DwPwParams p, int B) {
     if (p.NF < 1) p.NF = 1;
     if (p.NF * p.Fout > 128 || (p.NF * p.Fout) % 4) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile: Fout = %d", p.Fout);
     dim3 grid((unsigned)((p.T + p.NF - 1) / p.NF), (unsigned)B);
+    DFB_PROF(MODE == DW_DF0 ? "k_dwpw[df_conv0]" : "k_dwpw", s);
     k_dwpw<MODE><<<grid, 256, smem, s>>>(p);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
@@ -813,6 +816,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if ((rc = need(m, "enc.erb_conv0.w", c.inp_kt * 3 * kCh, &w)) || (rc = need(m, "enc.erb_conv0.b", kCh, &bb))) return rc;
         dim3 grid((unsigned)((T + kE0Frames - 1) / kE0Frames), (unsigned)B);
         int smem = (kE0Frames + c.inp_kt - 1) * (E + 2) * 4;
+        DFB_PROF("k_erb_conv0", s);
         k_erb_conv0<<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead);
         DFB_LAUNCH_CHECK();
     }
@@ -906,6 +910,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         }
         int per_cta = kMaskWarps * kMaskChunk;
         dim3 grid((unsigned)((T + per_cta - 1) / per_cta), (unsigned)B);
+        DFB_PROF("k_mask_out", s);
         k_mask_out<<<grid, 32 * kMaskWarps, smem, s>>>(f.e0, f.d1, ps, pb, w, bb, d_m, T, E, c.conv_kt);
         DFB_LAUNCH_CHECK();
     }
@@ -936,6 +941,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         int64_t rows = M * Fd;
         int smem = (c.df_pathway_kt * O2 * (kCh / 2) + O2 * O2 + O2) * 4;
         if (c.df_order != 5) return fail(DFB_ERR_UNSUPPORTED, "df_order %d (built kernels: 5)", c.df_order);
+        DFB_PROF("k_df_convp", s);
         k_df_convp<5><<<(unsigned)((rows + 127) / 128), 128, smem, s>>>(f.c0, w1, w2, bb, d_coefs, rows, T, Fd, c.df_pathway_kt);
         DFB_LAUNCH_CHECK();
     }

@@ -98,16 +98,20 @@ def df_features(audio: Tensor, df: DF, nb_df: int, device=None, alpha: float = 0
 
 @torch.no_grad()
 def enhance(model: DfNet, df_state: DF, audio: Tensor, pad: bool = True,
-            atten_lim_db: Optional[float] = None) -> Tensor:
+            atten_lim_db: Optional[float] = None, out: Optional[Tensor] = None) -> Tensor:
     """enhance.py:206-250: audio f32 CPU [C,T] @ model sr -> enhanced f32 CPU [C,T]
-    (or [C, (T // hop) * hop], delayed by n_fft - hop, when ``pad`` is False)."""
+    (or [C, (T // hop) * hop], delayed by n_fft - hop, when ``pad`` is False).
+    ``out`` (extension): optional preallocated (e.g. pinned) CPU tensor for the result."""
     model.eval()
     if audio.dim() != 2:
         raise ValueError("audio must have shape [C, T]")
     x = audio.detach().to("cpu", torch.float32).contiguous()
     c, t = x.shape
     out_len = int(_lib.lib().dfb_enhance_out_len(df_state.handle, t, 1 if pad else 0))
-    out = torch.empty((c, out_len), dtype=torch.float32)
+    if out is None:
+        out = torch.empty((c, out_len), dtype=torch.float32)
+    elif out.shape != (c, out_len) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float32 CPU tensor of shape {(c, out_len)}")
     lim = abs(float(atten_lim_db)) if atten_lim_db is not None else 0.0
     check(_lib.lib().dfb_enhance_host(model.handle, df_state.handle, x.data_ptr(), c, t, 1 if pad else 0,
                                       lim, out.data_ptr()))

@@ -42,6 +42,13 @@ const char *dfb_version(void);
 /* number of CUDA kernels this library has launched in the calling process (all handles) */
 int64_t dfb_kernel_launches(void);
 
+/* Per-kernel timing with CUDA events on the launching stream (used by bench.py for the roofline
+ * numbers).  on != 0 enables it; only_kernel (may be NULL) restricts it to one kernel name.
+ * dfb_profile_report synchronises the device, writes "name count total_ms\n" lines for everything
+ * recorded since the previous report into buf and returns the number of bytes written. */
+int dfb_profile_enable(int on, const char *only_kernel);
+int64_t dfb_profile_report(char *buf, int64_t buflen);
+
 /* ------------------------------------------------------------------ DSP state ------------
  * Replaces libDF `DFState` as exposed by pyDF `DF` (pyDF/src/lib.rs:14-136,
  * libDF/src/lib.rs:104-154).  Holds the vorbis window, FFT twiddles and ERB tables on the device.

@@ -1,0 +1,235 @@
+"""GPU: the CUDA path (through the C ABI / its Python mirror) against the CPU oracle on the same
+seeded inputs, against the committed golden fixtures, and through size-independent properties at
+larger sizes.  Tolerances: integer indexing (ERB widths, frame counts, crop offsets) bit exact;
+floating point RMS(out - oracle) <= 1e-4 as BASELINE.json states (measured: ~2e-8)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import dfnet_oracle as O
+import libdf_oracle as LO
+from tests_common import synth_audio
+
+from deepfilternet_b200 import DfNet, _lib, enhance, enhance_device, init_df, libdf
+from deepfilternet_b200.config import ModelConfig, load_config
+from deepfilternet_b200.enhance import df_features
+from deepfilternet_b200.model import find_checkpoint, load_state_dict_file
+from deepfilternet_b200.weights import random_state_dict
+
+RMS_TOL = 1e-4  # BASELINE.json north_star
+
+
+def rms(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean()))
+
+
+def cfg_of(kind):
+    base = dict(conv_ch=64, df_pathway_kernel_size_t=5)
+    if kind == "dfn3":
+        return ModelConfig(model="deepfilternet3", conv_lookahead=2, df_lookahead=2, emb_num_layers=3, df_num_layers=2,
+                           lin_groups=16, enc_lin_groups=32, df_gru_skip="groupedlinear", **base)
+    if kind == "dfn2":
+        return ModelConfig(model="deepfilternet2", conv_lookahead=2, df_lookahead=2, emb_num_layers=3, df_num_layers=2,
+                           lin_groups=8, enc_lin_groups=8, enc_concat=True, **base)
+    return ModelConfig(model="deepfilternet3", conv_lookahead=0, df_lookahead=0, conv_kernel=(2, 3), emb_hidden_dim=512,
+                       df_hidden_dim=512, emb_num_layers=3, df_num_layers=3, lin_groups=16, enc_lin_groups=16,
+                       df_gru_skip="groupedlinear", **base)
+
+
+@pytest.fixture(scope="module")
+def states():
+    return libdf.DF(48000, 960, 480, 32, 2), LO.DF(48000, 960, 480, 32, 2)
+
+
+# ------------------------------------------------------------------ libdf (pyDF boundary) ----
+def test_df_accessors(states):
+    st, ost = states
+    assert st.erb_widths().dtype == np.uint64 and st.erb_widths().tolist() == ost.erb_widths().tolist()
+    assert np.array_equal(st.fft_window(), ost.fft_window())
+    assert (st.sr(), st.fft_size(), st.hop_size(), st.nb_erb()) == (48000, 960, 480, 32)
+
+
+@pytest.mark.parametrize("C,T", [(1, 480), (1, 479 + 480), (3, 12345), (2, 48000)])
+def test_analysis_synthesis(states, C, T):
+    st, ost = states
+    x = synth_audio(C, T, seed=11).numpy()
+    a, b = st.analysis(x), ost.analysis(x)
+    assert a.shape == b.shape == (C, T // 480, 481) and a.dtype == np.complex64
+    assert np.abs(a - b).max() < 1e-6
+    y, z = st.synthesis(b.copy()), ost.synthesis(b.copy())
+    assert y.shape == z.shape == (C, (T // 480) * 480)
+    assert np.abs(y - z).max() < 2e-6
+
+
+def test_analysis_errors(states):
+    st, _ = states
+    with pytest.raises(RuntimeError, match="empty or not contiguous"):
+        st.analysis(np.zeros((2, 9600), np.float32)[:, ::2])
+    with pytest.raises(RuntimeError, match="empty or not contiguous"):
+        st.analysis(np.zeros((0, 960), np.float32))
+    assert st.analysis(np.zeros((2, 100), np.float32)).shape == (2, 0, 481)  # shorter than one hop
+    with pytest.raises(RuntimeError):
+        libdf.DF(48000, 960, 500, 32, 2)  # hop * 2 > fft (libDF/src/lib.rs:111)
+
+
+def test_stft_istft_reconstruction(states):
+    """libDF/src/transforms.rs:618-638 on the GPU kernels."""
+    st, _ = states
+    x = synth_audio(2, 96000, seed=3).numpy()
+    y = st.synthesis(st.analysis(x))
+    d = 480
+    for c in range(2):
+        a, b = x[c, :-d], y[c, d:]
+        corr = float(np.dot(a, b) / np.sqrt(np.dot(a, a) * np.dot(b, b)))
+        assert corr > 1 - 1e-6
+
+
+def test_erb_family(states):
+    st, ost = states
+    rng = np.random.default_rng(0)
+    spec = (rng.standard_normal((2, 50, 481)) + 1j * rng.standard_normal((2, 50, 481))).astype(np.complex64) * 0.01
+    w = st.erb_widths()
+    for db in (True, False):
+        a, b = libdf.erb(spec, w, db), LO.erb(spec, w, db)
+        assert a.shape == (2, 50, 32) and np.allclose(a, b, rtol=1e-5, atol=2e-5)
+    assert libdf.erb(spec[0], w).shape == (50, 32) and libdf.erb(spec[None], w).shape == (1, 2, 50, 32)
+    with pytest.raises(ValueError, match="Dimension not supported for erb"):
+        libdf.erb(spec[0, 0], w)
+    e = LO.erb(spec, w)
+    assert np.array_equal(libdf.erb_norm(e, 0.99), LO.erb_norm(e, 0.99))
+    s0 = rng.standard_normal((2, 32)).astype(np.float32)
+    assert np.array_equal(libdf.erb_norm(e, 0.9, s0), LO.erb_norm(e, 0.9, s0))
+    assert np.abs(libdf.unit_norm(spec[..., :96].copy(), 0.99) - LO.unit_norm(spec[..., :96].copy(), 0.99)).max() < 1e-5
+    u0 = np.abs(rng.standard_normal((2, 481))).astype(np.float32) + 0.01
+    assert np.abs(libdf.unit_norm(spec, 0.95, u0) - LO.unit_norm(spec, 0.95, u0)).max() < 1e-5
+    assert np.array_equal(libdf.unit_norm_init(96), LO.unit_norm_init(96))
+    g = rng.uniform(0, 1, (2, 7, 32)).astype(np.float32)
+    assert np.array_equal(libdf.erb_inv(g, w), LO.erb_inv(g, w))
+    with pytest.raises(ValueError, match="Number of erb bands do not match"):
+        libdf.erb_inv(g[..., :31], w)
+
+
+def test_df_features_matches_reference_composition(states):
+    """df_features (enhance.py:190-203) == analysis -> erb -> erb_norm / unit_norm, one fused pass."""
+    st, ost = states
+    x = synth_audio(3, 24000, seed=7)
+    sp, fe, fs = df_features(x, st, 96, alpha=0.99)
+    spec = ost.analysis(x.numpy())
+    assert np.abs(sp.numpy() - torch.view_as_real(torch.from_numpy(spec)).unsqueeze(1).numpy()).max() < 1e-6
+    assert np.abs(fe.numpy()[:, 0] - LO.erb_norm(LO.erb(spec, ost.erb_widths()), 0.99)).max() < 2e-6
+    ref = torch.view_as_real(torch.from_numpy(LO.unit_norm(np.ascontiguousarray(spec[..., :96]), 0.99))).unsqueeze(1)
+    assert np.abs(fs.numpy() - ref.numpy()).max() < 1e-5
+
+
+# ------------------------------------------------------------------ DfNet.forward ----
+@pytest.mark.parametrize("kind,B,T", [("dfn3", 3, 24000), ("dfn3", 1, 4800), ("dfn2", 2, 19200), ("ll", 5, 14400),
+                                      ("dfn3", 9, 9600), ("ll", 17, 4800)])
+def test_forward_random_weights(states, kind, B, T):
+    st, _ = states
+    cfg = cfg_of(kind)
+    sd = random_state_dict(cfg, seed=2)
+    model = DfNet(cfg, sd, st)
+    audio = synth_audio(B, T, seed=21)
+    out_o, aux = O.enhance(sd, cfg.as_dict(), audio, return_all=True)
+    spec_e, m, lsnr, last = model(aux["spec"], aux["erb_feat"], aux["spec_feat"])
+    assert spec_e.shape == aux["spec_e"].shape and m.shape == aux["m"].shape and lsnr.shape == aux["lsnr"].shape
+    assert rms(m, aux["m"]) < 1e-5 and rms(spec_e, aux["spec_e"]) < 1e-6
+    assert np.abs(lsnr.numpy() - aux["lsnr"].numpy()).max() < 1e-3
+    if cfg.model == "deepfilternet3":
+        assert last.shape == (B, 5, aux["m"].shape[2], 96, 2)
+        assert rms(last.permute(0, 2, 3, 1, 4).reshape(aux["coefs"].shape), aux["coefs"]) < 1e-5
+    out = enhance(model, st, audio)
+    assert out.shape == audio.shape and rms(out, out_o) < RMS_TOL
+    # CUDA-tensor in, CUDA-tensor out through the same forward
+    r = model(aux["spec"].cuda(), aux["erb_feat"].cuda(), aux["spec_feat"].cuda())
+    assert r[0].is_cuda and rms(r[0].cpu(), aux["spec_e"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
+def test_golden_reference_outputs(name, golden_dir, model_dir):
+    """Against outputs of the reference's own modules (tests/golden, made by oracle/gen_golden.py)."""
+    g = np.load(os.path.join(golden_dir, f"dfnet_{name}.npz"))
+    model, st, suffix, epoch = init_df(os.path.join(model_dir, name), log_level="ERROR")
+    assert suffix == name
+    audio = torch.from_numpy(g["audio"])
+    assert rms(enhance(model, st, audio), g["enhanced"]) < RMS_TOL
+    o = enhance(model, st, audio, pad=False)
+    assert o.shape == g["enhanced_nopad"].shape and rms(o, g["enhanced_nopad"]) < RMS_TOL
+    assert rms(enhance(model, st, audio, atten_lim_db=12.0), g["enhanced_atten12"]) < RMS_TOL
+    spec_e, m, lsnr, _ = model(torch.from_numpy(g["spec"]), torch.from_numpy(g["feat_erb"]), torch.from_numpy(g["feat_spec"]))
+    assert rms(spec_e, g["spec_e"]) < 1e-6 and rms(m, g["m"]) < 1e-5 and np.abs(lsnr.numpy() - g["lsnr"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
+def test_si_sdr_known_answer_gpu(name, golden_dir, model_dir):
+    """The reference CI's known answer (df/scripts/test_df.py:44-78, atol = rtol = 1e-4) on the CUDA path."""
+    import ref_harness as rh
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))[name]
+    model, st, _, epoch = init_df(os.path.join(model_dir, name), log_level="ERROR")
+    assert epoch == kat["epoch"]
+    noisy = torch.from_numpy(rh.read_wav(os.path.join(golden_dir, "assets", "noisy_snr0.wav")))
+    clean = rh.read_wav(os.path.join(golden_dir, "assets", "clean_freesound_33711.wav"))
+    out = enhance(model, st, noisy, pad=True)
+    s = rh.si_sdr(clean, out.numpy())
+    assert abs(s - kat["target"]) <= 1e-4 + 1e-4 * abs(kat["target"]), (s, kat["target"])
+
+
+# ------------------------------------------------------------------ enhance(): properties at size ----
+def test_enhance_streams_are_independent_and_batched_equals_single(states):
+    """Per-channel state reset (pyDF/src/lib.rs:56-58): a stream's output does not depend on its
+    batch neighbours or its position in the batch (covers the GRU cluster grouping and the
+    stream-group chunking of dfb_enhance)."""
+    st, _ = states
+    cfg = cfg_of("dfn3")
+    model = DfNet(cfg, random_state_dict(cfg, seed=4), st)
+    audio = synth_audio(40, 48000, seed=31).cuda()
+    full = enhance_device(model, st, audio)
+    perm = torch.randperm(40, generator=torch.Generator().manual_seed(0)).cuda()
+    shuffled = enhance_device(model, st, audio[perm].contiguous())
+    assert torch.equal(full[perm], shuffled) or rms(full[perm].cpu(), shuffled.cpu()) < 1e-7
+    single = enhance_device(model, st, audio[7:8].contiguous())
+    assert rms(full[7:8].cpu(), single.cpu()) < 1e-7
+    torch.cuda.synchronize()
+
+
+def test_enhance_full_size_properties(states):
+    """BASELINE configs[1] shape per stream (10 s) at reduced batch: finite output, exact length,
+    silence in -> silence out, and the oracle on a sample of the streams."""
+    st, _ = states
+    cfg = cfg_of("dfn3")
+    sd = random_state_dict(cfg, seed=5)
+    model = DfNet(cfg, sd, st)
+    audio = synth_audio(16, 480000, seed=41)
+    audio[3] = 0.0
+    out = enhance(model, st, audio)
+    assert out.shape == audio.shape and torch.isfinite(out).all()
+    assert out[3].abs().max() < 1e-6
+    ref = O.enhance(sd, cfg.as_dict(), audio[5:6])
+    assert rms(out[5:6], ref) < RMS_TOL
+
+
+def test_enhance_edge_lengths(states):
+    st, _ = states
+    cfg = cfg_of("dfn3")
+    sd = random_state_dict(cfg, seed=6)
+    model = DfNet(cfg, sd, st)
+    for T in (1, 479, 480, 481, 1000, 4801):
+        audio = synth_audio(2, T, seed=T)
+        out = enhance(model, st, audio)
+        assert out.shape == (2, T)
+        assert rms(out, O.enhance(sd, cfg.as_dict(), audio)) < RMS_TOL
+    with pytest.raises(RuntimeError):
+        enhance(model, st, torch.zeros(1, 100), pad=False)  # shorter than one hop without padding
+
+
+def test_launch_counter_counts_own_kernels(states):
+    st, _ = states
+    n0 = _lib.lib().dfb_kernel_launches()
+    st.analysis(np.zeros((1, 4800), np.float32))
+    assert _lib.lib().dfb_kernel_launches() == n0 + 1

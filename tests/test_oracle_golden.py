@@ -1,0 +1,116 @@
+"""CPU: the oracle (oracle/) against every golden vector / known answer the reference's own tests
+hold for this path."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dfnet_oracle as O
+import libdf_oracle as LO
+
+from deepfilternet_b200.config import load_config
+from deepfilternet_b200.model import find_checkpoint, load_state_dict_file
+
+
+def test_erb_widths_match_checkpoint_buffers(golden_dir):
+    """libDF/src/lib.rs:68-100 must reproduce the band layout stored in the shipped `erb_fb` buffers."""
+    g = json.load(open(os.path.join(golden_dir, "erb_widths.json")))
+    p = g["params"]
+    w = LO.erb_widths(p["sr"], p["fft_size"], p["nb_bands"], p["min_nb_freqs"])
+    for name, ref in g["from_checkpoint_erb_fb"].items():
+        assert w.tolist() == ref, name
+    assert int(w.sum()) == p["fft_size"] // 2 + 1
+
+
+def test_stft_istft_delay():
+    """libDF/src/transforms.rs:618-638 (test_stft_istft_delay): correlation > 1 - 1e-6 after the
+    n_fft - hop delay."""
+    rng = np.random.default_rng(0)
+    st = LO.DF(48000, 960, 480, 32, 2)
+    x = (rng.standard_normal((1, 48000)) * 0.1).astype(np.float32)
+    y = st.synthesis(st.analysis(x))
+    d = 960 - 480
+    a, b = x[0, : -d], y[0, d:]
+    corr = float(np.dot(a, b) / np.sqrt(np.dot(a, a) * np.dot(b, b)))
+    assert corr > 1 - 1e-6
+    assert np.abs(a - b).max() < 1e-5
+
+
+def test_band_gain_exact():
+    """libDF/src/lib.rs:626-652 (test_erb_inout): band gains multiply every bin of the band exactly."""
+    w = LO.erb_widths(24000, 192, 24, 1)
+    rng = np.random.default_rng(1)
+    x = (rng.uniform(-1, 1, (1, 97)) + 1j * rng.uniform(-1, 1, (1, 97))).astype(np.complex64)
+    mask = np.ones((1, 24), dtype=np.float32)
+    mask[0, 3], mask[0, 23] = 0.3, 0.5
+    gains = LO.erb_inv(mask, w)
+    out = x * gains
+    o = 0
+    for b, n in enumerate(w):
+        assert np.array_equal(out[0, o:o + n], x[0, o:o + n] * mask[0, b])
+        o += n
+
+
+def test_erb_identity():
+    """DeepFilterNet/df/modules.py:929-947 (test_erb): libdf.erb(db=False) == |X|^2 @ erb_fb."""
+    rng = np.random.default_rng(2)
+    w = LO.erb_widths(48000, 960, 32, 2)
+    x = (rng.standard_normal((2, 5, 481)) + 1j * rng.standard_normal((2, 5, 481))).astype(np.complex64)
+    fb = np.zeros((481, 32), dtype=np.float32)
+    o = 0
+    for b, n in enumerate(w):
+        fb[o:o + n, b] = 1.0 / n
+        o += n
+    ref = (np.abs(x) ** 2) @ fb
+    assert np.allclose(LO.erb(x, w, db=False), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_unit_norm_matches_exponential_unit_norm():
+    """modules.py:950-967 (test_unit_norm): libdf.unit_norm == ExponentialUnitNorm recursion."""
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((1, 20, 96)) + 1j * rng.standard_normal((1, 20, 96))).astype(np.complex64)
+    a = 0.99
+    out = LO.unit_norm(x, a)
+    s = LO.unit_norm_init(96)[0].astype(np.float32)
+    for t in range(20):
+        s = np.abs(x[0, t]).astype(np.float32) * np.float32(1 - a) + s * np.float32(a)
+        assert np.allclose(out[0, t], x[0, t] / np.sqrt(s), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
+def test_dfnet_oracle_matches_reference_modules(name, golden_dir, model_dir):
+    """tests/golden/dfnet_<model>.npz were produced by the reference's own DfNet / enhance()."""
+    g = np.load(os.path.join(golden_dir, f"dfnet_{name}.npz"))
+    cfg = load_config(os.path.join(model_dir, name, "config.ini"), env={})
+    sd = load_state_dict_file(find_checkpoint(os.path.join(model_dir, name, "checkpoints"))[0])
+    audio = torch.from_numpy(g["audio"])
+    out, aux = O.enhance(sd, cfg.as_dict(), audio, pad=True, return_all=True)
+    assert np.abs(aux["spec"].numpy() - g["spec"]).max() < 1e-7
+    assert np.abs(aux["erb_feat"].numpy() - g["feat_erb"]).max() < 1e-6
+    assert np.abs(aux["spec_feat"].numpy() - g["feat_spec"]).max() < 1e-6
+    assert np.abs(aux["m"].numpy() - g["m"]).max() < 1e-5
+    assert np.abs(aux["lsnr"].numpy() - g["lsnr"]).max() < 1e-3
+    assert np.abs(aux["spec_e"].numpy() - g["spec_e"]).max() < 1e-6
+    assert float(np.sqrt(((out.numpy() - g["enhanced"]) ** 2).mean())) < 1e-6
+    o2 = O.enhance(sd, cfg.as_dict(), audio, pad=False)
+    assert o2.shape == g["enhanced_nopad"].shape
+    assert float(np.sqrt(((o2.numpy() - g["enhanced_nopad"]) ** 2).mean())) < 1e-6
+    o3 = O.enhance(sd, cfg.as_dict(), audio, pad=True, atten_lim_db=12.0)
+    assert float(np.sqrt(((o3.numpy() - g["enhanced_atten12"]) ** 2).mean())) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
+def test_si_sdr_known_answer(name, golden_dir, model_dir):
+    """DeepFilterNet/df/scripts/test_df.py:44-78: SI-SDR of enhance(noisy_snr0) vs clean, atol=rtol=1e-4."""
+    import ref_harness as rh
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))[name]
+    cfg = load_config(os.path.join(model_dir, name, "config.ini"), env={})
+    sd = load_state_dict_file(find_checkpoint(os.path.join(model_dir, name, "checkpoints"))[0])
+    noisy = torch.from_numpy(rh.read_wav(os.path.join(golden_dir, "assets", "noisy_snr0.wav")))
+    clean = rh.read_wav(os.path.join(golden_dir, "assets", "clean_freesound_33711.wav"))
+    assert noisy.shape[1] == kat["n_samples"]
+    out = O.enhance(sd, cfg.as_dict(), noisy, pad=True)
+    s = rh.si_sdr(clean, out.numpy())
+    assert abs(s - kat["target"]) <= 1e-4 + 1e-4 * abs(kat["target"]), (s, kat["target"])
