@@ -127,8 +127,26 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def cpu_reference_run(cfg, sd, streams: int, steps: int, warmup: int, threads: int):
-    """The reference's CPU path restated (oracle/): C DSP + torch-CPU DNN, all host threads."""
+def host_threads() -> int:
+    """Host cores this process may actually use (affinity mask and cgroup CPU quota respected)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def cpu_reference_run(cfg, sd, steps: int, warmup: int, threads: int, budget_s: float):
+    """The reference's CPU path restated (oracle/): C DSP + torch-CPU DNN with `threads` host
+    threads.  The per-step sample (whole 10 s streams of the same synthetic workload) is sized from
+    a 1-stream probe so that the run stays near `budget_s` seconds."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dfnet_oracle
@@ -136,15 +154,21 @@ def cpu_reference_run(cfg, sd, streams: int, steps: int, warmup: int, threads: i
     from tests_common import synth_audio
     libdf_oracle.build()
     torch.set_num_threads(threads)
-    audio = synth_audio(streams, SR * SECONDS, seed=1234)
     cfgd = cfg.as_dict()
+    probe = synth_audio(1, SR * SECONDS, seed=1234)
+    dfnet_oracle.enhance(sd, cfgd, probe[:, : SR * 2])
+    t0 = time.perf_counter()
+    dfnet_oracle.enhance(sd, cfgd, probe)
+    t_probe = time.perf_counter() - t0
+    streams = int(max(1, min(32, budget_s / max(steps + warmup, 1) / max(t_probe, 1e-3))))
+    audio = synth_audio(streams, SR * SECONDS, seed=1234)
     for _ in range(warmup):
-        dfnet_oracle.enhance(sd, cfgd, audio[:1, : SR * 2])
+        dfnet_oracle.enhance(sd, cfgd, audio)
     t0 = time.perf_counter()
     for _ in range(steps):
         dfnet_oracle.enhance(sd, cfgd, audio)
     dt = time.perf_counter() - t0
-    return streams * SECONDS * steps / dt, dt / steps
+    return streams * SECONDS * steps / dt, dt / steps, streams
 
 
 def main():
@@ -173,13 +197,12 @@ def main():
               "global_streams": a.streams * n_gpus, "parallelism": f"stream-sharded x{n_gpus}, no collective",
               "weights": weights_kind,
               "l2": "inputs larger than L2 (batch audio 245 MB + >9 GB of activations per step)"}
-    threads = os.cpu_count() or 1
+    threads = host_threads()
 
     if a.impl == "reference":
         if rank != 0:
             return
-        sample_streams = 16
-        v, s_per_step = cpu_reference_run(cfg, sd, sample_streams, a.steps, min(a.warmup, 1), threads)
+        v, s_per_step, sample_streams = cpu_reference_run(cfg, sd, a.steps, min(a.warmup, 1), threads, budget_s=90.0)
         line = {"impl": "reference", "metric": "48kHz audio-sec/sec (batched enhance)", "value": v,
                 "unit": "audio-s/s", "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -306,9 +329,9 @@ def main():
     torch.cuda.synchronize()
     line["rtf_batch1"] = (ev0.elapsed_time(ev1) / 5 / 1e3) / a.seconds
     if n_gpus == 1 and not a.no_cpu_baseline:
-        v, s_step = cpu_reference_run(cfg, sd, 16, 2, 1, threads)
+        v, s_step, ns = cpu_reference_run(cfg, sd, 2, 0, threads, budget_s=25.0)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                "sample": f"2 steps of 16 streams x {a.seconds} s (CPU oracle port: C libDF restatement "
+                                "sample": f"2 steps of {ns} streams x {a.seconds} s (CPU oracle port: C libDF restatement "
                                           f"+ torch-CPU DfNet, {threads} threads), {s_step:.2f} s/step"}
     print(json.dumps(line))
     if world > 1:

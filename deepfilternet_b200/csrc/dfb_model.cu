@@ -904,8 +904,9 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             return rc;
         static bool attr_done = false;
         int smem = (kMaskWarps * 2 * (E + 2) * kMaskLd + c.conv_kt * 3 * kCh) * 4;
-        if (!attr_done) {
-            DFB_CUDA(cudaFuncSetAttribute(k_mask_out, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (!attr_done) {  // sized for the largest supported configuration (nb_erb 64, kt 2)
+            DFB_CUDA(cudaFuncSetAttribute(k_mask_out, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (kMaskWarps * 2 * (64 + 2) * kMaskLd + 2 * 3 * kCh) * 4));
             attr_done = true;
         }
         int per_cta = kMaskWarps * kMaskChunk;
