@@ -319,10 +319,12 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
 //   r = s(xr + Whr h + bhr), z = s(xz + Whz h + bhz), n = tanh(xn + r (Whn h + bhn)), h' = (1-z) n + z h
 // xproj = W_ih x + b_ih comes from k_grouped_linear.  One thread-block CLUSTER owns a group of Bc
 // streams for the whole sequence: CTA `rank` keeps the W_hh rows of its U = H / C hidden units
-// (3U rows x H) in REGISTERS (384 threads x 128 weights), the hidden state of the group lives in
-// shared memory of every CTA and the new slice is broadcast through DSMEM each step; one cluster
-// barrier per time step.  H = 256: C = 4, U = 64, 2 lanes per row;  H = 512: C = 16, U = 32, 4 lanes.
-constexpr int kGruThreads = 384, kGruWPerThread = 128, kGruSB = 4, kGruMaxBc = 16;
+// (3U rows x H) in REGISTERS: 384 threads, each an 8-row x 16-k tile (128 weights), so a thread
+// reads only 16 h values per stream and step from shared memory; the H/16 lanes that share a row
+// group combine their partial sums with a shuffle reduce-scatter.  The hidden state of the group
+// lives in shared memory of every CTA; the new slice is broadcast through DSMEM each step; one
+// cluster barrier per time step.  H = 256: C = 4, U = 64;  H = 512: C = 16, U = 32.
+constexpr int kGruThreads = 384, kGruRT = 8, kGruKT = 16, kGruSB = 4, kGruMaxBc = 16;
 
 struct GruParams {
     const float *xproj;  // [B,T,3H]
@@ -336,10 +338,12 @@ struct GruParams {
 template <int H, int C>
 __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
     constexpr int U = H / C;                       // hidden units per CTA
-    constexpr int KS = kGruThreads / (3 * U);      // lanes per weight row
-    constexpr int KR = H / KS;                     // k-range per lane (= 128)
-    static_assert(KR == kGruWPerThread, "layout");
-    constexpr int HP = H + 4 * KS;                 // padded h row (bank spread between k-parts)
+    constexpr int LPR = H / kGruKT;                // lanes sharing one row group (16 or 32)
+    constexpr int NRG = 3 * U / kGruRT;            // row groups per CTA
+    static_assert(NRG * LPR == kGruThreads, "layout");
+    constexpr int V = kGruRT * kGruSB;             // partial sums per thread and stream chunk (32)
+    constexpr int VF = V / LPR;                    // fully reduced values a lane ends up with
+    constexpr int HP = H + 4;                      // padded h row
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int group = blockIdx.x / C;
@@ -349,27 +353,43 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
     float (*s_h)[kGruMaxBc][HP] = reinterpret_cast<float (*)[kGruMaxBc][HP]>(gru_smem);            // [2][Bc][HP]
     float (*s_pre)[kGruMaxBc + 1] = reinterpret_cast<float (*)[kGruMaxBc + 1]>(gru_smem + 2 * kGruMaxBc * HP);  // [3U]
     const int tid = threadIdx.x;
-    const int row = tid / KS, kp = tid % KS;       // row in [0, 3U): gate = row / U, unit = row % U
-    const int gate = row / U, unit = row % U;
-    // weights -> registers
-    float w[kGruWPerThread];
-    {
-        const float *src = p.whh + ((int64_t)gate * H + rank * U + unit) * H + kp * KR;
+    const int rg = tid / LPR, kl = tid % LPR;      // row group, k slice [16 kl, 16 kl + 16)
+    // weights -> registers: w[r][k] = Whh[global_row(8 rg + r)][16 kl + k]
+    float w[kGruRT][kGruKT];
 #pragma unroll
-        for (int i = 0; i < kGruWPerThread; i += 4) {
-            float4 v = *reinterpret_cast<const float4 *>(src + i);
-            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+    for (int r = 0; r < kGruRT; r++) {
+        const int row = rg * kGruRT + r;           // row in [0, 3U): gate = row / U, unit = row % U
+        const float *src = p.whh + ((int64_t)(row / U) * H + rank * U + (row % U)) * H + kl * kGruKT;
+#pragma unroll
+        for (int k = 0; k < kGruKT; k += 4) {
+            float4 v = *reinterpret_cast<const float4 *>(src + k);
+            w[r][k] = v.x; w[r][k + 1] = v.y; w[r][k + 2] = v.z; w[r][k + 3] = v.w;
         }
     }
+    // index of the first fully reduced value this lane owns after the reduce-scatter
+    int vbase = 0;
+#pragma unroll
+    for (int bit = LPR / 2, n = V / 2; bit >= 1 && n >= 1; bit >>= 1, n >>= 1)
+        if (kl & bit) vbase += n;
     for (int i = tid; i < 2 * kGruMaxBc * HP; i += kGruThreads) gru_smem[i] = 0.f;  // h0 = 0
+    // gate-phase items (s, u): this thread's slots
+    constexpr int kItems = (kGruMaxBc * U + kGruThreads - 1) / kGruThreads;
+    float bh[kItems][3];
+#pragma unroll
+    for (int it = 0; it < kItems; it++) {
+        int item = tid + it * kGruThreads;
+        int u = item % U;
+        bh[it][0] = p.bhh[rank * U + u]; bh[it][1] = p.bhh[H + rank * U + u]; bh[it][2] = p.bhh[2 * H + rank * U + u];
+    }
     cluster.sync();
     int cur = 0;
     for (int t = 0; t < p.T; t++) {
         // prefetch the input projections of this step for the gate phase (independent of h)
-        float xr[(kGruMaxBc * 64 + kGruThreads - 1) / kGruThreads][3];
-        {
-            int it = 0;
-            for (int item = tid; item < nb * U; item += kGruThreads, it++) {
+        float xr[kItems][3];
+#pragma unroll
+        for (int it = 0; it < kItems; it++) {
+            int item = tid + it * kGruThreads;
+            if (item < nb * U) {
                 int s = item / U, u = item - s * U;
                 const float *xp = p.xproj + ((int64_t)(b0 + s) * p.T + t) * (3 * H) + rank * U + u;
                 xr[it][0] = xp[0]; xr[it][1] = xp[H]; xr[it][2] = xp[2 * H];
@@ -377,42 +397,62 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
         }
         // matvec: pre[row][s] = sum_k W[row][k] h[s][k]
         for (int sc = 0; sc < nb; sc += kGruSB) {
-            float acc[kGruSB];
+            float acc[V];
 #pragma unroll
-            for (int s = 0; s < kGruSB; s++) acc[s] = 0.f;
-            const float *hb = &s_h[cur][sc][kp * (KR + 4)];
+            for (int i = 0; i < V; i++) acc[i] = 0.f;
 #pragma unroll
-            for (int k = 0; k < KR; k += 4) {
+            for (int s = 0; s < kGruSB; s++) {
+                // h is stored permuted (hpos) so that the LPR lanes read consecutive float4s
+                const float *hb = &s_h[cur][sc + s][kl * 4];
 #pragma unroll
-                for (int s = 0; s < kGruSB; s++) {
-                    float4 hv = *reinterpret_cast<const float4 *>(hb + s * HP + k);
-                    acc[s] += w[k] * hv.x; acc[s] += w[k + 1] * hv.y; acc[s] += w[k + 2] * hv.z; acc[s] += w[k + 3] * hv.w;
+                for (int k = 0; k < kGruKT; k += 4) {
+                    float4 hv = *reinterpret_cast<const float4 *>(hb + (k / 4) * LPR * 4);
+#pragma unroll
+                    for (int r = 0; r < kGruRT; r++) {
+                        float a = acc[r * kGruSB + s];
+                        a += w[r][k] * hv.x; a += w[r][k + 1] * hv.y; a += w[r][k + 2] * hv.z; a += w[r][k + 3] * hv.w;
+                        acc[r * kGruSB + s] = a;
+                    }
+                }
+            }
+            // reduce-scatter over the LPR lanes of this row group
+#pragma unroll
+            for (int bit = LPR / 2, n = V / 2; bit >= 1 && n >= 1; bit >>= 1, n >>= 1) {
+                const bool up = (kl & bit) != 0;
+#pragma unroll
+                for (int i = 0; i < V / 2; i++) {
+                    if (i < n) {
+                        float send = up ? acc[i] : acc[i + n];
+                        float keep = up ? acc[i + n] : acc[i];
+                        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                    }
                 }
             }
 #pragma unroll
-            for (int s = 0; s < kGruSB; s++) {
-#pragma unroll
-                for (int o = 1; o < KS; o <<= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
-                if (kp == 0 && sc + s < nb) s_pre[row][sc + s] = acc[s];
+            for (int i = 0; i < VF; i++) {
+                int v = vbase + i;                      // v = r * kGruSB + s
+                int r = v / kGruSB, s = v % kGruSB;
+                if (sc + s < nb) s_pre[rg * kGruRT + r][sc + s] = acc[i];
             }
         }
         __syncthreads();
         // gates
-        {
-            int it = 0;
-            for (int item = tid; item < nb * U; item += kGruThreads, it++) {
+#pragma unroll
+        for (int it = 0; it < kItems; it++) {
+            int item = tid + it * kGruThreads;
+            if (item < nb * U) {
                 int s = item / U, u = item - s * U;
                 int gu = rank * U + u;
-                float br = p.bhh[gu], bz = p.bhh[H + gu], bn = p.bhh[2 * H + gu];
-                float r = sigmoidf_(xr[it][0] + s_pre[u][s] + br);
-                float z = sigmoidf_(xr[it][1] + s_pre[U + u][s] + bz);
-                float n = tanhf(xr[it][2] + r * (s_pre[2 * U + u][s] + bn));
-                float hprev = s_h[cur][s][(gu / KR) * (KR + 4) + (gu % KR)];
+                float r = sigmoidf_(xr[it][0] + s_pre[u][s] + bh[it][0]);
+                float z = sigmoidf_(xr[it][1] + s_pre[U + u][s] + bh[it][1]);
+                float n = tanhf(xr[it][2] + r * (s_pre[2 * U + u][s] + bh[it][2]));
+                const int hp = (((gu % kGruKT) / 4) * LPR + gu / kGruKT) * 4 + (gu & 3);  // hpos(gu)
+                float hprev = s_h[cur][s][hp];
                 float hn = (1.f - z) * n + z * hprev;
                 int64_t o = ((int64_t)(b0 + s) * p.T + t) * H + gu;
                 p.hout[o] = p.res ? hn + p.res[o] : hn;
                 // broadcast the new value to every CTA of the cluster (DSMEM)
-                float *dst_local = &s_h[cur ^ 1][s][(gu / KR) * (KR + 4) + (gu % KR)];
+                float *dst_local = &s_h[cur ^ 1][s][hp];
 #pragma unroll
                 for (int c = 0; c < C; c++) *cluster.map_shared_rank(dst_local, c) = hn;
             }
@@ -481,54 +521,72 @@ k_mask_out(const float *__restrict__ e0, const float *__restrict__ d1, const flo
 // ------------------------------------------------- DF pathway conv + coefficient sum ----
 // coefs[b,t,f,:] (already holding tanh(df_out(c))) += relu( pw( conv_t(c0) ) + b ):
 // df_convp = grouped (2) temporal conv C -> 2*O with kernel (ktp,1), 1x1 conv, BN, ReLU
-// (deepfilternet3.py:293-295, 328-330).  One thread per (b,t,f) row.
-constexpr int kMaxO2 = 16;
-template <int ORDER>
-__global__ void __launch_bounds__(128)
+// (deepfilternet3.py:293-295, 328-330).  One thread owns bin f and a run of kCpR consecutive
+// frames: every c0 row it loads feeds up to ktp output frames, so c0 is read (kCpR+ktp-1)/kCpR
+// times instead of ktp times; the taps of the current channel quad are register resident.
+constexpr int kMaxO2 = 16, kCpR = 4, kCpRuns = 2;
+template <int ORDER, int KTP>
+__global__ void __launch_bounds__(192, 2)
 k_df_convp(const float *__restrict__ c0 /*[B,T,Fd,64]*/, const float *__restrict__ w1 /*[ktp][O2][32]*/,
            const float *__restrict__ w2 /*[O2][O2]*/, const float *__restrict__ bias, float *__restrict__ coefs,
-           int64_t rows, int T, int Fd, int ktp) {
-    constexpr int O2 = 2 * ORDER;
+           int T, int Fd) {
+    constexpr int O2 = 2 * ORDER, CG = kCh / 2;
     extern __shared__ __align__(16) float sw[];  // w1 | w2 | bias
-    const int n1 = ktp * O2 * (kCh / 2);
+    constexpr int n1 = KTP * O2 * CG;
     for (int i = threadIdx.x; i < n1; i += blockDim.x) sw[i] = w1[i];
     for (int i = threadIdx.x; i < O2 * O2; i += blockDim.x) sw[n1 + i] = w2[i];
     for (int i = threadIdx.x; i < O2; i += blockDim.x) sw[n1 + O2 * O2 + i] = bias[i];
     __syncthreads();
-    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows) return;
-    const int f = (int)(row % Fd);
-    const int64_t bt = row / Fd;
-    const int t = (int)(bt % T);
-    float acc[O2];
+    const int f = threadIdx.x % Fd, run = threadIdx.x / Fd;
+    const int b = blockIdx.y;
+    const int t0 = (blockIdx.x * kCpRuns + run) * kCpR;
+    if (t0 >= T) return;
+    float acc[kCpR][O2];
 #pragma unroll
-    for (int o = 0; o < O2; o++) acc[o] = 0.f;
-    for (int dt = 0; dt < ktp; dt++) {
-        int tp = t - (ktp - 1) + dt;
-        if (tp < 0) continue;
-        const float *src = c0 + ((bt - t + tp) * Fd + f) * kCh;
-        const float *wdt = sw + dt * O2 * (kCh / 2);
+    for (int r = 0; r < kCpR; r++)
 #pragma unroll
-        for (int g = 0; g < 2; g++) {
+        for (int o = 0; o < O2; o++) acc[r][o] = 0.f;
+    const float *base = c0 + ((int64_t)b * T * Fd + f) * kCh;
 #pragma unroll
-            for (int c4 = 0; c4 < kCh / 2; c4 += 4) {
-                float4 x = *reinterpret_cast<const float4 *>(src + g * (kCh / 2) + c4);
+    for (int g = 0; g < 2; g++) {
+        for (int c4 = 0; c4 < CG; c4 += 4) {
+            float4 wv[KTP][ORDER];
 #pragma unroll
-                for (int o = 0; o < ORDER; o++) {
-                    float4 ww = *reinterpret_cast<const float4 *>(wdt + (g * ORDER + o) * (kCh / 2) + c4);
-                    acc[g * ORDER + o] += x.x * ww.x + x.y * ww.y + x.z * ww.z + x.w * ww.w;
+            for (int dt = 0; dt < KTP; dt++)
+#pragma unroll
+                for (int o = 0; o < ORDER; o++)
+                    wv[dt][o] = *reinterpret_cast<const float4 *>(sw + (dt * O2 + g * ORDER + o) * CG + c4);
+#pragma unroll
+            for (int j = 0; j < kCpR + KTP - 1; j++) {
+                const int tp = t0 - (KTP - 1) + j;
+                if (tp < 0 || tp >= T) continue;
+                const float4 x = *reinterpret_cast<const float4 *>(base + (int64_t)tp * Fd * kCh + g * CG + c4);
+#pragma unroll
+                for (int dt = 0; dt < KTP; dt++) {
+                    const int r = j - dt;  // output frame t0 + r uses tap dt of input frame t0 + r - (KTP-1) + dt
+                    if (r < 0 || r >= kCpR) continue;
+#pragma unroll
+                    for (int o = 0; o < ORDER; o++) {
+                        const float4 ww = wv[dt][o];
+                        acc[r][g * ORDER + o] += x.x * ww.x + x.y * ww.y + x.z * ww.z + x.w * ww.w;
+                    }
                 }
             }
         }
     }
     const float *s2 = sw + n1, *sb = sw + n1 + O2 * O2;
-    float *dst = coefs + row * O2;
 #pragma unroll
-    for (int n = 0; n < O2; n++) {
-        float v = sb[n];
+    for (int r = 0; r < kCpR; r++) {
+        const int t = t0 + r;
+        if (t >= T) break;
+        float *dst = coefs + (((int64_t)b * T + t) * Fd + f) * O2;
 #pragma unroll
-        for (int k = 0; k < O2; k++) v += acc[k] * s2[k * O2 + n];
-        dst[n] += fmaxf(v, 0.f);
+        for (int n = 0; n < O2; n++) {
+            float v = sb[n];
+#pragma unroll
+            for (int k = 0; k < O2; k++) v += acc[r][k] * s2[k * O2 + n];
+            dst[n] += fmaxf(v, 0.f);
+        }
     }
 }
 
@@ -547,6 +605,7 @@ struct dfb_model {
     std::map<std::string, std::pair<const float *, int64_t>> dbg;  // activations of the last forward
     std::vector<GruLayerW> enc_gru, erb_gru, df_gru;
     float *slab = nullptr;
+    int precision = 0;  // 0: fp32 FFMA everywhere; 1: TF32 tensor cores (tcgen05) for the dense contractions
     Arena arena;
     cudaStream_t stream = nullptr;
     const float *get(const std::string &n) const {
@@ -621,6 +680,12 @@ extern "C" void dfb_model_free(dfb_model *m) {
     delete m;
 }
 
+extern "C" int dfb_model_set_precision(dfb_model *m, int mode) {
+    if (!m || mode < 0 || mode > 1) return fail(DFB_ERR_INVALID, "precision mode must be 0 (fp32) or 1 (tf32)");
+    m->precision = mode;
+    return DFB_OK;
+}
+
 extern "C" int64_t dfb_model_debug_fetch(dfb_model *m, const char *name, float *h_out, int64_t max_numel) {
     if (!m || !name || !h_out) return fail(DFB_ERR_INVALID, "null argument");
     auto it = m->dbg.find(name);
@@ -652,8 +717,7 @@ int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const fl
 
 template <int H, int C>
 int launch_gru_t(cudaStream_t s, const GruParams &p, int ngroups) {
-    constexpr int KS = kGruThreads / (3 * (H / C));
-    constexpr int smem = (2 * kGruMaxBc * (H + 4 * KS) + 3 * (H / C) * (kGruMaxBc + 1)) * 4;
+    constexpr int smem = (2 * kGruMaxBc * (H + 4) + 3 * (H / C) * (kGruMaxBc + 1)) * 4;
     static bool attr_done = false;
     if (!attr_done) {
         if (C > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru<H, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -698,7 +762,13 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         if ((rc = need(m, (base + ".w_hh").c_str(), (int64_t)3 * H * H, &w_hh))) return rc;
         if ((rc = need(m, (base + ".b_ih").c_str(), 3 * H, &b_ih))) return rc;
         if ((rc = need(m, (base + ".b_hh").c_str(), 3 * H, &b_hh))) return rc;
-        rc = run_gl(s, cur_in, cur_dim, w_ih_t, b_ih, nullptr, 0, xproj, 3 * H, M, 1, cur_dim, 3 * H, ACT_NONE);
+        if (m->precision == 1) {
+            const float *w_ih;
+            if ((rc = need(m, (base + ".w_ih").c_str(), (int64_t)3 * H * cur_dim, &w_ih))) return rc;
+            rc = launch_gemm_tf32(s, cur_in, cur_dim, w_ih, b_ih, xproj, 3 * H, M, 3 * H, cur_dim, ACT_NONE);
+        } else {
+            rc = run_gl(s, cur_in, cur_dim, w_ih_t, b_ih, nullptr, 0, xproj, 3 * H, M, 1, cur_dim, 3 * H, ACT_NONE);
+        }
         if (rc) return rc;
         float *dst = (l == layers - 1) ? y : tmp_h;
         GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, 0};
@@ -939,11 +1009,13 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
             (rc = need(m, "df_dec.df_convp.w2", O2 * O2, &w2)) || (rc = need(m, "df_dec.df_convp.b", O2, &bb)))
             return rc;
-        int64_t rows = M * Fd;
         int smem = (c.df_pathway_kt * O2 * (kCh / 2) + O2 * O2 + O2) * 4;
-        if (c.df_order != 5) return fail(DFB_ERR_UNSUPPORTED, "df_order %d (built kernels: 5)", c.df_order);
+        if (c.df_order != 5 || c.df_pathway_kt != 5 || Fd * kCpRuns > 192)
+            return fail(DFB_ERR_UNSUPPORTED, "df_order %d / df_pathway_kernel_size_t %d (built kernels: 5, 5)", c.df_order,
+                        c.df_pathway_kt);
+        dim3 grid((unsigned)((T + kCpR * kCpRuns - 1) / (kCpR * kCpRuns)), (unsigned)B);
         DFB_PROF("k_df_convp", s);
-        k_df_convp<5><<<(unsigned)((rows + 127) / 128), 128, smem, s>>>(f.c0, w1, w2, bb, d_coefs, rows, T, Fd, c.df_pathway_kt);
+        k_df_convp<5, 5><<<grid, Fd * kCpRuns, smem, s>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
         DFB_LAUNCH_CHECK();
     }
     return DFB_OK;

@@ -1,0 +1,260 @@
+// dfb_tc.cu -- 5th-generation tensor-core (tcgen05) kernels for the dense contractions of the path.
+//
+//   k_gemm_tf32:  Y[M,N] = act(X[M,K] . W[N,K]^T + bias)          (GRU input projections W_ih x + b_ih,
+//                 torch.nn.GRU inside SqueezedGRU[_S], DeepFilterNet/df/modules.py:684,723)
+//
+// Structure (one CTA per 128 x BN output tile, 4 warps):
+//   warp 0 / lane 0 : TMA producer  -- cp.async.bulk.tensor (128B swizzle) of the X and W k-blocks into
+//                     a 4-stage shared-memory ring, completion on "full" mbarriers
+//   warp 1 / lane 0 : MMA issuer    -- tcgen05.mma.cta_group::1.kind::tf32, 128 x BN x 8 per instruction,
+//                     accumulator in TMEM; tcgen05.commit releases the ring slot / signals the epilogue
+//   warps 0-3       : epilogue      -- tcgen05.ld 32x32b (one TMEM lane = one output row per thread),
+//                     + bias, activation, 128-byte row segments to global memory
+// Operands are fp32 in HBM; the tensor maps use the TFLOAT32 element type so the TMA engine hands the
+// tensor core tf32 values; accumulation is fp32.  Parity of the whole path with TF32 contractions is
+// checked end to end (tests/test_gpu_parity.py, RMS <= 1e-4 vs the fp32 oracle).
+#include <cuda.h>
+
+#include "dfb_common.cuh"
+
+namespace dfb {
+
+// ----------------------------------------------------------------------------- PTX helpers ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle, rows of exactly 128 bytes
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 | layout << 61)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;               // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;     // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;               // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major (InstrDescriptor)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tc_act(float x, int act) {
+    switch (act) {
+        case 1: return fmaxf(x, 0.f);
+        case 2: return tanhf(x);
+        case 3: return 1.f / (1.f + expf(-x));
+        default: return x;
+    }
+}
+
+// ---------------------------------------------------------------------------- GEMM kernel ----
+constexpr int kTcBM = 128, kTcBK = 32, kTcStages = 4;
+
+template <int BN>
+struct TcSmem {
+    alignas(1024) float a[kTcStages][kTcBM * kTcBK];
+    alignas(1024) float b[kTcStages][BN * kTcBK];
+    alignas(8) uint64_t full[kTcStages];
+    uint64_t empty[kTcStages];
+    uint64_t tmem_full;
+    uint32_t tmem_base;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(128)
+k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const float *__restrict__ bias, float *__restrict__ Y, int64_t ldy, int M, int N, int K, int act) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    TcSmem<BN> &sm = *reinterpret_cast<TcSmem<BN> *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * BN;
+    const int nkb = K / kTcBK;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kTcStages; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        mbar_init(&sm.tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    if (threadIdx.x == 0) {
+        // ===== TMA producer
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % kTcStages, it = kb / kTcStages;
+            if (it > 0) mbar_wait(&sm.empty[s], (it - 1) & 1);
+            mbar_expect_tx(&sm.full[s], (kTcBM + BN) * kTcBK * 4);
+            tma_load_2d(sm.a[s], &tmA, kb * kTcBK, m0, &sm.full[s]);
+            tma_load_2d(sm.b[s], &tmB, kb * kTcBK, n0, &sm.full[s]);
+        }
+    } else if (threadIdx.x == 32) {
+        // ===== MMA issuer
+        constexpr uint32_t idesc = umma_idesc_tf32(kTcBM, BN);
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % kTcStages, it = kb / kTcStages;
+            mbar_wait(&sm.full[s], it & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
+#pragma unroll
+            for (int k = 0; k < kTcBK / 8; k++) {
+                umma_tf32(tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+            }
+            umma_commit(&sm.empty[s]);  // frees this ring slot once the MMAs above have read it
+        }
+        umma_commit(&sm.tmem_full);
+    }
+    __syncwarp();
+    // ===== epilogue: all 4 warps, warp w owns TMEM lanes [32 w, 32 w + 32) = rows m0 + 32 w + lane
+    mbar_wait(&sm.tmem_full, 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+        if (m < M) {
+            float *dst = Y + (int64_t)m * ldy + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                o.x = tc_act(v[j] + (bias ? bias[n0 + c + j] : 0.f), act);
+                o.y = tc_act(v[j + 1] + (bias ? bias[n0 + c + j + 1] : 0.f), act);
+                o.z = tc_act(v[j + 2] + (bias ? bias[n0 + c + j + 2] : 0.f), act);
+                o.w = tc_act(v[j + 3] + (bias ? bias[n0 + c + j + 3] : 0.f), act);
+                *reinterpret_cast<float4 *>(dst + j) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, BN);
+}
+
+// ------------------------------------------------------------------------------- host side ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows][cols] (row pitch ld floats), box = [box_rows][32 floats], 128-byte swizzle
+static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void *)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return DFB_OK;
+}
+
+// Y[M,N] = act(X[M,K] . W[N,K]^T + bias); X row pitch ldx, W row pitch K, Y row pitch ldy.
+int launch_gemm_tf32(cudaStream_t s, const float *x, int64_t ldx, const float *w_nk, const float *bias, float *y,
+                     int64_t ldy, int64_t M, int N, int K, int act) {
+    constexpr int BN = 128;
+    if (N % BN || K % kTcBK || (ldx % 4) || (ldy % 4) || M <= 0 || ((uintptr_t)x & 15) || ((uintptr_t)w_nk & 15))
+        return fail(DFB_ERR_UNSUPPORTED, "tf32 GEMM shape M=%lld N=%d K=%d", (long long)M, N, K);
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, x, M, K, ldx, kTcBM)) || (rc = make_map(&mb, w_nk, N, K, K, BN))) return rc;
+    static bool attr_done = false;
+    const int smem = (int)sizeof(TcSmem<BN>) + 1024;
+    if (!attr_done) {
+        DFB_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((M + kTcBM - 1) / kTcBM), (unsigned)(N / BN));
+    DFB_PROF("k_gemm_tf32[gru_proj]", s);
+    k_gemm_tf32<BN><<<grid, 128, smem, s>>>(ma, mb, bias, y, ldy, (int)M, N, K, act);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+}
+
+}  // namespace dfb

@@ -105,6 +105,12 @@ class DfNet(nn.Module):
                                           widths.ctypes.data_as(C.POINTER(C.c_int64))))
         self._h = h
         self._derived = derived
+        self.set_precision(os.environ.get("DFB_PRECISION", "fp32"))
+
+    def set_precision(self, mode: str) -> None:
+        """'fp32': IEEE fp32 FFMA everywhere; 'tf32': tcgen05 TF32 tensor cores for the dense contractions."""
+        check(_lib.lib().dfb_model_set_precision(self._h, {"fp32": 0, "tf32": 1}[mode]))
+        self.precision = mode
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -151,6 +151,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
         n = gru_layers(sd, src)
         for l in range(n):
             out[f"{dst}.l{l}.w_ih_t"] = f32(_np(sd[f"{src}.weight_ih_l{l}"]).T)
+            out[f"{dst}.l{l}.w_ih"] = f32(_np(sd[f"{src}.weight_ih_l{l}"]))  # [3H][I]: B operand of the tcgen05 GEMM
             out[f"{dst}.l{l}.w_hh"] = f32(_np(sd[f"{src}.weight_hh_l{l}"]))
             out[f"{dst}.l{l}.b_ih"] = f32(_np(sd[f"{src}.bias_ih_l{l}"]))
             out[f"{dst}.l{l}.b_hh"] = f32(_np(sd[f"{src}.bias_hh_l{l}"]))
