@@ -21,12 +21,12 @@
 #include <string>
 
 #include "dfb_common.cuh"
+#include "dfb_dwpw.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace dfb {
 
-constexpr int kCh = 64;  // conv_ch of every shipped model
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3 };
 
@@ -97,21 +97,6 @@ k_erb_conv0(const float *__restrict__ fe, const float *__restrict__ w /*[kt][3][
 // (out[2j] = w1 x[j]; out[2j+1] = w2 x[j] + w0 x[j+1]; ConvTranspose2d padding 1, output_padding 1),
 // DF0 the grouped 2 -> 64 input conv on the complex features (with look-ahead shift).
 // Tile: NF frames x Fout rows (R = NF * Fout <= 128, multiple of 4); thread tile 4 rows x 8 cols.
-enum DwMode { DW_S1 = 0, DW_S2 = 1, DW_T2 = 2, DW_DF0 = 3 };
-constexpr int kLdA = kCh + 4;  // padded row stride of the A tile (floats)
-
-struct DwPwParams {
-    const float *in;      // [B,T,Fin,64]  (DF0: feat_spec [B,T,Fin,2])
-    const float *path;    // optional [B,T,Fin,64]
-    const float *ps, *pb; // pathway scale / bias [64]
-    const float *dw;      // [kt][3][64]
-    const float *pw;      // [64][64]
-    const float *bias;    // [64]
-    float *out;           // [B,T,Fout,64]
-    int64_t in_fs, path_fs, out_fs;  // frame strides (floats)
-    int T, Fin, Fout, kt, NF, lookahead;
-};
-
 template <int MODE>
 __global__ void __launch_bounds__(256) k_dwpw(DwPwParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -127,60 +112,13 @@ __global__ void __launch_bounds__(256) k_dwpw(DwPwParams p) {
     // ---- prologue: thread = (row slot, channel quad)
     {
         const int cq = tid & 15;
-        float4 wd[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) wd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = 0; i < p.kt * 3; i++)
-            wd[i + (3 - p.kt) * 3] = *reinterpret_cast<const float4 *>(p.dw + i * kCh + cq * 4);
-        float4 ps4 = make_float4(0.f, 0.f, 0.f, 0.f), pb4 = ps4;
-        if (p.path) {
-            ps4 = *reinterpret_cast<const float4 *>(p.ps + cq * 4);
-            pb4 = *reinterpret_cast<const float4 *>(p.pb + cq * 4);
-        }
+        DwTaps taps;
+        dw_load_taps(p, cq, taps);
         for (int r = tid >> 4; r < Rfull; r += 16) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < R) {
                 const int fr = r / p.Fout, fo = r - fr * p.Fout;
-                const int t = t0 + fr;
-#pragma unroll
-                for (int dt = 0; dt < 3; dt++) {
-                    if (dt < 3 - p.kt) continue;
-                    const int tp = t - (2 - dt);  // causal: taps at t-(kt-1) .. t
-                    if (tp < 0) continue;
-#pragma unroll
-                    for (int df = 0; df < 3; df++) {
-                        int fi;
-                        float4 wv;
-                        if (MODE == DW_S1 || MODE == DW_DF0) { fi = fo + df - 1; wv = wd[dt * 3 + df]; }
-                        else if (MODE == DW_S2) { fi = 2 * fo + df - 1; wv = wd[dt * 3 + df]; }
-                        else {  // DW_T2: df enumerates the (at most two) contributing taps
-                            if (df == 2) continue;
-                            if ((fo & 1) == 0) { if (df == 1) continue; fi = fo >> 1; wv = wd[dt * 3 + 1]; }
-                            else if (df == 0) { fi = fo >> 1; wv = wd[dt * 3 + 2]; }
-                            else { fi = (fo >> 1) + 1; wv = wd[dt * 3 + 0]; }
-                        }
-                        if (fi < 0 || fi >= p.Fin) continue;
-                        float4 x;
-                        if (MODE == DW_DF0) {
-                            // channels [0,32) read re, [32,64) read im (groups = 2); look-ahead shifted
-                            if (tp + p.lookahead >= p.T) continue;
-                            const float *src = p.in + ((int64_t)b * p.T + tp + p.lookahead) * p.in_fs + fi * 2;
-                            float v = (cq < 8) ? src[0] : src[1];
-                            x = make_float4(v, v, v, v);
-                        } else {
-                            const int64_t o = ((int64_t)b * p.T + tp);
-                            x = *reinterpret_cast<const float4 *>(p.in + o * p.in_fs + fi * kCh + cq * 4);
-                            if (p.path) {
-                                float4 e = *reinterpret_cast<const float4 *>(p.path + o * p.path_fs + fi * kCh + cq * 4);
-                                x.x += fmaxf(e.x * ps4.x + pb4.x, 0.f);
-                                x.y += fmaxf(e.y * ps4.y + pb4.y, 0.f);
-                                x.z += fmaxf(e.z * ps4.z + pb4.z, 0.f);
-                                x.w += fmaxf(e.w * ps4.w + pb4.w, 0.f);
-                            }
-                        }
-                        acc.x += x.x * wv.x; acc.y += x.y * wv.y; acc.z += x.z * wv.z; acc.w += x.w * wv.w;
-                    }
-                }
+                acc = dw_prologue<MODE>(p, taps, b, t0 + fr, fo, cq);
             }
             *reinterpret_cast<float4 *>(As + r * kLdA + cq * 4) = acc;
         }
@@ -322,9 +260,44 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
 // (3U rows x H) in REGISTERS: 384 threads, each an 8-row x 16-k tile (128 weights), so a thread
 // reads only 16 h values per stream and step from shared memory; the H/16 lanes that share a row
 // group combine their partial sums with a shuffle reduce-scatter.  The hidden state of the group
-// lives in shared memory of every CTA; the new slice is broadcast through DSMEM each step; one
-// cluster barrier per time step.  H = 256: C = 4, U = 64;  H = 512: C = 16, U = 32.
+// lives in shared memory of every CTA (double buffered); the new slice is broadcast with st.async
+// DSMEM stores that complete bytes on the receiver's mbarrier, so a step needs neither a cluster
+// barrier nor a memory fence (ncu on the first version: membar was the top stall, the release
+// fence of cluster.sync() waited for the global h stores).  H = 256: C = 4, U = 64;  H = 512: C = 16, U = 32.
 constexpr int kGruThreads = 384, kGruRT = 8, kGruKT = 16, kGruSB = 4, kGruMaxBc = 16;
+
+__device__ __forceinline__ uint32_t gru_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t gru_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// remote (DSMEM) store that completes `4` bytes on the destination CTA's mbarrier: no fence or
+// cluster barrier is needed on the consumer side, it just waits for the expected byte count
+__device__ __forceinline__ void gru_st_async(uint32_t dst, float v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
+                 "r"(__float_as_uint(v)), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void gru_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gru_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void gru_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gru_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gru_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(gru_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 struct GruParams {
     const float *xproj;  // [B,T,3H]
@@ -352,6 +325,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
     extern __shared__ __align__(16) float gru_smem[];
     float (*s_h)[kGruMaxBc][HP] = reinterpret_cast<float (*)[kGruMaxBc][HP]>(gru_smem);            // [2][Bc][HP]
     float (*s_pre)[kGruMaxBc + 1] = reinterpret_cast<float (*)[kGruMaxBc + 1]>(gru_smem + 2 * kGruMaxBc * HP);  // [3U]
+    __shared__ __align__(8) uint64_t s_bar[2];     // s_bar[b]: all of h for buffer b has arrived
     const int tid = threadIdx.x;
     const int rg = tid / LPR, kl = tid % LPR;      // row group, k slice [16 kl, 16 kl + 16)
     // weights -> registers: w[r][k] = Whh[global_row(8 rg + r)][16 kl + k]
@@ -381,9 +355,19 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
         int u = item % U;
         bh[it][0] = p.bhh[rank * U + u]; bh[it][1] = p.bhh[H + rank * U + u]; bh[it][2] = p.bhh[2 * H + rank * U + u];
     }
-    cluster.sync();
+    if (tid == 0) {
+        gru_mbar_init(&s_bar[0], 1);
+        gru_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();  // barriers initialised and h0 = 0 visible before any remote store can arrive
+    const uint32_t bar_local[2] = {gru_smem_u32(&s_bar[0]), gru_smem_u32(&s_bar[1])};
+    const uint32_t step_bytes = (uint32_t)(H * nb * 4);
     int cur = 0;
     for (int t = 0; t < p.T; t++) {
+        // arm the barrier of the other buffer for the h_{t+1} bytes, then wait for h_t
+        if (tid == 0 && t + 1 < p.T) gru_mbar_expect_tx(&s_bar[cur ^ 1], step_bytes);
+        if (t > 0) gru_mbar_wait(&s_bar[cur], (uint32_t)(((t - 1) >> 1) & 1));
         // prefetch the input projections of this step for the gate phase (independent of h)
         float xr[kItems][3];
 #pragma unroll
@@ -451,15 +435,19 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
                 float hn = (1.f - z) * n + z * hprev;
                 int64_t o = ((int64_t)(b0 + s) * p.T + t) * H + gu;
                 p.hout[o] = p.res ? hn + p.res[o] : hn;
-                // broadcast the new value to every CTA of the cluster (DSMEM)
-                float *dst_local = &s_h[cur ^ 1][s][hp];
+                if (t + 1 < p.T) {
+                    // broadcast the new value to every CTA of the cluster (st.async DSMEM store)
+                    const uint32_t dst_local = gru_smem_u32(&s_h[cur ^ 1][s][hp]);
 #pragma unroll
-                for (int c = 0; c < C; c++) *cluster.map_shared_rank(dst_local, c) = hn;
+                    for (int c = 0; c < C; c++) gru_st_async(gru_mapa(dst_local, c), hn, gru_mapa(bar_local[cur ^ 1], c));
+                }
             }
         }
-        cluster.sync();
+        // no CTA barrier here: s_pre is rewritten by the next step's matvec only after the mbarrier
+        // wait at the top of the loop, which needs every gate thread's sends (issued after its reads)
         cur ^= 1;
     }
+    cluster.sync();  // no CTA exits while peers may still address its shared memory
 }
 
 // --------------------------------------------------------------- ERB mask output conv ----
@@ -788,8 +776,16 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
     return DFB_OK;
 }
 
+}  // namespace
+namespace dfb {
 template <int MODE>
-int run_dwpw(cudaStream_t s, DwPwParams p, int B) {
+int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *pw_nk, int B);
+}
+namespace {
+
+template <int MODE>
+int run_dwpw(cudaStream_t s, DwPwParams p, int B, const float *pw_nk = nullptr) {
+    if (pw_nk) return launch_dwpw_tc<MODE>(s, p, pw_nk, B);
     static bool attr_done = false;
     const int smem = (kCh * kCh + 128 * kLdA) * 4;
     if (!attr_done) {
@@ -890,12 +886,15 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         k_erb_conv0<<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead);
         DFB_LAUNCH_CHECK();
     }
+    const float *pw_nk = nullptr;  // set by blk(): [C_out][C_in] 1x1 weights for the tensor-core path
     auto blk = [&](const char *name, DwPwParams &p) -> int {
         std::string n(name);
         int r;
         if ((r = need(m, (n + ".dw").c_str(), -1, &p.dw)) || (r = need(m, (n + ".pw").c_str(), kCh * kCh, &p.pw)) ||
             (r = need(m, (n + ".b").c_str(), kCh, &p.bias)))
             return r;
+        pw_nk = nullptr;
+        if (m->precision == 1 && (r = need(m, (n + ".pw_nk").c_str(), kCh * kCh, &pw_nk))) return r;
         return DFB_OK;
     };
     auto mk = [&](const float *in, int Fin, int64_t in_fs, float *out, int Fout, int64_t out_fs, int kt) {
@@ -906,16 +905,16 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     };
     {
         DwPwParams p = mk(f.e0, E, (int64_t)E * kCh, f.e1, E / 2, (int64_t)E / 2 * kCh, c.conv_kt);
-        if ((rc = blk("enc.erb_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B))) return rc;
+        if ((rc = blk("enc.erb_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
         p = mk(f.e1, E / 2, (int64_t)E / 2 * kCh, f.e2, E / 4, (int64_t)E / 4 * kCh, c.conv_kt);
-        if ((rc = blk("enc.erb_conv2", p)) || (rc = run_dwpw<DW_S2>(s, p, B))) return rc;
+        if ((rc = blk("enc.erb_conv2", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
         p = mk(f.e2, E / 4, (int64_t)E / 4 * kCh, f.e3, E / 4, e3_fs, c.conv_kt);
-        if ((rc = blk("enc.erb_conv3", p)) || (rc = run_dwpw<DW_S1>(s, p, B))) return rc;
+        if ((rc = blk("enc.erb_conv3", p)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_nk))) return rc;
         p = mk(d_feat_spec, Fd, (int64_t)Fd * 2, f.c0, Fd, (int64_t)Fd * kCh, c.inp_kt);
         p.lookahead = c.conv_lookahead;
-        if ((rc = blk("enc.df_conv0", p)) || (rc = run_dwpw<DW_DF0>(s, p, B))) return rc;
+        if ((rc = blk("enc.df_conv0", p)) || (rc = run_dwpw<DW_DF0>(s, p, B, pw_nk))) return rc;
         p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
-        if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B))) return rc;
+        if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
     }
     {
         // cemb = relu(df_fc_emb(c1 flat)); emb_in = e3 flat + cemb  (DFN2: concat)
@@ -963,11 +962,11 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             return DFB_OK;
         };
         DwPwParams p = mk(f.dec_emb, E / 4, ED, f.d3, E / 4, ED, c.conv_kt);
-        if ((rc = blk("erb_dec.convt3", p)) || (rc = path(p, "erb_dec.conv3p", f.e3, e3_fs)) || (rc = run_dwpw<DW_S1>(s, p, B))) return rc;
+        if ((rc = blk("erb_dec.convt3", p)) || (rc = path(p, "erb_dec.conv3p", f.e3, e3_fs)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_nk))) return rc;
         p = mk(f.d3, E / 4, ED, f.d2, E / 2, (int64_t)E / 2 * kCh, 1);
-        if ((rc = blk("erb_dec.convt2", p)) || (rc = path(p, "erb_dec.conv2p", f.e2, (int64_t)E / 4 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B))) return rc;
+        if ((rc = blk("erb_dec.convt2", p)) || (rc = path(p, "erb_dec.conv2p", f.e2, (int64_t)E / 4 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B, pw_nk))) return rc;
         p = mk(f.d2, E / 2, (int64_t)E / 2 * kCh, f.d1, E, (int64_t)E * kCh, 1);
-        if ((rc = blk("erb_dec.convt1", p)) || (rc = path(p, "erb_dec.conv1p", f.e1, (int64_t)E / 2 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B))) return rc;
+        if ((rc = blk("erb_dec.convt1", p)) || (rc = path(p, "erb_dec.conv1p", f.e1, (int64_t)E / 2 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B, pw_nk))) return rc;
         const float *ps, *pb, *w, *bb;
         if ((rc = need(m, "erb_dec.conv0p.s", kCh, &ps)) || (rc = need(m, "erb_dec.conv0p.b", kCh, &pb)) ||
             (rc = need(m, "erb_dec.conv0_out.w", c.conv_kt * 3 * kCh, &w)) || (rc = need(m, "erb_dec.conv0_out.b", 1, &bb)))

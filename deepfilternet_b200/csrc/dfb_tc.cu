@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include "dfb_common.cuh"
+#include "dfb_dwpw.cuh"
 
 namespace dfb {
 
@@ -118,7 +119,7 @@ __device__ __forceinline__ float tc_act(float x, int act) {
 }
 
 // ---------------------------------------------------------------------------- GEMM kernel ----
-constexpr int kTcBM = 128, kTcBK = 32, kTcStages = 4;
+constexpr int kTcBM = 128, kTcBK = 32, kTcStages = 2;  // 64 KB of operands per CTA -> 3 CTAs / SM
 
 template <int BN>
 struct TcSmem {
@@ -128,6 +129,7 @@ struct TcSmem {
     uint64_t empty[kTcStages];
     uint64_t tmem_full;
     uint32_t tmem_base;
+    alignas(16) float bias[BN];
 };
 
 template <int BN>
@@ -147,6 +149,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&sm.tmem_base, BN);
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) sm.bias[i] = bias ? bias[n0 + i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -190,10 +193,11 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float4 o;
-                o.x = tc_act(v[j] + (bias ? bias[n0 + c + j] : 0.f), act);
-                o.y = tc_act(v[j + 1] + (bias ? bias[n0 + c + j + 1] : 0.f), act);
-                o.z = tc_act(v[j + 2] + (bias ? bias[n0 + c + j + 2] : 0.f), act);
-                o.w = tc_act(v[j + 3] + (bias ? bias[n0 + c + j + 3] : 0.f), act);
+                const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[c + j]);
+                o.x = tc_act(v[j] + bv.x, act);
+                o.y = tc_act(v[j + 1] + bv.y, act);
+                o.z = tc_act(v[j + 2] + bv.z, act);
+                o.w = tc_act(v[j + 3] + bv.w, act);
                 *reinterpret_cast<float4 *>(dst + j) = o;
             }
         }
@@ -202,6 +206,138 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, BN);
 }
+
+// ------------------------------------------- fused depthwise -> 1x1 (tcgen05) -> ReLU ----
+// Tensor-core version of k_dwpw (dfb_model.cu): the prologue threads write the depthwise result
+// A[128 rows][64 ch] straight into shared memory in the UMMA K-major 128B-swizzle layout (two
+// [128 x 32] sub-tiles), one thread issues 8 tcgen05.mma (M128 N64 K8, tf32) against the 1x1 weight
+// tile, and all 8 warps read the fp32 accumulator from TMEM for the bias + ReLU epilogue.
+// Persistent: each CTA loops over row tiles; TMEM, barrier and the weight tile are set up once.
+struct DwTcSmem {
+    alignas(1024) float a[2][128 * 32];   // A sub-tiles (k chunk c: channels [32 c, 32 c + 32))
+    alignas(1024) float w[2][kCh * 32];   // B sub-tiles: W[n][k] = pw_nk[n][32 c + k]
+    alignas(16) float bias[kCh];
+    alignas(8) uint64_t mma_done;
+    uint32_t tmem_base;
+};
+
+// byte offset of (row r, 16-byte chunk j) inside a [rows x 128 B] sub-tile with 128-byte swizzle
+__device__ __forceinline__ uint32_t sw128_off(int r, int j) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dwpw_tc(DwPwParams p, const float *__restrict__ pw_nk, int B, int tiles_per_stream) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    DwTcSmem &sm = *reinterpret_cast<DwTcSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- one-time setup: weights (B operand), bias, barrier, TMEM
+    for (int i = tid; i < kCh * 16; i += 256) {  // (n, 16-byte chunk j over k)
+        const int n = i >> 4, jj = i & 15, c = jj >> 3, j = jj & 7;
+        float4 v = *reinterpret_cast<const float4 *>(pw_nk + n * kCh + c * 32 + j * 4);
+        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sm.w[c]) + sw128_off(n, j)) = v;
+    }
+    if (tid < kCh) sm.bias[tid] = p.bias[tid];
+    if (tid == 0) {
+        mbar_init(&sm.mma_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 64);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const int cq = tid & 15;
+    DwTaps taps;
+    dw_load_taps(p, cq, taps);
+    const int total_tiles = B * tiles_per_stream;
+    constexpr uint32_t idesc = umma_idesc_tf32(128, kCh);
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_stream, t0 = (tile - b * tiles_per_stream) * p.NF;
+        const int nf = min(p.NF, p.T - t0);
+        const int R = nf * p.Fout;
+        // ---- prologue into swizzled smem (rows >= R are zero)
+        for (int r = tid >> 4; r < 128; r += 16) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < R) {
+                const int fr = r / p.Fout, fo = r - fr * p.Fout;
+                acc = dw_prologue<MODE>(p, taps, b, t0 + fr, fo, cq);
+            }
+            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sm.a[cq >> 3]) + sw128_off(r, cq & 7)) = acc;
+        }
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint32_t a0 = smem_u32(sm.a[c]), b0 = smem_u32(sm.w[c]);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_tf32(tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (c | k) != 0);
+            }
+            umma_commit(&sm.mma_done);
+        }
+        __syncwarp();
+        mbar_wait(&sm.mma_done, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue: warp w reads TMEM lanes [32 (w % 4), +32), columns [32 (w / 4), +32)
+        {
+            const int r = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 32;
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+            if (r < R) {
+                const int fr = r / p.Fout, fo = r - fr * p.Fout;
+                float *dst = p.out + ((int64_t)b * p.T + t0 + fr) * p.out_fs + fo * kCh + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[c0 + j]);
+                    float4 o = make_float4(fmaxf(v[j] + bv.x, 0.f), fmaxf(v[j + 1] + bv.y, 0.f),
+                                           fmaxf(v[j + 2] + bv.z, 0.f), fmaxf(v[j + 3] + bv.w, 0.f));
+                    *reinterpret_cast<float4 *>(dst + j) = o;
+                }
+            }
+        }
+        // the accumulator and the A tile are reused by the next tile: order the TMEM reads before it
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+template <int MODE>
+int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *pw_nk, int B) {
+    static bool attr_done = false;
+    const int smem = (int)sizeof(DwTcSmem) + 1024;
+    static int resident = 0;  // CTAs that fit on the device at once (persistent grid size)
+    if (!attr_done) {
+        DFB_CUDA(cudaFuncSetAttribute(k_dwpw_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int dev = 0, num_sms = 0, per_sm = 0;
+        DFB_CUDA(cudaGetDevice(&dev));
+        DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dwpw_tc<MODE>, 256, smem));
+        resident = num_sms * (per_sm > 0 ? per_sm : 1);
+        attr_done = true;
+    }
+    p.NF = 128 / p.Fout;
+    if (p.NF < 1) p.NF = 1;
+    if (p.NF * p.Fout > 128) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile: Fout = %d", p.Fout);
+    const int tiles_per_stream = (p.T + p.NF - 1) / p.NF;
+    const int64_t total = (int64_t)B * tiles_per_stream;
+    const int ctas = (int)(total < (int64_t)resident ? total : (int64_t)resident);
+    DFB_PROF(MODE == DW_DF0 ? "k_dwpw_tc[df_conv0]" : "k_dwpw_tc", s);
+    k_dwpw_tc<MODE><<<ctas, 256, smem, s>>>(p, pw_nk, B, tiles_per_stream);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+}
+template int launch_dwpw_tc<DW_S1>(cudaStream_t, DwPwParams, const float *, int);
+template int launch_dwpw_tc<DW_S2>(cudaStream_t, DwPwParams, const float *, int);
+template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int);
+template int launch_dwpw_tc<DW_DF0>(cudaStream_t, DwPwParams, const float *, int);
 
 // ------------------------------------------------------------------------------- host side ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

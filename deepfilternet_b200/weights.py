@@ -85,6 +85,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
         s, b = _bn_fold(sd, f"{prefix}.{bns[0]}")
         out[prefix + ".dw"] = f32(dw[:, 0].transpose(1, 2, 0))
         out[prefix + ".pw"] = f32((pw * s[:, None]).T)
+        out[prefix + ".pw_nk"] = f32(pw * s[:, None])  # [C_out][C_in]: B operand of the tcgen05 kernel
         out[prefix + ".b"] = f32(b)
         return dw.shape[2]
 
@@ -102,6 +103,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
     s, b = _bn_fold(sd, f"enc.df_conv0.{bns[0]}")
     out["enc.df_conv0.dw"] = f32(dw[:, 0].transpose(1, 2, 0))
     out["enc.df_conv0.pw"] = f32((pw * s[:, None]).T)
+    out["enc.df_conv0.pw_nk"] = f32(pw * s[:, None])
     out["enc.df_conv0.b"] = f32(b)
     # --- decoder pathway convs (depthwise 1x1 + BN + ReLU)
     for n in (3, 2, 1, 0):

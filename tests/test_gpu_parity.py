@@ -22,6 +22,10 @@ from deepfilternet_b200.model import find_checkpoint, load_state_dict_file
 from deepfilternet_b200.weights import random_state_dict
 
 RMS_TOL = 1e-4  # BASELINE.json north_star
+# DFB_PRECISION=tf32 runs the dense contractions on tcgen05 TF32 tensor cores: the end-to-end bound
+# stays 1e-4 RMS, the tolerances on intermediate tensors widen (10-bit mantissa products).
+TF32 = os.environ.get("DFB_PRECISION", "fp32") == "tf32"
+TOL_M, TOL_SPEC, TOL_COEF, TOL_LSNR = (2e-3, 2e-5, 2e-3, 0.5) if TF32 else (1e-5, 1e-6, 1e-5, 1e-3)
 
 
 def rms(a, b):
@@ -139,16 +143,16 @@ def test_forward_random_weights(states, kind, B, T):
     out_o, aux = O.enhance(sd, cfg.as_dict(), audio, return_all=True)
     spec_e, m, lsnr, last = model(aux["spec"], aux["erb_feat"], aux["spec_feat"])
     assert spec_e.shape == aux["spec_e"].shape and m.shape == aux["m"].shape and lsnr.shape == aux["lsnr"].shape
-    assert rms(m, aux["m"]) < 1e-5 and rms(spec_e, aux["spec_e"]) < 1e-6
-    assert np.abs(lsnr.numpy() - aux["lsnr"].numpy()).max() < 1e-3
+    assert rms(m, aux["m"]) < TOL_M and rms(spec_e, aux["spec_e"]) < TOL_SPEC
+    assert np.abs(lsnr.numpy() - aux["lsnr"].numpy()).max() < TOL_LSNR
     if cfg.model == "deepfilternet3":
         assert last.shape == (B, 5, aux["m"].shape[2], 96, 2)
-        assert rms(last.permute(0, 2, 3, 1, 4).reshape(aux["coefs"].shape), aux["coefs"]) < 1e-5
+        assert rms(last.permute(0, 2, 3, 1, 4).reshape(aux["coefs"].shape), aux["coefs"]) < TOL_COEF
     out = enhance(model, st, audio)
     assert out.shape == audio.shape and rms(out, out_o) < RMS_TOL
     # CUDA-tensor in, CUDA-tensor out through the same forward
     r = model(aux["spec"].cuda(), aux["erb_feat"].cuda(), aux["spec_feat"].cuda())
-    assert r[0].is_cuda and rms(r[0].cpu(), aux["spec_e"]) < 1e-6
+    assert r[0].is_cuda and rms(r[0].cpu(), aux["spec_e"]) < TOL_SPEC
 
 
 @pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
@@ -163,7 +167,7 @@ def test_golden_reference_outputs(name, golden_dir, model_dir):
     assert o.shape == g["enhanced_nopad"].shape and rms(o, g["enhanced_nopad"]) < RMS_TOL
     assert rms(enhance(model, st, audio, atten_lim_db=12.0), g["enhanced_atten12"]) < RMS_TOL
     spec_e, m, lsnr, _ = model(torch.from_numpy(g["spec"]), torch.from_numpy(g["feat_erb"]), torch.from_numpy(g["feat_spec"]))
-    assert rms(spec_e, g["spec_e"]) < 1e-6 and rms(m, g["m"]) < 1e-5 and np.abs(lsnr.numpy() - g["lsnr"]).max() < 1e-3
+    assert rms(spec_e, g["spec_e"]) < TOL_SPEC and rms(m, g["m"]) < TOL_M and np.abs(lsnr.numpy() - g["lsnr"]).max() < TOL_LSNR
 
 
 @pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
