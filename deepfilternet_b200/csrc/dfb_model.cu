@@ -266,6 +266,21 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
 // fence of cluster.sync() waited for the global h stores).  H = 256: C = 4, U = 64;  H = 512: C = 16, U = 32.
 constexpr int kGruThreads = 384, kGruRT = 8, kGruKT = 16, kGruSB = 4, kGruMaxBc = 16;
 
+// packed fp32x2 FMA (Blackwell FFMA2): d = a * b + c on both halves; a scalar b is broadcast by the
+// compiler through the .F32 operand form, so a pair of W rows costs one issue slot per (k, stream)
+__device__ __forceinline__ unsigned long long gru_pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void gru_unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long gru_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t gru_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t gru_mapa(uint32_t saddr, uint32_t rank) {
     uint32_t r;
@@ -328,16 +343,18 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
     __shared__ __align__(8) uint64_t s_bar[2];     // s_bar[b]: all of h for buffer b has arrived
     const int tid = threadIdx.x;
     const int rg = tid / LPR, kl = tid % LPR;      // row group, k slice [16 kl, 16 kl + 16)
-    // weights -> registers: w[r][k] = Whh[global_row(8 rg + r)][16 kl + k]
-    float w[kGruRT][kGruKT];
+    // weights -> registers as row pairs: w2[rp][k] = (Whh[row(2 rp)][16 kl + k], Whh[row(2 rp + 1)][16 kl + k])
+    unsigned long long w2[kGruRT / 2][kGruKT];
 #pragma unroll
-    for (int r = 0; r < kGruRT; r++) {
-        const int row = rg * kGruRT + r;           // row in [0, 3U): gate = row / U, unit = row % U
-        const float *src = p.whh + ((int64_t)(row / U) * H + rank * U + (row % U)) * H + kl * kGruKT;
+    for (int rp = 0; rp < kGruRT / 2; rp++) {
+        const int row0 = rg * kGruRT + 2 * rp, row1 = row0 + 1;  // row in [0, 3U): gate = row / U, unit = row % U
+        const float *s0 = p.whh + ((int64_t)(row0 / U) * H + rank * U + (row0 % U)) * H + kl * kGruKT;
+        const float *s1 = p.whh + ((int64_t)(row1 / U) * H + rank * U + (row1 % U)) * H + kl * kGruKT;
 #pragma unroll
         for (int k = 0; k < kGruKT; k += 4) {
-            float4 v = *reinterpret_cast<const float4 *>(src + k);
-            w[r][k] = v.x; w[r][k + 1] = v.y; w[r][k + 2] = v.z; w[r][k + 3] = v.w;
+            float4 a = *reinterpret_cast<const float4 *>(s0 + k), c = *reinterpret_cast<const float4 *>(s1 + k);
+            w2[rp][k] = gru_pack2(a.x, c.x); w2[rp][k + 1] = gru_pack2(a.y, c.y);
+            w2[rp][k + 2] = gru_pack2(a.z, c.z); w2[rp][k + 3] = gru_pack2(a.w, c.w);
         }
     }
     // index of the first fully reduced value this lane owns after the reduce-scatter
@@ -381,9 +398,11 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
         }
         // matvec: pre[row][s] = sum_k W[row][k] h[s][k]
         for (int sc = 0; sc < nb; sc += kGruSB) {
-            float acc[V];
+            unsigned long long acc2[kGruRT / 2][kGruSB];
 #pragma unroll
-            for (int i = 0; i < V; i++) acc[i] = 0.f;
+            for (int rp = 0; rp < kGruRT / 2; rp++)
+#pragma unroll
+                for (int s = 0; s < kGruSB; s++) acc2[rp][s] = 0ull;
 #pragma unroll
             for (int s = 0; s < kGruSB; s++) {
                 // h is stored permuted (hpos) so that the LPR lanes read consecutive float4s
@@ -391,14 +410,23 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
 #pragma unroll
                 for (int k = 0; k < kGruKT; k += 4) {
                     float4 hv = *reinterpret_cast<const float4 *>(hb + (k / 4) * LPR * 4);
+                    const unsigned long long h0 = gru_pack2(hv.x, hv.x), h1 = gru_pack2(hv.y, hv.y),
+                                             h2 = gru_pack2(hv.z, hv.z), h3 = gru_pack2(hv.w, hv.w);
 #pragma unroll
-                    for (int r = 0; r < kGruRT; r++) {
-                        float a = acc[r * kGruSB + s];
-                        a += w[r][k] * hv.x; a += w[r][k + 1] * hv.y; a += w[r][k + 2] * hv.z; a += w[r][k + 3] * hv.w;
-                        acc[r * kGruSB + s] = a;
+                    for (int rp = 0; rp < kGruRT / 2; rp++) {
+                        unsigned long long a = acc2[rp][s];
+                        a = gru_ffma2(w2[rp][k], h0, a); a = gru_ffma2(w2[rp][k + 1], h1, a);
+                        a = gru_ffma2(w2[rp][k + 2], h2, a); a = gru_ffma2(w2[rp][k + 3], h3, a);
+                        acc2[rp][s] = a;
                     }
                 }
             }
+            float acc[V];
+#pragma unroll
+            for (int rp = 0; rp < kGruRT / 2; rp++)
+#pragma unroll
+                for (int s = 0; s < kGruSB; s++)
+                    gru_unpack2(acc2[rp][s], acc[(2 * rp) * kGruSB + s], acc[(2 * rp + 1) * kGruSB + s]);
             // reduce-scatter over the LPR lanes of this row group
 #pragma unroll
             for (int bit = LPR / 2, n = V / 2; bit >= 1 && n >= 1; bit >>= 1, n >>= 1) {

@@ -208,16 +208,20 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // ------------------------------------------- fused depthwise -> 1x1 (tcgen05) -> ReLU ----
-// Tensor-core version of k_dwpw (dfb_model.cu): the prologue threads write the depthwise result
-// A[128 rows][64 ch] straight into shared memory in the UMMA K-major 128B-swizzle layout (two
-// [128 x 32] sub-tiles), one thread issues 8 tcgen05.mma (M128 N64 K8, tf32) against the 1x1 weight
-// tile, and all 8 warps read the fp32 accumulator from TMEM for the bias + ReLU epilogue.
-// Persistent: each CTA loops over row tiles; TMEM, barrier and the weight tile are set up once.
+// Tensor-core version of k_dwpw (dfb_model.cu), persistent over 128-row tiles and warp specialised:
+//   warps 0-3 : producers -- depthwise (+pathway) prologue, tf32-rounded (RN), written straight into
+//               shared memory in the UMMA K-major 128B-swizzle layout (two [128 x 32] sub-tiles)
+//   warp  8   : one lane issues 8 tcgen05.mma (M128 N64 K8, kind::tf32) per tile against the 1x1
+//               weight tile; tcgen05.commit frees the A buffer and publishes the accumulator
+//   warps 4-7 : epilogue -- tcgen05.ld of the fp32 accumulator (TMEM lane = tile row), bias + ReLU,
+//               256-byte row stores
+// A tile and accumulator are double buffered so the three stages of consecutive tiles overlap.
 struct DwTcSmem {
-    alignas(1024) float a[2][128 * 32];   // A sub-tiles (k chunk c: channels [32 c, 32 c + 32))
-    alignas(1024) float w[2][kCh * 32];   // B sub-tiles: W[n][k] = pw_nk[n][32 c + k]
+    alignas(1024) float a[2][2][128 * 32];   // [buffer][k chunk c: channels [32 c, 32 c + 32)]
+    alignas(1024) float w[2][kCh * 32];      // B sub-tiles: W[n][k] = pw_nk[n][32 c + k]
     alignas(16) float bias[kCh];
-    alignas(8) uint64_t mma_done;
+    alignas(8) uint64_t a_full[2];
+    uint64_t a_empty[2], t_full[2], t_empty[2];
     uint32_t tmem_base;
 };
 
@@ -225,88 +229,134 @@ struct DwTcSmem {
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+constexpr int kDwTcThreads = 288;
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k_dwpw_tc(DwPwParams p, const float *__restrict__ pw_nk, int B, int tiles_per_stream) {
+__global__ void __launch_bounds__(kDwTcThreads, 2) k_dwpw_tc(DwPwParams p, const float *__restrict__ pw_nk, int B, int tiles_per_stream) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     DwTcSmem &sm = *reinterpret_cast<DwTcSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // ---- one-time setup: weights (B operand), bias, barrier, TMEM
-    for (int i = tid; i < kCh * 16; i += 256) {  // (n, 16-byte chunk j over k)
+    // ---- one-time setup: weights (B operand), bias, barriers, TMEM
+    for (int i = tid; i < kCh * 16; i += kDwTcThreads) {  // (n, 16-byte chunk j over k)
         const int n = i >> 4, jj = i & 15, c = jj >> 3, j = jj & 7;
         float4 v = *reinterpret_cast<const float4 *>(pw_nk + n * kCh + c * 32 + j * 4);
+        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
         *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sm.w[c]) + sw128_off(n, j)) = v;
     }
     if (tid < kCh) sm.bias[tid] = p.bias[tid];
     if (tid == 0) {
-        mbar_init(&sm.mma_done, 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.a_full[i], 4);    // one arrive per producer warp
+            mbar_init(&sm.a_empty[i], 1);   // tcgen05.commit
+            mbar_init(&sm.t_full[i], 1);    // tcgen05.commit
+            mbar_init(&sm.t_empty[i], 4);   // one arrive per epilogue warp
+        }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, 64);
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 128);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const int cq = tid & 15;
-    DwTaps taps;
-    dw_load_taps(p, cq, taps);
     const int total_tiles = B * tiles_per_stream;
-    constexpr uint32_t idesc = umma_idesc_tf32(128, kCh);
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_stream, t0 = (tile - b * tiles_per_stream) * p.NF;
-        const int nf = min(p.NF, p.T - t0);
-        const int R = nf * p.Fout;
-        // ---- prologue into swizzled smem (rows >= R are zero)
-        for (int r = tid >> 4; r < 128; r += 16) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < R) {
-                const int fr = r / p.Fout, fo = r - fr * p.Fout;
-                acc = dw_prologue<MODE>(p, taps, b, t0 + fr, fo, cq);
+
+    if (warp < 4) {
+        // ================================================================= producers
+        const int cq = tid & 15, slot = tid >> 4;  // 16 channel quads x 8 row slots
+        DwTaps taps;
+        dw_load_taps(p, cq, taps);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            const int buf = it & 1, n = it >> 1;
+            const int b = tile / tiles_per_stream, t0 = (tile - b * tiles_per_stream) * p.NF;
+            const int R = min(p.NF, p.T - t0) * p.Fout;
+            if (n > 0) mbar_wait(&sm.a_empty[buf], (n - 1) & 1);
+            unsigned char *abase = reinterpret_cast<unsigned char *>(sm.a[buf][cq >> 3]);
+#pragma unroll 4
+            for (int r = slot; r < 128; r += 8) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < R) {
+                    const int fr = r / p.Fout, fo = r - fr * p.Fout;
+                    acc = dw_prologue<MODE>(p, taps, b, t0 + fr, fo, cq);
+                    acc.x = to_tf32(acc.x); acc.y = to_tf32(acc.y); acc.z = to_tf32(acc.z); acc.w = to_tf32(acc.w);
+                }
+                *reinterpret_cast<float4 *>(abase + sw128_off(r, cq & 7)) = acc;
             }
-            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sm.a[cq >> 3]) + sw128_off(r, cq & 7)) = acc;
+            fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.a_full[buf]);
         }
-        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (tid == 0) {
+    } else if (warp == 8) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(128, kCh);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+                const int buf = it & 1, n = it >> 1;
+                mbar_wait(&sm.a_full[buf], n & 1);
+                if (n > 0) mbar_wait(&sm.t_empty[buf], (n - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const uint32_t a0 = smem_u32(sm.a[buf][c]), b0 = smem_u32(sm.w[c]);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        umma_tf32(tmem + buf * 64, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
+                                  (c | k) != 0);
+                }
+                umma_commit(&sm.a_empty[buf]);
+                umma_commit(&sm.t_full[buf]);
+            }
+        }
+    } else {
+        // ================================================================= epilogue (warps 4-7)
+        const int q = warp - 4;  // TMEM lane quarter of this warp (warp % 4)
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            const int buf = it & 1, n = it >> 1;
+            const int b = tile / tiles_per_stream, t0 = (tile - b * tiles_per_stream) * p.NF;
+            const int R = min(p.NF, p.T - t0) * p.Fout;
+            mbar_wait(&sm.t_full[buf], n & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const uint32_t a0 = smem_u32(sm.a[c]), b0 = smem_u32(sm.w[c]);
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    umma_tf32(tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (c | k) != 0);
-            }
-            umma_commit(&sm.mma_done);
-        }
-        __syncwarp();
-        mbar_wait(&sm.mma_done, phase);
-        phase ^= 1;
-        tc_fence_after();
-        // ---- epilogue: warp w reads TMEM lanes [32 (w % 4), +32), columns [32 (w / 4), +32)
-        {
-            const int r = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 32;
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+            float v0[32], v1[32];
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + buf * 64;
+            tmem_ld32(ta, v0);
+            tmem_ld32(ta + 32, v1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.t_empty[buf]);
+            const int r = q * 32 + lane;
             if (r < R) {
                 const int fr = r / p.Fout, fo = r - fr * p.Fout;
-                float *dst = p.out + ((int64_t)b * p.T + t0 + fr) * p.out_fs + fo * kCh + c0;
+                float *dst = p.out + ((int64_t)b * p.T + t0 + fr) * p.out_fs + fo * kCh;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[c0 + j]);
-                    float4 o = make_float4(fmaxf(v[j] + bv.x, 0.f), fmaxf(v[j + 1] + bv.y, 0.f),
-                                           fmaxf(v[j + 2] + bv.z, 0.f), fmaxf(v[j + 3] + bv.w, 0.f));
-                    *reinterpret_cast<float4 *>(dst + j) = o;
+                    const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[j]);
+                    *reinterpret_cast<float4 *>(dst + j) = make_float4(fmaxf(v0[j] + bv.x, 0.f), fmaxf(v0[j + 1] + bv.y, 0.f),
+                                                                      fmaxf(v0[j + 2] + bv.z, 0.f), fmaxf(v0[j + 3] + bv.w, 0.f));
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[32 + j]);
+                    *reinterpret_cast<float4 *>(dst + 32 + j) = make_float4(fmaxf(v1[j] + bv.x, 0.f), fmaxf(v1[j + 1] + bv.y, 0.f),
+                                                                           fmaxf(v1[j + 2] + bv.z, 0.f), fmaxf(v1[j + 3] + bv.w, 0.f));
                 }
             }
         }
-        // the accumulator and the A tile are reused by the next tile: order the TMEM reads before it
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
     }
-    if (warp == 0) tmem_dealloc(tmem, 64);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 template <int MODE>
@@ -319,7 +369,7 @@ int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *pw_nk, int B) {
         int dev = 0, num_sms = 0, per_sm = 0;
         DFB_CUDA(cudaGetDevice(&dev));
         DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dwpw_tc<MODE>, 256, smem));
+        DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dwpw_tc<MODE>, kDwTcThreads, smem));
         resident = num_sms * (per_sm > 0 ? per_sm : 1);
         attr_done = true;
     }
@@ -330,7 +380,7 @@ int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *pw_nk, int B) {
     const int64_t total = (int64_t)B * tiles_per_stream;
     const int ctas = (int)(total < (int64_t)resident ? total : (int64_t)resident);
     DFB_PROF(MODE == DW_DF0 ? "k_dwpw_tc[df_conv0]" : "k_dwpw_tc", s);
-    k_dwpw_tc<MODE><<<ctas, 256, smem, s>>>(p, pw_nk, B, tiles_per_stream);
+    k_dwpw_tc<MODE><<<ctas, kDwTcThreads, smem, s>>>(p, pw_nk, B, tiles_per_stream);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }
