@@ -321,6 +321,7 @@ struct GruParams {
     const float *res;    // optional [B,T,H] added to the OUTPUT only (identity skip, modules.py:696)
     float *hout;         // [B,T,H]
     int B, T, Bc;
+    long long *dbg;      // optional [T][8] clock64 phase stamps of CTA 0 (dfb_debug_gru_timing)
 };
 
 template <int H, int C>
@@ -384,7 +385,10 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
     for (int t = 0; t < p.T; t++) {
         // arm the barrier of the other buffer for the h_{t+1} bytes, then wait for h_t
         if (tid == 0 && t + 1 < p.T) gru_mbar_expect_tx(&s_bar[cur ^ 1], step_bytes);
+        const bool dbg_on = p.dbg && blockIdx.x == 0 && tid == 0;
+        if (dbg_on) p.dbg[t * 8 + 0] = clock64();
         if (t > 0) gru_mbar_wait(&s_bar[cur], (uint32_t)(((t - 1) >> 1) & 1));
+        if (dbg_on) p.dbg[t * 8 + 1] = clock64();
         // prefetch the input projections of this step for the gate phase (independent of h)
         float xr[kItems][3];
 #pragma unroll
@@ -427,6 +431,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
 #pragma unroll
                 for (int s = 0; s < kGruSB; s++)
                     gru_unpack2(acc2[rp][s], acc[(2 * rp) * kGruSB + s], acc[(2 * rp + 1) * kGruSB + s]);
+            if (dbg_on && sc == 0) p.dbg[t * 8 + 2] = clock64();
             // reduce-scatter over the LPR lanes of this row group
 #pragma unroll
             for (int bit = LPR / 2, n = V / 2; bit >= 1 && n >= 1; bit >>= 1, n >>= 1) {
@@ -447,7 +452,9 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
                 if (sc + s < nb) s_pre[rg * kGruRT + r][sc + s] = acc[i];
             }
         }
+        if (dbg_on) p.dbg[t * 8 + 3] = clock64();
         __syncthreads();
+        if (dbg_on) p.dbg[t * 8 + 4] = clock64();
         // gates
 #pragma unroll
         for (int it = 0; it < kItems; it++) {
@@ -471,6 +478,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
                 }
             }
         }
+        if (dbg_on) p.dbg[t * 8 + 5] = clock64();
         // no CTA barrier here: s_pre is rewritten by the next step's matvec only after the mbarrier
         // wait at the top of the loop, which needs every gate thread's sends (issued after its reads)
         cur ^= 1;
@@ -621,6 +629,8 @@ struct dfb_model {
     std::map<std::string, std::pair<const float *, int64_t>> dbg;  // activations of the last forward
     std::vector<GruLayerW> enc_gru, erb_gru, df_gru;
     float *slab = nullptr;
+    int gru_tc = 0;  // 1: tensor-core recurrence (BF16 hi/lo split operands) for H = 256
+    long long *gru_dbg = nullptr;  // device buffer for dfb_debug_gru_timing
     int precision = 0;  // 0: fp32 FFMA everywhere; 1: TF32 tensor cores (tcgen05) for the dense contractions
     Arena arena;
     cudaStream_t stream = nullptr;
@@ -696,9 +706,28 @@ extern "C" void dfb_model_free(dfb_model *m) {
     delete m;
 }
 
+// Debug: when `steps` > 0, every following GRU launch stamps clock64() phases of CTA 0 into a device
+// buffer [steps][8] (0 step start, 1 h arrived, 2 matvec done, 3 reduce + s_pre stored, 4 CTA barrier
+// passed, 5 gates + sends issued); returns them for the LAST launch when called with h_out != NULL.
+extern "C" int dfb_debug_gru_timing(dfb_model *m, int steps, long long *h_out) {
+    if (!m) return fail(DFB_ERR_INVALID, "null model");
+    cudaSetDevice(m->device);
+    if (h_out && m->gru_dbg) {
+        DFB_CUDA(cudaDeviceSynchronize());
+        DFB_CUDA(cudaMemcpy(h_out, m->gru_dbg, sizeof(long long) * 8 * steps, cudaMemcpyDeviceToHost));
+    }
+    if (m->gru_dbg) { cudaFree(m->gru_dbg); m->gru_dbg = nullptr; }
+    if (steps > 0 && !h_out) {
+        DFB_CUDA(cudaMalloc(&m->gru_dbg, sizeof(long long) * 8 * steps));
+        DFB_CUDA(cudaMemset(m->gru_dbg, 0, sizeof(long long) * 8 * steps));
+    }
+    return DFB_OK;
+}
+
 extern "C" int dfb_model_set_precision(dfb_model *m, int mode) {
-    if (!m || mode < 0 || mode > 1) return fail(DFB_ERR_INVALID, "precision mode must be 0 (fp32) or 1 (tf32)");
-    m->precision = mode;
+    if (!m || mode < 0 || mode > 3) return fail(DFB_ERR_INVALID, "precision mode out of range");
+    m->precision = mode & 1;   // bit 0: TF32 tcgen05 for the dense feed-forward contractions
+    m->gru_tc = (mode >> 1) & 1;  // bit 1: tensor-core GRU recurrence (BF16x3 split, ~fp32 accurate)
     return DFB_OK;
 }
 
@@ -787,8 +816,10 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         }
         if (rc) return rc;
         float *dst = (l == layers - 1) ? y : tmp_h;
-        GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, 0};
-        if (H == 256) {
+        GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, 0, m->gru_dbg};
+        if (H == 256 && m->gru_tc) {
+            rc = launch_gru_tc(s, xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T);
+        } else if (H == 256) {
             p.Bc = pick_bc(B, 148 / 4);
             rc = launch_gru_t<256, 4>(s, p, (B + p.Bc - 1) / p.Bc);
         } else {

@@ -13,7 +13,9 @@
 // Operands are fp32 in HBM; the tensor maps use the TFLOAT32 element type so the TMA engine hands the
 // tensor core tf32 values; accumulation is fp32.  Parity of the whole path with TF32 contractions is
 // checked end to end (tests/test_gpu_parity.py, RMS <= 1e-4 vs the fp32 oracle).
+#include <cooperative_groups.h>
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "dfb_common.cuh"
 #include "dfb_dwpw.cuh"
@@ -388,6 +390,257 @@ template int launch_dwpw_tc<DW_S1>(cudaStream_t, DwPwParams, const float *, int)
 template int launch_dwpw_tc<DW_S2>(cudaStream_t, DwPwParams, const float *, int);
 template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int);
 template int launch_dwpw_tc<DW_DF0>(cudaStream_t, DwPwParams, const float *, int);
+
+// ================================================================ tensor-core GRU recurrence ====
+// torch.nn.GRU cell (DeepFilterNet/df/modules.py:684,723), hidden size 256.  A cluster of 8 CTAs owns
+// up to 16 streams for the whole sequence.  CTA `rank` keeps the W_hh rows of its 32 hidden units
+// (3 gates x 32 rows x 256) in SHARED MEMORY as a BF16 hi/lo split (W = hi + lo to ~2^-17), UMMA
+// K-major 128B-swizzle layout; the hidden state of the group is the B operand ([16 streams][256],
+// also BF16 hi/lo).  Per time step one thread issues 48 tcgen05.mma (M128 N16 K16, kind::f16:
+// hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM); four warps read the pre-activations from TMEM,
+// apply the gates in fp32 and broadcast the new hidden state with st.async DSMEM stores that
+// complete bytes on every peer's mbarrier (no cluster barrier, no fence on the step's critical path).
+// The fp32 hidden state of a CTA's own units stays in registers; only the MMA operand is split BF16.
+namespace cg = cooperative_groups;
+
+constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtN = 16, kGtRows = 3 * kGtU, kGtThreads = 160;
+
+struct GruTcSmem {
+    alignas(1024) unsigned char w[2][4][kGtRows * 128];   // [hi|lo][k chunk of 64][96 rows x 128 B]
+    alignas(1024) unsigned char h[2][2][4][kGtN * 128];   // [buffer][hi|lo][k chunk][16 rows x 128 B]
+    float pre[3][kGtU][kGtN + 1];
+    alignas(8) uint64_t bar_h[2];
+    uint64_t t_full;
+    uint32_t tmem_base;
+};
+
+struct GruTcParams {
+    const float *xproj;  // [B,T,3H]
+    const float *whh;    // [3H][H]
+    const float *bhh;    // [3H]
+    const float *res;    // optional [B,T,H], added to the OUTPUT only
+    float *hout;         // [B,T,H]
+    int B, T, Bc;
+};
+
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_b32(uint32_t dst, uint32_t v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst), "r"(v), "r"(mbar) : "memory");
+}
+// x = hi + lo with hi, lo bf16 (round to nearest); returns them as the low/high half of a u32 pair
+__device__ __forceinline__ void bf16_split(float x, unsigned short &hi, unsigned short &lo) {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+}
+__device__ __forceinline__ float gt_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    GruTcSmem &sm = *reinterpret_cast<GruTcSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int group = blockIdx.x / kGtC;
+    const int b0 = group * p.Bc;
+    const int nb = min(p.Bc, p.B - b0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = kGtH, T = p.T;
+    // ---- W_hh slice -> BF16 hi/lo, swizzled K-major (row rho = gate * 32 + unit)
+    for (int i = tid; i < kGtRows * (H / 8); i += kGtThreads) {  // (row, 16-byte chunk of 8 elements)
+        const int rho = i / (H / 8), j8 = i - rho * (H / 8);     // j8 in [0, 32): elements [8 j8, 8 j8 + 8)
+        const int g = rho / kGtU, u = rho - g * kGtU;
+        const float *src = p.whh + ((int64_t)g * H + rank * kGtU + u) * H + j8 * 8;
+        float4 x0 = *reinterpret_cast<const float4 *>(src), x1 = *reinterpret_cast<const float4 *>(src + 4);
+        float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        unsigned short hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) bf16_split(xv[e], hi[e], lo[e]);
+        uint4 vh = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16, hi[6] | (uint32_t)hi[7] << 16);
+        uint4 vl = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16, lo[6] | (uint32_t)lo[7] << 16);
+        const int c = j8 >> 3, j = j8 & 7;
+        *reinterpret_cast<uint4 *>(sm.w[0][c] + sw128_off(rho, j)) = vh;
+        *reinterpret_cast<uint4 *>(sm.w[1][c] + sw128_off(rho, j)) = vl;
+    }
+    for (int i = tid; i < (int)sizeof(sm.h) / 16; i += kGtThreads) reinterpret_cast<uint4 *>(&sm.h[0][0][0][0])[i] = make_uint4(0, 0, 0, 0);  // h0 = 0
+    if (tid == 0) {
+        mbar_init(&sm.bar_h[0], 1);
+        mbar_init(&sm.bar_h[1], 1);
+        mbar_init(&sm.t_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 32);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote store
+    const uint32_t tmem = sm.tmem_base;
+    const uint32_t step_bytes = (uint32_t)(nb * H * 4);  // hi + lo, 2 bytes each, per stream and unit
+
+    if (warp == 4) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, kGtN);
+            for (int t = 0; t < T; t++) {
+                const int cur = t & 1;
+                if (t + 1 < T) mbar_expect_tx(&sm.bar_h[cur ^ 1], step_bytes);
+                if (t > 0) mbar_wait(&sm.bar_h[cur], (uint32_t)(((t - 1) >> 1) & 1));
+                fence_proxy_async();
+                tc_fence_after();
+                bool first = true;
+#pragma unroll
+                for (int combo = 0; combo < 3; combo++) {
+                    const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t a0 = smem_u32(sm.w[wa][c]), bb = smem_u32(sm.h[cur][hb][c]);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            umma_bf16(tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(bb + k * 32), idesc, first ? 0u : 1u);
+                            first = false;
+                        }
+                    }
+                }
+                umma_commit(&sm.t_full);
+            }
+        }
+    } else {
+        // ================================================================= gate warps (0-3)
+        // item = (unit pair up, stream s): tid -> up = tid % 16, s = tid / 16 + 8 j
+        const int up = tid & 15;
+        const int gu = rank * kGtU + 2 * up;       // first of the two global hidden units of this thread
+        float hprev[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        const float2 bhr = *reinterpret_cast<const float2 *>(p.bhh + gu), bhz = *reinterpret_cast<const float2 *>(p.bhh + H + gu),
+                     bhn = *reinterpret_cast<const float2 *>(p.bhh + 2 * H + gu);
+        // destination byte offset of this unit pair inside an h sub-tile row: chunk c = gu / 64
+        const int hc = gu >> 6, kk = gu & 63;
+        const uint32_t bar_local[2] = {smem_u32(&sm.bar_h[0]), smem_u32(&sm.bar_h[1])};
+        for (int t = 0; t < T; t++) {
+            const int cur = t & 1;
+            float2 xr[2], xz[2], xn[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int s = (tid >> 4) + 8 * j;
+                if (s < nb) {
+                    const float *xp = p.xproj + ((int64_t)(b0 + s) * T + t) * (3 * H) + gu;
+                    xr[j] = *reinterpret_cast<const float2 *>(xp);
+                    xz[j] = *reinterpret_cast<const float2 *>(xp + H);
+                    xn[j] = *reinterpret_cast<const float2 *>(xp + 2 * H);
+                }
+            }
+            mbar_wait(&sm.t_full, (uint32_t)(t & 1));
+            tc_fence_after();
+            if (warp < 3) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+                for (int s = 0; s < kGtN; s++) sm.pre[warp][lane][s] = v[s];
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four gate warps only
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int s = (tid >> 4) + 8 * j;
+                if (s < nb) {
+                    float hn[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int u = 2 * up + e;
+                        const float r = gt_sigmoid((e ? xr[j].y : xr[j].x) + sm.pre[0][u][s] + (e ? bhr.y : bhr.x));
+                        const float z = gt_sigmoid((e ? xz[j].y : xz[j].x) + sm.pre[1][u][s] + (e ? bhz.y : bhz.x));
+                        const float n = tanhf((e ? xn[j].y : xn[j].x) + r * (sm.pre[2][u][s] + (e ? bhn.y : bhn.x)));
+                        hn[e] = (1.f - z) * n + z * hprev[j][e];
+                        hprev[j][e] = hn[e];
+                    }
+                    const int64_t o = ((int64_t)(b0 + s) * T + t) * H + gu;
+                    float2 ov = make_float2(hn[0], hn[1]);
+                    if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
+                    *reinterpret_cast<float2 *>(p.hout + o) = ov;
+                    if (t + 1 < T) {
+                        unsigned short h0, l0, h1, l1;
+                        bf16_split(hn[0], h0, l0);
+                        bf16_split(hn[1], h1, l1);
+                        const uint32_t vhi = h0 | (uint32_t)h1 << 16, vlo = l0 | (uint32_t)l1 << 16;
+                        const uint32_t off = sw128_off(s, kk >> 3) + (kk & 7) * 2;
+                        const uint32_t dhi = smem_u32(sm.h[cur ^ 1][0][hc]) + off, dlo = smem_u32(sm.h[cur ^ 1][1][hc]) + off;
+#pragma unroll
+                        for (int c = 0; c < kGtC; c++) {
+                            const uint32_t bar = mapa_u32(bar_local[cur ^ 1], c);
+                            st_async_b32(mapa_u32(dhi, c), vhi, bar);
+                            st_async_b32(mapa_u32(dlo, c), vlo, bar);
+                        }
+                    }
+                }
+            }
+            // sm.pre is rewritten only after the next t_full, i.e. after every CTA's sends of this step
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster.sync();  // no CTA exits while peers may still address its shared memory
+    if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
+                  int B, int T) {
+    static bool attr_done = false;
+    const int smem = (int)sizeof(GruTcSmem) + 1024;
+    if (!attr_done) {
+        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    GruTcParams p{xproj, whh, bhh, res, hout, B, T, 0};
+    // streams per cluster: fill the cluster's N = 16 columns, but spread small batches over more SMs
+    int bc = (B + 17) / 18;  // 18 clusters of 8 CTAs = 144 SMs
+    if (bc < 4) bc = 4;
+    if (bc > kGtN) bc = kGtN;
+    p.Bc = bc;
+    const int ngroups = (B + bc - 1) / bc;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(ngroups * kGtC));
+    cfg.blockDim = dim3(kGtThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kGtC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    DFB_PROF("k_gru_tc", s);
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc, p));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return DFB_OK;
+}
 
 // ------------------------------------------------------------------------------- host side ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

@@ -109,7 +109,7 @@ class DfNet(nn.Module):
 
     def set_precision(self, mode: str) -> None:
         """'fp32': IEEE fp32 FFMA everywhere; 'tf32': tcgen05 TF32 tensor cores for the dense contractions."""
-        check(_lib.lib().dfb_model_set_precision(self._h, {"fp32": 0, "tf32": 1}[mode]))
+        check(_lib.lib().dfb_model_set_precision(self._h, {"fp32": 0, "tf32": 1, "fp32+gru_tc": 2, "tf32+gru_tc": 3}[mode]))
         self.precision = mode
 
     def __del__(self):

@@ -169,6 +169,9 @@ int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad);
 /* Arithmetic of the dense contractions (GRU input projections, 1x1 convs): 0 = IEEE fp32 FFMA,
  * 1 = TF32 tensor cores (tcgen05, fp32 accumulate).  Everything else is always fp32. */
 int dfb_model_set_precision(dfb_model *m, int mode);
+/* Debug aid: steps > 0 with h_out == NULL arms clock64() phase stamps ([steps][8]) for the following
+ * GRU launches; a second call with h_out != NULL copies the stamps of the last launch and disarms. */
+int dfb_debug_gru_timing(dfb_model *m, int steps, long long *h_out);
 /* Debug aid for parity tests: copies the named activation of the LAST forward pass on this handle
  * (e0,e1,e2,e3,c0,c1,emb_in,emb,dec_emb,d3,d2,d1,dfc) to the host; returns the element count
  * (or a negative dfb_status).  Valid until the next call on the handle. */

@@ -1,0 +1,31 @@
+"""Prints the per-phase clock64 timeline of the GRU kernel (CTA 0) -- run on the GPU box."""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from deepfilternet_b200 import DfNet, _lib, enhance_device, libdf
+from deepfilternet_b200.config import ModelConfig
+from deepfilternet_b200.weights import random_state_dict
+from tests_common import synth_audio
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+cfg = ModelConfig(model="deepfilternet3", conv_ch=64, conv_lookahead=2, df_lookahead=2, emb_num_layers=3, df_num_layers=2,
+                  lin_groups=16, enc_lin_groups=32, df_gru_skip="groupedlinear", df_pathway_kernel_size_t=5)
+st = libdf.DF(48000, 960, 480, 32, 2)
+model = DfNet(cfg, random_state_dict(cfg, 0), st)
+audio = synth_audio(B, 48000 * 2, device="cuda")
+enhance_device(model, st, audio); torch.cuda.synchronize()
+T = (48000 * 2 + 960) // 480
+L = _lib.lib()
+L.dfb_debug_gru_timing(model.handle, T, None)
+enhance_device(model, st, audio); torch.cuda.synchronize()
+buf = np.zeros((T, 8), dtype=np.int64)
+L.dfb_debug_gru_timing(model.handle, T, buf.ctypes.data)
+d = buf[20:180]
+names = ["wait h", "matvec", "reduce+store", "cta barrier", "gates+send", "loop tail"]
+step = np.diff(d[:, 0])
+print(f"B={B}  cycles/step median {np.median(step):.0f}  mean {step.mean():.0f}")
+for i, n in enumerate(names[:5]):
+    seg = d[:, i + 1] - d[:, i]
+    print(f"  {n:14s} median {np.median(seg):7.0f}  mean {seg.mean():7.0f}  max {seg.max():7.0f}")
+seg = d[1:, 0] - d[:-1, 5]
+print(f"  {'loop tail':14s} median {np.median(seg):7.0f}")
