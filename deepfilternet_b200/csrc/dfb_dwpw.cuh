@@ -8,6 +8,22 @@ namespace dfb {
 
 constexpr int kCh = 64;  // conv_ch of every shipped model
 
+// packed fp32x2 FMA (Blackwell FFMA2): d = a * b + c on both halves.  A scalar operand packed as
+// (x, x) is turned into the broadcast operand form by ptxas, so it costs no extra instruction.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 enum DwMode { DW_S1 = 0, DW_S2 = 1, DW_T2 = 2, DW_DF0 = 3 };
 constexpr int kLdA = kCh + 4;  // padded row stride of the A tile (floats)
 

@@ -396,18 +396,23 @@ template int launch_dwpw_tc<DW_DF0>(cudaStream_t, DwPwParams, const float *, int
 // up to 16 streams for the whole sequence.  CTA `rank` keeps the W_hh rows of its 32 hidden units
 // (3 gates x 32 rows x 256) in SHARED MEMORY as a BF16 hi/lo split (W = hi + lo to ~2^-17), UMMA
 // K-major 128B-swizzle layout; the hidden state of the group is the B operand ([16 streams][256],
-// also BF16 hi/lo).  Per time step one thread issues 48 tcgen05.mma (M128 N16 K16, kind::f16:
-// hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM); four warps read the pre-activations from TMEM,
-// apply the gates in fp32 and broadcast the new hidden state with st.async DSMEM stores that
-// complete bytes on every peer's mbarrier (no cluster barrier, no fence on the step's critical path).
-// The fp32 hidden state of a CTA's own units stays in registers; only the MMA operand is split BF16.
+// also BF16 hi/lo, K-major core-matrix layout without swizzle so that a CTA's 32 units form two
+// contiguous 512-byte pieces).  Per time step one thread issues 48 tcgen05.mma (M128 N16 K16,
+// kind::f16: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM); eight warps read the pre-activations
+// from TMEM, apply the gates in fp32, write the CTA's slice of the new state into its own operand
+// buffer and broadcast it with bulk DSMEM copies (cp.async.bulk shared::cta -> shared::cluster)
+// that complete bytes on each peer's mbarrier -- no cluster barrier or fence on the step's critical
+// path.  The fp32 hidden state of a CTA's own units stays in registers; only the MMA operand is BF16.
 namespace cg = cooperative_groups;
 
-constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtN = 16, kGtRows = 3 * kGtU, kGtThreads = 160;
+constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtN = 16, kGtRows = 3 * kGtU;
+constexpr int kGtGateThreads = 256, kGtThreads = kGtGateThreads + 32;
+constexpr int kGtHPiece = 4 * 128;            // one CTA's units in one 8-stream row group: 4 core matrices
+constexpr int kGtHSbo = (kGtH / 8) * 128;     // row-group stride of the h operand (32 core matrices)
 
 struct GruTcSmem {
-    alignas(1024) unsigned char w[2][4][kGtRows * 128];   // [hi|lo][k chunk of 64][96 rows x 128 B]
-    alignas(1024) unsigned char h[2][2][4][kGtN * 128];   // [buffer][hi|lo][k chunk][16 rows x 128 B]
+    alignas(1024) unsigned char w[2][4][kGtRows * 128];   // [hi|lo][k chunk of 64][96 rows x 128 B], SW128
+    alignas(1024) unsigned char h[2][2][2 * kGtHSbo];     // [buffer][hi|lo][row group][k core matrix][8 rows x 16 B]
     float pre[3][kGtU][kGtN + 1];
     alignas(8) uint64_t bar_h[2];
     uint64_t t_full;
@@ -425,6 +430,16 @@ struct GruTcParams {
 
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// K-major operand without swizzle: 8 x 16 B core matrices, LBO = stride between K-adjacent core
+// matrices, SBO = stride between 8-row groups (cute/arch/mma_sm100_desc.hpp, LayoutType::SWIZZLE_NONE)
+__device__ __forceinline__ uint64_t umma_desc_interleave(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -453,17 +468,22 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_async_b32(uint32_t dst, uint32_t v, uint32_t mbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst), "r"(v), "r"(mbar) : "memory");
+// bulk copy own shared memory -> a peer CTA's shared memory, completing `bytes` on the peer's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+                 "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+                 : "memory");
 }
-// x = hi + lo with hi, lo bf16 (round to nearest); returns them as the low/high half of a u32 pair
+// x = hi + lo with hi, lo bf16 (round to nearest)
 __device__ __forceinline__ void bf16_split(float x, unsigned short &hi, unsigned short &lo) {
     __nv_bfloat16 h = __float2bfloat16_rn(x);
     __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
     hi = __bfloat16_as_ushort(h);
     lo = __bfloat16_as_ushort(l);
 }
-__device__ __forceinline__ float gt_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// gates with the MUFU exp2 / reciprocal approximations (each ~1e-7 relative)
+__device__ __forceinline__ float gt_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float gt_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
@@ -475,6 +495,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     const int nb = min(p.Bc, p.B - b0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = kGtH, T = p.T;
+    const int npiece = nb > 8 ? 2 : 1;  // 8-stream row groups that carry data
     // ---- W_hh slice -> BF16 hi/lo, swizzled K-major (row rho = gate * 32 + unit)
     for (int i = tid; i < kGtRows * (H / 8); i += kGtThreads) {  // (row, 16-byte chunk of 8 elements)
         const int rho = i / (H / 8), j8 = i - rho * (H / 8);     // j8 in [0, 32): elements [8 j8, 8 j8 + 8)
@@ -491,10 +512,10 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
         *reinterpret_cast<uint4 *>(sm.w[0][c] + sw128_off(rho, j)) = vh;
         *reinterpret_cast<uint4 *>(sm.w[1][c] + sw128_off(rho, j)) = vl;
     }
-    for (int i = tid; i < (int)sizeof(sm.h) / 16; i += kGtThreads) reinterpret_cast<uint4 *>(&sm.h[0][0][0][0])[i] = make_uint4(0, 0, 0, 0);  // h0 = 0
+    for (int i = tid; i < (int)sizeof(sm.h) / 16; i += kGtThreads) reinterpret_cast<uint4 *>(&sm.h[0][0][0])[i] = make_uint4(0, 0, 0, 0);  // h0 = 0
     if (tid == 0) {
-        mbar_init(&sm.bar_h[0], 1);
-        mbar_init(&sm.bar_h[1], 1);
+        mbar_init(&sm.bar_h[0], 2);   // MMA thread's expect_tx arrive + one gate-warp arrive (own slice written)
+        mbar_init(&sm.bar_h[1], 2);
         mbar_init(&sm.t_full, 1);
         fence_barrier_init();
     }
@@ -503,11 +524,11 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote store
+    cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t step_bytes = (uint32_t)(nb * H * 4);  // hi + lo, 2 bytes each, per stream and unit
+    const uint32_t step_bytes = (uint32_t)((kGtC - 1) * 2 * npiece * kGtHPiece);  // from the 7 peers: hi + lo pieces
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ================================================================= MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, kGtN);
@@ -521,12 +542,14 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
 #pragma unroll
                 for (int combo = 0; combo < 3; combo++) {
                     const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
+                    const uint32_t hbase = smem_u32(sm.h[cur][hb]);
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        const uint32_t a0 = smem_u32(sm.w[wa][c]), bb = smem_u32(sm.h[cur][hb][c]);
+                        const uint32_t a0 = smem_u32(sm.w[wa][c]);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            umma_bf16(tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(bb + k * 32), idesc, first ? 0u : 1u);
+                        for (int k = 0; k < 4; k++) {  // K step of 16 = two core matrices of the h operand
+                            umma_bf16(tmem, umma_desc_sw128(a0 + k * 32),
+                                      umma_desc_interleave(hbase + (c * 8 + k * 2) * 128, 128, kGtHSbo), idesc, first ? 0u : 1u);
                             first = false;
                         }
                     }
@@ -535,28 +558,25 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             }
         }
     } else {
-        // ================================================================= gate warps (0-3)
-        // item = (unit pair up, stream s): tid -> up = tid % 16, s = tid / 16 + 8 j
-        const int up = tid & 15;
+        // ================================================================= gate warps (0-7)
+        // one item per thread: unit pair up = tid % 16 (units 2 up, 2 up + 1 of this CTA), stream s = tid / 16
+        const int up = tid & 15, s = tid >> 4;
+        const bool active = s < nb;
         const int gu = rank * kGtU + 2 * up;       // first of the two global hidden units of this thread
-        float hprev[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        float hprev0 = 0.f, hprev1 = 0.f;
         const float2 bhr = *reinterpret_cast<const float2 *>(p.bhh + gu), bhz = *reinterpret_cast<const float2 *>(p.bhh + H + gu),
                      bhn = *reinterpret_cast<const float2 *>(p.bhh + 2 * H + gu);
-        // destination byte offset of this unit pair inside an h sub-tile row: chunk c = gu / 64
-        const int hc = gu >> 6, kk = gu & 63;
-        const uint32_t bar_local[2] = {smem_u32(&sm.bar_h[0]), smem_u32(&sm.bar_h[1])};
+        // byte offset of this (stream, unit pair) inside an h operand: row group s / 8, core matrix gu / 8
+        const uint32_t hoff = (uint32_t)((s >> 3) * kGtHSbo + (gu >> 3) * 128 + (s & 7) * 16 + (gu & 7) * 2);
+        const uint32_t piece0 = (uint32_t)(rank * kGtHPiece);  // this CTA's slice inside row group 0
         for (int t = 0; t < T; t++) {
             const int cur = t & 1;
-            float2 xr[2], xz[2], xn[2];
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int s = (tid >> 4) + 8 * j;
-                if (s < nb) {
-                    const float *xp = p.xproj + ((int64_t)(b0 + s) * T + t) * (3 * H) + gu;
-                    xr[j] = *reinterpret_cast<const float2 *>(xp);
-                    xz[j] = *reinterpret_cast<const float2 *>(xp + H);
-                    xn[j] = *reinterpret_cast<const float2 *>(xp + 2 * H);
-                }
+            float2 xr = make_float2(0.f, 0.f), xz = xr, xn = xr;
+            if (active) {
+                const float *xp = p.xproj + ((int64_t)(b0 + s) * T + t) * (3 * H) + gu;
+                xr = *reinterpret_cast<const float2 *>(xp);
+                xz = *reinterpret_cast<const float2 *>(xp + H);
+                xn = *reinterpret_cast<const float2 *>(xp + 2 * H);
             }
             mbar_wait(&sm.t_full, (uint32_t)(t & 1));
             tc_fence_after();
@@ -564,46 +584,46 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                 float v[16];
                 tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
 #pragma unroll
-                for (int s = 0; s < kGtN; s++) sm.pre[warp][lane][s] = v[s];
+                for (int ss = 0; ss < kGtN; ss++) sm.pre[warp][lane][ss] = v[ss];
             }
             tc_fence_before();
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four gate warps only
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int s = (tid >> 4) + 8 * j;
-                if (s < nb) {
-                    float hn[2];
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int u = 2 * up + e;
-                        const float r = gt_sigmoid((e ? xr[j].y : xr[j].x) + sm.pre[0][u][s] + (e ? bhr.y : bhr.x));
-                        const float z = gt_sigmoid((e ? xz[j].y : xz[j].x) + sm.pre[1][u][s] + (e ? bhz.y : bhz.x));
-                        const float n = tanhf((e ? xn[j].y : xn[j].x) + r * (sm.pre[2][u][s] + (e ? bhn.y : bhn.x)));
-                        hn[e] = (1.f - z) * n + z * hprev[j][e];
-                        hprev[j][e] = hn[e];
-                    }
-                    const int64_t o = ((int64_t)(b0 + s) * T + t) * H + gu;
-                    float2 ov = make_float2(hn[0], hn[1]);
-                    if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
-                    *reinterpret_cast<float2 *>(p.hout + o) = ov;
-                    if (t + 1 < T) {
-                        unsigned short h0, l0, h1, l1;
-                        bf16_split(hn[0], h0, l0);
-                        bf16_split(hn[1], h1, l1);
-                        const uint32_t vhi = h0 | (uint32_t)h1 << 16, vlo = l0 | (uint32_t)l1 << 16;
-                        const uint32_t off = sw128_off(s, kk >> 3) + (kk & 7) * 2;
-                        const uint32_t dhi = smem_u32(sm.h[cur ^ 1][0][hc]) + off, dlo = smem_u32(sm.h[cur ^ 1][1][hc]) + off;
-#pragma unroll
-                        for (int c = 0; c < kGtC; c++) {
-                            const uint32_t bar = mapa_u32(bar_local[cur ^ 1], c);
-                            st_async_b32(mapa_u32(dhi, c), vhi, bar);
-                            st_async_b32(mapa_u32(dlo, c), vlo, bar);
-                        }
-                    }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight gate warps only
+            if (active) {
+                const int u0 = 2 * up;
+                const float r0 = gt_sigmoid(xr.x + sm.pre[0][u0][s] + bhr.x), r1 = gt_sigmoid(xr.y + sm.pre[0][u0 + 1][s] + bhr.y);
+                const float z0 = gt_sigmoid(xz.x + sm.pre[1][u0][s] + bhz.x), z1 = gt_sigmoid(xz.y + sm.pre[1][u0 + 1][s] + bhz.y);
+                const float n0 = gt_tanh(xn.x + r0 * (sm.pre[2][u0][s] + bhn.x)), n1 = gt_tanh(xn.y + r1 * (sm.pre[2][u0 + 1][s] + bhn.y));
+                hprev0 = (1.f - z0) * n0 + z0 * hprev0;
+                hprev1 = (1.f - z1) * n1 + z1 * hprev1;
+                const int64_t o = ((int64_t)(b0 + s) * T + t) * H + gu;
+                float2 ov = make_float2(hprev0, hprev1);
+                if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
+                *reinterpret_cast<float2 *>(p.hout + o) = ov;
+                if (t + 1 < T) {
+                    unsigned short h0, l0, h1, l1;
+                    bf16_split(hprev0, h0, l0);
+                    bf16_split(hprev1, h1, l1);
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1][0] + hoff) = h0 | (uint32_t)h1 << 16;
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1][1] + hoff) = l0 | (uint32_t)l1 << 16;
                 }
             }
-            // sm.pre is rewritten only after the next t_full, i.e. after every CTA's sends of this step
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t + 1 < T) {
+                fence_proxy_async();  // own slice (generic stores) -> visible to the bulk-copy / tensor-core proxy
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 0) {
+                    if (lane == 0) mbar_arrive(&sm.bar_h[cur ^ 1]);  // own slice is in place
+                    // lanes 0..27: (peer among the 7 others, hi|lo, row group) -> one 512-byte bulk copy each
+                    const int pi = lane >> 2, hl = (lane >> 1) & 1, ng = lane & 1;
+                    if (pi < kGtC - 1 && ng < npiece) {
+                        const int peer = pi + (pi >= rank ? 1 : 0);
+                        const uint32_t src = smem_u32(sm.h[cur ^ 1][hl]) + ng * kGtHSbo + piece0;
+                        dsmem_bulk_copy(mapa_u32(src, peer), src, kGtHPiece, mapa_u32(smem_u32(&sm.bar_h[cur ^ 1]), peer));
+                    }
+                }
+            } else {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            // sm.pre is rewritten only after the next t_full, i.e. after every CTA's copies of this step
         }
     }
     tc_fence_before();
