@@ -128,11 +128,11 @@ __global__ void __launch_bounds__(256) k_dwpw(DwPwParams p) {
     const int RG = Rfull >> 2;
     const int cgid = tid & 7, rg = tid >> 3;
     if (rg >= RG) return;
-    unsigned long long acc2[4][4];  // [row][column pair]
+    float acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc2[i][j] = 0ull;
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
 #pragma unroll 4
     for (int k = 0; k < kCh; k += 4) {
         float4 a[4];
@@ -140,24 +140,16 @@ __global__ void __launch_bounds__(256) k_dwpw(DwPwParams p) {
         for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(As + (rg + RG * i) * kLdA + k);
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(Ws + (k + kk) * kCh + cgid * 8);
-            const float4 w1 = *reinterpret_cast<const float4 *>(Ws + (k + kk) * kCh + cgid * 8 + 4);
-            const unsigned long long wp0 = f2_pack(w0.x, w0.y), wp1 = f2_pack(w0.z, w0.w), wp2 = f2_pack(w1.x, w1.y),
-                                     wp3 = f2_pack(w1.z, w1.w);
+            float4 w0 = *reinterpret_cast<const float4 *>(Ws + (k + kk) * kCh + cgid * 8);
+            float4 w1 = *reinterpret_cast<const float4 *>(Ws + (k + kk) * kCh + cgid * 8 + 4);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-                const unsigned long long ap = f2_pack(av, av);
-                acc2[i][0] = f2_fma(ap, wp0, acc2[i][0]); acc2[i][1] = f2_fma(ap, wp1, acc2[i][1]);
-                acc2[i][2] = f2_fma(ap, wp2, acc2[i][2]); acc2[i][3] = f2_fma(ap, wp3, acc2[i][3]);
+                float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                acc[i][0] += av * w0.x; acc[i][1] += av * w0.y; acc[i][2] += av * w0.z; acc[i][3] += av * w0.w;
+                acc[i][4] += av * w1.x; acc[i][5] += av * w1.y; acc[i][6] += av * w1.z; acc[i][7] += av * w1.w;
             }
         }
     }
-    float acc[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) f2_unpack(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
     const float4 b0 = *reinterpret_cast<const float4 *>(p.bias + cgid * 8);
     const float4 b1 = *reinterpret_cast<const float4 *>(p.bias + cgid * 8 + 4);
 #pragma unroll
@@ -202,9 +194,11 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
     const int64_t m0 = (int64_t)blockIdx.x * kGlBM;
     const int tid = threadIdx.x;
     const int tc = tid & 15, tr = tid >> 4;  // thread tile: rows tr + 16 i, cols 4 tc .. 4 tc + 3
-    unsigned long long acc2[4][2];  // [row][column pair]
+    float acc[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) acc2[i][0] = acc2[i][1] = 0ull;
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
     const float *xg = p.x + (int64_t)g * p.Ig;
     const float *wg = p.w + (int64_t)g * p.Ig * p.Hg;
     for (int k0 = 0; k0 < p.Ig; k0 += kGlBK) {
@@ -230,24 +224,15 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
             for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(&As[tr + 16 * i][k]);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
-                const float4 w = *reinterpret_cast<const float4 *>(&Ws[k + kk][tc * 4]);
-                const unsigned long long wp0 = f2_pack(w.x, w.y), wp1 = f2_pack(w.z, w.w);
+                float4 w = *reinterpret_cast<const float4 *>(&Ws[k + kk][tc * 4]);
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-                    const unsigned long long ap = f2_pack(av, av);
-                    acc2[i][0] = f2_fma(ap, wp0, acc2[i][0]);
-                    acc2[i][1] = f2_fma(ap, wp1, acc2[i][1]);
+                    float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                    acc[i][0] += av * w.x; acc[i][1] += av * w.y; acc[i][2] += av * w.z; acc[i][3] += av * w.w;
                 }
             }
         }
         __syncthreads();
-    }
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        f2_unpack(acc2[i][0], acc[i][0], acc[i][1]);
-        f2_unpack(acc2[i][1], acc[i][2], acc[i][3]);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -833,7 +818,7 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         float *dst = (l == layers - 1) ? y : tmp_h;
         GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, 0, m->gru_dbg};
         if (H == 256 && m->gru_tc) {
-            rc = launch_gru_tc(s, xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T);
+            rc = launch_gru_tc(s, xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, m->gru_dbg);
         } else if (H == 256) {
             p.Bc = pick_bc(B, 148 / 4);
             rc = launch_gru_t<256, 4>(s, p, (B + p.Bc - 1) / p.Bc);

@@ -426,6 +426,7 @@ struct GruTcParams {
     const float *res;    // optional [B,T,H], added to the OUTPUT only
     float *hout;         // [B,T,H]
     int B, T, Bc;
+    long long *dbg;      // optional [T][8] clock64 stamps of CTA 0 (0-3: MMA thread, 4-7: gate thread 0)
 };
 
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
@@ -532,28 +533,41 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
         // ================================================================= MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, kGtN);
+            // descriptors are address + constant bits: build the bases once, step with integer adds
+            uint64_t adesc[2][4], bdesc[2][2];
+#pragma unroll
+            for (int wa = 0; wa < 2; wa++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) adesc[wa][c] = umma_desc_sw128(smem_u32(sm.w[wa][c]));
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int hb = 0; hb < 2; hb++) bdesc[b][hb] = umma_desc_interleave(smem_u32(sm.h[b][hb]), 128, kGtHSbo);
+            const bool dbg_on = p.dbg && blockIdx.x == 0;
             for (int t = 0; t < T; t++) {
                 const int cur = t & 1;
+                if (dbg_on) p.dbg[t * 8 + 0] = clock64();
                 if (t + 1 < T) mbar_expect_tx(&sm.bar_h[cur ^ 1], step_bytes);
                 if (t > 0) mbar_wait(&sm.bar_h[cur], (uint32_t)(((t - 1) >> 1) & 1));
+                if (dbg_on) p.dbg[t * 8 + 1] = clock64();
                 fence_proxy_async();
                 tc_fence_after();
                 bool first = true;
 #pragma unroll
                 for (int combo = 0; combo < 3; combo++) {
                     const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
-                    const uint32_t hbase = smem_u32(sm.h[cur][hb]);
+                    const uint64_t bb = cur ? bdesc[1][hb] : bdesc[0][hb];
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        const uint32_t a0 = smem_u32(sm.w[wa][c]);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {  // K step of 16 = two core matrices of the h operand
-                            umma_bf16(tmem, umma_desc_sw128(a0 + k * 32),
-                                      umma_desc_interleave(hbase + (c * 8 + k * 2) * 128, 128, kGtHSbo), idesc, first ? 0u : 1u);
+                        for (int k = 0; k < 4; k++) {  // K step of 16: 32 B of the W row, two core matrices of h
+                            umma_bf16(tmem, adesc[wa][c] + (uint64_t)(k * 2), bb + (uint64_t)((c * 8 + k * 2) * 8), idesc,
+                                      first ? 0u : 1u);
                             first = false;
                         }
                     }
                 }
+                if (dbg_on) p.dbg[t * 8 + 2] = clock64();
                 umma_commit(&sm.t_full);
             }
         }
@@ -578,7 +592,10 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                 xz = *reinterpret_cast<const float2 *>(xp + H);
                 xn = *reinterpret_cast<const float2 *>(xp + 2 * H);
             }
+            const bool gdbg = p.dbg && blockIdx.x == 0 && tid == 0;
+            if (gdbg) p.dbg[t * 8 + 4] = clock64();
             mbar_wait(&sm.t_full, (uint32_t)(t & 1));
+            if (gdbg) p.dbg[t * 8 + 5] = clock64();
             tc_fence_after();
             if (warp < 3) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
                 float v[16];
@@ -607,6 +624,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                     *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1][1] + hoff) = l0 | (uint32_t)l1 << 16;
                 }
             }
+            if (gdbg) p.dbg[t * 8 + 6] = clock64();
             if (t + 1 < T) {
                 fence_proxy_async();  // own slice (generic stores) -> visible to the bulk-copy / tensor-core proxy
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -623,6 +641,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             } else {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
+            if (gdbg) p.dbg[t * 8 + 7] = clock64();
             // sm.pre is rewritten only after the next t_full, i.e. after every CTA's copies of this step
         }
     }
@@ -633,14 +652,14 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
 }
 
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
-                  int B, int T) {
+                  int B, int T, long long *dbg) {
     static bool attr_done = false;
     const int smem = (int)sizeof(GruTcSmem) + 1024;
     if (!attr_done) {
         DFB_CUDA(cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    GruTcParams p{xproj, whh, bhh, res, hout, B, T, 0};
+    GruTcParams p{xproj, whh, bhh, res, hout, B, T, 0, dbg};
     // streams per cluster: fill the cluster's N = 16 columns, but spread small batches over more SMs
     int bc = (B + 17) / 18;  // 18 clusters of 8 CTAs = 144 SMs
     if (bc < 4) bc = 4;

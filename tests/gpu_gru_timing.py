@@ -21,6 +21,15 @@ enhance_device(model, st, audio); torch.cuda.synchronize()
 buf = np.zeros((T, 8), dtype=np.int64)
 L.dfb_debug_gru_timing(model.handle, T, buf.ctypes.data)
 d = buf[20:180]
+if os.environ.get("DFB_PRECISION", "").endswith("gru_tc"):
+    step = np.diff(d[:, 0])
+    print(f"TC GRU B={B}  cycles/step median {np.median(step):.0f}")
+    for a, b_, n in [(0, 1, "mma: wait h"), (1, 2, "mma: issue 48"), (4, 5, "gate: wait t_full"), (5, 6, "gate: ld+gates+write"), (6, 7, "gate: fence+bar+copy")]:
+        seg = d[:, b_] - d[:, a]
+        print(f"  {n:22s} median {np.median(seg):7.0f}  max {seg.max():7.0f}")
+    print(f"  {'mma commit -> gate saw':22s} median {np.median(d[:, 5] - d[:, 2]):7.0f}")
+    print(f"  {'gate done -> next h':22s} median {np.median(d[1:, 1] - d[:-1, 7]):7.0f}")
+    sys.exit(0)
 names = ["wait h", "matvec", "reduce+store", "cta barrier", "gates+send", "loop tail"]
 step = np.diff(d[:, 0])
 print(f"B={B}  cycles/step median {np.median(step):.0f}  mean {step.mean():.0f}")
