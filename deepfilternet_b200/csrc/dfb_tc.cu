@@ -410,8 +410,10 @@ constexpr int kGtGateThreads = 256, kGtThreads = kGtGateThreads + 32;
 constexpr int kGtHPiece = 4 * 128;            // one CTA's units in one 8-stream row group: 4 core matrices
 constexpr int kGtHSbo = (kGtH / 8) * 128;     // row-group stride of the h operand (32 core matrices)
 
+constexpr int kGtWCols = kGtH / 2;            // TMEM columns of one W plane: 2 bf16 per 32-bit column
+constexpr int kGtDCol = 2 * kGtWCols;         // accumulator columns start after W_hi | W_lo
+
 struct GruTcSmem {
-    alignas(1024) unsigned char w[2][4][kGtRows * 128];   // [hi|lo][k chunk of 64][96 rows x 128 B], SW128
     alignas(1024) unsigned char h[2][2][2 * kGtHSbo];     // [buffer][hi|lo][row group][k core matrix][8 rows x 16 B]
     float pre[3][kGtU][kGtN + 1];
     alignas(8) uint64_t bar_h[2];
@@ -450,6 +452,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand from TMEM (lane = row, one 32-bit column = two consecutive bf16 K elements), B from smem
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -497,22 +521,6 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = kGtH, T = p.T;
     const int npiece = nb > 8 ? 2 : 1;  // 8-stream row groups that carry data
-    // ---- W_hh slice -> BF16 hi/lo, swizzled K-major (row rho = gate * 32 + unit)
-    for (int i = tid; i < kGtRows * (H / 8); i += kGtThreads) {  // (row, 16-byte chunk of 8 elements)
-        const int rho = i / (H / 8), j8 = i - rho * (H / 8);     // j8 in [0, 32): elements [8 j8, 8 j8 + 8)
-        const int g = rho / kGtU, u = rho - g * kGtU;
-        const float *src = p.whh + ((int64_t)g * H + rank * kGtU + u) * H + j8 * 8;
-        float4 x0 = *reinterpret_cast<const float4 *>(src), x1 = *reinterpret_cast<const float4 *>(src + 4);
-        float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        unsigned short hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) bf16_split(xv[e], hi[e], lo[e]);
-        uint4 vh = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16, hi[6] | (uint32_t)hi[7] << 16);
-        uint4 vl = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16, lo[6] | (uint32_t)lo[7] << 16);
-        const int c = j8 >> 3, j = j8 & 7;
-        *reinterpret_cast<uint4 *>(sm.w[0][c] + sw128_off(rho, j)) = vh;
-        *reinterpret_cast<uint4 *>(sm.w[1][c] + sw128_off(rho, j)) = vl;
-    }
     for (int i = tid; i < (int)sizeof(sm.h) / 16; i += kGtThreads) reinterpret_cast<uint4 *>(&sm.h[0][0][0])[i] = make_uint4(0, 0, 0, 0);  // h0 = 0
     if (tid == 0) {
         mbar_init(&sm.bar_h[0], 2);   // MMA thread's expect_tx arrive + one gate-warp arrive (own slice written)
@@ -520,25 +528,47 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
         mbar_init(&sm.t_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, 32);
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
     const uint32_t tmem = sm.tmem_base;
+    // ---- W_hh slice -> TMEM as BF16 hi | lo planes: lane = row rho (gate * 32 + unit; lanes 96..127 zero),
+    //      column j of a plane = elements (2 j, 2 j + 1).  Warps 0-3 own lane quarters 0-3.
+    if (warp < 4) {
+        const int rho = warp * 32 + lane;
+        const int g = rho / kGtU, u = rho - g * kGtU;
+        const float *src = p.whh + ((int64_t)g * H + rank * kGtU + u) * H;
+        for (int cb = 0; cb < kGtWCols / 32; cb++) {  // 32 columns = 64 elements per store
+            uint32_t vh[32], vl[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rho < kGtRows) x = *reinterpret_cast<const float4 *>(src + cb * 64 + i * 2);
+                unsigned short h0, l0, h1, l1, h2, l2, h3, l3;
+                bf16_split(x.x, h0, l0); bf16_split(x.y, h1, l1); bf16_split(x.z, h2, l2); bf16_split(x.w, h3, l3);
+                vh[i] = h0 | (uint32_t)h1 << 16; vh[i + 1] = h2 | (uint32_t)h3 << 16;
+                vl[i] = l0 | (uint32_t)l1 << 16; vl[i + 1] = l2 | (uint32_t)l3 << 16;
+            }
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + cb * 32;
+            tmem_st32(ta, vh);
+            tmem_st32(ta + kGtWCols, vl);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
     const uint32_t step_bytes = (uint32_t)((kGtC - 1) * 2 * npiece * kGtHPiece);  // from the 7 peers: hi + lo pieces
 
     if (warp == 8) {
         // ================================================================= MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, kGtN);
-            // descriptors are address + constant bits: build the bases once, step with integer adds
-            uint64_t adesc[2][4], bdesc[2][2];
-#pragma unroll
-            for (int wa = 0; wa < 2; wa++)
-#pragma unroll
-                for (int c = 0; c < 4; c++) adesc[wa][c] = umma_desc_sw128(smem_u32(sm.w[wa][c]));
+            // B descriptors are address + constant bits: build the bases once, step with integer adds
+            uint64_t bdesc[2][2];
 #pragma unroll
             for (int b = 0; b < 2; b++)
 #pragma unroll
@@ -558,13 +588,10 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                     const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
                     const uint64_t bb = cur ? bdesc[1][hb] : bdesc[0][hb];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {  // K step of 16: 32 B of the W row, two core matrices of h
-                            umma_bf16(tmem, adesc[wa][c] + (uint64_t)(k * 2), bb + (uint64_t)((c * 8 + k * 2) * 8), idesc,
-                                      first ? 0u : 1u);
-                            first = false;
-                        }
+                    for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
+                        umma_bf16_ts(tmem + kGtDCol, tmem + wa * kGtWCols + ks * 8, bb + (uint64_t)(ks * 2 * 8), idesc,
+                                     first ? 0u : 1u);
+                        first = false;
                     }
                 }
                 if (dbg_on) p.dbg[t * 8 + 2] = clock64();
@@ -599,7 +626,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             tc_fence_after();
             if (warp < 3) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
                 float v[16];
-                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kGtDCol, v);
 #pragma unroll
                 for (int ss = 0; ss < kGtN; ss++) sm.pre[warp][lane][ss] = v[ss];
             }
@@ -612,10 +639,6 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                 const float n0 = gt_tanh(xn.x + r0 * (sm.pre[2][u0][s] + bhn.x)), n1 = gt_tanh(xn.y + r1 * (sm.pre[2][u0 + 1][s] + bhn.y));
                 hprev0 = (1.f - z0) * n0 + z0 * hprev0;
                 hprev1 = (1.f - z1) * n1 + z1 * hprev1;
-                const int64_t o = ((int64_t)(b0 + s) * T + t) * H + gu;
-                float2 ov = make_float2(hprev0, hprev1);
-                if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
-                *reinterpret_cast<float2 *>(p.hout + o) = ov;
                 if (t + 1 < T) {
                     unsigned short h0, l0, h1, l1;
                     bf16_split(hprev0, h0, l0);
@@ -641,6 +664,12 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             } else {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
+            if (active) {  // global result last: nothing on the recurrence's critical path waits for it
+                const int64_t o = ((int64_t)(b0 + s) * T + t) * H + gu;
+                float2 ov = make_float2(hprev0, hprev1);
+                if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
+                *reinterpret_cast<float2 *>(p.hout + o) = ov;
+            }
             if (gdbg) p.dbg[t * 8 + 7] = clock64();
             // sm.pre is rewritten only after the next t_full, i.e. after every CTA's copies of this step
         }
@@ -648,13 +677,15 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     tc_fence_before();
     __syncthreads();
     cluster.sync();  // no CTA exits while peers may still address its shared memory
-    if (warp == 0) tmem_dealloc(tmem, 32);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
                   int B, int T, long long *dbg) {
     static bool attr_done = false;
-    const int smem = (int)sizeof(GruTcSmem) + 1024;
+    // the kernel allocates all 512 TMEM columns (W_hh lives there), so only one CTA may be resident
+    // per SM: request more than half of the shared memory to enforce it
+    const int smem = (int)sizeof(GruTcSmem) + 1024 > 120 * 1024 ? (int)sizeof(GruTcSmem) + 1024 : 120 * 1024;
     if (!attr_done) {
         DFB_CUDA(cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
