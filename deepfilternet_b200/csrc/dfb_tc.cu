@@ -412,6 +412,8 @@ constexpr int kGtHSbo = (kGtH / 8) * 128;     // row-group stride of the h opera
 
 constexpr int kGtWCols = kGtH / 2;            // TMEM columns of one W plane: 2 bf16 per 32-bit column
 constexpr int kGtDCol = 2 * kGtWCols;         // accumulator columns start after W_hi | W_lo
+constexpr int kGtAcc = 4;                     // independent accumulators (k steps round-robin) so that
+                                              // consecutive tiny MMAs do not serialise on one TMEM tile
 
 struct GruTcSmem {
     alignas(1024) unsigned char h[2][2][2 * kGtHSbo];     // [buffer][hi|lo][row group][k core matrix][8 rows x 16 B]
@@ -582,16 +584,14 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                 if (dbg_on) p.dbg[t * 8 + 1] = clock64();
                 fence_proxy_async();
                 tc_fence_after();
-                bool first = true;
 #pragma unroll
                 for (int combo = 0; combo < 3; combo++) {
                     const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
                     const uint64_t bb = cur ? bdesc[1][hb] : bdesc[0][hb];
 #pragma unroll
                     for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
-                        umma_bf16_ts(tmem + kGtDCol, tmem + wa * kGtWCols + ks * 8, bb + (uint64_t)(ks * 2 * 8), idesc,
-                                     first ? 0u : 1u);
-                        first = false;
+                        umma_bf16_ts(tmem + kGtDCol + (ks % kGtAcc) * kGtN, tmem + wa * kGtWCols + ks * 8,
+                                     bb + (uint64_t)(ks * 2 * 8), idesc, (combo == 0 && ks < kGtAcc) ? 0u : 1u);
                     }
                 }
                 if (dbg_on) p.dbg[t * 8 + 2] = clock64();
@@ -625,8 +625,14 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             if (gdbg) p.dbg[t * 8 + 5] = clock64();
             tc_fence_after();
             if (warp < 3) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
-                float v[16];
+                float v[16], v2[16];
                 tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kGtDCol, v);
+#pragma unroll
+                for (int a = 1; a < kGtAcc; a++) {
+                    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kGtDCol + a * kGtN, v2);
+#pragma unroll
+                    for (int ss = 0; ss < kGtN; ss++) v[ss] += v2[ss];
+                }
 #pragma unroll
                 for (int ss = 0; ss < kGtN; ss++) sm.pre[warp][lane][ss] = v[ss];
             }
@@ -650,6 +656,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             if (gdbg) p.dbg[t * 8 + 6] = clock64();
             if (t + 1 < T) {
                 fence_proxy_async();  // own slice (generic stores) -> visible to the bulk-copy / tensor-core proxy
+                if (gdbg) p.dbg[t * 8 + 3] = clock64();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (warp == 0) {
                     if (lane == 0) mbar_arrive(&sm.bar_h[cur ^ 1]);  // own slice is in place
@@ -691,21 +698,27 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
         attr_done = true;
     }
     GruTcParams p{xproj, whh, bhh, res, hout, B, T, 0, dbg};
-    // streams per cluster: fill the cluster's N = 16 columns, but spread small batches over more SMs
-    int bc = (B + 17) / 18;  // 18 clusters of 8 CTAs = 144 SMs
-    if (bc < 4) bc = 4;
-    if (bc > kGtN) bc = kGtN;
-    p.Bc = bc;
-    const int ngroups = (B + bc - 1) / bc;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(ngroups * kGtC));
     cfg.blockDim = dim3(kGtThreads);
     cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kGtC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    // streams per cluster: a step costs the same for 1..16 streams, so use as few clusters as
+    // possible but never more than can be resident at once (a second wave would double the time)
+    static int max_clusters = 0;
+    if (!max_clusters) {
+        cfg.gridDim = dim3(kGtC * 64);
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, k_gru_tc, &cfg) != cudaSuccess || max_clusters < 1) max_clusters = 8;
+    }
+    int bc = (B + max_clusters - 1) / max_clusters;
+    if (bc < 8) bc = 8;
+    if (bc > kGtN) bc = kGtN;
+    p.Bc = bc;
+    const int ngroups = (B + bc - 1) / bc;
+    cfg.gridDim = dim3((unsigned)(ngroups * kGtC));
+    cfg.stream = s;
     DFB_PROF("k_gru_tc", s);
     DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc, p));
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -12,19 +12,20 @@ cfg = ModelConfig(model="deepfilternet3", conv_ch=64, conv_lookahead=2, df_looka
                   lin_groups=16, enc_lin_groups=32, df_gru_skip="groupedlinear", df_pathway_kernel_size_t=5)
 st = libdf.DF(48000, 960, 480, 32, 2)
 model = DfNet(cfg, random_state_dict(cfg, 0), st)
-audio = synth_audio(B, 48000 * 2, device="cuda")
+SEC = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+audio = synth_audio(B, 48000 * SEC, device="cuda")
 enhance_device(model, st, audio); torch.cuda.synchronize()
-T = (48000 * 2 + 960) // 480
+T = (48000 * SEC + 960) // 480
 L = _lib.lib()
 L.dfb_debug_gru_timing(model.handle, T, None)
 enhance_device(model, st, audio); torch.cuda.synchronize()
 buf = np.zeros((T, 8), dtype=np.int64)
 L.dfb_debug_gru_timing(model.handle, T, buf.ctypes.data)
-d = buf[20:180]
+d = buf[20:T - 20]
 if os.environ.get("DFB_PRECISION", "").endswith("gru_tc"):
     step = np.diff(d[:, 0])
     print(f"TC GRU B={B}  cycles/step median {np.median(step):.0f}")
-    for a, b_, n in [(0, 1, "mma: wait h"), (1, 2, "mma: issue 48"), (4, 5, "gate: wait t_full"), (5, 6, "gate: ld+gates+write"), (6, 7, "gate: fence+bar+copy")]:
+    for a, b_, n in [(0, 1, "mma: wait h"), (1, 2, "mma: issue 48"), (4, 5, "gate: wait t_full"), (5, 6, "gate: ld+gates+write"), (6, 3, "gate: fence"), (3, 7, "gate: bar+copy+gstore")]:
         seg = d[:, b_] - d[:, a]
         print(f"  {n:22s} median {np.median(seg):7.0f}  max {seg.max():7.0f}")
     print(f"  {'mma commit -> gate saw':22s} median {np.median(d[:, 5] - d[:, 2]):7.0f}")
