@@ -407,16 +407,20 @@ namespace cg = cooperative_groups;
 
 constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtN = 16, kGtRows = 3 * kGtU;
 constexpr int kGtGateThreads = 256, kGtThreads = kGtGateThreads + 32;
-constexpr int kGtHPiece = 4 * 128;            // one CTA's units in one 8-stream row group: 4 core matrices
-constexpr int kGtHSbo = (kGtH / 8) * 128;     // row-group stride of the h operand (32 core matrices)
+// h operand (B, K-major, no swizzle) as 8 x 16 B core matrices ordered [k core matrix][row group][hi|lo]:
+// a CTA's 32 units (4 k core matrices) are one contiguous 2 KB piece -> one bulk DSMEM copy per peer
+constexpr int kGtHLbo = 512;                  // stride between K-adjacent core matrices
+constexpr int kGtHSbo = 256;                  // stride between the two 8-stream row groups
+constexpr int kGtHPlane = 128;                // hi -> lo
+constexpr int kGtHPiece = 4 * kGtHLbo;        // one CTA's slice
+constexpr int kGtHBuf = (kGtH / 8) * kGtHLbo; // one buffer (16 KB)
 
 constexpr int kGtWCols = kGtH / 2;            // TMEM columns of one W plane: 2 bf16 per 32-bit column
 constexpr int kGtDCol = 2 * kGtWCols;         // accumulator columns start after W_hi | W_lo
-constexpr int kGtAcc = 4;                     // independent accumulators (k steps round-robin) so that
-                                              // consecutive tiny MMAs do not serialise on one TMEM tile
+constexpr int kGtAcc = 1;                     // accumulators (tried 4 round-robin: no gain, the limit was issue overhead)
 
 struct GruTcSmem {
-    alignas(1024) unsigned char h[2][2][2 * kGtHSbo];     // [buffer][hi|lo][row group][k core matrix][8 rows x 16 B]
+    alignas(1024) unsigned char h[2][kGtHBuf];            // [buffer][k core matrix][row group][hi|lo][8 rows x 16 B]
     float pre[3][kGtU][kGtN + 1];
     alignas(8) uint64_t bar_h[2];
     uint64_t t_full;
@@ -465,6 +469,30 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// warp-convergent variants: every lane executes the call with identical operands and one elected lane
+// issues the instruction.  Keeping control flow uniform lets ptxas hold the operands in uniform
+// registers; issuing from inside `if (lane == 0)` made it wrap every MMA in an ELECT / R2UR /
+// BRA.U.ANY loop (~50 cycles per tcgen05.mma, measured with clock64).
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -522,8 +550,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     const int nb = min(p.Bc, p.B - b0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = kGtH, T = p.T;
-    const int npiece = nb > 8 ? 2 : 1;  // 8-stream row groups that carry data
-    for (int i = tid; i < (int)sizeof(sm.h) / 16; i += kGtThreads) reinterpret_cast<uint4 *>(&sm.h[0][0][0])[i] = make_uint4(0, 0, 0, 0);  // h0 = 0
+    for (int i = tid; i < (int)sizeof(sm.h) / 16; i += kGtThreads) reinterpret_cast<uint4 *>(&sm.h[0][0])[i] = make_uint4(0, 0, 0, 0);  // h0 = 0
     if (tid == 0) {
         mbar_init(&sm.bar_h[0], 2);   // MMA thread's expect_tx arrive + one gate-warp arrive (own slice written)
         mbar_init(&sm.bar_h[1], 2);
@@ -563,40 +590,36 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     __syncthreads();
     tc_fence_after();
     cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
-    const uint32_t step_bytes = (uint32_t)((kGtC - 1) * 2 * npiece * kGtHPiece);  // from the 7 peers: hi + lo pieces
+    const uint32_t step_bytes = (uint32_t)((kGtC - 1) * kGtHPiece);  // one 2 KB piece from each of the 7 peers
 
     if (warp == 8) {
-        // ================================================================= MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, kGtN);
-            // B descriptors are address + constant bits: build the bases once, step with integer adds
-            uint64_t bdesc[2][2];
+        // ================================================================= MMA issuer (whole warp, elected lane issues)
+        constexpr uint32_t idesc = umma_idesc_bf16(128, kGtN);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint64_t bd0 = umma_desc_interleave(smem_u32(sm.h[0]), kGtHLbo, kGtHSbo);
+        const uint64_t bd1 = umma_desc_interleave(smem_u32(sm.h[1]), kGtHLbo, kGtHSbo);
+        const bool dbg_on = p.dbg && blockIdx.x == 0 && lane == 0;
+        for (int t = 0; t < T; t++) {
+            const int cur = t & 1;
+            if (dbg_on) p.dbg[t * 8 + 0] = clock64();
+            if (lane == 0 && t + 1 < T) mbar_expect_tx(&sm.bar_h[cur ^ 1], step_bytes);
+            if (t > 0) mbar_wait(&sm.bar_h[cur], (uint32_t)(((t - 1) >> 1) & 1));
+            if (dbg_on) p.dbg[t * 8 + 1] = clock64();
+            fence_proxy_async();
+            tc_fence_after();
+            const uint64_t bb = cur ? bd1 : bd0;
 #pragma unroll
-            for (int b = 0; b < 2; b++)
+            for (int combo = 0; combo < 3; combo++) {
+                const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
 #pragma unroll
-                for (int hb = 0; hb < 2; hb++) bdesc[b][hb] = umma_desc_interleave(smem_u32(sm.h[b][hb]), 128, kGtHSbo);
-            const bool dbg_on = p.dbg && blockIdx.x == 0;
-            for (int t = 0; t < T; t++) {
-                const int cur = t & 1;
-                if (dbg_on) p.dbg[t * 8 + 0] = clock64();
-                if (t + 1 < T) mbar_expect_tx(&sm.bar_h[cur ^ 1], step_bytes);
-                if (t > 0) mbar_wait(&sm.bar_h[cur], (uint32_t)(((t - 1) >> 1) & 1));
-                if (dbg_on) p.dbg[t * 8 + 1] = clock64();
-                fence_proxy_async();
-                tc_fence_after();
-#pragma unroll
-                for (int combo = 0; combo < 3; combo++) {
-                    const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
-                    const uint64_t bb = cur ? bdesc[1][hb] : bdesc[0][hb];
-#pragma unroll
-                    for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
-                        umma_bf16_ts(tmem + kGtDCol + (ks % kGtAcc) * kGtN, tmem + wa * kGtWCols + ks * 8,
-                                     bb + (uint64_t)(ks * 2 * 8), idesc, (combo == 0 && ks < kGtAcc) ? 0u : 1u);
-                    }
+                for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
+                    umma_bf16_ts_elect(tmem_u + kGtDCol, tmem_u + wa * kGtWCols + ks * 8,
+                                       bb + (uint64_t)((ks * 2 * kGtHLbo + hb * kGtHPlane) >> 4), idesc,
+                                       (combo == 0 && ks == 0) ? 0u : 1u);
                 }
-                if (dbg_on) p.dbg[t * 8 + 2] = clock64();
-                umma_commit(&sm.t_full);
             }
+            if (dbg_on) p.dbg[t * 8 + 2] = clock64();
+            umma_commit_elect(&sm.t_full);
         }
     } else {
         // ================================================================= gate warps (0-7)
@@ -607,9 +630,9 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
         float hprev0 = 0.f, hprev1 = 0.f;
         const float2 bhr = *reinterpret_cast<const float2 *>(p.bhh + gu), bhz = *reinterpret_cast<const float2 *>(p.bhh + H + gu),
                      bhn = *reinterpret_cast<const float2 *>(p.bhh + 2 * H + gu);
-        // byte offset of this (stream, unit pair) inside an h operand: row group s / 8, core matrix gu / 8
-        const uint32_t hoff = (uint32_t)((s >> 3) * kGtHSbo + (gu >> 3) * 128 + (s & 7) * 16 + (gu & 7) * 2);
-        const uint32_t piece0 = (uint32_t)(rank * kGtHPiece);  // this CTA's slice inside row group 0
+        // byte offset of this (stream, unit pair) inside an h buffer (hi plane): core matrix gu / 8, row group s / 8
+        const uint32_t hoff = (uint32_t)((gu >> 3) * kGtHLbo + (s >> 3) * kGtHSbo + (s & 7) * 16 + (gu & 7) * 2);
+        const uint32_t piece0 = (uint32_t)(rank * kGtHPiece);  // this CTA's slice of a buffer
         for (int t = 0; t < T; t++) {
             const int cur = t & 1;
             float2 xr = make_float2(0.f, 0.f), xz = xr, xn = xr;
@@ -625,14 +648,8 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             if (gdbg) p.dbg[t * 8 + 5] = clock64();
             tc_fence_after();
             if (warp < 3) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
-                float v[16], v2[16];
+                float v[16];
                 tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kGtDCol, v);
-#pragma unroll
-                for (int a = 1; a < kGtAcc; a++) {
-                    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kGtDCol + a * kGtN, v2);
-#pragma unroll
-                    for (int ss = 0; ss < kGtN; ss++) v[ss] += v2[ss];
-                }
 #pragma unroll
                 for (int ss = 0; ss < kGtN; ss++) sm.pre[warp][lane][ss] = v[ss];
             }
@@ -649,8 +666,8 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                     unsigned short h0, l0, h1, l1;
                     bf16_split(hprev0, h0, l0);
                     bf16_split(hprev1, h1, l1);
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1][0] + hoff) = h0 | (uint32_t)h1 << 16;
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1][1] + hoff) = l0 | (uint32_t)l1 << 16;
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff) = h0 | (uint32_t)h1 << 16;
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff + kGtHPlane) = l0 | (uint32_t)l1 << 16;
                 }
             }
             if (gdbg) p.dbg[t * 8 + 6] = clock64();
@@ -658,14 +675,14 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                 fence_proxy_async();  // own slice (generic stores) -> visible to the bulk-copy / tensor-core proxy
                 if (gdbg) p.dbg[t * 8 + 3] = clock64();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (warp == 0) {
-                    if (lane == 0) mbar_arrive(&sm.bar_h[cur ^ 1]);  // own slice is in place
-                    // lanes 0..27: (peer among the 7 others, hi|lo, row group) -> one 512-byte bulk copy each
-                    const int pi = lane >> 2, hl = (lane >> 1) & 1, ng = lane & 1;
-                    if (pi < kGtC - 1 && ng < npiece) {
-                        const int peer = pi + (pi >= rank ? 1 : 0);
-                        const uint32_t src = smem_u32(sm.h[cur ^ 1][hl]) + ng * kGtHSbo + piece0;
+                if (lane == 0) {
+                    // warp w < 7 copies the CTA's 2 KB slice to peer w (skipping itself); warp 7 signals the local barrier
+                    if (warp < kGtC - 1) {
+                        const int peer = warp + (warp >= rank ? 1 : 0);
+                        const uint32_t src = smem_u32(sm.h[cur ^ 1]) + piece0;
                         dsmem_bulk_copy(mapa_u32(src, peer), src, kGtHPiece, mapa_u32(smem_u32(&sm.bar_h[cur ^ 1]), peer));
+                    } else {
+                        mbar_arrive(&sm.bar_h[cur ^ 1]);  // own slice is in place
                     }
                 }
             } else {
