@@ -394,15 +394,21 @@ template int launch_dwpw_tc<DW_DF0>(cudaStream_t, DwPwParams, const float *, int
 // ================================================================ tensor-core GRU recurrence ====
 // torch.nn.GRU cell (DeepFilterNet/df/modules.py:684,723), hidden size 256.  A cluster of 8 CTAs owns
 // up to 16 streams for the whole sequence.  CTA `rank` keeps the W_hh rows of its 32 hidden units
-// (3 gates x 32 rows x 256) in SHARED MEMORY as a BF16 hi/lo split (W = hi + lo to ~2^-17), UMMA
-// K-major 128B-swizzle layout; the hidden state of the group is the B operand ([16 streams][256],
-// also BF16 hi/lo, K-major core-matrix layout without swizzle so that a CTA's 32 units form two
-// contiguous 512-byte pieces).  Per time step one thread issues 48 tcgen05.mma (M128 N16 K16,
-// kind::f16: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM); eight warps read the pre-activations
-// from TMEM, apply the gates in fp32, write the CTA's slice of the new state into its own operand
-// buffer and broadcast it with bulk DSMEM copies (cp.async.bulk shared::cta -> shared::cluster)
-// that complete bytes on each peer's mbarrier -- no cluster barrier or fence on the step's critical
-// path.  The fp32 hidden state of a CTA's own units stays in registers; only the MMA operand is BF16.
+// (3 gates x 32 rows x 256) resident in TENSOR MEMORY for the whole kernel as a BF16 hi/lo split
+// (W = hi + lo to ~2^-17; lane = row, 2 x 128 columns); the hidden state of the group is the B
+// operand in shared memory ([16 streams][256], BF16 hi/lo, K-major core matrices ordered so that a
+// CTA's 32 units are one contiguous 2 KB piece).  Per time step one warp issues 48 tcgen05.mma
+// (TS mode: A from TMEM, B from smem; M128 N16 K16, kind::f16: hi*hi + lo*hi + hi*lo, fp32
+// accumulate in TMEM); eight warps read the pre-activations from TMEM, apply the gates in fp32,
+// write the CTA's slice of the new state into its own operand buffer and broadcast it with one
+// bulk DSMEM copy per peer (cp.async.bulk shared::cta -> shared::cluster) that completes bytes on
+// the peer's mbarrier -- no cluster barrier or fence on the step's critical path.  The fp32 hidden
+// state of a CTA's own units stays in registers; only the MMA operand is BF16.
+// Measured step timeline (clock64, B = 128): 48 MMAs 640 cycles, commit -> gates 110, TMEM load +
+// gates 590, fence + barrier + copy issue 310, DSMEM flight 720  =>  2380 cycles / step
+// (the FFMA kernel k_gru: 4700).  History: issuing the MMAs from inside `if (lane == 0)` cost
+// ~50 cycles per instruction (ptxas wrapped each in an ELECT / R2UR / BRA.U.ANY loop); 4-byte
+// st.async broadcasts (4096 per CTA and step) and W_hh in shared memory were also tried first.
 namespace cg = cooperative_groups;
 
 constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtN = 16, kGtRows = 3 * kGtU;
@@ -417,7 +423,6 @@ constexpr int kGtHBuf = (kGtH / 8) * kGtHLbo; // one buffer (16 KB)
 
 constexpr int kGtWCols = kGtH / 2;            // TMEM columns of one W plane: 2 bf16 per 32-bit column
 constexpr int kGtDCol = 2 * kGtWCols;         // accumulator columns start after W_hi | W_lo
-constexpr int kGtAcc = 1;                     // accumulators (tried 4 round-robin: no gain, the limit was issue overhead)
 
 struct GruTcSmem {
     alignas(1024) unsigned char h[2][kGtHBuf];            // [buffer][k core matrix][row group][hi|lo][8 rows x 16 B]
