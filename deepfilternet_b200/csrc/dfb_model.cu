@@ -14,6 +14,7 @@
 // Arithmetic: IEEE fp32 (FFMA) everywhere; accumulation order differs from ATen's, which is
 // inside the 1e-4 RMS parity bound (tests/test_gpu_parity.py).
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 #include <cmath>
 #include <cstring>
@@ -181,6 +182,7 @@ struct GlParams {
     int64_t M;
     int G, Ig, Hg, act;
     float oscale, ooffset;
+    unsigned short *y_hi, *y_lo;  // optional BF16 hi/lo planes of y (same pitch): operand of a tcgen05 GEMM
 };
 constexpr int kGlBM = 64, kGlBN = 64, kGlBK = 32;
 
@@ -248,6 +250,11 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
             v = act_apply(v, p.act) * p.oscale + p.ooffset;
             if (p.res) v += p.res[m * p.ldr + col];
             p.y[m * p.ldy + col] = v;
+            if (p.y_hi) {
+                __nv_bfloat16 hb = __float2bfloat16_rn(v);
+                p.y_hi[m * p.ldy + col] = __bfloat16_as_ushort(hb);
+                p.y_lo[m * p.ldy + col] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hb)));
+            }
         }
     }
 }
@@ -629,6 +636,7 @@ struct dfb_model {
     std::map<std::string, std::pair<const float *, int64_t>> dbg;  // activations of the last forward
     std::vector<GruLayerW> enc_gru, erb_gru, df_gru;
     float *slab = nullptr;
+    int proj_tc = 0; // 1: GRU input projections on the BF16x3 tcgen05 GEMM (needs gru_tc)
     int gru_tc = 0;  // 1: tensor-core recurrence (BF16 hi/lo split operands) for H = 256
     long long *gru_dbg = nullptr;  // device buffer for dfb_debug_gru_timing
     int precision = 0;  // 0: fp32 FFMA everywhere; 1: TF32 tensor cores (tcgen05) for the dense contractions
@@ -725,9 +733,10 @@ extern "C" int dfb_debug_gru_timing(dfb_model *m, int steps, long long *h_out) {
 }
 
 extern "C" int dfb_model_set_precision(dfb_model *m, int mode) {
-    if (!m || mode < 0 || mode > 3) return fail(DFB_ERR_INVALID, "precision mode out of range");
+    if (!m || mode < 0 || mode > 7) return fail(DFB_ERR_INVALID, "precision mode out of range");
     m->precision = mode & 1;   // bit 0: TF32 tcgen05 for the dense feed-forward contractions
     m->gru_tc = (mode >> 1) & 1;  // bit 1: tensor-core GRU recurrence (BF16x3 split, ~fp32 accurate)
+    m->proj_tc = (mode >> 2) & 1; // bit 2: GRU input projections on the BF16x3 tcgen05 GEMM
     return DFB_OK;
 }
 
@@ -749,8 +758,8 @@ namespace {
 
 int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const float *bias, const float *res,
            int64_t ldr, float *y, int64_t ldy, int64_t M, int G, int I, int Hh, int act, float oscale = 1.f,
-           float ooffset = 0.f) {
-    GlParams p{x, ldx, w, bias, res, ldr, y, ldy, M, G, I / G, Hh / G, act, oscale, ooffset};
+           float ooffset = 0.f, unsigned short *y_hi = nullptr, unsigned short *y_lo = nullptr) {
+    GlParams p{x, ldx, w, bias, res, ldr, y, ldy, M, G, I / G, Hh / G, act, oscale, ooffset, y_hi, y_lo};
     if ((p.Ig % 4) || (ldx % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: K not a multiple of 4");
     int tiles = (p.Hg + kGlBN - 1) / kGlBN;
     dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(G * tiles));
@@ -794,11 +803,17 @@ int pick_bc(int B, int max_clusters) {
 }
 
 // x [M, in_dim] -> multi-layer GRU -> y [M, H]  (uses xproj scratch [M,3H] and h ping-pong buffers)
+// x_hi/x_lo: BF16 planes of x (written by the producing grouped linear), pl_hi/pl_lo: scratch planes for the
+// inter-layer hidden state; used when the projection runs on the BF16x3 tensor-core GEMM.
 int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, const float *x, int in_dim,
-            const float *res_last, float *y, float *xproj, float *tmp_h, int B, int T) {
+            const float *res_last, float *y, float *xproj, float *tmp_h, int B, int T,
+            unsigned short *x_hi = nullptr, unsigned short *x_lo = nullptr, unsigned short *pl_hi = nullptr,
+            unsigned short *pl_lo = nullptr) {
     const int64_t M = (int64_t)B * T;
     const float *cur_in = x;
     int cur_dim = in_dim;
+    const bool tc_proj = m->proj_tc && H == 256 && m->gru_tc && x_hi && pl_hi;
+    const unsigned short *cur_hi = x_hi, *cur_lo = x_lo;
     for (int l = 0; l < layers; l++) {
         std::string base = std::string(name) + ".l" + std::to_string(l);
         const float *w_ih_t, *w_hh, *b_ih, *b_hh;
@@ -807,7 +822,13 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         if ((rc = need(m, (base + ".w_hh").c_str(), (int64_t)3 * H * H, &w_hh))) return rc;
         if ((rc = need(m, (base + ".b_ih").c_str(), 3 * H, &b_ih))) return rc;
         if ((rc = need(m, (base + ".b_hh").c_str(), 3 * H, &b_hh))) return rc;
-        if (m->precision == 1) {
+        if (tc_proj) {
+            const float *w_hi, *w_lo;  // bf16 planes packed two per float
+            if ((rc = need(m, (base + ".w_ih_hi").c_str(), (int64_t)3 * H * cur_dim / 2, &w_hi)) ||
+                (rc = need(m, (base + ".w_ih_lo").c_str(), (int64_t)3 * H * cur_dim / 2, &w_lo)))
+                return rc;
+            rc = launch_gemm_bf16x3(s, cur_hi, cur_lo, cur_dim, w_hi, w_lo, b_ih, xproj, 3 * H, M, 3 * H, cur_dim);
+        } else if (m->precision == 1) {
             const float *w_ih;
             if ((rc = need(m, (base + ".w_ih").c_str(), (int64_t)3 * H * cur_dim, &w_ih))) return rc;
             rc = launch_gemm_tf32(s, cur_in, cur_dim, w_ih, b_ih, xproj, 3 * H, M, 3 * H, cur_dim, ACT_NONE);
@@ -818,7 +839,10 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         float *dst = (l == layers - 1) ? y : tmp_h;
         GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, 0, m->gru_dbg};
         if (H == 256 && m->gru_tc) {
-            rc = launch_gru_tc(s, xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, m->gru_dbg);
+            const bool planes = tc_proj && l < layers - 1;
+            rc = launch_gru_tc(s, xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, planes ? pl_hi : nullptr,
+                               planes ? pl_lo : nullptr, B, T, m->gru_dbg);
+            cur_hi = pl_hi; cur_lo = pl_lo;
         } else if (H == 256) {
             p.Bc = pick_bc(B, 148 / 4);
             rc = launch_gru_t<256, 4>(s, p, (B + p.Bc - 1) / p.Bc);
@@ -866,6 +890,7 @@ int run_dwpw(cudaStream_t s, DwPwParams p, int B, const float *pw_nk = nullptr) 
 // Buffers of one forward pass (all from the model arena).
 struct FwdBufs {
     float *e0, *e1, *e2, *e3, *c0, *c1, *emb_in, *emb, *g_a, *g_b, *g_h, *xproj, *dec_emb, *d3, *d2, *d1, *dfc;
+    unsigned short *ga_hi, *ga_lo, *gh_hi, *gh_lo;  // BF16 planes of g_a / inter-layer h (tensor-core projections)
 };
 
 // Carves the activations of `M` frames out of `a` (or only counts bytes when a == nullptr).
@@ -890,6 +915,8 @@ static size_t fwd_plan(const dfb_model_config &c, size_t M, Arena *a, FwdBufs *f
     t.xproj = take(M * 3 * Hmax);
     t.dec_emb = take(M * ED); t.d3 = take(M * ED); t.d2 = take(M * (E / 2) * kCh);
     t.d1 = take(M * E * kCh); t.dfc = take(M * Hmax);
+    t.ga_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.ga_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
+    t.gh_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.gh_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
     if (f) *f = t;
     return bytes + 4096;
 }
@@ -990,9 +1017,11 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         // enc.emb_gru: linear_in + ReLU -> GRU -> [linear_out + ReLU]
         const float *w_in, *w_out = nullptr;
         if ((rc = need(m, "enc.emb_gru.in.gl", (int64_t)emb_in_dim * H / c.g_enc_in, &w_in))) return rc;
-        if ((rc = run_gl(s, f.emb_in, emb_in_dim, w_in, nullptr, nullptr, 0, f.g_a, H, M, c.g_enc_in, emb_in_dim, H, ACT_RELU))) return rc;
+        if ((rc = run_gl(s, f.emb_in, emb_in_dim, w_in, nullptr, nullptr, 0, f.g_a, H, M, c.g_enc_in, emb_in_dim, H, ACT_RELU, 1.f, 0.f,
+                         f.ga_hi, f.ga_lo))) return rc;
         float *gout = c.g_enc_out ? f.g_b : f.emb;
-        if ((rc = run_gru(m, s, "enc.emb_gru", c.enc_gru_layers, H, f.g_a, H, nullptr, gout, f.xproj, f.g_h, B, T))) return rc;
+        if ((rc = run_gru(m, s, "enc.emb_gru", c.enc_gru_layers, H, f.g_a, H, nullptr, gout, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
+                          f.gh_hi, f.gh_lo))) return rc;
         if (c.g_enc_out) {
             if ((rc = need(m, "enc.emb_gru.out.gl", (int64_t)H * ED / c.g_enc_out, &w_out))) return rc;
             if ((rc = run_gl(s, f.g_b, H, w_out, nullptr, nullptr, 0, f.emb, emb_dim, M, c.g_enc_out, H, ED, ACT_RELU))) return rc;
@@ -1007,10 +1036,12 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     {
         const float *w_in, *w_out;
         if ((rc = need(m, "erb_dec.emb_gru.in.gl", (int64_t)emb_dim * H / c.g_erb_in, &w_in))) return rc;
-        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a, H, M, c.g_erb_in, emb_dim, H, ACT_RELU))) return rc;
+        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a, H, M, c.g_erb_in, emb_dim, H, ACT_RELU, 1.f, 0.f,
+                         f.ga_hi, f.ga_lo))) return rc;
         // DFN2 (SqueezedGRU): identity skip around the GRU, y = GRU(x) + x  (modules.py:695-697)
         const float *res = c.model_kind == 2 ? f.g_a : nullptr;
-        if ((rc = run_gru(m, s, "erb_dec.emb_gru", c.erb_gru_layers, H, f.g_a, H, res, f.g_b, f.xproj, f.g_h, B, T))) return rc;
+        if ((rc = run_gru(m, s, "erb_dec.emb_gru", c.erb_gru_layers, H, f.g_a, H, res, f.g_b, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
+                          f.gh_hi, f.gh_lo))) return rc;
         if ((rc = need(m, "erb_dec.emb_gru.out.gl", (int64_t)H * ED / c.g_erb_out, &w_out))) return rc;
         if ((rc = run_gl(s, f.g_b, H, w_out, nullptr, nullptr, 0, f.dec_emb, ED, M, c.g_erb_out, H, ED, ACT_RELU))) return rc;
         auto path = [&](DwPwParams &p, const char *pn, const float *pt, int64_t pfs) -> int {
@@ -1047,9 +1078,11 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     {
         const float *w_in, *w_out;
         if ((rc = need(m, "df_dec.df_gru.in.gl", (int64_t)emb_dim * Hd / c.g_df_in, &w_in))) return rc;
-        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a, Hd, M, c.g_df_in, emb_dim, Hd, ACT_RELU))) return rc;
+        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a, Hd, M, c.g_df_in, emb_dim, Hd, ACT_RELU, 1.f, 0.f,
+                         f.ga_hi, f.ga_lo))) return rc;
         const float *res = c.model_kind == 2 ? f.g_a : nullptr;
-        if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a, Hd, res, f.dfc, f.xproj, f.g_h, B, T))) return rc;
+        if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a, Hd, res, f.dfc, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
+                          f.gh_hi, f.gh_lo))) return rc;
         if (c.g_df_skip) {
             const float *w_skip;
             if ((rc = need(m, "df_dec.df_skip.gl", (int64_t)emb_dim * Hd / c.g_df_skip, &w_skip))) return rc;

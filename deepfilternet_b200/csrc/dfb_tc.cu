@@ -75,6 +75,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -207,6 +219,117 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, BN);
+}
+
+// ------------------------------------------------------------- BF16x3 GEMM (projections) ----
+// Y[M,N] = X[M,K] . W[N,K]^T + bias with fp32-level accuracy on the BF16 tensor pipe: both operands
+// are stored as BF16 hi/lo planes (x = hi + lo to ~2^-17; X planes written by the producing kernel's
+// epilogue, W planes split on the host) and every product is hi*hi + lo*hi + hi*lo with fp32
+// accumulation in TMEM.  One CTA per 128 x 64 output tile; warp 4 = TMA producer (four 2-D bulk
+// tensor loads per 64-wide k block, 128B swizzle), warp 5 = MMA issuer (12 tcgen05.mma per k block,
+// elect.sync issue), warps 0-3 = epilogue (tcgen05.ld, + bias, 256-byte row stores).
+constexpr int kBxBM = 128, kBxBN = 64, kBxBK = 64, kBxStages = 2;
+
+struct BxSmem {
+    alignas(1024) unsigned char a[kBxStages][2][kBxBM * 128];  // [stage][hi|lo][128 rows x 64 bf16]
+    alignas(1024) unsigned char b[kBxStages][2][kBxBN * 128];
+    alignas(16) float bias[kBxBN];
+    alignas(8) uint64_t full[kBxStages];
+    uint64_t empty[kBxStages];
+    uint64_t tmem_full;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void umma_bf16_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(192)
+k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+              const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+              const float *__restrict__ bias, float *__restrict__ Y, int64_t ldy, int M, int N, int K) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    BxSmem &sm = *reinterpret_cast<BxSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBxBM, n0 = blockIdx.y * kBxBN;
+    const int nkb = K / kBxBK;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBxStages; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        mbar_init(&sm.tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, kBxBN);
+    if (threadIdx.x < kBxBN) sm.bias[threadIdx.x] = bias ? bias[n0 + threadIdx.x] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    if (warp == 4) {
+        // ===== TMA producer
+        if (lane == 0) {
+            tma_prefetch_desc(&tmAhi); tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % kBxStages, it = kb / kBxStages;
+                if (it > 0) mbar_wait(&sm.empty[s], (it - 1) & 1);
+                mbar_expect_tx(&sm.full[s], 2 * (kBxBM + kBxBN) * 128);
+                tma_load_2d(sm.a[s][0], &tmAhi, kb * kBxBK, m0, &sm.full[s]);
+                tma_load_2d(sm.a[s][1], &tmAlo, kb * kBxBK, m0, &sm.full[s]);
+                tma_load_2d(sm.b[s][0], &tmBhi, kb * kBxBK, n0, &sm.full[s]);
+                tma_load_2d(sm.b[s][1], &tmBlo, kb * kBxBK, n0, &sm.full[s]);
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer (whole warp, elected lane issues)
+        constexpr uint32_t idesc = umma_idesc_bf16(kBxBM, kBxBN);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % kBxStages, it = kb / kBxStages;
+            mbar_wait(&sm.full[s], it & 1);
+            tc_fence_after();
+            const uint64_t ah = umma_desc_sw128(smem_u32(sm.a[s][0])), al = umma_desc_sw128(smem_u32(sm.a[s][1]));
+            const uint64_t bh = umma_desc_sw128(smem_u32(sm.b[s][0])), bl = umma_desc_sw128(smem_u32(sm.b[s][1]));
+#pragma unroll
+            for (int k = 0; k < kBxBK / 16; k++) {  // 32 bytes per K step inside the 128-byte swizzle row
+                umma_bf16_ss_elect(tmem_u, ah + 2 * k, bh + 2 * k, idesc, (kb | k) != 0);
+                umma_bf16_ss_elect(tmem_u, al + 2 * k, bh + 2 * k, idesc, 1u);
+                umma_bf16_ss_elect(tmem_u, ah + 2 * k, bl + 2 * k, idesc, 1u);
+            }
+            umma_commit_elect(&sm.empty[s]);
+        }
+        umma_commit_elect(&sm.tmem_full);
+    } else {
+        // ===== epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) = rows m0 + 32 w + lane
+        mbar_wait(&sm.tmem_full, 0);
+        tc_fence_after();
+        const int m = m0 + warp * 32 + lane;
+        float v0[32], v1[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v0);
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32, v1);
+        if (m < M) {
+            float *dst = Y + (int64_t)m * ldy + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[j]);
+                *reinterpret_cast<float4 *>(dst + j) = make_float4(v0[j] + bv.x, v0[j + 1] + bv.y, v0[j + 2] + bv.z, v0[j + 3] + bv.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[32 + j]);
+                *reinterpret_cast<float4 *>(dst + 32 + j) = make_float4(v1[j] + bv.x, v1[j + 1] + bv.y, v1[j + 2] + bv.z, v1[j + 3] + bv.w);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kBxBN);
 }
 
 // ------------------------------------------- fused depthwise -> 1x1 (tcgen05) -> ReLU ----
@@ -438,13 +561,11 @@ struct GruTcParams {
     const float *bhh;    // [3H]
     const float *res;    // optional [B,T,H], added to the OUTPUT only
     float *hout;         // [B,T,H]
+    unsigned short *hout_hi, *hout_lo;  // optional BF16 hi/lo planes of hout (A operand of the next projection GEMM)
     int B, T, Bc;
     long long *dbg;      // optional [T][8] clock64 stamps of CTA 0 (0-3: MMA thread, 4-7: gate thread 0)
 };
 
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 // K-major operand without swizzle: 8 x 16 B core matrices, LBO = stride between K-adjacent core
 // matrices, SBO = stride between 8-row groups (cute/arch/mma_sm100_desc.hpp, LayoutType::SWIZZLE_NONE)
 __device__ __forceinline__ uint64_t umma_desc_interleave(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -489,15 +610,6 @@ __device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tme
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-        "}\n" ::"r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -641,6 +753,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
         for (int t = 0; t < T; t++) {
             const int cur = t & 1;
             float2 xr = make_float2(0.f, 0.f), xz = xr, xn = xr;
+            uint32_t vhi = 0, vlo = 0;
             if (active) {
                 const float *xp = p.xproj + ((int64_t)(b0 + s) * T + t) * (3 * H) + gu;
                 xr = *reinterpret_cast<const float2 *>(xp);
@@ -667,12 +780,16 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                 const float n0 = gt_tanh(xn.x + r0 * (sm.pre[2][u0][s] + bhn.x)), n1 = gt_tanh(xn.y + r1 * (sm.pre[2][u0 + 1][s] + bhn.y));
                 hprev0 = (1.f - z0) * n0 + z0 * hprev0;
                 hprev1 = (1.f - z1) * n1 + z1 * hprev1;
-                if (t + 1 < T) {
+                {
                     unsigned short h0, l0, h1, l1;
                     bf16_split(hprev0, h0, l0);
                     bf16_split(hprev1, h1, l1);
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff) = h0 | (uint32_t)h1 << 16;
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff + kGtHPlane) = l0 | (uint32_t)l1 << 16;
+                    vhi = h0 | (uint32_t)h1 << 16;
+                    vlo = l0 | (uint32_t)l1 << 16;
+                }
+                if (t + 1 < T) {
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff) = vhi;
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff + kGtHPlane) = vlo;
                 }
             }
             if (gdbg) p.dbg[t * 8 + 6] = clock64();
@@ -698,6 +815,10 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                 float2 ov = make_float2(hprev0, hprev1);
                 if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
                 *reinterpret_cast<float2 *>(p.hout + o) = ov;
+                if (p.hout_hi) {  // residual-free h (the next layer's projection input)
+                    *reinterpret_cast<uint32_t *>(p.hout_hi + o) = vhi;
+                    *reinterpret_cast<uint32_t *>(p.hout_lo + o) = vlo;
+                }
             }
             if (gdbg) p.dbg[t * 8 + 7] = clock64();
             // sm.pre is rewritten only after the next t_full, i.e. after every CTA's copies of this step
@@ -710,7 +831,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
 }
 
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
-                  int B, int T, long long *dbg) {
+                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg) {
     static bool attr_done = false;
     // the kernel allocates all 512 TMEM columns (W_hh lives there), so only one CTA may be resident
     // per SM: request more than half of the shared memory to enforce it
@@ -719,7 +840,7 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
         DFB_CUDA(cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    GruTcParams p{xproj, whh, bhh, res, hout, B, T, 0, dbg};
+    GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, B, T, 0, dbg};
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kGtThreads);
     cfg.dynamicSmemBytes = smem;
@@ -776,6 +897,44 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t c
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return DFB_OK;
+}
+
+// 2-D bf16 row-major [rows][cols] (row pitch ld elements), box = [box_rows][64 elements = 128 B], 128-byte swizzle
+static int make_map_bf16(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r);
+    return DFB_OK;
+}
+
+// Y[M,N] = X . W^T + bias with X, W given as BF16 hi/lo planes (X: [M][K] pitch ldx, W: [N][K] pitch K)
+int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64_t ldx, const void *w_hi, const void *w_lo,
+                       const float *bias, float *y, int64_t ldy, int64_t M, int N, int K) {
+    if (N % kBxBN || K % kBxBK || (ldx % 8) || (ldy % 4) || M <= 0)
+        return fail(DFB_ERR_UNSUPPORTED, "bf16x3 GEMM shape M=%lld N=%d K=%d", (long long)M, N, K);
+    CUtensorMap mah, mal, mbh, mbl;
+    int rc;
+    if ((rc = make_map_bf16(&mah, x_hi, M, K, ldx, kBxBM)) || (rc = make_map_bf16(&mal, x_lo, M, K, ldx, kBxBM)) ||
+        (rc = make_map_bf16(&mbh, w_hi, N, K, K, kBxBN)) || (rc = make_map_bf16(&mbl, w_lo, N, K, K, kBxBN)))
+        return rc;
+    static bool attr_done = false;
+    const int smem = (int)sizeof(BxSmem) + 1024;
+    if (!attr_done) {
+        DFB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((M + kBxBM - 1) / kBxBM), (unsigned)(N / kBxBN));
+    DFB_PROF("k_gemm_bf16x3[gru_proj]", s);
+    k_gemm_bf16x3<<<grid, 192, smem, s>>>(mah, mal, mbh, mbl, bias, y, ldy, (int)M, N, K);
+    DFB_LAUNCH_CHECK();
     return DFB_OK;
 }
 

@@ -54,6 +54,16 @@ def _bn_fold(sd, p: str) -> Tuple[np.ndarray, np.ndarray]:
     return scale, b - mu * scale
 
 
+def bf16_planes(w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """fp32 -> (hi, lo) BF16 planes with w ~= hi + lo (both round-to-nearest-even), each returned as a
+    float32 array holding two BF16 values per element (the C ABI moves fp32 tensors only)."""
+    t = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.to(torch.float32)).to(torch.bfloat16)
+    pack = lambda b: np.ascontiguousarray(b.contiguous().view(torch.int16).numpy().view(np.float32))
+    return pack(hi), pack(lo)
+
+
 def gru_layers(sd, prefix: str) -> int:
     n = 0
     while f"{prefix}.weight_ih_l{n}" in sd:
@@ -154,6 +164,8 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
         for l in range(n):
             out[f"{dst}.l{l}.w_ih_t"] = f32(_np(sd[f"{src}.weight_ih_l{l}"]).T)
             out[f"{dst}.l{l}.w_ih"] = f32(_np(sd[f"{src}.weight_ih_l{l}"]))  # [3H][I]: B operand of the tcgen05 GEMM
+            hi, lo = bf16_planes(_np(sd[f"{src}.weight_ih_l{l}"]))              # [3H][I] BF16 hi / lo, two per float
+            out[f"{dst}.l{l}.w_ih_hi"], out[f"{dst}.l{l}.w_ih_lo"] = hi, lo
             out[f"{dst}.l{l}.w_hh"] = f32(_np(sd[f"{src}.weight_hh_l{l}"]))
             out[f"{dst}.l{l}.b_ih"] = f32(_np(sd[f"{src}.bias_ih_l{l}"]))
             out[f"{dst}.l{l}.b_hh"] = f32(_np(sd[f"{src}.bias_hh_l{l}"]))
