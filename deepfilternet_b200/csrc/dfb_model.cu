@@ -642,6 +642,8 @@ struct dfb_model {
     int precision = 0;  // 0: fp32 FFMA everywhere; 1: TF32 tensor cores (tcgen05) for the dense contractions
     Arena arena;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;             // DF decoder branch runs here, concurrently with the ERB decoder
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     const float *get(const std::string &n) const {
         auto it = t.find(n);
         return it == t.end() ? nullptr : it->second.first;
@@ -697,7 +699,10 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
         m->t[tt.name] = {dst, tt.numel};
         off += ((size_t)tt.numel * 4 + 255) & ~size_t(255);
     }
-    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         dfb_model_free(m);
         return fail(DFB_ERR_CUDA, "stream creation failed");
     }
@@ -711,6 +716,9 @@ extern "C" void dfb_model_free(dfb_model *m) {
     m->arena.release();
     if (m->slab) cudaFree(m->slab);
     if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->aux) cudaStreamDestroy(m->aux);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
 }
 
@@ -891,6 +899,9 @@ int run_dwpw(cudaStream_t s, DwPwParams p, int B, const float *pw_nk = nullptr) 
 struct FwdBufs {
     float *e0, *e1, *e2, *e3, *c0, *c1, *emb_in, *emb, *g_a, *g_b, *g_h, *xproj, *dec_emb, *d3, *d2, *d1, *dfc;
     unsigned short *ga_hi, *ga_lo, *gh_hi, *gh_lo;  // BF16 planes of g_a / inter-layer h (tensor-core projections)
+    // second set of GRU scratch: the DF decoder runs concurrently with the ERB decoder on another stream
+    float *g_a2, *g_h2, *xproj2;
+    unsigned short *ga2_hi, *ga2_lo, *gh2_hi, *gh2_lo;
 };
 
 // Carves the activations of `M` frames out of `a` (or only counts bytes when a == nullptr).
@@ -917,6 +928,9 @@ static size_t fwd_plan(const dfb_model_config &c, size_t M, Arena *a, FwdBufs *f
     t.d1 = take(M * E * kCh); t.dfc = take(M * Hmax);
     t.ga_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.ga_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
     t.gh_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.gh_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
+    t.g_a2 = take(M * Hmax); t.g_h2 = take(M * Hmax); t.xproj2 = take(M * 3 * Hmax);
+    t.ga2_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.ga2_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
+    t.gh2_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.gh2_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
     if (f) *f = t;
     return bytes + 4096;
 }
@@ -951,7 +965,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     int rc;
     FwdBufs f{};
     fwd_plan(c, (size_t)M, &arena, &f);
-    if (!f.dfc) return fail(DFB_ERR_OOM, "forward workspace exhausted for %lld frames", (long long)M);
+    if (!f.gh2_lo) return fail(DFB_ERR_OOM, "forward workspace exhausted for %lld frames", (long long)M);
     m->dbg.clear();
     m->dbg["e0"] = {f.e0, M * E * kCh}; m->dbg["e1"] = {f.e1, M * (E / 2) * kCh}; m->dbg["e2"] = {f.e2, M * (E / 4) * kCh};
     m->dbg["e3"] = {f.e3, c.enc_concat ? M * emb_in_dim : M * ED}; m->dbg["c0"] = {f.c0, M * Fd * kCh};
@@ -1032,6 +1046,46 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             if ((rc = run_gl(s, f.emb, emb_dim, lw, lb, nullptr, 0, d_lsnr, 1, M, 1, emb_dim, 1, ACT_SIGMOID, c.lsnr_scale, c.lsnr_offset))) return rc;
         }
     }
+    // fork: the two decoders only share read-only encoder outputs
+    DFB_CUDA(cudaEventRecord(m->ev_fork, s));
+    DFB_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+    // ---- DF decoder (deepfilternet3.py:323-331), on the auxiliary stream (forked after the encoder)
+    {
+        cudaStream_t s = m->aux;  // shadows the caller stream inside this block
+        const float *w_in, *w_out;
+        if ((rc = need(m, "df_dec.df_gru.in.gl", (int64_t)emb_dim * Hd / c.g_df_in, &w_in))) return rc;
+        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a2, Hd, M, c.g_df_in, emb_dim, Hd, ACT_RELU, 1.f, 0.f,
+                         f.ga2_hi, f.ga2_lo))) return rc;
+        const float *res = c.model_kind == 2 ? f.g_a2 : nullptr;
+        if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a2, Hd, res, f.dfc, f.xproj2, f.g_h2, B, T, f.ga2_hi, f.ga2_lo,
+                          f.gh2_hi, f.gh2_lo))) return rc;
+        if (c.g_df_skip) {
+            const float *w_skip;
+            if ((rc = need(m, "df_dec.df_skip.gl", (int64_t)emb_dim * Hd / c.g_df_skip, &w_skip))) return rc;
+            if ((rc = run_gl(s, f.emb, emb_dim, w_skip, nullptr, f.dfc, Hd, f.dfc, Hd, M, c.g_df_skip, emb_dim, Hd, ACT_NONE))) return rc;
+        }
+        if (d_alpha && c.model_kind == 2) {  // alpha = sigmoid(df_fc_a(c)), deepfilternet2.py:368
+            const float *aw, *ab;
+            if ((rc = need(m, "df_dec.df_fc_a.w", Hd, &aw)) || (rc = need(m, "df_dec.df_fc_a.b", 1, &ab))) return rc;
+            if ((rc = run_gl(s, f.dfc, Hd, aw, ab, nullptr, 0, d_alpha, 1, M, 1, Hd, 1, ACT_SIGMOID))) return rc;
+        }
+        const int O2 = 2 * c.df_order;
+        if ((rc = need(m, "df_dec.df_out.gl", (int64_t)Hd * Fd * O2 / c.g_df_out, &w_out))) return rc;
+        if ((rc = run_gl(s, f.dfc, Hd, w_out, nullptr, nullptr, 0, d_coefs, (int64_t)Fd * O2, M, c.g_df_out, Hd, Fd * O2, ACT_TANH))) return rc;
+        const float *w1, *w2, *bb;
+        if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
+            (rc = need(m, "df_dec.df_convp.w2", O2 * O2, &w2)) || (rc = need(m, "df_dec.df_convp.b", O2, &bb)))
+            return rc;
+        int smem = (c.df_pathway_kt * O2 * (kCh / 2) + O2 * O2 + O2) * 4;
+        if (c.df_order != 5 || c.df_pathway_kt != 5 || Fd * kCpRuns > 192)
+            return fail(DFB_ERR_UNSUPPORTED, "df_order %d / df_pathway_kernel_size_t %d (built kernels: 5, 5)", c.df_order,
+                        c.df_pathway_kt);
+        dim3 grid((unsigned)((T + kCpR * kCpRuns - 1) / (kCpR * kCpRuns)), (unsigned)B);
+        DFB_PROF("k_df_convp", s);
+        k_df_convp<5, 5><<<grid, Fd * kCpRuns, smem, s>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
+        DFB_LAUNCH_CHECK();
+    }
+    DFB_CUDA(cudaEventRecord(m->ev_join, m->aux));
     // ---- ERB decoder (deepfilternet3.py:245-254)
     {
         const float *w_in, *w_out;
@@ -1074,41 +1128,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         k_mask_out<<<grid, 32 * kMaskWarps, smem, s>>>(f.e0, f.d1, ps, pb, w, bb, d_m, T, E, c.conv_kt);
         DFB_LAUNCH_CHECK();
     }
-    // ---- DF decoder (deepfilternet3.py:323-331)
-    {
-        const float *w_in, *w_out;
-        if ((rc = need(m, "df_dec.df_gru.in.gl", (int64_t)emb_dim * Hd / c.g_df_in, &w_in))) return rc;
-        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a, Hd, M, c.g_df_in, emb_dim, Hd, ACT_RELU, 1.f, 0.f,
-                         f.ga_hi, f.ga_lo))) return rc;
-        const float *res = c.model_kind == 2 ? f.g_a : nullptr;
-        if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a, Hd, res, f.dfc, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
-                          f.gh_hi, f.gh_lo))) return rc;
-        if (c.g_df_skip) {
-            const float *w_skip;
-            if ((rc = need(m, "df_dec.df_skip.gl", (int64_t)emb_dim * Hd / c.g_df_skip, &w_skip))) return rc;
-            if ((rc = run_gl(s, f.emb, emb_dim, w_skip, nullptr, f.dfc, Hd, f.dfc, Hd, M, c.g_df_skip, emb_dim, Hd, ACT_NONE))) return rc;
-        }
-        if (d_alpha && c.model_kind == 2) {  // alpha = sigmoid(df_fc_a(c)), deepfilternet2.py:368
-            const float *aw, *ab;
-            if ((rc = need(m, "df_dec.df_fc_a.w", Hd, &aw)) || (rc = need(m, "df_dec.df_fc_a.b", 1, &ab))) return rc;
-            if ((rc = run_gl(s, f.dfc, Hd, aw, ab, nullptr, 0, d_alpha, 1, M, 1, Hd, 1, ACT_SIGMOID))) return rc;
-        }
-        const int O2 = 2 * c.df_order;
-        if ((rc = need(m, "df_dec.df_out.gl", (int64_t)Hd * Fd * O2 / c.g_df_out, &w_out))) return rc;
-        if ((rc = run_gl(s, f.dfc, Hd, w_out, nullptr, nullptr, 0, d_coefs, (int64_t)Fd * O2, M, c.g_df_out, Hd, Fd * O2, ACT_TANH))) return rc;
-        const float *w1, *w2, *bb;
-        if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
-            (rc = need(m, "df_dec.df_convp.w2", O2 * O2, &w2)) || (rc = need(m, "df_dec.df_convp.b", O2, &bb)))
-            return rc;
-        int smem = (c.df_pathway_kt * O2 * (kCh / 2) + O2 * O2 + O2) * 4;
-        if (c.df_order != 5 || c.df_pathway_kt != 5 || Fd * kCpRuns > 192)
-            return fail(DFB_ERR_UNSUPPORTED, "df_order %d / df_pathway_kernel_size_t %d (built kernels: 5, 5)", c.df_order,
-                        c.df_pathway_kt);
-        dim3 grid((unsigned)((T + kCpR * kCpRuns - 1) / (kCpR * kCpRuns)), (unsigned)B);
-        DFB_PROF("k_df_convp", s);
-        k_df_convp<5, 5><<<grid, Fd * kCpRuns, smem, s>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
-        DFB_LAUNCH_CHECK();
-    }
+    DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));  // join
     return DFB_OK;
 }
 

@@ -105,12 +105,14 @@ class DfNet(nn.Module):
                                           widths.ctypes.data_as(C.POINTER(C.c_int64))))
         self._h = h
         self._derived = derived
-        self.set_precision(os.environ.get("DFB_PRECISION", "fp32+gru_tc"))
+        self.set_precision(os.environ.get("DFB_PRECISION", "fp32+gru_tc+proj_tc"))
 
     def set_precision(self, mode: str) -> None:
         """Arithmetic of the contractions (everything else is always IEEE fp32):
           'fp32'         FFMA everywhere
-          'fp32+gru_tc'  (default) as 'fp32', but the GRU recurrence of H = 256 models runs on tcgen05 tensor
+          'fp32+gru_tc+proj_tc'  (default) as 'fp32+gru_tc' plus the GRU input projections on the BF16x3
+                         tcgen05 GEMM (operands as BF16 hi/lo planes, 3 MMAs per product; 1e-7 .. 4e-7 RMS)
+          'fp32+gru_tc'  as 'fp32', but the GRU recurrence of H = 256 models runs on tcgen05 tensor
                          cores with BF16 hi/lo split operands (3 MMAs per product, fp32 accumulate: ~2^-17
                          relative, measured 5e-8 RMS end to end)
           'tf32' / 'tf32+gru_tc'  additionally TF32 tcgen05 for the feed-forward contractions (faster GEMMs,
