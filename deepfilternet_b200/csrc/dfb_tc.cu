@@ -855,9 +855,10 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
         cfg.gridDim = dim3(kGtC * 64);
         if (cudaOccupancyMaxActiveClusters(&max_clusters, k_gru_tc, &cfg) != cudaSuccess || max_clusters < 1) max_clusters = 8;
     }
-    int bc = (B + max_clusters - 1) / max_clusters;
-    if (bc < 8) bc = 8;
-    if (bc > kGtN) bc = kGtN;
+    // (a step costs the same for any N <= 16, and leaving SMs free lets the other decoder branch's
+    // recurrence run concurrently on the auxiliary stream)
+    int bc = kGtN;
+    (void)max_clusters;
     p.Bc = bc;
     const int ngroups = (B + bc - 1) / bc;
     cfg.gridDim = dim3((unsigned)(ngroups * kGtC));
