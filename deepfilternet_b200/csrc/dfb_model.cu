@@ -41,49 +41,56 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// ------------------------------------------------------------------- erb_conv0 ----
-// Dense 1 -> 64 conv, kernel (kt,3), causal in time, BN folded, ReLU.  modules.py:18-72 with
-// in_ch = 1 (groups = 1, not separable); feature look-ahead: deepfilternet3.py:359,409-410.
-// in  fe [B,T,E]; out e0 [B,T,E,64].  One CTA = kE0Frames frames; thread = (f, channel quad).
-constexpr int kE0Frames = 8;
+// ------------------------------------------------------- input convs (erb_conv0, df_conv0) ----
+// Dense CIN -> 64 conv, kernel (kt,3), causal in time, BN folded, ReLU.
+//   erb_conv0 (CIN = 1): modules.py:18-72 with in_ch = 1 (groups = 1, not separable).
+//   df_conv0  (CIN = 2): grouped 2 -> 64 (kt,3) conv followed by the 64 x 64 1x1 conv and BN.  The two
+//     linear maps are composed on the host (weights.py): W[dt][df][ri][n] = sum_{c in group ri}
+//     dw[dt][df][c] * pw[c][n], so the 64-wide intermediate never exists: 18 instead of 73 MACs per output.
+// Feature look-ahead: deepfilternet3.py:359,409-410.
+// in  x [B,T,F,CIN]; out [B,T,F,64].  One CTA = kInFrames frames; thread = (f slot, channel quad), taps in registers.
+constexpr int kInFrames = 8;
+template <int CIN>
 __global__ void __launch_bounds__(256)
-k_erb_conv0(const float *__restrict__ fe, const float *__restrict__ w /*[kt][3][64]*/,
-            const float *__restrict__ bias, float *__restrict__ out, int T, int E, int kt, int lookahead) {
-    extern __shared__ float s_in[];  // [(kE0Frames + kt - 1)][E + 2]
-    const int b = blockIdx.y, t0 = blockIdx.x * kE0Frames;
-    const int rows = kE0Frames + kt - 1, ld = E + 2;
+k_conv_in(const float *__restrict__ x, const float *__restrict__ w /*[kt][3][CIN][64]*/, const float *__restrict__ bias,
+          float *__restrict__ out, int T, int F, int kt, int lookahead) {
+    extern __shared__ float s_in[];  // [(kInFrames + kt - 1)][(F + 2) * CIN]
+    const int b = blockIdx.y, t0 = blockIdx.x * kInFrames;
+    const int rows = kInFrames + kt - 1, ld = (F + 2) * CIN;
     for (int i = threadIdx.x; i < rows * ld; i += blockDim.x) {
-        int r = i / ld, f = i - r * ld - 1;
+        int r = i / ld, j = i - r * ld;
+        int f = j / CIN - 1, ci = j - (f + 1) * CIN;
         int tp = t0 - (kt - 1) + r;  // time index in the look-ahead shifted feature sequence
         float v = 0.f;
-        if (f >= 0 && f < E && tp >= 0 && tp + lookahead < T) v = fe[((int64_t)b * T + tp + lookahead) * E + f];
+        if (f >= 0 && f < F && tp >= 0 && tp + lookahead < T) v = x[(((int64_t)b * T + tp + lookahead) * F + f) * CIN + ci];
         s_in[i] = v;
     }
     const int cq = threadIdx.x & 15, fl = threadIdx.x >> 4;  // 16 channel quads x 16 f per pass
-    float4 wr[9];
+    float4 wr[9 * CIN];
 #pragma unroll
-    for (int i = 0; i < 9; i++) wr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = 0; i < kt * 3; i++) wr[i + (3 - kt) * 3] = *reinterpret_cast<const float4 *>(w + i * kCh + cq * 4);
+    for (int i = 0; i < 9 * CIN; i++)
+        wr[i] = (i >= (3 - kt) * 3 * CIN) ? *reinterpret_cast<const float4 *>(w + (i - (3 - kt) * 3 * CIN) * kCh + cq * 4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 bv = *reinterpret_cast<const float4 *>(bias + cq * 4);
     __syncthreads();
-    for (int fr = 0; fr < kE0Frames; fr++) {
+    for (int fr = 0; fr < kInFrames; fr++) {
         int t = t0 + fr;
         if (t >= T) break;
-        for (int f = fl; f < E; f += 16) {
+        for (int f = fl; f < F; f += 16) {
             float4 acc = bv;
 #pragma unroll
             for (int dt = 0; dt < 3; dt++) {
                 if (dt < 3 - kt) continue;
-                const float *row = s_in + (fr + dt - (3 - kt)) * ld + f;  // f-1 .. f+1 -> +0..+2
+                const float *row = s_in + (fr + dt - (3 - kt)) * ld + f * CIN;  // f-1 .. f+1 -> +0 .. +2
 #pragma unroll
-                for (int df = 0; df < 3; df++) {
-                    float x = row[df];
-                    float4 ww = wr[dt * 3 + df];
-                    acc.x += x * ww.x; acc.y += x * ww.y; acc.z += x * ww.z; acc.w += x * ww.w;
+                for (int j = 0; j < 3 * CIN; j++) {
+                    const float xv = row[j];
+                    const float4 ww = wr[dt * 3 * CIN + j];
+                    acc.x += xv * ww.x; acc.y += xv * ww.y; acc.z += xv * ww.z; acc.w += xv * ww.w;
                 }
             }
             acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-            *reinterpret_cast<float4 *>(out + (((int64_t)b * T + t) * E + f) * kCh + cq * 4) = acc;
+            *reinterpret_cast<float4 *>(out + (((int64_t)b * T + t) * F + f) * kCh + cq * 4) = acc;
         }
     }
 }
@@ -980,10 +987,10 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     {
         const float *w, *bb;
         if ((rc = need(m, "enc.erb_conv0.w", c.inp_kt * 3 * kCh, &w)) || (rc = need(m, "enc.erb_conv0.b", kCh, &bb))) return rc;
-        dim3 grid((unsigned)((T + kE0Frames - 1) / kE0Frames), (unsigned)B);
-        int smem = (kE0Frames + c.inp_kt - 1) * (E + 2) * 4;
-        DFB_PROF("k_erb_conv0", s);
-        k_erb_conv0<<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead);
+        dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
+        int smem = (kInFrames + c.inp_kt - 1) * (E + 2) * 4;
+        DFB_PROF("k_conv_in[erb_conv0]", s);
+        k_conv_in<1><<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead);
         DFB_LAUNCH_CHECK();
     }
     const float *pw_nk = nullptr;  // set by blk(): [C_out][C_in] 1x1 weights for the tensor-core path
@@ -1010,9 +1017,15 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if ((rc = blk("enc.erb_conv2", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
         p = mk(f.e2, E / 4, (int64_t)E / 4 * kCh, f.e3, E / 4, e3_fs, c.conv_kt);
         if ((rc = blk("enc.erb_conv3", p)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_nk))) return rc;
-        p = mk(d_feat_spec, Fd, (int64_t)Fd * 2, f.c0, Fd, (int64_t)Fd * kCh, c.inp_kt);
-        p.lookahead = c.conv_lookahead;
-        if ((rc = blk("enc.df_conv0", p)) || (rc = run_dwpw<DW_DF0>(s, p, B, pw_nk))) return rc;
+        {
+            const float *w, *bb;
+            if ((rc = need(m, "enc.df_conv0.w", c.inp_kt * 3 * 2 * kCh, &w)) || (rc = need(m, "enc.df_conv0.b", kCh, &bb))) return rc;
+            dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
+            int smem = (kInFrames + c.inp_kt - 1) * (Fd + 2) * 2 * 4;
+            DFB_PROF("k_conv_in[df_conv0]", s);
+            k_conv_in<2><<<grid, 256, smem, s>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead);
+            DFB_LAUNCH_CHECK();
+        }
         p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
         if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
     }

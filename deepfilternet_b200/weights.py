@@ -13,7 +13,8 @@ Packed tensors (name -> layout):
                                       convt2, convt1 (ConvTranspose2d taps as stored, kt = 1)
   <blk>.pw          [C_in][C_out]     1x1 conv, transposed, BN folded
   <blk>.b           [C]
-  enc.df_conv0.dw   [kt][3][C]        2->C grouped conv: out channel c reads input c // (C/2)
+  enc.df_conv0.w    [kt][3][2][C]     grouped 2->C conv composed with its 1x1 conv and BN (direct K = 18 conv)
+  enc.df_conv0.dw   [kt][3][C]        (unfused form, kept for reference) 2->C grouped conv taps
   enc.df_conv0.pw/.b
   erb_dec.conv{3,2,1,0}p.s / .b  [C]  depthwise 1x1 + BN folded: relu(x * s + b)
   erb_dec.conv0_out.w [kt][3][C]      C->1 conv, BN folded;  erb_dec.conv0_out.b [1]
@@ -111,6 +112,11 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
     assert dw.shape[2] == inp_kt
     pw = _np(sd[f"enc.df_conv0.{convs[1]}.weight"]).astype(np.float64)[:, :, 0, 0]
     s, b = _bn_fold(sd, f"enc.df_conv0.{bns[0]}")
+    # composed weights of the direct 2 -> C conv: W[dt][df][ri][n] = sum_{c in group ri} dw[c][dt][df] * pw'[n][c]
+    g = C // 2
+    pws = pw * s[:, None]                                 # [n][c], BN folded
+    weff = np.stack([np.einsum("ctf,nc->tfn", dw[ri * g:(ri + 1) * g, 0], pws[:, ri * g:(ri + 1) * g]) for ri in range(2)], axis=2)
+    out["enc.df_conv0.w"] = f32(weff)                     # [kt][3][2][C]
     out["enc.df_conv0.dw"] = f32(dw[:, 0].transpose(1, 2, 0))
     out["enc.df_conv0.pw"] = f32((pw * s[:, None]).T)
     out["enc.df_conv0.pw_nk"] = f32(pw * s[:, None])
