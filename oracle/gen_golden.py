@@ -75,6 +75,30 @@ def main():
             spec=spec.numpy(), feat_erb=ef.numpy(), feat_spec=sf.numpy(), spec_e=spec_e.numpy(),
             m=m.numpy(), lsnr=lsnr.numpy(),
             coefs=(c if c.dim() == 5 else torch.zeros(0)).numpy())
+    # DeepFilterNet3_ll ships only as ONNX: build the reference DfNet from its config (epoch="none"),
+    # load the transplanted weights (deepfilternet_b200/onnx_import.py) and record the reference outputs.
+    sys.path.insert(0, ROOT)
+    from deepfilternet_b200.config import load_config
+    from deepfilternet_b200.onnx_import import state_dict_from_onnx_dir
+    ll_dir = os.path.join(d, "DeepFilterNet3_ll_onnx")
+    model, st, _, _ = init_df(ll_dir, log_file=None, log_level="ERROR", epoch="none")
+    sd_ll = state_dict_from_onnx_dir(ll_dir, load_config(os.path.join(ll_dir, "config.ini"), env={}))
+    missing, unexpected = model.load_state_dict(sd_ll, strict=False)
+    assert not unexpected and all(k in ("erb_fb", "mask.erb_inv_fb") or "df_fc_a" in k for k in missing), (missing, unexpected)
+    model.eval()
+    out = enhance(model, st, noisy, pad=True)
+    kat["DeepFilterNet3_ll"] = dict(target=None, reference_modules_plus_oracle=rh.si_sdr(clean, out.numpy()), epoch=0,
+                                    n_samples=int(noisy.shape[1]))
+    print("DeepFilterNet3_ll", kat["DeepFilterNet3_ll"])
+    x = torch.stack([noisy[0, 96000:120000], 0.5 * noisy[0, 130000:154000]])
+    y = enhance(model, st, x, pad=True)
+    xa = F.pad(x, (0, st.fft_size()))
+    spec, ef, sf = df_features(xa, st, 96)
+    with torch.no_grad():
+        spec_e, m, lsnr, c = model(spec.clone(), ef, sf)
+    np.savez_compressed(os.path.join(GOLD, "dfnet_DeepFilterNet3_ll.npz"), audio=x.numpy(), enhanced=y.numpy(),
+                        spec=spec.numpy(), feat_erb=ef.numpy(), feat_spec=sf.numpy(), spec_e=spec_e.numpy(), m=m.numpy(),
+                        lsnr=lsnr.numpy())
     with open(os.path.join(GOLD, "erb_widths.json"), "w") as f:
         json.dump(dict(params=dict(sr=48000, fft_size=960, nb_bands=32, min_nb_freqs=2),
                        from_checkpoint_erb_fb=widths), f, indent=1)

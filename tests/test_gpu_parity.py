@@ -170,6 +170,17 @@ def test_golden_reference_outputs(name, golden_dir, model_dir):
     assert rms(spec_e, g["spec_e"]) < TOL_SPEC and rms(m, g["m"]) < TOL_M and np.abs(lsnr.numpy() - g["lsnr"]).max() < TOL_LSNR
 
 
+def test_ll_onnx_model_end_to_end(golden_dir, model_dir):
+    """DeepFilterNet3_ll (ONNX-only weights, H = 512, zero look-ahead, kt = 2 convs): init_df on the ONNX
+    directory, against the reference modules' outputs with the transplanted weights."""
+    g = np.load(os.path.join(golden_dir, "dfnet_DeepFilterNet3_ll.npz"))
+    model, st, suffix, epoch = init_df(os.path.join(model_dir, "DeepFilterNet3_ll"), log_level="ERROR")
+    assert (model.cfg.conv_lookahead, model.cfg.df_lookahead, model.cfg.emb_hidden_dim) == (0, 0, 512)
+    assert rms(enhance(model, st, torch.from_numpy(g["audio"])), g["enhanced"]) < RMS_TOL
+    spec_e, m, lsnr, _ = model(torch.from_numpy(g["spec"]), torch.from_numpy(g["feat_erb"]), torch.from_numpy(g["feat_spec"]))
+    assert rms(spec_e, g["spec_e"]) < TOL_SPEC and rms(m, g["m"]) < TOL_M
+
+
 @pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
 def test_si_sdr_known_answer_gpu(name, golden_dir, model_dir):
     """The reference CI's known answer (df/scripts/test_df.py:44-78, atol = rtol = 1e-4) on the CUDA path."""

@@ -101,6 +101,36 @@ def test_dfnet_oracle_matches_reference_modules(name, golden_dir, model_dir):
     assert float(np.sqrt(((o3.numpy() - g["enhanced_atten12"]) ** 2).mean())) < 1e-6
 
 
+def test_ll_oracle_matches_reference_modules_with_transplanted_onnx_weights(golden_dir, model_dir):
+    """DeepFilterNet3_ll ships only as ONNX: tests/golden/dfnet_DeepFilterNet3_ll.npz holds the outputs of the
+    reference DfNet (built from the _ll config) carrying the transplanted weights."""
+    from deepfilternet_b200.onnx_import import state_dict_from_onnx_dir
+    d = os.path.join(model_dir, "DeepFilterNet3_ll")
+    cfg = load_config(os.path.join(d, "config.ini"), env={})
+    sd = state_dict_from_onnx_dir(d, cfg)
+    g = np.load(os.path.join(golden_dir, "dfnet_DeepFilterNet3_ll.npz"))
+    out, aux = O.enhance(sd, cfg.as_dict(), torch.from_numpy(g["audio"]), pad=True, return_all=True)
+    assert np.abs(aux["m"].numpy() - g["m"]).max() < 1e-5
+    assert np.abs(aux["spec_e"].numpy() - g["spec_e"]).max() < 1e-6
+    assert float(np.sqrt(((out.numpy() - g["enhanced"]) ** 2).mean())) < 1e-6
+
+
+def test_onnx_transplant_equals_checkpoint(model_dir):
+    """The ONNX export of DeepFilterNet3 ships next to its checkpoint: the transplant must reproduce the
+    checkpoint's packed tensors (BN folded by torch at export vs folded here)."""
+    from deepfilternet_b200.onnx_import import state_dict_from_onnx_dir
+    from deepfilternet_b200.weights import pack_state_dict
+    d = os.path.join(model_dir, "DeepFilterNet3_onnx")
+    if not os.path.isdir(d):
+        pytest.skip("DeepFilterNet3_onnx not unpacked")
+    cfg = load_config(os.path.join(model_dir, "DeepFilterNet3", "config.ini"), env={})
+    pa, da = pack_state_dict(state_dict_from_onnx_dir(d, cfg), cfg)
+    pb, db = pack_state_dict(load_state_dict_file(find_checkpoint(os.path.join(model_dir, "DeepFilterNet3", "checkpoints"))[0]), cfg)
+    assert da == db and set(pb) <= set(pa)
+    for k, b in pb.items():
+        assert np.abs(pa[k] - b).max() <= 1e-6 * (np.abs(b).max() + 1e-12) + 1e-9, k
+
+
 @pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
 def test_si_sdr_known_answer(name, golden_dir, model_dir):
     """DeepFilterNet/df/scripts/test_df.py:44-78: SI-SDR of enhance(noisy_snr0) vs clean, atol=rtol=1e-4."""
