@@ -35,14 +35,20 @@ SR, SECONDS, STREAMS_PER_GPU = 48000, 10, 128
 FLOP_PER_FRAME = {"DeepFilterNet3": 6_614_784, "DeepFilterNet2": 6_956_800, "DeepFilterNet3_ll": 21_846_784}
 # Per-kernel algorithmic figures per frame per stream for the roofline line ("Kernels")
 KERNEL_MODEL = {
-    # name: (bound, unit per frame, "bytes"|"flops")
+    # name: (bound, algorithmic unit per frame per stream, "bytes"|"flops")   -- DESIGN.md section 4
     "k_analysis": ("hbm", 1920 + 3848 + 128, "bytes"),
     "k_feat_norm": ("hbm", 128 + 768 + 128 + 768, "bytes"),
     "k_apply_synthesis": ("hbm", 3848 + 128 + 3840 + 1920, "bytes"),
-    "k_grouped_linear[gru_proj]": ("tensor", 2 * 5 * 256 * 768, "flops"),   # 5 GRU layers, W_ih x
-    "k_gru": ("tensor", 2 * 5 * 256 * 768, "flops"),                        # 5 GRU layers, W_hh h
+    "k_gru_tc": ("tensor", 2 * 5 * 256 * 768, "flops"),                      # 5 GRU layers, W_hh h (fp32-equivalent flops)
+    "k_gru": ("tensor", 2 * 5 * 256 * 768, "flops"),
+    "k_gemm_bf16x3[gru_proj]": ("tensor", 2 * 5 * 256 * 768, "flops"),      # 5 GRU layers, W_ih x
+    "k_grouped_linear[gru_proj]": ("tensor", 2 * 5 * 256 * 768, "flops"),
+    "k_grouped_linear": ("tensor", 2 * (3072 * 16 + 512 * 16 + 256 * 32 + 512 * 16 + 256 * 32 + 512 * 32 + 512 * 16 + 256 * 60), "flops"),
     "k_dwpw": ("tensor", 2 * 64 * 64 * (16 + 8 + 8 + 48 + 8 + 16 + 32), "flops"),
-    "k_dwpw[df_conv0]": ("tensor", 2 * 64 * 64 * 96, "flops"),
+    "k_conv_in[df_conv0]": ("hbm", 96 * 8 + 96 * 256, "bytes"),             # reads feat_spec, writes c0
+    "k_conv_in[erb_conv0]": ("hbm", 128 + 32 * 256, "bytes"),
+    "k_df_convp": ("hbm", 96 * 256 + 2 * 96 * 40, "bytes"),                 # reads c0 once, read-modify-write coefs
+    "k_mask_out": ("hbm", 2 * 32 * 256 + 128, "bytes"),
 }
 
 

@@ -191,46 +191,60 @@ struct GlParams {
     float oscale, ooffset;
     unsigned short *y_hi, *y_lo;  // optional BF16 hi/lo planes of y (same pitch): operand of a tcgen05 GEMM
 };
-constexpr int kGlBM = 64, kGlBN = 64, kGlBK = 32;
+constexpr int kGlBM = 64, kGlBN = 64, kGlBK = 32, kGlMaxGpc = 4;
 
+// Narrow groups (Hg = 16 or 32) are packed kGpc = 64 / Hg per CTA so that all 256 threads own real
+// output columns (the first version ran one group per CTA: 25 % of the threads active for Hg = 16).
 __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
-    __shared__ __align__(16) float As[kGlBM][kGlBK + 4];
+    __shared__ __align__(16) float As[kGlMaxGpc][kGlBM][kGlBK + 4];
     __shared__ __align__(16) float Ws[kGlBK][kGlBN];
-    const int tiles_per_group = (p.Hg + kGlBN - 1) / kGlBN;
-    const int g = blockIdx.y / tiles_per_group, nt = blockIdx.y - g * tiles_per_group;
-    const int n0 = nt * kGlBN;
-    const int ncols = min(kGlBN, p.Hg - n0);
+    const int gpc = (p.Hg < kGlBN && kGlBN % p.Hg == 0) ? min(kGlBN / p.Hg, p.G) : 1;  // groups per CTA
+    const int tiles_per_group = (p.Hg + kGlBN - 1) / kGlBN;                         // > 1 only when gpc == 1
+    const int gb = blockIdx.y / tiles_per_group, nt = blockIdx.y - gb * tiles_per_group;
+    const int g0 = gb * gpc;                       // first group of this CTA
+    const int n0 = nt * kGlBN;                     // column offset inside the group (gpc == 1)
+    const int wcols = gpc > 1 ? p.Hg : min(kGlBN, p.Hg - n0);  // valid columns per group in this tile
+    const int ngrp = min(gpc, p.G - g0);
     const int64_t m0 = (int64_t)blockIdx.x * kGlBM;
     const int tid = threadIdx.x;
     const int tc = tid & 15, tr = tid >> 4;  // thread tile: rows tr + 16 i, cols 4 tc .. 4 tc + 3
+    const int gsub = gpc > 1 ? (tc * 4) / p.Hg : 0;  // which of the CTA's groups this thread's columns belong to
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-    const float *xg = p.x + (int64_t)g * p.Ig;
-    const float *wg = p.w + (int64_t)g * p.Ig * p.Hg;
     for (int k0 = 0; k0 < p.Ig; k0 += kGlBK) {
         const int kc = min(kGlBK, p.Ig - k0);
-        // A tile: 64 rows x 32 k  (8 threads x float4 per row)
-        for (int i = tid; i < kGlBM * (kGlBK / 4); i += 256) {
-            int r = i >> 3, kq = (i & 7) * 4;
+        // A tiles: per group 64 rows x 32 k  (8 threads x float4 per row)
+        for (int i = tid; i < ngrp * kGlBM * (kGlBK / 4); i += 256) {
+            const int gs = i / (kGlBM * (kGlBK / 4)), rem = i - gs * (kGlBM * (kGlBK / 4));
+            const int r = rem >> 3, kq = (rem & 7) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            int64_t m = m0 + r;
-            if (m < p.M && kq < kc) v = *reinterpret_cast<const float4 *>(xg + m * p.ldx + k0 + kq);
-            *reinterpret_cast<float4 *>(&As[r][kq]) = v;
+            const int64_t m = m0 + r;
+            if (m < p.M && kq < kc) v = *reinterpret_cast<const float4 *>(p.x + m * p.ldx + (int64_t)(g0 + gs) * p.Ig + k0 + kq);
+            *reinterpret_cast<float4 *>(&As[gs][r][kq]) = v;
         }
-        // W tile: 32 k x 64 n
+        // W tile: 32 k x 64 columns (column n -> group n / Hg when several groups share the CTA)
         for (int i = tid; i < kGlBK * kGlBN; i += 256) {
-            int k = i >> 6, n = i & 63;
-            Ws[k][n] = (k < kc && n < ncols) ? wg[(int64_t)(k0 + k) * p.Hg + n0 + n] : 0.f;
+            const int k = i >> 6, n = i & 63;
+            float v = 0.f;
+            if (k < kc) {
+                if (gpc > 1) {
+                    const int gs = n / p.Hg, nn = n - gs * p.Hg;
+                    if (gs < ngrp) v = p.w[((int64_t)(g0 + gs) * p.Ig + k0 + k) * p.Hg + nn];
+                } else if (n < wcols) {
+                    v = p.w[((int64_t)g0 * p.Ig + k0 + k) * p.Hg + n0 + n];
+                }
+            }
+            Ws[k][n] = v;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kGlBK; k += 4) {
             float4 a[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(&As[tr + 16 * i][k]);
+            for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(&As[gsub][tr + 16 * i][k]);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
                 float4 w = *reinterpret_cast<const float4 *>(&Ws[k + kk][tc * 4]);
@@ -243,24 +257,46 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
         }
         __syncthreads();
     }
+    // columns of this thread: group g0 + gsub, inside-group offset nn0 .. nn0 + 3
+    const int nn0 = gpc > 1 ? tc * 4 - gsub * p.Hg : n0 + tc * 4;
+    if (gsub >= ngrp) return;
+    const int colbase = (g0 + gsub) * p.Hg + nn0;
+    const int nvalid = min(4, p.Hg - nn0);  // <= 0 when the thread's columns are past the group end
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         int64_t m = m0 + tr + 16 * i;
-        if (m >= p.M) continue;
+        if (m >= p.M || nvalid <= 0) continue;
+        float v[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            int n = tc * 4 + j;
-            if (n >= ncols) continue;
-            int col = g * p.Hg + n0 + n;
-            float v = acc[i][j];
-            if (p.bias) v += p.bias[col];
-            v = act_apply(v, p.act) * p.oscale + p.ooffset;
-            if (p.res) v += p.res[m * p.ldr + col];
-            p.y[m * p.ldy + col] = v;
-            if (p.y_hi) {
-                __nv_bfloat16 hb = __float2bfloat16_rn(v);
-                p.y_hi[m * p.ldy + col] = __bfloat16_as_ushort(hb);
-                p.y_lo[m * p.ldy + col] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hb)));
+            v[j] = acc[i][j];
+            if (j < nvalid) {
+                const int col = colbase + j;
+                if (p.bias) v[j] += p.bias[col];
+                v[j] = act_apply(v[j], p.act) * p.oscale + p.ooffset;
+                if (p.res) v[j] += p.res[m * p.ldr + col];
+            }
+        }
+        float *dst = p.y + m * p.ldy + colbase;
+        if (nvalid == 4 && (((uintptr_t)dst) & 15) == 0) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int j = 0; j < nvalid; j++) dst[j] = v[j];
+        }
+        if (p.y_hi) {
+            unsigned short hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                __nv_bfloat16 hb = __float2bfloat16_rn(v[j]);
+                hi[j] = __bfloat16_as_ushort(hb);
+                lo[j] = __bfloat16_as_ushort(__float2bfloat16_rn(v[j] - __bfloat162float(hb)));
+            }
+            unsigned short *dh = p.y_hi + m * p.ldy + colbase, *dl = p.y_lo + m * p.ldy + colbase;
+            if (nvalid == 4 && (((uintptr_t)dh) & 7) == 0) {
+                *reinterpret_cast<uint2 *>(dh) = make_uint2(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16);
+                *reinterpret_cast<uint2 *>(dl) = make_uint2(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16);
+            } else {
+                for (int j = 0; j < nvalid; j++) { dh[j] = hi[j]; dl[j] = lo[j]; }
             }
         }
     }
@@ -777,7 +813,8 @@ int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const fl
     GlParams p{x, ldx, w, bias, res, ldr, y, ldy, M, G, I / G, Hh / G, act, oscale, ooffset, y_hi, y_lo};
     if ((p.Ig % 4) || (ldx % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: K not a multiple of 4");
     int tiles = (p.Hg + kGlBN - 1) / kGlBN;
-    dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(G * tiles));
+    int gpc = (p.Hg < kGlBN && kGlBN % p.Hg == 0) ? (kGlBN / p.Hg < G ? kGlBN / p.Hg : G) : 1;
+    dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(((G + gpc - 1) / gpc) * tiles));
     DFB_PROF(p.G == 1 && p.bias && p.Hg >= 512 ? "k_grouped_linear[gru_proj]" : "k_grouped_linear", s);
     k_grouped_linear<<<grid, 256, 0, s>>>(p);
     DFB_LAUNCH_CHECK();
