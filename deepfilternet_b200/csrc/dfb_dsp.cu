@@ -15,6 +15,7 @@
 // f32[B,Tf,32] and c64[B,Tf,96]; every kernel reads/writes whole rows with consecutive lanes on
 // consecutive addresses.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "dfb_common.cuh"
@@ -112,6 +113,24 @@ __device__ __forceinline__ void warp_fft480(LoadF load, const float2 (&tw)[kN1],
     }
     __syncwarp();
     if (lane < kN2) fft480_pass_a<INV>(a, tw, buf, lane);
+    __syncwarp();
+    float2 b[kN2];
+    if (lane < kN1) fft480_pass_b<INV>(b, buf, lane);
+    __syncwarp();
+    if (lane < kN1) fft480_store_natural(b, buf, lane);
+    __syncwarp();
+}
+
+// variant with the pass-A twiddles of this lane read from memory (tw_lane -> 20 float2)
+template <bool INV, typename LoadF>
+__device__ __forceinline__ void warp_fft480_twptr(LoadF load, const float2 *tw_lane, float2 *buf, int lane) {
+    float2 a[kN1];
+    if (lane < kN2) {
+#pragma unroll
+        for (int n1 = 0; n1 < kN1; n1++) a[n1] = load(kN2 * n1 + lane);
+    }
+    __syncwarp();
+    if (lane < kN2) fft480_pass_a_ptr<INV>(a, tw_lane, buf, lane);
     __syncwarp();
     float2 b[kN2];
     if (lane < kN1) fft480_pass_b<INV>(b, buf, lane);
@@ -327,7 +346,7 @@ __device__ __forceinline__ float2 apply_bin(const ApplyParams &p, const DspTable
     return y;
 }
 
-__global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis(ApplyParams p, DspTables tb) {
+__global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis_generic(ApplyParams p, DspTables tb) {
     __shared__ __align__(16) float s_win[kFft];
     __shared__ __align__(16) float2 s_tw960[241];
     __shared__ __align__(16) float2 s_buf[kSynWarps][kTileFloat2];
@@ -376,6 +395,147 @@ __global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis(ApplyParams 
             // reads of nat complete inside pass A before pass B overwrites it (warp syncs inside)
             warp_fft480<true>([&](int n) { return nat[n]; }, tw, nat, lane);
             // nat[n] = (x[2n], x[2n+1]); window in place
+#pragma unroll
+            for (int j = 0; j < 15; j++) {
+                int n = lane + 32 * j;
+                float2 v = nat[n];
+                float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * n);
+                nat[n] = make_float2(v.x * w.x, v.y * w.y);
+            }
+            __syncwarp();
+            float *orow = p.audio + (int64_t)b * p.out_stride;
+#pragma unroll
+            for (int j = 0; j < 15; j++) {
+                int i = lane + 32 * j;
+                float o = yb[i] + tail[j];      // lib.rs:407-411
+                tail[j] = yb[kHop + i];         // lib.rs:423-426 (hop == fft/2)
+                int64_t g = (int64_t)t * kHop + i - p.out_offset;
+                if (t >= t0 && g >= 0 && g < p.out_len) orow[g] = o;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Specialised version for the shipped models (df_order 5, nb_df 96, 32 ERB bands): a lane owns the bins
+// k = lane + 32 j (and 480 - k) for every frame of its chunk, so the deep-filter input history of its DF
+// bins lives in registers as a 5-deep shift register (one new look-ahead value per bin and frame instead of
+// five reloads), the band gains come from one register per lane via warp shuffles, and all global loads of
+// a frame are issued up front, coalesced (256-byte rows), before any use.
+template <int ORDER, int NDFJ, int MINB>
+__global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyParams p, DspTables tb) {
+    __shared__ __align__(16) float s_win[kFft];
+    __shared__ __align__(16) float2 s_tw960[241];
+    __shared__ __align__(16) float2 s_buf[kSynWarps][kTileFloat2];
+    __shared__ __align__(16) float2 s_twa[kN2 * kN1];  // pass-A twiddles, reloaded into registers per frame
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kFft; i += blockDim.x) s_win[i] = tb.window[i];
+    for (int i = tid; i < 241; i += blockDim.x) s_tw960[i] = tb.tw960[i];
+    for (int i = tid; i < kN2 * kN1; i += blockDim.x) s_twa[i] = tb.tw_a_inv[i];
+    __syncthreads();
+    const int t0 = (blockIdx.x * kSynWarps + warp) * kSynChunk;
+    if (t0 >= p.Tf) return;
+    const int t1 = min(t0 + kSynChunk, p.Tf);
+    const int Tf = p.Tf, L = p.lookahead, back = ORDER - 1 - L;
+    const float2 *srow0 = p.spec + (int64_t)b * Tf * kF;
+    const float *mrow0 = p.m + (int64_t)b * Tf * 32;
+    const bool masked_df = p.mode == 2;
+    // bands of this lane's bins: bk[j] for k = lane + 32 j, bn[j] for 480 - k
+    unsigned long long bkp = 0, bnp = 0;  // 8 band indices each, one byte per j
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int k = lane + 32 * j;
+        bkp |= (unsigned long long)(k <= 240 ? tb.band_of_bin[k] : 0) << (8 * j);
+        bnp |= (unsigned long long)(k <= 240 ? tb.band_of_bin[kC - k] : 0) << (8 * j);
+    }
+#define BK(j) ((int)((bkp >> (8 * (j))) & 0xff))
+#define BN(j) ((int)((bnp >> (8 * (j))) & 0xff))
+    float2 *nat = s_buf[warp];
+    float *yb = reinterpret_cast<float *>(nat);
+    float tail[15];
+#pragma unroll
+    for (int j = 0; j < 15; j++) tail[j] = 0.f;
+    // S'[tt][k] for the DF bins; tt = t + o - back.  Rows outside [0, Tf) are zero (multiframe.py:72-74).
+    auto load_df_row = [&](int tt, float2 (&dst)[NDFJ]) {
+        float g = 1.f;
+        const bool ok = tt >= 0 && tt < Tf;
+        float mrow = (ok && masked_df) ? mrow0[(int64_t)tt * 32 + lane] : 1.f;
+#pragma unroll
+        for (int j = 0; j < NDFJ; j++) {
+            float2 v = ok ? srow0[(int64_t)tt * kF + lane + 32 * j] : make_float2(0.f, 0.f);
+            if (masked_df) { g = __shfl_sync(0xffffffffu, mrow, BK(j)); v.x *= g; v.y *= g; }
+            dst[j] = v;
+        }
+    };
+    const int tstart = t0 > 0 ? t0 - 1 : 0;
+    float2 hist[ORDER][NDFJ];
+#pragma unroll
+    for (int o = 1; o < ORDER; o++) load_df_row(tstart + o - 1 - back, hist[o]);  // becomes taps 0..O-2 after the first shift
+    for (int t = tstart; t < t1; t++) {
+        // ---- loads of this frame, all issued before use
+        const float mcur = mrow0[(int64_t)t * 32 + lane];
+#pragma unroll
+        for (int o = 0; o < ORDER - 1; o++)
+#pragma unroll
+            for (int j = 0; j < NDFJ; j++) hist[o][j] = hist[o + 1][j];
+        load_df_row(t + L, hist[ORDER - 1]);
+        float2 cf[NDFJ][ORDER];
+        const float2 *crow = reinterpret_cast<const float2 *>(p.coefs + ((int64_t)b * Tf + t) * (NDFJ * 32) * (2 * ORDER));
+#pragma unroll
+        for (int j = 0; j < NDFJ; j++)
+#pragma unroll
+            for (int o = 0; o < ORDER; o++) cf[j][o] = crow[(lane + 32 * j) * ORDER + o];
+        float2 xk[8], xn[8];
+        const float2 *srow = srow0 + (int64_t)t * kF;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = lane + 32 * j;
+            xk[j] = (k <= 240 && (j >= NDFJ || p.atten_lim > 0.f)) ? srow[k] : make_float2(0.f, 0.f);
+            xn[j] = k <= 240 ? srow[kC - k] : make_float2(0.f, 0.f);
+        }
+        // ---- deep filter (bins < 96), gain (others), optional attenuation limit
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = lane + 32 * j;
+            float2 y;
+            if (j < NDFJ) {
+                float yr = 0.f, yi = 0.f;
+#pragma unroll
+                for (int o = 0; o < ORDER; o++) {
+                    const float2 s = hist[o][j], w = cf[j][o];
+                    yr += s.x * w.x - s.y * w.y;
+                    yi += s.x * w.y + s.y * w.x;
+                }
+                y = make_float2(yr, yi);
+            } else {
+                const float g = __shfl_sync(0xffffffffu, mcur, BK(j));
+                y = make_float2(xk[j].x * g, xk[j].y * g);
+            }
+            const float gn = __shfl_sync(0xffffffffu, mcur, BN(j));
+            float2 yn = make_float2(xn[j].x * gn, xn[j].y * gn);
+            if (p.atten_lim > 0.f) {
+                const float a = p.atten_lim, c = 1.f - a;
+                y.x = xk[j].x * a + y.x * c; y.y = xk[j].y * a + y.y * c;
+                yn.x = xn[j].x * a + yn.x * c; yn.y = xn[j].y * a + yn.y * c;
+            }
+            if (k <= 240) {
+                if (p.spec_out && t >= t0) {
+                    float2 *orow = p.spec_out + ((int64_t)b * Tf + t) * kF;
+                    orow[k] = y;
+                    orow[kC - k] = yn;
+                }
+                if (k == 0) { y.y = 0.f; yn.y = 0.f; }  // imag of DC / Nyquist ignored (lib.rs:402)
+                const float2 w = s_tw960[k];
+                float2 zk, znk;
+                irfft_merge(y, yn, make_float2(w.x, -w.y), zk, znk);
+                nat[k] = zk;
+                if (k > 0 && k < 240) nat[kC - k] = znk;
+            }
+        }
+        __syncwarp();
+        if (p.audio) {
+            warp_fft480_twptr<true>([&](int n) { return nat[n]; }, s_twa + (lane < kN2 ? lane : 0) * kN1, nat, lane);
 #pragma unroll
             for (int j = 0; j < 15; j++) {
                 int n = lane + 32 * j;
@@ -619,7 +779,13 @@ int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaS
     int per_cta = kSynWarps * kSynChunk;
     dim3 grid((unsigned)((p.Tf + per_cta - 1) / per_cta), (unsigned)B);
     DFB_PROF("k_apply_synthesis", s);
-    k_apply_synthesis<<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
+    static const int minb = getenv("DFB_APPLY_MINB") ? atoi(getenv("DFB_APPLY_MINB")) : 3;
+    if (p.mode != 0 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs && minb == 3)
+        k_apply_synthesis<5, 3, 3><<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
+    else if (p.mode != 0 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs && minb == 2)
+        k_apply_synthesis<5, 3, 2><<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
+    else
+        k_apply_synthesis_generic<<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }

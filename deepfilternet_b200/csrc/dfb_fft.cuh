@@ -209,6 +209,14 @@ DFB_HD void fft480_pass_a(float2 (&a)[kN1], const float2 (&tw)[kN1], float2* til
     for (int k1 = 0; k1 < kN1; k1++) tile[k1 * kTileStride + lane] = cmul(a[k1], tw[k1]);
 }
 
+// Same with the twiddles read through a pointer (e.g. shared memory) instead of held in registers.
+template <bool INV>
+DFB_HD void fft480_pass_a_ptr(float2 (&a)[kN1], const float2* tw, float2* tile, int lane) {
+    Dft<kN1, INV>::run(a);
+#pragma unroll
+    for (int k1 = 0; k1 < kN1; k1++) tile[k1 * kTileStride + lane] = cmul(a[k1], tw[k1]);
+}
+
 // Pass B, read phase: lane k1 < 20 gathers its column and transforms it.
 template <bool INV>
 DFB_HD void fft480_pass_b(float2 (&b)[kN2], const float2* tile, int lane) {
