@@ -99,7 +99,7 @@ constexpr int kFft = 960, kHop = 480, kF = 481;
 constexpr int kAnaWarps = 8;           // frames per CTA in the analysis kernel (one per warp)
 constexpr int kSynWarps = 4;           // warps per CTA in the synthesis kernel
 constexpr int kSynChunk = 16;          // consecutive frames per warp in the synthesis kernel
-constexpr int kAnaSmem = sizeof(float) * ((kAnaWarps + 1) * 480 + 960) + sizeof(float2) * (242 + kAnaWarps * kTileFloat2);
+constexpr int kAnaSmem = sizeof(float) * ((kAnaWarps + 1) * 480 + 960) + sizeof(float2) * (242 + kN2 * kN1 + kAnaWarps * kTileFloat2);
 
 // One warp: 480-point complex FFT of the values gathered by `load(n)` (n = 24 n1 + lane), result
 // in natural order in buf[0..480).  `buf` is a per-warp shared buffer of kTileFloat2 float2 that
@@ -142,14 +142,15 @@ __device__ __forceinline__ void warp_fft480_twptr(LoadF load, const float2 *tw_l
 // ---------------------------------------------------------------------------- analysis ----
 // grid (ceil(Tf / kAnaWarps), B), block 32 * kAnaWarps.  Warp w transforms frame t0 + w.
 // Algorithmic HBM bytes per frame: 1920 R (audio hop) + 3848 W (spec) + 128 W (erb dB).
-__global__ void __launch_bounds__(32 * kAnaWarps)
+__global__ void __launch_bounds__(32 * kAnaWarps, 3)
 k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restrict__ spec,
            float *__restrict__ erb_db, DspTables tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_stage = reinterpret_cast<float *>(smem_raw);                    // (W + 1) * hop
     float *s_win = s_stage + (kAnaWarps + 1) * kHop;                         // fft
     float2 *s_tw960 = reinterpret_cast<float2 *>(s_win + kFft);              // 241 (+1 pad)
-    float2 *s_buf = s_tw960 + 242;                                           // W * kTileFloat2
+    float2 *s_twa = s_tw960 + 242;                                           // pass-A twiddles [24][20]
+    float2 *s_buf = s_twa + kN2 * kN1;                                       // W * kTileFloat2
     const int b = blockIdx.y, t0 = blockIdx.x * kAnaWarps;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *x = audio + (int64_t)b * T;
@@ -162,21 +163,19 @@ k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restric
     }
     for (int i = tid; i < kFft; i += blockDim.x) s_win[i] = tb.window[i];
     for (int i = tid; i < 241; i += blockDim.x) s_tw960[i] = tb.tw960[i];
-    float2 tw[kN1];
-#pragma unroll
-    for (int k1 = 0; k1 < kN1; k1++) tw[k1] = lane < kN2 ? tb.tw_a_fwd[lane * kN1 + k1] : make_float2(0.f, 0.f);
+    for (int i = tid; i < kN2 * kN1; i += blockDim.x) s_twa[i] = tb.tw_a_fwd[i];
     __syncthreads();
     const int t = t0 + warp;
     if (t >= Tf) return;
     const float *fr = s_stage + warp * kHop;  // frame t = samples [(t-1) hop, (t+1) hop)
     float2 *nat = s_buf + warp * kTileFloat2;
-    warp_fft480<false>(
+    warp_fft480_twptr<false>(
         [&](int n) {
             float2 v = *reinterpret_cast<const float2 *>(fr + 2 * n);
             float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * n);
             return make_float2(v.x * w.x, v.y * w.y);
         },
-        tw, nat, lane);
+        s_twa + (lane < kN2 ? lane : 0) * kN1, nat, lane);
     // split step + wnorm, write spec row, keep |X|^2 for the band energies
     float2 *row = spec + ((int64_t)b * Tf + t) * kF;
     float pk[8], pnk[8];
@@ -779,7 +778,7 @@ int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaS
     int per_cta = kSynWarps * kSynChunk;
     dim3 grid((unsigned)((p.Tf + per_cta - 1) / per_cta), (unsigned)B);
     DFB_PROF("k_apply_synthesis", s);
-    static const int minb = getenv("DFB_APPLY_MINB") ? atoi(getenv("DFB_APPLY_MINB")) : 3;
+    static const int minb = getenv("DFB_APPLY_MINB") ? atoi(getenv("DFB_APPLY_MINB")) : 2;  // 2 CTAs/SM without spills measured fastest
     if (p.mode != 0 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs && minb == 3)
         k_apply_synthesis<5, 3, 3><<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
     else if (p.mode != 0 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs && minb == 2)

@@ -686,7 +686,7 @@ struct dfb_model {
     Arena arena;
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;             // DF decoder branch runs here, concurrently with the ERB decoder
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork_enc = nullptr, ev_join_enc = nullptr;
     const float *get(const std::string &n) const {
         auto it = t.find(n);
         return it == t.end() ? nullptr : it->second.first;
@@ -745,7 +745,9 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork_enc, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join_enc, cudaEventDisableTiming) != cudaSuccess) {
         dfb_model_free(m);
         return fail(DFB_ERR_CUDA, "stream creation failed");
     }
@@ -762,6 +764,8 @@ extern "C" void dfb_model_free(dfb_model *m) {
     if (m->aux) cudaStreamDestroy(m->aux);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->ev_fork_enc) cudaEventDestroy(m->ev_fork_enc);
+    if (m->ev_join_enc) cudaEventDestroy(m->ev_join_enc);
     delete m;
 }
 
@@ -1041,6 +1045,9 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if (m->precision == 1 && (r = need(m, (n + ".pw_nk").c_str(), kCh * kCh, &pw_nk))) return r;
         return DFB_OK;
     };
+    cudaStream_t sa = m->aux;  // the DF-branch input convs run concurrently with the ERB-branch convs
+    DFB_CUDA(cudaEventRecord(m->ev_fork_enc, s));
+    DFB_CUDA(cudaStreamWaitEvent(sa, m->ev_fork_enc, 0));
     auto mk = [&](const float *in, int Fin, int64_t in_fs, float *out, int Fout, int64_t out_fs, int kt) {
         DwPwParams p{};
         p.in = in; p.Fin = Fin; p.in_fs = in_fs; p.out = out; p.Fout = Fout; p.out_fs = out_fs; p.kt = kt; p.T = T;
@@ -1048,24 +1055,30 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         return p;
     };
     {
+        DwPwParams p{};
+        {
+            const float *w, *bb;
+            if ((rc = need(m, "enc.df_conv0.w", c.inp_kt * 3 * 2 * kCh, &w)) || (rc = need(m, "enc.df_conv0.b", kCh, &bb))) return rc;
+            dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
+            int smem = (kInFrames + c.inp_kt - 1) * (Fd + 2) * 2 * 4;
+            DFB_PROF("k_conv_in[df_conv0]", sa);
+            k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead);
+            DFB_LAUNCH_CHECK();
+        }
+        p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
+        if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(sa, p, B, pw_nk))) return rc;
+        DFB_CUDA(cudaEventRecord(m->ev_join_enc, sa));
+    }
+    {
         DwPwParams p = mk(f.e0, E, (int64_t)E * kCh, f.e1, E / 2, (int64_t)E / 2 * kCh, c.conv_kt);
         if ((rc = blk("enc.erb_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
         p = mk(f.e1, E / 2, (int64_t)E / 2 * kCh, f.e2, E / 4, (int64_t)E / 4 * kCh, c.conv_kt);
         if ((rc = blk("enc.erb_conv2", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
         p = mk(f.e2, E / 4, (int64_t)E / 4 * kCh, f.e3, E / 4, e3_fs, c.conv_kt);
         if ((rc = blk("enc.erb_conv3", p)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_nk))) return rc;
-        {
-            const float *w, *bb;
-            if ((rc = need(m, "enc.df_conv0.w", c.inp_kt * 3 * 2 * kCh, &w)) || (rc = need(m, "enc.df_conv0.b", kCh, &bb))) return rc;
-            dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
-            int smem = (kInFrames + c.inp_kt - 1) * (Fd + 2) * 2 * 4;
-            DFB_PROF("k_conv_in[df_conv0]", s);
-            k_conv_in<2><<<grid, 256, smem, s>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead);
-            DFB_LAUNCH_CHECK();
-        }
-        p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
-        if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
+
     }
+    DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join_enc, 0));  // c0 / c1 ready
     {
         // cemb = relu(df_fc_emb(c1 flat)); emb_in = e3 flat + cemb  (DFN2: concat)
         const float *w;
