@@ -63,6 +63,9 @@ SIGNATURES = {
     "dfb_erb_widths": (_I, [_I, _I, _I, _I, _I64P]),
     "dfb_analysis": (_I, [_VP, _VP, _I64, _I64, _VP, _VP]),
     "dfb_analysis_host": (_I, [_VP, _VP, _I64, _I64, _VP]),
+    "dfb_analysis_host_ex": (_I, [_VP, _VP, _I64, _I64, _I, _VP]),
+    "dfb_synthesis_host_ex": (_I, [_VP, _VP, _I64, _I64, _I, _VP]),
+    "dfb_state_reset": (_I, [_VP]),
     "dfb_synthesis": (_I, [_VP, _VP, _I64, _I64, _VP, _VP]),
     "dfb_synthesis_host": (_I, [_VP, _VP, _I64, _I64, _VP]),
     "dfb_erb_host": (_I, [_I, _VP, _I64, _I64, _I64P, _I, _I, _VP]),

@@ -103,6 +103,11 @@ struct ApplyParams {
     int64_t out_len;
     int Tf, mode, nb_df, order, lookahead;
     float atten_lim;      // 0 = off
+    // carried ISTFT state (pyDF synthesis(reset=False), mode 0 only): channel 0 starts from init_tail,
+    // channel c > 0 from the tail left by channel c - 1; the tail after the last frame goes to final_tail
+    const float *init_tail;  // [hop] or null
+    float *final_tail;       // [hop] or null
+    int carry;
 };
 
 }  // namespace dfb
@@ -110,7 +115,7 @@ struct ApplyParams {
 struct dfb_state;
 namespace dfb {
 int launch_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, float *d_erb_db,
-                    cudaStream_t s);
+                    cudaStream_t s, const float *d_init_mem = nullptr);
 int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float *d_spec, int Fd, int64_t spec_stride,
                      int64_t C, int64_t Tf, float alpha, const float *d_erb_state, const float *d_unit_state,
                      float *d_feat_erb, float *d_feat_spec, cudaStream_t s);
@@ -134,4 +139,6 @@ struct dfb_state {
     dfb::DspTables tb{};
     dfb::Arena arena;          // scratch of the *_host entry points
     cudaStream_t stream = nullptr;
+    // STFT / ISTFT memories carried between calls (libDF analysis_mem / synthesis_mem, lib.rs:60-62)
+    std::vector<float> analysis_mem, synthesis_mem;
 };

@@ -144,7 +144,7 @@ __device__ __forceinline__ void warp_fft480_twptr(LoadF load, const float2 *tw_l
 // Algorithmic HBM bytes per frame: 1920 R (audio hop) + 3848 W (spec) + 128 W (erb dB).
 __global__ void __launch_bounds__(32 * kAnaWarps, 3)
 k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restrict__ spec,
-           float *__restrict__ erb_db, DspTables tb) {
+           float *__restrict__ erb_db, DspTables tb, const float *__restrict__ init_mem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_stage = reinterpret_cast<float *>(smem_raw);                    // (W + 1) * hop
     float *s_win = s_stage + (kAnaWarps + 1) * kHop;                         // fft
@@ -159,7 +159,10 @@ k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restric
     const int64_t s_end = (int64_t)Tf * kHop;
     for (int i = tid; i < (kAnaWarps + 1) * kHop; i += blockDim.x) {
         int64_t s = s0 + i;
-        s_stage[i] = (s >= 0 && s < s_end) ? __ldg(x + s) : 0.f;
+        float v = 0.f;
+        if (s >= 0 && s < s_end) v = __ldg(x + s);
+        else if (s < 0 && init_mem) v = init_mem[(int64_t)b * kHop + (kHop + s)];  // carried analysis_mem (reset = False)
+        s_stage[i] = v;
     }
     for (int i = tid; i < kFft; i += blockDim.x) s_win[i] = tb.window[i];
     for (int i = tid; i < 241; i += blockDim.x) s_tw960[i] = tb.tw960[i];
@@ -366,8 +369,11 @@ __global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis_generic(Appl
     float *yb = reinterpret_cast<float *>(nat);  // 960 windowed samples of the current frame
     float tail[15];
 #pragma unroll
-    for (int j = 0; j < 15; j++) tail[j] = 0.f;
-    for (int t = (t0 > 0 ? t0 - 1 : 0); t < t1; t++) {
+    for (int j = 0; j < 15; j++) tail[j] = (p.carry && t0 == 0 && b == 0 && p.init_tail) ? p.init_tail[lane + 32 * j] : 0.f;
+    // carried state: channel b > 0 continues from the tail of channel b - 1's last frame, which is row -1
+    // relative to this channel in the contiguous [C,Tf,F] spectrum (mode 0 only)
+    const int tstart = t0 > 0 ? t0 - 1 : ((p.carry && b > 0) ? -1 : 0);
+    for (int t = tstart; t < t1; t++) {
         const float *crow = p.coefs ? p.coefs + ((int64_t)b * p.Tf + t) * p.nb_df * (2 * p.order) : nullptr;
         // gather X[k], X[480-k], merge into Z (natural order in `nat`)
 #pragma unroll
@@ -413,6 +419,10 @@ __global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis_generic(Appl
             }
         }
         __syncwarp();
+    }
+    if (p.final_tail && b == (int)gridDim.y - 1 && t1 == p.Tf) {
+#pragma unroll
+        for (int j = 0; j < 15; j++) p.final_tail[lane + 32 * j] = tail[j];
     }
 }
 
@@ -645,6 +655,8 @@ extern "C" int dfb_state_create(dfb_state **out, int device, int sr, int fft_siz
     dfb_state *st = new dfb_state();
     st->device = device; st->sr = sr; st->fft = fft_size; st->hop = hop_size; st->nb_erb = nb_erb;
     st->min_nb_erb_freqs = min_nb_erb_freqs;
+    st->analysis_mem.assign(fft_size - hop_size, 0.f);
+    st->synthesis_mem.assign(fft_size - hop_size, 0.f);
     st->erb.resize(nb_erb);
     dfb_erb_widths(sr, fft_size, nb_erb, min_nb_erb_freqs, st->erb.data());
     const int F = fft_size / 2 + 1;
@@ -747,13 +759,13 @@ extern "C" int dfb_state_params(const dfb_state *st, int *sr, int *fft, int *hop
 namespace dfb {
 
 int launch_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, float *d_erb_db,
-                    cudaStream_t s) {
+                    cudaStream_t s, const float *d_init_mem) {
     int64_t Tf = T / st->hop;
     if (C <= 0 || Tf <= 0) return DFB_OK;
     if (C > 65535) return fail(DFB_ERR_INVALID, "more than 65535 channels per call");
     dim3 grid((unsigned)((Tf + kAnaWarps - 1) / kAnaWarps), (unsigned)C);
     DFB_PROF("k_analysis", s);
-    k_analysis<<<grid, 32 * kAnaWarps, kAnaSmem, s>>>(d_audio, T, (int)Tf, (float2 *)d_spec, d_erb_db, st->tb);
+    k_analysis<<<grid, 32 * kAnaWarps, kAnaSmem, s>>>(d_audio, T, (int)Tf, (float2 *)d_spec, d_erb_db, st->tb, d_init_mem);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }
@@ -797,21 +809,43 @@ extern "C" int dfb_analysis(dfb_state *st, const float *d_audio, int64_t C, int6
     return launch_analysis(st, d_audio, C, T, d_spec, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int dfb_analysis_host(dfb_state *st, const float *h_audio, int64_t C, int64_t T, float *h_spec) {
+// pyDF DF.analysis(input, reset): reset != 0 starts every channel from zero memory (pyDF/src/lib.rs:56-58);
+// reset == 0 carries the STFT memory from the previous call into channel 0 and from channel c into c + 1
+// (one DFState is shared by all channels).  Either way the memory left behind is the last hop of the last channel.
+extern "C" int dfb_analysis_host_ex(dfb_state *st, const float *h_audio, int64_t C, int64_t T, int reset, float *h_spec) {
     if (!st || !h_audio || !h_spec) return fail(DFB_ERR_INVALID, "null argument");
     if (C <= 0 || T <= 0) return fail(DFB_ERR_INVALID, "[df] Input array empty or not contiguous.");
     DFB_CUDA(cudaSetDevice(st->device));
-    int64_t Tf = T / st->hop;
+    const int64_t Tf = T / st->hop, hop = st->hop;
     size_t nb_in = sizeof(float) * C * T, nb_out = sizeof(float) * 2 * C * Tf * st->tb.F;
-    int rc = st->arena.reserve(nb_in + nb_out + 1024);
+    int rc = st->arena.reserve(nb_in + nb_out + sizeof(float) * C * hop + 2048);
     if (rc) return rc;
     st->arena.reset();
     float *d_in = st->arena.take<float>(C * T), *d_out = st->arena.take<float>(2 * C * Tf * st->tb.F + 2);
+    float *d_mem = nullptr;
     DFB_CUDA(cudaMemcpyAsync(d_in, h_audio, nb_in, cudaMemcpyHostToDevice, st->stream));
-    rc = launch_analysis(st, d_in, C, T, d_out, nullptr, st->stream);
+    std::vector<float> mem;
+    if (!reset && Tf > 0) {
+        mem.resize((size_t)C * hop);
+        memcpy(mem.data(), st->analysis_mem.data(), sizeof(float) * hop);
+        for (int64_t c = 1; c < C; c++) memcpy(mem.data() + c * hop, h_audio + (c - 1) * T + (Tf - 1) * hop, sizeof(float) * hop);
+        d_mem = st->arena.take<float>(C * hop);
+        DFB_CUDA(cudaMemcpyAsync(d_mem, mem.data(), sizeof(float) * C * hop, cudaMemcpyHostToDevice, st->stream));
+    }
+    rc = launch_analysis(st, d_in, C, T, d_out, nullptr, st->stream, d_mem);
     if (rc) return rc;
     if (nb_out) DFB_CUDA(cudaMemcpyAsync(h_spec, d_out, nb_out, cudaMemcpyDeviceToHost, st->stream));
     DFB_CUDA(cudaStreamSynchronize(st->stream));
+    if (Tf > 0) memcpy(st->analysis_mem.data(), h_audio + (C - 1) * T + (Tf - 1) * hop, sizeof(float) * hop);
+    return DFB_OK;
+}
+extern "C" int dfb_analysis_host(dfb_state *st, const float *h_audio, int64_t C, int64_t T, float *h_spec) {
+    return dfb_analysis_host_ex(st, h_audio, C, T, 1, h_spec);
+}
+extern "C" int dfb_state_reset(dfb_state *st) {
+    if (!st) return fail(DFB_ERR_INVALID, "null state");
+    std::fill(st->analysis_mem.begin(), st->analysis_mem.end(), 0.f);
+    std::fill(st->synthesis_mem.begin(), st->synthesis_mem.end(), 0.f);
     return DFB_OK;
 }
 
@@ -824,21 +858,33 @@ extern "C" int dfb_synthesis(dfb_state *st, const float *d_spec, int64_t C, int6
     return launch_apply_synthesis(st, p, C, (cudaStream_t)stream);
 }
 
-extern "C" int dfb_synthesis_host(dfb_state *st, const float *h_spec, int64_t C, int64_t Tf, float *h_audio) {
+// pyDF DF.synthesis(input, reset): see dfb_analysis_host_ex for the reset semantics (pyDF/src/lib.rs:91-93).
+extern "C" int dfb_synthesis_host_ex(dfb_state *st, const float *h_spec, int64_t C, int64_t Tf, int reset, float *h_audio) {
     if (!st || !h_spec || !h_audio) return fail(DFB_ERR_INVALID, "null argument");
     if (C <= 0 || Tf <= 0) return fail(DFB_ERR_INVALID, "[df] Input array empty or not contiguous.");
     DFB_CUDA(cudaSetDevice(st->device));
-    size_t nb_in = sizeof(float) * 2 * C * Tf * st->tb.F, nb_out = sizeof(float) * C * Tf * st->hop;
-    int rc = st->arena.reserve(nb_in + nb_out + 1024);
+    const int64_t hop = st->hop;
+    size_t nb_in = sizeof(float) * 2 * C * Tf * st->tb.F, nb_out = sizeof(float) * C * Tf * hop;
+    int rc = st->arena.reserve(nb_in + nb_out + sizeof(float) * 2 * hop + 2048);
     if (rc) return rc;
     st->arena.reset();
-    float *d_in = st->arena.take<float>(2 * C * Tf * st->tb.F), *d_out = st->arena.take<float>(C * Tf * st->hop);
+    float *d_in = st->arena.take<float>(2 * C * Tf * st->tb.F), *d_out = st->arena.take<float>(C * Tf * hop);
+    float *d_init = st->arena.take<float>(hop), *d_final = st->arena.take<float>(hop);
     DFB_CUDA(cudaMemcpyAsync(d_in, h_spec, nb_in, cudaMemcpyHostToDevice, st->stream));
-    rc = dfb_synthesis(st, d_in, C, Tf, d_out, st->stream);
+    DFB_CUDA(cudaMemcpyAsync(d_init, st->synthesis_mem.data(), sizeof(float) * hop, cudaMemcpyHostToDevice, st->stream));
+    ApplyParams p{};
+    p.spec = (const float2 *)d_in; p.audio = d_out; p.out_stride = Tf * hop; p.out_offset = 0;
+    p.out_len = Tf * hop; p.Tf = (int)Tf; p.mode = 0;
+    p.carry = reset ? 0 : 1; p.init_tail = d_init; p.final_tail = d_final;
+    rc = launch_apply_synthesis(st, p, C, st->stream);
     if (rc) return rc;
     DFB_CUDA(cudaMemcpyAsync(h_audio, d_out, nb_out, cudaMemcpyDeviceToHost, st->stream));
+    DFB_CUDA(cudaMemcpyAsync(st->synthesis_mem.data(), d_final, sizeof(float) * hop, cudaMemcpyDeviceToHost, st->stream));
     DFB_CUDA(cudaStreamSynchronize(st->stream));
     return DFB_OK;
+}
+extern "C" int dfb_synthesis_host(dfb_state *st, const float *h_spec, int64_t C, int64_t Tf, float *h_audio) {
+    return dfb_synthesis_host_ex(st, h_spec, C, Tf, 1, h_audio);
 }
 
 namespace {

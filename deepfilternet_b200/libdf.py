@@ -6,8 +6,8 @@ kernels of libdfb200.so through its C ABI (host-pointer entry points).
 Differences kept on purpose (documented in INTEGRATION.md):
   * ``DF.synthesis`` / ``erb_norm`` do not clobber their inputs (the reference mutates them through
     ``unsafe as_array_mut``, pyDF/src/lib.rs:87,262);
-  * ``reset=False`` (carrying STFT memories across calls) is not provided: every call starts each
-    channel from the reset state, i.e. the reference's default ``reset=True``;
+  * ``reset=False`` carries the STFT / ISTFT memories across calls and channels exactly like the
+    reference's shared ``DFState`` (channel 0 continues the previous call, channel c continues c - 1);
   * only fft_size=960 / hop_size=480 kernels are built (all shipped models).
 """
 from __future__ import annotations
@@ -88,13 +88,11 @@ class DF:
         x = np.asarray(input)
         if x.dtype != np.float32 or x.ndim != 2:
             raise TypeError("argument 'input': expected a 2-D float32 numpy array")
-        if reset is not None and not reset:
-            raise NotImplementedError("DF.analysis(reset=False) is not provided by the B200 drop-in")
         _require(x)
         c, t = x.shape
         out = np.empty((c, t // self._hop, self._fft // 2 + 1), dtype=np.complex64)
         if out.size:
-            check(_lib.lib().dfb_analysis_host(self._h, _ptr(x), c, t, _ptr(out)))
+            check(_lib.lib().dfb_analysis_host_ex(self._h, _ptr(x), c, t, 1 if (reset is None or reset) else 0, _ptr(out)))
         return out
 
     def synthesis(self, input: np.ndarray, reset: Optional[bool] = True) -> np.ndarray:
@@ -102,14 +100,12 @@ class DF:
         x = np.asarray(input)
         if x.dtype != np.complex64 or x.ndim != 3:
             raise TypeError("argument 'input': expected a 3-D complex64 numpy array")
-        if reset is not None and not reset:
-            raise NotImplementedError("DF.synthesis(reset=False) is not provided by the B200 drop-in")
         _require(x)
         c, tf, f = x.shape
         if f != self._fft // 2 + 1:
             raise RuntimeError(f"DF shape error: expected {self._fft // 2 + 1} frequency bins, got {f}")
         out = np.empty((c, tf * self._hop), dtype=np.float32)
-        check(_lib.lib().dfb_synthesis_host(self._h, _ptr(x), c, tf, _ptr(out)))
+        check(_lib.lib().dfb_synthesis_host_ex(self._h, _ptr(x), c, tf, 1 if (reset is None or reset) else 0, _ptr(out)))
         return out
 
     def erb_widths(self) -> np.ndarray:
@@ -135,7 +131,7 @@ class DF:
         return self._nb
 
     def reset(self) -> None:
-        return None  # no carried state: every call starts from the reset state
+        check(_lib.lib().dfb_state_reset(self._h))
 
 
 def _widths(erb_fb) -> np.ndarray:

@@ -52,9 +52,9 @@ int64_t dfb_profile_report(char *buf, int64_t buflen);
 /* ------------------------------------------------------------------ DSP state ------------
  * Replaces libDF `DFState` as exposed by pyDF `DF` (pyDF/src/lib.rs:14-136,
  * libDF/src/lib.rs:104-154).  Holds the vorbis window, FFT twiddles and ERB tables on the device.
- * Unlike the reference there are no per-object analysis / synthesis memories: every call below
- * starts each channel from the reset state, which is what pyDF does with its default
- * `reset=True` (pyDF/src/lib.rs:56-58, 91-93). */
+ * The analysis / synthesis memories (lib.rs:60-62) are carried by the *_host_ex entry points exactly as
+ * pyDF does with `reset=False`; the device-pointer entry points and the fused enhance path always start
+ * each channel from the reset state (pyDF's default `reset=True`, pyDF/src/lib.rs:56-58, 91-93). */
 typedef struct dfb_state dfb_state;
 
 /* pyDF DF.__new__ (pyDF/src/lib.rs:22-39) -> DFState::new (libDF/src/lib.rs:104-154).
@@ -73,11 +73,17 @@ int dfb_erb_widths(int sr, int fft_size, int nb_erb, int min_nb_freqs, int64_t *
  * audio f32[C, T] (row stride T) -> spec c64[C, T / hop, F].  Trailing partial frame dropped. */
 int dfb_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, void *stream);
 int dfb_analysis_host(dfb_state *st, const float *h_audio, int64_t C, int64_t T, float *h_spec);
+/* same with pyDF's `reset` argument: reset == 0 carries the STFT memory across calls and channels exactly like
+ * the shared DFState of the reference (channel 0 continues the previous call, channel c continues c - 1) */
+int dfb_analysis_host_ex(dfb_state *st, const float *h_audio, int64_t C, int64_t T, int reset, float *h_spec);
+/* pyDF DF.reset (pyDF/src/lib.rs:133-135): zero the carried analysis / synthesis memories */
+int dfb_state_reset(dfb_state *st);
 
 /* pyDF DF.synthesis (pyDF/src/lib.rs:74-107) -> frame_synthesis (libDF/src/lib.rs:396-427).
  * spec c64[C, Tf, F] -> audio f32[C, Tf * hop].  Does NOT clobber its input (the reference does). */
 int dfb_synthesis(dfb_state *st, const float *d_spec, int64_t C, int64_t Tf, float *d_audio, void *stream);
 int dfb_synthesis_host(dfb_state *st, const float *h_spec, int64_t C, int64_t Tf, float *h_audio);
+int dfb_synthesis_host_ex(dfb_state *st, const float *h_spec, int64_t C, int64_t Tf, int reset, float *h_audio);
 
 /* libdf.erb (pyDF/src/lib.rs:142-192) -> compute_band_corr (+dB) (libDF/src/lib.rs:280-295,
  * transforms.rs:236-253).  spec c64[n_frames, F] -> f32[n_frames, E]; widths host int64[E]. */

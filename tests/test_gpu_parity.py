@@ -71,6 +71,37 @@ def test_analysis_synthesis(states, C, T):
     assert np.abs(y - z).max() < 2e-6
 
 
+def test_analysis_synthesis_carried_state(states):
+    """pyDF `reset=False` (pyDF/src/lib.rs:56-58, 91-93): the shared DFState carries the STFT / ISTFT memories
+    from call to call and from channel c to channel c + 1; `DF.reset()` clears them."""
+    st, ost = states
+    st.reset(), ost.reset()
+    x = synth_audio(3, 9600 + 123, seed=5).numpy()
+    for i, (lo, hi) in enumerate([(0, 2400), (2400, 2880), (2880, 9723)]):   # chunked streaming incl. a 1-frame call
+        xa = np.ascontiguousarray(x[:, lo:hi])
+        a, b = st.analysis(xa, reset=False), ost.analysis(xa, reset=False)
+        assert np.abs(a - b).max() < 1e-6, i
+        y, z = st.synthesis(b.copy(), reset=False), ost.synthesis(b.copy(), reset=False)
+        assert np.abs(y - z).max() < 2e-6, i
+    # a reset=True call still leaves the last channel's memory behind for a following reset=False call
+    a, b = st.analysis(x, reset=True), ost.analysis(x, reset=True)
+    y, z = st.synthesis(b.copy(), reset=True), ost.synthesis(b.copy(), reset=True)
+    x2 = synth_audio(1, 4800, seed=6).numpy()
+    a, b = st.analysis(x2, reset=False), ost.analysis(x2, reset=False)
+    assert np.abs(a - b).max() < 1e-6
+    y, z = st.synthesis(b.copy(), reset=False), ost.synthesis(b.copy(), reset=False)
+    assert np.abs(y - z).max() < 2e-6
+    # single-channel streaming in chunks == one reset call over the whole signal
+    st.reset()
+    whole = st.analysis(x[:1, :9600], reset=True)
+    st.reset()
+    parts = np.concatenate([st.analysis(np.ascontiguousarray(x[:1, o:o + 1920]), reset=False) for o in range(0, 9600, 1920)], 1)
+    assert np.array_equal(whole, parts)
+    st.reset(), ost.reset()
+    assert np.abs(st.analysis(x2, reset=False) - ost.analysis(x2, reset=False)).max() < 1e-6
+    st.reset(), ost.reset()
+
+
 def test_analysis_errors(states):
     st, _ = states
     with pytest.raises(RuntimeError, match="empty or not contiguous"):
