@@ -809,6 +809,8 @@ extern "C" int dfb_analysis(dfb_state *st, const float *d_audio, int64_t C, int6
     return launch_analysis(st, d_audio, C, T, d_spec, nullptr, (cudaStream_t)stream);
 }
 
+extern "C" int dfb_state_reset(dfb_state *st);
+
 // pyDF DF.analysis(input, reset): reset != 0 starts every channel from zero memory (pyDF/src/lib.rs:56-58);
 // reset == 0 carries the STFT memory from the previous call into channel 0 and from channel c into c + 1
 // (one DFState is shared by all channels).  Either way the memory left behind is the last hop of the last channel.
@@ -817,6 +819,7 @@ extern "C" int dfb_analysis_host_ex(dfb_state *st, const float *h_audio, int64_t
     if (C <= 0 || T <= 0) return fail(DFB_ERR_INVALID, "[df] Input array empty or not contiguous.");
     DFB_CUDA(cudaSetDevice(st->device));
     const int64_t Tf = T / st->hop, hop = st->hop;
+    if (reset) dfb_state_reset(st);  // DFState::reset clears BOTH memories (libDF/src/lib.rs:156-159)
     size_t nb_in = sizeof(float) * C * T, nb_out = sizeof(float) * 2 * C * Tf * st->tb.F;
     int rc = st->arena.reserve(nb_in + nb_out + sizeof(float) * C * hop + 2048);
     if (rc) return rc;
@@ -864,6 +867,7 @@ extern "C" int dfb_synthesis_host_ex(dfb_state *st, const float *h_spec, int64_t
     if (C <= 0 || Tf <= 0) return fail(DFB_ERR_INVALID, "[df] Input array empty or not contiguous.");
     DFB_CUDA(cudaSetDevice(st->device));
     const int64_t hop = st->hop;
+    if (reset) dfb_state_reset(st);  // clears the analysis memory as well (libDF/src/lib.rs:156-159)
     size_t nb_in = sizeof(float) * 2 * C * Tf * st->tb.F, nb_out = sizeof(float) * C * Tf * hop;
     int rc = st->arena.reserve(nb_in + nb_out + sizeof(float) * 2 * hop + 2048);
     if (rc) return rc;

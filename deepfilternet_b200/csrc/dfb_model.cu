@@ -592,74 +592,92 @@ k_mask_out(const float *__restrict__ e0, const float *__restrict__ d1, const flo
     }
 }
 
-// ------------------------------------------------- DF pathway conv + coefficient sum ----
-// coefs[b,t,f,:] (already holding tanh(df_out(c))) += relu( pw( conv_t(c0) ) + b ):
-// df_convp = grouped (2) temporal conv C -> 2*O with kernel (ktp,1), 1x1 conv, BN, ReLU
-// (deepfilternet3.py:293-295, 328-330).  One thread owns bin f and a run of kCpR consecutive
-// frames: every c0 row it loads feeds up to ktp output frames, so c0 is read (kCpR+ktp-1)/kCpR
-// times instead of ktp times; the taps of the current channel quad are register resident.
-constexpr int kMaxO2 = 16, kCpR = 4, kCpRuns = 2;
-template <int ORDER, int KTP>
-__global__ void __launch_bounds__(192, 2)
+// ------------------------------------------------- DF pathway conv ----
+// coefs[b,t,f,:] = relu( pw( conv_t(c0) ) + b ); the df_out projection later adds tanh(df_out(c)) on top
+// (deepfilternet3.py:293-295, 328-330).  df_convp = grouped (2) temporal conv C -> 2*O with kernel (ktp,1),
+// 1x1 conv, BN, ReLU.
+// Half a warp owns one frequency bin f and marches along t: lane q holds channel quad q of the 256-byte c0 row
+// (so a warp load is 512 contiguous bytes and every c0 element is read once per chunk), keeps its 4 channels'
+// taps for all (dt, o) in registers for the whole kernel, and accumulates the ktp in-flight output frames in
+// rotating registers.  A finished frame is reduced over the 8 lanes of its channel group with shuffles, the two
+// groups are exchanged, and lanes 0..2*O-1 apply the 1x1 conv + bias + ReLU and store 40 contiguous bytes.
+constexpr int kMaxO2 = 16, kCpWarps = 4, kCpChunk = 128;
+template <int ORDER, int KTP, int MINB>
+__global__ void __launch_bounds__(32 * kCpWarps, MINB)
 k_df_convp(const float *__restrict__ c0 /*[B,T,Fd,64]*/, const float *__restrict__ w1 /*[ktp][O2][32]*/,
            const float *__restrict__ w2 /*[O2][O2]*/, const float *__restrict__ bias, float *__restrict__ coefs,
            int T, int Fd) {
     constexpr int O2 = 2 * ORDER, CG = kCh / 2;
-    extern __shared__ __align__(16) float sw[];  // w1 | w2 | bias
-    constexpr int n1 = KTP * O2 * CG;
-    for (int i = threadIdx.x; i < n1; i += blockDim.x) sw[i] = w1[i];
-    for (int i = threadIdx.x; i < O2 * O2; i += blockDim.x) sw[n1 + i] = w2[i];
-    for (int i = threadIdx.x; i < O2; i += blockDim.x) sw[n1 + O2 * O2 + i] = bias[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane & 15, g = q >> 3, cq = q & 7;
+    const int f_raw = (blockIdx.x * kCpWarps + warp) * 2 + (lane >> 4);
+    const bool f_ok = f_raw < Fd;
+    const int f = f_ok ? f_raw : Fd - 1;
+    const int b = blockIdx.z;
+    const int t_begin = blockIdx.y * kCpChunk, t_end = min(T, t_begin + kCpChunk);
+    float4 wv[KTP][ORDER];
+#pragma unroll
+    for (int dt = 0; dt < KTP; dt++)
+#pragma unroll
+        for (int o = 0; o < ORDER; o++)
+            wv[dt][o] = __ldg(reinterpret_cast<const float4 *>(w1 + (dt * O2 + g * ORDER + o) * CG + 4 * cq));
+    __shared__ float s_w2[O2 * O2 + O2];  // 1x1 conv | bias; lane q < O2 applies column q
+    for (int i = threadIdx.x; i < O2 * O2; i += blockDim.x) s_w2[i] = w2[i];
+    if (threadIdx.x < O2) s_w2[O2 * O2 + threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
-    const int f = threadIdx.x % Fd, run = threadIdx.x / Fd;
-    const int b = blockIdx.y;
-    const int t0 = (blockIdx.x * kCpRuns + run) * kCpR;
-    if (t0 >= T) return;
-    float acc[kCpR][O2];
+    const float *s2c = s_w2 + (q < O2 ? q : 0);
+    float acc[KTP][ORDER];
 #pragma unroll
-    for (int r = 0; r < kCpR; r++)
+    for (int u = 0; u < KTP; u++)
 #pragma unroll
-        for (int o = 0; o < O2; o++) acc[r][o] = 0.f;
-    const float *base = c0 + ((int64_t)b * T * Fd + f) * kCh;
+        for (int o = 0; o < ORDER; o++) acc[u][o] = 0.f;
+    const float *base = c0 + ((int64_t)b * T * Fd + f) * kCh + 4 * q;
+    const int64_t fs = (int64_t)Fd * kCh;
+    const int tstart = t_begin - (KTP - 1);
+    auto load = [&](int tp) -> float4 {
+        return (tp >= 0 && tp < t_end) ? __ldg(reinterpret_cast<const float4 *>(base + (int64_t)tp * fs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 xn[KTP];
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
-        for (int c4 = 0; c4 < CG; c4 += 4) {
-            float4 wv[KTP][ORDER];
+    for (int u = 0; u < KTP; u++) xn[u] = load(tstart + u);
+    for (int tb = tstart; tb < t_end; tb += KTP) {
+        float4 x[KTP];
 #pragma unroll
-            for (int dt = 0; dt < KTP; dt++)
+        for (int u = 0; u < KTP; u++) { x[u] = xn[u]; xn[u] = load(tb + KTP + u); }  // prefetch the next group
 #pragma unroll
-                for (int o = 0; o < ORDER; o++)
-                    wv[dt][o] = *reinterpret_cast<const float4 *>(sw + (dt * O2 + g * ORDER + o) * CG + c4);
+        for (int u = 0; u < KTP; u++) {
+            const int tp = tb + u;
+            // input frame tp feeds output frame tp + (KTP-1) - dt through tap dt; slot = output frame mod KTP
 #pragma unroll
-            for (int j = 0; j < kCpR + KTP - 1; j++) {
-                const int tp = t0 - (KTP - 1) + j;
-                if (tp < 0 || tp >= T) continue;
-                const float4 x = *reinterpret_cast<const float4 *>(base + (int64_t)tp * Fd * kCh + g * CG + c4);
+            for (int dt = 0; dt < KTP; dt++) {
+                const int slot = (u + KTP - 1 - dt) % KTP;
 #pragma unroll
-                for (int dt = 0; dt < KTP; dt++) {
-                    const int r = j - dt;  // output frame t0 + r uses tap dt of input frame t0 + r - (KTP-1) + dt
-                    if (r < 0 || r >= kCpR) continue;
-#pragma unroll
-                    for (int o = 0; o < ORDER; o++) {
-                        const float4 ww = wv[dt][o];
-                        acc[r][g * ORDER + o] += x.x * ww.x + x.y * ww.y + x.z * ww.z + x.w * ww.w;
-                    }
+                for (int o = 0; o < ORDER; o++) {
+                    const float4 ww = wv[dt][o];
+                    float a = dt == 0 ? 0.f : acc[slot][o];
+                    a = fmaf(x[u].x, ww.x, a); a = fmaf(x[u].y, ww.y, a);
+                    a = fmaf(x[u].z, ww.z, a); a = fmaf(x[u].w, ww.w, a);
+                    acc[slot][o] = a;
                 }
             }
-        }
-    }
-    const float *s2 = sw + n1, *sb = sw + n1 + O2 * O2;
+            if (tp >= t_begin && tp < t_end) {  // output frame tp (slot u) is complete; warp-uniform condition
+                float v[ORDER], w[ORDER];
 #pragma unroll
-    for (int r = 0; r < kCpR; r++) {
-        const int t = t0 + r;
-        if (t >= T) break;
-        float *dst = coefs + (((int64_t)b * T + t) * Fd + f) * O2;
+                for (int o = 0; o < ORDER; o++) {
+                    float r = acc[u][o];
+                    r += __shfl_xor_sync(0xffffffffu, r, 1);
+                    r += __shfl_xor_sync(0xffffffffu, r, 2);
+                    r += __shfl_xor_sync(0xffffffffu, r, 4);
+                    v[o] = r;
+                    w[o] = __shfl_xor_sync(0xffffffffu, r, 8);  // the other channel group's sums
+                }
+                float out = s2c[O2 * O2];
 #pragma unroll
-        for (int n = 0; n < O2; n++) {
-            float v = sb[n];
+                for (int k = 0; k < ORDER; k++) out = fmaf(g ? w[k] : v[k], s2c[k * O2], out);
 #pragma unroll
-            for (int k = 0; k < O2; k++) v += acc[r][k] * s2[k * O2 + n];
-            dst[n] += fmaxf(v, 0.f);
+                for (int k = 0; k < ORDER; k++) out = fmaf(g ? v[k] : w[k], s2c[(ORDER + k) * O2], out);
+                if (q < O2 && f_ok) coefs[(((int64_t)b * T + tp) * Fd + f) * O2 + q] = fmaxf(out, 0.f);
+            }
         }
     }
 }
@@ -1045,7 +1063,9 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if (m->precision == 1 && (r = need(m, (n + ".pw_nk").c_str(), kCh * kCh, &pw_nk))) return r;
         return DFB_OK;
     };
-    cudaStream_t sa = m->aux;  // the DF-branch input convs run concurrently with the ERB-branch convs
+    // the DF-branch input convs run concurrently with the ERB-branch convs (DFB_SERIAL=1: one stream, for profiling)
+    static const bool serial = getenv("DFB_SERIAL") && atoi(getenv("DFB_SERIAL"));
+    cudaStream_t sa = serial ? s : m->aux;
     DFB_CUDA(cudaEventRecord(m->ev_fork_enc, s));
     DFB_CUDA(cudaStreamWaitEvent(sa, m->ev_fork_enc, 0));
     auto mk = [&](const float *in, int Fin, int64_t in_fs, float *out, int Fout, int64_t out_fs, int kt) {
@@ -1068,6 +1088,22 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
         if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(sa, p, B, pw_nk))) return rc;
         DFB_CUDA(cudaEventRecord(m->ev_join_enc, sa));
+        // DF pathway conv (needs c0 only): queued behind df_conv1 on the auxiliary stream so that it fills the SMs
+        // the encoder GRU clusters leave idle instead of lengthening the decoder tail
+        const int O2 = 2 * c.df_order;
+        const float *w1, *w2, *bb;
+        if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
+            (rc = need(m, "df_dec.df_convp.w2", O2 * O2, &w2)) || (rc = need(m, "df_dec.df_convp.b", O2, &bb)))
+            return rc;
+        if (c.df_order != 5 || c.df_pathway_kt != 5)
+            return fail(DFB_ERR_UNSUPPORTED, "df_order %d / df_pathway_kernel_size_t %d (built kernels: 5, 5)", c.df_order,
+                        c.df_pathway_kt);
+        dim3 grid((unsigned)((Fd + 2 * kCpWarps - 1) / (2 * kCpWarps)), (unsigned)((T + kCpChunk - 1) / kCpChunk), (unsigned)B);
+        DFB_PROF("k_df_convp", sa);
+        static const int minb = getenv("DFB_CONVP_MINB") ? atoi(getenv("DFB_CONVP_MINB")) : 2;
+        if (minb == 2) k_df_convp<5, 5, 2><<<grid, 32 * kCpWarps, 0, sa>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
+        else k_df_convp<5, 5, 3><<<grid, 32 * kCpWarps, 0, sa>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
+        DFB_LAUNCH_CHECK();
     }
     {
         DwPwParams p = mk(f.e0, E, (int64_t)E * kCh, f.e1, E / 2, (int64_t)E / 2 * kCh, c.conv_kt);
@@ -1111,10 +1147,10 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     }
     // fork: the two decoders only share read-only encoder outputs
     DFB_CUDA(cudaEventRecord(m->ev_fork, s));
-    DFB_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+    DFB_CUDA(cudaStreamWaitEvent(sa, m->ev_fork, 0));
     // ---- DF decoder (deepfilternet3.py:323-331), on the auxiliary stream (forked after the encoder)
     {
-        cudaStream_t s = m->aux;  // shadows the caller stream inside this block
+        cudaStream_t s = sa;  // shadows the caller stream inside this block
         const float *w_in, *w_out;
         if ((rc = need(m, "df_dec.df_gru.in.gl", (int64_t)emb_dim * Hd / c.g_df_in, &w_in))) return rc;
         if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a2, Hd, M, c.g_df_in, emb_dim, Hd, ACT_RELU, 1.f, 0.f,
@@ -1134,21 +1170,10 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         }
         const int O2 = 2 * c.df_order;
         if ((rc = need(m, "df_dec.df_out.gl", (int64_t)Hd * Fd * O2 / c.g_df_out, &w_out))) return rc;
-        if ((rc = run_gl(s, f.dfc, Hd, w_out, nullptr, nullptr, 0, d_coefs, (int64_t)Fd * O2, M, c.g_df_out, Hd, Fd * O2, ACT_TANH))) return rc;
-        const float *w1, *w2, *bb;
-        if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
-            (rc = need(m, "df_dec.df_convp.w2", O2 * O2, &w2)) || (rc = need(m, "df_dec.df_convp.b", O2, &bb)))
-            return rc;
-        int smem = (c.df_pathway_kt * O2 * (kCh / 2) + O2 * O2 + O2) * 4;
-        if (c.df_order != 5 || c.df_pathway_kt != 5 || Fd * kCpRuns > 192)
-            return fail(DFB_ERR_UNSUPPORTED, "df_order %d / df_pathway_kernel_size_t %d (built kernels: 5, 5)", c.df_order,
-                        c.df_pathway_kt);
-        dim3 grid((unsigned)((T + kCpR * kCpRuns - 1) / (kCpR * kCpRuns)), (unsigned)B);
-        DFB_PROF("k_df_convp", s);
-        k_df_convp<5, 5><<<grid, Fd * kCpRuns, smem, s>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
-        DFB_LAUNCH_CHECK();
+        // coefs = tanh(df_out(c)) + df_convp(c0); the pathway term was written by k_df_convp on this stream earlier
+        if ((rc = run_gl(s, f.dfc, Hd, w_out, nullptr, d_coefs, (int64_t)Fd * O2, d_coefs, (int64_t)Fd * O2, M, c.g_df_out, Hd, Fd * O2, ACT_TANH))) return rc;
     }
-    DFB_CUDA(cudaEventRecord(m->ev_join, m->aux));
+    DFB_CUDA(cudaEventRecord(m->ev_join, sa));
     // ---- ERB decoder (deepfilternet3.py:245-254)
     {
         const float *w_in, *w_out;
