@@ -697,6 +697,7 @@ struct dfb_model {
     std::map<std::string, std::pair<const float *, int64_t>> dbg;  // activations of the last forward
     std::vector<GruLayerW> enc_gru, erb_gru, df_gru;
     float *slab = nullptr;
+    int conv_tc = 0; // 1: 1x1 convs of the separable blocks on the BF16x3 tcgen05 path
     int proj_tc = 0; // 1: GRU input projections on the BF16x3 tcgen05 GEMM (needs gru_tc)
     int gru_tc = 0;  // 1: tensor-core recurrence (BF16 hi/lo split operands) for H = 256
     long long *gru_dbg = nullptr;  // device buffer for dfb_debug_gru_timing
@@ -806,10 +807,11 @@ extern "C" int dfb_debug_gru_timing(dfb_model *m, int steps, long long *h_out) {
 }
 
 extern "C" int dfb_model_set_precision(dfb_model *m, int mode) {
-    if (!m || mode < 0 || mode > 7) return fail(DFB_ERR_INVALID, "precision mode out of range");
+    if (!m || mode < 0 || mode > 15) return fail(DFB_ERR_INVALID, "precision mode out of range");
     m->precision = mode & 1;   // bit 0: TF32 tcgen05 for the dense feed-forward contractions
     m->gru_tc = (mode >> 1) & 1;  // bit 1: tensor-core GRU recurrence (BF16x3 split, ~fp32 accurate)
     m->proj_tc = (mode >> 2) & 1; // bit 2: GRU input projections on the BF16x3 tcgen05 GEMM
+    m->conv_tc = (mode >> 3) & 1; // bit 3: 1x1 convs of the separable blocks on the BF16x3 tcgen05 path
     return DFB_OK;
 }
 
@@ -936,13 +938,13 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
 }  // namespace
 namespace dfb {
 template <int MODE>
-int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *pw_nk, int B);
+int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *w_sw, int B);
 }
 namespace {
 
 template <int MODE>
-int run_dwpw(cudaStream_t s, DwPwParams p, int B, const float *pw_nk = nullptr) {
-    if (pw_nk) return launch_dwpw_tc<MODE>(s, p, pw_nk, B);
+int run_dwpw(cudaStream_t s, DwPwParams p, int B, const float *w_sw = nullptr) {
+    if (w_sw) return launch_dwpw_tc<MODE>(s, p, w_sw, B);
     static bool attr_done = false;
     const int smem = (kCh * kCh + 128 * kLdA) * 4;
     if (!attr_done) {
@@ -1052,15 +1054,15 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         k_conv_in<1><<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead);
         DFB_LAUNCH_CHECK();
     }
-    const float *pw_nk = nullptr;  // set by blk(): [C_out][C_in] 1x1 weights for the tensor-core path
+    const float *pw_sw = nullptr;  // set by blk(): swizzled BF16 hi | lo image of the [C_out][C_in] 1x1 weights (tensor-core path)
     auto blk = [&](const char *name, DwPwParams &p) -> int {
         std::string n(name);
         int r;
         if ((r = need(m, (n + ".dw").c_str(), -1, &p.dw)) || (r = need(m, (n + ".pw").c_str(), kCh * kCh, &p.pw)) ||
             (r = need(m, (n + ".b").c_str(), kCh, &p.bias)))
             return r;
-        pw_nk = nullptr;
-        if (m->precision == 1 && (r = need(m, (n + ".pw_nk").c_str(), kCh * kCh, &pw_nk))) return r;
+        pw_sw = nullptr;
+        if (m->conv_tc && (r = need(m, (n + ".pw_sw").c_str(), kCh * kCh, &pw_sw))) return r;
         return DFB_OK;
     };
     // the DF-branch input convs run concurrently with the ERB-branch convs (DFB_SERIAL=1: one stream, for profiling)
@@ -1086,7 +1088,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             DFB_LAUNCH_CHECK();
         }
         p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
-        if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(sa, p, B, pw_nk))) return rc;
+        if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(sa, p, B, pw_sw))) return rc;
         DFB_CUDA(cudaEventRecord(m->ev_join_enc, sa));
         // DF pathway conv (needs c0 only): queued behind df_conv1 on the auxiliary stream so that it fills the SMs
         // the encoder GRU clusters leave idle instead of lengthening the decoder tail
@@ -1107,11 +1109,11 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     }
     {
         DwPwParams p = mk(f.e0, E, (int64_t)E * kCh, f.e1, E / 2, (int64_t)E / 2 * kCh, c.conv_kt);
-        if ((rc = blk("enc.erb_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
+        if ((rc = blk("enc.erb_conv1", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_sw))) return rc;
         p = mk(f.e1, E / 2, (int64_t)E / 2 * kCh, f.e2, E / 4, (int64_t)E / 4 * kCh, c.conv_kt);
-        if ((rc = blk("enc.erb_conv2", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_nk))) return rc;
+        if ((rc = blk("enc.erb_conv2", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_sw))) return rc;
         p = mk(f.e2, E / 4, (int64_t)E / 4 * kCh, f.e3, E / 4, e3_fs, c.conv_kt);
-        if ((rc = blk("enc.erb_conv3", p)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_nk))) return rc;
+        if ((rc = blk("enc.erb_conv3", p)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_sw))) return rc;
 
     }
     DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join_enc, 0));  // c0 / c1 ready
@@ -1194,11 +1196,11 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             return DFB_OK;
         };
         DwPwParams p = mk(f.dec_emb, E / 4, ED, f.d3, E / 4, ED, c.conv_kt);
-        if ((rc = blk("erb_dec.convt3", p)) || (rc = path(p, "erb_dec.conv3p", f.e3, e3_fs)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_nk))) return rc;
+        if ((rc = blk("erb_dec.convt3", p)) || (rc = path(p, "erb_dec.conv3p", f.e3, e3_fs)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_sw))) return rc;
         p = mk(f.d3, E / 4, ED, f.d2, E / 2, (int64_t)E / 2 * kCh, 1);
-        if ((rc = blk("erb_dec.convt2", p)) || (rc = path(p, "erb_dec.conv2p", f.e2, (int64_t)E / 4 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B, pw_nk))) return rc;
+        if ((rc = blk("erb_dec.convt2", p)) || (rc = path(p, "erb_dec.conv2p", f.e2, (int64_t)E / 4 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B, pw_sw))) return rc;
         p = mk(f.d2, E / 2, (int64_t)E / 2 * kCh, f.d1, E, (int64_t)E * kCh, 1);
-        if ((rc = blk("erb_dec.convt1", p)) || (rc = path(p, "erb_dec.conv1p", f.e1, (int64_t)E / 2 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B, pw_nk))) return rc;
+        if ((rc = blk("erb_dec.convt1", p)) || (rc = path(p, "erb_dec.conv1p", f.e1, (int64_t)E / 2 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B, pw_sw))) return rc;
         const float *ps, *pb, *w, *bb;
         if ((rc = need(m, "erb_dec.conv0p.s", kCh, &ps)) || (rc = need(m, "erb_dec.conv0p.b", kCh, &pb)) ||
             (rc = need(m, "erb_dec.conv0_out.w", c.conv_kt * 3 * kCh, &w)) || (rc = need(m, "erb_dec.conv0_out.b", 1, &bb)))

@@ -333,20 +333,22 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 }
 
 // ------------------------------------------- fused depthwise -> 1x1 (tcgen05) -> ReLU ----
-// Tensor-core version of k_dwpw (dfb_model.cu), persistent over 128-row tiles and warp specialised:
-//   warps 0-3 : producers -- depthwise (+pathway) prologue, tf32-rounded (RN), written straight into
-//               shared memory in the UMMA K-major 128B-swizzle layout (two [128 x 32] sub-tiles)
-//   warp  8   : one lane issues 8 tcgen05.mma (M128 N64 K8, kind::tf32) per tile against the 1x1
-//               weight tile; tcgen05.commit frees the A buffer and publishes the accumulator
-//   warps 4-7 : epilogue -- tcgen05.ld of the fp32 accumulator (TMEM lane = tile row), bias + ReLU,
-//               256-byte row stores
-// A tile and accumulator are double buffered so the three stages of consecutive tiles overlap.
-struct DwTcSmem {
-    alignas(1024) float a[2][2][128 * 32];   // [buffer][k chunk c: channels [32 c, 32 c + 32)]
-    alignas(1024) float w[2][kCh * 32];      // B sub-tiles: W[n][k] = pw_nk[n][32 c + k]
+// Tensor-core version of k_dwpw (dfb_model.cu) at fp32-level accuracy (BF16x3): one CTA per 128-row tile.
+//   1. all 256 threads run the depthwise (+pathway) prologue (shared with the FFMA kernel), split the result
+//      x = hi + lo into BF16 planes and write them straight into shared memory in the UMMA K-major 128B-swizzle
+//      layout (a row of 64 channels is exactly one 128-byte swizzle row);
+//   2. warp 0 issues 12 tcgen05.mma (M128 N64 K16; hi*hi + lo*hi + hi*lo) against the pre-split 1x1 weights,
+//      fp32 accumulator in 64 TMEM columns;
+//   3. all 8 warps read their TMEM lane quarter / column half (tcgen05.ld), add bias, ReLU and stage the fp32
+//      tile in the (now free) operand buffers with an XOR chunk swizzle -- conflict free for row-per-lane writes;
+//   4. the CTA streams the staged tile out with fully coalesced 512-byte warp stores.
+// 3 CTAs per SM overlap each other's load / MMA / store phases.
+struct DxSmem {
+    alignas(1024) unsigned char a[2][128 * 128];  // A hi | lo planes; afterwards the fp32 [128][64] output staging tile
+    alignas(1024) unsigned char w[2][kCh * 128];  // W hi | lo planes: [n][k] BF16
     alignas(16) float bias[kCh];
-    alignas(8) uint64_t a_full[2];
-    uint64_t a_empty[2], t_full[2], t_empty[2];
+    alignas(8) uint64_t mma_done;
+    uint64_t raw_full;
     uint32_t tmem_base;
 };
 
@@ -362,157 +364,193 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// (x.x, x.y) -> packed bf16x2 hi plane and lo plane (x = hi + lo, both round to nearest even)
+__device__ __forceinline__ void bf16x2_split(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float2 hf = __bfloat1622float2(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    lo = *reinterpret_cast<uint32_t *>(&l);
+}
 
-constexpr int kDwTcThreads = 288;
+constexpr int kDxThreads = 256;
 
+// 1-D bulk copy global -> own shared memory, completing on an mbarrier (TMA engine, no registers involved)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// dw_prologue (dfb_dwpw.cuh) reading the raw input / pathway frames of this tile from shared memory:
+// raw row (frame tq, bin fi) at ((tq - tq0) * Fin + fi) * 256 bytes.
 template <int MODE>
-__global__ void __launch_bounds__(kDwTcThreads, 2) k_dwpw_tc(DwPwParams p, const float *__restrict__ pw_nk, int B, int tiles_per_stream) {
-    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    DwTcSmem &sm = *reinterpret_cast<DwTcSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // ---- one-time setup: weights (B operand), bias, barriers, TMEM
-    for (int i = tid; i < kCh * 16; i += kDwTcThreads) {  // (n, 16-byte chunk j over k)
-        const int n = i >> 4, jj = i & 15, c = jj >> 3, j = jj & 7;
-        float4 v = *reinterpret_cast<const float4 *>(pw_nk + n * kCh + c * 32 + j * 4);
-        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sm.w[c]) + sw128_off(n, j)) = v;
-    }
-    if (tid < kCh) sm.bias[tid] = p.bias[tid];
-    if (tid == 0) {
-        for (int i = 0; i < 2; i++) {
-            mbar_init(&sm.a_full[i], 4);    // one arrive per producer warp
-            mbar_init(&sm.a_empty[i], 1);   // tcgen05.commit
-            mbar_init(&sm.t_full[i], 1);    // tcgen05.commit
-            mbar_init(&sm.t_empty[i], 4);   // one arrive per epilogue warp
+__device__ __forceinline__ float4 dw_prologue_smem(const DwPwParams &p, const DwTaps &tp, const float *raw_in, const float *raw_path,
+                                                   int tq0, int t, int fo, int cq) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dt = 0; dt < 3; dt++) {
+        if (dt < 3 - p.kt) continue;
+        const int tq = t - (2 - dt);  // causal: taps at t-(kt-1) .. t
+        if (tq < 0) continue;
+#pragma unroll
+        for (int df = 0; df < 3; df++) {
+            int fi;
+            float4 wv;
+            if (MODE == DW_S1) { fi = fo + df - 1; wv = tp.wd[dt * 3 + df]; }
+            else if (MODE == DW_S2) { fi = 2 * fo + df - 1; wv = tp.wd[dt * 3 + df]; }
+            else {  // DW_T2: df enumerates the (at most two) contributing taps
+                if (df == 2) continue;
+                if ((fo & 1) == 0) { if (df == 1) continue; fi = fo >> 1; wv = tp.wd[dt * 3 + 1]; }
+                else if (df == 0) { fi = fo >> 1; wv = tp.wd[dt * 3 + 2]; }
+                else { fi = (fo >> 1) + 1; wv = tp.wd[dt * 3 + 0]; }
+            }
+            if (fi < 0 || fi >= p.Fin) continue;
+            const int o = ((tq - tq0) * p.Fin + fi) * kCh + cq * 4;
+            float4 x = *reinterpret_cast<const float4 *>(raw_in + o);
+            if (raw_path) {
+                const float4 e = *reinterpret_cast<const float4 *>(raw_path + o);
+                x.x += fmaxf(e.x * tp.ps4.x + tp.pb4.x, 0.f);
+                x.y += fmaxf(e.y * tp.ps4.y + tp.pb4.y, 0.f);
+                x.z += fmaxf(e.z * tp.ps4.z + tp.pb4.z, 0.f);
+                x.w += fmaxf(e.w * tp.ps4.w + tp.pb4.w, 0.f);
+            }
+            acc.x += x.x * wv.x; acc.y += x.y * wv.y; acc.z += x.z * wv.z; acc.w += x.w * wv.w;
         }
-        fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, 128);
-    fence_proxy_async();
+    return acc;
+}
+
+// Shared memory: DxSmem followed by the raw input frames [(NF + kt - 1) * Fin][64] and, for the decoder blocks,
+// the pathway frames of the same shape.  Thread 0 asks the TMA engine for every frame the tile needs (one
+// contiguous Fin * 256-byte bulk copy per frame) plus the pre-swizzled 16 KB weight image, so a CTA has its
+// whole input in flight at once without holding it in registers.
+template <int MODE>
+__global__ void __launch_bounds__(kDxThreads, 2)
+k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 k] BF16, 128B-swizzled rows */) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    DxSmem &sm = *reinterpret_cast<DxSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, t0 = blockIdx.x * p.NF;
+    const int nf = min(p.NF, p.T - t0);
+    const int R = nf * p.Fout;  // rows actually present
+    const int tq0 = t0 - (p.kt - 1);
+    const int raw_frames = p.NF + p.kt - 1;
+    float *raw_in = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(&sm) + sizeof(DxSmem));
+    float *raw_path = p.path ? raw_in + raw_frames * p.Fin * kCh : nullptr;
+    if (tid == 0) {
+        mbar_init(&sm.mma_done, 1);
+        mbar_init(&sm.raw_full, 1);
+        fence_barrier_init();
+        const uint32_t fbytes = (uint32_t)p.Fin * kCh * 4;
+        const int ta = max(tq0, 0), tb = t0 + nf;  // frames [ta, tb)
+        mbar_expect_tx(&sm.raw_full, (uint32_t)(tb - ta) * fbytes * (p.path ? 2u : 1u) + 2u * kCh * 128u);
+        for (int t = ta; t < tb; t++) {
+            bulk_load(raw_in + (t - tq0) * p.Fin * kCh, p.in + ((int64_t)b * p.T + t) * p.in_fs, fbytes, &sm.raw_full);
+            if (p.path) bulk_load(raw_path + (t - tq0) * p.Fin * kCh, p.path + ((int64_t)b * p.T + t) * p.path_fs, fbytes, &sm.raw_full);
+        }
+        bulk_load(sm.w[0], w_sw, 2 * kCh * 128, &sm.raw_full);
+    }
+    if (warp == 1) tmem_alloc(&sm.tmem_base, kCh);
+    if (tid < kCh) sm.bias[tid] = p.bias[tid];
+    const int cq = tid & 15, slot = tid >> 4;
+    DwTaps taps;
+    dw_load_taps(p, cq, taps);
+    __syncthreads();  // barrier initialised before anyone waits on it
+    mbar_wait(&sm.raw_full, 0);
+    // ---- prologue: thread = (row slot, channel quad); rows r = slot + 16 i
+#pragma unroll 2
+    for (int i = 0; i < 8; i++) {
+        const int r = slot + 16 * i;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < R) {
+            const int fr = r / p.Fout, fo = r - fr * p.Fout;
+            acc = dw_prologue_smem<MODE>(p, taps, raw_in, raw_path, tq0, t0 + fr, fo, cq);
+        }
+        uint2 hi, lo;
+        bf16x2_split(acc.x, acc.y, hi.x, lo.x);
+        bf16x2_split(acc.z, acc.w, hi.y, lo.y);
+        const uint32_t off = sw128_off(r, cq >> 1) + (cq & 1) * 8;
+        *reinterpret_cast<uint2 *>(sm.a[0] + off) = hi;
+        *reinterpret_cast<uint2 *>(sm.a[1] + off) = lo;
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const int total_tiles = B * tiles_per_stream;
-
-    if (warp < 4) {
-        // ================================================================= producers
-        const int cq = tid & 15, slot = tid >> 4;  // 16 channel quads x 8 row slots
-        DwTaps taps;
-        dw_load_taps(p, cq, taps);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-            const int buf = it & 1, n = it >> 1;
-            const int b = tile / tiles_per_stream, t0 = (tile - b * tiles_per_stream) * p.NF;
-            const int R = min(p.NF, p.T - t0) * p.Fout;
-            if (n > 0) mbar_wait(&sm.a_empty[buf], (n - 1) & 1);
-            unsigned char *abase = reinterpret_cast<unsigned char *>(sm.a[buf][cq >> 3]);
-#pragma unroll 4
-            for (int r = slot; r < 128; r += 8) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < R) {
-                    const int fr = r / p.Fout, fo = r - fr * p.Fout;
-                    acc = dw_prologue<MODE>(p, taps, b, t0 + fr, fo, cq);
-                    acc.x = to_tf32(acc.x); acc.y = to_tf32(acc.y); acc.z = to_tf32(acc.z); acc.w = to_tf32(acc.w);
-                }
-                *reinterpret_cast<float4 *>(abase + sw128_off(r, cq & 7)) = acc;
-            }
-            fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.a_full[buf]);
+    if (warp == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, kCh);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint64_t ah = umma_desc_sw128(smem_u32(sm.a[0])), al = umma_desc_sw128(smem_u32(sm.a[1]));
+        const uint64_t bh = umma_desc_sw128(smem_u32(sm.w[0])), bl = umma_desc_sw128(smem_u32(sm.w[1]));
+#pragma unroll
+        for (int k = 0; k < kCh / 16; k++) {  // 32 bytes per K step inside the 128-byte swizzle row
+            umma_bf16_ss_elect(tmem_u, ah + 2 * k, bh + 2 * k, idesc, k != 0);
+            umma_bf16_ss_elect(tmem_u, al + 2 * k, bh + 2 * k, idesc, 1u);
+            umma_bf16_ss_elect(tmem_u, ah + 2 * k, bl + 2 * k, idesc, 1u);
         }
-    } else if (warp == 8) {
-        // ================================================================= MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(128, kCh);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-                const int buf = it & 1, n = it >> 1;
-                mbar_wait(&sm.a_full[buf], n & 1);
-                if (n > 0) mbar_wait(&sm.t_empty[buf], (n - 1) & 1);
-                tc_fence_after();
+        umma_commit_elect(&sm.mma_done);
+    }
+    mbar_wait(&sm.mma_done, 0);
+    tc_fence_after();
+    // ---- accumulator -> bias + ReLU -> staging tile (row r, 16-byte chunk j at r * 256 + ((j ^ (r & 15)) << 4))
+    unsigned char *stage = sm.a[0];
+    {
+        const int q = warp & 3, ch = warp >> 2;  // TMEM lane quarter, column half
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ch * 32, v);
+        const int r = q * 32 + lane;
+        unsigned char *row = stage + r * 256;
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const uint32_t a0 = smem_u32(sm.a[buf][c]), b0 = smem_u32(sm.w[c]);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        umma_tf32(tmem + buf * 64, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
-                                  (c | k) != 0);
-                }
-                umma_commit(&sm.a_empty[buf]);
-                umma_commit(&sm.t_full[buf]);
-            }
-        }
-    } else {
-        // ================================================================= epilogue (warps 4-7)
-        const int q = warp - 4;  // TMEM lane quarter of this warp (warp % 4)
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-            const int buf = it & 1, n = it >> 1;
-            const int b = tile / tiles_per_stream, t0 = (tile - b * tiles_per_stream) * p.NF;
-            const int R = min(p.NF, p.T - t0) * p.Fout;
-            mbar_wait(&sm.t_full[buf], n & 1);
-            tc_fence_after();
-            float v0[32], v1[32];
-            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + buf * 64;
-            tmem_ld32(ta, v0);
-            tmem_ld32(ta + 32, v1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.t_empty[buf]);
-            const int r = q * 32 + lane;
-            if (r < R) {
-                const int fr = r / p.Fout, fo = r - fr * p.Fout;
-                float *dst = p.out + ((int64_t)b * p.T + t0 + fr) * p.out_fs + fo * kCh;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[j]);
-                    *reinterpret_cast<float4 *>(dst + j) = make_float4(fmaxf(v0[j] + bv.x, 0.f), fmaxf(v0[j + 1] + bv.y, 0.f),
-                                                                      fmaxf(v0[j + 2] + bv.z, 0.f), fmaxf(v0[j + 3] + bv.w, 0.f));
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[32 + j]);
-                    *reinterpret_cast<float4 *>(dst + 32 + j) = make_float4(fmaxf(v1[j] + bv.x, 0.f), fmaxf(v1[j + 1] + bv.y, 0.f),
-                                                                           fmaxf(v1[j + 2] + bv.z, 0.f), fmaxf(v1[j + 3] + bv.w, 0.f));
-                }
-            }
+        for (int jj = 0; jj < 8; jj++) {
+            const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[ch * 32 + jj * 4]);
+            const float4 o = make_float4(fmaxf(v[jj * 4] + bv.x, 0.f), fmaxf(v[jj * 4 + 1] + bv.y, 0.f),
+                                         fmaxf(v[jj * 4 + 2] + bv.z, 0.f), fmaxf(v[jj * 4 + 3] + bv.w, 0.f));
+            *reinterpret_cast<float4 *>(row + (((ch * 8 + jj) ^ (r & 15)) << 4)) = o;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 1) tmem_dealloc(tmem, kCh);
+    // ---- coalesced write-out: half a warp per 256-byte row
+    {
+        const int j = tid & 15;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = (tid >> 4) + 16 * i;
+            if (r < R) {
+                const int fr = r / p.Fout, fo = r - fr * p.Fout;
+                const float4 o = *reinterpret_cast<const float4 *>(stage + r * 256 + ((j ^ (r & 15)) << 4));
+                *reinterpret_cast<float4 *>(p.out + ((int64_t)b * p.T + t0 + fr) * p.out_fs + fo * kCh + j * 4) = o;
+            }
+        }
+    }
 }
 
 template <int MODE>
-int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *pw_nk, int B) {
-    static bool attr_done = false;
-    const int smem = (int)sizeof(DwTcSmem) + 1024;
-    static int resident = 0;  // CTAs that fit on the device at once (persistent grid size)
-    if (!attr_done) {
-        DFB_CUDA(cudaFuncSetAttribute(k_dwpw_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int dev = 0, num_sms = 0, per_sm = 0;
-        DFB_CUDA(cudaGetDevice(&dev));
-        DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dwpw_tc<MODE>, kDwTcThreads, smem));
-        resident = num_sms * (per_sm > 0 ? per_sm : 1);
-        attr_done = true;
-    }
+int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *w_sw, int B) {
+    static int attr_smem = 0;
     p.NF = 128 / p.Fout;
     if (p.NF < 1) p.NF = 1;
     if (p.NF * p.Fout > 128) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile: Fout = %d", p.Fout);
-    const int tiles_per_stream = (p.T + p.NF - 1) / p.NF;
-    const int64_t total = (int64_t)B * tiles_per_stream;
-    const int ctas = (int)(total < (int64_t)resident ? total : (int64_t)resident);
-    DFB_PROF(MODE == DW_DF0 ? "k_dwpw_tc[df_conv0]" : "k_dwpw_tc", s);
-    k_dwpw_tc<MODE><<<ctas, kDwTcThreads, smem, s>>>(p, pw_nk, B, tiles_per_stream);
+    const int raw = (p.NF + p.kt - 1) * p.Fin * kCh * 4 * (p.path ? 2 : 1);
+    const int smem = (int)sizeof(DxSmem) + 1024 + raw;
+    if (smem > 227 * 1024) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile needs %d bytes of shared memory", smem);
+    if ((p.in_fs * 4) % 16 || (p.path && (p.path_fs * 4) % 16)) return fail(DFB_ERR_UNSUPPORTED, "dwpw: unaligned frame stride");
+    if (smem > attr_smem) {
+        DFB_CUDA(cudaFuncSetAttribute(k_dwpw_bx<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    dim3 grid((unsigned)((p.T + p.NF - 1) / p.NF), (unsigned)B);
+    DFB_PROF("k_dwpw_bx", s);
+    k_dwpw_bx<MODE><<<grid, kDxThreads, smem, s>>>(p, w_sw);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }
 template int launch_dwpw_tc<DW_S1>(cudaStream_t, DwPwParams, const float *, int);
 template int launch_dwpw_tc<DW_S2>(cudaStream_t, DwPwParams, const float *, int);
 template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int);
-template int launch_dwpw_tc<DW_DF0>(cudaStream_t, DwPwParams, const float *, int);
 
 // ================================================================ tensor-core GRU recurrence ====
 // torch.nn.GRU cell (DeepFilterNet/df/modules.py:684,723), hidden size 256.  A cluster of 8 CTAs owns

@@ -118,7 +118,7 @@ class DfNet(nn.Module):
           'tf32' / 'tf32+gru_tc'  additionally TF32 tcgen05 for the feed-forward contractions (faster GEMMs,
                          but ~1e-5 .. 3e-4 RMS end to end depending on the signal -- NOT within the 1e-4
                          parity bound on loud speech; kept for experiments only)."""
-        check(_lib.lib().dfb_model_set_precision(self._h, {"fp32": 0, "tf32": 1, "fp32+gru_tc": 2, "tf32+gru_tc": 3, "fp32+gru_tc+proj_tc": 6}[mode]))
+        check(_lib.lib().dfb_model_set_precision(self._h, {"fp32": 0, "tf32": 1, "fp32+gru_tc": 2, "tf32+gru_tc": 3, "fp32+gru_tc+proj_tc": 6, "fp32+gru_tc+proj_tc+conv_tc": 14}[mode]))
         self.precision = mode
 
     def __del__(self):

@@ -65,6 +65,23 @@ def bf16_planes(w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return pack(hi), pack(lo)
 
 
+def umma_sw128_image(w_nk: np.ndarray) -> np.ndarray:
+    """[N][64] fp32 -> the shared-memory image of the K-major, 128-byte-swizzled tcgen05 B operand: BF16 hi plane
+    then lo plane, each N rows of 128 bytes with 16-byte chunk j of row n stored at chunk j ^ (n & 7)."""
+    hi, lo = bf16_planes(w_nk)
+    n = w_nk.shape[0]
+    assert w_nk.shape[1] == 64 and n % 8 == 0
+    planes = []
+    for pl in (hi, lo):
+        c = pl.reshape(n, 8, 4)  # [row][16-byte chunk][4 floats = 8 bf16]
+        o = np.empty_like(c)
+        rows = np.arange(n)
+        for j in range(8):
+            o[rows, j ^ (rows & 7)] = c[rows, j]
+        planes.append(o.reshape(-1))
+    return np.ascontiguousarray(np.concatenate(planes))
+
+
 def gru_layers(sd, prefix: str) -> int:
     n = 0
     while f"{prefix}.weight_ih_l{n}" in sd:
@@ -97,6 +114,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
         out[prefix + ".dw"] = f32(dw[:, 0].transpose(1, 2, 0))
         out[prefix + ".pw"] = f32((pw * s[:, None]).T)
         out[prefix + ".pw_nk"] = f32(pw * s[:, None])  # [C_out][C_in]: B operand of the tcgen05 kernel
+        out[prefix + ".pw_sw"] = umma_sw128_image(out[prefix + ".pw_nk"])  # BF16x3 tcgen05 path
         out[prefix + ".b"] = f32(b)
         return dw.shape[2]
 
