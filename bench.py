@@ -45,9 +45,11 @@ KERNEL_MODEL = {
     "k_grouped_linear[gru_proj]": ("tensor", 2 * 5 * 256 * 768, "flops"),
     "k_grouped_linear": ("tensor", 2 * (3072 * 16 + 512 * 16 + 256 * 32 + 512 * 16 + 256 * 32 + 512 * 32 + 512 * 16 + 256 * 60), "flops"),
     "k_dwpw": ("tensor", 2 * 64 * 64 * (16 + 8 + 8 + 48 + 8 + 16 + 32), "flops"),
+    # fused depthwise -> tcgen05 1x1: rows read (input + pathway) + rows written, 256 B each, over the 7 separable blocks
+    "k_dwpw_bx": ("hbm", 256 * ((96 + 48) + (32 + 16) + (16 + 8) + (8 + 8) + (8 + 8 + 8) + (8 + 8 + 16) + (16 + 16 + 32)), "bytes"),
     "k_conv_in[df_conv0]": ("hbm", 96 * 8 + 96 * 256, "bytes"),             # reads feat_spec, writes c0
     "k_conv_in[erb_conv0]": ("hbm", 128 + 32 * 256, "bytes"),
-    "k_df_convp": ("hbm", 96 * 256 + 2 * 96 * 40, "bytes"),                 # reads c0 once, read-modify-write coefs
+    "k_df_convp": ("hbm", 96 * 256 + 96 * 40, "bytes"),                     # reads c0 once, writes the pathway term of coefs
     "k_mask_out": ("hbm", 2 * 32 * 256 + 128, "bytes"),
 }
 

@@ -37,6 +37,7 @@ struct DwPwParams {
     float *out;           // [B,T,Fout,64]
     int64_t in_fs, path_fs, out_fs;  // frame strides (floats)
     int T, Fin, Fout, kt, NF, lookahead;
+    int fo_magic;         // ceil(65536 / Fout): r / Fout == (r * fo_magic) >> 16 for r < 128 (tensor-core kernel)
 };
 
 

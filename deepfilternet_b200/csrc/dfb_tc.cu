@@ -334,27 +334,25 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 
 // ------------------------------------------- fused depthwise -> 1x1 (tcgen05) -> ReLU ----
 // Tensor-core version of k_dwpw (dfb_model.cu) at fp32-level accuracy (BF16x3): one CTA per 128-row tile.
-//   1. all 256 threads run the depthwise (+pathway) prologue (shared with the FFMA kernel), split the result
-//      x = hi + lo into BF16 planes and write them straight into shared memory in the UMMA K-major 128B-swizzle
-//      layout (a row of 64 channels is exactly one 128-byte swizzle row);
-//   2. warp 0 issues 12 tcgen05.mma (M128 N64 K16; hi*hi + lo*hi + hi*lo) against the pre-split 1x1 weights,
-//      fp32 accumulator in 64 TMEM columns;
+//   0. thread 0 asks the TMA engine for every raw input (and pathway) frame of the tile -- one contiguous
+//      Fin * 256-byte bulk copy per frame -- plus the pre-swizzled 16 KB weight image: the CTA's whole input is
+//      in flight at once without passing through registers;
+//   1. all 256 threads run the depthwise (+pathway) prologue out of shared memory (thread = channel quad x 8
+//      consecutive rows), split the result x = hi + lo into BF16 planes and write them in the UMMA K-major
+//      128B-swizzle layout (a row of 64 channels is exactly one 128-byte swizzle row);
+//   2. warp 0 issues 12 tcgen05.mma (M128 N64 K16; hi*hi + lo*hi + hi*lo), fp32 accumulator in 64 TMEM columns;
 //   3. all 8 warps read their TMEM lane quarter / column half (tcgen05.ld), add bias, ReLU and stage the fp32
-//      tile in the (now free) operand buffers with an XOR chunk swizzle -- conflict free for row-per-lane writes;
-//   4. the CTA streams the staged tile out with fully coalesced 512-byte warp stores.
-// 3 CTAs per SM overlap each other's load / MMA / store phases.
-struct DxSmem {
-    alignas(1024) unsigned char a[2][128 * 128];  // A hi | lo planes; afterwards the fp32 [128][64] output staging tile
-    alignas(1024) unsigned char w[2][kCh * 128];  // W hi | lo planes: [n][k] BF16
-    alignas(16) float bias[kCh];
-    alignas(8) uint64_t mma_done;
-    uint64_t raw_full;
-    uint32_t tmem_base;
-};
+//      tile in the (now free) operand planes with an XOR chunk swizzle -- conflict free for row-per-lane writes;
+//   4. the CTA streams the staged tile out with coalesced 256-byte half-warp stores.
+// Two CTAs per SM overlap each other's load / MMA / store phases.  Shared memory (1024-byte aligned base):
+//   [0, 32K) A hi | lo planes (later the fp32 staging tile)   [32K, 48K) W hi | lo   [48K, 48K + raw) raw frames
+//   then bias[64], two mbarriers, the TMEM base address.
+constexpr int kDxThreads = 256;
+constexpr uint32_t kDxW = 32768, kDxRaw = 49152, kDxTail = 64 * 4 + 32;
 
 // byte offset of (row r, 16-byte chunk j) inside a [rows x 128 B] sub-tile with 128-byte swizzle
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+    return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -364,7 +362,7 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-// (x.x, x.y) -> packed bf16x2 hi plane and lo plane (x = hi + lo, both round to nearest even)
+// (x0, x1) -> packed bf16x2 hi plane and lo plane (x = hi + lo, both round to nearest even)
 __device__ __forceinline__ void bf16x2_split(float x0, float x1, uint32_t &hi, uint32_t &lo) {
     __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
     const float2 hf = __bfloat1622float2(h);
@@ -372,181 +370,246 @@ __device__ __forceinline__ void bf16x2_split(float x0, float x1, uint32_t &hi, u
     hi = *reinterpret_cast<uint32_t *>(&h);
     lo = *reinterpret_cast<uint32_t *>(&l);
 }
-
-constexpr int kDxThreads = 256;
-
+// explicit shared-window accesses on 32-bit addresses (the struct-over-aligned-raw-buffer idiom makes the
+// compiler fall back to generic LD / ST and 64-bit address arithmetic)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
 // 1-D bulk copy global -> own shared memory, completing on an mbarrier (TMA engine, no registers involved)
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
                  : "memory");
 }
-
-// dw_prologue (dfb_dwpw.cuh) reading the raw input / pathway frames of this tile from shared memory:
-// raw row (frame tq, bin fi) at ((tq - tq0) * Fin + fi) * 256 bytes.
-template <int MODE>
-__device__ __forceinline__ float4 dw_prologue_smem(const DwPwParams &p, const DwTaps &tp, const float *raw_in, const float *raw_path,
-                                                   int tq0, int t, int fo, int cq) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int dt = 0; dt < 3; dt++) {
-        if (dt < 3 - p.kt) continue;
-        const int tq = t - (2 - dt);  // causal: taps at t-(kt-1) .. t
-        if (tq < 0) continue;
-#pragma unroll
-        for (int df = 0; df < 3; df++) {
-            int fi;
-            float4 wv;
-            if (MODE == DW_S1) { fi = fo + df - 1; wv = tp.wd[dt * 3 + df]; }
-            else if (MODE == DW_S2) { fi = 2 * fo + df - 1; wv = tp.wd[dt * 3 + df]; }
-            else {  // DW_T2: df enumerates the (at most two) contributing taps
-                if (df == 2) continue;
-                if ((fo & 1) == 0) { if (df == 1) continue; fi = fo >> 1; wv = tp.wd[dt * 3 + 1]; }
-                else if (df == 0) { fi = fo >> 1; wv = tp.wd[dt * 3 + 2]; }
-                else { fi = (fo >> 1) + 1; wv = tp.wd[dt * 3 + 0]; }
-            }
-            if (fi < 0 || fi >= p.Fin) continue;
-            const int o = ((tq - tq0) * p.Fin + fi) * kCh + cq * 4;
-            float4 x = *reinterpret_cast<const float4 *>(raw_in + o);
-            if (raw_path) {
-                const float4 e = *reinterpret_cast<const float4 *>(raw_path + o);
-                x.x += fmaxf(e.x * tp.ps4.x + tp.pb4.x, 0.f);
-                x.y += fmaxf(e.y * tp.ps4.y + tp.pb4.y, 0.f);
-                x.z += fmaxf(e.z * tp.ps4.z + tp.pb4.z, 0.f);
-                x.w += fmaxf(e.w * tp.ps4.w + tp.pb4.w, 0.f);
-            }
-            acc.x += x.x * wv.x; acc.y += x.y * wv.y; acc.z += x.z * wv.z; acc.w += x.w * wv.w;
-        }
-    }
-    return acc;
+__device__ __forceinline__ float4 f4_fma(float4 x, float4 w, float4 a) {
+    return make_float4(fmaf(x.x, w.x, a.x), fmaf(x.y, w.y, a.y), fmaf(x.z, w.z, a.z), fmaf(x.w, w.w, a.w));
 }
 
-// Shared memory: DxSmem followed by the raw input frames [(NF + kt - 1) * Fin][64] and, for the decoder blocks,
-// the pathway frames of the same shape.  Thread 0 asks the TMA engine for every frame the tile needs (one
-// contiguous Fin * 256-byte bulk copy per frame) plus the pre-swizzled 16 KB weight image, so a CTA has its
-// whole input in flight at once without holding it in registers.
-template <int MODE>
+template <int MODE, int KT, int PATH>
 __global__ void __launch_bounds__(kDxThreads, 2)
 k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 k] BF16, 128B-swizzled rows */) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    DxSmem &sm = *reinterpret_cast<DxSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
+    const uint32_t sb = smem_u32(tc_smem_raw);
+    if (sb & 1023u) __trap();  // the swizzled operand planes need a 1024-byte aligned base
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, t0 = blockIdx.x * p.NF;
     const int nf = min(p.NF, p.T - t0);
     const int R = nf * p.Fout;  // rows actually present
-    const int tq0 = t0 - (p.kt - 1);
-    const int raw_frames = p.NF + p.kt - 1;
-    float *raw_in = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(&sm) + sizeof(DxSmem));
-    float *raw_path = p.path ? raw_in + raw_frames * p.Fin * kCh : nullptr;
+    const int tq0 = t0 - (KT - 1);
+    const uint32_t fbytes = (uint32_t)p.Fin * kCh * 4;
+    const uint32_t raw_in = sb + kDxRaw, raw_path = raw_in + (uint32_t)(p.NF + KT - 1) * fbytes;
+    const uint32_t tail = raw_in + (uint32_t)(p.NF + KT - 1) * fbytes * (PATH ? 2u : 1u);
+    const uint32_t s_bias = tail, bar_mma = tail + 256, bar_raw = tail + 264, s_tmem = tail + 272;
     if (tid == 0) {
-        mbar_init(&sm.mma_done, 1);
-        mbar_init(&sm.raw_full, 1);
+        mbar_init_a(bar_mma, 1);
+        mbar_init_a(bar_raw, 1);
         fence_barrier_init();
-        const uint32_t fbytes = (uint32_t)p.Fin * kCh * 4;
         const int ta = max(tq0, 0), tb = t0 + nf;  // frames [ta, tb)
-        mbar_expect_tx(&sm.raw_full, (uint32_t)(tb - ta) * fbytes * (p.path ? 2u : 1u) + 2u * kCh * 128u);
+        mbar_expect_tx_a(bar_raw, (uint32_t)(tb - ta) * fbytes * (PATH ? 2u : 1u) + 2u * kCh * 128u);
         for (int t = ta; t < tb; t++) {
-            bulk_load(raw_in + (t - tq0) * p.Fin * kCh, p.in + ((int64_t)b * p.T + t) * p.in_fs, fbytes, &sm.raw_full);
-            if (p.path) bulk_load(raw_path + (t - tq0) * p.Fin * kCh, p.path + ((int64_t)b * p.T + t) * p.path_fs, fbytes, &sm.raw_full);
+            bulk_load(raw_in + (uint32_t)(t - tq0) * fbytes, p.in + ((int64_t)b * p.T + t) * p.in_fs, fbytes, bar_raw);
+            if (PATH) bulk_load(raw_path + (uint32_t)(t - tq0) * fbytes, p.path + ((int64_t)b * p.T + t) * p.path_fs, fbytes, bar_raw);
         }
-        bulk_load(sm.w[0], w_sw, 2 * kCh * 128, &sm.raw_full);
+        bulk_load(sb + kDxW, w_sw, 2 * kCh * 128, bar_raw);
     }
-    if (warp == 1) tmem_alloc(&sm.tmem_base, kCh);
-    if (tid < kCh) sm.bias[tid] = p.bias[tid];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(kCh) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < kCh / 4) sts128(s_bias + tid * 16, __ldg(reinterpret_cast<const float4 *>(p.bias) + tid));
+    // ---- depthwise taps of this thread's channel quad, pathway affine
     const int cq = tid & 15, slot = tid >> 4;
-    DwTaps taps;
-    dw_load_taps(p, cq, taps);
-    __syncthreads();  // barrier initialised before anyone waits on it
-    mbar_wait(&sm.raw_full, 0);
-    // ---- prologue: thread = (row slot, channel quad); rows r = slot + 16 i
-#pragma unroll 2
-    for (int i = 0; i < 8; i++) {
-        const int r = slot + 16 * i;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < R) {
-            const int fr = r / p.Fout, fo = r - fr * p.Fout;
-            acc = dw_prologue_smem<MODE>(p, taps, raw_in, raw_path, tq0, t0 + fr, fo, cq);
+    float4 wd[KT][3], ps4, pb4;
+#pragma unroll
+    for (int dt = 0; dt < KT; dt++)
+#pragma unroll
+        for (int df = 0; df < 3; df++) wd[dt][df] = __ldg(reinterpret_cast<const float4 *>(p.dw + (dt * 3 + df) * kCh) + cq);
+    if (PATH) {
+        ps4 = __ldg(reinterpret_cast<const float4 *>(p.ps) + cq);
+        pb4 = __ldg(reinterpret_cast<const float4 *>(p.pb) + cq);
+    }
+    // rows r = 8 slot + i: (frame fr, bin fo) by multiply-shift division (exact for r < 128), then incrementally
+    int fr = (8 * slot * p.fo_magic) >> 16, fo = 8 * slot - fr * p.Fout;
+    __syncthreads();  // barriers initialised before anyone waits on them
+    mbar_wait_a(bar_raw, 0);
+    // ---- prologue
+    auto rd = [&](uint32_t a) -> float4 {
+        float4 x = lds128(a);
+        if (PATH) {
+            const float4 e = lds128(a + (raw_path - raw_in));
+            x.x += fmaxf(fmaf(e.x, ps4.x, pb4.x), 0.f); x.y += fmaxf(fmaf(e.y, ps4.y, pb4.y), 0.f);
+            x.z += fmaxf(fmaf(e.z, ps4.z, pb4.z), 0.f); x.w += fmaxf(fmaf(e.w, ps4.w, pb4.w), 0.f);
         }
-        uint2 hi, lo;
-        bf16x2_split(acc.x, acc.y, hi.x, lo.x);
-        bf16x2_split(acc.z, acc.w, hi.y, lo.y);
-        const uint32_t off = sw128_off(r, cq >> 1) + (cq & 1) * 8;
-        *reinterpret_cast<uint2 *>(sm.a[0] + off) = hi;
-        *reinterpret_cast<uint2 *>(sm.a[1] + off) = lo;
+        return x;
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int r = 8 * slot + i;
+        float4 acc = zero4;
+        if (r < R) {
+#pragma unroll
+            for (int dt = 0; dt < KT; dt++) {
+                // tap dt reads frame t - (KT-1-dt) = raw frame fr + dt; before the start of the stream it is zero padding
+                if (KT > 1 && tq0 + fr + dt < 0) continue;
+                const uint32_t fb = raw_in + (uint32_t)(fr + dt) * fbytes + cq * 16;
+                if (MODE == DW_S1) {
+                    const uint32_t a = fb + (uint32_t)fo * 256;
+                    if (fo > 0) acc = f4_fma(rd(a - 256), wd[dt][0], acc);
+                    acc = f4_fma(rd(a), wd[dt][1], acc);
+                    if (fo + 1 < p.Fin) acc = f4_fma(rd(a + 256), wd[dt][2], acc);
+                } else if (MODE == DW_S2) {
+                    const uint32_t a = fb + (uint32_t)fo * 512;
+                    if (fo > 0) acc = f4_fma(rd(a - 256), wd[dt][0], acc);
+                    acc = f4_fma(rd(a), wd[dt][1], acc);
+                    acc = f4_fma(rd(a + 256), wd[dt][2], acc);
+                } else {  // DW_T2: out[2j] = w1 x[j]; out[2j+1] = w2 x[j] + w0 x[j+1]
+                    const uint32_t a = fb + (uint32_t)(fo >> 1) * 256;
+                    if ((fo & 1) == 0) {
+                        acc = f4_fma(rd(a), wd[dt][1], acc);
+                    } else {
+                        acc = f4_fma(rd(a), wd[dt][2], acc);
+                        if ((fo >> 1) + 1 < p.Fin) acc = f4_fma(rd(a + 256), wd[dt][0], acc);
+                    }
+                }
+            }
+        }
+        uint32_t h0, l0, h1, l1;
+        bf16x2_split(acc.x, acc.y, h0, l0);
+        bf16x2_split(acc.z, acc.w, h1, l1);
+        const uint32_t off = sb + sw128_off(r, cq >> 1) + (cq & 1) * 8;
+        sts64(off, h0, h1);
+        sts64(off + 16384, l0, l1);
+        if (++fo == p.Fout) { fo = 0; fr++; }
     }
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = sm.tmem_base;
+    const uint32_t tmem = lds32(s_tmem);
     if (warp == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, kCh);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-        const uint64_t ah = umma_desc_sw128(smem_u32(sm.a[0])), al = umma_desc_sw128(smem_u32(sm.a[1]));
-        const uint64_t bh = umma_desc_sw128(smem_u32(sm.w[0])), bl = umma_desc_sw128(smem_u32(sm.w[1]));
+        const uint64_t ah = umma_desc_sw128(sb), al = umma_desc_sw128(sb + 16384);
+        const uint64_t bh = umma_desc_sw128(sb + kDxW), bl = umma_desc_sw128(sb + kDxW + 8192);
 #pragma unroll
         for (int k = 0; k < kCh / 16; k++) {  // 32 bytes per K step inside the 128-byte swizzle row
             umma_bf16_ss_elect(tmem_u, ah + 2 * k, bh + 2 * k, idesc, k != 0);
             umma_bf16_ss_elect(tmem_u, al + 2 * k, bh + 2 * k, idesc, 1u);
             umma_bf16_ss_elect(tmem_u, ah + 2 * k, bl + 2 * k, idesc, 1u);
         }
-        umma_commit_elect(&sm.mma_done);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred e;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+            "}\n" ::"r"(bar_mma)
+            : "memory");
     }
-    mbar_wait(&sm.mma_done, 0);
+    mbar_wait_a(bar_mma, 0);
     tc_fence_after();
     // ---- accumulator -> bias + ReLU -> staging tile (row r, 16-byte chunk j at r * 256 + ((j ^ (r & 15)) << 4))
-    unsigned char *stage = sm.a[0];
     {
         const int q = warp & 3, ch = warp >> 2;  // TMEM lane quarter, column half
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ch * 32, v);
         const int r = q * 32 + lane;
-        unsigned char *row = stage + r * 256;
+        const uint32_t row = sb + r * 256;
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
-            const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[ch * 32 + jj * 4]);
-            const float4 o = make_float4(fmaxf(v[jj * 4] + bv.x, 0.f), fmaxf(v[jj * 4 + 1] + bv.y, 0.f),
-                                         fmaxf(v[jj * 4 + 2] + bv.z, 0.f), fmaxf(v[jj * 4 + 3] + bv.w, 0.f));
-            *reinterpret_cast<float4 *>(row + (((ch * 8 + jj) ^ (r & 15)) << 4)) = o;
+            const float4 bv = lds128(s_bias + (ch * 8 + jj) * 16);
+            sts128(row + (((ch * 8 + jj) ^ (r & 15)) << 4),
+                   make_float4(fmaxf(v[jj * 4] + bv.x, 0.f), fmaxf(v[jj * 4 + 1] + bv.y, 0.f), fmaxf(v[jj * 4 + 2] + bv.z, 0.f),
+                               fmaxf(v[jj * 4 + 3] + bv.w, 0.f)));
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, kCh);
-    // ---- coalesced write-out: half a warp per 256-byte row
+    // ---- coalesced write-out: half a warp per 256-byte row, 8 consecutive rows per thread
     {
         const int j = tid & 15;
+        int fr2 = (8 * slot * p.fo_magic) >> 16, fo2 = 8 * slot - fr2 * p.Fout;
+        float *dst = p.out + ((int64_t)b * p.T + t0 + fr2) * p.out_fs + fo2 * kCh + j * 4;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int r = (tid >> 4) + 16 * i;
-            if (r < R) {
-                const int fr = r / p.Fout, fo = r - fr * p.Fout;
-                const float4 o = *reinterpret_cast<const float4 *>(stage + r * 256 + ((j ^ (r & 15)) << 4));
-                *reinterpret_cast<float4 *>(p.out + ((int64_t)b * p.T + t0 + fr) * p.out_fs + fo * kCh + j * 4) = o;
-            }
+            const int r = 8 * slot + i;
+            if (r < R) *reinterpret_cast<float4 *>(dst) = lds128(sb + r * 256 + ((j ^ (r & 15)) << 4));
+            dst += kCh;
+            if (++fo2 == p.Fout) { fo2 = 0; dst += p.out_fs - (int64_t)p.Fout * kCh; }
         }
     }
 }
 
-template <int MODE>
-int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *w_sw, int B) {
+template <int MODE, int KT, int PATH>
+static int launch_dwpw_bx(cudaStream_t s, const DwPwParams &p, const float *w_sw, int B) {
     static int attr_smem = 0;
-    p.NF = 128 / p.Fout;
-    if (p.NF < 1) p.NF = 1;
-    if (p.NF * p.Fout > 128) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile: Fout = %d", p.Fout);
-    const int raw = (p.NF + p.kt - 1) * p.Fin * kCh * 4 * (p.path ? 2 : 1);
-    const int smem = (int)sizeof(DxSmem) + 1024 + raw;
+    const int raw = (p.NF + KT - 1) * p.Fin * kCh * 4 * (PATH ? 2 : 1);
+    const int smem = (int)kDxRaw + raw + (int)kDxTail;
     if (smem > 227 * 1024) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile needs %d bytes of shared memory", smem);
-    if ((p.in_fs * 4) % 16 || (p.path && (p.path_fs * 4) % 16)) return fail(DFB_ERR_UNSUPPORTED, "dwpw: unaligned frame stride");
     if (smem > attr_smem) {
-        DFB_CUDA(cudaFuncSetAttribute(k_dwpw_bx<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DFB_CUDA(cudaFuncSetAttribute(k_dwpw_bx<MODE, KT, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
     dim3 grid((unsigned)((p.T + p.NF - 1) / p.NF), (unsigned)B);
     DFB_PROF("k_dwpw_bx", s);
-    k_dwpw_bx<MODE><<<grid, kDxThreads, smem, s>>>(p, w_sw);
+    k_dwpw_bx<MODE, KT, PATH><<<grid, kDxThreads, smem, s>>>(p, w_sw);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
+}
+
+template <int MODE>
+int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *w_sw, int B) {
+    p.NF = 128 / p.Fout;
+    if (p.NF < 1) p.NF = 1;
+    if (p.NF * p.Fout > 128) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile: Fout = %d", p.Fout);
+    p.fo_magic = (65536 + p.Fout - 1) / p.Fout;
+    for (int r = 0; r < 128; r++)
+        if (((r * p.fo_magic) >> 16) != r / p.Fout) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile: Fout = %d", p.Fout);
+    if ((p.in_fs * 4) % 16 || (p.path && (p.path_fs * 4) % 16)) return fail(DFB_ERR_UNSUPPORTED, "dwpw: unaligned frame stride");
+    const bool path = p.path != nullptr;
+    if (MODE == DW_S1) {
+        if (p.kt == 1) return path ? launch_dwpw_bx<DW_S1, 1, 1>(s, p, w_sw, B) : launch_dwpw_bx<DW_S1, 1, 0>(s, p, w_sw, B);
+        if (p.kt == 2) return path ? launch_dwpw_bx<DW_S1, 2, 1>(s, p, w_sw, B) : launch_dwpw_bx<DW_S1, 2, 0>(s, p, w_sw, B);
+    } else if (MODE == DW_S2 && !path) {
+        if (p.kt == 1) return launch_dwpw_bx<DW_S2, 1, 0>(s, p, w_sw, B);
+        if (p.kt == 2) return launch_dwpw_bx<DW_S2, 2, 0>(s, p, w_sw, B);
+    } else if (MODE == DW_T2 && path && p.kt == 1) {
+        return launch_dwpw_bx<DW_T2, 1, 1>(s, p, w_sw, B);
+    }
+    return fail(DFB_ERR_UNSUPPORTED, "dwpw tensor-core path: mode %d kt %d path %d", MODE, p.kt, (int)path);
 }
 template int launch_dwpw_tc<DW_S1>(cudaStream_t, DwPwParams, const float *, int);
 template int launch_dwpw_tc<DW_S2>(cudaStream_t, DwPwParams, const float *, int);

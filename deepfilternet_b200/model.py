@@ -105,12 +105,14 @@ class DfNet(nn.Module):
                                           widths.ctypes.data_as(C.POINTER(C.c_int64))))
         self._h = h
         self._derived = derived
-        self.set_precision(os.environ.get("DFB_PRECISION", "fp32+gru_tc+proj_tc"))
+        self.set_precision(os.environ.get("DFB_PRECISION", "fp32+gru_tc+proj_tc+conv_tc"))
 
     def set_precision(self, mode: str) -> None:
         """Arithmetic of the contractions (everything else is always IEEE fp32):
           'fp32'         FFMA everywhere
-          'fp32+gru_tc+proj_tc'  (default) as 'fp32+gru_tc' plus the GRU input projections on the BF16x3
+          'fp32+gru_tc+proj_tc+conv_tc'  (default) as below plus the 1x1 convs of the separable conv blocks on
+                         the fused BF16x3 tcgen05 kernel (k_dwpw_bx)
+          'fp32+gru_tc+proj_tc'  as 'fp32+gru_tc' plus the GRU input projections on the BF16x3
                          tcgen05 GEMM (operands as BF16 hi/lo planes, 3 MMAs per product; 1e-7 .. 4e-7 RMS)
           'fp32+gru_tc'  as 'fp32', but the GRU recurrence of H = 256 models runs on tcgen05 tensor
                          cores with BF16 hi/lo split operands (3 MMAs per product, fp32 accumulate: ~2^-17
