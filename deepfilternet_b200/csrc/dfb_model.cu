@@ -839,7 +839,12 @@ int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const fl
     int tiles = (p.Hg + kGlBN - 1) / kGlBN;
     int gpc = (p.Hg < kGlBN && kGlBN % p.Hg == 0) ? (kGlBN / p.Hg < G ? kGlBN / p.Hg : G) : 1;
     dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(((G + gpc - 1) / gpc) * tiles));
-    DFB_PROF(p.G == 1 && p.bias && p.Hg >= 512 ? "k_grouped_linear[gru_proj]" : "k_grouped_linear", s);
+    // DFB_PROF_DETAIL=1 splits the grouped linears by shape in the profile (I x H / G)
+    static const bool detail = getenv("DFB_PROF_DETAIL") && atoi(getenv("DFB_PROF_DETAIL"));
+    char name[64];
+    if (detail) snprintf(name, sizeof name, "k_grouped_linear[%dx%d/%d]", I, Hh, G);
+    else snprintf(name, sizeof name, "%s", p.G == 1 && p.bias && p.Hg >= 512 ? "k_grouped_linear[gru_proj]" : "k_grouped_linear");
+    DFB_PROF(name, s);
     k_grouped_linear<<<grid, 256, 0, s>>>(p);
     DFB_LAUNCH_CHECK();
     return DFB_OK;

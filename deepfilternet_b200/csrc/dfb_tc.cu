@@ -225,18 +225,26 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // Y[M,N] = X[M,K] . W[N,K]^T + bias with fp32-level accuracy on the BF16 tensor pipe: both operands
 // are stored as BF16 hi/lo planes (x = hi + lo to ~2^-17; X planes written by the producing kernel's
 // epilogue, W planes split on the host) and every product is hi*hi + lo*hi + hi*lo with fp32
-// accumulation in TMEM.  One CTA per 128 x 64 output tile; warp 4 = TMA producer (four 2-D bulk
-// tensor loads per 64-wide k block, 128B swizzle), warp 5 = MMA issuer (12 tcgen05.mma per k block,
-// elect.sync issue), warps 0-3 = epilogue (tcgen05.ld, + bias, 256-byte row stores).
-constexpr int kBxBM = 128, kBxBN = 64, kBxBK = 64, kBxStages = 2;
+// accumulation in TMEM.
+// W-stationary, transposed: a persistent CTA owns 128 output columns; its W slice [128 n][K <= 256] sits in
+// TENSOR MEMORY for the whole kernel (hi | lo planes, 256 columns) and is the MMA's A operand (TS mode), the
+// X tiles (128 rows x 64 k per stage, hi + lo = 32 KB) stream through a 6-stage TMA ring as the B operand,
+// and the accumulator D[n][m] (two 128-column TMEM buffers) comes out transposed: TMEM lane = output column,
+// so every epilogue store instruction writes 128 contiguous bytes of one output row.
+// History (ncu): one CTA per 128 x 64 tile re-read the X tile 12 times -- 2.3 GB of L2 -> SM traffic per
+// projection, lts-bound at 6 TB/s, IPC 0.24; an X-stationary version could keep only 80 KB of W in flight
+// next to its 128 KB X tile and was latency bound.  Here all of shared memory is the in-flight ring.
+// warps 0-7 = W load (0-3), then epilogue (lane quarter = warp % 4, column half = warp / 4; two warps per
+// scheduler -- with four the epilogue's dependent address / store chain was the bottleneck, ncu: 80 % of the
+// samples); warp 8 = TMA producer; warp 9 = MMA issuer (elect.sync issue).
+constexpr int kBxBM = 128 /* x rows per tile (MMA N) */, kBxBN = 128 /* output columns per CTA (MMA M) */, kBxBK = 64,
+              kBxStages = 6, kBxMaxK = 256;
 
 struct BxSmem {
-    alignas(1024) unsigned char a[kBxStages][2][kBxBM * 128];  // [stage][hi|lo][128 rows x 64 bf16]
-    alignas(1024) unsigned char b[kBxStages][2][kBxBN * 128];
-    alignas(16) float bias[kBxBN];
+    alignas(1024) unsigned char x[kBxStages][2][kBxBM * 128];  // [stage][hi|lo][128 rows x 64 bf16], 128B swizzle
     alignas(8) uint64_t full[kBxStages];
     uint64_t empty[kBxStages];
-    uint64_t tmem_full;
+    uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
@@ -251,85 +259,154 @@ __device__ __forceinline__ void umma_bf16_ss_elect(uint32_t tmem_d, uint64_t ade
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from TMEM (lane = row, one 32-bit column = two consecutive bf16 K elements), B from smem; every lane
+// executes the call with identical operands and one elected lane issues (see the GRU kernel for why)
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-__global__ void __launch_bounds__(192)
-k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
-              const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+constexpr int kBxThreads = 320;
+__global__ void __launch_bounds__(kBxThreads, 1)
+k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo,
+              const unsigned short *__restrict__ w_hi, const unsigned short *__restrict__ w_lo /* [N][K] BF16 */,
               const float *__restrict__ bias, float *__restrict__ Y, int64_t ldy, int M, int N, int K) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     BxSmem &sm = *reinterpret_cast<BxSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBxBM, n0 = blockIdx.y * kBxBN;
-    const int nkb = K / kBxBK;
+    const int n0 = blockIdx.x * kBxBN;
+    const int nkb = K / kBxBK, wcols = K / 2;             // TMEM columns of one W plane
+    const int ntiles = (M + kBxBM - 1) / kBxBM;
+    const uint32_t dcol = 2 * (kBxMaxK / 2);              // accumulators behind the two W planes
     if (threadIdx.x == 0) {
         for (int s = 0; s < kBxStages; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        mbar_init(&sm.tmem_full, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 8); }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, kBxBN);
-    if (threadIdx.x < kBxBN) sm.bias[threadIdx.x] = bias ? bias[n0 + threadIdx.x] : 0.f;
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    if (warp == 4) {
-        // ===== TMA producer
+    if (warp < 4) {
+        // ---- W slice -> TMEM: lane = output column n0 + 32 warp + lane, column j of a plane = k elements (2 j, 2 j + 1)
+        const int n = n0 + warp * 32 + lane;
+        for (int cb = 0; cb < nkb; cb++) {  // 64 k elements = 32 columns per store
+            uint32_t vh[32], vl[32];
+            const uint4 *ph = reinterpret_cast<const uint4 *>(w_hi + (int64_t)n * K + cb * 64);
+            const uint4 *pl = reinterpret_cast<const uint4 *>(w_lo + (int64_t)n * K + cb * 64);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint4 a = n < N ? __ldg(ph + i) : make_uint4(0, 0, 0, 0), c = n < N ? __ldg(pl + i) : make_uint4(0, 0, 0, 0);
+                vh[4 * i] = a.x; vh[4 * i + 1] = a.y; vh[4 * i + 2] = a.z; vh[4 * i + 3] = a.w;
+                vl[4 * i] = c.x; vl[4 * i + 1] = c.y; vl[4 * i + 2] = c.z; vl[4 * i + 3] = c.w;
+            }
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + cb * 32;
+            tmem_st32(ta, vh);
+            tmem_st32(ta + wcols, vl);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 8) {
+        // ===== TMA producer: X tiles of this CTA's row groups
         if (lane == 0) {
-            tma_prefetch_desc(&tmAhi); tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % kBxStages, it = kb / kBxStages;
-                if (it > 0) mbar_wait(&sm.empty[s], (it - 1) & 1);
-                mbar_expect_tx(&sm.full[s], 2 * (kBxBM + kBxBN) * 128);
-                tma_load_2d(sm.a[s][0], &tmAhi, kb * kBxBK, m0, &sm.full[s]);
-                tma_load_2d(sm.a[s][1], &tmAlo, kb * kBxBK, m0, &sm.full[s]);
-                tma_load_2d(sm.b[s][0], &tmBhi, kb * kBxBK, n0, &sm.full[s]);
-                tma_load_2d(sm.b[s][1], &tmBlo, kb * kBxBK, n0, &sm.full[s]);
-            }
+            tma_prefetch_desc(&tmXhi); tma_prefetch_desc(&tmXlo);
+            int it = 0;
+            for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y)
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % kBxStages, n = it / kBxStages;
+                    if (n > 0) mbar_wait(&sm.empty[s], (n - 1) & 1);
+                    mbar_expect_tx(&sm.full[s], 2 * kBxBM * 128);
+                    tma_load_2d(sm.x[s][0], &tmXhi, kb * kBxBK, tile * kBxBM, &sm.full[s]);
+                    tma_load_2d(sm.x[s][1], &tmXlo, kb * kBxBK, tile * kBxBM, &sm.full[s]);
+                }
         }
-    } else if (warp == 5) {
-        // ===== MMA issuer (whole warp, elected lane issues)
-        constexpr uint32_t idesc = umma_idesc_bf16(kBxBM, kBxBN);
+    } else if (warp == 9) {
+        // ===== MMA issuer (whole warp, elected lane issues): D[n][m] += W[n][k] . X[m][k]
+        constexpr uint32_t idesc = umma_idesc_bf16(kBxBN, kBxBM);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % kBxStages, it = kb / kBxStages;
-            mbar_wait(&sm.full[s], it & 1);
+        int it = 0, li = 0;
+        for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y, li++) {
+            const int buf = li & 1;
+            if (li >= 2) mbar_wait(&sm.tmem_empty[buf], ((li >> 1) - 1) & 1);
             tc_fence_after();
-            const uint64_t ah = umma_desc_sw128(smem_u32(sm.a[s][0])), al = umma_desc_sw128(smem_u32(sm.a[s][1]));
-            const uint64_t bh = umma_desc_sw128(smem_u32(sm.b[s][0])), bl = umma_desc_sw128(smem_u32(sm.b[s][1]));
+            const uint32_t d = tmem_u + dcol + buf * kBxBM;
+            for (int kb = 0; kb < nkb; kb++, it++) {
+                const int s = it % kBxStages, n = it / kBxStages;
+                mbar_wait(&sm.full[s], n & 1);
+                tc_fence_after();
+                const uint64_t xh = umma_desc_sw128(smem_u32(sm.x[s][0])), xl = umma_desc_sw128(smem_u32(sm.x[s][1]));
 #pragma unroll
-            for (int k = 0; k < kBxBK / 16; k++) {  // 32 bytes per K step inside the 128-byte swizzle row
-                umma_bf16_ss_elect(tmem_u, ah + 2 * k, bh + 2 * k, idesc, (kb | k) != 0);
-                umma_bf16_ss_elect(tmem_u, al + 2 * k, bh + 2 * k, idesc, 1u);
-                umma_bf16_ss_elect(tmem_u, ah + 2 * k, bl + 2 * k, idesc, 1u);
+                for (int k = 0; k < kBxBK / 16; k++) {  // K step 16: 8 TMEM columns of W, 32 bytes inside the swizzle row of X
+                    const uint32_t wh = tmem_u + kb * 32 + k * 8;
+                    umma_bf16_ts_elect(d, wh, xh + 2 * k, idesc, (kb | k) != 0);
+                    umma_bf16_ts_elect(d, wh + wcols, xh + 2 * k, idesc, 1u);
+                    umma_bf16_ts_elect(d, wh, xl + 2 * k, idesc, 1u);
+                }
+                umma_commit_elect(&sm.empty[s]);
             }
-            umma_commit_elect(&sm.empty[s]);
+            umma_commit_elect(&sm.tmem_full[buf]);
         }
-        umma_commit_elect(&sm.tmem_full);
     } else {
-        // ===== epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) = rows m0 + 32 w + lane
-        mbar_wait(&sm.tmem_full, 0);
-        tc_fence_after();
-        const int m = m0 + warp * 32 + lane;
-        float v0[32], v1[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v0);
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32, v1);
-        if (m < M) {
-            float *dst = Y + (int64_t)m * ldy + n0;
+        // ===== epilogue: warp w owns TMEM lanes [32 (w % 4), +32) = output columns n0 + 32 (w % 4) + lane and the
+        //       accumulator columns (= rows of Y) [64 (w / 4), +64) of every tile
+        const int q = warp & 3, half = warp >> 2;
+        const int n = n0 + q * 32 + lane;
+        const float bn = (bias && n < N) ? __ldg(bias + n) : 0.f;
+        int li = 0;
+        for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y, li++) {
+            const int buf = li & 1;
+            mbar_wait(&sm.tmem_full[buf], (li >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + dcol + buf * kBxBM + half * 64;
+            const int m0 = tile * kBxBM + half * 64;
+            float v0[32], v1[32];
+            tmem_ld32(ta, v0);
+            tmem_ld32(ta + 32, v1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);  // accumulator read: hand the buffer back before the stores
+            float *dst = Y + (int64_t)m0 * ldy + n;
+            if (m0 + 64 <= M && n < N) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[j]);
-                *reinterpret_cast<float4 *>(dst + j) = make_float4(v0[j] + bv.x, v0[j + 1] + bv.y, v0[j + 2] + bv.z, v0[j + 3] + bv.w);
-            }
+                for (int j = 0; j < 32; j++) { *dst = v0[j] + bn; dst += ldy; }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[32 + j]);
-                *reinterpret_cast<float4 *>(dst + 32 + j) = make_float4(v1[j] + bv.x, v1[j + 1] + bv.y, v1[j + 2] + bv.z, v1[j + 3] + bv.w);
+                for (int j = 0; j < 32; j++) { *dst = v1[j] + bn; dst += ldy; }
+            } else if (n < N) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) { if (m0 + j < M) *dst = v0[j] + bn; dst += ldy; }
+#pragma unroll
+                for (int j = 0; j < 32; j++) { if (m0 + 32 + j < M) *dst = v1[j] + bn; dst += ldy; }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, kBxBN);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------- fused depthwise -> 1x1 (tcgen05) -> ReLU ----
@@ -353,9 +430,6 @@ constexpr uint32_t kDxW = 32768, kDxRaw = 49152, kDxTail = 64 * 4 + 32;
 // byte offset of (row r, 16-byte chunk j) inside a [rows x 128 B] sub-tile with 128-byte swizzle
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
     return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
@@ -698,32 +772,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// warp-convergent variants: every lane executes the call with identical operands and one elected lane
-// issues the instruction.  Keeping control flow uniform lets ptxas hold the operands in uniform
-// registers; issuing from inside `if (lane == 0)` made it wrap every MMA in an ELECT / R2UR /
-// BRA.U.ANY loop (~50 cycles per tcgen05.mma, measured with clock64).
-__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-        "r"(r[31])
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -1020,22 +1068,30 @@ static int make_map_bf16(CUtensorMap *map, const void *base, int64_t rows, int64
 // Y[M,N] = X . W^T + bias with X, W given as BF16 hi/lo planes (X: [M][K] pitch ldx, W: [N][K] pitch K)
 int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64_t ldx, const void *w_hi, const void *w_lo,
                        const float *bias, float *y, int64_t ldy, int64_t M, int N, int K) {
-    if (N % kBxBN || K % kBxBK || (ldx % 8) || (ldy % 4) || M <= 0)
+    if (N % kBxBN || K % kBxBK || K > kBxMaxK || (ldx % 8) || M <= 0 || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15))
         return fail(DFB_ERR_UNSUPPORTED, "bf16x3 GEMM shape M=%lld N=%d K=%d", (long long)M, N, K);
-    CUtensorMap mah, mal, mbh, mbl;
+    CUtensorMap mxh, mxl;
     int rc;
-    if ((rc = make_map_bf16(&mah, x_hi, M, K, ldx, kBxBM)) || (rc = make_map_bf16(&mal, x_lo, M, K, ldx, kBxBM)) ||
-        (rc = make_map_bf16(&mbh, w_hi, N, K, K, kBxBN)) || (rc = make_map_bf16(&mbl, w_lo, N, K, K, kBxBN)))
-        return rc;
-    static bool attr_done = false;
+    if ((rc = make_map_bf16(&mxh, x_hi, M, K, ldx, kBxBM)) || (rc = make_map_bf16(&mxl, x_lo, M, K, ldx, kBxBM))) return rc;
+    static int num_sms = 0;
     const int smem = (int)sizeof(BxSmem) + 1024;
-    if (!attr_done) {
+    if (!num_sms) {
         DFB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
+        int dev = 0;
+        DFB_CUDA(cudaGetDevice(&dev));
+        DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    dim3 grid((unsigned)((M + kBxBM - 1) / kBxBM), (unsigned)(N / kBxBN));
+    // persistent: one CTA per SM; blockIdx.x = column slice (fastest, so the CTAs that stream the same X tiles are
+    // co-scheduled and share them through L2), blockIdx.y = row group
+    const int nslices = N / kBxBN;
+    const int ntiles = (int)((M + kBxBM - 1) / kBxBM);
+    int groups = num_sms / nslices;
+    if (groups < 1) groups = 1;
+    if (groups > ntiles) groups = ntiles;
+    dim3 grid((unsigned)nslices, (unsigned)groups);
     DFB_PROF("k_gemm_bf16x3[gru_proj]", s);
-    k_gemm_bf16x3<<<grid, 192, smem, s>>>(mah, mal, mbh, mbl, bias, y, ldy, (int)M, N, K);
+    k_gemm_bf16x3<<<grid, kBxThreads, smem, s>>>(mxh, mxl, reinterpret_cast<const unsigned short *>(w_hi),
+                                          reinterpret_cast<const unsigned short *>(w_lo), bias, y, ldy, (int)M, N, K);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }
