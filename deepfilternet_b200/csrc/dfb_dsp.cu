@@ -267,10 +267,17 @@ __global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
         float s;
         if (erb_state) s = erb_state[(int64_t)b * E + j];
         else s = (E == 1) ? -60.f : __fadd_rn(-60.f, __fmul_rn((float)j, __fdiv_rn(-30.f, (float)(E - 1))));
+        // software pipelined: the loads of batch n + 1 are in flight while batch n runs its (sequential) EMA
+        float vn[kPf];
+#pragma unroll
+        for (int u = 0; u < kPf; u++) vn[u] = (u < Tf) ? src[(int64_t)u * erb_stride_t] : 0.f;
         for (int t = 0; t < Tf; t += kPf) {
             float v[kPf];
 #pragma unroll
-            for (int u = 0; u < kPf; u++) v[u] = (t + u < Tf) ? src[(int64_t)(t + u) * erb_stride_t] : 0.f;
+            for (int u = 0; u < kPf; u++) {
+                v[u] = vn[u];
+                vn[u] = (t + kPf + u < Tf) ? src[(int64_t)(t + kPf + u) * erb_stride_t] : 0.f;
+            }
 #pragma unroll
             for (int u = 0; u < kPf; u++) {
                 if (t + u < Tf) {
@@ -286,17 +293,29 @@ __global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
         float s;
         if (unit_state) s = unit_state[(int64_t)b * Fd + k];
         else s = (Fd == 1) ? 0.001f : __fadd_rn(0.001f, __fmul_rn((float)k, __fdiv_rn(__fsub_rn(0.0001f, 0.001f), (float)(Fd - 1))));
+        float2 vn[kPf];
+#pragma unroll
+        for (int u = 0; u < kPf; u++) vn[u] = (u < Tf) ? src[(int64_t)u * spec_stride_t] : make_float2(0.f, 0.f);
         for (int t = 0; t < Tf; t += kPf) {
             float2 v[kPf];
+            float nrm[kPf], sv[kPf];
 #pragma unroll
-            for (int u = 0; u < kPf; u++)
-                v[u] = (t + u < Tf) ? src[(int64_t)(t + u) * spec_stride_t] : make_float2(0.f, 0.f);
+            for (int u = 0; u < kPf; u++) {
+                v[u] = vn[u];
+                vn[u] = (t + kPf + u < Tf) ? src[(int64_t)(t + kPf + u) * spec_stride_t] : make_float2(0.f, 0.f);
+            }
+            // the magnitudes and the normalisation are independent across frames; only the two-op EMA chain is serial
+#pragma unroll
+            for (int u = 0; u < kPf; u++) nrm[u] = hypotf(v[u].x, v[u].y);
+#pragma unroll
+            for (int u = 0; u < kPf; u++) {
+                if (t + u < Tf) s = __fadd_rn(__fmul_rn(nrm[u], one_m_alpha), __fmul_rn(s, alpha));
+                sv[u] = s;
+            }
 #pragma unroll
             for (int u = 0; u < kPf; u++) {
                 if (t + u < Tf) {
-                    float nrm = hypotf(v[u].x, v[u].y);
-                    s = __fadd_rn(__fmul_rn(nrm, one_m_alpha), __fmul_rn(s, alpha));
-                    float d = __fsqrt_rn(s);
+                    float d = __fsqrt_rn(sv[u]);
                     dst[(int64_t)(t + u) * Fd] = make_float2(__fdiv_rn(v[u].x, d), __fdiv_rn(v[u].y, d));
                 }
             }

@@ -38,6 +38,12 @@ struct DwPwParams {
     int64_t in_fs, path_fs, out_fs;  // frame strides (floats)
     int T, Fin, Fout, kt, NF, lookahead;
     int fo_magic;         // ceil(65536 / Fout): r / Fout == (r * fo_magic) >> 16 for r < 128 (tensor-core kernel)
+    // fused ERB mask head (tensor-core kernel, last decoder block, kt = 1): m = sigmoid(conv0_out(conv0p(e0) + out))
+    const float *mk_e0;   // [B,T,Fout,64] or null
+    const float *mk_ps, *mk_pb;  // conv0p affine [64]
+    const float *mk_w;    // conv0_out taps [3][64]
+    const float *mk_bias; // [1]
+    float *mk_out;        // m [B,T,Fout]
 };
 
 

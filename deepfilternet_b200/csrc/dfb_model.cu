@@ -214,30 +214,48 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    // loader roles are fixed per thread (no per-element division): A tile -- row ar + 32 i of group ags, k quad akq;
+    // W tile -- column quad wn (group wgs, in-group offset wnn), rows wk + 16 i
+    const int akq = (tid & 7) * 4, ar = tid >> 3;
+    const int wn = (tid & 15) * 4, wk = tid >> 4;
+    int wgs = 0, wnn = n0 + wn;
+    if (gpc > 1) { wgs = wn / p.Hg; wnn = wn - wgs * p.Hg; }
+    const bool wvec = (p.Hg & 3) == 0;                       // a column quad never straddles a group and is 16-byte aligned
+    const bool wok = gpc > 1 ? wgs < ngrp : wn < wcols;
+    const float *xrow[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int64_t m = m0 + ar + 32 * i;
+        xrow[i] = m < p.M ? p.x + m * p.ldx + (int64_t)g0 * p.Ig + akq : nullptr;
+    }
+    const float *wbase = p.w + ((int64_t)(g0 + wgs) * p.Ig) * p.Hg + wnn;
     for (int k0 = 0; k0 < p.Ig; k0 += kGlBK) {
         const int kc = min(kGlBK, p.Ig - k0);
         // A tiles: per group 64 rows x 32 k  (8 threads x float4 per row)
-        for (int i = tid; i < ngrp * kGlBM * (kGlBK / 4); i += 256) {
-            const int gs = i / (kGlBM * (kGlBK / 4)), rem = i - gs * (kGlBM * (kGlBK / 4));
-            const int r = rem >> 3, kq = (rem & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int64_t m = m0 + r;
-            if (m < p.M && kq < kc) v = *reinterpret_cast<const float4 *>(p.x + m * p.ldx + (int64_t)(g0 + gs) * p.Ig + k0 + kq);
-            *reinterpret_cast<float4 *>(&As[gs][r][kq]) = v;
+        for (int gs = 0; gs < ngrp; gs++) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (xrow[i] && akq < kc) v = *reinterpret_cast<const float4 *>(xrow[i] + gs * p.Ig + k0);
+                *reinterpret_cast<float4 *>(&As[gs][ar + 32 * i][akq]) = v;
+            }
         }
         // W tile: 32 k x 64 columns (column n -> group n / Hg when several groups share the CTA)
-        for (int i = tid; i < kGlBK * kGlBN; i += 256) {
-            const int k = i >> 6, n = i & 63;
-            float v = 0.f;
-            if (k < kc) {
-                if (gpc > 1) {
-                    const int gs = n / p.Hg, nn = n - gs * p.Hg;
-                    if (gs < ngrp) v = p.w[((int64_t)(g0 + gs) * p.Ig + k0 + k) * p.Hg + nn];
-                } else if (n < wcols) {
-                    v = p.w[((int64_t)g0 * p.Ig + k0 + k) * p.Hg + n0 + n];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int k = wk + 16 * i;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < kc && wok) {
+                const float *src = wbase + (int64_t)(k0 + k) * p.Hg;
+                if (wvec) {
+                    if (gpc > 1 || wn + 3 < wcols) v = *reinterpret_cast<const float4 *>(src);
+                    else { v.x = src[0]; if (wn + 1 < wcols) v.y = src[1]; if (wn + 2 < wcols) v.z = src[2]; }
+                } else {
+                    const int lim = gpc > 1 ? p.Hg - wnn : wcols - wn;
+                    v.x = src[0]; if (lim > 1) v.y = src[1]; if (lim > 2) v.z = src[2]; if (lim > 3) v.w = src[3];
                 }
             }
-            Ws[k][n] = v;
+            *reinterpret_cast<float4 *>(&Ws[k][wn]) = v;
         }
         __syncthreads();
 #pragma unroll
@@ -836,6 +854,7 @@ int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const fl
            float ooffset = 0.f, unsigned short *y_hi = nullptr, unsigned short *y_lo = nullptr) {
     GlParams p{x, ldx, w, bias, res, ldr, y, ldy, M, G, I / G, Hh / G, act, oscale, ooffset, y_hi, y_lo};
     if ((p.Ig % 4) || (ldx % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: K not a multiple of 4");
+    if (G > 1 && (p.Hg % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: group width %d not a multiple of 4", p.Hg);
     int tiles = (p.Hg + kGlBN - 1) / kGlBN;
     int gpc = (p.Hg < kGlBN && kGlBN % p.Hg == 0) ? (kGlBN / p.Hg < G ? kGlBN / p.Hg : G) : 1;
     dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(((G + gpc - 1) / gpc) * tiles));
@@ -1204,12 +1223,24 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if ((rc = blk("erb_dec.convt3", p)) || (rc = path(p, "erb_dec.conv3p", f.e3, e3_fs)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_sw))) return rc;
         p = mk(f.d3, E / 4, ED, f.d2, E / 2, (int64_t)E / 2 * kCh, 1);
         if ((rc = blk("erb_dec.convt2", p)) || (rc = path(p, "erb_dec.conv2p", f.e2, (int64_t)E / 4 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B, pw_sw))) return rc;
-        p = mk(f.d2, E / 2, (int64_t)E / 2 * kCh, f.d1, E, (int64_t)E * kCh, 1);
-        if ((rc = blk("erb_dec.convt1", p)) || (rc = path(p, "erb_dec.conv1p", f.e1, (int64_t)E / 2 * kCh)) || (rc = run_dwpw<DW_T2>(s, p, B, pw_sw))) return rc;
         const float *ps, *pb, *w, *bb;
         if ((rc = need(m, "erb_dec.conv0p.s", kCh, &ps)) || (rc = need(m, "erb_dec.conv0p.b", kCh, &pb)) ||
             (rc = need(m, "erb_dec.conv0_out.w", c.conv_kt * 3 * kCh, &w)) || (rc = need(m, "erb_dec.conv0_out.b", 1, &bb)))
             return rc;
+        p = mk(f.d2, E / 2, (int64_t)E / 2 * kCh, f.d1, E, (int64_t)E * kCh, 1);
+        if ((rc = blk("erb_dec.convt1", p)) || (rc = path(p, "erb_dec.conv1p", f.e1, (int64_t)E / 2 * kCh))) return rc;
+        // kt = 1 models on the tensor-core path: the mask head is evaluated in convt1's epilogue and d1 never leaves the SM
+        const bool fused_mask = pw_sw && c.conv_kt == 1 && 128 % E == 0;
+        if (fused_mask) {
+            p.mk_e0 = f.e0; p.mk_ps = ps; p.mk_pb = pb; p.mk_w = w; p.mk_bias = bb; p.mk_out = d_m;
+            p.out = nullptr;
+            m->dbg.erase("d1");
+        }
+        if ((rc = run_dwpw<DW_T2>(s, p, B, pw_sw))) return rc;
+        if (fused_mask) {
+            DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));  // join
+            return DFB_OK;
+        }
         static bool attr_done = false;
         int smem = (kMaskWarps * 2 * (E + 2) * kMaskLd + c.conv_kt * 3 * kCh) * 4;
         if (!attr_done) {  // sized for the largest supported configuration (nb_erb 64, kt 2)

@@ -491,7 +491,11 @@ __device__ __forceinline__ float4 f4_fma(float4 x, float4 w, float4 a) {
     return make_float4(fmaf(x.x, w.x, a.x), fmaf(x.y, w.y, a.y), fmaf(x.z, w.z, a.z), fmaf(x.w, w.w, a.w));
 }
 
-template <int MODE, int KT, int PATH>
+// MASK = 1 (last ERB decoder block of the kt = 1 models): the tile holds whole frames, so the mask head
+//   m[t,f] = sigmoid(sum_{df,c} w[df][c] * (relu(e0 * ps + pb) + out)[t][f+df-1][c] + bias)
+// (conv0_out(conv0p(e0) + convt1(...)), deepfilternet3.py:253) is evaluated right on the staged fp32 tile and
+// `out` itself never goes to HBM (p.out may be null).
+template <int MODE, int KT, int PATH, int MASK>
 __global__ void __launch_bounds__(kDxThreads, 2)
 k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 k] BF16, 128B-swizzled rows */) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
@@ -504,14 +508,20 @@ k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 
     const int tq0 = t0 - (KT - 1);
     const uint32_t fbytes = (uint32_t)p.Fin * kCh * 4;
     const uint32_t raw_in = sb + kDxRaw, raw_path = raw_in + (uint32_t)(p.NF + KT - 1) * fbytes;
-    const uint32_t tail = raw_in + (uint32_t)(p.NF + KT - 1) * fbytes * (PATH ? 2u : 1u);
+    const uint32_t raw_e0 = raw_in + (uint32_t)(p.NF + KT - 1) * fbytes * (PATH ? 2u : 1u);  // MASK: [NF][Fout][64]
+    const uint32_t obytes = (uint32_t)p.Fout * kCh * 4;
+    const uint32_t tail = raw_e0 + (MASK ? (uint32_t)p.NF * obytes : 0u);
     const uint32_t s_bias = tail, bar_mma = tail + 256, bar_raw = tail + 264, s_tmem = tail + 272;
+    const uint32_t s_mask = raw_in;  // MASK: ps | pb | w[3][64], written over the raw input frames once they are converted
     if (tid == 0) {
         mbar_init_a(bar_mma, 1);
         mbar_init_a(bar_raw, 1);
         fence_barrier_init();
         const int ta = max(tq0, 0), tb = t0 + nf;  // frames [ta, tb)
-        mbar_expect_tx_a(bar_raw, (uint32_t)(tb - ta) * fbytes * (PATH ? 2u : 1u) + 2u * kCh * 128u);
+        mbar_expect_tx_a(bar_raw, (uint32_t)(tb - ta) * fbytes * (PATH ? 2u : 1u) + 2u * kCh * 128u + (MASK ? (uint32_t)nf * obytes : 0u));
+        if (MASK)
+            for (int t = t0; t < tb; t++)
+                bulk_load(raw_e0 + (uint32_t)(t - t0) * obytes, p.mk_e0 + ((int64_t)b * p.T + t) * p.Fout * kCh, obytes, bar_raw);
         for (int t = ta; t < tb; t++) {
             bulk_load(raw_in + (uint32_t)(t - tq0) * fbytes, p.in + ((int64_t)b * p.T + t) * p.in_fs, fbytes, bar_raw);
             if (PATH) bulk_load(raw_path + (uint32_t)(t - tq0) * fbytes, p.path + ((int64_t)b * p.T + t) * p.path_fs, fbytes, bar_raw);
@@ -593,6 +603,13 @@ k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = lds32(s_tmem);
+    if (MASK && tid >= 64 && tid < 64 + 80) {  // ps | pb | w[3][64] as 80 float4
+        const int i = tid - 64;
+        const float4 *src = i < 16 ? reinterpret_cast<const float4 *>(p.mk_ps) + i
+                          : i < 32 ? reinterpret_cast<const float4 *>(p.mk_pb) + (i - 16)
+                                   : reinterpret_cast<const float4 *>(p.mk_w) + (i - 32);
+        sts128(s_mask + i * 16, __ldg(src));
+    }
     if (warp == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, kCh);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -632,8 +649,51 @@ k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, kCh);
+    if (MASK) {
+        // thread = (channel quad j, 8 consecutive rows of one frame): X = relu(e0 * ps + pb) + out is formed once per
+        // (row, quad), each row feeds the three taps of its neighbours, and the 16 quads are reduced with shuffles
+        const int j = tid & 15, r0 = 8 * slot;
+        const int fr = (r0 * p.fo_magic) >> 16, f0 = r0 - fr * p.Fout;   // Fout % 8 == 0: the 8 rows share a frame
+        const float4 s4 = lds128(s_mask + j * 16), b4 = lds128(s_mask + 256 + j * 16);
+        const float4 w0 = lds128(s_mask + 512 + j * 16), w1 = lds128(s_mask + 512 + 256 + j * 16), w2 = lds128(s_mask + 512 + 512 + j * 16);
+        float part[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) part[i] = 0.f;
+        if (r0 < R) {
+#pragma unroll
+            for (int i = -1; i <= 8; i++) {
+                const int f2 = f0 + i, r2 = r0 + i;
+                if (f2 < 0 || f2 >= p.Fout) continue;
+                const float4 d = lds128(sb + r2 * 256 + ((j ^ (r2 & 15)) << 4));
+                const float4 e = lds128(raw_e0 + r2 * 256 + j * 16);
+                float4 x;
+                x.x = fmaxf(fmaf(e.x, s4.x, b4.x), 0.f) + d.x; x.y = fmaxf(fmaf(e.y, s4.y, b4.y), 0.f) + d.y;
+                x.z = fmaxf(fmaf(e.z, s4.z, b4.z), 0.f) + d.z; x.w = fmaxf(fmaf(e.w, s4.w, b4.w), 0.f) + d.w;
+                // row r2 is tap df = 0 of output r2 + 1, tap 1 of r2, tap 2 of r2 - 1
+                if (i + 1 < 8) part[i + 1 < 0 ? 0 : i + 1] += x.x * w0.x + x.y * w0.y + x.z * w0.z + x.w * w0.w;
+                if (i >= 0 && i < 8) part[i < 0 ? 0 : (i > 7 ? 7 : i)] += x.x * w1.x + x.y * w1.y + x.z * w1.z + x.w * w1.w;
+                if (i - 1 >= 0) part[i - 1 > 7 ? 7 : i - 1] += x.x * w2.x + x.y * w2.y + x.z * w2.z + x.w * w2.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float v = part[i];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            part[i] = v;
+        }
+        if (r0 < R && j < 8) {
+            float z = part[0];
+#pragma unroll
+            for (int i = 1; i < 8; i++) z = j == i ? part[i] : z;
+            z += __ldg(p.mk_bias);
+            p.mk_out[((int64_t)b * p.T + t0 + fr) * p.Fout + f0 + j] = 1.f / (1.f + expf(-z));
+        }
+    }
     // ---- coalesced write-out: half a warp per 256-byte row, 8 consecutive rows per thread
-    {
+    if (!MASK || p.out) {
         const int j = tid & 15;
         int fr2 = (8 * slot * p.fo_magic) >> 16, fo2 = 8 * slot - fr2 * p.Fout;
         float *dst = p.out + ((int64_t)b * p.T + t0 + fr2) * p.out_fs + fo2 * kCh + j * 4;
@@ -647,19 +707,19 @@ k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 
     }
 }
 
-template <int MODE, int KT, int PATH>
+template <int MODE, int KT, int PATH, int MASK = 0>
 static int launch_dwpw_bx(cudaStream_t s, const DwPwParams &p, const float *w_sw, int B) {
     static int attr_smem = 0;
-    const int raw = (p.NF + KT - 1) * p.Fin * kCh * 4 * (PATH ? 2 : 1);
+    const int raw = (p.NF + KT - 1) * p.Fin * kCh * 4 * (PATH ? 2 : 1) + (MASK ? p.NF * p.Fout * kCh * 4 : 0);
     const int smem = (int)kDxRaw + raw + (int)kDxTail;
     if (smem > 227 * 1024) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile needs %d bytes of shared memory", smem);
     if (smem > attr_smem) {
-        DFB_CUDA(cudaFuncSetAttribute(k_dwpw_bx<MODE, KT, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DFB_CUDA(cudaFuncSetAttribute(k_dwpw_bx<MODE, KT, PATH, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
     dim3 grid((unsigned)((p.T + p.NF - 1) / p.NF), (unsigned)B);
     DFB_PROF("k_dwpw_bx", s);
-    k_dwpw_bx<MODE, KT, PATH><<<grid, kDxThreads, smem, s>>>(p, w_sw);
+    k_dwpw_bx<MODE, KT, PATH, MASK><<<grid, kDxThreads, smem, s>>>(p, w_sw);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }
@@ -681,6 +741,9 @@ int launch_dwpw_tc(cudaStream_t s, DwPwParams p, const float *w_sw, int B) {
         if (p.kt == 1) return launch_dwpw_bx<DW_S2, 1, 0>(s, p, w_sw, B);
         if (p.kt == 2) return launch_dwpw_bx<DW_S2, 2, 0>(s, p, w_sw, B);
     } else if (MODE == DW_T2 && path && p.kt == 1) {
+        if (p.mk_e0) {
+            return launch_dwpw_bx<DW_T2, 1, 1, 1>(s, p, w_sw, B);
+        }
         return launch_dwpw_bx<DW_T2, 1, 1>(s, p, w_sw, B);
     }
     return fail(DFB_ERR_UNSUPPORTED, "dwpw tensor-core path: mode %d kt %d path %d", MODE, p.kt, (int)path);
