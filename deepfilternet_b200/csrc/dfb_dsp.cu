@@ -608,9 +608,16 @@ extern "C" int64_t dfb_profile_report(char *buf, int64_t buflen) {
     std::vector<std::string> names;
     std::vector<double> ms;
     std::vector<int64_t> cnt;
+    // DFB_PROF_TIMELINE=1: start / end of every launch relative to the first one, to stderr (critical-path analysis)
+    static const bool timeline = getenv("DFB_PROF_TIMELINE") && atoi(getenv("DFB_PROF_TIMELINE"));
     for (auto &r : g_prof) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) t = 0.f;
+        if (timeline) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, g_prof.front().a, r.a);
+            fprintf(stderr, "[timeline] %-34s %9.3f %9.3f\n", r.name.c_str(), t0, t0 + t);
+        }
         size_t i = 0;
         for (; i < names.size(); i++) if (names[i] == r.name) break;
         if (i == names.size()) { names.push_back(r.name); ms.push_back(0); cnt.push_back(0); }

@@ -723,7 +723,11 @@ struct dfb_model {
     Arena arena;
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;             // DF decoder branch runs here, concurrently with the ERB decoder
+    // forward() hops from the caller's stream onto `hi` (and `aux`), both at the greatest stream priority; `low`
+    // (least priority) carries work that is off the critical path and only fills SMs the recurrences leave idle
+    cudaStream_t hi = nullptr, low = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork_enc = nullptr, ev_join_enc = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_c0 = nullptr, ev_convp = nullptr, ev_skip = nullptr;
     const float *get(const std::string &n) const {
         auto it = t.find(n);
         return it == t.end() ? nullptr : it->second.first;
@@ -779,8 +783,17 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
         m->t[tt.name] = {dst, tt.numel};
         off += ((size_t)tt.numel * 4 + 255) & ~size_t(255);
     }
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&m->aux, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&m->hi, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&m->low, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_c0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_convp, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_skip, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_fork_enc, cudaEventDisableTiming) != cudaSuccess ||
@@ -799,6 +812,10 @@ extern "C" void dfb_model_free(dfb_model *m) {
     if (m->slab) cudaFree(m->slab);
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->aux) cudaStreamDestroy(m->aux);
+    if (m->hi) cudaStreamDestroy(m->hi);
+    if (m->low) cudaStreamDestroy(m->low);
+    for (cudaEvent_t e : {m->ev_in, m->ev_out, m->ev_c0, m->ev_convp, m->ev_skip})
+        if (e) cudaEventDestroy(e);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->ev_fork_enc) cudaEventDestroy(m->ev_fork_enc);
@@ -908,7 +925,7 @@ int pick_bc(int B, int max_clusters) {
 int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, const float *x, int in_dim,
             const float *res_last, float *y, float *xproj, float *tmp_h, int B, int T,
             unsigned short *x_hi = nullptr, unsigned short *x_lo = nullptr, unsigned short *pl_hi = nullptr,
-            unsigned short *pl_lo = nullptr) {
+            unsigned short *pl_lo = nullptr, int wide = 0) {
     const int64_t M = (int64_t)B * T;
     const float *cur_in = x;
     int cur_dim = in_dim;
@@ -941,7 +958,7 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         if (H == 256 && m->gru_tc) {
             const bool planes = tc_proj && l < layers - 1;
             rc = launch_gru_tc(s, xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, planes ? pl_hi : nullptr,
-                               planes ? pl_lo : nullptr, B, T, m->gru_dbg);
+                               planes ? pl_lo : nullptr, B, T, m->gru_dbg, wide);
             cur_hi = pl_hi; cur_lo = pl_lo;
         } else if (H == 256) {
             p.Bc = pick_bc(B, 148 / 4);
@@ -992,7 +1009,7 @@ struct FwdBufs {
     float *e0, *e1, *e2, *e3, *c0, *c1, *emb_in, *emb, *g_a, *g_b, *g_h, *xproj, *dec_emb, *d3, *d2, *d1, *dfc;
     unsigned short *ga_hi, *ga_lo, *gh_hi, *gh_lo;  // BF16 planes of g_a / inter-layer h (tensor-core projections)
     // second set of GRU scratch: the DF decoder runs concurrently with the ERB decoder on another stream
-    float *g_a2, *g_h2, *xproj2;
+    float *g_a2, *g_h2, *xproj2, *dfskip;
     unsigned short *ga2_hi, *ga2_lo, *gh2_hi, *gh2_lo;
 };
 
@@ -1020,7 +1037,7 @@ static size_t fwd_plan(const dfb_model_config &c, size_t M, Arena *a, FwdBufs *f
     t.d1 = take(M * E * kCh); t.dfc = take(M * Hmax);
     t.ga_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.ga_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
     t.gh_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.gh_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
-    t.g_a2 = take(M * Hmax); t.g_h2 = take(M * Hmax); t.xproj2 = take(M * 3 * Hmax);
+    t.g_a2 = take(M * Hmax); t.g_h2 = take(M * Hmax); t.xproj2 = take(M * 3 * Hmax); t.dfskip = take(M * Hmax);
     t.ga2_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.ga2_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
     t.gh2_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.gh2_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
     if (f) *f = t;
@@ -1047,8 +1064,24 @@ extern "C" int dfb_model_forward(dfb_model *m, const float *d_feat_erb, const fl
 }
 
 static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
-                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s) {
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in) {
     const dfb_model_config &c = m->cfg;
+    // DFB_SERIAL=1: everything on the caller's stream (profiling: per-kernel times without overlap)
+    static const bool serial = getenv("DFB_SERIAL") && atoi(getenv("DFB_SERIAL"));
+    cudaStream_t s = serial ? s_in : m->hi;
+    cudaStream_t sl = serial ? s_in : m->low;
+    if (!serial) {
+        DFB_CUDA(cudaEventRecord(m->ev_in, s_in));
+        DFB_CUDA(cudaStreamWaitEvent(s, m->ev_in, 0));
+    }
+    auto finish = [&]() -> int {  // join the branches and hand the result back to the caller's stream
+        DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
+        if (!serial) {
+            DFB_CUDA(cudaEventRecord(m->ev_out, s));
+            DFB_CUDA(cudaStreamWaitEvent(s_in, m->ev_out, 0));
+        }
+        return DFB_OK;
+    };
     const int64_t M = (int64_t)B * T;
     const int E = c.nb_erb, Fd = c.nb_df, H = c.emb_hidden, Hd = c.df_hidden;
     const int ED = E / 4 * kCh;  // embedding width (512)
@@ -1057,7 +1090,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     int rc;
     FwdBufs f{};
     fwd_plan(c, (size_t)M, &arena, &f);
-    if (!f.gh2_lo) return fail(DFB_ERR_OOM, "forward workspace exhausted for %lld frames", (long long)M);
+    if (!f.gh2_lo || !f.dfskip) return fail(DFB_ERR_OOM, "forward workspace exhausted for %lld frames", (long long)M);
     m->dbg.clear();
     m->dbg["e0"] = {f.e0, M * E * kCh}; m->dbg["e1"] = {f.e1, M * (E / 2) * kCh}; m->dbg["e2"] = {f.e2, M * (E / 4) * kCh};
     m->dbg["e3"] = {f.e3, c.enc_concat ? M * emb_in_dim : M * ED}; m->dbg["c0"] = {f.c0, M * Fd * kCh};
@@ -1089,8 +1122,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if (m->conv_tc && (r = need(m, (n + ".pw_sw").c_str(), kCh * kCh, &pw_sw))) return r;
         return DFB_OK;
     };
-    // the DF-branch input convs run concurrently with the ERB-branch convs (DFB_SERIAL=1: one stream, for profiling)
-    static const bool serial = getenv("DFB_SERIAL") && atoi(getenv("DFB_SERIAL"));
+    // the DF-branch input convs run concurrently with the ERB-branch convs
     cudaStream_t sa = serial ? s : m->aux;
     DFB_CUDA(cudaEventRecord(m->ev_fork_enc, s));
     DFB_CUDA(cudaStreamWaitEvent(sa, m->ev_fork_enc, 0));
@@ -1110,12 +1142,15 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             DFB_PROF("k_conv_in[df_conv0]", sa);
             k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead);
             DFB_LAUNCH_CHECK();
+            DFB_CUDA(cudaEventRecord(m->ev_c0, sa));
         }
         p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
         if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(sa, p, B, pw_sw))) return rc;
         DFB_CUDA(cudaEventRecord(m->ev_join_enc, sa));
-        // DF pathway conv (needs c0 only): queued behind df_conv1 on the auxiliary stream so that it fills the SMs
-        // the encoder GRU clusters leave idle instead of lengthening the decoder tail
+        // DF pathway conv (needs c0 only; its result is consumed by the very last DF-decoder kernel): on the
+        // low-priority stream, so its CTAs only take SMs that the critical path -- the encoder convs now, the GRU
+        // clusters later -- leaves idle (timeline: on the auxiliary stream it delayed df_fc_emb by 1.8 ms)
+        DFB_CUDA(cudaStreamWaitEvent(sl, m->ev_c0, 0));
         const int O2 = 2 * c.df_order;
         const float *w1, *w2, *bb;
         if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
@@ -1125,11 +1160,14 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             return fail(DFB_ERR_UNSUPPORTED, "df_order %d / df_pathway_kernel_size_t %d (built kernels: 5, 5)", c.df_order,
                         c.df_pathway_kt);
         dim3 grid((unsigned)((Fd + 2 * kCpWarps - 1) / (2 * kCpWarps)), (unsigned)((T + kCpChunk - 1) / kCpChunk), (unsigned)B);
-        DFB_PROF("k_df_convp", sa);
-        static const int minb = getenv("DFB_CONVP_MINB") ? atoi(getenv("DFB_CONVP_MINB")) : 2;
-        if (minb == 2) k_df_convp<5, 5, 2><<<grid, 32 * kCpWarps, 0, sa>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
-        else k_df_convp<5, 5, 3><<<grid, 32 * kCpWarps, 0, sa>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
-        DFB_LAUNCH_CHECK();
+        {
+            DFB_PROF("k_df_convp", sl);
+            static const int minb = getenv("DFB_CONVP_MINB") ? atoi(getenv("DFB_CONVP_MINB")) : 2;
+            if (minb == 2) k_df_convp<5, 5, 2><<<grid, 32 * kCpWarps, 0, sl>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
+            else k_df_convp<5, 5, 3><<<grid, 32 * kCpWarps, 0, sl>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
+            DFB_LAUNCH_CHECK();
+        }
+        DFB_CUDA(cudaEventRecord(m->ev_convp, sl));
     }
     {
         DwPwParams p = mk(f.e0, E, (int64_t)E * kCh, f.e1, E / 2, (int64_t)E / 2 * kCh, c.conv_kt);
@@ -1174,6 +1212,16 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     // fork: the two decoders only share read-only encoder outputs
     DFB_CUDA(cudaEventRecord(m->ev_fork, s));
     DFB_CUDA(cudaStreamWaitEvent(sa, m->ev_fork, 0));
+    // DFN3's grouped-linear skip around the DF GRU does not depend on the recurrence: evaluate it here (the ERB
+    // branch has the slack) and let the last GRU layer add it as its output residual, instead of a kernel on the
+    // DF branch's tail, which is the critical path of the decoder phase
+    const bool early_skip = c.g_df_skip && c.model_kind != 2;
+    if (early_skip) {
+        const float *w_skip;
+        if ((rc = need(m, "df_dec.df_skip.gl", (int64_t)emb_dim * Hd / c.g_df_skip, &w_skip))) return rc;
+        if ((rc = run_gl(s, f.emb, emb_dim, w_skip, nullptr, nullptr, 0, f.dfskip, Hd, M, c.g_df_skip, emb_dim, Hd, ACT_NONE))) return rc;
+        DFB_CUDA(cudaEventRecord(m->ev_skip, s));
+    }
     // ---- DF decoder (deepfilternet3.py:323-331), on the auxiliary stream (forked after the encoder)
     {
         cudaStream_t s = sa;  // shadows the caller stream inside this block
@@ -1181,10 +1229,11 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if ((rc = need(m, "df_dec.df_gru.in.gl", (int64_t)emb_dim * Hd / c.g_df_in, &w_in))) return rc;
         if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a2, Hd, M, c.g_df_in, emb_dim, Hd, ACT_RELU, 1.f, 0.f,
                          f.ga2_hi, f.ga2_lo))) return rc;
-        const float *res = c.model_kind == 2 ? f.g_a2 : nullptr;
+        const float *res = c.model_kind == 2 ? f.g_a2 : (early_skip ? f.dfskip : nullptr);
+        if (early_skip) DFB_CUDA(cudaStreamWaitEvent(s, m->ev_skip, 0));
         if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a2, Hd, res, f.dfc, f.xproj2, f.g_h2, B, T, f.ga2_hi, f.ga2_lo,
-                          f.gh2_hi, f.gh2_lo))) return rc;
-        if (c.g_df_skip) {
+                          f.gh2_hi, f.gh2_lo, 1))) return rc;
+        if (c.g_df_skip && !early_skip) {
             const float *w_skip;
             if ((rc = need(m, "df_dec.df_skip.gl", (int64_t)emb_dim * Hd / c.g_df_skip, &w_skip))) return rc;
             if ((rc = run_gl(s, f.emb, emb_dim, w_skip, nullptr, f.dfc, Hd, f.dfc, Hd, M, c.g_df_skip, emb_dim, Hd, ACT_NONE))) return rc;
@@ -1196,7 +1245,8 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         }
         const int O2 = 2 * c.df_order;
         if ((rc = need(m, "df_dec.df_out.gl", (int64_t)Hd * Fd * O2 / c.g_df_out, &w_out))) return rc;
-        // coefs = tanh(df_out(c)) + df_convp(c0); the pathway term was written by k_df_convp on this stream earlier
+        // coefs = tanh(df_out(c)) + df_convp(c0); the pathway term was written by k_df_convp on the low-priority stream
+        DFB_CUDA(cudaStreamWaitEvent(s, m->ev_convp, 0));
         if ((rc = run_gl(s, f.dfc, Hd, w_out, nullptr, d_coefs, (int64_t)Fd * O2, d_coefs, (int64_t)Fd * O2, M, c.g_df_out, Hd, Fd * O2, ACT_TANH))) return rc;
     }
     DFB_CUDA(cudaEventRecord(m->ev_join, sa));
@@ -1237,10 +1287,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             m->dbg.erase("d1");
         }
         if ((rc = run_dwpw<DW_T2>(s, p, B, pw_sw))) return rc;
-        if (fused_mask) {
-            DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));  // join
-            return DFB_OK;
-        }
+        if (fused_mask) return finish();
         static bool attr_done = false;
         int smem = (kMaskWarps * 2 * (E + 2) * kMaskLd + c.conv_kt * 3 * kCh) * 4;
         if (!attr_done) {  // sized for the largest supported configuration (nb_erb 64, kt 2)
@@ -1254,8 +1301,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         k_mask_out<<<grid, 32 * kMaskWarps, smem, s>>>(f.e0, f.d1, ps, pb, w, bb, d_m, T, E, c.conv_kt);
         DFB_LAUNCH_CHECK();
     }
-    DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));  // join
-    return DFB_OK;
+    return finish();
 }
 
 static int apply_mode(const dfb_model *m) { return m->cfg.model_kind == 2 ? 2 : 1; }

@@ -772,22 +772,29 @@ template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int)
 // st.async broadcasts (4096 per CTA and step) and W_hh in shared memory were also tried first.
 namespace cg = cooperative_groups;
 
-constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtN = 16, kGtRows = 3 * kGtU;
+constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtRows = 3 * kGtU;
 constexpr int kGtGateThreads = 256, kGtThreads = kGtGateThreads + 32;
 // h operand (B, K-major, no swizzle) as 8 x 16 B core matrices ordered [k core matrix][row group][hi|lo]:
-// a CTA's 32 units (4 k core matrices) are one contiguous 2 KB piece -> one bulk DSMEM copy per peer
-constexpr int kGtHLbo = 512;                  // stride between K-adjacent core matrices
-constexpr int kGtHSbo = 256;                  // stride between the two 8-stream row groups
-constexpr int kGtHPlane = 128;                // hi -> lo
-constexpr int kGtHPiece = 4 * kGtHLbo;        // one CTA's slice
-constexpr int kGtHBuf = (kGtH / 8) * kGtHLbo; // one buffer (16 KB)
+// a CTA's 32 units (4 k core matrices) are one contiguous piece (2 KB for 16 streams) -> one bulk DSMEM copy per peer.
+// NS = streams per cluster (MMA N): 16 (lowest step latency) or 32 (half as many clusters: the DF decoder's
+// recurrence uses it for large batches so that it is co-resident with the ERB decoder's -- at most 15 clusters
+// of 8 CTAs fit on the device, and two launches of 8 clusters made the second one run in two waves).
+template <int NS>
+struct GtCfg {
+    static constexpr int kLbo = (NS / 8) * 256;       // stride between K-adjacent core matrices
+    static constexpr int kSbo = 256;                  // stride between 8-stream row groups
+    static constexpr int kPlane = 128;                // hi -> lo
+    static constexpr int kPiece = 4 * kLbo;           // one CTA's slice
+    static constexpr int kBuf = (kGtH / 8) * kLbo;    // one buffer (16 KB / 32 KB)
+};
 
 constexpr int kGtWCols = kGtH / 2;            // TMEM columns of one W plane: 2 bf16 per 32-bit column
 constexpr int kGtDCol = 2 * kGtWCols;         // accumulator columns start after W_hi | W_lo
 
+template <int NS>
 struct GruTcSmem {
-    alignas(1024) unsigned char h[2][kGtHBuf];            // [buffer][k core matrix][row group][hi|lo][8 rows x 16 B]
-    float pre[3][kGtU][kGtN + 1];
+    alignas(1024) unsigned char h[2][GtCfg<NS>::kBuf];   // [buffer][k core matrix][row group][hi|lo][8 rows x 16 B]
+    float pre[3][kGtU][NS + 1];
     alignas(8) uint64_t bar_h[2];
     uint64_t t_full;
     uint32_t tmem_base;
@@ -813,27 +820,6 @@ __device__ __forceinline__ uint64_t umma_desc_interleave(uint32_t saddr, uint32_
     d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// A operand from TMEM (lane = row, one 32-bit column = two consecutive bf16 K elements), B from smem
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -869,9 +855,12 @@ __device__ __forceinline__ void bf16_split(float x, unsigned short &hi, unsigned
 __device__ __forceinline__ float gt_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gt_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
+template <int NS>
 __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
+    using Cfg = GtCfg<NS>;
+    constexpr int NP = NS / 16;  // stream passes per gate thread
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    GruTcSmem &sm = *reinterpret_cast<GruTcSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
+    GruTcSmem<NS> &sm = *reinterpret_cast<GruTcSmem<NS> *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int group = blockIdx.x / kGtC;
@@ -919,14 +908,14 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     __syncthreads();
     tc_fence_after();
     cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
-    const uint32_t step_bytes = (uint32_t)((kGtC - 1) * kGtHPiece);  // one 2 KB piece from each of the 7 peers
+    const uint32_t step_bytes = (uint32_t)((kGtC - 1) * Cfg::kPiece);  // one piece from each of the 7 peers
 
     if (warp == 8) {
         // ================================================================= MMA issuer (whole warp, elected lane issues)
-        constexpr uint32_t idesc = umma_idesc_bf16(128, kGtN);
+        constexpr uint32_t idesc = umma_idesc_bf16(128, NS);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-        const uint64_t bd0 = umma_desc_interleave(smem_u32(sm.h[0]), kGtHLbo, kGtHSbo);
-        const uint64_t bd1 = umma_desc_interleave(smem_u32(sm.h[1]), kGtHLbo, kGtHSbo);
+        const uint64_t bd0 = umma_desc_interleave(smem_u32(sm.h[0]), Cfg::kLbo, Cfg::kSbo);
+        const uint64_t bd1 = umma_desc_interleave(smem_u32(sm.h[1]), Cfg::kLbo, Cfg::kSbo);
         const bool dbg_on = p.dbg && blockIdx.x == 0 && lane == 0;
         for (int t = 0; t < T; t++) {
             const int cur = t & 1;
@@ -943,7 +932,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
 #pragma unroll
                 for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
                     umma_bf16_ts_elect(tmem_u + kGtDCol, tmem_u + wa * kGtWCols + ks * 8,
-                                       bb + (uint64_t)((ks * 2 * kGtHLbo + hb * kGtHPlane) >> 4), idesc,
+                                       bb + (uint64_t)((ks * 2 * Cfg::kLbo + hb * Cfg::kPlane) >> 4), idesc,
                                        (combo == 0 && ks == 0) ? 0u : 1u);
                 }
             }
@@ -952,25 +941,37 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
         }
     } else {
         // ================================================================= gate warps (0-7)
-        // one item per thread: unit pair up = tid % 16 (units 2 up, 2 up + 1 of this CTA), stream s = tid / 16
-        const int up = tid & 15, s = tid >> 4;
-        const bool active = s < nb;
+        // NP items per thread: unit pair up = tid % 16 (units 2 up, 2 up + 1 of this CTA), streams s0 + 16 q
+        const int up = tid & 15, s0 = tid >> 4;
         const int gu = rank * kGtU + 2 * up;       // first of the two global hidden units of this thread
-        float hprev0 = 0.f, hprev1 = 0.f;
+        float hprev0[NP], hprev1[NP];
+        uint32_t hoff[NP];
+        bool active[NP];
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            const int s = s0 + 16 * q;
+            hprev0[q] = hprev1[q] = 0.f;
+            active[q] = s < nb;
+            // byte offset of this (stream, unit pair) inside an h buffer (hi plane): core matrix gu / 8, row group s / 8
+            hoff[q] = (uint32_t)((gu >> 3) * Cfg::kLbo + (s >> 3) * Cfg::kSbo + (s & 7) * 16 + (gu & 7) * 2);
+        }
         const float2 bhr = *reinterpret_cast<const float2 *>(p.bhh + gu), bhz = *reinterpret_cast<const float2 *>(p.bhh + H + gu),
                      bhn = *reinterpret_cast<const float2 *>(p.bhh + 2 * H + gu);
-        // byte offset of this (stream, unit pair) inside an h buffer (hi plane): core matrix gu / 8, row group s / 8
-        const uint32_t hoff = (uint32_t)((gu >> 3) * kGtHLbo + (s >> 3) * kGtHSbo + (s & 7) * 16 + (gu & 7) * 2);
-        const uint32_t piece0 = (uint32_t)(rank * kGtHPiece);  // this CTA's slice of a buffer
+        const uint32_t piece0 = (uint32_t)(rank * Cfg::kPiece);  // this CTA's slice of a buffer
         for (int t = 0; t < T; t++) {
             const int cur = t & 1;
-            float2 xr = make_float2(0.f, 0.f), xz = xr, xn = xr;
-            uint32_t vhi = 0, vlo = 0;
-            if (active) {
-                const float *xp = p.xproj + ((int64_t)(b0 + s) * T + t) * (3 * H) + gu;
-                xr = *reinterpret_cast<const float2 *>(xp);
-                xz = *reinterpret_cast<const float2 *>(xp + H);
-                xn = *reinterpret_cast<const float2 *>(xp + 2 * H);
+            float2 xr[NP], xz[NP], xn[NP];
+            uint32_t vhi[NP], vlo[NP];
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                xr[q] = make_float2(0.f, 0.f); xz[q] = xr[q]; xn[q] = xr[q];
+                vhi[q] = vlo[q] = 0;
+                if (active[q]) {
+                    const float *xp = p.xproj + ((int64_t)(b0 + s0 + 16 * q) * T + t) * (3 * H) + gu;
+                    xr[q] = *reinterpret_cast<const float2 *>(xp);
+                    xz[q] = *reinterpret_cast<const float2 *>(xp + H);
+                    xn[q] = *reinterpret_cast<const float2 *>(xp + 2 * H);
+                }
             }
             const bool gdbg = p.dbg && blockIdx.x == 0 && tid == 0;
             if (gdbg) p.dbg[t * 8 + 4] = clock64();
@@ -978,30 +979,34 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             if (gdbg) p.dbg[t * 8 + 5] = clock64();
             tc_fence_after();
             if (warp < 3) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kGtDCol, v);
 #pragma unroll
-                for (int ss = 0; ss < kGtN; ss++) sm.pre[warp][lane][ss] = v[ss];
+                for (int q = 0; q < NP; q++) {
+                    float v[16];
+                    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kGtDCol + 16 * q, v);
+#pragma unroll
+                    for (int ss = 0; ss < 16; ss++) sm.pre[warp][lane][16 * q + ss] = v[ss];
+                }
             }
             tc_fence_before();
             asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight gate warps only
-            if (active) {
-                const int u0 = 2 * up;
-                const float r0 = gt_sigmoid(xr.x + sm.pre[0][u0][s] + bhr.x), r1 = gt_sigmoid(xr.y + sm.pre[0][u0 + 1][s] + bhr.y);
-                const float z0 = gt_sigmoid(xz.x + sm.pre[1][u0][s] + bhz.x), z1 = gt_sigmoid(xz.y + sm.pre[1][u0 + 1][s] + bhz.y);
-                const float n0 = gt_tanh(xn.x + r0 * (sm.pre[2][u0][s] + bhn.x)), n1 = gt_tanh(xn.y + r1 * (sm.pre[2][u0 + 1][s] + bhn.y));
-                hprev0 = (1.f - z0) * n0 + z0 * hprev0;
-                hprev1 = (1.f - z1) * n1 + z1 * hprev1;
-                {
-                    unsigned short h0, l0, h1, l1;
-                    bf16_split(hprev0, h0, l0);
-                    bf16_split(hprev1, h1, l1);
-                    vhi = h0 | (uint32_t)h1 << 16;
-                    vlo = l0 | (uint32_t)l1 << 16;
-                }
+            const int u0 = 2 * up;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                if (!active[q]) continue;
+                const int s = s0 + 16 * q;
+                const float r0 = gt_sigmoid(xr[q].x + sm.pre[0][u0][s] + bhr.x), r1 = gt_sigmoid(xr[q].y + sm.pre[0][u0 + 1][s] + bhr.y);
+                const float z0 = gt_sigmoid(xz[q].x + sm.pre[1][u0][s] + bhz.x), z1 = gt_sigmoid(xz[q].y + sm.pre[1][u0 + 1][s] + bhz.y);
+                const float n0 = gt_tanh(xn[q].x + r0 * (sm.pre[2][u0][s] + bhn.x)), n1 = gt_tanh(xn[q].y + r1 * (sm.pre[2][u0 + 1][s] + bhn.y));
+                hprev0[q] = (1.f - z0) * n0 + z0 * hprev0[q];
+                hprev1[q] = (1.f - z1) * n1 + z1 * hprev1[q];
+                unsigned short h0, l0, h1, l1;
+                bf16_split(hprev0[q], h0, l0);
+                bf16_split(hprev1[q], h1, l1);
+                vhi[q] = h0 | (uint32_t)h1 << 16;
+                vlo[q] = l0 | (uint32_t)l1 << 16;
                 if (t + 1 < T) {
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff) = vhi;
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff + kGtHPlane) = vlo;
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff[q]) = vhi[q];
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff[q] + Cfg::kPlane) = vlo[q];
                 }
             }
             if (gdbg) p.dbg[t * 8 + 6] = clock64();
@@ -1010,11 +1015,11 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
                 if (gdbg) p.dbg[t * 8 + 3] = clock64();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (lane == 0) {
-                    // warp w < 7 copies the CTA's 2 KB slice to peer w (skipping itself); warp 7 signals the local barrier
+                    // warp w < 7 copies the CTA's slice to peer w (skipping itself); warp 7 signals the local barrier
                     if (warp < kGtC - 1) {
                         const int peer = warp + (warp >= rank ? 1 : 0);
                         const uint32_t src = smem_u32(sm.h[cur ^ 1]) + piece0;
-                        dsmem_bulk_copy(mapa_u32(src, peer), src, kGtHPiece, mapa_u32(smem_u32(&sm.bar_h[cur ^ 1]), peer));
+                        dsmem_bulk_copy(mapa_u32(src, peer), src, Cfg::kPiece, mapa_u32(smem_u32(&sm.bar_h[cur ^ 1]), peer));
                     } else {
                         mbar_arrive(&sm.bar_h[cur ^ 1]);  // own slice is in place
                     }
@@ -1022,14 +1027,16 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             } else {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            if (active) {  // global result last: nothing on the recurrence's critical path waits for it
-                const int64_t o = ((int64_t)(b0 + s) * T + t) * H + gu;
-                float2 ov = make_float2(hprev0, hprev1);
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                if (!active[q]) continue;  // global result last: nothing on the recurrence's critical path waits for it
+                const int64_t o = ((int64_t)(b0 + s0 + 16 * q) * T + t) * H + gu;
+                float2 ov = make_float2(hprev0[q], hprev1[q]);
                 if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
                 *reinterpret_cast<float2 *>(p.hout + o) = ov;
                 if (p.hout_hi) {  // residual-free h (the next layer's projection input)
-                    *reinterpret_cast<uint32_t *>(p.hout_hi + o) = vhi;
-                    *reinterpret_cast<uint32_t *>(p.hout_lo + o) = vlo;
+                    *reinterpret_cast<uint32_t *>(p.hout_hi + o) = vhi[q];
+                    *reinterpret_cast<uint32_t *>(p.hout_lo + o) = vlo[q];
                 }
             }
             if (gdbg) p.dbg[t * 8 + 7] = clock64();
@@ -1042,17 +1049,17 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
-                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg) {
+template <int NS>
+static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     static bool attr_done = false;
     // the kernel allocates all 512 TMEM columns (W_hh lives there), so only one CTA may be resident
     // per SM: request more than half of the shared memory to enforce it
-    const int smem = (int)sizeof(GruTcSmem) + 1024 > 120 * 1024 ? (int)sizeof(GruTcSmem) + 1024 : 120 * 1024;
+    const int need = (int)sizeof(GruTcSmem<NS>) + 1024;
+    const int smem = need > 120 * 1024 ? need : 120 * 1024;
     if (!attr_done) {
-        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, B, T, 0, dbg};
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kGtThreads);
     cfg.dynamicSmemBytes = smem;
@@ -1060,25 +1067,23 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kGtC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    // streams per cluster: a step costs the same for 1..16 streams, so use as few clusters as
-    // possible but never more than can be resident at once (a second wave would double the time)
-    static int max_clusters = 0;
-    if (!max_clusters) {
-        cfg.gridDim = dim3(kGtC * 64);
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, k_gru_tc, &cfg) != cudaSuccess || max_clusters < 1) max_clusters = 8;
-    }
-    // (a step costs the same for any N <= 16, and leaving SMs free lets the other decoder branch's
-    // recurrence run concurrently on the auxiliary stream)
-    int bc = kGtN;
-    (void)max_clusters;
-    p.Bc = bc;
-    const int ngroups = (B + bc - 1) / bc;
+    p.Bc = NS;
+    const int ngroups = (p.B + NS - 1) / NS;
     cfg.gridDim = dim3((unsigned)(ngroups * kGtC));
     cfg.stream = s;
     DFB_PROF("k_gru_tc", s);
-    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc, p));
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS>, p));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return DFB_OK;
+}
+
+// wide != 0: 32 streams per cluster when the batch needs more than 4 clusters of 16 (see GtCfg)
+int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
+                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg, int wide) {
+    GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, B, T, 0, dbg};
+    static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
+    const bool use32 = force ? force == 32 : (wide && B > 64);
+    return use32 ? launch_gru_tc_n<32>(s, p) : launch_gru_tc_n<16>(s, p);
 }
 
 // ------------------------------------------------------------------------------- host side ----
