@@ -22,7 +22,7 @@ enhance_device(model, st, audio); torch.cuda.synchronize()
 buf = np.zeros((T, 8), dtype=np.int64)
 L.dfb_debug_gru_timing(model.handle, T, buf.ctypes.data)
 d = buf[20:T - 20]
-if os.environ.get("DFB_PRECISION", "").endswith("gru_tc"):
+if "gru_tc" in os.environ.get("DFB_PRECISION", "fp32+gru_tc+proj_tc+conv_tc"):
     step = np.diff(d[:, 0])
     print(f"TC GRU B={B}  cycles/step median {np.median(step):.0f}")
     for a, b_, n in [(0, 1, "mma: wait h"), (1, 2, "mma: issue 48"), (4, 5, "gate: wait t_full"), (5, 6, "gate: ld+gates+write"), (6, 3, "gate: fence"), (3, 7, "gate: bar+copy+gstore")]:
