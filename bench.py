@@ -54,6 +54,16 @@ KERNEL_MODEL = {
 }
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` capture of one
+# forward at 32 streams x 10 s (profiles/r01_ncu_summary_final.md); every kernel's traffic is proportional to the
+# number of streams, so `roofline.traffic` scales these by streams / 32.
+NCU_TRAFFIC_32 = {
+    "k_gru_tc": 99.5e6 + 19.2e6, "k_gemm_bf16x3[gru_proj]": 33.7e6 + 40.4e6, "k_analysis": 61.6e6 + 71.9e6,
+    "k_apply_synthesis": 272.5e6 + 46.7e6, "k_df_convp": 793.2e6 + 115.1e6, "k_conv_in[df_conv0]": 24.7e6 + 728.5e6,
+    "k_conv_in[erb_conv0]": 4.1e6 + 203.5e6, "k_feat_norm": 32.6e6 + 0.5e6,
+}
+
+
 def model_config(name: str):
     from deepfilternet_b200.config import ModelConfig, load_config
     p = os.path.join(ROOT, "models", "_ref", name, "config.ini")
@@ -312,7 +322,10 @@ def main():
     else:
         achieved, peak, unit = per_launch / avg_launch_s / 1e12, tf_sust, "TFLOP/s"
     roofline = {"kernel": kname, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak if peak else None,
+                "traffic": (NCU_TRAFFIC_32[kname] * a.streams / 32.0) if kname in NCU_TRAFFIC_32 else None,
+                "traffic_source": "ncu --set full at 32 streams (profiles/r01_ncu_summary_final.md), scaled by streams / 32",
+                "peak_source": peak_src,
                 "launches_per_step": launches_per_step, "avg_launch_ms": avg_launch_s * 1e3,
                 "share_of_step": tot_ms / total_prof_ms,
                 "kernel_ms_per_step": {k: round(v[1] / a.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},

@@ -279,3 +279,37 @@ def test_launch_counter_counts_own_kernels(states):
     n0 = _lib.lib().dfb_kernel_launches()
     st.analysis(np.zeros((1, 4800), np.float32))
     assert _lib.lib().dfb_kernel_launches() == n0 + 1
+
+
+@pytest.mark.parametrize("kind", ["dfn3", "dfn2", "ll"])
+def test_precision_modes_agree_with_oracle(states, kind):
+    """Every arithmetic mode of the contractions (FFMA everywhere ... BF16x3 tcgen05 for the recurrence, the GRU
+    projections and the separable conv blocks incl. the fused mask head) stays inside the 1e-4 bound; the
+    tensor-core modes must also agree with the all-FFMA mode to ~1e-6."""
+    st, _ = states
+    cfg = cfg_of(kind)
+    sd = random_state_dict(cfg, seed=9)
+    model = DfNet(cfg, sd, st)
+    audio = synth_audio(3, 14400, seed=31)
+    ref = O.enhance(sd, cfg.as_dict(), audio)
+    outs = {}
+    for mode in ("fp32", "fp32+gru_tc", "fp32+gru_tc+proj_tc", "fp32+gru_tc+proj_tc+conv_tc"):
+        model.set_precision(mode)
+        outs[mode] = enhance(model, st, audio)
+        assert rms(outs[mode], ref) < RMS_TOL, mode
+    for mode, o in outs.items():
+        assert rms(o, outs["fp32"]) < 5e-6, mode
+
+
+def test_wide_batch_matches_oracle(states):
+    """More than 64 streams: the DF decoder's recurrence switches to 32 streams per cluster and the batched
+    kernels run with ragged last tiles; a few of the streams are checked against the oracle."""
+    st, _ = states
+    cfg = cfg_of("dfn3")
+    sd = random_state_dict(cfg, seed=12)
+    model = DfNet(cfg, sd, st)
+    audio = synth_audio(70, 7200, seed=41)
+    out = enhance(model, st, audio)
+    assert out.shape == audio.shape
+    for i in (0, 17, 33, 64, 69):  # both halves of a 32-stream cluster, the ragged last cluster
+        assert rms(out[i:i + 1], O.enhance(sd, cfg.as_dict(), audio[i:i + 1])) < RMS_TOL, i
