@@ -773,7 +773,7 @@ template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int)
 namespace cg = cooperative_groups;
 
 constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtRows = 3 * kGtU;
-constexpr int kGtGateThreads = 256, kGtThreads = kGtGateThreads + 32;
+// gate threads: one per (unit pair, stream) item = 16 * NS; plus the MMA warp
 // h operand (B, K-major, no swizzle) as 8 x 16 B core matrices ordered [k core matrix][row group][hi|lo]:
 // a CTA's 32 units (4 k core matrices) are one contiguous piece (2 KB for 16 streams) -> one bulk DSMEM copy per peer.
 // NS = streams per cluster (MMA N): 16 (lowest step latency) or 32 (half as many clusters: the DF decoder's
@@ -781,6 +781,9 @@ constexpr int kGtGateThreads = 256, kGtThreads = kGtGateThreads + 32;
 // of 8 CTAs fit on the device, and two launches of 8 clusters made the second one run in two waves).
 template <int NS>
 struct GtCfg {
+    static constexpr int kGateThreads = 16 * NS;      // 256 / 512
+    static constexpr int kThreads = kGateThreads + 32;
+    static constexpr int kMmaWarp = kGateThreads / 32;
     static constexpr int kLbo = (NS / 8) * 256;       // stride between K-adjacent core matrices
     static constexpr int kSbo = 256;                  // stride between 8-stream row groups
     static constexpr int kPlane = 128;                // hi -> lo
@@ -856,9 +859,9 @@ __device__ __forceinline__ float gt_sigmoid(float x) { return __fdividef(1.f, 1.
 __device__ __forceinline__ float gt_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 template <int NS>
-__global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
+__global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p) {
     using Cfg = GtCfg<NS>;
-    constexpr int NP = NS / 16;  // stream passes per gate thread
+    constexpr int kGtThreads = Cfg::kThreads;
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     GruTcSmem<NS> &sm = *reinterpret_cast<GruTcSmem<NS> *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
     cg::cluster_group cluster = cg::this_cluster();
@@ -910,7 +913,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
     cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
     const uint32_t step_bytes = (uint32_t)((kGtC - 1) * Cfg::kPiece);  // one piece from each of the 7 peers
 
-    if (warp == 8) {
+    if (warp == Cfg::kMmaWarp) {
         // ================================================================= MMA issuer (whole warp, elected lane issues)
         constexpr uint32_t idesc = umma_idesc_bf16(128, NS);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -940,103 +943,87 @@ __global__ void __launch_bounds__(kGtThreads, 1) k_gru_tc(GruTcParams p) {
             umma_commit_elect(&sm.t_full);
         }
     } else {
-        // ================================================================= gate warps (0-7)
-        // NP items per thread: unit pair up = tid % 16 (units 2 up, 2 up + 1 of this CTA), streams s0 + 16 q
-        const int up = tid & 15, s0 = tid >> 4;
+        // ================================================================= gate warps (16 NS threads)
+        // one item per thread: unit pair up = tid % 16 (units 2 up, 2 up + 1 of this CTA), stream s = tid / 16.
+        // (The first 32-stream version kept 256 gate threads with two items each: 4550 cycles per step instead of 2600.)
+        const int up = tid & 15, s = tid >> 4;
+        const bool active = s < nb;
         const int gu = rank * kGtU + 2 * up;       // first of the two global hidden units of this thread
-        float hprev0[NP], hprev1[NP];
-        uint32_t hoff[NP];
-        bool active[NP];
-#pragma unroll
-        for (int q = 0; q < NP; q++) {
-            const int s = s0 + 16 * q;
-            hprev0[q] = hprev1[q] = 0.f;
-            active[q] = s < nb;
-            // byte offset of this (stream, unit pair) inside an h buffer (hi plane): core matrix gu / 8, row group s / 8
-            hoff[q] = (uint32_t)((gu >> 3) * Cfg::kLbo + (s >> 3) * Cfg::kSbo + (s & 7) * 16 + (gu & 7) * 2);
-        }
+        float hprev0 = 0.f, hprev1 = 0.f;
         const float2 bhr = *reinterpret_cast<const float2 *>(p.bhh + gu), bhz = *reinterpret_cast<const float2 *>(p.bhh + H + gu),
                      bhn = *reinterpret_cast<const float2 *>(p.bhh + 2 * H + gu);
+        // byte offset of this (stream, unit pair) inside an h buffer (hi plane): core matrix gu / 8, row group s / 8
+        const uint32_t hoff = (uint32_t)((gu >> 3) * Cfg::kLbo + (s >> 3) * Cfg::kSbo + (s & 7) * 16 + (gu & 7) * 2);
         const uint32_t piece0 = (uint32_t)(rank * Cfg::kPiece);  // this CTA's slice of a buffer
+        // TMEM loaders: warp w reads lane quarter w % 4 (gates r, z, n = quarters 0-2), streams [16 (w / 4), +16)
+        const bool loader = (warp & 3) < 3 && (warp >> 2) < NS / 16;
         for (int t = 0; t < T; t++) {
             const int cur = t & 1;
-            float2 xr[NP], xz[NP], xn[NP];
-            uint32_t vhi[NP], vlo[NP];
-#pragma unroll
-            for (int q = 0; q < NP; q++) {
-                xr[q] = make_float2(0.f, 0.f); xz[q] = xr[q]; xn[q] = xr[q];
-                vhi[q] = vlo[q] = 0;
-                if (active[q]) {
-                    const float *xp = p.xproj + ((int64_t)(b0 + s0 + 16 * q) * T + t) * (3 * H) + gu;
-                    xr[q] = *reinterpret_cast<const float2 *>(xp);
-                    xz[q] = *reinterpret_cast<const float2 *>(xp + H);
-                    xn[q] = *reinterpret_cast<const float2 *>(xp + 2 * H);
-                }
+            float2 xr = make_float2(0.f, 0.f), xz = xr, xn = xr;
+            uint32_t vhi = 0, vlo = 0;
+            if (active) {
+                const float *xp = p.xproj + ((int64_t)(b0 + s) * T + t) * (3 * H) + gu;
+                xr = *reinterpret_cast<const float2 *>(xp);
+                xz = *reinterpret_cast<const float2 *>(xp + H);
+                xn = *reinterpret_cast<const float2 *>(xp + 2 * H);
             }
             const bool gdbg = p.dbg && blockIdx.x == 0 && tid == 0;
             if (gdbg) p.dbg[t * 8 + 4] = clock64();
             mbar_wait(&sm.t_full, (uint32_t)(t & 1));
             if (gdbg) p.dbg[t * 8 + 5] = clock64();
             tc_fence_after();
-            if (warp < 3) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
+            if (loader) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
+                const int g = warp & 3, q = warp >> 2;
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + kGtDCol + 16 * q, v);
 #pragma unroll
-                for (int q = 0; q < NP; q++) {
-                    float v[16];
-                    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kGtDCol + 16 * q, v);
-#pragma unroll
-                    for (int ss = 0; ss < 16; ss++) sm.pre[warp][lane][16 * q + ss] = v[ss];
-                }
+                for (int ss = 0; ss < 16; ss++) sm.pre[g][lane][16 * q + ss] = v[ss];
             }
             tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight gate warps only
-            const int u0 = 2 * up;
-#pragma unroll
-            for (int q = 0; q < NP; q++) {
-                if (!active[q]) continue;
-                const int s = s0 + 16 * q;
-                const float r0 = gt_sigmoid(xr[q].x + sm.pre[0][u0][s] + bhr.x), r1 = gt_sigmoid(xr[q].y + sm.pre[0][u0 + 1][s] + bhr.y);
-                const float z0 = gt_sigmoid(xz[q].x + sm.pre[1][u0][s] + bhz.x), z1 = gt_sigmoid(xz[q].y + sm.pre[1][u0 + 1][s] + bhz.y);
-                const float n0 = gt_tanh(xn[q].x + r0 * (sm.pre[2][u0][s] + bhn.x)), n1 = gt_tanh(xn[q].y + r1 * (sm.pre[2][u0 + 1][s] + bhn.y));
-                hprev0[q] = (1.f - z0) * n0 + z0 * hprev0[q];
-                hprev1[q] = (1.f - z1) * n1 + z1 * hprev1[q];
+            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kGateThreads) : "memory");  // the gate warps only
+            if (active) {
+                const int u0 = 2 * up;
+                const float r0 = gt_sigmoid(xr.x + sm.pre[0][u0][s] + bhr.x), r1 = gt_sigmoid(xr.y + sm.pre[0][u0 + 1][s] + bhr.y);
+                const float z0 = gt_sigmoid(xz.x + sm.pre[1][u0][s] + bhz.x), z1 = gt_sigmoid(xz.y + sm.pre[1][u0 + 1][s] + bhz.y);
+                const float n0 = gt_tanh(xn.x + r0 * (sm.pre[2][u0][s] + bhn.x)), n1 = gt_tanh(xn.y + r1 * (sm.pre[2][u0 + 1][s] + bhn.y));
+                hprev0 = (1.f - z0) * n0 + z0 * hprev0;
+                hprev1 = (1.f - z1) * n1 + z1 * hprev1;
                 unsigned short h0, l0, h1, l1;
-                bf16_split(hprev0[q], h0, l0);
-                bf16_split(hprev1[q], h1, l1);
-                vhi[q] = h0 | (uint32_t)h1 << 16;
-                vlo[q] = l0 | (uint32_t)l1 << 16;
+                bf16_split(hprev0, h0, l0);
+                bf16_split(hprev1, h1, l1);
+                vhi = h0 | (uint32_t)h1 << 16;
+                vlo = l0 | (uint32_t)l1 << 16;
                 if (t + 1 < T) {
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff[q]) = vhi[q];
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff[q] + Cfg::kPlane) = vlo[q];
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff) = vhi;
+                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff + Cfg::kPlane) = vlo;
                 }
             }
             if (gdbg) p.dbg[t * 8 + 6] = clock64();
             if (t + 1 < T) {
                 fence_proxy_async();  // own slice (generic stores) -> visible to the bulk-copy / tensor-core proxy
                 if (gdbg) p.dbg[t * 8 + 3] = clock64();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kGateThreads) : "memory");
                 if (lane == 0) {
                     // warp w < 7 copies the CTA's slice to peer w (skipping itself); warp 7 signals the local barrier
                     if (warp < kGtC - 1) {
                         const int peer = warp + (warp >= rank ? 1 : 0);
                         const uint32_t src = smem_u32(sm.h[cur ^ 1]) + piece0;
                         dsmem_bulk_copy(mapa_u32(src, peer), src, Cfg::kPiece, mapa_u32(smem_u32(&sm.bar_h[cur ^ 1]), peer));
-                    } else {
+                    } else if (warp == kGtC - 1) {
                         mbar_arrive(&sm.bar_h[cur ^ 1]);  // own slice is in place
                     }
                 }
             } else {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kGateThreads) : "memory");
             }
-#pragma unroll
-            for (int q = 0; q < NP; q++) {
-                if (!active[q]) continue;  // global result last: nothing on the recurrence's critical path waits for it
-                const int64_t o = ((int64_t)(b0 + s0 + 16 * q) * T + t) * H + gu;
-                float2 ov = make_float2(hprev0[q], hprev1[q]);
+            if (active) {  // global result last: nothing on the recurrence's critical path waits for it
+                const int64_t o = ((int64_t)(b0 + s) * T + t) * H + gu;
+                float2 ov = make_float2(hprev0, hprev1);
                 if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
                 *reinterpret_cast<float2 *>(p.hout + o) = ov;
                 if (p.hout_hi) {  // residual-free h (the next layer's projection input)
-                    *reinterpret_cast<uint32_t *>(p.hout_hi + o) = vhi[q];
-                    *reinterpret_cast<uint32_t *>(p.hout_lo + o) = vlo[q];
+                    *reinterpret_cast<uint32_t *>(p.hout_hi + o) = vhi;
+                    *reinterpret_cast<uint32_t *>(p.hout_lo + o) = vlo;
                 }
             }
             if (gdbg) p.dbg[t * 8 + 7] = clock64();
@@ -1061,7 +1048,7 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
         attr_done = true;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(kGtThreads);
+    cfg.blockDim = dim3(GtCfg<NS>::kThreads);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
