@@ -90,19 +90,21 @@ def load_weights(name: str, cfg):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  The sampler is started before the warm-up (the tool
+    needs ~100 ms to come up and the timed region of 10 steps is only ~140 ms long); `window()` brackets the timed
+    regions with wall-clock stamps and only samples inside the window are reported."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -110,7 +112,40 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def window_begin(self):
+        self.t0 = time.time()
+
+    def window_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def parse(lines, t0=None, t1=None) -> dict:
+        def collect(filtered):
+            sm, mx, reasons = [], None, set()
+            for ts, ln in lines:
+                if filtered and t0 is not None and t1 is not None and not (t0 <= ts <= t1 + 0.06):
+                    continue
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 10:
+                    continue
+                try:
+                    sm.append(float(f[2])); mx = float(f[3])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        sm, mx, reasons = collect(True)
+        scope = "timed regions"
+        if not sm:  # nothing landed inside the window: fall back to everything sampled under load (warm-up included)
+            sm, mx, reasons = collect(False)
+            scope = "warm-up + timed regions"
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "scope": scope}
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -120,21 +155,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return self.parse(self.lines, self.t0, self.t1)
 
 
 def peaks():
@@ -261,13 +282,14 @@ def main():
             torch.cuda.synchronize()
 
     # ---------------- device-resident timing
+    clocks = ClockSampler(dev_index)
+    clocks.start()
     for _ in range(a.warmup):
         enhance_device(model, st, audio, out=out)
     sync_all()
     L.dfb_profile_report(ctypes_buf(), 1 << 16)  # drain
     L.dfb_profile_enable(1, None)
-    clocks = ClockSampler(dev_index)
-    clocks.start()
+    clocks.window_begin()
     launches0 = L.dfb_kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -278,7 +300,6 @@ def main():
     sync_all()
     ms = ev0.elapsed_time(ev1)
     launches = int(L.dfb_kernel_launches() - launches0)
-    clk = clocks.stop()
     buf = ctypes_buf()
     n = L.dfb_profile_report(buf, 1 << 16)
     L.dfb_profile_enable(0, None)
@@ -295,6 +316,8 @@ def main():
         enhance(model, st, host_in, out=host_out)   # synchronous: returns with the result on the host
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks.window_end()
+    clk = clocks.stop()
     times = torch.tensor([ms / 1e3, e2e_s], dtype=torch.float64, device=f"cuda:{dev_index}")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
