@@ -127,3 +127,50 @@ def test_fft_index_algebra_on_host(tmp_path):
                            os.path.join(ROOT, "tests", "host", "fft_host_test.cu")], stderr=subprocess.DEVNULL)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout
+
+
+def test_umma_sw128_image_layout():
+    """The pre-swizzled BF16 hi | lo image of the 1x1 conv weights (the tcgen05 B operand the conv kernel fetches with
+    one bulk copy): un-swizzling chunk j ^ (n & 7) of row n must give back hi + lo ~= w to BF16x2 accuracy."""
+    import torch
+    from deepfilternet_b200.weights import bf16_planes, umma_sw128_image
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((64, 64)).astype(np.float32)
+    img = umma_sw128_image(w)
+    assert img.dtype == np.float32 and img.size == 2 * 64 * 32  # two planes of 64 rows x 128 bytes
+    planes = img.view(np.int16).reshape(2, 64, 8, 8)             # [plane][row][16-byte chunk][8 bf16]
+    rec = np.zeros((2, 64, 64), dtype=np.float32)
+    for n in range(64):
+        for j in range(8):
+            chunk = planes[:, n, j ^ (n & 7)]                    # where chunk j of row n was stored
+            rec[:, n, 8 * j:8 * j + 8] = torch.from_numpy(chunk.copy()).view(torch.bfloat16).to(torch.float32).numpy()
+    hi, lo = bf16_planes(w)
+    as_f32 = lambda p: torch.from_numpy(p.view(np.int16).copy()).view(torch.bfloat16).to(torch.float32).numpy().reshape(64, 64)
+    assert np.array_equal(rec[0], as_f32(hi)) and np.array_equal(rec[1], as_f32(lo))
+    assert np.abs(rec[0] + rec[1] - w).max() <= 2.0 ** -16 * np.abs(w).max()
+
+
+def test_bench_bookkeeping():
+    """bench.py's clock parser and kernel table (no GPU): nvidia-smi csv lines -> median clock / throttle reasons
+    inside the timed window; every kernel name the library's profiler can emit has a roofline model entry."""
+    import importlib.util
+    import re
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    now = time.time()
+    mk = lambda ts, sm, cap: (ts, f"2026/01/01 00:00:00.000, 0, {sm}, 1965, 600.0, 0x0, Not Active, Not Active, Not Active, {cap}")
+    lines = [mk(now - 2.0, 1200, "Not Active"), mk(now - 0.2, 1950, "Active"), mk(now - 0.1, 1965, "Not Active")]
+    r = bench.ClockSampler.parse(lines, now - 0.3, now)
+    assert r["samples"] == 2 and r["sm_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"] and r["scope"] == "timed regions"
+    r = bench.ClockSampler.parse(lines, now + 1, now + 2)
+    assert r["samples"] == 3 and r["scope"].startswith("warm-up")
+    names = set()
+    csrc = os.path.join(root, "deepfilternet_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith(".cu"):
+            names |= set(re.findall(r'DFB_PROF\("([^"]+)"', open(os.path.join(csrc, f)).read()))
+    default_path = {n for n in names if not n.startswith(("k_gru", "k_gemm_tf32", "k_dwpw", "k_mask_out")) or n in ("k_gru_tc", "k_dwpw_bx")}
+    assert default_path <= set(bench.KERNEL_MODEL) | {"k_grouped_linear"}, default_path - set(bench.KERNEL_MODEL)
