@@ -785,9 +785,14 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
     }
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    // the DF branch (`aux`) is the critical path of both the encoder-conv and the decoder phase (launch timeline), so
+    // the ERB branch's stream may sit one or more levels below it (numerically greater = lower priority)
+    static const int erb_offset = getenv("DFB_ERB_PRIO_OFFSET") ? atoi(getenv("DFB_ERB_PRIO_OFFSET")) : 0;
+    int prio_hi = prio_greatest + erb_offset;
+    if (prio_hi > prio_least) prio_hi = prio_least;
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&m->aux, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&m->hi, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&m->hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&m->low, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming) != cudaSuccess ||
