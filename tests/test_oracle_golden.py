@@ -152,3 +152,32 @@ def test_si_sdr_known_answer(name, golden_dir, model_dir):
     out = O.enhance(sd, cfg.as_dict(), noisy, pad=True)
     s = rh.si_sdr(clean, out.numpy())
     assert abs(s - kat["target"]) <= 1e-4 + 1e-4 * abs(kat["target"]), (s, kat["target"])
+
+
+def test_oracle_carried_state_semantics():
+    """pyDF `reset` argument (pyDF/src/lib.rs:56-58, 91-93; DFState::reset libDF/src/lib.rs:156-159) in the oracle that
+    the GPU `libdf` mirror is checked against: chunked `reset=False` streaming of one channel equals the one-shot
+    transform, channel c continues channel c - 1, and a `reset=True` call clears BOTH memories first."""
+    import libdf_oracle as LO
+    from tests_common import synth_audio
+    st = LO.DF(48000, 960, 480, 32, 2)
+    x = synth_audio(2, 9600, seed=8).numpy()
+    whole = st.analysis(x[:1], reset=True)
+    st.reset()
+    parts = np.concatenate([st.analysis(np.ascontiguousarray(x[:1, o:o + 2400]), reset=False) for o in range(0, 9600, 2400)], 1)
+    assert np.array_equal(whole, parts)
+    # two channels without reset == the concatenated signal in one channel
+    st.reset()
+    two = st.analysis(x, reset=False)
+    st.reset()
+    cat = st.analysis(x.reshape(1, -1), reset=True)
+    assert np.array_equal(two.reshape(1, -1, 481), cat)
+    # synthesis: chunked streaming == one shot; and analysis(reset=True) wipes the synthesis memory as well
+    st.reset()
+    y_whole = st.synthesis(whole.copy(), reset=True)
+    st.reset()
+    y_parts = np.concatenate([st.synthesis(whole[:, o:o + 5].copy(), reset=False) for o in range(0, 20, 5)], 1)
+    assert np.array_equal(y_whole, y_parts)
+    st.synthesis(whole.copy(), reset=True)       # leaves a non-zero synthesis memory behind
+    st.analysis(x[:1], reset=True)               # DFState::reset clears it
+    assert np.array_equal(st.synthesis(whole.copy(), reset=False), y_whole)
