@@ -54,6 +54,18 @@ struct ProfScope {
 };
 #define DFB_PROF(name, stream) dfb::ProfScope prof_scope__(name, stream)
 
+// Function attributes (dynamic shared memory limit, cluster size) are per device: launch sites set them the first
+// time they run on each device of the process.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        return !(mask.fetch_or(bit) & bit);
+    }
+};
+
 // Selects `device` and verifies it is a Blackwell part; no CPU fallback exists.
 int use_device(int device);
 

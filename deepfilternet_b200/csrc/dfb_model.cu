@@ -894,11 +894,10 @@ int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const fl
 template <int H, int C>
 int launch_gru_t(cudaStream_t s, const GruParams &p, int ngroups) {
     constexpr int smem = (2 * kGruMaxBc * (H + 4) + 3 * (H / C) * (kGruMaxBc + 1)) * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         if (C > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru<H, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         DFB_CUDA(cudaFuncSetAttribute(k_gru<H, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(ngroups * C));
@@ -991,11 +990,10 @@ namespace {
 template <int MODE>
 int run_dwpw(cudaStream_t s, DwPwParams p, int B, const float *w_sw = nullptr) {
     if (w_sw) return launch_dwpw_tc<MODE>(s, p, w_sw, B);
-    static bool attr_done = false;
+    static PerDeviceOnce attr_once;
     const int smem = (kCh * kCh + 128 * kLdA) * 4;
-    if (!attr_done) {
+    if (attr_once.first()) {
         DFB_CUDA(cudaFuncSetAttribute(k_dwpw<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     p.NF = 128 / p.Fout;
     if (p.NF < 1) p.NF = 1;
@@ -1293,12 +1291,11 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         }
         if ((rc = run_dwpw<DW_T2>(s, p, B, pw_sw))) return rc;
         if (fused_mask) return finish();
-        static bool attr_done = false;
+        static PerDeviceOnce attr_once;
         int smem = (kMaskWarps * 2 * (E + 2) * kMaskLd + c.conv_kt * 3 * kCh) * 4;
-        if (!attr_done) {  // sized for the largest supported configuration (nb_erb 64, kt 2)
+        if (attr_once.first()) {  // sized for the largest supported configuration (nb_erb 64, kt 2)
             DFB_CUDA(cudaFuncSetAttribute(k_mask_out, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (kMaskWarps * 2 * (64 + 2) * kMaskLd + 2 * 3 * kCh) * 4));
-            attr_done = true;
         }
         int per_cta = kMaskWarps * kMaskChunk;
         dim3 grid((unsigned)((T + per_cta - 1) / per_cta), (unsigned)B);

@@ -709,13 +709,16 @@ k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 
 
 template <int MODE, int KT, int PATH, int MASK = 0>
 static int launch_dwpw_bx(cudaStream_t s, const DwPwParams &p, const float *w_sw, int B) {
-    static int attr_smem = 0;
+    static int attr_smem[64] = {0};  // per device: largest dynamic shared memory size set so far
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
     const int raw = (p.NF + KT - 1) * p.Fin * kCh * 4 * (PATH ? 2 : 1) + (MASK ? p.NF * p.Fout * kCh * 4 : 0);
     const int smem = (int)kDxRaw + raw + (int)kDxTail;
     if (smem > 227 * 1024) return fail(DFB_ERR_UNSUPPORTED, "dwpw tile needs %d bytes of shared memory", smem);
-    if (smem > attr_smem) {
+    if (smem > attr_smem[dev]) {
         DFB_CUDA(cudaFuncSetAttribute(k_dwpw_bx<MODE, KT, PATH, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+        attr_smem[dev] = smem;
     }
     dim3 grid((unsigned)((p.T + p.NF - 1) / p.NF), (unsigned)B);
     DFB_PROF("k_dwpw_bx", s);
@@ -1038,14 +1041,13 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
 
 template <int NS>
 static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
-    static bool attr_done = false;
+    static PerDeviceOnce attr_once;
     // the kernel allocates all 512 TMEM columns (W_hh lives there), so only one CTA may be resident
     // per SM: request more than half of the shared memory to enforce it
     const int need = (int)sizeof(GruTcSmem<NS>) + 1024;
     const int smem = need > 120 * 1024 ? need : 120 * 1024;
-    if (!attr_done) {
+    if (attr_once.first()) {
         DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(GtCfg<NS>::kThreads);
@@ -1128,14 +1130,12 @@ int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64
     CUtensorMap mxh, mxl;
     int rc;
     if ((rc = make_map_bf16(&mxh, x_hi, M, K, ldx, kBxBM)) || (rc = make_map_bf16(&mxl, x_lo, M, K, ldx, kBxBM))) return rc;
-    static int num_sms = 0;
+    static PerDeviceOnce attr_once;
     const int smem = (int)sizeof(BxSmem) + 1024;
-    if (!num_sms) {
-        DFB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int dev = 0;
-        DFB_CUDA(cudaGetDevice(&dev));
-        DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    if (attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0, num_sms = 0;
+    DFB_CUDA(cudaGetDevice(&dev));
+    DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     // persistent: one CTA per SM; blockIdx.x = column slice (fastest, so the CTAs that stream the same X tiles are
     // co-scheduled and share them through L2), blockIdx.y = row group
     const int nslices = N / kBxBN;
@@ -1160,11 +1160,10 @@ int launch_gemm_tf32(cudaStream_t s, const float *x, int64_t ldx, const float *w
     CUtensorMap ma, mb;
     int rc;
     if ((rc = make_map(&ma, x, M, K, ldx, kTcBM)) || (rc = make_map(&mb, w_nk, N, K, K, BN))) return rc;
-    static bool attr_done = false;
+    static PerDeviceOnce attr_once;
     const int smem = (int)sizeof(TcSmem<BN>) + 1024;
-    if (!attr_done) {
+    if (attr_once.first()) {
         DFB_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     dim3 grid((unsigned)((M + kTcBM - 1) / kTcBM), (unsigned)(N / BN));
     DFB_PROF("k_gemm_tf32[gru_proj]", s);
