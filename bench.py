@@ -44,6 +44,7 @@ KERNEL_MODEL = {
     "k_gemm_bf16x3[gru_proj]": ("tensor", 2 * 5 * 256 * 768, "flops"),      # 5 GRU layers, W_ih x
     "k_grouped_linear[gru_proj]": ("tensor", 2 * 5 * 256 * 768, "flops"),
     "k_grouped_linear": ("tensor", 2 * (3072 * 16 + 512 * 16 + 256 * 32 + 512 * 16 + 256 * 32 + 512 * 32 + 512 * 16 + 256 * 60), "flops"),
+    "k_gl_ws": ("tensor", 2 * (3072 * 16 + 512 * 16 + 256 * 32 + 512 * 16 + 256 * 32 + 512 * 32 + 512 * 16 + 256 * 60), "flops"),  # experimental GL
     "k_dwpw": ("tensor", 2 * 64 * 64 * (16 + 8 + 8 + 48 + 8 + 16 + 32), "flops"),
     # fused depthwise -> tcgen05 1x1: rows read (input + pathway) + rows written, 256 B each, over the 7 separable blocks
     "k_dwpw_bx": ("hbm", 256 * ((96 + 48) + (32 + 16) + (16 + 8) + (8 + 8) + (8 + 8 + 8) + (8 + 8 + 16) + (16 + 16 + 32)), "bytes"),

@@ -320,6 +320,127 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
     }
 }
 
+// ------------------------------------------------- grouped linear, weight-stationary (experimental) ----
+// Same contract as k_grouped_linear.  EXPERIMENTAL (DFB_GL_WS=1, off by default, not yet validated on a GPU):
+// every thread keeps the weights of its CPT output columns (IG x CPT values) in registers for the whole kernel,
+// persistent CTAs stream row tiles through a cp.async double buffer, and a row's inputs are read from shared
+// memory as broadcasts (all threads of a group read the same address; groups are padded to IG + 4 floats so that the
+// groups of a warp hit different banks).  Motivation (ncu): the tiled kernel spends two thirds of its instructions
+// outside the FFMA loop and exposes the global-load latency of every tile.
+struct GlWsGeom {
+    int tpg;    // threads per group (power of two >= ceil(Hg / CPT))
+    int gcta;   // groups per CTA (grid.y = G / gcta)
+    int rs;     // row slots = 256 / (gcta * tpg)
+    int R;      // rows per tile
+};
+
+template <int IG, int CPT>
+__global__ void __launch_bounds__(256, (IG * CPT > 80) ? 1 : 2) k_gl_ws(GlParams p, GlWsGeom q) {
+    extern __shared__ __align__(16) float gl_smem[];
+    constexpr int GS = IG + 4;                    // padded group stride (floats)
+    const int XP = q.gcta * GS;                   // padded row pitch (floats)
+    const int tid = threadIdx.x;
+    const int per_slot = q.gcta * q.tpg;
+    const int slot = tid / per_slot, within = tid - slot * per_slot;
+    const int gl = within / q.tpg, tc = within - gl * q.tpg;
+    const int g = blockIdx.y * q.gcta + gl;       // global group
+    const int col0 = tc * CPT;                    // first in-group column of this thread
+    // ---- weights of this thread's columns -> registers
+    float w[IG][CPT];
+#pragma unroll
+    for (int k = 0; k < IG; k++)
+#pragma unroll
+        for (int c = 0; c < CPT; c++)
+            w[k][c] = (col0 + c < p.Hg) ? __ldg(p.w + ((int64_t)g * IG + k) * p.Hg + col0 + c) : 0.f;
+    float bias[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; c++) bias[c] = (p.bias && col0 + c < p.Hg) ? __ldg(p.bias + g * p.Hg + col0 + c) : 0.f;
+    const int64_t ntiles = (p.M + q.R - 1) / q.R;
+    const int cpr = q.gcta * (IG / 4);            // 16-byte chunks per row
+    const int nchunks = q.R * cpr;
+    const int64_t xcol0 = (int64_t)blockIdx.y * q.gcta * IG;
+    auto prefetch = [&](int64_t tile, float *buf) {
+        const int64_t m0 = tile * q.R;
+        for (int idx = tid; idx < nchunks; idx += 256) {
+            const int r = idx / cpr, c = idx - r * cpr;
+            const int cg = c / (IG / 4), k4 = c - cg * (IG / 4);
+            float *dst = buf + r * XP + cg * GS + k4 * 4;
+            const int64_t m = m0 + r;
+            if (m < p.M) {
+                const float *src = p.x + m * p.ldx + xcol0 + cg * IG + k4 * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+            } else {
+                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float *bufs[2] = {gl_smem, gl_smem + q.R * XP};
+    int64_t tile = blockIdx.x;
+    if (tile < ntiles) prefetch(tile, bufs[0]);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+        float *cur = (it & 1) ? bufs[1] : bufs[0];
+        float *nxt = (it & 1) ? bufs[0] : bufs[1];
+        if (tile + gridDim.x < ntiles) {
+            prefetch(tile + gridDim.x, nxt);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int64_t m0 = tile * q.R;
+        for (int r = slot; r < q.R; r += q.rs) {
+            const int64_t m = m0 + r;
+            if (m >= p.M || slot >= q.rs) break;
+            const float *xs = cur + r * XP + gl * GS;
+            float acc[CPT], acc2[CPT];  // two chains per column: a lone accumulator would serialise IG dependent FMAs
+#pragma unroll
+            for (int c = 0; c < CPT; c++) acc[c] = acc2[c] = 0.f;
+#pragma unroll
+            for (int k = 0; k < IG; k += 4) {
+                const float4 xv = *reinterpret_cast<const float4 *>(xs + k);
+#pragma unroll
+                for (int c = 0; c < CPT; c++) {
+                    acc[c] += xv.x * w[k][c];
+                    acc2[c] += xv.y * w[k + 1][c];
+                    acc[c] += xv.z * w[k + 2][c];
+                    acc2[c] += xv.w * w[k + 3][c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CPT; c++) acc[c] += acc2[c];
+            const int colbase = g * p.Hg + col0;
+            float v[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; c++) {
+                v[c] = act_apply(acc[c] + bias[c], p.act) * p.oscale + p.ooffset;
+                if (p.res && col0 + c < p.Hg) v[c] += p.res[m * p.ldr + colbase + c];
+            }
+            float *dst = p.y + m * p.ldy + colbase;
+            const bool full = col0 + CPT <= p.Hg;
+            if (CPT == 4 && full && (((uintptr_t)dst) & 15) == 0) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[CPT > 1 ? 1 : 0], v[CPT > 2 ? 2 : 0], v[CPT > 3 ? 3 : 0]);
+            } else if (CPT == 2 && full && (((uintptr_t)dst) & 7) == 0) {
+                *reinterpret_cast<float2 *>(dst) = make_float2(v[0], v[CPT > 1 ? 1 : 0]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPT; c++)
+                    if (col0 + c < p.Hg) dst[c] = v[c];
+            }
+            if (p.y_hi) {
+#pragma unroll
+                for (int c = 0; c < CPT; c++) {
+                    if (col0 + c >= p.Hg) continue;
+                    const __nv_bfloat16 hb = __float2bfloat16_rn(v[c]);
+                    p.y_hi[m * p.ldy + colbase + c] = __bfloat16_as_ushort(hb);
+                    p.y_lo[m * p.ldy + colbase + c] = __bfloat16_as_ushort(__float2bfloat16_rn(v[c] - __bfloat162float(hb)));
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with `cur` before the next iteration prefetches into it
+    }
+}
+
 // ------------------------------------------------------------------- GRU recurrence ----
 // torch.nn.GRU cell (gate order r, z, n; modules.py:684,723):
 //   r = s(xr + Whr h + bhr), z = s(xz + Whz h + bhz), n = tanh(xn + r (Whn h + bhn)), h' = (1-z) n + z h
@@ -871,12 +992,61 @@ extern "C" int64_t dfb_model_workspace_bytes(const dfb_model *m) { return m ? (i
 
 namespace {
 
+template <int IG, int CPT>
+int launch_gl_ws(cudaStream_t s, const GlParams &p) {
+    GlWsGeom q;
+    const int need = (p.Hg + CPT - 1) / CPT;
+    q.tpg = 1;
+    while (q.tpg < need) q.tpg *= 2;
+    if (q.tpg > 256) return DFB_ERR_UNSUPPORTED;
+    q.gcta = 256 / q.tpg < p.G ? 256 / q.tpg : p.G;
+    if (p.G % q.gcta) return DFB_ERR_UNSUPPORTED;
+    q.rs = 256 / (q.gcta * q.tpg);
+    const int row_bytes = q.gcta * (IG + 4) * 4;
+    q.R = 40 * 1024 / row_bytes;
+    if (q.R > 32) q.R = 32;
+    if (q.R < q.rs) q.R = q.rs;
+    q.R -= q.R % q.rs;
+    const int smem = 2 * q.R * row_bytes;
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_gl_ws<IG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if (smem > 100 * 1024) return DFB_ERR_UNSUPPORTED;
+    int dev = 0, num_sms = 0;
+    DFB_CUDA(cudaGetDevice(&dev));
+    DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t ntiles = (p.M + q.R - 1) / q.R;
+    const int gy = p.G / q.gcta;
+    int64_t gx = (int64_t)2 * num_sms / gy;
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    DFB_PROF("k_gl_ws", s);
+    k_gl_ws<IG, CPT><<<dim3((unsigned)gx, (unsigned)gy), 256, smem, s>>>(p, q);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+}
+
+// shapes of the shipped models; anything else falls back to k_grouped_linear
+int run_gl_ws(cudaStream_t s, const GlParams &p) {
+    if (p.Ig == 96 && p.Hg == 16) return launch_gl_ws<96, 1>(s, p);   // df_fc_emb
+    if (p.Ig == 32 && p.Hg == 16) return launch_gl_ws<32, 2>(s, p);   // 512 -> 256 / 16
+    if (p.Ig == 64 && p.Hg == 32) return launch_gl_ws<64, 1>(s, p);   // 512 -> 256 / 8
+    if (p.Ig == 16 && p.Hg == 32) return launch_gl_ws<16, 2>(s, p);   // 256 -> 512 / 16
+    if (p.Ig == 16 && p.Hg == 60) return launch_gl_ws<16, 4>(s, p);   // 256 -> 960 / 16
+    return DFB_ERR_UNSUPPORTED;
+}
+
 int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const float *bias, const float *res,
            int64_t ldr, float *y, int64_t ldy, int64_t M, int G, int I, int Hh, int act, float oscale = 1.f,
            float ooffset = 0.f, unsigned short *y_hi = nullptr, unsigned short *y_lo = nullptr) {
     GlParams p{x, ldx, w, bias, res, ldr, y, ldy, M, G, I / G, Hh / G, act, oscale, ooffset, y_hi, y_lo};
     if ((p.Ig % 4) || (ldx % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: K not a multiple of 4");
     if (G > 1 && (p.Hg % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: group width %d not a multiple of 4", p.Hg);
+    // experimental weight-stationary kernel for the shapes of the shipped models (DFB_GL_WS=1)
+    static const bool gl_ws = getenv("DFB_GL_WS") && atoi(getenv("DFB_GL_WS"));
+    if (gl_ws && G > 1 && ldx % 4 == 0 && (((uintptr_t)x) & 15) == 0) {
+        int rc = run_gl_ws(s, p);
+        if (rc != DFB_ERR_UNSUPPORTED) return rc;
+    }
     int tiles = (p.Hg + kGlBN - 1) / kGlBN;
     int gpc = (p.Hg < kGlBN && kGlBN % p.Hg == 0) ? (kGlBN / p.Hg < G ? kGlBN / p.Hg : G) : 1;
     dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(((G + gpc - 1) / gpc) * tiles));
