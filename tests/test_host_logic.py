@@ -174,3 +174,15 @@ def test_bench_bookkeeping():
             names |= set(re.findall(r'DFB_PROF\("([^"]+)"', open(os.path.join(csrc, f)).read()))
     default_path = {n for n in names if not n.startswith(("k_gru", "k_gemm_tf32", "k_dwpw", "k_mask_out")) or n in ("k_gru_tc", "k_dwpw_bx")}
     assert default_path <= set(bench.KERNEL_MODEL) | {"k_grouped_linear"}, default_path - set(bench.KERNEL_MODEL)
+
+
+def test_experimental_gl_ws_index_mapping():
+    """Index-level numpy emulation of the (gated, experimental) weight-stationary grouped-linear kernel: thread ->
+    (row slot, group, columns), padded shared-memory layout, tile geometry -- every output written exactly once and
+    equal to the einsum, for the five grouped-linear shapes of the shipped models."""
+    import importlib.util
+    root = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("emu_gl_ws", os.path.join(root, "host", "emu_gl_ws.py"))
+    emu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emu)   # runs the five shapes on import and asserts
+    emu.run(5, 16, 32, 16, 2, seed=3)  # fewer rows than one tile
