@@ -85,6 +85,7 @@ SIGNATURES = {
     "dfb_enhance_out_len": (_I64, [_VP, _I64, _I]),
     "dfb_model_workspace_bytes": (_I64, [_VP]),
     "dfb_model_set_precision": (_I, [_VP, _I]),
+    "dfb_model_set_max_workspace": (_I, [_VP, _I64]),
     "dfb_debug_gru_timing": (_I, [_VP, _I, _VP]),
     "dfb_model_debug_fetch": (_I64, [_VP, C.c_char_p, _VP, _I64]),
 }

@@ -58,6 +58,8 @@ class ModelConfig:
     df_hidden_dim: int = 256
     df_num_layers: int = 3
     df_gru_skip: str = "none"
+    emb_gru_skip: str = "none"
+    emb_gru_skip_enc: str = "none"
     df_pathway_kernel_size_t: int = 1
     enc_concat: bool = False
     lin_groups: int = 1
@@ -148,6 +150,8 @@ def load_config(path: str, env: Optional[dict] = None) -> ModelConfig:
         c.enc_concat = get("enc_concat", False, _bool, S)
         c.lin_groups = get("linear_groups", 1, int, S)
         c.enc_lin_groups = get("enc_linear_groups", 16, int, S)
+        c.emb_gru_skip = get("emb_gru_skip", "none", str, S).lower()
+        c.emb_gru_skip_enc = get("emb_gru_skip_enc", "none", str, S).lower()
     else:  # deepfilternet2.py:26-75
         c.convt_kernel = c.conv_kernel  # deepfilternet2.py:225-228 uses conv_kernel for convt
         c.emb_num_layers = get("emb_num_layers", 2, int, S)
@@ -166,4 +170,18 @@ def load_config(path: str, env: Optional[dict] = None) -> ModelConfig:
         raise ValueError("hop_size * 2 <= fft_size required (libDF/src/lib.rs:111)")
     if c.df_n_iter != 1:
         raise NotImplementedError("df_n_iter != 1")
+    check_supported(c)
     return c
+
+
+def check_supported(c: "ModelConfig") -> None:
+    """Options the kernels do not implement must fail loudly instead of being dropped (all shipped
+    configs use emb_gru_skip* = none and df_gru_skip in {none, groupedlinear})."""
+    if c.model == "deepfilternet3":
+        if c.emb_gru_skip != "none" or c.emb_gru_skip_enc != "none":
+            raise NotImplementedError(
+                f"emb_gru_skip={c.emb_gru_skip!r} / emb_gru_skip_enc={c.emb_gru_skip_enc!r}: only 'none' is built "
+                "(deepfilternet3.py:125-133, 232-236)")
+        if c.df_gru_skip not in ("none", "groupedlinear"):
+            raise NotImplementedError(
+                f"df_gru_skip={c.df_gru_skip!r}: only 'none' and 'groupedlinear' are built (deepfilternet3.py:296-306)")

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,14 +56,31 @@ struct ProfScope {
 #define DFB_PROF(name, stream) dfb::ProfScope prof_scope__(name, stream)
 
 // Function attributes (dynamic shared memory limit, cluster size) are per device: launch sites set them the first
-// time they run on each device of the process.
+// time they run on each device of the process.  `first()` hands the caller a guard that holds the mutex while the
+// one-time setup runs, so a second host thread cannot launch before the attribute is in place:
+//     if (auto g = once.first()) { cudaFuncSetAttribute(...); }
 struct PerDeviceOnce {
-    std::atomic<unsigned long long> mask{0};
-    bool first() {
+    std::mutex mu;
+    std::atomic<unsigned long long> done{0};
+    struct Guard {
+        std::unique_lock<std::mutex> lk;
+        PerDeviceOnce *o = nullptr;
+        unsigned long long bit = 0;
+        Guard() = default;
+        Guard(Guard &&g) noexcept : lk(std::move(g.lk)), o(g.o), bit(g.bit) {}
+        explicit operator bool() const { return lk.owns_lock(); }
+        ~Guard() { if (lk.owns_lock()) o->done.fetch_or(bit, std::memory_order_release); }
+    };
+    Guard first() {
         int d = 0;
         cudaGetDevice(&d);
         const unsigned long long bit = 1ull << (d & 63);
-        return !(mask.fetch_or(bit) & bit);
+        Guard g;
+        if (done.load(std::memory_order_acquire) & bit) return g;
+        g.lk = std::unique_lock<std::mutex>(mu);
+        if (done.load(std::memory_order_acquire) & bit) { g.lk.unlock(); g.lk.release(); return g; }
+        g.o = this; g.bit = bit;
+        return g;
     }
 };
 

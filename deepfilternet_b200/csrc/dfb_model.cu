@@ -842,6 +842,8 @@ struct dfb_model {
     long long *gru_dbg = nullptr;  // device buffer for dfb_debug_gru_timing
     int precision = 0;  // 0: fp32 FFMA everywhere; 1: TF32 tensor cores (tcgen05) for the dense contractions
     Arena arena;
+    size_t max_workspace = size_t(24) << 30;  // dfb_enhance groups streams so that the arena stays below this
+    std::vector<int64_t> erb_widths;          // band table the model was built for (checked against the dfb_state)
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;             // DF decoder branch runs here, concurrently with the ERB decoder
     // forward() hops from the caller's stream onto `hi` (and `aux`), both at the greatest stream priority; `low`
@@ -867,7 +869,6 @@ static int need(const dfb_model *m, const char *name, int64_t numel, const float
 
 extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_config *cfg, const dfb_tensor *tensors,
                                 int n_tensors, const int64_t *erb_widths) {
-    (void)erb_widths;
     if (!out || !cfg || !tensors) return fail(DFB_ERR_INVALID, "null argument");
     *out = nullptr;
     if (cfg->conv_ch != kCh) return fail(DFB_ERR_UNSUPPORTED, "conv_ch = %d (built kernels: 64)", cfg->conv_ch);
@@ -884,6 +885,11 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
     dfb_model *m = new dfb_model();
     m->device = device;
     m->cfg = *cfg;
+    if (erb_widths) m->erb_widths.assign(erb_widths, erb_widths + cfg->nb_erb);
+    if (const char *e = getenv("DFB_MAX_WORKSPACE_MB")) {
+        const long long mb = atoll(e);
+        if (mb > 0) m->max_workspace = (size_t)mb << 20;
+    }
     // upload: one slab; GRU w_ih is stored transposed ([I][3H]) for the projection GEMM
     size_t total = 0;
     for (int i = 0; i < n_tensors; i++) total += ((size_t)tensors[i].numel * 4 + 255) & ~size_t(255);
@@ -1009,7 +1015,7 @@ int launch_gl_ws(cudaStream_t s, const GlParams &p) {
     q.R -= q.R % q.rs;
     const int smem = 2 * q.R * row_bytes;
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_gl_ws<IG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if (auto once_guard = attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_gl_ws<IG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     if (smem > 100 * 1024) return DFB_ERR_UNSUPPORTED;
     int dev = 0, num_sms = 0;
     DFB_CUDA(cudaGetDevice(&dev));
@@ -1065,7 +1071,7 @@ template <int H, int C>
 int launch_gru_t(cudaStream_t s, const GruParams &p, int ngroups) {
     constexpr int smem = (2 * kGruMaxBc * (H + 4) + 3 * (H / C) * (kGruMaxBc + 1)) * 4;
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) {
+    if (auto once_guard = attr_once.first()) {
         if (C > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru<H, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         DFB_CUDA(cudaFuncSetAttribute(k_gru<H, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
@@ -1162,7 +1168,7 @@ int run_dwpw(cudaStream_t s, DwPwParams p, int B, const float *w_sw = nullptr) {
     if (w_sw) return launch_dwpw_tc<MODE>(s, p, w_sw, B);
     static PerDeviceOnce attr_once;
     const int smem = (kCh * kCh + 128 * kLdA) * 4;
-    if (attr_once.first()) {
+    if (auto once_guard = attr_once.first()) {
         DFB_CUDA(cudaFuncSetAttribute(k_dwpw<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     p.NF = 128 / p.Fout;
@@ -1236,7 +1242,19 @@ extern "C" int dfb_model_forward(dfb_model *m, const float *d_feat_erb, const fl
     return rc;
 }
 
+static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in);
+
 static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in) {
+    const int rc = forward_body(m, arena, d_feat_erb, d_feat_spec, B, T, d_m, d_coefs, d_lsnr, d_alpha, s_in);
+    // an early return may leave work on the forked internal streams un-joined while the caller goes on to reuse
+    // the arena: drain the device before handing the error back (error path only)
+    if (rc) cudaDeviceSynchronize();
+    return rc;
+}
+
+static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
                         float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in) {
     const dfb_model_config &c = m->cfg;
     // DFB_SERIAL=1: everything on the caller's stream (profiling: per-kernel times without overlap)
@@ -1463,7 +1481,7 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if (fused_mask) return finish();
         static PerDeviceOnce attr_once;
         int smem = (kMaskWarps * 2 * (E + 2) * kMaskLd + c.conv_kt * 3 * kCh) * 4;
-        if (attr_once.first()) {  // sized for the largest supported configuration (nb_erb 64, kt 2)
+        if (auto once_guard = attr_once.first()) {  // sized for the largest supported configuration (nb_erb 64, kt 2)
             DFB_CUDA(cudaFuncSetAttribute(k_mask_out, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (kMaskWarps * 2 * (64 + 2) * kMaskLd + 2 * 3 * kCh) * 4));
         }
@@ -1476,11 +1494,25 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     return finish();
 }
 
+// The workspace is sized from the model's band layout but the DSP kernels index with the state's: they must agree.
+static int check_state(const dfb_model *m, const dfb_state *st) {
+    if (m->device != st->device) return fail(DFB_ERR_INVALID, "model and state live on different devices");
+    if (st->tb.E != m->cfg.nb_erb)
+        return fail(DFB_ERR_INVALID, "DF state has %d ERB bands, the model was built for %d", st->tb.E, m->cfg.nb_erb);
+    if (!m->erb_widths.empty())
+        for (int i = 0; i < m->cfg.nb_erb; i++)
+            if (m->erb_widths[i] != st->erb[i])
+                return fail(DFB_ERR_INVALID, "DF state's ERB band %d is %lld bins wide, the model was built for %lld", i,
+                            (long long)st->erb[i], (long long)m->erb_widths[i]);
+    return DFB_OK;
+}
+
 static int apply_mode(const dfb_model *m) { return m->cfg.model_kind == 2 ? 2 : 1; }
 
 extern "C" int dfb_apply(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_m, const float *d_coefs,
                          int64_t B, int64_t T, float *d_spec_e, void *stream) {
     if (!m || !st || !d_spec || !d_m || !d_coefs || !d_spec_e) return fail(DFB_ERR_INVALID, "null argument");
+    if (int rcs = check_state(m, st)) return rcs;
     DFB_CUDA(cudaSetDevice(m->device));
     dfb::ApplyParams p{};
     p.spec = (const float2 *)d_spec; p.m = d_m; p.coefs = d_coefs; p.audio = nullptr; p.spec_out = (float2 *)d_spec_e;
@@ -1492,6 +1524,7 @@ extern "C" int dfb_model_forward_full(dfb_model *m, dfb_state *st, const float *
                                       const float *d_feat_spec, int64_t B, int64_t T, float *d_spec_e, float *d_m,
                                       float *d_lsnr, float *d_coefs, float *d_alpha, void *stream) {
     if (!m || !st || !d_spec || !d_feat_erb || !d_feat_spec || !d_spec_e) return fail(DFB_ERR_INVALID, "null argument");
+    if (int rcs = check_state(m, st)) return rcs;
     DFB_CUDA(cudaSetDevice(m->device));
     const int64_t M = B * T;
     const int O2 = 2 * m->cfg.df_order;
@@ -1516,14 +1549,19 @@ extern "C" int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad) 
 }
 
 // enhance(): df/enhance.py:206-250.  Streams are processed in groups so that the workspace stays
-// below kMaxWorkspace; streams are independent (per-channel state reset, pyDF/src/lib.rs:56-58).
-constexpr size_t kMaxWorkspace = size_t(24) << 30;
+// below the model's workspace cap (24 GB by default; dfb_model_set_max_workspace / DFB_MAX_WORKSPACE_MB); streams
+// are independent (per-channel state reset, pyDF/src/lib.rs:56-58).
+extern "C" int dfb_model_set_max_workspace(dfb_model *m, int64_t bytes) {
+    if (!m || bytes <= 0) return fail(DFB_ERR_INVALID, "bad workspace cap");
+    m->max_workspace = (size_t)bytes;
+    return DFB_OK;
+}
 
 extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, int64_t B, int64_t T, int pad,
                            float atten_lim_db, float *d_out, void *stream) {
     if (!m || !st || !d_audio || !d_out) return fail(DFB_ERR_INVALID, "null argument");
     if (B <= 0 || T <= 0) return fail(DFB_ERR_INVALID, "empty input");
-    if (m->device != st->device) return fail(DFB_ERR_INVALID, "model and state live on different devices");
+    if (int rcs = check_state(m, st)) return rcs;
     DFB_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = (cudaStream_t)stream;
     const dfb_model_config &c = m->cfg;
@@ -1535,7 +1573,7 @@ extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, in
     const int64_t out_len = dfb_enhance_out_len(st, T, pad);
     const size_t per_stream = ((size_t)Tp + (size_t)Tf * (2 * F + E + 2 * Fd + E + (size_t)Fd * O2)) * 4 +
                               fwd_plan(c, (size_t)Tf, nullptr, nullptr) + 8192;
-    int64_t group = (int64_t)(kMaxWorkspace / per_stream);
+    int64_t group = (int64_t)(m->max_workspace / per_stream);
     if (group < 1) group = 1;
     if (group > B) group = B;
     if (group > 65535) group = 65535;

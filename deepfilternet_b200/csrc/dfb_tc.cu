@@ -1046,7 +1046,7 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     // per SM: request more than half of the shared memory to enforce it
     const int need = (int)sizeof(GruTcSmem<NS>) + 1024;
     const int smem = need > 120 * 1024 ? need : 120 * 1024;
-    if (attr_once.first()) {
+    if (auto once_guard = attr_once.first()) {
         DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     cudaLaunchConfig_t cfg{};
@@ -1132,7 +1132,7 @@ int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64
     if ((rc = make_map_bf16(&mxh, x_hi, M, K, ldx, kBxBM)) || (rc = make_map_bf16(&mxl, x_lo, M, K, ldx, kBxBM))) return rc;
     static PerDeviceOnce attr_once;
     const int smem = (int)sizeof(BxSmem) + 1024;
-    if (attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (auto once_guard = attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0, num_sms = 0;
     DFB_CUDA(cudaGetDevice(&dev));
     DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1162,7 +1162,7 @@ int launch_gemm_tf32(cudaStream_t s, const float *x, int64_t ldx, const float *w
     if ((rc = make_map(&ma, x, M, K, ldx, kTcBM)) || (rc = make_map(&mb, w_nk, N, K, K, BN))) return rc;
     static PerDeviceOnce attr_once;
     const int smem = (int)sizeof(TcSmem<BN>) + 1024;
-    if (attr_once.first()) {
+    if (auto once_guard = attr_once.first()) {
         DFB_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     dim3 grid((unsigned)((M + kTcBM - 1) / kTcBM), (unsigned)(N / BN));

@@ -76,10 +76,17 @@ def init_df(
     return model, df_state, suffix, ep
 
 
-def df_features(audio: Tensor, df: DF, nb_df: int, device=None, alpha: float = 0.99
+def df_features(audio: Tensor, df: DF, nb_df: int, device=None, alpha: Optional[float] = None
                 ) -> Tuple[Tensor, Tensor, Tensor]:
     """enhance.py:190-203: audio f32 CPU [C,T] -> (spec [C,1,Tf,F,2], erb_feat [C,1,Tf,E],
-    spec_feat [C,1,Tf,nb_df,2]); one fused device pass."""
+    spec_feat [C,1,Tf,nb_df,2]); one fused device pass.  ``alpha`` defaults to the reference's
+    ``get_norm_alpha()`` (df/utils.py:108-124) of the config the DF state was loaded with (``init_df`` /
+    ``load_model`` stash it on the DF object), else to the value for norm_tau = 1."""
+    if alpha is None:
+        alpha = getattr(df, "norm_alpha", None)
+    if alpha is None:
+        from .config import ModelConfig
+        alpha = ModelConfig(sr=df.sr(), hop_size=df.hop_size()).norm_alpha
     x = np.ascontiguousarray(audio.detach().cpu().numpy(), dtype=np.float32)
     if x.ndim != 2 or x.size == 0:
         raise RuntimeError("[df] Input array empty or not contiguous.")
@@ -123,12 +130,17 @@ def enhance_device(model: DfNet, df_state: DF, audio: Tensor, pad: bool = True,
                    atten_lim_db: Optional[float] = None, out: Optional[Tensor] = None) -> Tensor:
     """Device-resident variant of :func:`enhance`: ``audio`` is a CUDA tensor [B,T] on the model's
     device and the result stays there (asynchronous on the current stream)."""
-    if not audio.is_cuda or audio.dtype != torch.float32 or not audio.is_contiguous():
-        raise ValueError("enhance_device expects a contiguous float32 CUDA tensor")
+    if not audio.is_cuda or audio.dtype != torch.float32 or not audio.is_contiguous() or audio.dim() != 2:
+        raise ValueError("enhance_device expects a contiguous float32 CUDA tensor of shape [B, T]")
+    if audio.device != model.cuda_device:
+        raise ValueError(f"audio lives on {audio.device}, the model on {model.cuda_device}")
     b, t = audio.shape
     out_len = int(_lib.lib().dfb_enhance_out_len(df_state.handle, t, 1 if pad else 0))
     if out is None:
         out = torch.empty((b, out_len), dtype=torch.float32, device=audio.device)
+    elif (out.shape != (b, out_len) or out.dtype != torch.float32 or not out.is_cuda or out.device != audio.device
+          or not out.is_contiguous()):
+        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {(b, out_len)} on {audio.device}")
     lim = abs(float(atten_lim_db)) if atten_lim_db is not None else 0.0
     with torch.cuda.device(audio.device):
         stream = torch.cuda.current_stream(audio.device).cuda_stream

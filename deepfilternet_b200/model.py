@@ -79,6 +79,10 @@ class DfNet(nn.Module):
             cfg.sr, cfg.fft_size, cfg.hop_size, cfg.nb_erb, cfg.min_nb_erb_freqs, device=self._device)
         if self.df_state.device != self._device:
             raise ValueError("df_state lives on a different device than the model")
+        if (self.df_state.nb_erb() != cfg.nb_erb or self.df_state.fft_size() != cfg.fft_size
+                or self.df_state.hop_size() != cfg.hop_size):
+            raise ValueError("df_state was built with a different nb_erb / fft_size / hop_size than the model config")
+        self.df_state.norm_alpha = cfg.norm_alpha  # read by df_features (enhance.py:192)
         # keep the reference tensors (state_dict() parity); buffers, not parameters: inference only
         self._sd_names = []
         for k, v in state_dict.items():
@@ -146,6 +150,10 @@ class DfNet(nn.Module):
     @property
     def cuda_device(self) -> torch.device:
         return torch.device("cuda", self._device)
+
+    def set_max_workspace(self, nbytes: int) -> None:
+        """Cap of the per-call device workspace of enhance(): larger batches are processed in stream groups."""
+        check(_lib.lib().dfb_model_set_max_workspace(self._h, int(nbytes)))
 
     def workspace_bytes(self) -> int:
         return int(_lib.lib().dfb_model_workspace_bytes(self._h))

@@ -172,9 +172,16 @@ int dfb_enhance_host(dfb_model *m, dfb_state *st, const float *h_audio, int64_t 
                      float atten_lim_db, float *h_out);
 /* output length of dfb_enhance for a given input length */
 int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad);
-/* Arithmetic of the dense contractions (GRU input projections, 1x1 convs): 0 = IEEE fp32 FFMA,
- * 1 = TF32 tensor cores (tcgen05, fp32 accumulate).  Everything else is always fp32. */
+/* Arithmetic of the dense contractions -- a bit mask; everything that is not a contraction is always IEEE fp32:
+ *   bit 1 (2): GRU recurrence W_hh h on tcgen05 with BF16 hi/lo split operands (3 MMAs per product, fp32 accumulate)
+ *   bit 2 (4): GRU input projections W_ih x on the BF16x3 tcgen05 GEMM
+ *   bit 3 (8): 1x1 convs of the separable conv blocks and the grouped linears on the BF16x3 tcgen05 kernels
+ * 0 = FFMA everywhere; 14 = the default of the Python mirror (deepfilternet_b200/model.py set_precision).
+ * BF16x3 is ~2^-17 relative per product: 1e-7 .. 4e-7 RMS end to end against the fp32 oracle (bound 1e-4). */
 int dfb_model_set_precision(dfb_model *m, int mode);
+/* Cap (bytes) of the per-call device workspace of dfb_enhance; streams are processed in groups that fit below it
+ * (default 24 GB, or DFB_MAX_WORKSPACE_MB in the environment at dfb_model_create). */
+int dfb_model_set_max_workspace(dfb_model *m, int64_t bytes);
 /* Debug aid: steps > 0 with h_out == NULL arms clock64() phase stamps ([steps][8]) for the following
  * GRU launches; a second call with h_out != NULL copies the stamps of the last launch and disarms. */
 int dfb_debug_gru_timing(dfb_model *m, int steps, long long *h_out);

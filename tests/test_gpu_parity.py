@@ -313,3 +313,92 @@ def test_wide_batch_matches_oracle(states):
     assert out.shape == audio.shape
     for i in (0, 17, 33, 64, 69):  # both halves of a 32-stream cluster, the ragged last cluster
         assert rms(out[i:i + 1], O.enhance(sd, cfg.as_dict(), audio[i:i + 1])) < RMS_TOL, i
+
+
+# ------------------------------------------------------------------ BASELINE configs at size ----
+def _pretrained_or_random(name, kind, model_dir_path):
+    """(cfg, state_dict) of a shipped model when models/_ref travelled with the snapshot, else random weights."""
+    p = os.path.join(model_dir_path, name)
+    if os.path.isdir(os.path.join(p, "checkpoints")):
+        cfg = load_config(os.path.join(p, "config.ini"), env={})
+        cp, _ = find_checkpoint(os.path.join(p, "checkpoints"))
+        return cfg, load_state_dict_file(cp)
+    cfg = cfg_of(kind)
+    return cfg, random_state_dict(cfg, seed=3)
+
+
+@pytest.mark.parametrize("name,kind,B,seconds,rows", [
+    ("DeepFilterNet3", "dfn3", 128, 10, (0, 37, 90, 127)),     # cfg2: k_gru_tc<32> (DF decoder) over 1002 steps
+    ("DeepFilterNet2", "dfn2", 512, 10, (0, 200, 511)),        # cfg3
+    ("DeepFilterNet3_ll", "ll", 256, 10, (3, 255)),            # cfg4 per-GPU shard: H = 512 GRUs, kt = 2 convs
+    ("DeepFilterNet3", "dfn3", 24, 30, (5, 23)),               # cfg5 stream length: 3002 frames of state integration
+])
+def test_baseline_configs_at_size(states, model_dir, name, kind, B, seconds, rows):
+    """SURVEY 8d "parity gate on every config": the CUDA path at the BASELINE batch shapes against the oracle on a
+    sample of the streams (the oracle needs seconds per stream), plus finiteness / exact length of the whole batch."""
+    st, _ = states
+    if name == "DeepFilterNet3_ll":
+        cfg = cfg_of("ll")
+        sd = random_state_dict(cfg, seed=3)
+    else:
+        cfg, sd = _pretrained_or_random(name, kind, model_dir)
+    model = DfNet(cfg, sd, st)
+    audio = synth_audio(B, 48000 * seconds, seed=77, device="cuda")
+    out = enhance_device(model, st, audio)
+    torch.cuda.synchronize()
+    assert out.shape == audio.shape and torch.isfinite(out).all()
+    idx = list(rows)
+    ref = O.enhance(sd, cfg.as_dict(), audio[idx].cpu())
+    got = out[idx].cpu()
+    for j, i in enumerate(idx):
+        assert rms(got[j], ref[j]) < RMS_TOL, (name, i, rms(got[j], ref[j]))
+
+
+def test_stream_groups_with_ragged_last_group(states):
+    """dfb_enhance processes the batch in stream groups that fit the workspace cap: force three groups (16, 16, 8 of
+    40 streams) and require the same output as the single-group run, and the oracle on streams of every group."""
+    st, _ = states
+    cfg = cfg_of("dfn3")
+    sd = random_state_dict(cfg, seed=8)
+    model = DfNet(cfg, sd, st)
+    audio = synth_audio(40, 48000, seed=51, device="cuda")
+    full = enhance_device(model, st, audio).clone()
+    torch.cuda.synchronize()
+    ws_one = model.workspace_bytes()
+    per_stream = ws_one / 40
+    model.set_max_workspace(int(per_stream * 16.5))
+    grouped = enhance_device(model, st, audio)
+    torch.cuda.synchronize()
+    assert torch.equal(full, grouped) or rms(full.cpu(), grouped.cpu()) < 1e-7
+    host = enhance(model, st, audio.cpu())          # the host entry point takes the same grouped route
+    assert rms(host, full.cpu()) < 1e-7
+    for i in (0, 15, 16, 31, 32, 39):
+        assert rms(grouped[i:i + 1].cpu(), O.enhance(sd, cfg.as_dict(), audio[i:i + 1].cpu())) < RMS_TOL, i
+    model.set_max_workspace(24 << 30)
+
+
+@pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
+def test_whole_asset_rms_against_oracle(name, golden_dir, model_dir):
+    """Pretrained weights on the whole 10.6 s reference recording: RMS(out - oracle) <= 1e-4 (the SI-SDR KAT above
+    is a scalar with 1e-4 relative slack; this compares every sample)."""
+    import ref_harness as rh
+    model, st, _, _ = init_df(os.path.join(model_dir, name), log_level="ERROR")
+    noisy = torch.from_numpy(rh.read_wav(os.path.join(golden_dir, "assets", "noisy_snr0.wav")))
+    out = enhance(model, st, noisy, pad=True)
+    ref = O.enhance(model.state_dict(), model.cfg.as_dict(), noisy)
+    assert out.shape == ref.shape and rms(out, ref) < RMS_TOL
+
+
+def test_mismatched_df_state_is_rejected(states):
+    """A DF state with another band layout than the model's must be refused, not indexed out of bounds."""
+    st, _ = states
+    cfg = cfg_of("dfn3")
+    sd = random_state_dict(cfg, seed=1)
+    with pytest.raises(ValueError):
+        DfNet(cfg, sd, libdf.DF(48000, 960, 480, 24, 2))
+    model = DfNet(cfg, sd, st)
+    other = libdf.DF(48000, 960, 480, 32, 1)      # same band count, different widths (min_nb_erb_freqs = 1)
+    with pytest.raises(RuntimeError):
+        enhance(model, other, synth_audio(1, 4800, seed=1))
+    with pytest.raises(ValueError):
+        enhance_device(model, st, synth_audio(2, 4800, seed=1).cuda(), out=torch.empty(2, 100, device="cuda"))
