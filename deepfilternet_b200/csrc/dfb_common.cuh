@@ -152,13 +152,19 @@ int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float 
 int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaStream_t s);
 // tensor-core GRU recurrence, H = 256 (dfb_tc.cu)
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
-                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg = nullptr, int wide = 0);
+                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg = nullptr, int wide = 0,
+                  int planes_res = 0);
 // BF16x3 tcgen05 GEMM on hi/lo planes (dfb_tc.cu)
 int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64_t ldx, const void *w_hi, const void *w_lo,
                        const float *bias, float *y, int64_t ldy, int64_t M, int N, int K);
-// tcgen05 TF32 GEMM (dfb_tc.cu): Y[M,N] = act(X[M,K] . W[N,K]^T + bias)
-int launch_gemm_tf32(cudaStream_t s, const float *x, int64_t ldx, const float *w_nk, const float *bias, float *y,
-                     int64_t ldy, int64_t M, int N, int K, int act);
+// BF16x3 tcgen05 grouped linear on hi/lo planes + host-packed weight image (dfb_gl.cu); DFB_ERR_UNSUPPORTED when the
+// shape is outside the kernel (the caller falls back to the FFMA kernel)
+int launch_gl_bx(cudaStream_t s, const unsigned short *x_hi, const unsigned short *x_lo, int64_t ldx, const float *w_img,
+                 const float *res, int64_t ldr, float *y, int64_t ldy, unsigned short *y_hi, unsigned short *y_lo, int64_t ldp,
+                 int64_t M, int G, int Ig, int Hg, int act, float oscale, float ooffset);
+bool gl_bx_geometry(int G, int Ig, int Hg, int *gpc_out, int *hgp_out, int *stages_out);
+// fp32 [M][K] -> BF16 hi / lo planes [M][K]
+int launch_to_planes(cudaStream_t s, const float *x, int64_t ldx, int64_t M, int K, unsigned short *hi, unsigned short *lo);
 }  // namespace dfb
 
 struct dfb_state {

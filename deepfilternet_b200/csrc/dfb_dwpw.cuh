@@ -34,7 +34,8 @@ struct DwPwParams {
     const float *dw;      // [kt][3][64]
     const float *pw;      // [64][64]
     const float *bias;    // [64]
-    float *out;           // [B,T,Fout,64]
+    float *out;           // [B,T,Fout,64] (may be null when only the BF16 planes are wanted)
+    unsigned short *out_hi, *out_lo;  // optional BF16 hi / lo planes of `out` (same indexing): operand of a tcgen05 consumer
     int64_t in_fs, path_fs, out_fs;  // frame strides (floats)
     int T, Fin, Fout, kt, NF, lookahead;
     int fo_magic;         // ceil(65536 / Fout): r / Fout == (r * fo_magic) >> 16 for r < 128 (tensor-core kernel)

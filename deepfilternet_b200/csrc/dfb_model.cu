@@ -320,127 +320,6 @@ __global__ void __launch_bounds__(256) k_grouped_linear(GlParams p) {
     }
 }
 
-// ------------------------------------------------- grouped linear, weight-stationary (experimental) ----
-// Same contract as k_grouped_linear.  EXPERIMENTAL (DFB_GL_WS=1, off by default, not yet validated on a GPU):
-// every thread keeps the weights of its CPT output columns (IG x CPT values) in registers for the whole kernel,
-// persistent CTAs stream row tiles through a cp.async double buffer, and a row's inputs are read from shared
-// memory as broadcasts (all threads of a group read the same address; groups are padded to IG + 4 floats so that the
-// groups of a warp hit different banks).  Motivation (ncu): the tiled kernel spends two thirds of its instructions
-// outside the FFMA loop and exposes the global-load latency of every tile.
-struct GlWsGeom {
-    int tpg;    // threads per group (power of two >= ceil(Hg / CPT))
-    int gcta;   // groups per CTA (grid.y = G / gcta)
-    int rs;     // row slots = 256 / (gcta * tpg)
-    int R;      // rows per tile
-};
-
-template <int IG, int CPT>
-__global__ void __launch_bounds__(256, (IG * CPT > 80) ? 1 : 2) k_gl_ws(GlParams p, GlWsGeom q) {
-    extern __shared__ __align__(16) float gl_smem[];
-    constexpr int GS = IG + 4;                    // padded group stride (floats)
-    const int XP = q.gcta * GS;                   // padded row pitch (floats)
-    const int tid = threadIdx.x;
-    const int per_slot = q.gcta * q.tpg;
-    const int slot = tid / per_slot, within = tid - slot * per_slot;
-    const int gl = within / q.tpg, tc = within - gl * q.tpg;
-    const int g = blockIdx.y * q.gcta + gl;       // global group
-    const int col0 = tc * CPT;                    // first in-group column of this thread
-    // ---- weights of this thread's columns -> registers
-    float w[IG][CPT];
-#pragma unroll
-    for (int k = 0; k < IG; k++)
-#pragma unroll
-        for (int c = 0; c < CPT; c++)
-            w[k][c] = (col0 + c < p.Hg) ? __ldg(p.w + ((int64_t)g * IG + k) * p.Hg + col0 + c) : 0.f;
-    float bias[CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; c++) bias[c] = (p.bias && col0 + c < p.Hg) ? __ldg(p.bias + g * p.Hg + col0 + c) : 0.f;
-    const int64_t ntiles = (p.M + q.R - 1) / q.R;
-    const int cpr = q.gcta * (IG / 4);            // 16-byte chunks per row
-    const int nchunks = q.R * cpr;
-    const int64_t xcol0 = (int64_t)blockIdx.y * q.gcta * IG;
-    auto prefetch = [&](int64_t tile, float *buf) {
-        const int64_t m0 = tile * q.R;
-        for (int idx = tid; idx < nchunks; idx += 256) {
-            const int r = idx / cpr, c = idx - r * cpr;
-            const int cg = c / (IG / 4), k4 = c - cg * (IG / 4);
-            float *dst = buf + r * XP + cg * GS + k4 * 4;
-            const int64_t m = m0 + r;
-            if (m < p.M) {
-                const float *src = p.x + m * p.ldx + xcol0 + cg * IG + k4 * 4;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-            } else {
-                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    float *bufs[2] = {gl_smem, gl_smem + q.R * XP};
-    int64_t tile = blockIdx.x;
-    if (tile < ntiles) prefetch(tile, bufs[0]);
-    for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
-        float *cur = (it & 1) ? bufs[1] : bufs[0];
-        float *nxt = (it & 1) ? bufs[0] : bufs[1];
-        if (tile + gridDim.x < ntiles) {
-            prefetch(tile + gridDim.x, nxt);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const int64_t m0 = tile * q.R;
-        for (int r = slot; r < q.R; r += q.rs) {
-            const int64_t m = m0 + r;
-            if (m >= p.M || slot >= q.rs) break;
-            const float *xs = cur + r * XP + gl * GS;
-            float acc[CPT], acc2[CPT];  // two chains per column: a lone accumulator would serialise IG dependent FMAs
-#pragma unroll
-            for (int c = 0; c < CPT; c++) acc[c] = acc2[c] = 0.f;
-#pragma unroll
-            for (int k = 0; k < IG; k += 4) {
-                const float4 xv = *reinterpret_cast<const float4 *>(xs + k);
-#pragma unroll
-                for (int c = 0; c < CPT; c++) {
-                    acc[c] += xv.x * w[k][c];
-                    acc2[c] += xv.y * w[k + 1][c];
-                    acc[c] += xv.z * w[k + 2][c];
-                    acc2[c] += xv.w * w[k + 3][c];
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < CPT; c++) acc[c] += acc2[c];
-            const int colbase = g * p.Hg + col0;
-            float v[CPT];
-#pragma unroll
-            for (int c = 0; c < CPT; c++) {
-                v[c] = act_apply(acc[c] + bias[c], p.act) * p.oscale + p.ooffset;
-                if (p.res && col0 + c < p.Hg) v[c] += p.res[m * p.ldr + colbase + c];
-            }
-            float *dst = p.y + m * p.ldy + colbase;
-            const bool full = col0 + CPT <= p.Hg;
-            if (CPT == 4 && full && (((uintptr_t)dst) & 15) == 0) {
-                *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[CPT > 1 ? 1 : 0], v[CPT > 2 ? 2 : 0], v[CPT > 3 ? 3 : 0]);
-            } else if (CPT == 2 && full && (((uintptr_t)dst) & 7) == 0) {
-                *reinterpret_cast<float2 *>(dst) = make_float2(v[0], v[CPT > 1 ? 1 : 0]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < CPT; c++)
-                    if (col0 + c < p.Hg) dst[c] = v[c];
-            }
-            if (p.y_hi) {
-#pragma unroll
-                for (int c = 0; c < CPT; c++) {
-                    if (col0 + c >= p.Hg) continue;
-                    const __nv_bfloat16 hb = __float2bfloat16_rn(v[c]);
-                    p.y_hi[m * p.ldy + colbase + c] = __bfloat16_as_ushort(hb);
-                    p.y_lo[m * p.ldy + colbase + c] = __bfloat16_as_ushort(__float2bfloat16_rn(v[c] - __bfloat162float(hb)));
-                }
-            }
-        }
-        __syncthreads();  // everyone is done with `cur` before the next iteration prefetches into it
-    }
-}
-
 // ------------------------------------------------------------------- GRU recurrence ----
 // torch.nn.GRU cell (gate order r, z, n; modules.py:684,723):
 //   r = s(xr + Whr h + bhr), z = s(xz + Whz h + bhz), n = tanh(xn + r (Whn h + bhn)), h' = (1-z) n + z h
@@ -840,7 +719,6 @@ struct dfb_model {
     int proj_tc = 0; // 1: GRU input projections on the BF16x3 tcgen05 GEMM (needs gru_tc)
     int gru_tc = 0;  // 1: tensor-core recurrence (BF16 hi/lo split operands) for H = 256
     long long *gru_dbg = nullptr;  // device buffer for dfb_debug_gru_timing
-    int precision = 0;  // 0: fp32 FFMA everywhere; 1: TF32 tensor cores (tcgen05) for the dense contractions
     Arena arena;
     size_t max_workspace = size_t(24) << 30;  // dfb_enhance groups streams so that the arena stays below this
     std::vector<int64_t> erb_widths;          // band table the model was built for (checked against the dfb_state)
@@ -974,11 +852,10 @@ extern "C" int dfb_debug_gru_timing(dfb_model *m, int steps, long long *h_out) {
 }
 
 extern "C" int dfb_model_set_precision(dfb_model *m, int mode) {
-    if (!m || mode < 0 || mode > 15) return fail(DFB_ERR_INVALID, "precision mode out of range");
-    m->precision = mode & 1;   // bit 0: TF32 tcgen05 for the dense feed-forward contractions
+    if (!m || mode < 0 || mode > 15 || (mode & 1)) return fail(DFB_ERR_INVALID, "precision mode out of range (bit 0 is reserved)");
     m->gru_tc = (mode >> 1) & 1;  // bit 1: tensor-core GRU recurrence (BF16x3 split, ~fp32 accurate)
     m->proj_tc = (mode >> 2) & 1; // bit 2: GRU input projections on the BF16x3 tcgen05 GEMM
-    m->conv_tc = (mode >> 3) & 1; // bit 3: 1x1 convs of the separable blocks on the BF16x3 tcgen05 path
+    m->conv_tc = (mode >> 3) & 1; // bit 3: 1x1 convs of the separable blocks and the grouped linears on the BF16x3 tcgen05 kernels
     return DFB_OK;
 }
 
@@ -998,61 +875,12 @@ extern "C" int64_t dfb_model_workspace_bytes(const dfb_model *m) { return m ? (i
 
 namespace {
 
-template <int IG, int CPT>
-int launch_gl_ws(cudaStream_t s, const GlParams &p) {
-    GlWsGeom q;
-    const int need = (p.Hg + CPT - 1) / CPT;
-    q.tpg = 1;
-    while (q.tpg < need) q.tpg *= 2;
-    if (q.tpg > 256) return DFB_ERR_UNSUPPORTED;
-    q.gcta = 256 / q.tpg < p.G ? 256 / q.tpg : p.G;
-    if (p.G % q.gcta) return DFB_ERR_UNSUPPORTED;
-    q.rs = 256 / (q.gcta * q.tpg);
-    const int row_bytes = q.gcta * (IG + 4) * 4;
-    q.R = 40 * 1024 / row_bytes;
-    if (q.R > 32) q.R = 32;
-    if (q.R < q.rs) q.R = q.rs;
-    q.R -= q.R % q.rs;
-    const int smem = 2 * q.R * row_bytes;
-    static PerDeviceOnce attr_once;
-    if (auto once_guard = attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_gl_ws<IG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    if (smem > 100 * 1024) return DFB_ERR_UNSUPPORTED;
-    int dev = 0, num_sms = 0;
-    DFB_CUDA(cudaGetDevice(&dev));
-    DFB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    const int64_t ntiles = (p.M + q.R - 1) / q.R;
-    const int gy = p.G / q.gcta;
-    int64_t gx = (int64_t)2 * num_sms / gy;
-    if (gx < 1) gx = 1;
-    if (gx > ntiles) gx = ntiles;
-    DFB_PROF("k_gl_ws", s);
-    k_gl_ws<IG, CPT><<<dim3((unsigned)gx, (unsigned)gy), 256, smem, s>>>(p, q);
-    DFB_LAUNCH_CHECK();
-    return DFB_OK;
-}
-
-// shapes of the shipped models; anything else falls back to k_grouped_linear
-int run_gl_ws(cudaStream_t s, const GlParams &p) {
-    if (p.Ig == 96 && p.Hg == 16) return launch_gl_ws<96, 1>(s, p);   // df_fc_emb
-    if (p.Ig == 32 && p.Hg == 16) return launch_gl_ws<32, 2>(s, p);   // 512 -> 256 / 16
-    if (p.Ig == 64 && p.Hg == 32) return launch_gl_ws<64, 1>(s, p);   // 512 -> 256 / 8
-    if (p.Ig == 16 && p.Hg == 32) return launch_gl_ws<16, 2>(s, p);   // 256 -> 512 / 16
-    if (p.Ig == 16 && p.Hg == 60) return launch_gl_ws<16, 4>(s, p);   // 256 -> 960 / 16
-    return DFB_ERR_UNSUPPORTED;
-}
-
 int run_gl(cudaStream_t s, const float *x, int64_t ldx, const float *w, const float *bias, const float *res,
            int64_t ldr, float *y, int64_t ldy, int64_t M, int G, int I, int Hh, int act, float oscale = 1.f,
            float ooffset = 0.f, unsigned short *y_hi = nullptr, unsigned short *y_lo = nullptr) {
     GlParams p{x, ldx, w, bias, res, ldr, y, ldy, M, G, I / G, Hh / G, act, oscale, ooffset, y_hi, y_lo};
     if ((p.Ig % 4) || (ldx % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: K not a multiple of 4");
     if (G > 1 && (p.Hg % 4)) return fail(DFB_ERR_UNSUPPORTED, "grouped linear: group width %d not a multiple of 4", p.Hg);
-    // experimental weight-stationary kernel for the shapes of the shipped models (DFB_GL_WS=1)
-    static const bool gl_ws = getenv("DFB_GL_WS") && atoi(getenv("DFB_GL_WS"));
-    if (gl_ws && G > 1 && ldx % 4 == 0 && (((uintptr_t)x) & 15) == 0) {
-        int rc = run_gl_ws(s, p);
-        if (rc != DFB_ERR_UNSUPPORTED) return rc;
-    }
     int tiles = (p.Hg + kGlBN - 1) / kGlBN;
     int gpc = (p.Hg < kGlBN && kGlBN % p.Hg == 0) ? (kGlBN / p.Hg < G ? kGlBN / p.Hg : G) : 1;
     dim3 grid((unsigned)((M + kGlBM - 1) / kGlBM), (unsigned)(((G + gpc - 1) / gpc) * tiles));
@@ -1105,7 +933,9 @@ int pick_bc(int B, int max_clusters) {
 int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, const float *x, int in_dim,
             const float *res_last, float *y, float *xproj, float *tmp_h, int B, int T,
             unsigned short *x_hi = nullptr, unsigned short *x_lo = nullptr, unsigned short *pl_hi = nullptr,
-            unsigned short *pl_lo = nullptr, int wide = 0) {
+            unsigned short *pl_lo = nullptr, int wide = 0, unsigned short *out_hi = nullptr, unsigned short *out_lo = nullptr,
+            bool *out_planes_ok = nullptr) {
+    if (out_planes_ok) *out_planes_ok = false;
     const int64_t M = (int64_t)B * T;
     const float *cur_in = x;
     int cur_dim = in_dim;
@@ -1125,10 +955,6 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
                 (rc = need(m, (base + ".w_ih_lo").c_str(), (int64_t)3 * H * cur_dim / 2, &w_lo)))
                 return rc;
             rc = launch_gemm_bf16x3(s, cur_hi, cur_lo, cur_dim, w_hi, w_lo, b_ih, xproj, 3 * H, M, 3 * H, cur_dim);
-        } else if (m->precision == 1) {
-            const float *w_ih;
-            if ((rc = need(m, (base + ".w_ih").c_str(), (int64_t)3 * H * cur_dim, &w_ih))) return rc;
-            rc = launch_gemm_tf32(s, cur_in, cur_dim, w_ih, b_ih, xproj, 3 * H, M, 3 * H, cur_dim, ACT_NONE);
         } else {
             rc = run_gl(s, cur_in, cur_dim, w_ih_t, b_ih, nullptr, 0, xproj, 3 * H, M, 1, cur_dim, 3 * H, ACT_NONE);
         }
@@ -1136,9 +962,12 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         float *dst = (l == layers - 1) ? y : tmp_h;
         GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, 0, m->gru_dbg};
         if (H == 256 && m->gru_tc) {
-            const bool planes = tc_proj && l < layers - 1;
-            rc = launch_gru_tc(s, xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, planes ? pl_hi : nullptr,
-                               planes ? pl_lo : nullptr, B, T, m->gru_dbg, wide);
+            const bool last = l == layers - 1;
+            const bool planes = last ? out_hi != nullptr : tc_proj;
+            // the last layer's planes feed a grouped linear and include the residual; the others feed the next projection
+            rc = launch_gru_tc(s, xproj, w_hh, b_hh, last ? res_last : nullptr, dst, planes ? (last ? out_hi : pl_hi) : nullptr,
+                               planes ? (last ? out_lo : pl_lo) : nullptr, B, T, m->gru_dbg, wide, last ? 1 : 0);
+            if (last && planes && out_planes_ok) *out_planes_ok = true;
             cur_hi = pl_hi; cur_lo = pl_lo;
         } else if (H == 256) {
             p.Bc = pick_bc(B, 148 / 4);
@@ -1190,6 +1019,8 @@ struct FwdBufs {
     // second set of GRU scratch: the DF decoder runs concurrently with the ERB decoder on another stream
     float *g_a2, *g_h2, *xproj2, *dfskip;
     unsigned short *ga2_hi, *ga2_lo, *gh2_hi, *gh2_lo;
+    // BF16 hi / lo planes of the grouped linears' inputs (tensor-core path): c1, emb_in, GRU outputs, emb
+    unsigned short *c1_hi, *c1_lo, *embin_hi, *embin_lo, *gb_hi, *gb_lo, *emb_hi, *emb_lo, *dfc_hi, *dfc_lo;
 };
 
 // Carves the activations of `M` frames out of `a` (or only counts bytes when a == nullptr).
@@ -1219,6 +1050,12 @@ static size_t fwd_plan(const dfb_model_config &c, size_t M, Arena *a, FwdBufs *f
     t.g_a2 = take(M * Hmax); t.g_h2 = take(M * Hmax); t.xproj2 = take(M * 3 * Hmax); t.dfskip = take(M * Hmax);
     t.ga2_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.ga2_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
     t.gh2_hi = reinterpret_cast<unsigned short *>(take(M * Hmax / 2)); t.gh2_lo = reinterpret_cast<unsigned short *>(take(M * Hmax / 2));
+    auto take16 = [&](size_t n) { return reinterpret_cast<unsigned short *>(take((n + 1) / 2)); };
+    t.c1_hi = take16(M * (Fd / 2) * kCh); t.c1_lo = take16(M * (Fd / 2) * kCh);
+    t.embin_hi = take16(M * emb_in_dim); t.embin_lo = take16(M * emb_in_dim);
+    t.gb_hi = take16(M * Hmax); t.gb_lo = take16(M * Hmax);
+    t.emb_hi = take16(M * emb_dim); t.emb_lo = take16(M * emb_dim);
+    t.dfc_hi = take16(M * Hmax); t.dfc_lo = take16(M * Hmax);
     if (f) *f = t;
     return bytes + 4096;
 }
@@ -1281,7 +1118,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     int rc;
     FwdBufs f{};
     fwd_plan(c, (size_t)M, &arena, &f);
-    if (!f.gh2_lo || !f.dfskip) return fail(DFB_ERR_OOM, "forward workspace exhausted for %lld frames", (long long)M);
+    if (!f.gh2_lo || !f.dfskip || !f.dfc_lo) return fail(DFB_ERR_OOM, "forward workspace exhausted for %lld frames", (long long)M);
     m->dbg.clear();
     m->dbg["e0"] = {f.e0, M * E * kCh}; m->dbg["e1"] = {f.e1, M * (E / 2) * kCh}; m->dbg["e2"] = {f.e2, M * (E / 4) * kCh};
     m->dbg["e3"] = {f.e3, c.enc_concat ? M * emb_in_dim : M * ED}; m->dbg["c0"] = {f.c0, M * Fd * kCh};
@@ -1291,6 +1128,46 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     m->dbg["g_a"] = {f.g_a, M * (H > Hd ? H : Hd)}; m->dbg["g_b"] = {f.g_b, M * (H > Hd ? H : Hd)};
     m->dbg["xproj"] = {f.xproj, M * 3 * (H > Hd ? H : Hd)};
     const int64_t e3_fs = c.enc_concat ? 2 * ED : ED;
+    // BF16 hi / lo planes [M][K] (row pitch `ld` elements) of a grouped linear's input; `ok` = already written by the producer
+    struct Pl { unsigned short *hi, *lo; int64_t ld; bool ok; };
+    Pl pl_c1{f.c1_hi, f.c1_lo, (int64_t)Fd / 2 * kCh, false}, pl_embin{f.embin_hi, f.embin_lo, emb_in_dim, false},
+       pl_gb{f.gb_hi, f.gb_lo, H, false}, pl_emb{f.emb_hi, f.emb_lo, emb_dim, false}, pl_dfc{f.dfc_hi, f.dfc_lo, Hd, false},
+       pl_ga{f.ga_hi, f.ga_lo, H, false}, pl_ga2{f.ga2_hi, f.ga2_lo, Hd, false};
+    const bool gl_tc = m->conv_tc != 0;
+    // planes of `x` for a tensor-core consumer: converts on `st` unless the producer already wrote them
+    auto ensure_planes = [&](cudaStream_t st, const float *x, int64_t ldx, int K, Pl &pl) -> int {
+        if (pl.ok) return DFB_OK;
+        if (pl.ld != K) return fail(DFB_ERR_INVALID, "plane pitch mismatch");
+        int r = launch_to_planes(st, x, ldx, M, K, pl.hi, pl.lo);
+        if (!r) pl.ok = true;
+        return r;
+    };
+    // grouped linear `wname` ([G][I/G][Hh/G]): the BF16x3 tcgen05 kernel when the tensor-core bit is set and the shape is
+    // built, else the FFMA kernel.  xin: planes of x (converted on demand); yout (optional): planes of y to produce,
+    // ycol: column offset of y inside its plane buffer
+    auto gl = [&](cudaStream_t st, const char *wname, const float *x, int64_t ldx, Pl *xin, int G, int I, int Hh, int act,
+                  const float *res, int64_t ldr, float *y, int64_t ldy, Pl *yout, int64_t ycol = 0) -> int {
+        const float *w;
+        int r;
+        if ((r = need(m, wname, (int64_t)I * Hh / G, &w))) return r;
+        unsigned short *yh = yout ? yout->hi + ycol : nullptr, *yl = yout ? yout->lo + ycol : nullptr;
+        const std::string bx = std::string(wname) + "_bx";
+        int gpc, hgp, stages;
+        if (gl_tc && xin && m->get(bx) && gl_bx_geometry(G, I / G, Hh / G, &gpc, &hgp, &stages)) {
+            if ((r = ensure_planes(st, x, ldx, I, *xin))) return r;
+            r = launch_gl_bx(st, xin->hi, xin->lo, xin->ld, m->get(bx), res, ldr, y, ldy, yh, yl, yout ? yout->ld : 0, M, G, I / G,
+                             Hh / G, act, 1.f, 0.f);
+            if (r != DFB_ERR_UNSUPPORTED) {
+                if (!r && yout && (ycol == 0 || true)) yout->ok = true;
+                return r;
+            }
+        }
+        // NB: the FFMA kernel's plane output shares y's pitch, so it can only serve plane buffers with ld == ldy
+        const bool ffma_planes = yout && yout->ld == ldy;
+        r = run_gl(st, x, ldx, w, nullptr, res, ldr, y, ldy, M, G, I, Hh, act, 1.f, 0.f, ffma_planes ? yh : nullptr, ffma_planes ? yl : nullptr);
+        if (!r && yout) yout->ok = ffma_planes;
+        return r;
+    };
 
     // ---- encoder (deepfilternet3.py:166-185)
     {
@@ -1336,7 +1213,12 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             DFB_CUDA(cudaEventRecord(m->ev_c0, sa));
         }
         p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
-        if ((rc = blk("enc.df_conv1", p)) || (rc = run_dwpw<DW_S2>(sa, p, B, pw_sw))) return rc;
+        if ((rc = blk("enc.df_conv1", p))) return rc;
+        if (pw_sw && gl_tc) {  // c1 only feeds df_fc_emb: write its BF16 planes instead of the fp32 tensor
+            p.out = nullptr; p.out_hi = pl_c1.hi; p.out_lo = pl_c1.lo; pl_c1.ok = true;
+            m->dbg.erase("c1");
+        }
+        if ((rc = run_dwpw<DW_S2>(sa, p, B, pw_sw))) return rc;
         DFB_CUDA(cudaEventRecord(m->ev_join_enc, sa));
         // DF pathway conv (needs c0 only; its result is consumed by the very last DF-decoder kernel): on the
         // low-priority stream, so its CTAs only take SMs that the critical path -- the encoder convs now, the GRU
@@ -1366,34 +1248,39 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         p = mk(f.e1, E / 2, (int64_t)E / 2 * kCh, f.e2, E / 4, (int64_t)E / 4 * kCh, c.conv_kt);
         if ((rc = blk("enc.erb_conv2", p)) || (rc = run_dwpw<DW_S2>(s, p, B, pw_sw))) return rc;
         p = mk(f.e2, E / 4, (int64_t)E / 4 * kCh, f.e3, E / 4, e3_fs, c.conv_kt);
-        if ((rc = blk("enc.erb_conv3", p)) || (rc = run_dwpw<DW_S1>(s, p, B, pw_sw))) return rc;
+        if ((rc = blk("enc.erb_conv3", p))) return rc;
+        if (pw_sw && gl_tc && c.enc_concat) { p.out_hi = pl_embin.hi; p.out_lo = pl_embin.lo; }  // DFN2: e3 is the first half of emb_in
+        if ((rc = run_dwpw<DW_S1>(s, p, B, pw_sw))) return rc;
 
     }
     DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join_enc, 0));  // c0 / c1 ready
     {
         // cemb = relu(df_fc_emb(c1 flat)); emb_in = e3 flat + cemb  (DFN2: concat)
-        const float *w;
         const int I = Fd / 2 * kCh;
-        if ((rc = need(m, "enc.df_fc_emb.gl", (int64_t)I * ED / c.g_df_fc_emb, &w))) return rc;
-        if (c.enc_concat)
-            rc = run_gl(s, f.c1, I, w, nullptr, nullptr, 0, f.emb_in + ED, emb_in_dim, M, c.g_df_fc_emb, I, ED, ACT_RELU);
-        else
-            rc = run_gl(s, f.c1, I, w, nullptr, f.e3, ED, f.emb_in, emb_in_dim, M, c.g_df_fc_emb, I, ED, ACT_RELU);
+        const bool e3_planes = pw_sw && gl_tc && c.enc_concat;
+        if (c.enc_concat) {
+            rc = gl(s, "enc.df_fc_emb.gl", f.c1, I, &pl_c1, c.g_df_fc_emb, I, ED, ACT_RELU, nullptr, 0, f.emb_in + ED, emb_in_dim,
+                    &pl_embin, ED);
+            pl_embin.ok = pl_embin.ok && e3_planes;  // both halves must have been written as planes
+        } else {
+            rc = gl(s, "enc.df_fc_emb.gl", f.c1, I, &pl_c1, c.g_df_fc_emb, I, ED, ACT_RELU, f.e3, ED, f.emb_in, emb_in_dim, &pl_embin);
+        }
         if (rc) return rc;
     }
     {
         // enc.emb_gru: linear_in + ReLU -> GRU -> [linear_out + ReLU]
-        const float *w_in, *w_out = nullptr;
-        if ((rc = need(m, "enc.emb_gru.in.gl", (int64_t)emb_in_dim * H / c.g_enc_in, &w_in))) return rc;
-        if ((rc = run_gl(s, f.emb_in, emb_in_dim, w_in, nullptr, nullptr, 0, f.g_a, H, M, c.g_enc_in, emb_in_dim, H, ACT_RELU, 1.f, 0.f,
-                         f.ga_hi, f.ga_lo))) return rc;
+        if ((rc = gl(s, "enc.emb_gru.in.gl", f.emb_in, emb_in_dim, &pl_embin, c.g_enc_in, emb_in_dim, H, ACT_RELU, nullptr, 0, f.g_a, H,
+                     &pl_ga))) return rc;
         float *gout = c.g_enc_out ? f.g_b : f.emb;
+        Pl &pl_gout = c.g_enc_out ? pl_gb : pl_emb;
         if ((rc = run_gru(m, s, "enc.emb_gru", c.enc_gru_layers, H, f.g_a, H, nullptr, gout, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
-                          f.gh_hi, f.gh_lo))) return rc;
+                          f.gh_hi, f.gh_lo, 0, gl_tc ? pl_gout.hi : nullptr, gl_tc ? pl_gout.lo : nullptr, &pl_gout.ok))) return rc;
         if (c.g_enc_out) {
-            if ((rc = need(m, "enc.emb_gru.out.gl", (int64_t)H * ED / c.g_enc_out, &w_out))) return rc;
-            if ((rc = run_gl(s, f.g_b, H, w_out, nullptr, nullptr, 0, f.emb, emb_dim, M, c.g_enc_out, H, ED, ACT_RELU))) return rc;
+            if ((rc = gl(s, "enc.emb_gru.out.gl", f.g_b, H, &pl_gb, c.g_enc_out, H, ED, ACT_RELU, nullptr, 0, f.emb, emb_dim, &pl_emb)))
+                return rc;
         }
+        // the decoders read emb's planes on two streams: make sure they exist before the fork
+        if (gl_tc && (rc = ensure_planes(s, f.emb, emb_dim, emb_dim, pl_emb))) return rc;
         if (d_lsnr) {
             const float *lw, *lb;
             if ((rc = need(m, "enc.lsnr.w", emb_dim, &lw)) || (rc = need(m, "enc.lsnr.b", 1, &lb))) return rc;
@@ -1408,26 +1295,23 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     // DF branch's tail, which is the critical path of the decoder phase
     const bool early_skip = c.g_df_skip && c.model_kind != 2;
     if (early_skip) {
-        const float *w_skip;
-        if ((rc = need(m, "df_dec.df_skip.gl", (int64_t)emb_dim * Hd / c.g_df_skip, &w_skip))) return rc;
-        if ((rc = run_gl(s, f.emb, emb_dim, w_skip, nullptr, nullptr, 0, f.dfskip, Hd, M, c.g_df_skip, emb_dim, Hd, ACT_NONE))) return rc;
+        if ((rc = gl(s, "df_dec.df_skip.gl", f.emb, emb_dim, &pl_emb, c.g_df_skip, emb_dim, Hd, ACT_NONE, nullptr, 0, f.dfskip, Hd, nullptr)))
+            return rc;
         DFB_CUDA(cudaEventRecord(m->ev_skip, s));
     }
     // ---- DF decoder (deepfilternet3.py:323-331), on the auxiliary stream (forked after the encoder)
     {
         cudaStream_t s = sa;  // shadows the caller stream inside this block
-        const float *w_in, *w_out;
-        if ((rc = need(m, "df_dec.df_gru.in.gl", (int64_t)emb_dim * Hd / c.g_df_in, &w_in))) return rc;
-        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a2, Hd, M, c.g_df_in, emb_dim, Hd, ACT_RELU, 1.f, 0.f,
-                         f.ga2_hi, f.ga2_lo))) return rc;
+        if ((rc = gl(s, "df_dec.df_gru.in.gl", f.emb, emb_dim, &pl_emb, c.g_df_in, emb_dim, Hd, ACT_RELU, nullptr, 0, f.g_a2, Hd, &pl_ga2)))
+            return rc;
         const float *res = c.model_kind == 2 ? f.g_a2 : (early_skip ? f.dfskip : nullptr);
         if (early_skip) DFB_CUDA(cudaStreamWaitEvent(s, m->ev_skip, 0));
         if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a2, Hd, res, f.dfc, f.xproj2, f.g_h2, B, T, f.ga2_hi, f.ga2_lo,
-                          f.gh2_hi, f.gh2_lo, 1))) return rc;
+                          f.gh2_hi, f.gh2_lo, 1, gl_tc ? pl_dfc.hi : nullptr, gl_tc ? pl_dfc.lo : nullptr, &pl_dfc.ok))) return rc;
         if (c.g_df_skip && !early_skip) {
-            const float *w_skip;
-            if ((rc = need(m, "df_dec.df_skip.gl", (int64_t)emb_dim * Hd / c.g_df_skip, &w_skip))) return rc;
-            if ((rc = run_gl(s, f.emb, emb_dim, w_skip, nullptr, f.dfc, Hd, f.dfc, Hd, M, c.g_df_skip, emb_dim, Hd, ACT_NONE))) return rc;
+            if ((rc = gl(s, "df_dec.df_skip.gl", f.emb, emb_dim, &pl_emb, c.g_df_skip, emb_dim, Hd, ACT_NONE, f.dfc, Hd, f.dfc, Hd, nullptr)))
+                return rc;
+            pl_dfc.ok = false;
         }
         if (d_alpha && c.model_kind == 2) {  // alpha = sigmoid(df_fc_a(c)), deepfilternet2.py:368
             const float *aw, *ab;
@@ -1435,24 +1319,23 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             if ((rc = run_gl(s, f.dfc, Hd, aw, ab, nullptr, 0, d_alpha, 1, M, 1, Hd, 1, ACT_SIGMOID))) return rc;
         }
         const int O2 = 2 * c.df_order;
-        if ((rc = need(m, "df_dec.df_out.gl", (int64_t)Hd * Fd * O2 / c.g_df_out, &w_out))) return rc;
         // coefs = tanh(df_out(c)) + df_convp(c0); the pathway term was written by k_df_convp on the low-priority stream
         DFB_CUDA(cudaStreamWaitEvent(s, m->ev_convp, 0));
-        if ((rc = run_gl(s, f.dfc, Hd, w_out, nullptr, d_coefs, (int64_t)Fd * O2, d_coefs, (int64_t)Fd * O2, M, c.g_df_out, Hd, Fd * O2, ACT_TANH))) return rc;
+        if ((rc = gl(s, "df_dec.df_out.gl", f.dfc, Hd, &pl_dfc, c.g_df_out, Hd, Fd * O2, ACT_TANH, d_coefs, (int64_t)Fd * O2, d_coefs,
+                     (int64_t)Fd * O2, nullptr))) return rc;
     }
     DFB_CUDA(cudaEventRecord(m->ev_join, sa));
     // ---- ERB decoder (deepfilternet3.py:245-254)
     {
-        const float *w_in, *w_out;
-        if ((rc = need(m, "erb_dec.emb_gru.in.gl", (int64_t)emb_dim * H / c.g_erb_in, &w_in))) return rc;
-        if ((rc = run_gl(s, f.emb, emb_dim, w_in, nullptr, nullptr, 0, f.g_a, H, M, c.g_erb_in, emb_dim, H, ACT_RELU, 1.f, 0.f,
-                         f.ga_hi, f.ga_lo))) return rc;
+        if ((rc = gl(s, "erb_dec.emb_gru.in.gl", f.emb, emb_dim, &pl_emb, c.g_erb_in, emb_dim, H, ACT_RELU, nullptr, 0, f.g_a, H, &pl_ga)))
+            return rc;
         // DFN2 (SqueezedGRU): identity skip around the GRU, y = GRU(x) + x  (modules.py:695-697)
         const float *res = c.model_kind == 2 ? f.g_a : nullptr;
+        pl_gb.ok = false;
         if ((rc = run_gru(m, s, "erb_dec.emb_gru", c.erb_gru_layers, H, f.g_a, H, res, f.g_b, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
-                          f.gh_hi, f.gh_lo))) return rc;
-        if ((rc = need(m, "erb_dec.emb_gru.out.gl", (int64_t)H * ED / c.g_erb_out, &w_out))) return rc;
-        if ((rc = run_gl(s, f.g_b, H, w_out, nullptr, nullptr, 0, f.dec_emb, ED, M, c.g_erb_out, H, ED, ACT_RELU))) return rc;
+                          f.gh_hi, f.gh_lo, 0, gl_tc ? pl_gb.hi : nullptr, gl_tc ? pl_gb.lo : nullptr, &pl_gb.ok))) return rc;
+        if ((rc = gl(s, "erb_dec.emb_gru.out.gl", f.g_b, H, &pl_gb, c.g_erb_out, H, ED, ACT_RELU, nullptr, 0, f.dec_emb, ED, nullptr)))
+            return rc;
         auto path = [&](DwPwParams &p, const char *pn, const float *pt, int64_t pfs) -> int {
             std::string n(pn);
             p.path = pt; p.path_fs = pfs;

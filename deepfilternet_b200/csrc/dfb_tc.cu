@@ -1,225 +1,25 @@
 // dfb_tc.cu -- 5th-generation tensor-core (tcgen05) kernels for the dense contractions of the path.
 //
-//   k_gemm_tf32:  Y[M,N] = act(X[M,K] . W[N,K]^T + bias)          (GRU input projections W_ih x + b_ih,
-//                 torch.nn.GRU inside SqueezedGRU[_S], DeepFilterNet/df/modules.py:684,723)
-//
-// Structure (one CTA per 128 x BN output tile, 4 warps):
-//   warp 0 / lane 0 : TMA producer  -- cp.async.bulk.tensor (128B swizzle) of the X and W k-blocks into
-//                     a 4-stage shared-memory ring, completion on "full" mbarriers
-//   warp 1 / lane 0 : MMA issuer    -- tcgen05.mma.cta_group::1.kind::tf32, 128 x BN x 8 per instruction,
-//                     accumulator in TMEM; tcgen05.commit releases the ring slot / signals the epilogue
-//   warps 0-3       : epilogue      -- tcgen05.ld 32x32b (one TMEM lane = one output row per thread),
-//                     + bias, activation, 128-byte row segments to global memory
-// Operands are fp32 in HBM; the tensor maps use the TFLOAT32 element type so the TMA engine hands the
-// tensor core tf32 values; accumulation is fp32.  Parity of the whole path with TF32 contractions is
-// checked end to end (tests/test_gpu_parity.py, RMS <= 1e-4 vs the fp32 oracle).
+//   k_gemm_bf16x3: GRU input projections W_ih x + b_ih (torch.nn.GRU inside SqueezedGRU[_S], modules.py:684,723)
+//   k_dwpw_bx:     fused depthwise (+pathway) -> 1x1 conv -> ReLU blocks (Conv2dNormAct / ConvTranspose2dNormAct)
+//   k_gru_tc:      the GRU recurrence W_hh h with the weights resident in tensor memory
+// All three reach fp32-level accuracy on the BF16 tensor pipe by splitting both operands into BF16 hi + lo planes
+// (x = hi + lo to ~2^-17) and issuing hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM.
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "dfb_common.cuh"
 #include "dfb_dwpw.cuh"
+#include "dfb_ptx.cuh"
 
 namespace dfb {
 
 // ----------------------------------------------------------------------------- PTX helpers ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
 
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle, rows of exactly 128 bytes
-// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 | layout << 61)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;               // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;     // stride byte offset: 8 rows x 128 B
-    d |= (uint64_t)1 << 46;               // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;               // SWIZZLE_128B
-    return d;
-}
-// Instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major (InstrDescriptor)
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-        "}\n" ::"r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
 
-__device__ __forceinline__ float tc_act(float x, int act) {
-    switch (act) {
-        case 1: return fmaxf(x, 0.f);
-        case 2: return tanhf(x);
-        case 3: return 1.f / (1.f + expf(-x));
-        default: return x;
-    }
-}
-
-// ---------------------------------------------------------------------------- GEMM kernel ----
-constexpr int kTcBM = 128, kTcBK = 32, kTcStages = 2;  // 64 KB of operands per CTA -> 3 CTAs / SM
-
-template <int BN>
-struct TcSmem {
-    alignas(1024) float a[kTcStages][kTcBM * kTcBK];
-    alignas(1024) float b[kTcStages][BN * kTcBK];
-    alignas(8) uint64_t full[kTcStages];
-    uint64_t empty[kTcStages];
-    uint64_t tmem_full;
-    uint32_t tmem_base;
-    alignas(16) float bias[BN];
-};
-
-template <int BN>
-__global__ void __launch_bounds__(128)
-k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const float *__restrict__ bias, float *__restrict__ Y, int64_t ldy, int M, int N, int K, int act) {
-    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    TcSmem<BN> &sm = *reinterpret_cast<TcSmem<BN> *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * BN;
-    const int nkb = K / kTcBK;
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < kTcStages; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        mbar_init(&sm.tmem_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, BN);
-    for (int i = threadIdx.x; i < BN; i += blockDim.x) sm.bias[i] = bias ? bias[n0 + i] : 0.f;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = sm.tmem_base;
-    if (threadIdx.x == 0) {
-        // ===== TMA producer
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % kTcStages, it = kb / kTcStages;
-            if (it > 0) mbar_wait(&sm.empty[s], (it - 1) & 1);
-            mbar_expect_tx(&sm.full[s], (kTcBM + BN) * kTcBK * 4);
-            tma_load_2d(sm.a[s], &tmA, kb * kTcBK, m0, &sm.full[s]);
-            tma_load_2d(sm.b[s], &tmB, kb * kTcBK, n0, &sm.full[s]);
-        }
-    } else if (threadIdx.x == 32) {
-        // ===== MMA issuer
-        constexpr uint32_t idesc = umma_idesc_tf32(kTcBM, BN);
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % kTcStages, it = kb / kTcStages;
-            mbar_wait(&sm.full[s], it & 1);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
-#pragma unroll
-            for (int k = 0; k < kTcBK / 8; k++) {
-                umma_tf32(tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0);
-            }
-            umma_commit(&sm.empty[s]);  // frees this ring slot once the MMAs above have read it
-        }
-        umma_commit(&sm.tmem_full);
-    }
-    __syncwarp();
-    // ===== epilogue: all 4 warps, warp w owns TMEM lanes [32 w, 32 w + 32) = rows m0 + 32 w + lane
-    mbar_wait(&sm.tmem_full, 0);
-    tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
-        if (m < M) {
-            float *dst = Y + (int64_t)m * ldy + n0 + c;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                const float4 bv = *reinterpret_cast<const float4 *>(&sm.bias[c + j]);
-                o.x = tc_act(v[j] + bv.x, act);
-                o.y = tc_act(v[j + 1] + bv.y, act);
-                o.z = tc_act(v[j + 2] + bv.z, act);
-                o.w = tc_act(v[j + 3] + bv.w, act);
-                *reinterpret_cast<float4 *>(dst + j) = o;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, BN);
-}
 
 // ------------------------------------------------------------- BF16x3 GEMM (projections) ----
 // Y[M,N] = X[M,K] . W[N,K]^T + bias with fp32-level accuracy on the BF16 tensor pipe: both operands
@@ -248,44 +48,6 @@ struct BxSmem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void umma_bf16_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// A operand from TMEM (lane = row, one 32-bit column = two consecutive bf16 K elements), B from smem; every lane
-// executes the call with identical operands and one elected lane issues (see the GRU kernel for why)
-__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-        "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 constexpr int kBxThreads = 320;
 __global__ void __launch_bounds__(kBxThreads, 1)
@@ -427,69 +189,6 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__
 constexpr int kDxThreads = 256;
 constexpr uint32_t kDxW = 32768, kDxRaw = 49152, kDxTail = 64 * 4 + 32;
 
-// byte offset of (row r, 16-byte chunk j) inside a [rows x 128 B] sub-tile with 128-byte swizzle
-__device__ __forceinline__ uint32_t sw128_off(int r, int j) {
-    return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
-}
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-// (x0, x1) -> packed bf16x2 hi plane and lo plane (x = hi + lo, both round to nearest even)
-__device__ __forceinline__ void bf16x2_split(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    const float2 hf = __bfloat1622float2(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-    hi = *reinterpret_cast<uint32_t *>(&h);
-    lo = *reinterpret_cast<uint32_t *>(&l);
-}
-// explicit shared-window accesses on 32-bit addresses (the struct-over-aligned-raw-buffer idiom makes the
-// compiler fall back to generic LD / ST and 64-bit address arithmetic)
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-// 1-D bulk copy global -> own shared memory, completing on an mbarrier (TMA engine, no registers involved)
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ float4 f4_fma(float4 x, float4 w, float4 a) {
-    return make_float4(fmaf(x.x, w.x, a.x), fmaf(x.y, w.y, a.y), fmaf(x.z, w.z, a.z), fmaf(x.w, w.w, a.w));
-}
 
 // MASK = 1 (last ERB decoder block of the kt = 1 models): the tile holds whole frames, so the mask head
 //   m[t,f] = sigmoid(sum_{df,c} w[df][c] * (relu(e0 * ps + pb) + out)[t][f+df-1][c] + bias)
@@ -693,16 +392,26 @@ k_dwpw_bx(DwPwParams p, const float *__restrict__ w_sw /* [hi | lo] x [64 n][64 
         }
     }
     // ---- coalesced write-out: half a warp per 256-byte row, 8 consecutive rows per thread
-    if (!MASK || p.out) {
+    if (p.out || p.out_hi) {
         const int j = tid & 15;
         int fr2 = (8 * slot * p.fo_magic) >> 16, fo2 = 8 * slot - fr2 * p.Fout;
-        float *dst = p.out + ((int64_t)b * p.T + t0 + fr2) * p.out_fs + fo2 * kCh + j * 4;
+        int64_t off = ((int64_t)b * p.T + t0 + fr2) * p.out_fs + fo2 * kCh + j * 4;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int r = 8 * slot + i;
-            if (r < R) *reinterpret_cast<float4 *>(dst) = lds128(sb + r * 256 + ((j ^ (r & 15)) << 4));
-            dst += kCh;
-            if (++fo2 == p.Fout) { fo2 = 0; dst += p.out_fs - (int64_t)p.Fout * kCh; }
+            if (r < R) {
+                const float4 v = lds128(sb + r * 256 + ((j ^ (r & 15)) << 4));
+                if (p.out) *reinterpret_cast<float4 *>(p.out + off) = v;
+                if (p.out_hi) {
+                    uint32_t h0, l0, h1, l1;
+                    bf16x2_split(v.x, v.y, h0, l0);
+                    bf16x2_split(v.z, v.w, h1, l1);
+                    *reinterpret_cast<uint2 *>(p.out_hi + off) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2 *>(p.out_lo + off) = make_uint2(l0, l1);
+                }
+            }
+            off += kCh;
+            if (++fo2 == p.Fout) { fo2 = 0; off += p.out_fs - (int64_t)p.Fout * kCh; }
         }
     }
 }
@@ -813,53 +522,11 @@ struct GruTcParams {
     const float *res;    // optional [B,T,H], added to the OUTPUT only
     float *hout;         // [B,T,H]
     unsigned short *hout_hi, *hout_lo;  // optional BF16 hi/lo planes of hout (A operand of the next projection GEMM)
+    int planes_res;      // 1: the planes hold hout + res (input of a grouped linear), 0: the residual-free h
     int B, T, Bc;
     long long *dbg;      // optional [T][8] clock64 stamps of CTA 0 (0-3: MMA thread, 4-7: gate thread 0)
 };
 
-// K-major operand without swizzle: 8 x 16 B core matrices, LBO = stride between K-adjacent core
-// matrices, SBO = stride between 8-row groups (cute/arch/mma_sm100_desc.hpp, LayoutType::SWIZZLE_NONE)
-__device__ __forceinline__ uint64_t umma_desc_interleave(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-// bulk copy own shared memory -> a peer CTA's shared memory, completing `bytes` on the peer's mbarrier
-__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
-                 "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
-                 : "memory");
-}
-// x = hi + lo with hi, lo bf16 (round to nearest)
-__device__ __forceinline__ void bf16_split(float x, unsigned short &hi, unsigned short &lo) {
-    __nv_bfloat16 h = __float2bfloat16_rn(x);
-    __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-    hi = __bfloat16_as_ushort(h);
-    lo = __bfloat16_as_ushort(l);
-}
-// gates with the MUFU exp2 / reciprocal approximations (each ~1e-7 relative)
-__device__ __forceinline__ float gt_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float gt_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 template <int NS>
 __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p) {
@@ -1024,7 +691,8 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
                 float2 ov = make_float2(hprev0, hprev1);
                 if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
                 *reinterpret_cast<float2 *>(p.hout + o) = ov;
-                if (p.hout_hi) {  // residual-free h (the next layer's projection input)
+                if (p.hout_hi) {  // residual-free h (the next layer's projection input) or the layer output
+                    if (p.planes_res && p.res) bf16x2_split(ov.x, ov.y, vhi, vlo);
                     *reinterpret_cast<uint32_t *>(p.hout_hi + o) = vhi;
                     *reinterpret_cast<uint32_t *>(p.hout_lo + o) = vlo;
                 }
@@ -1068,8 +736,8 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
 
 // wide != 0: 32 streams per cluster when the batch needs more than 4 clusters of 16 (see GtCfg)
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
-                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg, int wide) {
-    GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, B, T, 0, dbg};
+                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg, int wide, int planes_res) {
+    GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, planes_res, B, T, 0, dbg};
     static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
     const bool use32 = force ? force == 32 : (wide && B > 64);
     return use32 ? launch_gru_tc_n<32>(s, p) : launch_gru_tc_n<16>(s, p);
@@ -1090,21 +758,6 @@ static PFN_encodeTiled get_encode() {
             fn = (PFN_encodeTiled)p;
     }
     return fn;
-}
-
-// 2-D fp32 row-major [rows][cols] (row pitch ld floats), box = [box_rows][32 floats], 128-byte swizzle
-static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void *)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return DFB_OK;
 }
 
 // 2-D bf16 row-major [rows][cols] (row pitch ld elements), box = [box_rows][64 elements = 128 B], 128-byte swizzle
@@ -1147,27 +800,6 @@ int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64
     DFB_PROF("k_gemm_bf16x3[gru_proj]", s);
     k_gemm_bf16x3<<<grid, kBxThreads, smem, s>>>(mxh, mxl, reinterpret_cast<const unsigned short *>(w_hi),
                                           reinterpret_cast<const unsigned short *>(w_lo), bias, y, ldy, (int)M, N, K);
-    DFB_LAUNCH_CHECK();
-    return DFB_OK;
-}
-
-// Y[M,N] = act(X[M,K] . W[N,K]^T + bias); X row pitch ldx, W row pitch K, Y row pitch ldy.
-int launch_gemm_tf32(cudaStream_t s, const float *x, int64_t ldx, const float *w_nk, const float *bias, float *y,
-                     int64_t ldy, int64_t M, int N, int K, int act) {
-    constexpr int BN = 128;
-    if (N % BN || K % kTcBK || (ldx % 4) || (ldy % 4) || M <= 0 || ((uintptr_t)x & 15) || ((uintptr_t)w_nk & 15))
-        return fail(DFB_ERR_UNSUPPORTED, "tf32 GEMM shape M=%lld N=%d K=%d", (long long)M, N, K);
-    CUtensorMap ma, mb;
-    int rc;
-    if ((rc = make_map(&ma, x, M, K, ldx, kTcBM)) || (rc = make_map(&mb, w_nk, N, K, K, BN))) return rc;
-    static PerDeviceOnce attr_once;
-    const int smem = (int)sizeof(TcSmem<BN>) + 1024;
-    if (auto once_guard = attr_once.first()) {
-        DFB_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
-    dim3 grid((unsigned)((M + kTcBM - 1) / kTcBM), (unsigned)(N / BN));
-    DFB_PROF("k_gemm_tf32[gru_proj]", s);
-    k_gemm_tf32<BN><<<grid, 128, smem, s>>>(ma, mb, bias, y, ldy, (int)M, N, K, act);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }

@@ -114,17 +114,15 @@ class DfNet(nn.Module):
     def set_precision(self, mode: str) -> None:
         """Arithmetic of the contractions (everything else is always IEEE fp32):
           'fp32'         FFMA everywhere
-          'fp32+gru_tc+proj_tc+conv_tc'  (default) as below plus the 1x1 convs of the separable conv blocks on
-                         the fused BF16x3 tcgen05 kernel (k_dwpw_bx)
-          'fp32+gru_tc+proj_tc'  as 'fp32+gru_tc' plus the GRU input projections on the BF16x3
-                         tcgen05 GEMM (operands as BF16 hi/lo planes, 3 MMAs per product; 1e-7 .. 4e-7 RMS)
-          'fp32+gru_tc'  as 'fp32', but the GRU recurrence of H = 256 models runs on tcgen05 tensor
-                         cores with BF16 hi/lo split operands (3 MMAs per product, fp32 accumulate: ~2^-17
-                         relative, measured 5e-8 RMS end to end)
-          'tf32' / 'tf32+gru_tc'  additionally TF32 tcgen05 for the feed-forward contractions (faster GEMMs,
-                         but ~1e-5 .. 3e-4 RMS end to end depending on the signal -- NOT within the 1e-4
-                         parity bound on loud speech; kept for experiments only)."""
-        check(_lib.lib().dfb_model_set_precision(self._h, {"fp32": 0, "tf32": 1, "fp32+gru_tc": 2, "tf32+gru_tc": 3, "fp32+gru_tc+proj_tc": 6, "fp32+gru_tc+proj_tc+conv_tc": 14}[mode]))
+          'fp32+gru_tc'  the GRU recurrence of H = 256 models on tcgen05 tensor cores with BF16 hi/lo split
+                         operands (3 MMAs per product, fp32 accumulate: ~2^-17 relative, 5e-8 RMS end to end)
+          'fp32+gru_tc+proj_tc'  plus the GRU input projections on the BF16x3 tcgen05 GEMM
+          'fp32+gru_tc+proj_tc+conv_tc'  (default) plus the 1x1 convs of the separable conv blocks (k_dwpw_bx) and
+                         the grouped linears (k_gl_bx) on BF16x3 tcgen05 kernels (1e-7 .. 4e-7 RMS end to end)."""
+        modes = {"fp32": 0, "fp32+gru_tc": 2, "fp32+gru_tc+proj_tc": 6, "fp32+gru_tc+proj_tc+conv_tc": 14}
+        if mode not in modes:
+            raise ValueError(f"unknown precision mode {mode!r}; one of {sorted(modes)}")
+        check(_lib.lib().dfb_model_set_precision(self._h, modes[mode]))
         self.precision = mode
 
     def __del__(self):

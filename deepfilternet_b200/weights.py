@@ -21,6 +21,7 @@ Packed tensors (name -> layout):
   df_dec.df_convp.w1 [kt5][10][C/2]   grouped (2) temporal conv: out o reads channels (o // 5) * C/2 + c
   df_dec.df_convp.w2 [10][10]         1x1 (in, out), BN folded;  df_dec.df_convp.b [10]
   *.gl              [G][I/G][H/G]     GroupedLinearEinsum weight as stored (modules.py:752-757)
+  *.gl_bx           BF16 hi | lo image of the same weight in the tcgen05 kernel's operand layout (gl_bx_image)
   <gru>.l{n}.w_ih_t [I][3H] (transposed for the projection GEMM), .w_hh [3H][H], .b_ih [3H],
                     .b_hh [3H]        torch.nn.GRU gate order (r,z,n)
   enc.lsnr.w [emb_out], enc.lsnr.b [1]
@@ -80,6 +81,25 @@ def umma_sw128_image(w_nk: np.ndarray) -> np.ndarray:
             o[rows, j ^ (rows & 7)] = c[rows, j]
         planes.append(o.reshape(-1))
     return np.ascontiguousarray(np.concatenate(planes))
+
+
+def gl_bx_image(w: np.ndarray) -> np.ndarray:
+    """GroupedLinearEinsum weight [G][Ig][Hg] -> the shared-memory image of the tcgen05 grouped-linear kernel's B operand
+    (csrc/dfb_gl.cu): BF16 hi plane then lo plane, each [G][Ig/8][Hgp/8][8 n][8 i] -- K-major 8 x 16-byte core matrices,
+    Hg zero-padded to a multiple of 16 (Hgp).  Returned as float32 words (two BF16 per element)."""
+    G, Ig, Hg = w.shape
+    assert Ig % 8 == 0
+    Hgp = (Hg + 15) // 16 * 16
+    wp = np.zeros((G, Ig, Hgp), dtype=np.float32)
+    wp[:, :, :Hg] = w
+    t = torch.from_numpy(wp)
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.to(torch.float32)).to(torch.bfloat16)
+    planes = []
+    for pl in (hi, lo):
+        a = pl.view(torch.int16).numpy().reshape(G, Ig // 8, 8, Hgp // 8, 8)   # [g][kc][i8][rg][n8]
+        planes.append(np.ascontiguousarray(a.transpose(0, 1, 3, 4, 2)).reshape(-1))  # [g][kc][rg][n8][i8]
+    return np.ascontiguousarray(np.concatenate(planes)).view(np.float32)
 
 
 def gru_layers(sd, prefix: str) -> int:
@@ -169,6 +189,8 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
     def gl(dst: str, src: str) -> int:
         w = _np(sd[src])
         out[dst] = f32(w)
+        if w.shape[1] % 16 == 0 and w.shape[2] % 4 == 0:
+            out[dst + "_bx"] = gl_bx_image(w)   # tcgen05 grouped linear (BF16x3)
         return w.shape[0]
 
     g = {}
