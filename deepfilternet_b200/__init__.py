@@ -13,5 +13,6 @@ from .config import ModelConfig, load_config  # noqa: F401
 from .dropin import install_dropin  # noqa: F401
 from .enhance import df_features, enhance, enhance_device, init_df  # noqa: F401
 from .model import DfNet, load_model  # noqa: F401
+from .streaming import DfStream  # noqa: F401
 
 __version__ = "0.1.0"

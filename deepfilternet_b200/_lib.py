@@ -84,6 +84,14 @@ SIGNATURES = {
     "dfb_enhance_host": (_I, [_VP, _VP, _VP, _I64, _I64, _I, _F, _VP]),
     "dfb_enhance_out_len": (_I64, [_VP, _I64, _I]),
     "dfb_model_workspace_bytes": (_I64, [_VP]),
+    "dfb_stream_create": (_I, [C.POINTER(_VP), _VP, _VP, _I64, _F]),
+    "dfb_stream_free": (None, [_VP]),
+    "dfb_stream_reset": (_I, [_VP]),
+    "dfb_stream_frame_length": (_I64, [_VP]),
+    "dfb_stream_latency_frames": (_I64, [_VP]),
+    "dfb_stream_process": (_I, [_VP, _VP, _I64, _VP, _VP]),
+    "dfb_stream_flush": (_I, [_VP, _VP, _VP]),
+    "dfb_stream_process_host": (_I, [_VP, _VP, _I64, _VP]),
     "dfb_model_set_precision": (_I, [_VP, _I]),
     "dfb_model_set_max_workspace": (_I, [_VP, _I64]),
     "dfb_debug_gru_timing": (_I, [_VP, _I, _VP]),

@@ -132,6 +132,11 @@ struct ApplyParams {
     int64_t out_offset;   // first synthesised sample that is written (n_fft - hop when pad)
     int64_t out_len;
     int Tf, mode, nb_df, order, lookahead;
+    // time-chunked execution (0 = whole signal): the spectrum buffer holds spec_T frames per stream of which Tv exist
+    // (rows >= Tv are the end of the stream: zero for the deep filter taps), m / coefs hold Tf; audio of frames < t_first
+    // is not written (they belong to the previous window and are only re-synthesised for the overlap-add tail)
+    int spec_T, Tv, t_first;
+    int mc_T;             // frames per stream in m / coefs (0 = Tf)
     float atten_lim;      // 0 = off
     // carried ISTFT state (pyDF synthesis(reset=False), mode 0 only): channel 0 starts from init_tail,
     // channel c > 0 from the tail left by channel c - 1; the tail after the last frame goes to final_tail
@@ -144,16 +149,25 @@ struct ApplyParams {
 
 struct dfb_state;
 namespace dfb {
+// frame window of launch_analysis: frames [t_begin, t_begin + nf) of a signal of T samples per row (row pitch row_stride,
+// 0 = T) go to rows out_t0 ... of buffers holding Tbuf frames per stream
+struct AnaWindow { int t_begin, nf, out_t0, Tbuf; int64_t row_stride; };
 int launch_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, float *d_erb_db,
-                    cudaStream_t s, const float *d_init_mem = nullptr);
+                    cudaStream_t s, const float *d_init_mem = nullptr, const AnaWindow *w = nullptr);
+// Ts: frames per stream in the buffers (0 = Tf; pointers pre-offset to the first frame); *_state_out: EMA states after
+// the last frame (may be null / alias the inputs)
 int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float *d_spec, int Fd, int64_t spec_stride,
                      int64_t C, int64_t Tf, float alpha, const float *d_erb_state, const float *d_unit_state,
-                     float *d_feat_erb, float *d_feat_spec, cudaStream_t s);
+                     float *d_feat_erb, float *d_feat_spec, cudaStream_t s, int64_t Ts = 0, float *d_erb_state_out = nullptr,
+                     float *d_unit_state_out = nullptr);
 int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaStream_t s);
+// time window of a recurrence launch: steps 0 .. T-1 are frames t0 .. of buffers holding Ts frames per stream; h0 (null:
+// zeros) / hT (null: not stored) are the carried hidden states [B][H]
+struct GruWindow { const float *h0; float *hT; int t0, Ts; };
 // tensor-core GRU recurrence, H = 256 (dfb_tc.cu)
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
                   unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg = nullptr, int wide = 0,
-                  int planes_res = 0);
+                  int planes_res = 0, const GruWindow *w = nullptr);
 // BF16x3 tcgen05 GEMM on hi/lo planes (dfb_tc.cu)
 int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64_t ldx, const void *w_hi, const void *w_lo,
                        const float *bias, float *y, int64_t ldy, int64_t M, int N, int K);

@@ -142,16 +142,20 @@ __device__ __forceinline__ void warp_fft480_twptr(LoadF load, const float2 *tw_l
 // ---------------------------------------------------------------------------- analysis ----
 // grid (ceil(Tf / kAnaWarps), B), block 32 * kAnaWarps.  Warp w transforms frame t0 + w.
 // Algorithmic HBM bytes per frame: 1920 R (audio hop) + 3848 W (spec) + 128 W (erb dB).
+// Frame window: the grid covers frames [t_begin, t_begin + nf) of every stream (time-chunked execution); their rows
+// go to out_t0 ... of spec / erb_db buffers that hold Tbuf frames per stream.  The whole-signal call is
+// (t_begin, nf, out_t0, Tbuf) = (0, Tf, 0, Tf).
 __global__ void __launch_bounds__(32 * kAnaWarps, 3)
 k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restrict__ spec,
-           float *__restrict__ erb_db, DspTables tb, const float *__restrict__ init_mem) {
+           float *__restrict__ erb_db, DspTables tb, const float *__restrict__ init_mem, int t_begin, int nf, int out_t0,
+           int Tbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_stage = reinterpret_cast<float *>(smem_raw);                    // (W + 1) * hop
     float *s_win = s_stage + (kAnaWarps + 1) * kHop;                         // fft
     float2 *s_tw960 = reinterpret_cast<float2 *>(s_win + kFft);              // 241 (+1 pad)
     float2 *s_twa = s_tw960 + 242;                                           // pass-A twiddles [24][20]
     float2 *s_buf = s_twa + kN2 * kN1;                                       // W * kTileFloat2
-    const int b = blockIdx.y, t0 = blockIdx.x * kAnaWarps;
+    const int b = blockIdx.y, tl0 = blockIdx.x * kAnaWarps, t0 = t_begin + tl0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *x = audio + (int64_t)b * T;
     // stage samples [(t0-1)*hop, (t0+W)*hop); zeros before the stream start (analysis_mem = 0)
@@ -169,7 +173,8 @@ k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restric
     for (int i = tid; i < kN2 * kN1; i += blockDim.x) s_twa[i] = tb.tw_a_fwd[i];
     __syncthreads();
     const int t = t0 + warp;
-    if (t >= Tf) return;
+    if (tl0 + warp >= nf || t >= Tf) return;
+    const int64_t orow = (int64_t)b * Tbuf + out_t0 + tl0 + warp;   // row of this frame in the output buffers
     const float *fr = s_stage + warp * kHop;  // frame t = samples [(t-1) hop, (t+1) hop)
     float2 *nat = s_buf + warp * kTileFloat2;
     warp_fft480_twptr<false>(
@@ -180,7 +185,7 @@ k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restric
         },
         s_twa + (lane < kN2 ? lane : 0) * kN1, nat, lane);
     // split step + wnorm, write spec row, keep |X|^2 for the band energies
-    float2 *row = spec + ((int64_t)b * Tf + t) * kF;
+    float2 *row = spec + orow * kF;
     float pk[8], pnk[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -216,7 +221,7 @@ k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restric
         float kinv = tb.erb_kinv[band];
         float acc = 0.f;
         for (int j = 0; j < n; j++) acc = __fadd_rn(acc, __fmul_rn(P[o + j], kinv));
-        erb_db[((int64_t)b * Tf + t) * tb.E + band] = __fmul_rn(log10f(__fadd_rn(acc, 1e-10f)), 10.f);
+        erb_db[orow * tb.E + band] = __fmul_rn(log10f(__fadd_rn(acc, 1e-10f)), 10.f);
     }
 }
 
@@ -255,15 +260,18 @@ __global__ void k_erb_inv(const float *__restrict__ gains, int64_t n_frames, int
 // grid B, block E + Fd threads (thread j < E: band j; else bin j - E).  Loads are batched kPf
 // frames ahead so the dependent chain is arithmetic only.
 constexpr int kPf = 8;
+// Ts = frames per stream in the four buffers (the pointers are pre-offset to the first frame to process, Tf = number of
+// frames processed); *_state_out (may alias the inputs) receive the EMA states after the last frame.
 __global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
                             const float2 *__restrict__ spec_in, int Fd, int64_t spec_stride_t, int Tf,
-                            float alpha, const float *__restrict__ erb_state, const float *__restrict__ unit_state,
-                            float *feat_erb, float2 *__restrict__ feat_spec) {
+                            float alpha, const float *erb_state, const float *unit_state,
+                            float *feat_erb, float2 *__restrict__ feat_spec, int Ts, float *erb_state_out,
+                            float *unit_state_out) {
     const int b = blockIdx.x, j = threadIdx.x;
     const float one_m_alpha = __fsub_rn(1.f, alpha);
     if (j < E) {
-        const float *src = erb_in + (int64_t)b * Tf * erb_stride_t + j;
-        float *dst = feat_erb + (int64_t)b * Tf * E + j;
+        const float *src = erb_in + (int64_t)b * Ts * erb_stride_t + j;
+        float *dst = feat_erb + (int64_t)b * Ts * E + j;
         float s;
         if (erb_state) s = erb_state[(int64_t)b * E + j];
         else s = (E == 1) ? -60.f : __fadd_rn(-60.f, __fmul_rn((float)j, __fdiv_rn(-30.f, (float)(E - 1))));
@@ -286,10 +294,11 @@ __global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
                 }
             }
         }
+        if (erb_state_out) erb_state_out[(int64_t)b * E + j] = s;
     } else if (j < E + Fd) {
         const int k = j - E;
-        const float2 *src = spec_in + (int64_t)b * Tf * spec_stride_t + k;
-        float2 *dst = feat_spec + (int64_t)b * Tf * Fd + k;
+        const float2 *src = spec_in + (int64_t)b * Ts * spec_stride_t + k;
+        float2 *dst = feat_spec + (int64_t)b * Ts * Fd + k;
         float s;
         if (unit_state) s = unit_state[(int64_t)b * Fd + k];
         else s = (Fd == 1) ? 0.001f : __fadd_rn(0.001f, __fmul_rn((float)k, __fdiv_rn(__fsub_rn(0.0001f, 0.001f), (float)(Fd - 1))));
@@ -320,6 +329,7 @@ __global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
                 }
             }
         }
+        if (unit_state_out) unit_state_out[(int64_t)b * Fd + k] = s;
     }
 }
 
@@ -348,9 +358,9 @@ __device__ __forceinline__ float2 apply_bin(const ApplyParams &p, const DspTable
         float yr = 0.f, yi = 0.f;
         for (int o = 0; o < p.order; o++) {
             int tt = t + o - (p.order - 1 - p.lookahead);
-            if (tt < 0 || tt >= p.Tf) continue;
+            if (tt < 0 || tt >= (p.Tv ? p.Tv : p.Tf)) continue;
             float2 s = srow0[(int64_t)tt * kF + k];
-            if (p.mode == 2) {
+            if (p.mode == 2 && tt < (p.mc_T ? p.mc_T : p.Tf)) {
                 float g = mrow0[(int64_t)tt * tb.E + band];
                 s.x *= g; s.y *= g;
             }
@@ -382,8 +392,9 @@ __global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis_generic(Appl
     const int t0 = (blockIdx.x * kSynWarps + warp) * kSynChunk;
     if (t0 >= p.Tf) return;
     const int t1 = min(t0 + kSynChunk, p.Tf);
-    const float2 *srow0 = p.spec + (int64_t)b * p.Tf * kF;
-    const float *mrow0 = p.m ? p.m + (int64_t)b * p.Tf * tb.E : nullptr;
+    const float2 *srow0 = p.spec + (int64_t)b * (p.spec_T ? p.spec_T : p.Tf) * kF;
+    const int mcT = p.mc_T ? p.mc_T : p.Tf;
+    const float *mrow0 = p.m ? p.m + (int64_t)b * mcT * tb.E : nullptr;
     float2 *nat = s_buf[warp];
     float *yb = reinterpret_cast<float *>(nat);  // 960 windowed samples of the current frame
     float tail[15];
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis_generic(Appl
     // relative to this channel in the contiguous [C,Tf,F] spectrum (mode 0 only)
     const int tstart = t0 > 0 ? t0 - 1 : ((p.carry && b > 0) ? -1 : 0);
     for (int t = tstart; t < t1; t++) {
-        const float *crow = p.coefs ? p.coefs + ((int64_t)b * p.Tf + t) * p.nb_df * (2 * p.order) : nullptr;
+        const float *crow = p.coefs ? p.coefs + ((int64_t)b * mcT + t) * p.nb_df * (2 * p.order) : nullptr;
         // gather X[k], X[480-k], merge into Z (natural order in `nat`)
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -434,7 +445,7 @@ __global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis_generic(Appl
                 float o = yb[i] + tail[j];      // lib.rs:407-411
                 tail[j] = yb[kHop + i];         // lib.rs:423-426 (hop == fft/2)
                 int64_t g = (int64_t)t * kHop + i - p.out_offset;
-                if (t >= t0 && g >= 0 && g < p.out_len) orow[g] = o;
+                if (t >= t0 && t >= p.t_first && g >= 0 && g < p.out_len) orow[g] = o;
             }
         }
         __syncwarp();
@@ -466,8 +477,10 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
     if (t0 >= p.Tf) return;
     const int t1 = min(t0 + kSynChunk, p.Tf);
     const int Tf = p.Tf, L = p.lookahead, back = ORDER - 1 - L;
-    const float2 *srow0 = p.spec + (int64_t)b * Tf * kF;
-    const float *mrow0 = p.m + (int64_t)b * Tf * 32;
+    const int Tv = p.Tv ? p.Tv : Tf;                       // spectrum rows >= Tv do not exist (end of the stream)
+    const float2 *srow0 = p.spec + (int64_t)b * (p.spec_T ? p.spec_T : Tf) * kF;
+    const int mcT = p.mc_T ? p.mc_T : Tf;                  // m / coefs rows per stream
+    const float *mrow0 = p.m + (int64_t)b * mcT * 32;
     const bool masked_df = p.mode == 2;
     // bands of this lane's bins: bk[j] for k = lane + 32 j, bn[j] for 480 - k
     unsigned long long bkp = 0, bnp = 0;  // 8 band indices each, one byte per j
@@ -487,8 +500,10 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
     // S'[tt][k] for the DF bins; tt = t + o - back.  Rows outside [0, Tf) are zero (multiframe.py:72-74).
     auto load_df_row = [&](int tt, float2 (&dst)[NDFJ]) {
         float g = 1.f;
-        const bool ok = tt >= 0 && tt < Tf;
-        float mrow = (ok && masked_df) ? mrow0[(int64_t)tt * 32 + lane] : 1.f;
+        const bool ok = tt >= 0 && tt < Tv;
+        // (DFN2) the mask of a look-ahead frame beyond the window's DNN frames does not exist yet: such rows are only
+        // read for frames that are re-synthesised in the next window
+        float mrow = (ok && masked_df && tt < mcT) ? mrow0[(int64_t)tt * 32 + lane] : 1.f;
 #pragma unroll
         for (int j = 0; j < NDFJ; j++) {
             float2 v = ok ? srow0[(int64_t)tt * kF + lane + 32 * j] : make_float2(0.f, 0.f);
@@ -509,7 +524,7 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
             for (int j = 0; j < NDFJ; j++) hist[o][j] = hist[o + 1][j];
         load_df_row(t + L, hist[ORDER - 1]);
         float2 cf[NDFJ][ORDER];
-        const float2 *crow = reinterpret_cast<const float2 *>(p.coefs + ((int64_t)b * Tf + t) * (NDFJ * 32) * (2 * ORDER));
+        const float2 *crow = reinterpret_cast<const float2 *>(p.coefs + ((int64_t)b * mcT + t) * (NDFJ * 32) * (2 * ORDER));
 #pragma unroll
         for (int j = 0; j < NDFJ; j++)
 #pragma unroll
@@ -579,7 +594,7 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
                 float o = yb[i] + tail[j];      // lib.rs:407-411
                 tail[j] = yb[kHop + i];         // lib.rs:423-426 (hop == fft/2)
                 int64_t g = (int64_t)t * kHop + i - p.out_offset;
-                if (t >= t0 && g >= 0 && g < p.out_len) orow[g] = o;
+                if (t >= t0 && t >= p.t_first && g >= 0 && g < p.out_len) orow[g] = o;
             }
         }
         __syncwarp();
@@ -785,26 +800,31 @@ extern "C" int dfb_state_params(const dfb_state *st, int *sr, int *fft, int *hop
 namespace dfb {
 
 int launch_analysis(dfb_state *st, const float *d_audio, int64_t C, int64_t T, float *d_spec, float *d_erb_db,
-                    cudaStream_t s, const float *d_init_mem) {
+                    cudaStream_t s, const float *d_init_mem, const AnaWindow *w) {
     int64_t Tf = T / st->hop;
     if (C <= 0 || Tf <= 0) return DFB_OK;
     if (C > 65535) return fail(DFB_ERR_INVALID, "more than 65535 channels per call");
-    dim3 grid((unsigned)((Tf + kAnaWarps - 1) / kAnaWarps), (unsigned)C);
+    const int t_begin = w ? w->t_begin : 0, nf = w ? w->nf : (int)Tf, out_t0 = w ? w->out_t0 : 0, Tbuf = w ? w->Tbuf : (int)Tf;
+    if (nf <= 0) return DFB_OK;
+    dim3 grid((unsigned)((nf + kAnaWarps - 1) / kAnaWarps), (unsigned)C);
     DFB_PROF("k_analysis", s);
-    k_analysis<<<grid, 32 * kAnaWarps, kAnaSmem, s>>>(d_audio, T, (int)Tf, (float2 *)d_spec, d_erb_db, st->tb, d_init_mem);
+    k_analysis<<<grid, 32 * kAnaWarps, kAnaSmem, s>>>(d_audio, w && w->row_stride ? w->row_stride : T, (int)Tf, (float2 *)d_spec,
+                                                     d_erb_db, st->tb, d_init_mem, t_begin, nf, out_t0, Tbuf);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }
 
 int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float *d_spec, int Fd, int64_t spec_stride,
                      int64_t C, int64_t Tf, float alpha, const float *d_erb_state, const float *d_unit_state,
-                     float *d_feat_erb, float *d_feat_spec, cudaStream_t s) {
+                     float *d_feat_erb, float *d_feat_spec, cudaStream_t s, int64_t Ts, float *d_erb_state_out,
+                     float *d_unit_state_out) {
     if (C <= 0 || Tf <= 0 || E + Fd == 0) return DFB_OK;
     if (E + Fd > 1024) return fail(DFB_ERR_INVALID, "E + F > 1024 in norm scan");
     int threads = ((E + Fd + 31) / 32) * 32;
     DFB_PROF("k_feat_norm", s);
     k_feat_norm<<<(unsigned)C, threads, 0, s>>>(d_erb, E, erb_stride, (const float2 *)d_spec, Fd, spec_stride, (int)Tf,
-                                               alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec);
+                                               alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec,
+                                               (int)(Ts > 0 ? Ts : Tf), d_erb_state_out, d_unit_state_out);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }

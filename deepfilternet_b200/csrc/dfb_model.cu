@@ -18,6 +18,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 
@@ -53,7 +54,8 @@ constexpr int kInFrames = 8;
 template <int CIN>
 __global__ void __launch_bounds__(256)
 k_conv_in(const float *__restrict__ x, const float *__restrict__ w /*[kt][3][CIN][64]*/, const float *__restrict__ bias,
-          float *__restrict__ out, int T, int F, int kt, int lookahead) {
+          float *__restrict__ out, int T, int F, int kt, int lookahead, int Tsx /* frames per stream in x */,
+          int Tx /* feature frames that exist; beyond = end of the stream = zero */) {
     extern __shared__ float s_in[];  // [(kInFrames + kt - 1)][(F + 2) * CIN]
     const int b = blockIdx.y, t0 = blockIdx.x * kInFrames;
     const int rows = kInFrames + kt - 1, ld = (F + 2) * CIN;
@@ -62,7 +64,7 @@ k_conv_in(const float *__restrict__ x, const float *__restrict__ w /*[kt][3][CIN
         int f = j / CIN - 1, ci = j - (f + 1) * CIN;
         int tp = t0 - (kt - 1) + r;  // time index in the look-ahead shifted feature sequence
         float v = 0.f;
-        if (f >= 0 && f < F && tp >= 0 && tp + lookahead < T) v = x[(((int64_t)b * T + tp + lookahead) * F + f) * CIN + ci];
+        if (f >= 0 && f < F && tp >= 0 && tp + lookahead < Tx) v = x[(((int64_t)b * Tsx + tp + lookahead) * F + f) * CIN + ci];
         s_in[i] = v;
     }
     const int cq = threadIdx.x & 15, fl = threadIdx.x >> 4;  // 16 channel quads x 16 f per pass
@@ -390,6 +392,10 @@ struct GruParams {
     float *hout;         // [B,T,H]
     int B, T, Bc;
     long long *dbg;      // optional [T][8] clock64 phase stamps of CTA 0 (dfb_debug_gru_timing)
+    // time-chunked execution (see GruWindow): frames t0 + t of buffers with Ts frames per stream, carried state h0 -> hT
+    const float *h0;
+    float *hT;
+    int t0, Ts;
 };
 
 template <int H, int C>
@@ -432,6 +438,13 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
     for (int bit = LPR / 2, n = V / 2; bit >= 1 && n >= 1; bit >>= 1, n >>= 1)
         if (kl & bit) vbase += n;
     for (int i = tid; i < 2 * kGruMaxBc * HP; i += kGruThreads) gru_smem[i] = 0.f;  // h0 = 0
+    if (p.h0) {  // carried state (every CTA of the cluster keeps the whole h of its streams)
+        __syncthreads();
+        for (int i = tid; i < nb * H; i += kGruThreads) {
+            const int s = i / H, gu = i - s * H;
+            s_h[0][s][(((gu % kGruKT) / 4) * LPR + gu / kGruKT) * 4 + (gu & 3)] = p.h0[(int64_t)(b0 + s) * H + gu];
+        }
+    }
     // gate-phase items (s, u): this thread's slots
     constexpr int kItems = (kGruMaxBc * U + kGruThreads - 1) / kGruThreads;
     float bh[kItems][3];
@@ -464,7 +477,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
             int item = tid + it * kGruThreads;
             if (item < nb * U) {
                 int s = item / U, u = item - s * U;
-                const float *xp = p.xproj + ((int64_t)(b0 + s) * p.T + t) * (3 * H) + rank * U + u;
+                const float *xp = p.xproj + ((int64_t)(b0 + s) * p.Ts + p.t0 + t) * (3 * H) + rank * U + u;
                 xr[it][0] = xp[0]; xr[it][1] = xp[H]; xr[it][2] = xp[2 * H];
             }
         }
@@ -536,8 +549,9 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru(GruParams p) {
                 const int hp = (((gu % kGruKT) / 4) * LPR + gu / kGruKT) * 4 + (gu & 3);  // hpos(gu)
                 float hprev = s_h[cur][s][hp];
                 float hn = (1.f - z) * n + z * hprev;
-                int64_t o = ((int64_t)(b0 + s) * p.T + t) * H + gu;
+                int64_t o = ((int64_t)(b0 + s) * p.Ts + p.t0 + t) * H + gu;
                 p.hout[o] = p.res ? hn + p.res[o] : hn;
+                if (p.hT && t + 1 == p.T) p.hT[(int64_t)(b0 + s) * H + gu] = hn;
                 if (t + 1 < p.T) {
                     // broadcast the new value to every CTA of the cluster (st.async DSMEM store)
                     const uint32_t dst_local = gru_smem_u32(&s_h[cur ^ 1][s][hp]);
@@ -707,6 +721,8 @@ using namespace dfb;
 
 
 struct GruLayerW { const float *w_ih_t, *w_hh, *b_ih, *b_hh; int in_dim; };
+// carried hidden states of one GRU stack between time chunks: h = [layers][B][H]; t0 = first frame the recurrences run
+struct GruChunk { float *h; bool have_state; int t0; };
 
 struct dfb_model {
     int device;
@@ -722,7 +738,9 @@ struct dfb_model {
     Arena arena;
     size_t max_workspace = size_t(24) << 30;  // dfb_enhance groups streams so that the arena stays below this
     std::vector<int64_t> erb_widths;          // band table the model was built for (checked against the dfb_state)
+    Arena aux_arena;                          // carried stream state + padded input of dfb_enhance
     cudaStream_t stream = nullptr;
+    cudaStream_t h2d = nullptr, d2h = nullptr;  // copy streams of dfb_enhance_host (both copy engines next to the compute)
     cudaStream_t aux = nullptr;             // DF decoder branch runs here, concurrently with the ERB decoder
     // forward() hops from the caller's stream onto `hi` (and `aux`), both at the greatest stream priority; `low`
     // (least priority) carries work that is off the critical path and only fills SMs the recurrences leave idle
@@ -796,6 +814,8 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
     int prio_hi = prio_greatest + erb_offset;
     if (prio_hi > prio_least) prio_hi = prio_least;
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&m->h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&m->d2h, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&m->aux, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaStreamCreateWithPriority(&m->hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&m->low, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
@@ -819,6 +839,9 @@ extern "C" void dfb_model_free(dfb_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     m->arena.release();
+    m->aux_arena.release();
+    if (m->h2d) cudaStreamDestroy(m->h2d);
+    if (m->d2h) cudaStreamDestroy(m->d2h);
     if (m->slab) cudaFree(m->slab);
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->aux) cudaStreamDestroy(m->aux);
@@ -934,8 +957,11 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
             const float *res_last, float *y, float *xproj, float *tmp_h, int B, int T,
             unsigned short *x_hi = nullptr, unsigned short *x_lo = nullptr, unsigned short *pl_hi = nullptr,
             unsigned short *pl_lo = nullptr, int wide = 0, unsigned short *out_hi = nullptr, unsigned short *out_lo = nullptr,
-            bool *out_planes_ok = nullptr) {
+            bool *out_planes_ok = nullptr, const GruChunk *ck = nullptr) {
     if (out_planes_ok) *out_planes_ok = false;
+    // time-chunked execution: the buffers hold T frames per stream, the recurrences run over frames [ck->t0, T) only and
+    // continue from / leave behind the carried per-layer states; the projections simply cover every row
+    const int t0 = ck ? ck->t0 : 0, Tn = T - t0;
     const int64_t M = (int64_t)B * T;
     const float *cur_in = x;
     int cur_dim = in_dim;
@@ -960,13 +986,15 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         }
         if (rc) return rc;
         float *dst = (l == layers - 1) ? y : tmp_h;
-        GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, T, 0, m->gru_dbg};
+        float *hs = ck && ck->h ? ck->h + (int64_t)l * B * H : nullptr;   // carried state of this layer [B][H]
+        GruWindow gw{ck && ck->have_state ? hs : nullptr, hs, t0, T};
+        GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, Tn, 0, m->gru_dbg, gw.h0, gw.hT, t0, T};
         if (H == 256 && m->gru_tc) {
             const bool last = l == layers - 1;
             const bool planes = last ? out_hi != nullptr : tc_proj;
             // the last layer's planes feed a grouped linear and include the residual; the others feed the next projection
             rc = launch_gru_tc(s, xproj, w_hh, b_hh, last ? res_last : nullptr, dst, planes ? (last ? out_hi : pl_hi) : nullptr,
-                               planes ? (last ? out_lo : pl_lo) : nullptr, B, T, m->gru_dbg, wide, last ? 1 : 0);
+                               planes ? (last ? out_lo : pl_lo) : nullptr, B, Tn, m->gru_dbg, wide, last ? 1 : 0, &gw);
             if (last && planes && out_planes_ok) *out_planes_ok = true;
             cur_hi = pl_hi; cur_lo = pl_lo;
         } else if (H == 256) {
@@ -1060,8 +1088,21 @@ static size_t fwd_plan(const dfb_model_config &c, size_t M, Arena *a, FwdBufs *f
     return bytes + 4096;
 }
 
+// Time-chunked execution (dfb_enhance's chunk loop, the streaming API): the window holds T frames per stream of which
+// the first Rc were already processed by the previous chunk (halo: the feed-forward layers recompute them from the
+// carried feature history, the recurrences skip them and continue from the carried hidden states).
+struct ChunkCtx {
+    int Rc;                        // halo frames at the head of the window
+    int Tsx, Tx;                   // feature buffers: frames per stream, frames that exist (beyond = end of stream)
+    float *h_enc, *h_erb, *h_df;   // carried GRU states [layers][B][H]
+    bool have_state;               // false for the first chunk of a stream (states start at zero)
+    float *dec_tail;               // (conv_kt == 2) last kHalo frames of dec_emb [B][kHalo][ED], right aligned
+    int dec_tail_n;                // frames of dec_tail that are valid
+};
+constexpr int kHalo = 8;           // >= temporal receptive field of every feed-forward chain of the shipped models
+
 static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
-                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s);
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s, ChunkCtx *cx = nullptr);
 
 extern "C" int dfb_model_forward(dfb_model *m, const float *d_feat_erb, const float *d_feat_spec, int64_t B64,
                                  int64_t T64, float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha,
@@ -1080,11 +1121,11 @@ extern "C" int dfb_model_forward(dfb_model *m, const float *d_feat_erb, const fl
 }
 
 static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
-                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in);
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in, ChunkCtx *cx);
 
 static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
-                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in) {
-    const int rc = forward_body(m, arena, d_feat_erb, d_feat_spec, B, T, d_m, d_coefs, d_lsnr, d_alpha, s_in);
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in, ChunkCtx *cx) {
+    const int rc = forward_body(m, arena, d_feat_erb, d_feat_spec, B, T, d_m, d_coefs, d_lsnr, d_alpha, s_in, cx);
     // an early return may leave work on the forked internal streams un-joined while the caller goes on to reuse
     // the arena: drain the device before handing the error back (error path only)
     if (rc) cudaDeviceSynchronize();
@@ -1092,8 +1133,12 @@ static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, con
 }
 
 static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
-                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in) {
+                        float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in, ChunkCtx *cx) {
     const dfb_model_config &c = m->cfg;
+    const int Tsx = cx ? cx->Tsx : T, Tx = cx ? cx->Tx : T;
+    GruChunk ck_enc{cx ? cx->h_enc : nullptr, cx && cx->have_state, cx ? cx->Rc : 0};
+    GruChunk ck_erb{cx ? cx->h_erb : nullptr, cx && cx->have_state, cx ? cx->Rc : 0};
+    GruChunk ck_df{cx ? cx->h_df : nullptr, cx && cx->have_state, cx ? cx->Rc : 0};
     // DFB_SERIAL=1: everything on the caller's stream (profiling: per-kernel times without overlap)
     static const bool serial = getenv("DFB_SERIAL") && atoi(getenv("DFB_SERIAL"));
     cudaStream_t s = serial ? s_in : m->hi;
@@ -1176,7 +1221,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
         int smem = (kInFrames + c.inp_kt - 1) * (E + 2) * 4;
         DFB_PROF("k_conv_in[erb_conv0]", s);
-        k_conv_in<1><<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead);
+        k_conv_in<1><<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead, Tsx, Tx);
         DFB_LAUNCH_CHECK();
     }
     const float *pw_sw = nullptr;  // set by blk(): swizzled BF16 hi | lo image of the [C_out][C_in] 1x1 weights (tensor-core path)
@@ -1208,7 +1253,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
             int smem = (kInFrames + c.inp_kt - 1) * (Fd + 2) * 2 * 4;
             DFB_PROF("k_conv_in[df_conv0]", sa);
-            k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead);
+            k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead, Tsx, Tx);
             DFB_LAUNCH_CHECK();
             DFB_CUDA(cudaEventRecord(m->ev_c0, sa));
         }
@@ -1274,7 +1319,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         float *gout = c.g_enc_out ? f.g_b : f.emb;
         Pl &pl_gout = c.g_enc_out ? pl_gb : pl_emb;
         if ((rc = run_gru(m, s, "enc.emb_gru", c.enc_gru_layers, H, f.g_a, H, nullptr, gout, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
-                          f.gh_hi, f.gh_lo, 0, gl_tc ? pl_gout.hi : nullptr, gl_tc ? pl_gout.lo : nullptr, &pl_gout.ok))) return rc;
+                          f.gh_hi, f.gh_lo, 0, gl_tc ? pl_gout.hi : nullptr, gl_tc ? pl_gout.lo : nullptr, &pl_gout.ok, cx ? &ck_enc : nullptr))) return rc;
         if (c.g_enc_out) {
             if ((rc = gl(s, "enc.emb_gru.out.gl", f.g_b, H, &pl_gb, c.g_enc_out, H, ED, ACT_RELU, nullptr, 0, f.emb, emb_dim, &pl_emb)))
                 return rc;
@@ -1307,7 +1352,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         const float *res = c.model_kind == 2 ? f.g_a2 : (early_skip ? f.dfskip : nullptr);
         if (early_skip) DFB_CUDA(cudaStreamWaitEvent(s, m->ev_skip, 0));
         if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a2, Hd, res, f.dfc, f.xproj2, f.g_h2, B, T, f.ga2_hi, f.ga2_lo,
-                          f.gh2_hi, f.gh2_lo, 1, gl_tc ? pl_dfc.hi : nullptr, gl_tc ? pl_dfc.lo : nullptr, &pl_dfc.ok))) return rc;
+                          f.gh2_hi, f.gh2_lo, 1, gl_tc ? pl_dfc.hi : nullptr, gl_tc ? pl_dfc.lo : nullptr, &pl_dfc.ok, cx ? &ck_df : nullptr))) return rc;
         if (c.g_df_skip && !early_skip) {
             if ((rc = gl(s, "df_dec.df_skip.gl", f.emb, emb_dim, &pl_emb, c.g_df_skip, emb_dim, Hd, ACT_NONE, f.dfc, Hd, f.dfc, Hd, nullptr)))
                 return rc;
@@ -1333,9 +1378,22 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         const float *res = c.model_kind == 2 ? f.g_a : nullptr;
         pl_gb.ok = false;
         if ((rc = run_gru(m, s, "erb_dec.emb_gru", c.erb_gru_layers, H, f.g_a, H, res, f.g_b, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
-                          f.gh_hi, f.gh_lo, 0, gl_tc ? pl_gb.hi : nullptr, gl_tc ? pl_gb.lo : nullptr, &pl_gb.ok))) return rc;
+                          f.gh_hi, f.gh_lo, 0, gl_tc ? pl_gb.hi : nullptr, gl_tc ? pl_gb.lo : nullptr, &pl_gb.ok, cx ? &ck_erb : nullptr))) return rc;
         if ((rc = gl(s, "erb_dec.emb_gru.out.gl", f.g_b, H, &pl_gb, c.g_erb_out, H, ED, ACT_RELU, nullptr, 0, f.dec_emb, ED, nullptr)))
             return rc;
+        if (cx && cx->dec_tail && c.conv_kt > 1) {
+            // kt = 2 decoder convs look one frame back into the halo, where this window's recurrence did not run: restore
+            // dec_emb there from the previous chunk, then keep this window's last frames for the next one
+            const size_t fb = sizeof(float) * ED;
+            const int nl = cx->Rc < cx->dec_tail_n ? cx->Rc : cx->dec_tail_n;
+            if (cx->have_state && nl > 0)
+                DFB_CUDA(cudaMemcpy2DAsync(f.dec_emb + (size_t)(cx->Rc - nl) * ED, fb * T, cx->dec_tail + (size_t)(kHalo - nl) * ED,
+                                           fb * kHalo, fb * nl, B, cudaMemcpyDeviceToDevice, s));
+            const int ns = T < kHalo ? T : kHalo;
+            DFB_CUDA(cudaMemcpy2DAsync(cx->dec_tail + (size_t)(kHalo - ns) * ED, fb * kHalo, f.dec_emb + (size_t)(T - ns) * ED, fb * T,
+                                       fb * ns, B, cudaMemcpyDeviceToDevice, s));
+            cx->dec_tail_n = ns;
+        }
         auto path = [&](DwPwParams &p, const char *pn, const float *pt, int64_t pfs) -> int {
             std::string n(pn);
             p.path = pt; p.path_fs = pfs;
@@ -1440,6 +1498,249 @@ extern "C" int dfb_model_set_max_workspace(dfb_model *m, int64_t bytes) {
     return DFB_OK;
 }
 
+
+// ============================================================== time-chunked executor ====
+// enhance() (df/enhance.py:206-250) and the streaming API run the path in TIME CHUNKS with carried per-stream state
+// (SURVEY.md Appendix D): memory is proportional to the chunk, not the signal; host copies of one chunk overlap the
+// compute of the next; and the frame-incremental API of the reference (libDF/src/tract.rs:509-642) is the same code
+// with a chunk of a few frames.  Per chunk the window [W0, d1) of DNN frames = kHalo already finished frames (their
+// feed-forward activations are recomputed from the carried feature history; receptive field <= 6 frames) + the new
+// frames [d0, d1); the recurrences run over the new frames only, from the carried hidden states.
+struct StreamState {
+    int B = 0;
+    int64_t a1 = 0, d1 = 0, e1 = 0;     // frames analysed / through the DNN / emitted as audio so far (absolute)
+    bool started = false, dnn_started = false;   // first analysis / first DNN chunk done (states are valid)
+    float *slab = nullptr;              // one allocation holding everything below
+    float *ana_mem = nullptr;           // [B][hop]       last input hop (streaming API; the batch path reads resident audio)
+    float *erb_state = nullptr, *unit_state = nullptr;   // [B][E], [B][Fd]  EMA states of the feature normalisation
+    float *h_enc = nullptr, *h_erb = nullptr, *h_df = nullptr;   // [layers][B][H]
+    float *t_spec = nullptr, *t_fe = nullptr, *t_fs = nullptr;   // last Hf = kHalo + Lmax frames of spec / features, right aligned
+    float *t_m = nullptr, *t_c = nullptr;                        // last kMcTail frames of m / coefs, right aligned
+    float *t_dec = nullptr;                                      // (conv_kt == 2) last kHalo frames of dec_emb
+    int n_feat = 0, n_mc = 0, n_dec = 0;                         // valid frames in the tails
+};
+constexpr int kMcTail = 6;   // >= lag + 3 (see run_chunk)
+
+struct ChunkGeom { int Lmax, lag, Hf; };
+static ChunkGeom chunk_geom(const dfb_model_config &c) {
+    ChunkGeom g;
+    g.Lmax = c.conv_lookahead > c.df_lookahead ? c.conv_lookahead : c.df_lookahead;
+    // DeepFilterNet2 filters the MASKED spectrum: frame t needs the masks of frames <= t + df_lookahead, so its audio
+    // trails the DNN frames by df_lookahead (deepfilternet2.py:494-503)
+    g.lag = c.model_kind == 2 ? c.df_lookahead : 0;
+    g.Hf = kHalo + g.Lmax;
+    return g;
+}
+
+static size_t state_floats(const dfb_model_config &c, const dfb_state *st, int B, size_t off[16]) {
+    const ChunkGeom g = chunk_geom(c);
+    const int E = c.nb_erb, Fd = c.nb_df, O2 = 2 * c.df_order, F = st->tb.F, ED = E / 4 * kCh;
+    size_t n = 0;
+    auto add = [&](int i, size_t k) { off[i] = n; n += (k + 63) & ~size_t(63); };
+    add(0, (size_t)B * st->hop); add(1, (size_t)B * E); add(2, (size_t)B * Fd);
+    add(3, (size_t)c.enc_gru_layers * B * c.emb_hidden); add(4, (size_t)c.erb_gru_layers * B * c.emb_hidden);
+    add(5, (size_t)c.df_gru_layers * B * c.df_hidden);
+    add(6, (size_t)B * g.Hf * 2 * F); add(7, (size_t)B * g.Hf * E); add(8, (size_t)B * g.Hf * 2 * Fd);
+    add(9, (size_t)B * kMcTail * E); add(10, (size_t)B * kMcTail * Fd * O2);
+    add(11, c.conv_kt > 1 ? (size_t)B * kHalo * ED : 0);
+    return n;
+}
+static void state_bind(StreamState &S, float *base, const size_t off[16], int B) {
+    S.B = B; S.slab = base;
+    S.ana_mem = base + off[0]; S.erb_state = base + off[1]; S.unit_state = base + off[2];
+    S.h_enc = base + off[3]; S.h_erb = base + off[4]; S.h_df = base + off[5];
+    S.t_spec = base + off[6]; S.t_fe = base + off[7]; S.t_fs = base + off[8];
+    S.t_m = base + off[9]; S.t_c = base + off[10]; S.t_dec = base + off[11];
+    S.a1 = S.d1 = S.e1 = 0; S.started = S.dnn_started = false; S.n_feat = S.n_mc = S.n_dec = 0;
+}
+
+// last n frames of buf [B][T][fe] -> tail [B][cap][fe] (right aligned), and back into frames [dst_t, dst_t + n) of a buffer
+static int save_tail(cudaStream_t s, const float *buf, int T, size_t fe, int n, float *tail, int cap, int B) {
+    if (n <= 0) return DFB_OK;
+    DFB_CUDA(cudaMemcpy2DAsync(tail + (size_t)(cap - n) * fe, sizeof(float) * fe * cap, buf + (size_t)(T - n) * fe, sizeof(float) * fe * T,
+                               sizeof(float) * fe * n, B, cudaMemcpyDeviceToDevice, s));
+    return DFB_OK;
+}
+static int load_tail(cudaStream_t s, float *buf, int T, size_t fe, int n, const float *tail, int cap, int dst_t, int B) {
+    if (n <= 0) return DFB_OK;
+    DFB_CUDA(cudaMemcpy2DAsync(buf + (size_t)dst_t * fe, sizeof(float) * fe * T, tail + (size_t)(cap - n) * fe, sizeof(float) * fe * cap,
+                               sizeof(float) * fe * n, B, cudaMemcpyDeviceToDevice, s));
+    return DFB_OK;
+}
+
+// bytes of workspace one window of Tw DNN frames needs per stream (features hold Tw + Lmax frames)
+static size_t chunk_bytes_per_stream(const dfb_model_config &c, const dfb_state *st, int Tw) {
+    const ChunkGeom g = chunk_geom(c);
+    const int E = c.nb_erb, Fd = c.nb_df, O2 = 2 * c.df_order, F = st->tb.F;
+    return (size_t)(Tw + g.Lmax) * (2 * F + E + 2 * Fd) * 4 + (size_t)Tw * (E + (size_t)Fd * O2) * 4 + fwd_plan(c, (size_t)Tw, nullptr, nullptr) +
+           16384;
+}
+
+// Where the audio of one chunk comes from and goes to.
+struct ChunkIO {
+    const float *audio; int64_t audio_T, audio_stride;  // signal the analysis reads: T samples per row (row pitch audio_stride)
+    int64_t audio_frame0;     // absolute frame index of the signal's first frame (0: resident whole signal; a0: streaming chunk)
+    const float *init_mem;    // [B][hop] samples before audio[0] (streaming) or null (zeros)
+    float *out; int64_t out_stride, out_len;
+    int64_t out_sample0;      // absolute synthesis sample (frame * hop + i) that lands at out[0]
+    float atten_lim;
+};
+
+// One chunk: analyse frames [S.a1, a1n), run the DNN over [S.d1, d1n), emit audio of frames [S.e1, e1n).
+// Tf_end: total frames of the stream when known (features / spectrum beyond it are zero), else -1.
+static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO &io, int64_t a1n, int64_t d1n, int64_t e1n,
+                     cudaStream_t s) {
+    const dfb_model_config &c = m->cfg;
+    const ChunkGeom g = chunk_geom(c);
+    const int B = S.B, E = c.nb_erb, Fd = c.nb_df, O2 = 2 * c.df_order, F = st->tb.F, hop = st->hop, ED = E / 4 * kCh;
+    const int64_t W0 = S.d1 > kHalo ? S.d1 - kHalo : 0;
+    const int Rc = (int)(S.d1 - W0), Tw = (int)(d1n - W0), Tsb = Tw + g.Lmax;
+    const int n_hist = (int)(S.a1 - W0);                 // feature frames of the window that are already known
+    const int n_new = (int)(a1n - S.a1), Tv = (int)(a1n - W0);
+    if (Tw < Rc || n_hist < 0 || n_hist > S.n_feat || Tv > Tsb || Tsb <= 0)
+        return fail(DFB_ERR_INVALID, "inconsistent chunk geometry");
+    const bool run_dnn = d1n > S.d1;      // a short streaming call may only add look-ahead frames
+    int rc;
+    m->arena.reset();
+    float *spec = m->arena.take<float>((size_t)B * Tsb * F * 2 + 2);
+    float *fe = m->arena.take<float>((size_t)B * Tsb * E);
+    float *fs = m->arena.take<float>((size_t)B * Tsb * Fd * 2);
+    float *mm = m->arena.take<float>((size_t)B * (Tw + 1) * E);
+    float *cc = m->arena.take<float>((size_t)B * (Tw + 1) * Fd * O2);
+    if (!cc) return fail(DFB_ERR_OOM, "chunk workspace exhausted");
+    // ---- features: carried history, then the new frames
+    if ((rc = load_tail(s, spec, Tsb, (size_t)2 * F, n_hist, S.t_spec, g.Hf, 0, B)) || (rc = load_tail(s, fe, Tsb, E, n_hist, S.t_fe, g.Hf, 0, B)) ||
+        (rc = load_tail(s, fs, Tsb, (size_t)2 * Fd, n_hist, S.t_fs, g.Hf, 0, B)))
+        return rc;
+    if (n_new > 0) {
+        AnaWindow w{(int)(S.a1 - io.audio_frame0), n_new, n_hist, Tsb, io.audio_stride};
+        if ((rc = launch_analysis(st, io.audio, B, io.audio_T, spec, fe, s, io.init_mem, &w))) return rc;
+        if ((rc = launch_feat_norm(fe + (size_t)n_hist * E, E, E, spec + (size_t)n_hist * 2 * F, Fd, F, B, n_new, c.norm_alpha,
+                                   S.started ? S.erb_state : nullptr, S.started ? S.unit_state : nullptr, fe + (size_t)n_hist * E,
+                                   fs + (size_t)n_hist * 2 * Fd, s, Tsb, S.erb_state, S.unit_state)))
+            return rc;
+    }
+    // ---- DNN over the window
+    if (run_dnn) {
+    ChunkCtx cx{Rc, Tsb, Tv, S.h_enc, S.h_erb, S.h_df, S.dnn_started, c.conv_kt > 1 ? S.t_dec : nullptr, S.n_dec};
+    if ((rc = forward_impl(m, m->arena, fe, fs, B, Tw, mm, cc, nullptr, nullptr, s, &cx))) return rc;
+    S.n_dec = cx.dec_tail_n;
+    S.dnn_started = true;
+    // the halo rows of m / coefs come from skipped recurrences: restore the last finished frames from the previous chunk
+    // (the apply kernel re-synthesises frame e0 - 1 for its overlap-add tail; DFN2's masked taps reach 2 frames further back)
+    if (Rc > 0 && S.n_mc > 0) {
+        const int n = S.n_mc < Rc ? S.n_mc : Rc;
+        if ((rc = load_tail(s, mm, Tw, E, n, S.t_m, kMcTail, Rc - n, B)) || (rc = load_tail(s, cc, Tw, (size_t)Fd * O2, n, S.t_c, kMcTail, Rc - n, B)))
+            return rc;
+    }
+    }
+    // ---- apply + synthesis of frames [e0, e1n)
+    if (run_dnn && e1n > S.e1) {
+        dfb::ApplyParams p{};
+        p.spec = (const float2 *)spec; p.m = mm; p.coefs = cc; p.audio = io.out; p.spec_out = nullptr;
+        p.out_stride = io.out_stride; p.out_len = io.out_len;
+        p.out_offset = io.out_sample0 - W0 * hop;     // g = t_window * hop + i - out_offset
+        p.Tf = (int)(e1n - W0); p.spec_T = Tsb; p.Tv = Tv; p.mc_T = Tw; p.t_first = (int)(S.e1 - W0);
+        p.mode = apply_mode(m); p.nb_df = Fd; p.order = c.df_order; p.lookahead = c.df_lookahead;
+        p.atten_lim = io.atten_lim;
+        if ((rc = launch_apply_synthesis(st, p, B, s))) return rc;
+    }
+    // ---- carry
+    {
+        const int nf = Tv < g.Hf ? Tv : g.Hf;
+        // the feature buffers hold Tsb frames per stream of which the first Tv are valid: keep the last nf valid ones
+        const size_t fes[3] = {(size_t)2 * F, (size_t)E, (size_t)2 * Fd};
+        float *bufs[3] = {spec, fe, fs}, *tails[3] = {S.t_spec, S.t_fe, S.t_fs};
+        for (int i = 0; i < 3; i++)
+            DFB_CUDA(cudaMemcpy2DAsync(tails[i] + (size_t)(g.Hf - nf) * fes[i], sizeof(float) * fes[i] * g.Hf,
+                                       bufs[i] + (size_t)(Tv - nf) * fes[i], sizeof(float) * fes[i] * Tsb, sizeof(float) * fes[i] * nf, B,
+                                       cudaMemcpyDeviceToDevice, s));
+        S.n_feat = nf;
+        if (run_dnn) {
+            const int nm = Tw < kMcTail ? Tw : kMcTail;
+            if ((rc = save_tail(s, mm, Tw, E, nm, S.t_m, kMcTail, B)) || (rc = save_tail(s, cc, Tw, (size_t)Fd * O2, nm, S.t_c, kMcTail, B))) return rc;
+            S.n_mc = nm;
+        }
+    }
+    (void)ED;
+    S.a1 = a1n; S.d1 = d1n; if (run_dnn) S.e1 = e1n;
+    S.started = true;
+    return DFB_OK;
+}
+
+// Chunk length (new DNN frames per chunk) for B streams under the workspace cap; 0 when not even a short chunk fits.
+static int pick_chunk(const dfb_model *m, const dfb_state *st, int64_t B, int64_t Tf, int min_chunks) {
+    const size_t per_frame = chunk_bytes_per_stream(m->cfg, st, 1024) / 1024 + 1;   // bytes per stream and window frame
+    const ChunkGeom g = chunk_geom(m->cfg);
+    int64_t tw = (int64_t)(m->max_workspace / ((size_t)B * per_frame)) - g.Lmax - 8;
+    int64_t tc = tw - kHalo;
+    if (tc > Tf) tc = Tf;
+    if (min_chunks > 1 && Tf >= (int64_t)min_chunks * 64) {
+        const int64_t t2 = (Tf + min_chunks - 1) / min_chunks;
+        if (t2 < tc) tc = t2;
+    }
+    if (tc < 1) return 0;
+    if (tc < Tf && tc < 32) return 0;   // a chunk this short wastes most of its window on the halo: use stream groups
+    return (int)tc;
+}
+// Runs the chunk loop over `nb` streams whose padded signal d_x [nb][Tp] is resident (or becomes resident chunk by chunk:
+// `before` / `after` are called around every chunk with the sample ranges it reads / has written).
+struct ChunkHooks {
+    // analysis of this chunk reads input samples [x0, x1) of every stream; output samples [y0, y1) have been written
+    std::function<int(int64_t x0, int64_t x1)> before;
+    std::function<int(int64_t y0, int64_t y1)> after;
+};
+
+static int enhance_group(dfb_model *m, dfb_state *st, const float *d_x, int64_t nb, int64_t Tp, int64_t in_valid, int pad,
+                         float lim, float *d_out, int64_t out_len, int tc, cudaStream_t s, const ChunkHooks *hooks) {
+    const dfb_model_config &c = m->cfg;
+    const ChunkGeom g = chunk_geom(c);
+    const int hop = st->hop, fft = st->fft;
+    const int64_t Tf = Tp / hop;
+    size_t off[16];
+    const size_t nstate = state_floats(c, st, (int)nb, off);
+    float *slab = m->aux_arena.take<float>(nstate);
+    if (!slab) return fail(DFB_ERR_OOM, "stream state arena exhausted");
+    StreamState S;
+    state_bind(S, slab, off, (int)nb);
+    int rc = DFB_OK;
+    const int64_t delay = pad ? fft - hop : 0;
+    while (S.d1 < Tf) {
+        const int64_t d1n = S.d1 + tc < Tf ? S.d1 + tc : Tf;
+        const int64_t a1n = d1n + g.Lmax < Tf ? d1n + g.Lmax : Tf;
+        const int64_t e1n = d1n == Tf ? Tf : d1n - g.lag;
+        if (hooks && hooks->before) {
+            int64_t x0 = S.a1 * hop, x1 = a1n * hop;
+            if (x1 > in_valid) x1 = in_valid;
+            if (x0 < x1 && (rc = hooks->before(x0, x1))) break;
+        }
+        const int64_t e0 = S.e1;
+        ChunkIO io{d_x, Tp, Tp, 0, nullptr, d_out, out_len, out_len, delay, lim};
+        if ((rc = run_chunk(m, st, S, io, a1n, d1n, e1n > S.e1 ? e1n : S.e1, s))) break;
+        if (hooks && hooks->after) {
+            int64_t y0 = e0 * hop - delay, y1 = S.e1 * hop - delay;
+            if (y0 < 0) y0 = 0;
+            if (y1 > out_len) y1 = out_len;
+            if (y0 < y1 && (rc = hooks->after(y0, y1))) break;
+        }
+    }
+    return rc;
+}
+
+// enhance(): df/enhance.py:206-250.  Time chunks (above) inside stream groups: a group is as many streams as fit the
+// workspace cap with a reasonable chunk; streams are independent (per-channel state reset, pyDF/src/lib.rs:56-58).
+static int enhance_plan(dfb_model *m, dfb_state *st, int64_t B, int64_t Tf, int min_chunks, int64_t *group_out, int *tc_out) {
+    int64_t group = B > 65535 ? 65535 : B;
+    int tc = 0;
+    while ((tc = pick_chunk(m, st, group, Tf, min_chunks)) == 0) {
+        if (group == 1) return fail(DFB_ERR_OOM, "workspace cap of %zu bytes is too small for a single stream", m->max_workspace);
+        group = (group + 1) / 2;
+    }
+    *group_out = group; *tc_out = tc;
+    const ChunkGeom g = chunk_geom(m->cfg);
+    return m->arena.reserve(chunk_bytes_per_stream(m->cfg, st, tc + kHalo) * (size_t)group + ((size_t)g.Lmax << 10) + (2 << 20));
+}
+
 extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, int64_t B, int64_t T, int pad,
                            float atten_lim_db, float *d_out, void *stream) {
     if (!m || !st || !d_audio || !d_out) return fail(DFB_ERR_INVALID, "null argument");
@@ -1447,66 +1748,234 @@ extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, in
     if (int rcs = check_state(m, st)) return rcs;
     DFB_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = (cudaStream_t)stream;
-    const dfb_model_config &c = m->cfg;
-    const int hop = st->hop, fft = st->fft, F = st->tb.F, E = c.nb_erb, Fd = c.nb_df, O2 = 2 * c.df_order;
+    const int hop = st->hop, fft = st->fft;
     // pad = True appends fft zeros (enhance.py:230-233): Tf = (T + fft) / hop
     const int64_t Tp = pad ? T + fft : T;
     const int64_t Tf = Tp / hop;
     if (Tf <= 0) return fail(DFB_ERR_INVALID, "input shorter than one hop");
     const int64_t out_len = dfb_enhance_out_len(st, T, pad);
-    const size_t per_stream = ((size_t)Tp + (size_t)Tf * (2 * F + E + 2 * Fd + E + (size_t)Fd * O2)) * 4 +
-                              fwd_plan(c, (size_t)Tf, nullptr, nullptr) + 8192;
-    int64_t group = (int64_t)(m->max_workspace / per_stream);
-    if (group < 1) group = 1;
-    if (group > B) group = B;
-    if (group > 65535) group = 65535;
-    int rc = m->arena.reserve(per_stream * (size_t)group + (2 << 20));
-    if (rc) return rc;
+    int64_t group = 0;
+    int tc = 0, rc;
+    if ((rc = enhance_plan(m, st, B, Tf, 1, &group, &tc))) return rc;
     const float lim = (atten_lim_db > 0.f) ? powf(10.f, -atten_lim_db / 20.f) : 0.f;
-    for (int64_t b0 = 0; b0 < B; b0 += group) {
+    size_t off[16];
+    if ((rc = m->aux_arena.reserve((state_floats(m->cfg, st, (int)group, off) + (pad ? (size_t)group * Tp : 0)) * sizeof(float) + 8192))) return rc;
+    for (int64_t b0 = 0; b0 < B && !rc; b0 += group) {
         const int64_t nb = (B - b0 < group) ? B - b0 : group;
-        m->arena.reset();
         const float *x = d_audio + b0 * T;
-        float *xp = nullptr;
+        m->aux_arena.reset();
+        float *xp = pad ? m->aux_arena.take<float>((size_t)nb * Tp) : nullptr;
         if (pad) {
-            xp = m->arena.take<float>((size_t)nb * Tp);
-            DFB_CUDA(cudaMemsetAsync(xp, 0, sizeof(float) * nb * Tp, s));
-            DFB_CUDA(cudaMemcpy2DAsync(xp, sizeof(float) * Tp, x, sizeof(float) * T, sizeof(float) * T, nb,
-                                       cudaMemcpyDeviceToDevice, s));
+            rc = cudaMemsetAsync(xp, 0, sizeof(float) * nb * Tp, s) != cudaSuccess ||
+                 cudaMemcpy2DAsync(xp, sizeof(float) * Tp, x, sizeof(float) * T, sizeof(float) * T, nb, cudaMemcpyDeviceToDevice, s) != cudaSuccess
+                     ? fail(DFB_ERR_CUDA, "padding copy failed") : DFB_OK;
             x = xp;
         }
-        float *spec = m->arena.take<float>((size_t)nb * Tf * F * 2 + 2);
-        float *fe = m->arena.take<float>((size_t)nb * Tf * E);
-        float *fs = m->arena.take<float>((size_t)nb * Tf * Fd * 2);
-        float *mm = m->arena.take<float>((size_t)nb * Tf * E);
-        float *cc = m->arena.take<float>((size_t)nb * Tf * Fd * O2);
-        if (!cc) return fail(DFB_ERR_OOM, "enhance workspace exhausted");
-        if ((rc = dfb_features(st, x, nb, Tp, Fd, c.norm_alpha, spec, fe, fs, s))) return rc;
-        if ((rc = forward_impl(m, m->arena, fe, fs, (int)nb, (int)Tf, mm, cc, nullptr, nullptr, s))) return rc;
-        dfb::ApplyParams p{};
-        p.spec = (const float2 *)spec; p.m = mm; p.coefs = cc; p.audio = d_out + b0 * out_len; p.spec_out = nullptr;
-        p.out_stride = out_len; p.out_offset = pad ? (fft - hop) : 0; p.out_len = out_len;
-        p.Tf = (int)Tf; p.mode = apply_mode(m); p.nb_df = Fd; p.order = c.df_order; p.lookahead = c.df_lookahead;
-        p.atten_lim = lim;
-        if ((rc = launch_apply_synthesis(st, p, nb, s))) return rc;
+        if (!rc) rc = enhance_group(m, st, x, nb, Tp, Tp, pad, lim, d_out + b0 * out_len, out_len, tc, s, nullptr);
     }
     m->arena.reset();
-    return DFB_OK;
+    return rc;
 }
 
+// Host buffers: the batch is staged chunk by chunk -- the H2D copy of chunk c + 1 and the D2H copy of chunk c - 1 run on
+// their own streams (both copy engines) while chunk c computes.
 extern "C" int dfb_enhance_host(dfb_model *m, dfb_state *st, const float *h_audio, int64_t B, int64_t T, int pad,
                                 float atten_lim_db, float *h_out) {
     if (!m || !st || !h_audio || !h_out) return fail(DFB_ERR_INVALID, "null argument");
     if (B <= 0 || T <= 0) return fail(DFB_ERR_INVALID, "empty input");
+    if (int rcs = check_state(m, st)) return rcs;
     DFB_CUDA(cudaSetDevice(m->device));
+    const int hop = st->hop, fft = st->fft;
+    const int64_t Tp = pad ? T + fft : T, Tf = Tp / hop;
+    if (Tf <= 0) return fail(DFB_ERR_INVALID, "input shorter than one hop");
     const int64_t out_len = dfb_enhance_out_len(st, T, pad);
-    int rc = st->arena.reserve(sizeof(float) * (size_t)B * (T + out_len) + 4096);
-    if (rc) return rc;
+    int64_t group = 0;
+    int tc = 0, rc;
+    static const int host_chunks = getenv("DFB_HOST_CHUNKS") ? atoi(getenv("DFB_HOST_CHUNKS")) : 6;
+    if ((rc = enhance_plan(m, st, B, Tf, host_chunks, &group, &tc))) return rc;
+    const float lim = (atten_lim_db > 0.f) ? powf(10.f, -atten_lim_db / 20.f) : 0.f;
+    size_t off[16];
+    if ((rc = m->aux_arena.reserve(state_floats(m->cfg, st, (int)group, off) * sizeof(float) + 8192))) return rc;
+    if ((rc = st->arena.reserve(sizeof(float) * (size_t)group * (Tp + out_len) + 4096))) return rc;
     st->arena.reset();
-    float *d_in = st->arena.take<float>((size_t)B * T), *d_out = st->arena.take<float>((size_t)B * out_len);
-    DFB_CUDA(cudaMemcpyAsync(d_in, h_audio, sizeof(float) * B * T, cudaMemcpyHostToDevice, m->stream));
-    if ((rc = dfb_enhance(m, st, d_in, B, T, pad, atten_lim_db, d_out, m->stream))) return rc;
-    DFB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(float) * B * out_len, cudaMemcpyDeviceToHost, m->stream));
-    DFB_CUDA(cudaStreamSynchronize(m->stream));
+    float *d_in = st->arena.take<float>((size_t)group * Tp), *d_out = st->arena.take<float>((size_t)group * out_len);
+    cudaStream_t sc = m->stream, sh = m->h2d, sd = m->d2h;
+    std::vector<cudaEvent_t> evs;
+    auto new_event = [&]() { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
+    for (int64_t b0 = 0; b0 < B && !rc; b0 += group) {
+        const int64_t nb = (B - b0 < group) ? B - b0 : group;
+        const float *hx = h_audio + b0 * T;
+        float *hy = h_out + b0 * out_len;
+        // the previous group's D2H copies read d_out and its compute read d_in: order this group's first writes after them
+        cudaEvent_t e0 = new_event();
+        DFB_CUDA(cudaEventRecord(e0, sd));
+        DFB_CUDA(cudaStreamWaitEvent(sc, e0, 0));
+        cudaEvent_t e1 = new_event();
+        DFB_CUDA(cudaEventRecord(e1, sc));
+        DFB_CUDA(cudaStreamWaitEvent(sh, e1, 0));
+        if (pad)  // zero tail of the padded rows (enhance.py:233)
+            DFB_CUDA(cudaMemset2DAsync(d_in + T, sizeof(float) * Tp, 0, sizeof(float) * (Tp - T), nb, sh));
+        ChunkHooks hooks;
+        hooks.before = [&](int64_t x0, int64_t x1) -> int {
+            if (x1 > T) x1 = T;
+            if (x0 < x1)
+                DFB_CUDA(cudaMemcpy2DAsync(d_in + x0, sizeof(float) * Tp, hx + x0, sizeof(float) * T, sizeof(float) * (x1 - x0), nb,
+                                           cudaMemcpyHostToDevice, sh));
+            cudaEvent_t e = new_event();
+            DFB_CUDA(cudaEventRecord(e, sh));
+            DFB_CUDA(cudaStreamWaitEvent(sc, e, 0));
+            return DFB_OK;
+        };
+        hooks.after = [&](int64_t y0, int64_t y1) -> int {
+            cudaEvent_t e = new_event();
+            DFB_CUDA(cudaEventRecord(e, sc));
+            DFB_CUDA(cudaStreamWaitEvent(sd, e, 0));
+            DFB_CUDA(cudaMemcpy2DAsync(hy + y0, sizeof(float) * out_len, d_out + y0, sizeof(float) * out_len, sizeof(float) * (y1 - y0), nb,
+                                       cudaMemcpyDeviceToHost, sd));
+            return DFB_OK;
+        };
+        m->aux_arena.reset();
+        rc = enhance_group(m, st, d_in, nb, Tp, T, pad, lim, d_out, out_len, tc, sc, &hooks);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sd), e3 = cudaStreamSynchronize(sh);
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    m->arena.reset();
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(DFB_ERR_CUDA, "enhance_host failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return DFB_OK;
+}
+
+// ============================================================== streaming API ====
+// Frame-incremental processing with carried state: the batched counterpart of the reference's single-stream runtime
+// (libDF/src/tract.rs:509-642 `DfTract::process`, C ABI libDF/src/capi.rs:83-253 df_create / df_process_frame / df_free).
+// Every call feeds n >= 1 hops per stream and returns n hops; the output trails the input by `latency` frames
+// (max(conv_lookahead, df_lookahead), + df_lookahead for DeepFilterNet2) on top of the STFT's own fft - hop samples,
+// i.e. the concatenated output equals enhance(pad=False) of the concatenated input delayed by latency * hop samples.
+struct dfb_stream {
+    dfb_model *m;
+    dfb_state *st;
+    int B;
+    float lim;
+    StreamState S;
+    float *slab = nullptr;
+    float *stage_in = nullptr, *stage_out = nullptr;   // device staging of the *_host entry point
+    size_t stage_cap = 0;
+};
+
+extern "C" int dfb_stream_create(dfb_stream **out, dfb_model *m, dfb_state *st, int64_t B, float atten_lim_db) {
+    if (!out || !m || !st || B <= 0 || B > 65535) return fail(DFB_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    if (int rcs = check_state(m, st)) return rcs;
+    DFB_CUDA(cudaSetDevice(m->device));
+    dfb_stream *h = new dfb_stream();
+    h->m = m; h->st = st; h->B = (int)B;
+    h->lim = (atten_lim_db > 0.f) ? powf(10.f, -atten_lim_db / 20.f) : 0.f;
+    size_t off[16];
+    const size_t n = state_floats(m->cfg, st, (int)B, off);
+    if (cudaMalloc(&h->slab, n * sizeof(float)) != cudaSuccess) { delete h; return fail(DFB_ERR_OOM, "stream state allocation failed"); }
+    cudaMemset(h->slab, 0, n * sizeof(float));
+    state_bind(h->S, h->slab, off, (int)B);
+    *out = h;
+    return DFB_OK;
+}
+
+extern "C" void dfb_stream_free(dfb_stream *h) {
+    if (!h) return;
+    cudaSetDevice(h->m->device);
+    if (h->slab) cudaFree(h->slab);
+    if (h->stage_in) cudaFree(h->stage_in);
+    if (h->stage_out) cudaFree(h->stage_out);
+    delete h;
+}
+
+extern "C" int dfb_stream_reset(dfb_stream *h) {
+    if (!h) return fail(DFB_ERR_INVALID, "null stream");
+    size_t off[16];
+    state_floats(h->m->cfg, h->st, h->B, off);
+    state_bind(h->S, h->slab, off, h->B);
+    return DFB_OK;
+}
+
+extern "C" int64_t dfb_stream_latency_frames(const dfb_stream *h) {
+    if (!h) return -1;
+    const ChunkGeom g = chunk_geom(h->m->cfg);
+    return g.Lmax + g.lag;
+}
+extern "C" int64_t dfb_stream_frame_length(const dfb_stream *h) { return h ? h->st->hop : -1; }  // capi.rs df_get_frame_length
+
+static int stream_step(dfb_stream *h, const float *d_in, int64_t n, bool flush, float *d_out, cudaStream_t s) {
+    dfb_model *m = h->m;
+    dfb_state *st = h->st;
+    StreamState &S = h->S;
+    const ChunkGeom g = chunk_geom(m->cfg);
+    const int hop = st->hop, B = h->B;
+    const int64_t Ltot = g.Lmax + g.lag;
+    const int64_t n_out = flush ? Ltot : n;
+    const int64_t a0 = S.a1, a1n = a0 + (flush ? 0 : n);
+    int64_t d1n = flush ? a1n : a1n - g.Lmax, e1n = flush ? a1n : d1n - g.lag;
+    if (d1n < S.d1) d1n = S.d1;
+    if (e1n < S.e1) e1n = S.e1;
+    // the window of this call: halo + new DNN frames (+ look-ahead)
+    const int64_t W0 = S.d1 > kHalo ? S.d1 - kHalo : 0;
+    const int Tw = (int)(d1n - W0);
+    int rc = m->arena.reserve(chunk_bytes_per_stream(m->cfg, st, Tw + 1) * (size_t)B + (2 << 20));
+    if (rc) return rc;
+    // output slot j (hop j of d_out) carries frame a0 - Ltot + j (flush: a1 - Ltot + j); frames < 0 are silence
+    const int64_t f0 = (flush ? S.a1 : a0) - Ltot;
+    if (f0 < 0 || e1n <= S.e1) DFB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * B * n_out * hop, s));
+    ChunkIO io{d_in, (flush ? 0 : n) * hop, (flush ? 0 : n) * hop, a0, S.started ? S.ana_mem : nullptr, d_out, n_out * hop, n_out * hop,
+               f0 * hop, h->lim};
+    if (!flush && a1n > a0) {
+        // zero analysis memory before the very first frame
+        if (!S.started) DFB_CUDA(cudaMemsetAsync(S.ana_mem, 0, sizeof(float) * B * hop, s));
+        io.init_mem = S.ana_mem;
+    }
+    if ((rc = run_chunk(m, st, S, io, a1n, d1n, e1n, s))) return rc;
+    if (!flush)  // carried analysis memory: the last hop of this call's input
+        DFB_CUDA(cudaMemcpy2DAsync(S.ana_mem, sizeof(float) * hop, d_in + (n - 1) * hop, sizeof(float) * n * hop, sizeof(float) * hop, B,
+                                   cudaMemcpyDeviceToDevice, s));
+    m->arena.reset();
+    return DFB_OK;
+}
+
+// d_in [B][n_frames * hop] -> d_out [B][n_frames * hop] (device pointers, asynchronous on `stream`)
+extern "C" int dfb_stream_process(dfb_stream *h, const float *d_in, int64_t n_frames, float *d_out, void *stream) {
+    if (!h || !d_in || !d_out || n_frames <= 0) return fail(DFB_ERR_INVALID, "bad argument");
+    DFB_CUDA(cudaSetDevice(h->m->device));
+    return stream_step(h, d_in, n_frames, false, d_out, (cudaStream_t)stream);
+}
+
+// End of the stream: the `latency` frames still in flight, computed with zero look-ahead exactly like the end of a
+// batch enhance(); d_out [B][latency * hop].  The stream must be reset before it is fed again.
+extern "C" int dfb_stream_flush(dfb_stream *h, float *d_out, void *stream) {
+    if (!h || !d_out) return fail(DFB_ERR_INVALID, "bad argument");
+    DFB_CUDA(cudaSetDevice(h->m->device));
+    if (dfb_stream_latency_frames(h) == 0) return DFB_OK;
+    return stream_step(h, nullptr, 0, true, d_out, (cudaStream_t)stream);
+}
+
+// host-pointer variant (synchronous): h_in / h_out [B][n_frames * hop]; h_in == NULL flushes into h_out [B][latency * hop]
+extern "C" int dfb_stream_process_host(dfb_stream *h, const float *h_in, int64_t n_frames, float *h_out) {
+    if (!h || !h_out || (h_in && n_frames <= 0)) return fail(DFB_ERR_INVALID, "bad argument");
+    DFB_CUDA(cudaSetDevice(h->m->device));
+    const bool flush = h_in == nullptr;
+    const int64_t nf = flush ? dfb_stream_latency_frames(h) : n_frames;
+    if (nf == 0) return DFB_OK;
+    const size_t bytes = sizeof(float) * (size_t)h->B * nf * h->st->hop;
+    if (bytes > h->stage_cap) {
+        if (h->stage_in) cudaFree(h->stage_in);
+        if (h->stage_out) cudaFree(h->stage_out);
+        h->stage_in = h->stage_out = nullptr; h->stage_cap = 0;
+        if (cudaMalloc(&h->stage_in, bytes) != cudaSuccess || cudaMalloc(&h->stage_out, bytes) != cudaSuccess)
+            return fail(DFB_ERR_OOM, "stream staging allocation failed");
+        h->stage_cap = bytes;
+    }
+    cudaStream_t s = h->m->stream;
+    if (!flush) DFB_CUDA(cudaMemcpyAsync(h->stage_in, h_in, bytes, cudaMemcpyHostToDevice, s));
+    int rc = stream_step(h, h->stage_in, nf, flush, h->stage_out, s);
+    if (rc) return rc;
+    DFB_CUDA(cudaMemcpyAsync(h_out, h->stage_out, bytes, cudaMemcpyDeviceToHost, s));
+    DFB_CUDA(cudaStreamSynchronize(s));
     return DFB_OK;
 }

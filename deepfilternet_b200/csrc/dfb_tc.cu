@@ -523,6 +523,11 @@ struct GruTcParams {
     float *hout;         // [B,T,H]
     unsigned short *hout_hi, *hout_lo;  // optional BF16 hi/lo planes of hout (A operand of the next projection GEMM)
     int planes_res;      // 1: the planes hold hout + res (input of a grouped linear), 0: the residual-free h
+    // time-chunked execution: steps t = 0 .. T-1 are frames t0 + t of buffers holding Ts frames per stream; the
+    // recurrence starts from h0 [B][256] (null: zeros) and leaves its final state in hT [B][256] (may alias h0)
+    const float *h0;
+    float *hT;
+    int t0, Ts;
     int B, T, Bc;
     long long *dbg;      // optional [T][8] clock64 stamps of CTA 0 (0-3: MMA thread, 4-7: gate thread 0)
 };
@@ -554,6 +559,19 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    if (p.h0) {  // carried state: every CTA builds the whole operand h_{-1} of its streams in buffer 0
+        for (int i = tid; i < nb * (kGtH / 2); i += kGtThreads) {
+            const int s = i / (kGtH / 2), gu = (i - s * (kGtH / 2)) * 2;
+            const float2 hv = *reinterpret_cast<const float2 *>(p.h0 + (int64_t)(b0 + s) * kGtH + gu);
+            unsigned short h0b, l0b, h1b, l1b;
+            bf16_split(hv.x, h0b, l0b);
+            bf16_split(hv.y, h1b, l1b);
+            const uint32_t off = (uint32_t)((gu >> 3) * Cfg::kLbo + (s >> 3) * Cfg::kSbo + (s & 7) * 16 + (gu & 7) * 2);
+            *reinterpret_cast<uint32_t *>(sm.h[0] + off) = h0b | (uint32_t)h1b << 16;
+            *reinterpret_cast<uint32_t *>(sm.h[0] + off + Cfg::kPlane) = l0b | (uint32_t)l1b << 16;
+        }
+        fence_proxy_async();
+    }
     // ---- W_hh slice -> TMEM as BF16 hi | lo planes: lane = row rho (gate * 32 + unit; lanes 96..127 zero),
     //      column j of a plane = elements (2 j, 2 j + 1).  Warps 0-3 own lane quarters 0-3.
     if (warp < 4) {
@@ -620,6 +638,10 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
         const bool active = s < nb;
         const int gu = rank * kGtU + 2 * up;       // first of the two global hidden units of this thread
         float hprev0 = 0.f, hprev1 = 0.f;
+        if (p.h0 && active) {
+            const float2 hv = *reinterpret_cast<const float2 *>(p.h0 + (int64_t)(b0 + s) * H + gu);
+            hprev0 = hv.x; hprev1 = hv.y;
+        }
         const float2 bhr = *reinterpret_cast<const float2 *>(p.bhh + gu), bhz = *reinterpret_cast<const float2 *>(p.bhh + H + gu),
                      bhn = *reinterpret_cast<const float2 *>(p.bhh + 2 * H + gu);
         // byte offset of this (stream, unit pair) inside an h buffer (hi plane): core matrix gu / 8, row group s / 8
@@ -632,7 +654,7 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
             float2 xr = make_float2(0.f, 0.f), xz = xr, xn = xr;
             uint32_t vhi = 0, vlo = 0;
             if (active) {
-                const float *xp = p.xproj + ((int64_t)(b0 + s) * T + t) * (3 * H) + gu;
+                const float *xp = p.xproj + ((int64_t)(b0 + s) * p.Ts + p.t0 + t) * (3 * H) + gu;
                 xr = *reinterpret_cast<const float2 *>(xp);
                 xz = *reinterpret_cast<const float2 *>(xp + H);
                 xn = *reinterpret_cast<const float2 *>(xp + 2 * H);
@@ -687,8 +709,9 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
                 asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kGateThreads) : "memory");
             }
             if (active) {  // global result last: nothing on the recurrence's critical path waits for it
-                const int64_t o = ((int64_t)(b0 + s) * T + t) * H + gu;
+                const int64_t o = ((int64_t)(b0 + s) * p.Ts + p.t0 + t) * H + gu;
                 float2 ov = make_float2(hprev0, hprev1);
+                if (p.hT && t + 1 == T) *reinterpret_cast<float2 *>(p.hT + (int64_t)(b0 + s) * H + gu) = ov;
                 if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
                 *reinterpret_cast<float2 *>(p.hout + o) = ov;
                 if (p.hout_hi) {  // residual-free h (the next layer's projection input) or the layer output
@@ -736,8 +759,10 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
 
 // wide != 0: 32 streams per cluster when the batch needs more than 4 clusters of 16 (see GtCfg)
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
-                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg, int wide, int planes_res) {
-    GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, planes_res, B, T, 0, dbg};
+                  unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg, int wide, int planes_res,
+                  const GruWindow *w) {
+    GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, planes_res, w ? w->h0 : nullptr, w ? w->hT : nullptr,
+                  w ? w->t0 : 0, w ? w->Ts : T, B, T, 0, dbg};
     static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
     const bool use32 = force ? force == 32 : (wide && B > 64);
     return use32 ? launch_gru_tc_n<32>(s, p) : launch_gru_tc_n<16>(s, p);

@@ -165,13 +165,39 @@ int dfb_model_forward_full(dfb_model *m, dfb_state *st, const float *d_spec, con
  * audio f32[B,T] -> enhanced f32[B,T_out].  pad != 0: zero-pad fft_size samples at the end and
  * crop the STFT delay (T_out = T); pad == 0: T_out = (T / hop) * hop, delayed by fft - hop.
  * atten_lim_db <= 0 disables the attenuation limit (enhance.py:238-240).
- * The apply + ISTFT stage is one fused kernel (gain x spectrum + deep filter + irFFT + OLA). */
+ * The apply + ISTFT stage is one fused kernel (gain x spectrum + deep filter + irFFT + OLA).
+ * The signal is processed in time chunks with carried state (see "streaming" below), so the device workspace does
+ * not grow with T; dfb_enhance_host additionally overlaps the H2D / D2H copies of neighbouring chunks with the compute. */
 int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, int64_t B, int64_t T, int pad,
                 float atten_lim_db, float *d_out, void *stream);
 int dfb_enhance_host(dfb_model *m, dfb_state *st, const float *h_audio, int64_t B, int64_t T, int pad,
                      float atten_lim_db, float *h_out);
 /* output length of dfb_enhance for a given input length */
 int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad);
+/* ------------------------------------------------------------------ streaming -----------------
+ * Frame-incremental processing with carried per-stream state: the batched counterpart of the reference's
+ * single-stream runtime `DfTract::process` (libDF/src/tract.rs:509-642) and its C ABI (libDF/src/capi.rs:83-253:
+ * df_create / df_get_frame_length / df_process_frame / df_free).  The state carried between calls is SURVEY.md
+ * Appendix D: STFT / ISTFT memories, normalisation EMAs, GRU hidden states, conv / deep-filter history.
+ * Every call feeds n >= 1 hops per stream and returns n hops; the output trails the input by
+ * dfb_stream_latency_frames() hops (the model's look-ahead) on top of the STFT's fft - hop samples: the concatenated
+ * output equals dfb_enhance(pad = 0) of the concatenated input, delayed by latency * hop samples.  dfb_enhance itself
+ * runs on the same time-chunked executor.  Not built: the LSNR stage gating (tract.rs:658-672) and the post filter
+ * (lib.rs:446-471) of the Rust runtime -- the Python path this library mirrors has neither. */
+typedef struct dfb_stream dfb_stream;
+/* capi.rs df_create: B independent streams on the model's device; atten_lim_db <= 0 disables the limit */
+int dfb_stream_create(dfb_stream **out, dfb_model *m, dfb_state *st, int64_t B, float atten_lim_db);
+void dfb_stream_free(dfb_stream *s);                       /* capi.rs df_free */
+int dfb_stream_reset(dfb_stream *s);                       /* back to the initial state (all memories zero) */
+int64_t dfb_stream_frame_length(const dfb_stream *s);      /* capi.rs df_get_frame_length: hop size in samples */
+int64_t dfb_stream_latency_frames(const dfb_stream *s);    /* hops the output trails the input by */
+/* capi.rs df_process_frame, batched and for n_frames hops at once: d_in / d_out f32[B][n_frames * hop] (device) */
+int dfb_stream_process(dfb_stream *s, const float *d_in, int64_t n_frames, float *d_out, void *stream);
+/* end of stream: the latency frames still in flight, d_out f32[B][latency * hop]; reset before feeding again */
+int dfb_stream_flush(dfb_stream *s, float *d_out, void *stream);
+/* host pointers, synchronous; h_in == NULL flushes into h_out f32[B][latency * hop] */
+int dfb_stream_process_host(dfb_stream *s, const float *h_in, int64_t n_frames, float *h_out);
+
 /* Arithmetic of the dense contractions -- a bit mask; everything that is not a contraction is always IEEE fp32:
  *   bit 1 (2): GRU recurrence W_hh h on tcgen05 with BF16 hi/lo split operands (3 MMAs per product, fp32 accumulate)
  *   bit 2 (4): GRU input projections W_ih x on the BF16x3 tcgen05 GEMM
@@ -179,8 +205,9 @@ int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad);
  * 0 = FFMA everywhere; 14 = the default of the Python mirror (deepfilternet_b200/model.py set_precision).
  * BF16x3 is ~2^-17 relative per product: 1e-7 .. 4e-7 RMS end to end against the fp32 oracle (bound 1e-4). */
 int dfb_model_set_precision(dfb_model *m, int mode);
-/* Cap (bytes) of the per-call device workspace of dfb_enhance; streams are processed in groups that fit below it
- * (default 24 GB, or DFB_MAX_WORKSPACE_MB in the environment at dfb_model_create). */
+/* Cap (bytes) of the per-call device workspace of dfb_enhance: the batch is processed in time chunks (and, for very
+ * large batches, stream groups) that fit below it (default 24 GB, or DFB_MAX_WORKSPACE_MB in the environment at
+ * dfb_model_create). */
 int dfb_model_set_max_workspace(dfb_model *m, int64_t bytes);
 /* Debug aid: steps > 0 with h_out == NULL arms clock64() phase stamps ([steps][8]) for the following
  * GRU launches; a second call with h_out != NULL copies the stamps of the last launch and disarms. */

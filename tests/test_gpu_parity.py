@@ -400,3 +400,64 @@ def test_mismatched_df_state_is_rejected(states):
         enhance(model, other, synth_audio(1, 4800, seed=1))
     with pytest.raises(ValueError):
         enhance_device(model, st, synth_audio(2, 4800, seed=1).cuda(), out=torch.empty(2, 100, device="cuda"))
+
+
+# ------------------------------------------------------------------ time chunks / streaming ----
+@pytest.mark.parametrize("kind", ["dfn3", "dfn2", "ll"])
+def test_time_chunked_enhance_equals_one_shot(states, kind):
+    """dfb_enhance runs in time chunks with carried state (STFT / ISTFT memories, norm EMAs, GRU states, conv and deep
+    filter history -- SURVEY Appendix D): a workspace cap that forces many short chunks must give the same audio as the
+    single-chunk run (bit identical up to the reduction order of the batched kernels), on the device and the host path."""
+    st, _ = states
+    cfg = cfg_of(kind)
+    sd = random_state_dict(cfg, seed=13)
+    model = DfNet(cfg, sd, st)
+    audio = synth_audio(3, 48000 * 3 + 123, seed=61, device="cuda")    # 301 frames + a partial hop
+    one = enhance_device(model, st, audio).clone()
+    torch.cuda.synchronize()
+    per_stream = model.workspace_bytes() / 3
+    model.set_max_workspace(int(per_stream * 3 * 60 / 303))           # ~ 50-frame windows -> 7+ chunks
+    many = enhance_device(model, st, audio).clone()
+    host = enhance(model, st, audio.cpu())
+    nopad = enhance_device(model, st, audio, pad=False).clone()
+    torch.cuda.synchronize()
+    model.set_max_workspace(24 << 30)
+    assert rms(one.cpu(), many.cpu()) < 1e-6 and rms(one.cpu(), host) < 1e-6
+    ref = O.enhance(sd, cfg.as_dict(), audio.cpu())
+    assert rms(many.cpu(), ref) < RMS_TOL
+    assert rms(nopad.cpu(), O.enhance(sd, cfg.as_dict(), audio.cpu(), pad=False)) < RMS_TOL
+
+
+@pytest.mark.parametrize("kind", ["dfn3", "dfn2", "ll"])
+def test_streaming_equals_one_shot(states, kind):
+    """SURVEY 8(f)-1: frame-incremental processing (DfTract::process, tract.rs:509-642) == one-shot enhance(pad=False)
+    delayed by the model's look-ahead, for ragged call sizes down to a single hop, device and host tensors."""
+    from deepfilternet_b200 import DfStream
+    st, _ = states
+    cfg = cfg_of(kind)
+    sd = random_state_dict(cfg, seed=14)
+    model = DfNet(cfg, sd, st)
+    hop, n = 480, 157
+    audio = synth_audio(2, hop * n, seed=71)
+    ref = enhance(model, st, audio, pad=False)            # [2, n * hop], delayed by fft - hop
+    s = DfStream(model, st, batch=2)
+    assert s.hop == hop and s.latency_frames == max(cfg.conv_lookahead, cfg.df_lookahead) + (cfg.df_lookahead if kind == "dfn2" else 0)
+    outs, pos = [], 0
+    for i, k in enumerate([1, 1, 2, 1, 7, 40, 1, 3, 64, 30, 7]):
+        x = audio[:, pos * hop:(pos + k) * hop]
+        outs.append(s.process(x.cuda() if i % 2 else x).cpu())
+        pos += k
+    assert pos == n
+    outs.append(s.flush())
+    got = torch.cat(outs, 1)
+    lat = s.latency_frames * hop
+    assert got.shape == (2, n * hop + lat)
+    assert got[:, :lat].abs().max() == 0
+    assert rms(got[:, lat:], ref) < 1e-6
+    # a reset stream reproduces itself; atten_lim is honoured
+    s.reset()
+    again = torch.cat([s.process(audio), s.flush()], 1)
+    assert rms(again, got) < 1e-6
+    s2 = DfStream(model, st, batch=2, atten_lim_db=12.0)
+    lim = torch.cat([s2.process(audio), s2.flush()], 1)[:, lat:]
+    assert rms(lim, enhance(model, st, audio, pad=False, atten_lim_db=12.0)) < 1e-6
