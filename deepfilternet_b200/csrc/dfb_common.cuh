@@ -167,7 +167,7 @@ struct GruWindow { const float *h0; float *hT; int t0, Ts; };
 // tensor-core GRU recurrence, H = 256 (dfb_tc.cu)
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
                   unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg = nullptr, int wide = 0,
-                  int planes_res = 0, const GruWindow *w = nullptr);
+                  int planes_res = 0, const GruWindow *w = nullptr, int H = 256);
 // BF16x3 tcgen05 GEMM on hi/lo planes (dfb_tc.cu)
 int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64_t ldx, const void *w_hi, const void *w_lo,
                        const float *bias, float *y, int64_t ldy, int64_t M, int N, int K);

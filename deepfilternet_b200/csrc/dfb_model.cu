@@ -965,7 +965,8 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
     const int64_t M = (int64_t)B * T;
     const float *cur_in = x;
     int cur_dim = in_dim;
-    const bool tc_proj = m->proj_tc && H == 256 && m->gru_tc && x_hi && pl_hi;
+    const bool tc_gru = m->gru_tc && (H == 256 || H == 512);
+    const bool tc_proj = m->proj_tc && tc_gru && x_hi && pl_hi && cur_dim % 64 == 0;
     const unsigned short *cur_hi = x_hi, *cur_lo = x_lo;
     for (int l = 0; l < layers; l++) {
         std::string base = std::string(name) + ".l" + std::to_string(l);
@@ -989,12 +990,12 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         float *hs = ck && ck->h ? ck->h + (int64_t)l * B * H : nullptr;   // carried state of this layer [B][H]
         GruWindow gw{ck && ck->have_state ? hs : nullptr, hs, t0, T};
         GruParams p{xproj, w_hh, b_hh, (l == layers - 1) ? res_last : nullptr, dst, B, Tn, 0, m->gru_dbg, gw.h0, gw.hT, t0, T};
-        if (H == 256 && m->gru_tc) {
+        if (tc_gru) {
             const bool last = l == layers - 1;
             const bool planes = last ? out_hi != nullptr : tc_proj;
             // the last layer's planes feed a grouped linear and include the residual; the others feed the next projection
             rc = launch_gru_tc(s, xproj, w_hh, b_hh, last ? res_last : nullptr, dst, planes ? (last ? out_hi : pl_hi) : nullptr,
-                               planes ? (last ? out_lo : pl_lo) : nullptr, B, Tn, m->gru_dbg, wide, last ? 1 : 0, &gw);
+                               planes ? (last ? out_lo : pl_lo) : nullptr, B, Tn, m->gru_dbg, wide, last ? 1 : 0, &gw, H);
             if (last && planes && out_planes_ok) *out_planes_ok = true;
             cur_hi = pl_hi; cur_lo = pl_lo;
         } else if (H == 256) {

@@ -53,7 +53,10 @@ constexpr int kBxThreads = 320;
 __global__ void __launch_bounds__(kBxThreads, 1)
 k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo,
               const unsigned short *__restrict__ w_hi, const unsigned short *__restrict__ w_lo /* [N][K] BF16 */,
-              const float *__restrict__ bias, float *__restrict__ Y, int64_t ldy, int M, int N, int K) {
+              const float *__restrict__ bias, float *__restrict__ Y, int64_t ldy, int M, int N, int K, int ldw, int k0,
+              int accumulate) {
+    // K > 256 (H = 512 projections) runs as passes over K slices of 256 (the W slice of one pass fills the tensor memory):
+    // this launch covers columns [k0, k0 + K) of X and W (W row pitch ldw) and, when `accumulate`, adds to Y
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     BxSmem &sm = *reinterpret_cast<BxSmem *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,8 +79,8 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__
         const int n = n0 + warp * 32 + lane;
         for (int cb = 0; cb < nkb; cb++) {  // 64 k elements = 32 columns per store
             uint32_t vh[32], vl[32];
-            const uint4 *ph = reinterpret_cast<const uint4 *>(w_hi + (int64_t)n * K + cb * 64);
-            const uint4 *pl = reinterpret_cast<const uint4 *>(w_lo + (int64_t)n * K + cb * 64);
+            const uint4 *ph = reinterpret_cast<const uint4 *>(w_hi + (int64_t)n * ldw + k0 + cb * 64);
+            const uint4 *pl = reinterpret_cast<const uint4 *>(w_lo + (int64_t)n * ldw + k0 + cb * 64);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const uint4 a = n < N ? __ldg(ph + i) : make_uint4(0, 0, 0, 0), c = n < N ? __ldg(pl + i) : make_uint4(0, 0, 0, 0);
@@ -103,8 +106,8 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__
                     const int s = it % kBxStages, n = it / kBxStages;
                     if (n > 0) mbar_wait(&sm.empty[s], (n - 1) & 1);
                     mbar_expect_tx(&sm.full[s], 2 * kBxBM * 128);
-                    tma_load_2d(sm.x[s][0], &tmXhi, kb * kBxBK, tile * kBxBM, &sm.full[s]);
-                    tma_load_2d(sm.x[s][1], &tmXlo, kb * kBxBK, tile * kBxBM, &sm.full[s]);
+                    tma_load_2d(sm.x[s][0], &tmXhi, k0 + kb * kBxBK, tile * kBxBM, &sm.full[s]);
+                    tma_load_2d(sm.x[s][1], &tmXlo, k0 + kb * kBxBK, tile * kBxBM, &sm.full[s]);
                 }
         }
     } else if (warp == 9) {
@@ -153,7 +156,12 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);  // accumulator read: hand the buffer back before the stores
             float *dst = Y + (int64_t)m0 * ldy + n;
-            if (m0 + 64 <= M && n < N) {
+            if (accumulate && n < N) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) { if (m0 + j < M) *dst += v0[j]; dst += ldy; }
+#pragma unroll
+                for (int j = 0; j < 32; j++) { if (m0 + 32 + j < M) *dst += v1[j]; dst += ldy; }
+            } else if (m0 + 64 <= M && n < N) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) { *dst = v0[j] + bn; dst += ldy; }
 #pragma unroll
@@ -484,31 +492,38 @@ template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int)
 // st.async broadcasts (4096 per CTA and step) and W_hh in shared memory were also tried first.
 namespace cg = cooperative_groups;
 
-constexpr int kGtH = 256, kGtC = 8, kGtU = kGtH / kGtC, kGtRows = 3 * kGtU;
+constexpr int kGtU = 32, kGtRows = 3 * kGtU;   // hidden units / W_hh rows per CTA (both hidden sizes)
 // gate threads: one per (unit pair, stream) item = 16 * NS; plus the MMA warp
 // h operand (B, K-major, no swizzle) as 8 x 16 B core matrices ordered [k core matrix][row group][hi|lo]:
 // a CTA's 32 units (4 k core matrices) are one contiguous piece (2 KB for 16 streams) -> one bulk DSMEM copy per peer.
 // NS = streams per cluster (MMA N): 16 (lowest step latency) or 32 (half as many clusters: the DF decoder's
 // recurrence uses it for large batches so that it is co-resident with the ERB decoder's -- at most 15 clusters
 // of 8 CTAs fit on the device, and two launches of 8 clusters made the second one run in two waves).
-template <int NS>
+// HH = hidden size: 256 (cluster of 8, W_hh hi | lo both in tensor memory) or 512 (DeepFilterNet3_ll: cluster of 16
+// -- non-portable size --, W_hh hi in tensor memory (256 columns), W_hh lo in shared memory as a second A operand).
+template <int NS, int HH>
 struct GtCfg {
+    static constexpr int kC = HH / kGtU;              // CTAs per cluster: 8 / 16
     static constexpr int kGateThreads = 16 * NS;      // 256 / 512
+    static constexpr int kGateWarps = kGateThreads / 32;
     static constexpr int kThreads = kGateThreads + 32;
     static constexpr int kMmaWarp = kGateThreads / 32;
     static constexpr int kLbo = (NS / 8) * 256;       // stride between K-adjacent core matrices
     static constexpr int kSbo = 256;                  // stride between 8-stream row groups
     static constexpr int kPlane = 128;                // hi -> lo
     static constexpr int kPiece = 4 * kLbo;           // one CTA's slice
-    static constexpr int kBuf = (kGtH / 8) * kLbo;    // one buffer (16 KB / 32 KB)
+    static constexpr int kBuf = (HH / 8) * kLbo;      // one buffer (16 KB / 32 KB at 256; 32 KB at 512 x 16)
+    static constexpr int kWCols = HH / 2;             // TMEM columns of one W plane: 2 bf16 per 32-bit column
+    static constexpr bool kLoSmem = HH > 256;         // W_lo does not fit next to W_hi and the accumulator
+    static constexpr int kDCol = 256;                 // accumulator columns: after W_hi | W_lo (256) or after W_hi (512)
+    static constexpr int kWloBytes = kLoSmem ? (HH / 8) * 16 * 128 : 16;   // [k core matrix][16 row groups][8 x 16 B]
+    static constexpr int kWloLbo = 16 * 128;          // stride between K-adjacent core matrices of the smem W_lo operand
 };
 
-constexpr int kGtWCols = kGtH / 2;            // TMEM columns of one W plane: 2 bf16 per 32-bit column
-constexpr int kGtDCol = 2 * kGtWCols;         // accumulator columns start after W_hi | W_lo
-
-template <int NS>
+template <int NS, int HH>
 struct GruTcSmem {
-    alignas(1024) unsigned char h[2][GtCfg<NS>::kBuf];   // [buffer][k core matrix][row group][hi|lo][8 rows x 16 B]
+    alignas(1024) unsigned char h[2][GtCfg<NS, HH>::kBuf];   // [buffer][k core matrix][row group][hi|lo][8 rows x 16 B]
+    alignas(128) unsigned char wlo[GtCfg<NS, HH>::kWloBytes];  // (HH = 512) W_hh lo plane, K-major core matrices, 128 rows
     float pre[3][kGtU][NS + 1];
     alignas(8) uint64_t bar_h[2];
     uint64_t t_full;
@@ -524,7 +539,7 @@ struct GruTcParams {
     unsigned short *hout_hi, *hout_lo;  // optional BF16 hi/lo planes of hout (A operand of the next projection GEMM)
     int planes_res;      // 1: the planes hold hout + res (input of a grouped linear), 0: the residual-free h
     // time-chunked execution: steps t = 0 .. T-1 are frames t0 + t of buffers holding Ts frames per stream; the
-    // recurrence starts from h0 [B][256] (null: zeros) and leaves its final state in hT [B][256] (may alias h0)
+    // recurrence starts from h0 [B][H] (null: zeros) and leaves its final state in hT [B][H] (may alias h0)
     const float *h0;
     float *hT;
     int t0, Ts;
@@ -533,12 +548,13 @@ struct GruTcParams {
 };
 
 
-template <int NS>
-__global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p) {
-    using Cfg = GtCfg<NS>;
+template <int NS, int HH>
+__global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcParams p) {
+    using Cfg = GtCfg<NS, HH>;
     constexpr int kGtThreads = Cfg::kThreads;
+    constexpr int kGtH = HH, kGtC = Cfg::kC, kGtWCols = Cfg::kWCols, kGtDCol = Cfg::kDCol;
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    GruTcSmem<NS> &sm = *reinterpret_cast<GruTcSmem<NS> *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
+    GruTcSmem<NS, HH> &sm = *reinterpret_cast<GruTcSmem<NS, HH> *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int group = blockIdx.x / kGtC;
@@ -591,15 +607,25 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
             }
             const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + cb * 32;
             tmem_st32(ta, vh);
-            tmem_st32(ta + kGtWCols, vl);
+            if (!Cfg::kLoSmem) {
+                tmem_st32(ta + kGtWCols, vl);
+            } else {
+                // row rho, elements [64 cb, +64) = 8 core-matrix rows of 16 bytes: core matrix k / 8, row group rho / 8
+                const uint32_t base = smem_u32(sm.wlo) + (uint32_t)(rho >> 3) * 128u + (uint32_t)(rho & 7) * 16u;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(cb * 8 + j) * Cfg::kWloLbo),
+                                 "r"(vl[4 * j]), "r"(vl[4 * j + 1]), "r"(vl[4 * j + 2]), "r"(vl[4 * j + 3]) : "memory");
+            }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (Cfg::kLoSmem) fence_proxy_async();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
-    const uint32_t step_bytes = (uint32_t)((kGtC - 1) * Cfg::kPiece);  // one piece from each of the 7 peers
+    const uint32_t step_bytes = (uint32_t)((kGtC - 1) * Cfg::kPiece);  // one piece from each of the peers
 
     if (warp == Cfg::kMmaWarp) {
         // ================================================================= MMA issuer (whole warp, elected lane issues)
@@ -607,6 +633,8 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
         const uint64_t bd0 = umma_desc_interleave(smem_u32(sm.h[0]), Cfg::kLbo, Cfg::kSbo);
         const uint64_t bd1 = umma_desc_interleave(smem_u32(sm.h[1]), Cfg::kLbo, Cfg::kSbo);
+        const uint64_t wlo_desc = umma_desc_interleave(smem_u32(sm.wlo), Cfg::kWloLbo, 128);
+        (void)wlo_desc;
         const bool dbg_on = p.dbg && blockIdx.x == 0 && lane == 0;
         for (int t = 0; t < T; t++) {
             const int cur = t & 1;
@@ -622,9 +650,13 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
                 const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
 #pragma unroll
                 for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
-                    umma_bf16_ts_elect(tmem_u + kGtDCol, tmem_u + wa * kGtWCols + ks * 8,
-                                       bb + (uint64_t)((ks * 2 * Cfg::kLbo + hb * Cfg::kPlane) >> 4), idesc,
-                                       (combo == 0 && ks == 0) ? 0u : 1u);
+                    const uint64_t bdesc = bb + (uint64_t)((ks * 2 * Cfg::kLbo + hb * Cfg::kPlane) >> 4);
+                    if (Cfg::kLoSmem && wa) {   // W_lo from shared memory (SS form): two core matrices per K step
+                        umma_bf16_ss_elect(tmem_u + kGtDCol, wlo_desc + (uint64_t)((ks * 2 * Cfg::kWloLbo) >> 4), bdesc, idesc, 1u);
+                    } else {
+                        umma_bf16_ts_elect(tmem_u + kGtDCol, tmem_u + wa * kGtWCols + ks * 8, bdesc, idesc,
+                                           (combo == 0 && ks == 0) ? 0u : 1u);
+                    }
                 }
             }
             if (dbg_on) p.dbg[t * 8 + 2] = clock64();
@@ -696,14 +728,14 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
                 if (gdbg) p.dbg[t * 8 + 3] = clock64();
                 asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kGateThreads) : "memory");
                 if (lane == 0) {
-                    // warp w < 7 copies the CTA's slice to peer w (skipping itself); warp 7 signals the local barrier
-                    if (warp < kGtC - 1) {
-                        const int peer = warp + (warp >= rank ? 1 : 0);
-                        const uint32_t src = smem_u32(sm.h[cur ^ 1]) + piece0;
+                    // gate warp w copies the CTA's slice to peers w, w + #warps, ... (skipping itself); the last gate warp
+                    // also signals the local barrier
+                    const uint32_t src = smem_u32(sm.h[cur ^ 1]) + piece0;
+                    for (int j = warp; j < kGtC - 1; j += Cfg::kGateWarps) {
+                        const int peer = j + (j >= rank ? 1 : 0);
                         dsmem_bulk_copy(mapa_u32(src, peer), src, Cfg::kPiece, mapa_u32(smem_u32(&sm.bar_h[cur ^ 1]), peer));
-                    } else if (warp == kGtC - 1) {
-                        mbar_arrive(&sm.bar_h[cur ^ 1]);  // own slice is in place
                     }
+                    if (warp == Cfg::kGateWarps - 1) mbar_arrive(&sm.bar_h[cur ^ 1]);  // own slice is in place
                 }
             } else {
                 asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kGateThreads) : "memory");
@@ -730,42 +762,47 @@ __global__ void __launch_bounds__(GtCfg<NS>::kThreads, 1) k_gru_tc(GruTcParams p
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int NS>
+template <int NS, int HH>
 static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
+    using Cfg = GtCfg<NS, HH>;
     static PerDeviceOnce attr_once;
     // the kernel allocates all 512 TMEM columns (W_hh lives there), so only one CTA may be resident
     // per SM: request more than half of the shared memory to enforce it
-    const int need = (int)sizeof(GruTcSmem<NS>) + 1024;
+    const int need = (int)sizeof(GruTcSmem<NS, HH>) + 1024;
     const int smem = need > 120 * 1024 ? need : 120 * 1024;
     if (auto once_guard = attr_once.first()) {
-        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(GtCfg<NS>::kThreads);
+    cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = kGtC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = Cfg::kC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     p.Bc = NS;
     const int ngroups = (p.B + NS - 1) / NS;
-    cfg.gridDim = dim3((unsigned)(ngroups * kGtC));
+    cfg.gridDim = dim3((unsigned)(ngroups * Cfg::kC));
     cfg.stream = s;
-    DFB_PROF("k_gru_tc", s);
-    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS>, p));
+    DFB_PROF(HH == 256 ? "k_gru_tc" : "k_gru_tc512", s);
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH>, p));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return DFB_OK;
 }
 
-// wide != 0: 32 streams per cluster when the batch needs more than 4 clusters of 16 (see GtCfg)
+// wide != 0: 32 streams per cluster when the batch needs more than 4 clusters of 16 (see GtCfg).  H = 512: clusters of
+// 16 CTAs with 16 streams (the h operand of 32 streams would not fit next to the W_lo plane in shared memory).
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
                   unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg, int wide, int planes_res,
-                  const GruWindow *w) {
+                  const GruWindow *w, int H) {
     GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, planes_res, w ? w->h0 : nullptr, w ? w->hT : nullptr,
                   w ? w->t0 : 0, w ? w->Ts : T, B, T, 0, dbg};
+    if (H == 512) return launch_gru_tc_n<16, 512>(s, p);
+    if (H != 256) return fail(DFB_ERR_UNSUPPORTED, "tensor-core recurrence: hidden size %d", H);
     static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
     const bool use32 = force ? force == 32 : (wide && B > 64);
-    return use32 ? launch_gru_tc_n<32>(s, p) : launch_gru_tc_n<16>(s, p);
+    return use32 ? launch_gru_tc_n<32, 256>(s, p) : launch_gru_tc_n<16, 256>(s, p);
 }
 
 // ------------------------------------------------------------------------------- host side ----
@@ -803,7 +840,7 @@ static int make_map_bf16(CUtensorMap *map, const void *base, int64_t rows, int64
 // Y[M,N] = X . W^T + bias with X, W given as BF16 hi/lo planes (X: [M][K] pitch ldx, W: [N][K] pitch K)
 int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64_t ldx, const void *w_hi, const void *w_lo,
                        const float *bias, float *y, int64_t ldy, int64_t M, int N, int K) {
-    if (N % kBxBN || K % kBxBK || K > kBxMaxK || (ldx % 8) || M <= 0 || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15))
+    if (N % kBxBN || K % kBxBK || (K > kBxMaxK && K % kBxMaxK) || (ldx % 8) || M <= 0 || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15))
         return fail(DFB_ERR_UNSUPPORTED, "bf16x3 GEMM shape M=%lld N=%d K=%d", (long long)M, N, K);
     CUtensorMap mxh, mxl;
     int rc;
@@ -822,10 +859,14 @@ int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64
     if (groups < 1) groups = 1;
     if (groups > ntiles) groups = ntiles;
     dim3 grid((unsigned)nslices, (unsigned)groups);
-    DFB_PROF("k_gemm_bf16x3[gru_proj]", s);
-    k_gemm_bf16x3<<<grid, kBxThreads, smem, s>>>(mxh, mxl, reinterpret_cast<const unsigned short *>(w_hi),
-                                          reinterpret_cast<const unsigned short *>(w_lo), bias, y, ldy, (int)M, N, K);
-    DFB_LAUNCH_CHECK();
+    const int kpass = K > kBxMaxK ? kBxMaxK : K;
+    for (int k0 = 0; k0 < K; k0 += kpass) {
+        DFB_PROF("k_gemm_bf16x3[gru_proj]", s);
+        k_gemm_bf16x3<<<grid, kBxThreads, smem, s>>>(mxh, mxl, reinterpret_cast<const unsigned short *>(w_hi),
+                                                  reinterpret_cast<const unsigned short *>(w_lo), bias, y, ldy, (int)M, N, kpass, K, k0,
+                                                  k0 > 0 ? 1 : 0);
+        DFB_LAUNCH_CHECK();
+    }
     return DFB_OK;
 }
 
