@@ -254,6 +254,36 @@ __global__ void k_erb_inv(const float *__restrict__ gains, int64_t n_frames, int
     out[i] = gains[fr * E + band_of_bin[k]];
 }
 
+// ------------------------------------------------------------- polyphase resampler ----
+// torchaudio.functional.resample as used by df/io.py:107-129 (the reference resamples files to / from the model rate,
+// enhance.py:56,85): out[c][i * nw + j] = sum_k kern[j][k] * xpad[c][i * og + k], xpad = x zero padded by `width` in
+// front (torchaudio _apply_sinc_resample_kernel: conv1d with stride og).  kern [nw][K = 2 width + og] is built on the
+// host exactly like torchaudio's _get_sinc_resample_kernel (io.py resample_kernel).
+__global__ void __launch_bounds__(256) k_resample(const float *__restrict__ x, int64_t T, const float *__restrict__ kern, int og, int nw,
+                                                  int width, int K, float *__restrict__ out, int64_t Tout) {
+    extern __shared__ float s_k[];   // the nw x K taps when they fit (else read through L1)
+    const bool in_smem = (size_t)nw * K * sizeof(float) <= 96 * 1024;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < nw * K; i += blockDim.x) s_k[i] = kern[i];
+        __syncthreads();
+    }
+    const float *kk = in_smem ? s_k : kern;
+    const int c = blockIdx.y;
+    const float *xc = x + (int64_t)c * T;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < Tout; n += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = n / nw;
+        const int j = (int)(n - i * nw);
+        const int64_t p0 = i * og - width;
+        const float *kr = kk + (size_t)j * K;
+        float acc = 0.f;
+        for (int k = 0; k < K; k++) {
+            const int64_t p = p0 + k;
+            if (p >= 0 && p < T) acc = fmaf(kr[k], xc[p], acc);
+        }
+        out[(int64_t)c * Tout + n] = acc;
+    }
+}
+
 // ------------------------------------------------------------- feature norm scans ----
 // Exponential mean norm of the ERB dB features and exponential unit norm of the first Fd bins,
 // sequential in t per (stream, band | bin) exactly like the reference loops.
@@ -1077,5 +1107,30 @@ extern "C" int dfb_features_host(dfb_state *st, const float *h_audio, int64_t C,
         DFB_CUDA(cudaMemcpyAsync(h_feat_spec, d_fs, sizeof(float) * n_fs, cudaMemcpyDeviceToHost, st->stream));
     }
     DFB_CUDA(cudaStreamSynchronize(st->stream));
+    return DFB_OK;
+}
+
+// df/io.py resample (torchaudio.functional.resample): h_audio [C][T] -> h_out [C][T_out]; h_kernel [nw][2 width + og]
+extern "C" int dfb_resample_host(int device, const float *h_audio, int64_t C, int64_t T, const float *h_kernel, int og, int nw,
+                                 int width, float *h_out, int64_t T_out) {
+    if (!h_audio || !h_kernel || !h_out || C <= 0 || T <= 0 || T_out <= 0 || og <= 0 || nw <= 0 || width < 0)
+        return fail(DFB_ERR_INVALID, "bad resample argument");
+    if (C > 65535) return fail(DFB_ERR_INVALID, "more than 65535 channels per call");
+    int rc = use_device(device);
+    if (rc) return rc;
+    const int K = 2 * width + og;
+    Scratch s;
+    float *d_in = s.alloc<float>(C * T), *d_out = s.alloc<float>(C * T_out), *d_k = s.alloc<float>((size_t)nw * K);
+    if (!d_in || !d_out || !d_k) return fail(DFB_ERR_OOM, "cudaMalloc failed");
+    DFB_CUDA(cudaMemcpy(d_in, h_audio, sizeof(float) * C * T, cudaMemcpyHostToDevice));
+    DFB_CUDA(cudaMemcpy(d_k, h_kernel, sizeof(float) * (size_t)nw * K, cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)nw * K * sizeof(float) <= 96 * 1024 ? (size_t)nw * K * sizeof(float) : 0;
+    static PerDeviceOnce attr_once;
+    if (auto once_guard = attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    int64_t blocks = (T_out + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    k_resample<<<dim3((unsigned)blocks, (unsigned)C), 256, smem>>>(d_in, T, d_k, og, nw, width, K, d_out, T_out);
+    DFB_LAUNCH_CHECK();
+    DFB_CUDA(cudaMemcpy(h_out, d_out, sizeof(float) * C * T_out, cudaMemcpyDeviceToHost));
     return DFB_OK;
 }

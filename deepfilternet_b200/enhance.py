@@ -15,6 +15,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import check
+from .io import load_audio, resample, save_audio
 from .libdf import DF
 from .model import DfNet, load_model
 
@@ -147,3 +148,87 @@ def enhance_device(model: DfNet, df_state: DF, audio: Tensor, pad: bool = True,
         check(_lib.lib().dfb_enhance(model.handle, df_state.handle, audio.data_ptr(), b, t, 1 if pad else 0,
                                      lim, out.data_ptr(), stream))
     return out
+
+
+# ------------------------------------------------------------------------------------------ CLI ----
+def parse_epoch_type(value: str) -> Union[int, str]:
+    """enhance.py:253-261."""
+    try:
+        return int(value)
+    except ValueError:
+        assert value in ("best", "latest")
+        return value
+
+
+def setup_df_argument_parser(default_log_level: str = "INFO", parser=None):
+    """enhance.py:299-339 (same options)."""
+    import argparse
+    if parser is None:
+        parser = argparse.ArgumentParser()
+    parser.add_argument("--model-base-dir", "-m", type=str, default=None,
+                        help="Model directory containing checkpoints and config, or a pretrained model name.")
+    parser.add_argument("--pf", help="Post-filter that slightly over-attenuates very noisy sections.", action="store_true")
+    parser.add_argument("--output-dir", "-o", type=str, default=None, help="Directory in which the enhanced audio files will be stored.")
+    parser.add_argument("--log-level", type=str, default=default_log_level, help="Logger verbosity. Can be one of (debug, info, error, none)")
+    parser.add_argument("--debug", "-d", action="store_const", const="DEBUG", dest="log_level")
+    parser.add_argument("--epoch", "-e", default="best", type=parse_epoch_type,
+                        help="Epoch for checkpoint loading. Can be one of ['best', 'latest', <int>].")
+    return parser
+
+
+def main(args) -> int:
+    """The `deepFilter` command (enhance.py:47-89): load each file at the model rate, enhance, resample back to the
+    file's rate, save next to it (or into --output-dir) with the model suffix."""
+    import glob
+    import time
+    model, df_state, suffix, _ = init_df(args.model_base_dir, post_filter=args.pf, log_level=args.log_level,
+                                         config_allow_defaults=True, epoch=args.epoch, mask_only=args.no_df_stage)
+    suffix = suffix if args.suffix else None
+    if args.output_dir is None:
+        args.output_dir = "."
+    elif not os.path.isdir(args.output_dir):
+        os.mkdir(args.output_dir)
+    df_sr = model.cfg.sr
+    if args.noisy_dir is not None:
+        if len(args.noisy_audio_files) > 0:
+            logger.error("Only one of `noisy_audio_files` or `noisy_dir` arguments are supported.")
+            return 1
+        input_files = sorted(glob.glob(args.noisy_dir + "/*"))
+    else:
+        assert len(args.noisy_audio_files) > 0, "No audio files provided"
+        input_files = args.noisy_audio_files
+    n_samples = len(input_files)
+    for i, file in enumerate(input_files):
+        if not os.path.isfile(file):
+            logger.warning("File not found: %s. Skipping...", file)
+            continue
+        audio, meta = load_audio(file, df_sr, verbose=False)
+        progress = (i + 1) / n_samples * 100
+        t0 = time.time()
+        audio = enhance(model, df_state, audio, pad=args.compensate_delay, atten_lim_db=args.atten_lim)
+        t = time.time() - t0
+        t_audio = audio.shape[-1] / df_sr
+        p_str = f"{progress:2.0f}% | " if n_samples > 1 else ""
+        logger.info("%sEnhanced noisy audio file '%s' in %.2fs (RT factor: %.3f)", p_str, os.path.basename(file), t, t / t_audio)
+        audio = resample(audio.to("cpu"), df_sr, meta.sample_rate)
+        save_audio(file, audio, sr=meta.sample_rate, output_dir=args.output_dir, suffix=suffix, log=False)
+    return 0
+
+
+def run(argv=None) -> int:
+    """enhance.py:342-379."""
+    parser = setup_df_argument_parser()
+    parser.add_argument("--no-delay-compensation", dest="compensate_delay", action="store_false",
+                        help="Don't add some padding to compensate the delay introduced by the real-time STFT/ISTFT implementation.")
+    parser.add_argument("--atten-lim", "-a", type=int, default=None,
+                        help="Attenuation limit in dB by mixing the enhanced signal with the noisy signal.")
+    parser.add_argument("noisy_audio_files", type=str, nargs="*", help="List of noisy files to enhance.")
+    parser.add_argument("--noisy-dir", "-i", type=str, default=None,
+                        help="Input directory containing noisy audio files. Use instead of `noisy_audio_files`.")
+    parser.add_argument("--no-suffix", action="store_false", dest="suffix", help="Don't add the model suffix to the enhanced audio files")
+    parser.add_argument("--no-df-stage", action="store_true")
+    return main(parser.parse_args(argv))
+
+
+if __name__ == "__main__":
+    raise SystemExit(run())

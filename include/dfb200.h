@@ -110,6 +110,12 @@ int dfb_features(dfb_state *st, const float *d_audio, int64_t C, int64_t T, int 
 int dfb_features_host(dfb_state *st, const float *h_audio, int64_t C, int64_t T, int nb_df, float alpha,
                       float *h_spec, float *h_feat_erb, float *h_feat_spec);
 
+/* df.io.resample (DeepFilterNet/df/io.py:107-129 -> torchaudio.functional.resample): polyphase sinc resampling on the
+ * device.  h_kernel f32[new][2 * width + orig] are the taps of torchaudio's _get_sinc_resample_kernel for the gcd-reduced
+ * rates (orig, new); audio f32[C][T] -> out f32[C][T_out], T_out = ceil(new * T / orig). */
+int dfb_resample_host(int device, const float *h_audio, int64_t C, int64_t T, const float *h_kernel, int orig, int new_rate,
+                      int width, float *h_out, int64_t T_out);
+
 /* ------------------------------------------------------------------ model ------------------
  * Replaces the forward pass of DeepFilterNet/df/deepfilternet3.py (DfNet :334-456) and
  * deepfilternet2.py (DfNet :374-505) for the shipped DeepFilterNet2 / 3 / 3_ll topologies. */

@@ -461,3 +461,58 @@ def test_streaming_equals_one_shot(states, kind):
     s2 = DfStream(model, st, batch=2, atten_lim_db=12.0)
     lim = torch.cat([s2.process(audio), s2.flush()], 1)[:, lat:]
     assert rms(lim, enhance(model, st, audio, pad=False, atten_lim_db=12.0)) < 1e-6
+
+
+# ------------------------------------------------------------------ callers either side of the path ----
+@pytest.mark.parametrize("orig,new,method", [(44100, 48000, "sinc_fast"), (48000, 16000, "sinc_best"), (16000, 48000, "kaiser_fast"),
+                                             (48000, 44100, "kaiser_best")])
+def test_resample_matches_torchaudio(orig, new, method):
+    """df.io.resample (io.py:107-129): the CUDA polyphase kernel against torchaudio.functional.resample -- the reference's
+    own dependency for this step -- with the reference's parameter sets."""
+    ta = pytest.importorskip("torchaudio")
+    from deepfilternet_b200.io import get_resample_params, resample
+    x = synth_audio(2, orig // 2 + 17, seed=3, sr=orig)
+    got = resample(x, orig, new, method=method)
+    ref = ta.functional.resample(x, orig, new, **get_resample_params(method))
+    assert got.shape == ref.shape and float((got - ref).abs().max()) < 2e-6
+    assert resample(x, orig, orig) is x
+
+
+def test_audio_io_and_cli_roundtrip(tmp_path, golden_dir, model_dir):
+    """df.io load_audio / save_audio on WAV files and the `deepFilter` CLI (enhance.py:47-89, 299-379): the file the CLI
+    writes equals enhance() of the loaded audio, int16-scaled like io.py:80-85."""
+    import ref_harness as rh
+    from deepfilternet_b200 import io as dio
+    from deepfilternet_b200.enhance import run
+    src = os.path.join(golden_dir, "assets", "noisy_snr0.wav")
+    audio, meta = dio.load_audio(src, 48000)
+    assert meta.sample_rate == 48000 and audio.shape[0] == meta.num_channels == 1
+    assert np.array_equal(audio.numpy(), rh.read_wav(src))
+    out_dir = tmp_path / "out"
+    assert run(["-m", os.path.join(model_dir, "DeepFilterNet3"), "-o", str(out_dir), "--log-level", "ERROR", src]) == 0
+    written, wmeta = dio.load_audio(str(out_dir / "noisy_snr0_DeepFilterNet3.wav"))
+    model, st, _, _ = init_df(os.path.join(model_dir, "DeepFilterNet3"), log_level="ERROR")
+    ref = (enhance(model, st, audio) * (1 << 15)).to(torch.int16).to(torch.float32) / 32768.0
+    assert wmeta.sample_rate == 48000 and written.shape == ref.shape
+    assert float((written - ref).abs().max()) <= 1.0 / 32768.0 + 1e-7
+    # float32 files and a rate the model does not run at: resampled in, resampled back out
+    x16 = dio.resample(audio[:, :48000], 48000, 16000)
+    p16 = dio.save_audio(str(tmp_path / "a16.wav"), x16, 16000, dtype=torch.float32)
+    back, m16 = dio.load_audio(p16, 48000, verbose=False)
+    assert m16.sample_rate == 16000 and m16.encoding == "PCM_F" and back.shape[1] == 48000
+
+
+def test_training_feature_producer(states):
+    """SURVEY 8(f)-4: FftDataset::get_sample's transform (dataset.rs:863-914) on device tensors == the oracle's
+    analysis -> erb -> erb_norm / unit_norm."""
+    from deepfilternet_b200.features import fft_features
+    st, ost = states
+    noisy, speech = synth_audio(3, 24000, seed=5), synth_audio(3, 24000, seed=6)
+    out = fft_features(st, noisy.cuda(), speech.cuda(), nb_spec=96, norm_alpha=0.99)
+    spec = ost.analysis(noisy.numpy())
+    assert np.abs(out["noisy"].cpu().numpy()[:, 0] - np.stack([spec.real, spec.imag], -1)).max() < 1e-6
+    sp = ost.analysis(speech.numpy())
+    assert np.abs(out["speech"].cpu().numpy()[:, 0] - np.stack([sp.real, sp.imag], -1)).max() < 1e-6
+    assert np.abs(out["feat_erb"].cpu().numpy()[:, 0] - LO.erb_norm(LO.erb(spec, ost.erb_widths()), 0.99)).max() < 2e-6
+    un = LO.unit_norm(np.ascontiguousarray(spec[..., :96]), 0.99)
+    assert np.abs(out["feat_spec"].cpu().numpy()[:, 0] - np.stack([un.real, un.imag], -1)).max() < 1e-5
