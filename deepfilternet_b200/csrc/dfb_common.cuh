@@ -137,6 +137,10 @@ struct ApplyParams {
     // is not written (they belong to the previous window and are only re-synthesised for the overlap-add tail)
     int spec_T, Tv, t_first;
     int mc_T;             // frames per stream in m / coefs (0 = Tf)
+    // optional stages: post filter (DFN3: on the enhanced spectrum, deepfilternet3.py:448-454; DFN2: on the ERB gains,
+    // modules.py:234-245 with beta = 0.02) and mask_only (run_df = False: no deep filter, every bin takes the ERB gain)
+    int pf, mask_only;
+    float pf_beta;
     float atten_lim;      // 0 = off
     // carried ISTFT state (pyDF synthesis(reset=False), mode 0 only): channel 0 starts from init_tail,
     // channel c > 0 from the tail left by channel c - 1; the tail after the last frame goes to final_tail

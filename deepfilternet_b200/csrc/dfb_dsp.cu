@@ -372,6 +372,21 @@ __global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
 // it re-synthesises frame t0-1 to obtain the tail of its first frame.
 // Algorithmic HBM bytes per frame (mode 1/2): 3848 R spec + 128 R m + 3840 R coefs + 1920 W audio.
 
+// Valin's post filter on an ERB gain (Mask.pf, modules.py:234-245)
+__device__ __forceinline__ float pf_gain_mask(float m, float beta) {
+    const float ms = fmaxf(m * sinf(3.14159265358979f * m / 2.f), 1e-12f);
+    const float q = m / ms;
+    return (1.f + beta) * m / (1.f + beta * q * q);
+}
+// ... and on an enhanced bin y of the noisy bin x (deepfilternet3.py:448-454): returns the factor for y
+__device__ __forceinline__ float pf_gain_spec(float2 y, float2 x, float beta) {
+    const float eps = 1e-12f;
+    const float mask = fminf(fmaxf(hypotf(y.x, y.y) / (hypotf(x.x, x.y) + eps), eps), 1.f);
+    const float ms = mask * fmaxf(sinf(3.14159265358979f * mask / 2.f), eps);
+    const float q = mask / ms;
+    return (1.f + beta) / (1.f + beta * q * q);
+}
+
 __device__ __forceinline__ float2 apply_bin(const ApplyParams &p, const DspTables &tb, const float2 *srow0,
                                             const float *mrow0, const float *crow, int t, int k) {
     // srow0 / mrow0: row pointers of frame 0 of this stream
@@ -379,8 +394,10 @@ __device__ __forceinline__ float2 apply_bin(const ApplyParams &p, const DspTable
     float2 y;
     if (p.mode == 0) return x;
     const int band = tb.band_of_bin[k];
-    if (k >= p.nb_df) {
+    const bool pf2 = p.pf && p.mode == 2;
+    if (k >= p.nb_df || p.mask_only) {
         float g = mrow0[(int64_t)t * tb.E + band];
+        if (pf2) g = pf_gain_mask(g, 0.02f);
         y = make_float2(x.x * g, x.y * g);
     } else {
         // Y[t,k] = sum_o S[t + o - (O-1-L), k] * W[o,t,k]   (multiframe.py:72-74,126-136)
@@ -392,6 +409,7 @@ __device__ __forceinline__ float2 apply_bin(const ApplyParams &p, const DspTable
             float2 s = srow0[(int64_t)tt * kF + k];
             if (p.mode == 2 && tt < (p.mc_T ? p.mc_T : p.Tf)) {
                 float g = mrow0[(int64_t)tt * tb.E + band];
+                if (pf2) g = pf_gain_mask(g, 0.02f);
                 s.x *= g; s.y *= g;
             }
             float wr = c[2 * o], wi = c[2 * o + 1];
@@ -400,6 +418,7 @@ __device__ __forceinline__ float2 apply_bin(const ApplyParams &p, const DspTable
         }
         y = make_float2(yr, yi);
     }
+    if (p.pf && p.mode == 1) { const float g = pf_gain_spec(y, x, p.pf_beta); y.x *= g; y.y *= g; }
     if (p.atten_lim > 0.f) {
         y.x = x.x * p.atten_lim + y.x * (1.f - p.atten_lim);
         y.y = x.y * p.atten_lim + y.y * (1.f - p.atten_lim);
@@ -511,7 +530,9 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
     const float2 *srow0 = p.spec + (int64_t)b * (p.spec_T ? p.spec_T : Tf) * kF;
     const int mcT = p.mc_T ? p.mc_T : Tf;                  // m / coefs rows per stream
     const float *mrow0 = p.m + (int64_t)b * mcT * 32;
-    const bool masked_df = p.mode == 2;
+    const bool masked_df = p.mode == 2 && !p.mask_only;
+    const bool pf1 = p.pf && p.mode == 1, pf2 = p.pf && p.mode == 2;
+    const bool need_xk = p.atten_lim > 0.f || pf1 || p.mask_only;   // noisy DF bins are only loaded when something reads them
     // bands of this lane's bins: bk[j] for k = lane + 32 j, bn[j] for 480 - k
     unsigned long long bkp = 0, bnp = 0;  // 8 band indices each, one byte per j
 #pragma unroll
@@ -534,6 +555,7 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
         // (DFN2) the mask of a look-ahead frame beyond the window's DNN frames does not exist yet: such rows are only
         // read for frames that are re-synthesised in the next window
         float mrow = (ok && masked_df && tt < mcT) ? mrow0[(int64_t)tt * 32 + lane] : 1.f;
+        if (pf2 && ok && masked_df && tt < mcT) mrow = pf_gain_mask(mrow, 0.02f);
 #pragma unroll
         for (int j = 0; j < NDFJ; j++) {
             float2 v = ok ? srow0[(int64_t)tt * kF + lane + 32 * j] : make_float2(0.f, 0.f);
@@ -547,7 +569,8 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
     for (int o = 1; o < ORDER; o++) load_df_row(tstart + o - 1 - back, hist[o]);  // becomes taps 0..O-2 after the first shift
     for (int t = tstart; t < t1; t++) {
         // ---- loads of this frame, all issued before use
-        const float mcur = mrow0[(int64_t)t * 32 + lane];
+        float mcur = mrow0[(int64_t)t * 32 + lane];
+        if (pf2) mcur = pf_gain_mask(mcur, 0.02f);
 #pragma unroll
         for (int o = 0; o < ORDER - 1; o++)
 #pragma unroll
@@ -564,7 +587,7 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int k = lane + 32 * j;
-            xk[j] = (k <= 240 && (j >= NDFJ || p.atten_lim > 0.f)) ? srow[k] : make_float2(0.f, 0.f);
+            xk[j] = (k <= 240 && (j >= NDFJ || need_xk)) ? srow[k] : make_float2(0.f, 0.f);
             xn[j] = k <= 240 ? srow[kC - k] : make_float2(0.f, 0.f);
         }
         // ---- deep filter (bins < 96), gain (others), optional attenuation limit
@@ -572,7 +595,7 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
         for (int j = 0; j < 8; j++) {
             const int k = lane + 32 * j;
             float2 y;
-            if (j < NDFJ) {
+            if (j < NDFJ && !p.mask_only) {
                 float yr = 0.f, yi = 0.f;
 #pragma unroll
                 for (int o = 0; o < ORDER; o++) {
@@ -587,6 +610,10 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
             }
             const float gn = __shfl_sync(0xffffffffu, mcur, BN(j));
             float2 yn = make_float2(xn[j].x * gn, xn[j].y * gn);
+            if (pf1) {
+                const float g1 = pf_gain_spec(y, xk[j], p.pf_beta), g2 = pf_gain_spec(yn, xn[j], p.pf_beta);
+                y.x *= g1; y.y *= g1; yn.x *= g2; yn.y *= g2;
+            }
             if (p.atten_lim > 0.f) {
                 const float a = p.atten_lim, c = 1.f - a;
                 y.x = xk[j].x * a + y.x * c; y.y = xk[j].y * a + y.y * c;

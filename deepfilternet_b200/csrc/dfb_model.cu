@@ -736,6 +736,8 @@ struct dfb_model {
     int gru_tc = 0;  // 1: tensor-core recurrence (BF16 hi/lo split operands) for H = 256
     long long *gru_dbg = nullptr;  // device buffer for dfb_debug_gru_timing
     Arena arena;
+    int post_filter = 0, mask_only = 0;       // optional stages (dfb_model_set_options)
+    float pf_beta = 0.02f;
     size_t max_workspace = size_t(24) << 30;  // dfb_enhance groups streams so that the arena stays below this
     std::vector<int64_t> erb_widths;          // band table the model was built for (checked against the dfb_state)
     Arena aux_arena;                          // carried stream state + padded input of dfb_enhance
@@ -1450,6 +1452,20 @@ static int check_state(const dfb_model *m, const dfb_state *st) {
 }
 
 static int apply_mode(const dfb_model *m) { return m->cfg.model_kind == 2 ? 2 : 1; }
+static void apply_options(const dfb_model *m, dfb::ApplyParams &p) {
+    p.pf = m->post_filter; p.pf_beta = m->pf_beta; p.mask_only = m->mask_only;
+}
+
+// init_df(post_filter=..., mask_only=...) (df/enhance.py:101-187): the post filter of deepfilternet3.py:448-454 (beta =
+// pf_beta) or, for DeepFilterNet2, Mask.pf on the ERB gains (modules.py:234-245, beta fixed at 0.02); mask_only = the
+// model built with run_df = False (checkpoint.py:32): no deep filtering stage.
+extern "C" int dfb_model_set_options(dfb_model *m, int post_filter, float pf_beta, int mask_only) {
+    if (!m) return fail(DFB_ERR_INVALID, "null model");
+    m->post_filter = post_filter ? 1 : 0;
+    m->pf_beta = pf_beta;
+    m->mask_only = mask_only ? 1 : 0;
+    return DFB_OK;
+}
 
 extern "C" int dfb_apply(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_m, const float *d_coefs,
                          int64_t B, int64_t T, float *d_spec_e, void *stream) {
@@ -1459,6 +1475,7 @@ extern "C" int dfb_apply(dfb_model *m, dfb_state *st, const float *d_spec, const
     dfb::ApplyParams p{};
     p.spec = (const float2 *)d_spec; p.m = d_m; p.coefs = d_coefs; p.audio = nullptr; p.spec_out = (float2 *)d_spec_e;
     p.Tf = (int)T; p.mode = apply_mode(m); p.nb_df = m->cfg.nb_df; p.order = m->cfg.df_order; p.lookahead = m->cfg.df_lookahead;
+    apply_options(m, p);
     return launch_apply_synthesis(st, p, B, (cudaStream_t)stream);
 }
 
@@ -1644,6 +1661,7 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
         p.Tf = (int)(e1n - W0); p.spec_T = Tsb; p.Tv = Tv; p.mc_T = Tw; p.t_first = (int)(S.e1 - W0);
         p.mode = apply_mode(m); p.nb_df = Fd; p.order = c.df_order; p.lookahead = c.df_lookahead;
         p.atten_lim = io.atten_lim;
+        apply_options(m, p);
         if ((rc = launch_apply_synthesis(st, p, B, s))) return rc;
     }
     // ---- carry

@@ -64,14 +64,12 @@ def init_df(
     if not os.path.isdir(model_base_dir):
         raise NotADirectoryError("Base directory not found at {}".format(model_base_dir))
     logger.setLevel(getattr(logging, str(log_level).upper(), logging.INFO))
-    if post_filter:
-        raise NotImplementedError("post_filter=True: the post filter is outside the built hot path")
-    if mask_only:
-        raise NotImplementedError("mask_only=True is outside the built hot path")
     if epoch is None or (isinstance(epoch, str) and epoch.lower() == "none"):
         raise NotImplementedError("epoch='none' (random weights): use weights.random_state_dict + DfNet")
-    model, df_state, ep = load_model(model_base_dir, epoch=epoch, device=device)
+    model, df_state, ep = load_model(model_base_dir, epoch=epoch, device=device, post_filter=post_filter, mask_only=mask_only)
     suffix = os.path.basename(os.path.abspath(model_base_dir))
+    if post_filter:
+        suffix += "_pf"   # enhance.py:183-184
     logger.info("Running on device cuda:%d", device)
     logger.info("Model loaded")
     return model, df_state, suffix, ep

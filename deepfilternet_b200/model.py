@@ -61,7 +61,7 @@ class DfNet(nn.Module):
     """B200 drop-in for ``df.deepfilternet3.DfNet`` / ``df.deepfilternet2.DfNet``."""
 
     def __init__(self, cfg: ModelConfig, state_dict: Dict[str, Tensor], df_state: Optional[DF] = None,
-                 device: Optional[int] = None):
+                 device: Optional[int] = None, run_df: bool = True):
         super().__init__()
         self.cfg = cfg
         self.nb_df = cfg.nb_df
@@ -70,10 +70,9 @@ class DfNet(nn.Module):
         self.df_lookahead = cfg.df_lookahead
         self.freq_bins = cfg.freq_bins
         self.erb_bins = cfg.nb_erb
-        self.run_df = True
-        self.post_filter = False
-        if cfg.mask_pf:
-            raise NotImplementedError("post filter (mask_pf) is off in all shipped configs and not built")
+        self.run_df = bool(run_df)            # False: init_df(mask_only=True) (checkpoint.py:32)
+        self.post_filter = bool(cfg.mask_pf)  # init_df(post_filter=True) sets mask_pf (enhance.py:152-153)
+        self.post_filter_beta = float(cfg.pf_beta)
         self._device = 0 if device is None else int(device)
         self.df_state = df_state if df_state is not None else DF(
             cfg.sr, cfg.fft_size, cfg.hop_size, cfg.nb_erb, cfg.min_nb_erb_freqs, device=self._device)
@@ -110,6 +109,7 @@ class DfNet(nn.Module):
         self._h = h
         self._derived = derived
         self.set_precision(os.environ.get("DFB_PRECISION", "fp32+gru_tc+proj_tc+conv_tc"))
+        check(_lib.lib().dfb_model_set_options(self._h, int(self.post_filter), self.post_filter_beta, int(not self.run_df)))
 
     def set_precision(self, mode: str) -> None:
         """Arithmetic of the contractions (everything else is always IEEE fp32):
@@ -193,9 +193,12 @@ class DfNet(nn.Module):
 
 
 def load_model(model_base_dir: str, epoch: Union[str, int, None] = "best", device: int = 0,
-               df_state: Optional[DF] = None, env: Optional[dict] = None) -> Tuple[DfNet, DF, int]:
+               df_state: Optional[DF] = None, env: Optional[dict] = None, post_filter: bool = False,
+               mask_only: bool = False) -> Tuple[DfNet, DF, int]:
     """init_model + read_cp for a reference model directory (``config.ini`` + ``checkpoints/``)."""
     cfg = load_config(os.path.join(model_base_dir, "config.ini"), env=env)
+    if post_filter:
+        cfg.mask_pf = True
     cp_dir = os.path.join(model_base_dir, "checkpoints")
     path, ep = find_checkpoint(cp_dir, epoch)
     if path is not None:
@@ -208,5 +211,5 @@ def load_model(model_base_dir: str, epoch: Union[str, int, None] = "best", devic
             raise FileNotFoundError(f"Could not find a checkpoint in {cp_dir}")
     if df_state is None:
         df_state = DF(cfg.sr, cfg.fft_size, cfg.hop_size, cfg.nb_erb, cfg.min_nb_erb_freqs, device=device)
-    model = DfNet(cfg, sd, df_state, device=device)
+    model = DfNet(cfg, sd, df_state, device=device, run_df=not mask_only)
     return model, df_state, int(ep)

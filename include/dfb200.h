@@ -211,6 +211,11 @@ int dfb_stream_process_host(dfb_stream *s, const float *h_in, int64_t n_frames, 
  * 0 = FFMA everywhere; 14 = the default of the Python mirror (deepfilternet_b200/model.py set_precision).
  * BF16x3 is ~2^-17 relative per product: 1e-7 .. 4e-7 RMS end to end against the fp32 oracle (bound 1e-4). */
 int dfb_model_set_precision(dfb_model *m, int mode);
+/* init_df(post_filter=..., mask_only=...) (DeepFilterNet/df/enhance.py:101-187).  post_filter: Valin's post filter -- for
+ * DeepFilterNet3 on the enhanced spectrum with beta = pf_beta (deepfilternet3.py:448-454), for DeepFilterNet2 on the ERB
+ * gains with beta = 0.02 (Mask.pf, modules.py:234-245).  mask_only: the model as built with run_df = False
+ * (checkpoint.py:32): no deep-filter stage, every bin takes the ERB gain. */
+int dfb_model_set_options(dfb_model *m, int post_filter, float pf_beta, int mask_only);
 /* Cap (bytes) of the per-call device workspace of dfb_enhance: the batch is processed in time chunks (and, for very
  * large batches, stream groups) that fit below it (default 24 GB, or DFB_MAX_WORKSPACE_MB in the environment at
  * dfb_model_create). */

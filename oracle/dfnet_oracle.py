@@ -20,6 +20,7 @@ compares this file with them.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -231,14 +232,31 @@ def dfnet_forward(sd: SD, cfg: dict, erb_widths, spec: Tensor, feat_erb: Tensor,
     e0, e1, e2, e3, emb, c0, lsnr = encoder(sd, cfg, fe, fs)
     m = erb_decoder(sd, cfg, emb, e3, e2, e1, e0)
     inv = erb_inv_matrix(erb_widths)
-    spec_m = apply_mask(spec, m, inv)
+    pf, mask_only = bool(cfg.get("mask_pf", False)), bool(cfg.get("mask_only", False))
+    m_app = m
+    if pf and cfg["model"] == "deepfilternet2":
+        # Mask.pf (modules.py:234-245, beta = 0.02): the post filter acts on the ERB gains
+        beta = 0.02
+        m_sin = m * torch.sin(math.pi * m / 2)
+        m_app = (1 + beta) * m / (1 + beta * m.div(m_sin.clamp_min(1e-12)).pow(2))
+    spec_m = apply_mask(spec, m_app, inv)
     coefs = df_decoder(sd, cfg, emb, c0)
     nb_df, order, la = cfg["nb_df"], cfg["df_order"], cfg["df_lookahead"]
     if cfg["model"] == "deepfilternet2":
-        spec_e = deep_filter(spec_m, coefs, nb_df, order, la)  # deepfilternet2.py:494-503
+        # deepfilternet2.py:494-503 (run_df = False with mask_only: checkpoint.py:32)
+        spec_e = spec_m if mask_only else deep_filter(spec_m, coefs, nb_df, order, la)
     else:
-        spec_e = deep_filter(spec, coefs, nb_df, order, la)  # deepfilternet3.py:442-443
-        spec_e[..., nb_df:, :] = spec_m[..., nb_df:, :]
+        if mask_only:  # deepfilternet3.py:444-446
+            spec_e = spec_m
+        else:
+            spec_e = deep_filter(spec, coefs, nb_df, order, la)  # deepfilternet3.py:442-443
+            spec_e[..., nb_df:, :] = spec_m[..., nb_df:, :]
+        if pf:  # deepfilternet3.py:448-454
+            beta, eps = float(cfg.get("pf_beta", 0.02)), 1e-12
+            mask = (torch.view_as_complex(spec_e.contiguous()).abs() / torch.view_as_complex(spec.contiguous()).abs().add(eps)).clamp(eps, 1)
+            mask_sin = mask * torch.sin(math.pi * mask / 2).clamp_min(eps)
+            g = (1 + beta) / (1 + beta * mask.div(mask_sin).pow(2))
+            spec_e = spec_e * g.unsqueeze(-1)
     return spec_e, m, lsnr, coefs
 
 

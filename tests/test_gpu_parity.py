@@ -516,3 +516,23 @@ def test_training_feature_producer(states):
     assert np.abs(out["feat_erb"].cpu().numpy()[:, 0] - LO.erb_norm(LO.erb(spec, ost.erb_widths()), 0.99)).max() < 2e-6
     un = LO.unit_norm(np.ascontiguousarray(spec[..., :96]), 0.99)
     assert np.abs(out["feat_spec"].cpu().numpy()[:, 0] - np.stack([un.real, un.imag], -1)).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
+def test_post_filter_and_mask_only(name, golden_dir, model_dir):
+    """init_df(post_filter=True) / init_df(mask_only=True) against the reference modules' outputs
+    (tests/golden/dfnet_pf.npz, oracle/gen_golden_pf.py) and, in streaming mode, against the one-shot path."""
+    from deepfilternet_b200 import DfStream
+    g = np.load(os.path.join(golden_dir, "dfnet_pf.npz"))
+    audio = torch.from_numpy(g["audio"])
+    model, st, suffix, _ = init_df(os.path.join(model_dir, name), post_filter=True, log_level="ERROR")
+    assert suffix == name + "_pf" and model.post_filter
+    assert rms(enhance(model, st, audio), g[f"{name}_pf"]) < RMS_TOL
+    assert rms(enhance(model, st, audio, atten_lim_db=12.0), g[f"{name}_pf_atten12"]) < RMS_TOL
+    x = audio[:, :480 * 50]
+    s = DfStream(model, st, batch=2)
+    got = torch.cat([s.process(x[:, :480 * 7]), s.process(x[:, 480 * 7:]), s.flush()], 1)[:, s.latency_frames * 480:]
+    assert rms(got, enhance(model, st, x, pad=False)) < 1e-6
+    model, st, _, _ = init_df(os.path.join(model_dir, name), mask_only=True, log_level="ERROR")
+    assert not model.run_df
+    assert rms(enhance(model, st, audio), g[f"{name}_mask_only"]) < RMS_TOL

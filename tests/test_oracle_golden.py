@@ -181,3 +181,23 @@ def test_oracle_carried_state_semantics():
     st.synthesis(whole.copy(), reset=True)       # leaves a non-zero synthesis memory behind
     st.analysis(x[:1], reset=True)               # DFState::reset clears it
     assert np.array_equal(st.synthesis(whole.copy(), reset=False), y_whole)
+
+
+@pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
+def test_oracle_post_filter_and_mask_only_match_reference_modules(name, golden_dir, model_dir):
+    """The optional stages: `init_df(post_filter=True)` (deepfilternet3.py:448-454 on the spectrum; DFN2: Mask.pf on the
+    ERB gains, modules.py:234-245) and `mask_only=True` (run_df = False), pinned to the reference modules' outputs
+    (tests/golden/dfnet_pf.npz, made by oracle/gen_golden_pf.py)."""
+    g = np.load(os.path.join(golden_dir, "dfnet_pf.npz"))
+    d = os.path.join(model_dir, name)
+    cfg = load_config(os.path.join(d, "config.ini"), env={})
+    sd = load_state_dict_file(find_checkpoint(os.path.join(d, "checkpoints"))[0])
+    audio = torch.from_numpy(g["audio"])
+    rmsd = lambda a, b: float(np.sqrt(((a.numpy() - b) ** 2).mean()))
+    c = dict(cfg.as_dict(), mask_pf=True)
+    assert rmsd(O.enhance(sd, c, audio), g[f"{name}_pf"]) < 1e-6
+    assert rmsd(O.enhance(sd, c, audio, atten_lim_db=12.0), g[f"{name}_pf_atten12"]) < 1e-6
+    c = dict(cfg.as_dict(), mask_only=True)
+    assert rmsd(O.enhance(sd, c, audio), g[f"{name}_mask_only"]) < 1e-6
+    # and they are not no-ops
+    assert rmsd(O.enhance(sd, cfg.as_dict(), audio), g[f"{name}_pf"]) > 1e-5
