@@ -90,6 +90,7 @@ SIGNATURES = {
     "dfb_stream_reset": (_I, [_VP]),
     "dfb_stream_frame_length": (_I64, [_VP]),
     "dfb_stream_latency_frames": (_I64, [_VP]),
+    "dfb_stream_set_lsnr_thresholds": (_I, [_VP, _I, _F, _F, _F]),
     "dfb_stream_process": (_I, [_VP, _VP, _I64, _VP, _VP]),
     "dfb_stream_flush": (_I, [_VP, _VP, _VP]),
     "dfb_stream_process_host": (_I, [_VP, _VP, _I64, _VP]),

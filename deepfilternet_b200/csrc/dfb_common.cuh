@@ -141,6 +141,10 @@ struct ApplyParams {
     // modules.py:234-245 with beta = 0.02) and mask_only (run_df = False: no deep filter, every bin takes the ERB gain)
     int pf, mask_only;
     float pf_beta;
+    // LSNR stage gating of the streaming runtime (libDF/src/tract.rs:658-672), mode 1 only: lsnr [B][mc_T] or null;
+    // lsnr < th_min -> zero gains, no DF; > th_erb -> frame passes unprocessed; > th_df -> gains only; else gains + DF
+    const float *lsnr;
+    float th_min, th_erb, th_df;
     float atten_lim;      // 0 = off
     // carried ISTFT state (pyDF synthesis(reset=False), mode 0 only): channel 0 starts from init_tail,
     // channel c > 0 from the tail left by channel c - 1; the tail after the last frame goes to final_tail

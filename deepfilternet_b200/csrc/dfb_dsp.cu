@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
     const float *mrow0 = p.m + (int64_t)b * mcT * 32;
     const bool masked_df = p.mode == 2 && !p.mask_only;
     const bool pf1 = p.pf && p.mode == 1, pf2 = p.pf && p.mode == 2;
-    const bool need_xk = p.atten_lim > 0.f || pf1 || p.mask_only;   // noisy DF bins are only loaded when something reads them
+    const bool need_xk = p.atten_lim > 0.f || pf1 || p.mask_only || p.lsnr;   // noisy DF bins are only loaded when something reads them
     // bands of this lane's bins: bk[j] for k = lane + 32 j, bn[j] for 480 - k
     unsigned long long bkp = 0, bnp = 0;  // 8 band indices each, one byte per j
 #pragma unroll
@@ -571,6 +571,11 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
         // ---- loads of this frame, all issued before use
         float mcur = mrow0[(int64_t)t * 32 + lane];
         if (pf2) mcur = pf_gain_mask(mcur, 0.02f);
+        int stage = 3;   // 0 zero gains, 1 unprocessed, 2 gains only, 3 gains + deep filter (tract.rs apply_stages)
+        if (p.lsnr) {
+            const float l = p.lsnr[(int64_t)b * mcT + t];
+            stage = l < p.th_min ? 0 : (l > p.th_erb ? 1 : (l > p.th_df ? 2 : 3));
+        }
 #pragma unroll
         for (int o = 0; o < ORDER - 1; o++)
 #pragma unroll
@@ -595,7 +600,7 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
         for (int j = 0; j < 8; j++) {
             const int k = lane + 32 * j;
             float2 y;
-            if (j < NDFJ && !p.mask_only) {
+            if (j < NDFJ && !p.mask_only && stage == 3) {
                 float yr = 0.f, yi = 0.f;
 #pragma unroll
                 for (int o = 0; o < ORDER; o++) {
@@ -610,7 +615,9 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
             }
             const float gn = __shfl_sync(0xffffffffu, mcur, BN(j));
             float2 yn = make_float2(xn[j].x * gn, xn[j].y * gn);
-            if (pf1) {
+            if (stage == 0) { y = make_float2(0.f, 0.f); yn = y; }
+            else if (stage == 1) { y = xk[j]; yn = xn[j]; }
+            if (pf1 && stage >= 2) {
                 const float g1 = pf_gain_spec(y, xk[j], p.pf_beta), g2 = pf_gain_spec(yn, xn[j], p.pf_beta);
                 y.x *= g1; y.y *= g1; yn.x *= g2; yn.y *= g2;
             }
@@ -892,6 +899,8 @@ int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaS
     if (p.mode != 0 && (p.nb_df > 240 || p.order > 8)) return fail(DFB_ERR_UNSUPPORTED, "nb_df > 240 or df_order > 8");
     int per_cta = kSynWarps * kSynChunk;
     dim3 grid((unsigned)((p.Tf + per_cta - 1) / per_cta), (unsigned)B);
+    if (p.lsnr && !(p.mode == 1 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs))
+        return fail(DFB_ERR_UNSUPPORTED, "LSNR stage gating is built for the DeepFilterNet3 apply kernel only");
     DFB_PROF("k_apply_synthesis", s);
     static const int minb = getenv("DFB_APPLY_MINB") ? atoi(getenv("DFB_APPLY_MINB")) : 2;  // 2 CTAs/SM without spills measured fastest
     if (p.mode != 0 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs && minb == 3)

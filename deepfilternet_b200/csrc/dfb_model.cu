@@ -1534,6 +1534,7 @@ struct StreamState {
     float *h_enc = nullptr, *h_erb = nullptr, *h_df = nullptr;   // [layers][B][H]
     float *t_spec = nullptr, *t_fe = nullptr, *t_fs = nullptr;   // last Hf = kHalo + Lmax frames of spec / features, right aligned
     float *t_m = nullptr, *t_c = nullptr;                        // last kMcTail frames of m / coefs, right aligned
+    float *t_l = nullptr;                                        // ... and of lsnr (stage gating)
     float *t_dec = nullptr;                                      // (conv_kt == 2) last kHalo frames of dec_emb
     int n_feat = 0, n_mc = 0, n_dec = 0;                         // valid frames in the tails
 };
@@ -1561,6 +1562,7 @@ static size_t state_floats(const dfb_model_config &c, const dfb_state *st, int B
     add(6, (size_t)B * g.Hf * 2 * F); add(7, (size_t)B * g.Hf * E); add(8, (size_t)B * g.Hf * 2 * Fd);
     add(9, (size_t)B * kMcTail * E); add(10, (size_t)B * kMcTail * Fd * O2);
     add(11, c.conv_kt > 1 ? (size_t)B * kHalo * ED : 0);
+    add(12, (size_t)B * kMcTail);
     return n;
 }
 static void state_bind(StreamState &S, float *base, const size_t off[16], int B) {
@@ -1568,7 +1570,7 @@ static void state_bind(StreamState &S, float *base, const size_t off[16], int B)
     S.ana_mem = base + off[0]; S.erb_state = base + off[1]; S.unit_state = base + off[2];
     S.h_enc = base + off[3]; S.h_erb = base + off[4]; S.h_df = base + off[5];
     S.t_spec = base + off[6]; S.t_fe = base + off[7]; S.t_fs = base + off[8];
-    S.t_m = base + off[9]; S.t_c = base + off[10]; S.t_dec = base + off[11];
+    S.t_m = base + off[9]; S.t_c = base + off[10]; S.t_dec = base + off[11]; S.t_l = base + off[12];
     S.a1 = S.d1 = S.e1 = 0; S.started = S.dnn_started = false; S.n_feat = S.n_mc = S.n_dec = 0;
 }
 
@@ -1602,6 +1604,7 @@ struct ChunkIO {
     float *out; int64_t out_stride, out_len;
     int64_t out_sample0;      // absolute synthesis sample (frame * hop + i) that lands at out[0]
     float atten_lim;
+    const float *lsnr_th;     // {min_db_thresh, max_db_erb_thresh, max_db_df_thresh} (tract.rs:658-672) or null: no gating
 };
 
 // One chunk: analyse frames [S.a1, a1n), run the DNN over [S.d1, d1n), emit audio of frames [S.e1, e1n).
@@ -1625,6 +1628,7 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
     float *fs = m->arena.take<float>((size_t)B * Tsb * Fd * 2);
     float *mm = m->arena.take<float>((size_t)B * (Tw + 1) * E);
     float *cc = m->arena.take<float>((size_t)B * (Tw + 1) * Fd * O2);
+    float *ll = io.lsnr_th ? m->arena.take<float>((size_t)B * (Tw + 1)) : nullptr;
     if (!cc) return fail(DFB_ERR_OOM, "chunk workspace exhausted");
     // ---- features: carried history, then the new frames
     if ((rc = load_tail(s, spec, Tsb, (size_t)2 * F, n_hist, S.t_spec, g.Hf, 0, B)) || (rc = load_tail(s, fe, Tsb, E, n_hist, S.t_fe, g.Hf, 0, B)) ||
@@ -1641,7 +1645,7 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
     // ---- DNN over the window
     if (run_dnn) {
     ChunkCtx cx{Rc, Tsb, Tv, S.h_enc, S.h_erb, S.h_df, S.dnn_started, c.conv_kt > 1 ? S.t_dec : nullptr, S.n_dec};
-    if ((rc = forward_impl(m, m->arena, fe, fs, B, Tw, mm, cc, nullptr, nullptr, s, &cx))) return rc;
+    if ((rc = forward_impl(m, m->arena, fe, fs, B, Tw, mm, cc, ll, nullptr, s, &cx))) return rc;
     S.n_dec = cx.dec_tail_n;
     S.dnn_started = true;
     // the halo rows of m / coefs come from skipped recurrences: restore the last finished frames from the previous chunk
@@ -1650,6 +1654,7 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
         const int n = S.n_mc < Rc ? S.n_mc : Rc;
         if ((rc = load_tail(s, mm, Tw, E, n, S.t_m, kMcTail, Rc - n, B)) || (rc = load_tail(s, cc, Tw, (size_t)Fd * O2, n, S.t_c, kMcTail, Rc - n, B)))
             return rc;
+        if (ll && (rc = load_tail(s, ll, Tw, 1, n, S.t_l, kMcTail, Rc - n, B))) return rc;
     }
     }
     // ---- apply + synthesis of frames [e0, e1n)
@@ -1662,6 +1667,7 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
         p.mode = apply_mode(m); p.nb_df = Fd; p.order = c.df_order; p.lookahead = c.df_lookahead;
         p.atten_lim = io.atten_lim;
         apply_options(m, p);
+        if (ll) { p.lsnr = ll; p.th_min = io.lsnr_th[0]; p.th_erb = io.lsnr_th[1]; p.th_df = io.lsnr_th[2]; }
         if ((rc = launch_apply_synthesis(st, p, B, s))) return rc;
     }
     // ---- carry
@@ -1678,6 +1684,7 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
         if (run_dnn) {
             const int nm = Tw < kMcTail ? Tw : kMcTail;
             if ((rc = save_tail(s, mm, Tw, E, nm, S.t_m, kMcTail, B)) || (rc = save_tail(s, cc, Tw, (size_t)Fd * O2, nm, S.t_c, kMcTail, B))) return rc;
+            if (ll && (rc = save_tail(s, ll, Tw, 1, nm, S.t_l, kMcTail, B))) return rc;
             S.n_mc = nm;
         }
     }
@@ -1734,7 +1741,7 @@ static int enhance_group(dfb_model *m, dfb_state *st, const float *d_x, int64_t 
             if (x0 < x1 && (rc = hooks->before(x0, x1))) break;
         }
         const int64_t e0 = S.e1;
-        ChunkIO io{d_x, Tp, Tp, 0, nullptr, d_out, out_len, out_len, delay, lim};
+        ChunkIO io{d_x, Tp, Tp, 0, nullptr, d_out, out_len, out_len, delay, lim, nullptr};
         if ((rc = run_chunk(m, st, S, io, a1n, d1n, e1n > S.e1 ? e1n : S.e1, s))) break;
         if (hooks && hooks->after) {
             int64_t y0 = e0 * hop - delay, y1 = S.e1 * hop - delay;
@@ -1878,6 +1885,8 @@ struct dfb_stream {
     float lim;
     StreamState S;
     float *slab = nullptr;
+    bool gating = false;
+    float th[3] = {-10.f, 30.f, 20.f};                 // tract.rs:180-185 defaults
     float *stage_in = nullptr, *stage_out = nullptr;   // device staging of the *_host entry point
     size_t stage_cap = 0;
 };
@@ -1916,6 +1925,17 @@ extern "C" int dfb_stream_reset(dfb_stream *h) {
     return DFB_OK;
 }
 
+// LSNR stage gating of the Rust runtime (libDF/src/tract.rs:658-672; thresholds tract.rs:180-185, DfParams of
+// deep-filter / capi.rs).  Off by default: the Python path this library mirrors does not gate.  DeepFilterNet3 only.
+extern "C" int dfb_stream_set_lsnr_thresholds(dfb_stream *h, int enable, float min_db_thresh, float max_db_erb_thresh,
+                                              float max_db_df_thresh) {
+    if (!h) return fail(DFB_ERR_INVALID, "null stream");
+    if (enable && h->m->cfg.model_kind == 2) return fail(DFB_ERR_UNSUPPORTED, "LSNR stage gating: DeepFilterNet3 topologies only");
+    h->gating = enable != 0;
+    h->th[0] = min_db_thresh; h->th[1] = max_db_erb_thresh; h->th[2] = max_db_df_thresh;
+    return DFB_OK;
+}
+
 extern "C" int64_t dfb_stream_latency_frames(const dfb_stream *h) {
     if (!h) return -1;
     const ChunkGeom g = chunk_geom(h->m->cfg);
@@ -1944,7 +1964,7 @@ static int stream_step(dfb_stream *h, const float *d_in, int64_t n, bool flush, 
     const int64_t f0 = (flush ? S.a1 : a0) - Ltot;
     if (f0 < 0 || e1n <= S.e1) DFB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * B * n_out * hop, s));
     ChunkIO io{d_in, (flush ? 0 : n) * hop, (flush ? 0 : n) * hop, a0, S.started ? S.ana_mem : nullptr, d_out, n_out * hop, n_out * hop,
-               f0 * hop, h->lim};
+               f0 * hop, h->lim, h->gating ? h->th : nullptr};
     if (!flush && a1n > a0) {
         // zero analysis memory before the very first frame
         if (!S.started) DFB_CUDA(cudaMemsetAsync(S.ana_mem, 0, sizeof(float) * B * hop, s));

@@ -42,6 +42,12 @@ class DfStream:
                 pass
             self._h = None
 
+    def set_lsnr_thresholds(self, min_db_thresh: float = -10.0, max_db_erb_thresh: float = 30.0,
+                            max_db_df_thresh: float = 20.0, enable: bool = True) -> None:
+        """Stage gating of the Rust runtime (tract.rs:658-672, defaults tract.rs:180-185); off unless called."""
+        check(_lib.lib().dfb_stream_set_lsnr_thresholds(self._h, int(enable), float(min_db_thresh), float(max_db_erb_thresh),
+                                                        float(max_db_df_thresh)))
+
     def reset(self) -> None:
         check(_lib.lib().dfb_stream_reset(self._h))
 

@@ -188,8 +188,8 @@ int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad);
  * Every call feeds n >= 1 hops per stream and returns n hops; the output trails the input by
  * dfb_stream_latency_frames() hops (the model's look-ahead) on top of the STFT's fft - hop samples: the concatenated
  * output equals dfb_enhance(pad = 0) of the concatenated input, delayed by latency * hop samples.  dfb_enhance itself
- * runs on the same time-chunked executor.  Not built: the LSNR stage gating (tract.rs:658-672) and the post filter
- * (lib.rs:446-471) of the Rust runtime -- the Python path this library mirrors has neither. */
+ * runs on the same time-chunked executor.  Optional stages: the post filter (dfb_model_set_options) and the Rust
+ * runtime's LSNR stage gating (dfb_stream_set_lsnr_thresholds); not built: its silent-frame skip (tract.rs:516-525). */
 typedef struct dfb_stream dfb_stream;
 /* capi.rs df_create: B independent streams on the model's device; atten_lim_db <= 0 disables the limit */
 int dfb_stream_create(dfb_stream **out, dfb_model *m, dfb_state *st, int64_t B, float atten_lim_db);
@@ -197,6 +197,12 @@ void dfb_stream_free(dfb_stream *s);                       /* capi.rs df_free */
 int dfb_stream_reset(dfb_stream *s);                       /* back to the initial state (all memories zero) */
 int64_t dfb_stream_frame_length(const dfb_stream *s);      /* capi.rs df_get_frame_length: hop size in samples */
 int64_t dfb_stream_latency_frames(const dfb_stream *s);    /* hops the output trails the input by */
+/* LSNR stage gating (libDF/src/tract.rs:658-672 apply_stages; defaults -10 / 30 / 20 dB, tract.rs:180-185): per frame,
+ * lsnr < min_db_thresh -> zero gains, no deep filter; > max_db_erb_thresh -> the frame passes unprocessed;
+ * > max_db_df_thresh -> ERB gains only; else gains + deep filter.  Off by default (the Python path never gates);
+ * DeepFilterNet3 topologies only. */
+int dfb_stream_set_lsnr_thresholds(dfb_stream *s, int enable, float min_db_thresh, float max_db_erb_thresh,
+                                   float max_db_df_thresh);
 /* capi.rs df_process_frame, batched and for n_frames hops at once: d_in / d_out f32[B][n_frames * hop] (device) */
 int dfb_stream_process(dfb_stream *s, const float *d_in, int64_t n_frames, float *d_out, void *stream);
 /* end of stream: the latency frames still in flight, d_out f32[B][latency * hop]; reset before feeding again */

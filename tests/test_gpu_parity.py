@@ -536,3 +536,35 @@ def test_post_filter_and_mask_only(name, golden_dir, model_dir):
     model, st, _, _ = init_df(os.path.join(model_dir, name), mask_only=True, log_level="ERROR")
     assert not model.run_df
     assert rms(enhance(model, st, audio), g[f"{name}_mask_only"]) < RMS_TOL
+
+
+def test_streaming_lsnr_stage_gating(states):
+    """tract.rs:658-672 `apply_stages` on the streaming path: thresholds that force one stage for every frame must
+    reproduce that stage's definition -- gains + DF (the ungated output), gains only (== mask_only), unprocessed (== the
+    noisy input through STFT/ISTFT), zero gains (silence) -- and the atten limit mixes the noisy signal back in."""
+    from deepfilternet_b200 import DfStream
+    st, _ = states
+    cfg = cfg_of("dfn3")
+    sd = random_state_dict(cfg, seed=15)
+    model = DfNet(cfg, sd, st)
+    hop, n = 480, 90
+    audio = synth_audio(2, hop * n, seed=81)
+
+    def run(model, **th):
+        s = DfStream(model, st, batch=2, atten_lim_db=th.pop("atten", None))
+        if th:
+            s.set_lsnr_thresholds(**th)
+        return torch.cat([s.process(audio[:, :hop * 33]), s.process(audio[:, hop * 33:]), s.flush()], 1)[:, s.latency_frames * hop:]
+
+    base = run(model)
+    assert rms(run(model, min_db_thresh=-1e9, max_db_erb_thresh=1e9, max_db_df_thresh=1e9), base) < 1e-7      # always stage 3
+    gains_only = run(model, min_db_thresh=-1e9, max_db_erb_thresh=1e9, max_db_df_thresh=-1e9)                 # always stage 2
+    mo = DfNet(cfg, sd, st, run_df=False)
+    assert rms(gains_only, run(mo)) < 1e-7 and rms(gains_only, base) > 1e-5
+    passthrough = run(model, min_db_thresh=-1e9, max_db_erb_thresh=-1e9, max_db_df_thresh=-1e9)               # always stage 1
+    ident = torch.from_numpy(st.synthesis(st.analysis(audio.numpy())))
+    assert rms(passthrough, ident) < 1e-6
+    assert run(model, min_db_thresh=1e9, max_db_erb_thresh=2e9, max_db_df_thresh=2e9).abs().max() < 1e-7      # always stage 0
+    lim = 10 ** (-12 / 20)
+    z = run(model, min_db_thresh=1e9, max_db_erb_thresh=2e9, max_db_df_thresh=2e9, atten=12.0)
+    assert rms(z, ident * lim) < 1e-6
