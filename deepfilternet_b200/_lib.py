@@ -97,6 +97,7 @@ SIGNATURES = {
     "dfb_model_set_precision": (_I, [_VP, _I]),
     "dfb_model_set_max_workspace": (_I, [_VP, _I64]),
     "dfb_model_set_options": (_I, [_VP, _I, _F, _I]),
+    "dfb_model_set_chunking": (_I, [_VP, _I, _I, _I]),
     "dfb_debug_gru_timing": (_I, [_VP, _I, _VP]),
     "dfb_model_debug_fetch": (_I64, [_VP, C.c_char_p, _VP, _I64]),
 }

@@ -736,6 +736,7 @@ struct dfb_model {
     int gru_tc = 0;  // 1: tensor-core recurrence (BF16 hi/lo split operands) for H = 256
     long long *gru_dbg = nullptr;  // device buffer for dfb_debug_gru_timing
     Arena arena;
+    int dev_chunks = 6, host_chunks = 6, n_lanes = 2;   // chunk pipeline (dfb_model_set_chunking)
     int post_filter = 0, mask_only = 0;       // optional stages (dfb_model_set_options)
     float pf_beta = 0.02f;
     size_t max_workspace = size_t(24) << 30;  // dfb_enhance groups streams so that the arena stays below this
@@ -743,12 +744,17 @@ struct dfb_model {
     Arena aux_arena;                          // carried stream state + padded input of dfb_enhance
     cudaStream_t stream = nullptr;
     cudaStream_t h2d = nullptr, d2h = nullptr;  // copy streams of dfb_enhance_host (both copy engines next to the compute)
-    cudaStream_t aux = nullptr;             // DF decoder branch runs here, concurrently with the ERB decoder
-    // forward() hops from the caller's stream onto `hi` (and `aux`), both at the greatest stream priority; `low`
-    // (least priority) carries work that is off the critical path and only fills SMs the recurrences leave idle
-    cudaStream_t hi = nullptr, low = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork_enc = nullptr, ev_join_enc = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_c0 = nullptr, ev_convp = nullptr, ev_skip = nullptr;
+    // One forward pass hops from the caller's stream onto the lane's internal streams: `hi` (ERB branch) and `aux` (DF
+    // branch) for the encoder phase, `dhi` / `daux` at the greatest priority for the decoder phase (the recurrences are
+    // the critical chain), `low` (least priority) for work off the critical path that only fills idle SMs.  Two lanes:
+    // consecutive time chunks alternate between them, so that the encoder phase of chunk c + 1 overlaps the decoder
+    // phase of chunk c (lane 1 has its own arena; everything outside the chunk loop uses lane 0).
+    struct Lane {
+        cudaStream_t main = nullptr, hi = nullptr, aux = nullptr, dhi = nullptr, daux = nullptr, low = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork_enc = nullptr, ev_join_enc = nullptr, ev_in = nullptr,
+                    ev_out = nullptr, ev_c0 = nullptr, ev_convp = nullptr, ev_skip = nullptr, ev_done = nullptr;
+    } lanes[2];
+    Arena arena1;                           // lane 1's activations (lane 0 uses `arena`)
     const float *get(const std::string &n) const {
         auto it = t.find(n);
         return it == t.end() ? nullptr : it->second.first;
@@ -784,6 +790,9 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
     m->device = device;
     m->cfg = *cfg;
     if (erb_widths) m->erb_widths.assign(erb_widths, erb_widths + cfg->nb_erb);
+    if (const char *e = getenv("DFB_DEVICE_CHUNKS")) m->dev_chunks = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("DFB_HOST_CHUNKS")) m->host_chunks = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("DFB_LANES")) m->n_lanes = atoi(e) == 1 ? 1 : 2;
     if (const char *e = getenv("DFB_MAX_WORKSPACE_MB")) {
         const long long mb = atoll(e);
         if (mb > 0) m->max_workspace = (size_t)mb << 20;
@@ -810,26 +819,24 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
     }
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    // the DF branch (`aux`) is the critical path of both the encoder-conv and the decoder phase (launch timeline), so
-    // the ERB branch's stream may sit one or more levels below it (numerically greater = lower priority)
-    static const int erb_offset = getenv("DFB_ERB_PRIO_OFFSET") ? atoi(getenv("DFB_ERB_PRIO_OFFSET")) : 0;
-    int prio_hi = prio_greatest + erb_offset;
-    if (prio_hi > prio_least) prio_hi = prio_least;
-    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&m->h2d, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&m->d2h, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&m->aux, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&m->hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&m->low, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_c0, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_convp, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_skip, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_fork_enc, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ev_join_enc, cudaEventDisableTiming) != cudaSuccess) {
+    // numerically greater = lower priority; the encoder phase sits one level below the decoder phase
+    int prio_enc = prio_greatest + 1;
+    if (prio_enc > prio_least) prio_enc = prio_least;
+    bool ok = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&m->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&m->d2h, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &L : m->lanes) {
+        ok = ok && cudaStreamCreateWithPriority(&L.main, cudaStreamNonBlocking, prio_enc) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&L.hi, cudaStreamNonBlocking, prio_enc) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&L.aux, cudaStreamNonBlocking, prio_enc) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&L.dhi, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&L.daux, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&L.low, cudaStreamNonBlocking, prio_least) == cudaSuccess;
+        for (cudaEvent_t *e : {&L.ev_fork, &L.ev_join, &L.ev_fork_enc, &L.ev_join_enc, &L.ev_in, &L.ev_out, &L.ev_c0, &L.ev_convp,
+                               &L.ev_skip, &L.ev_done})
+            ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
         dfb_model_free(m);
         return fail(DFB_ERR_CUDA, "stream creation failed");
     }
@@ -841,20 +848,18 @@ extern "C" void dfb_model_free(dfb_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     m->arena.release();
+    m->arena1.release();
     m->aux_arena.release();
     if (m->h2d) cudaStreamDestroy(m->h2d);
     if (m->d2h) cudaStreamDestroy(m->d2h);
     if (m->slab) cudaFree(m->slab);
     if (m->stream) cudaStreamDestroy(m->stream);
-    if (m->aux) cudaStreamDestroy(m->aux);
-    if (m->hi) cudaStreamDestroy(m->hi);
-    if (m->low) cudaStreamDestroy(m->low);
-    for (cudaEvent_t e : {m->ev_in, m->ev_out, m->ev_c0, m->ev_convp, m->ev_skip})
-        if (e) cudaEventDestroy(e);
-    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-    if (m->ev_join) cudaEventDestroy(m->ev_join);
-    if (m->ev_fork_enc) cudaEventDestroy(m->ev_fork_enc);
-    if (m->ev_join_enc) cudaEventDestroy(m->ev_join_enc);
+    for (auto &L : m->lanes) {
+        for (cudaStream_t st : {L.main, L.hi, L.aux, L.dhi, L.daux, L.low})
+            if (st) cudaStreamDestroy(st);
+        for (cudaEvent_t e : {L.ev_fork, L.ev_join, L.ev_fork_enc, L.ev_join_enc, L.ev_in, L.ev_out, L.ev_c0, L.ev_convp, L.ev_skip, L.ev_done})
+            if (e) cudaEventDestroy(e);
+    }
     delete m;
 }
 
@@ -1101,6 +1106,8 @@ struct ChunkCtx {
     bool have_state;               // false for the first chunk of a stream (states start at zero)
     float *dec_tail;               // (conv_kt == 2) last kHalo frames of dec_emb [B][kHalo][ED], right aligned
     int dec_tail_n;                // frames of dec_tail that are valid
+    int lane;                      // which of the model's two stream / event sets (and arenas) this chunk runs on
+    cudaEvent_t wait_dec;          // previous chunk finished (its decoder states / tails are final) or null
 };
 constexpr int kHalo = 8;           // >= temporal receptive field of every feed-forward chain of the shipped models
 
@@ -1144,17 +1151,18 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     GruChunk ck_df{cx ? cx->h_df : nullptr, cx && cx->have_state, cx ? cx->Rc : 0};
     // DFB_SERIAL=1: everything on the caller's stream (profiling: per-kernel times without overlap)
     static const bool serial = getenv("DFB_SERIAL") && atoi(getenv("DFB_SERIAL"));
-    cudaStream_t s = serial ? s_in : m->hi;
-    cudaStream_t sl = serial ? s_in : m->low;
+    dfb_model::Lane &L = m->lanes[cx ? cx->lane : 0];
+    cudaStream_t s = serial ? s_in : L.hi;
+    cudaStream_t sl = serial ? s_in : L.low;
     if (!serial) {
-        DFB_CUDA(cudaEventRecord(m->ev_in, s_in));
-        DFB_CUDA(cudaStreamWaitEvent(s, m->ev_in, 0));
+        DFB_CUDA(cudaEventRecord(L.ev_in, s_in));
+        DFB_CUDA(cudaStreamWaitEvent(s, L.ev_in, 0));
     }
     auto finish = [&]() -> int {  // join the branches and hand the result back to the caller's stream
-        DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
+        DFB_CUDA(cudaStreamWaitEvent(s, L.ev_join, 0));
         if (!serial) {
-            DFB_CUDA(cudaEventRecord(m->ev_out, s));
-            DFB_CUDA(cudaStreamWaitEvent(s_in, m->ev_out, 0));
+            DFB_CUDA(cudaEventRecord(L.ev_out, s));
+            DFB_CUDA(cudaStreamWaitEvent(s_in, L.ev_out, 0));
         }
         return DFB_OK;
     };
@@ -1239,9 +1247,9 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         return DFB_OK;
     };
     // the DF-branch input convs run concurrently with the ERB-branch convs
-    cudaStream_t sa = serial ? s : m->aux;
-    DFB_CUDA(cudaEventRecord(m->ev_fork_enc, s));
-    DFB_CUDA(cudaStreamWaitEvent(sa, m->ev_fork_enc, 0));
+    cudaStream_t sa = serial ? s : L.aux;
+    DFB_CUDA(cudaEventRecord(L.ev_fork_enc, s));
+    DFB_CUDA(cudaStreamWaitEvent(sa, L.ev_fork_enc, 0));
     auto mk = [&](const float *in, int Fin, int64_t in_fs, float *out, int Fout, int64_t out_fs, int kt) {
         DwPwParams p{};
         p.in = in; p.Fin = Fin; p.in_fs = in_fs; p.out = out; p.Fout = Fout; p.out_fs = out_fs; p.kt = kt; p.T = T;
@@ -1258,7 +1266,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             DFB_PROF("k_conv_in[df_conv0]", sa);
             k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead, Tsx, Tx);
             DFB_LAUNCH_CHECK();
-            DFB_CUDA(cudaEventRecord(m->ev_c0, sa));
+            DFB_CUDA(cudaEventRecord(L.ev_c0, sa));
         }
         p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);
         if ((rc = blk("enc.df_conv1", p))) return rc;
@@ -1267,11 +1275,11 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             m->dbg.erase("c1");
         }
         if ((rc = run_dwpw<DW_S2>(sa, p, B, pw_sw))) return rc;
-        DFB_CUDA(cudaEventRecord(m->ev_join_enc, sa));
+        DFB_CUDA(cudaEventRecord(L.ev_join_enc, sa));
         // DF pathway conv (needs c0 only; its result is consumed by the very last DF-decoder kernel): on the
         // low-priority stream, so its CTAs only take SMs that the critical path -- the encoder convs now, the GRU
         // clusters later -- leaves idle (timeline: on the auxiliary stream it delayed df_fc_emb by 1.8 ms)
-        DFB_CUDA(cudaStreamWaitEvent(sl, m->ev_c0, 0));
+        DFB_CUDA(cudaStreamWaitEvent(sl, L.ev_c0, 0));
         const int O2 = 2 * c.df_order;
         const float *w1, *w2, *bb;
         if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
@@ -1288,7 +1296,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             else k_df_convp<5, 5, 3><<<grid, 32 * kCpWarps, 0, sl>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
             DFB_LAUNCH_CHECK();
         }
-        DFB_CUDA(cudaEventRecord(m->ev_convp, sl));
+        DFB_CUDA(cudaEventRecord(L.ev_convp, sl));
     }
     {
         DwPwParams p = mk(f.e0, E, (int64_t)E * kCh, f.e1, E / 2, (int64_t)E / 2 * kCh, c.conv_kt);
@@ -1301,7 +1309,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if ((rc = run_dwpw<DW_S1>(s, p, B, pw_sw))) return rc;
 
     }
-    DFB_CUDA(cudaStreamWaitEvent(s, m->ev_join_enc, 0));  // c0 / c1 ready
+    DFB_CUDA(cudaStreamWaitEvent(s, L.ev_join_enc, 0));  // c0 / c1 ready
     {
         // cemb = relu(df_fc_emb(c1 flat)); emb_in = e3 flat + cemb  (DFN2: concat)
         const int I = Fd / 2 * kCh;
@@ -1336,8 +1344,15 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         }
     }
     // fork: the two decoders only share read-only encoder outputs
-    DFB_CUDA(cudaEventRecord(m->ev_fork, s));
-    DFB_CUDA(cudaStreamWaitEvent(sa, m->ev_fork, 0));
+    // the encoder phase is done (ev_fork also tells the next time chunk that it may start); the decoder phase runs on the
+    // lane's greatest-priority streams and, in the chunk pipeline, after the previous chunk's decoder has finished
+    DFB_CUDA(cudaEventRecord(L.ev_fork, s));
+    if (!serial) { s = L.dhi; sa = L.daux; DFB_CUDA(cudaStreamWaitEvent(s, L.ev_fork, 0)); }
+    DFB_CUDA(cudaStreamWaitEvent(sa, L.ev_fork, 0));
+    if (cx && cx->wait_dec) {
+        DFB_CUDA(cudaStreamWaitEvent(s, cx->wait_dec, 0));
+        DFB_CUDA(cudaStreamWaitEvent(sa, cx->wait_dec, 0));
+    }
     // DFN3's grouped-linear skip around the DF GRU does not depend on the recurrence: evaluate it here (the ERB
     // branch has the slack) and let the last GRU layer add it as its output residual, instead of a kernel on the
     // DF branch's tail, which is the critical path of the decoder phase
@@ -1345,7 +1360,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     if (early_skip) {
         if ((rc = gl(s, "df_dec.df_skip.gl", f.emb, emb_dim, &pl_emb, c.g_df_skip, emb_dim, Hd, ACT_NONE, nullptr, 0, f.dfskip, Hd, nullptr)))
             return rc;
-        DFB_CUDA(cudaEventRecord(m->ev_skip, s));
+        DFB_CUDA(cudaEventRecord(L.ev_skip, s));
     }
     // ---- DF decoder (deepfilternet3.py:323-331), on the auxiliary stream (forked after the encoder)
     {
@@ -1353,7 +1368,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if ((rc = gl(s, "df_dec.df_gru.in.gl", f.emb, emb_dim, &pl_emb, c.g_df_in, emb_dim, Hd, ACT_RELU, nullptr, 0, f.g_a2, Hd, &pl_ga2)))
             return rc;
         const float *res = c.model_kind == 2 ? f.g_a2 : (early_skip ? f.dfskip : nullptr);
-        if (early_skip) DFB_CUDA(cudaStreamWaitEvent(s, m->ev_skip, 0));
+        if (early_skip) DFB_CUDA(cudaStreamWaitEvent(s, L.ev_skip, 0));
         if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a2, Hd, res, f.dfc, f.xproj2, f.g_h2, B, T, f.ga2_hi, f.ga2_lo,
                           f.gh2_hi, f.gh2_lo, 1, gl_tc ? pl_dfc.hi : nullptr, gl_tc ? pl_dfc.lo : nullptr, &pl_dfc.ok, cx ? &ck_df : nullptr))) return rc;
         if (c.g_df_skip && !early_skip) {
@@ -1368,11 +1383,11 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         }
         const int O2 = 2 * c.df_order;
         // coefs = tanh(df_out(c)) + df_convp(c0); the pathway term was written by k_df_convp on the low-priority stream
-        DFB_CUDA(cudaStreamWaitEvent(s, m->ev_convp, 0));
+        DFB_CUDA(cudaStreamWaitEvent(s, L.ev_convp, 0));
         if ((rc = gl(s, "df_dec.df_out.gl", f.dfc, Hd, &pl_dfc, c.g_df_out, Hd, Fd * O2, ACT_TANH, d_coefs, (int64_t)Fd * O2, d_coefs,
                      (int64_t)Fd * O2, nullptr))) return rc;
     }
-    DFB_CUDA(cudaEventRecord(m->ev_join, sa));
+    DFB_CUDA(cudaEventRecord(L.ev_join, sa));
     // ---- ERB decoder (deepfilternet3.py:245-254)
     {
         if ((rc = gl(s, "erb_dec.emb_gru.in.gl", f.emb, emb_dim, &pl_emb, c.g_erb_in, emb_dim, H, ACT_RELU, nullptr, 0, f.g_a, H, &pl_ga)))
@@ -1436,6 +1451,16 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         DFB_LAUNCH_CHECK();
     }
     return finish();
+}
+
+// Chunk pipeline of dfb_enhance / dfb_enhance_host: signals of at least 64 * chunks frames are cut into >= `chunks` time
+// chunks (device-pointer / host-pointer entry point); lanes = 2 overlaps the encoder phase of chunk c + 1 with the decoder
+// phase of chunk c, lanes = 1 runs the chunks back to back.  Defaults 6 / 6 / 2 (DFB_DEVICE_CHUNKS, DFB_HOST_CHUNKS,
+// DFB_LANES at dfb_model_create).
+extern "C" int dfb_model_set_chunking(dfb_model *m, int device_chunks, int host_chunks, int lanes) {
+    if (!m || device_chunks < 1 || host_chunks < 1 || lanes < 1 || lanes > 2) return fail(DFB_ERR_INVALID, "bad chunking parameters");
+    m->dev_chunks = device_chunks; m->host_chunks = host_chunks; m->n_lanes = lanes;
+    return DFB_OK;
 }
 
 // The workspace is sized from the model's band layout but the DSP kernels index with the state's: they must agree.
@@ -1609,8 +1634,16 @@ struct ChunkIO {
 
 // One chunk: analyse frames [S.a1, a1n), run the DNN over [S.d1, d1n), emit audio of frames [S.e1, e1n).
 // Tf_end: total frames of the stream when known (features / spectrum beyond it are zero), else -1.
+// lane / pipelined: consecutive chunks of a batch call alternate between the model's two lanes (stream sets + arenas);
+// chunk c starts when chunk c - 1 has finished its ENCODER phase and its decoder phase waits for chunk c - 1 to finish
+// entirely, so encoder(c) overlaps decoder(c - 1).  `s` is the stream the chunk is enqueued on (the lane's main stream
+// in the pipeline, the caller's stream otherwise).
 static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO &io, int64_t a1n, int64_t d1n, int64_t e1n,
-                     cudaStream_t s) {
+                     cudaStream_t s, int lane = 0, bool pipelined = false) {
+    Arena &arena = lane ? m->arena1 : m->arena;
+    dfb_model::Lane &L = m->lanes[lane], &P = m->lanes[lane ^ 1];
+    const bool have_prev = pipelined && S.started;
+    if (have_prev) DFB_CUDA(cudaStreamWaitEvent(s, P.ev_fork, 0));   // previous chunk: features + encoder phase done
     const dfb_model_config &c = m->cfg;
     const ChunkGeom g = chunk_geom(c);
     const int B = S.B, E = c.nb_erb, Fd = c.nb_df, O2 = 2 * c.df_order, F = st->tb.F, hop = st->hop, ED = E / 4 * kCh;
@@ -1622,13 +1655,13 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
         return fail(DFB_ERR_INVALID, "inconsistent chunk geometry");
     const bool run_dnn = d1n > S.d1;      // a short streaming call may only add look-ahead frames
     int rc;
-    m->arena.reset();
-    float *spec = m->arena.take<float>((size_t)B * Tsb * F * 2 + 2);
-    float *fe = m->arena.take<float>((size_t)B * Tsb * E);
-    float *fs = m->arena.take<float>((size_t)B * Tsb * Fd * 2);
-    float *mm = m->arena.take<float>((size_t)B * (Tw + 1) * E);
-    float *cc = m->arena.take<float>((size_t)B * (Tw + 1) * Fd * O2);
-    float *ll = io.lsnr_th ? m->arena.take<float>((size_t)B * (Tw + 1)) : nullptr;
+    arena.reset();
+    float *spec = arena.take<float>((size_t)B * Tsb * F * 2 + 2);
+    float *fe = arena.take<float>((size_t)B * Tsb * E);
+    float *fs = arena.take<float>((size_t)B * Tsb * Fd * 2);
+    float *mm = arena.take<float>((size_t)B * (Tw + 1) * E);
+    float *cc = arena.take<float>((size_t)B * (Tw + 1) * Fd * O2);
+    float *ll = io.lsnr_th ? arena.take<float>((size_t)B * (Tw + 1)) : nullptr;
     if (!cc) return fail(DFB_ERR_OOM, "chunk workspace exhausted");
     // ---- features: carried history, then the new frames
     if ((rc = load_tail(s, spec, Tsb, (size_t)2 * F, n_hist, S.t_spec, g.Hf, 0, B)) || (rc = load_tail(s, fe, Tsb, E, n_hist, S.t_fe, g.Hf, 0, B)) ||
@@ -1642,10 +1675,22 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
                                    fs + (size_t)n_hist * 2 * Fd, s, Tsb, S.erb_state, S.unit_state)))
             return rc;
     }
+    {   // carry the feature history right away: the next chunk may start as soon as this chunk's encoder is done
+        const int nf = Tv < g.Hf ? Tv : g.Hf;
+        // the feature buffers hold Tsb frames per stream of which the first Tv are valid: keep the last nf valid ones
+        const size_t fes[3] = {(size_t)2 * F, (size_t)E, (size_t)2 * Fd};
+        float *bufs[3] = {spec, fe, fs}, *tails[3] = {S.t_spec, S.t_fe, S.t_fs};
+        for (int i = 0; i < 3; i++)
+            DFB_CUDA(cudaMemcpy2DAsync(tails[i] + (size_t)(g.Hf - nf) * fes[i], sizeof(float) * fes[i] * g.Hf,
+                                       bufs[i] + (size_t)(Tv - nf) * fes[i], sizeof(float) * fes[i] * Tsb, sizeof(float) * fes[i] * nf, B,
+                                       cudaMemcpyDeviceToDevice, s));
+        S.n_feat = nf;
+    }
     // ---- DNN over the window
     if (run_dnn) {
-    ChunkCtx cx{Rc, Tsb, Tv, S.h_enc, S.h_erb, S.h_df, S.dnn_started, c.conv_kt > 1 ? S.t_dec : nullptr, S.n_dec};
-    if ((rc = forward_impl(m, m->arena, fe, fs, B, Tw, mm, cc, ll, nullptr, s, &cx))) return rc;
+    ChunkCtx cx{Rc, Tsb, Tv, S.h_enc, S.h_erb, S.h_df, S.dnn_started, c.conv_kt > 1 ? S.t_dec : nullptr, S.n_dec, lane,
+                have_prev ? P.ev_done : nullptr};
+    if ((rc = forward_impl(m, arena, fe, fs, B, Tw, mm, cc, ll, nullptr, s, &cx))) return rc;
     S.n_dec = cx.dec_tail_n;
     S.dnn_started = true;
     // the halo rows of m / coefs come from skipped recurrences: restore the last finished frames from the previous chunk
@@ -1672,15 +1717,6 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
     }
     // ---- carry
     {
-        const int nf = Tv < g.Hf ? Tv : g.Hf;
-        // the feature buffers hold Tsb frames per stream of which the first Tv are valid: keep the last nf valid ones
-        const size_t fes[3] = {(size_t)2 * F, (size_t)E, (size_t)2 * Fd};
-        float *bufs[3] = {spec, fe, fs}, *tails[3] = {S.t_spec, S.t_fe, S.t_fs};
-        for (int i = 0; i < 3; i++)
-            DFB_CUDA(cudaMemcpy2DAsync(tails[i] + (size_t)(g.Hf - nf) * fes[i], sizeof(float) * fes[i] * g.Hf,
-                                       bufs[i] + (size_t)(Tv - nf) * fes[i], sizeof(float) * fes[i] * Tsb, sizeof(float) * fes[i] * nf, B,
-                                       cudaMemcpyDeviceToDevice, s));
-        S.n_feat = nf;
         if (run_dnn) {
             const int nm = Tw < kMcTail ? Tw : kMcTail;
             if ((rc = save_tail(s, mm, Tw, E, nm, S.t_m, kMcTail, B)) || (rc = save_tail(s, cc, Tw, (size_t)Fd * O2, nm, S.t_c, kMcTail, B))) return rc;
@@ -1689,6 +1725,10 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
         }
     }
     (void)ED;
+    if (pipelined) {
+        if (!run_dnn) DFB_CUDA(cudaEventRecord(L.ev_fork, s));   // no forward pass recorded it
+        DFB_CUDA(cudaEventRecord(L.ev_done, s));
+    }
     S.a1 = a1n; S.d1 = d1n; if (run_dnn) S.e1 = e1n;
     S.started = true;
     return DFB_OK;
@@ -1713,12 +1753,13 @@ static int pick_chunk(const dfb_model *m, const dfb_state *st, int64_t B, int64_
 // `before` / `after` are called around every chunk with the sample ranges it reads / has written).
 struct ChunkHooks {
     // analysis of this chunk reads input samples [x0, x1) of every stream; output samples [y0, y1) have been written
-    std::function<int(int64_t x0, int64_t x1)> before;
-    std::function<int(int64_t y0, int64_t y1)> after;
+    // `cs` is the stream the chunk's compute is enqueued on (must wait for the input / produces the output)
+    std::function<int(int64_t x0, int64_t x1, cudaStream_t cs)> before;
+    std::function<int(int64_t y0, int64_t y1, cudaStream_t cs)> after;
 };
 
 static int enhance_group(dfb_model *m, dfb_state *st, const float *d_x, int64_t nb, int64_t Tp, int64_t in_valid, int pad,
-                         float lim, float *d_out, int64_t out_len, int tc, cudaStream_t s, const ChunkHooks *hooks) {
+                         float lim, float *d_out, int64_t out_len, int tc, bool pipelined, cudaStream_t s, const ChunkHooks *hooks) {
     const dfb_model_config &c = m->cfg;
     const ChunkGeom g = chunk_geom(c);
     const int hop = st->hop, fft = st->fft;
@@ -1731,40 +1772,69 @@ static int enhance_group(dfb_model *m, dfb_state *st, const float *d_x, int64_t 
     state_bind(S, slab, off, (int)nb);
     int rc = DFB_OK;
     const int64_t delay = pad ? fft - hop : 0;
+    if (tc >= Tf) pipelined = false;      // a single chunk
+    cudaEvent_t ev_call = nullptr;
+    if (pipelined) {  // both lanes start after everything the caller has enqueued so far
+        DFB_CUDA(cudaEventCreateWithFlags(&ev_call, cudaEventDisableTiming));
+        DFB_CUDA(cudaEventRecord(ev_call, s));
+        DFB_CUDA(cudaStreamWaitEvent(m->lanes[0].main, ev_call, 0));
+        DFB_CUDA(cudaStreamWaitEvent(m->lanes[1].main, ev_call, 0));
+    }
+    int chunk = 0, last_lane = 0;
     while (S.d1 < Tf) {
         const int64_t d1n = S.d1 + tc < Tf ? S.d1 + tc : Tf;
         const int64_t a1n = d1n + g.Lmax < Tf ? d1n + g.Lmax : Tf;
         const int64_t e1n = d1n == Tf ? Tf : d1n - g.lag;
+        const int lane = pipelined ? (chunk & 1) : 0;
+        cudaStream_t cs = pipelined ? m->lanes[lane].main : s;
         if (hooks && hooks->before) {
             int64_t x0 = S.a1 * hop, x1 = a1n * hop;
             if (x1 > in_valid) x1 = in_valid;
-            if (x0 < x1 && (rc = hooks->before(x0, x1))) break;
+            if (x0 < x1 && (rc = hooks->before(x0, x1, cs))) break;
         }
         const int64_t e0 = S.e1;
         ChunkIO io{d_x, Tp, Tp, 0, nullptr, d_out, out_len, out_len, delay, lim, nullptr};
-        if ((rc = run_chunk(m, st, S, io, a1n, d1n, e1n > S.e1 ? e1n : S.e1, s))) break;
+        if ((rc = run_chunk(m, st, S, io, a1n, d1n, e1n > S.e1 ? e1n : S.e1, cs, lane, pipelined))) break;
         if (hooks && hooks->after) {
             int64_t y0 = e0 * hop - delay, y1 = S.e1 * hop - delay;
             if (y0 < 0) y0 = 0;
             if (y1 > out_len) y1 = out_len;
-            if (y0 < y1 && (rc = hooks->after(y0, y1))) break;
+            if (y0 < y1 && (rc = hooks->after(y0, y1, cs))) break;
         }
+        last_lane = lane;
+        chunk++;
+    }
+    if (pipelined) {  // hand the result back to the caller's stream (the last chunk finishes after all earlier ones)
+        if (chunk > 0) cudaStreamWaitEvent(s, m->lanes[last_lane].ev_done, 0);
+        if (chunk > 1) cudaStreamWaitEvent(s, m->lanes[last_lane ^ 1].ev_done, 0);
+        if (rc) cudaDeviceSynchronize();
+        cudaEventDestroy(ev_call);
     }
     return rc;
 }
 
 // enhance(): df/enhance.py:206-250.  Time chunks (above) inside stream groups: a group is as many streams as fit the
 // workspace cap with a reasonable chunk; streams are independent (per-channel state reset, pyDF/src/lib.rs:56-58).
-static int enhance_plan(dfb_model *m, dfb_state *st, int64_t B, int64_t Tf, int min_chunks, int64_t *group_out, int *tc_out) {
+static int enhance_plan(dfb_model *m, dfb_state *st, int64_t B, int64_t Tf, int min_chunks, int64_t *group_out, int *tc_out,
+                        bool *pipelined_out) {
+    // two lanes (DFB_LANES=1 turns the chunk pipeline off): each lane's arena may take half of the workspace cap
+    static const bool serial = getenv("DFB_SERIAL") && atoi(getenv("DFB_SERIAL"));
+    const bool pipelined = m->n_lanes == 2 && !serial && min_chunks > 1 && Tf >= (int64_t)min_chunks * 64;
+    const size_t cap = m->max_workspace;
+    if (pipelined) m->max_workspace = cap / 2;
     int64_t group = B > 65535 ? 65535 : B;
     int tc = 0;
     while ((tc = pick_chunk(m, st, group, Tf, min_chunks)) == 0) {
-        if (group == 1) return fail(DFB_ERR_OOM, "workspace cap of %zu bytes is too small for a single stream", m->max_workspace);
+        if (group == 1) { m->max_workspace = cap; return fail(DFB_ERR_OOM, "workspace cap of %zu bytes is too small for a single stream", cap); }
         group = (group + 1) / 2;
     }
-    *group_out = group; *tc_out = tc;
+    m->max_workspace = cap;
+    *group_out = group; *tc_out = tc; *pipelined_out = pipelined && tc < Tf;
     const ChunkGeom g = chunk_geom(m->cfg);
-    return m->arena.reserve(chunk_bytes_per_stream(m->cfg, st, tc + kHalo) * (size_t)group + ((size_t)g.Lmax << 10) + (2 << 20));
+    const size_t bytes = chunk_bytes_per_stream(m->cfg, st, tc + kHalo) * (size_t)group + ((size_t)g.Lmax << 10) + (2 << 20);
+    int rc = m->arena.reserve(bytes);
+    if (!rc && *pipelined_out) rc = m->arena1.reserve(bytes);
+    return rc;
 }
 
 extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, int64_t B, int64_t T, int pad,
@@ -1782,7 +1852,8 @@ extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, in
     const int64_t out_len = dfb_enhance_out_len(st, T, pad);
     int64_t group = 0;
     int tc = 0, rc;
-    if ((rc = enhance_plan(m, st, B, Tf, 1, &group, &tc))) return rc;
+    bool pipelined = false;
+    if ((rc = enhance_plan(m, st, B, Tf, m->dev_chunks, &group, &tc, &pipelined))) return rc;
     const float lim = (atten_lim_db > 0.f) ? powf(10.f, -atten_lim_db / 20.f) : 0.f;
     size_t off[16];
     if ((rc = m->aux_arena.reserve((state_floats(m->cfg, st, (int)group, off) + (pad ? (size_t)group * Tp : 0)) * sizeof(float) + 8192))) return rc;
@@ -1797,9 +1868,10 @@ extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, in
                      ? fail(DFB_ERR_CUDA, "padding copy failed") : DFB_OK;
             x = xp;
         }
-        if (!rc) rc = enhance_group(m, st, x, nb, Tp, Tp, pad, lim, d_out + b0 * out_len, out_len, tc, s, nullptr);
+        if (!rc) rc = enhance_group(m, st, x, nb, Tp, Tp, pad, lim, d_out + b0 * out_len, out_len, tc, pipelined, s, nullptr);
     }
     m->arena.reset();
+    m->arena1.reset();
     return rc;
 }
 
@@ -1817,8 +1889,8 @@ extern "C" int dfb_enhance_host(dfb_model *m, dfb_state *st, const float *h_audi
     const int64_t out_len = dfb_enhance_out_len(st, T, pad);
     int64_t group = 0;
     int tc = 0, rc;
-    static const int host_chunks = getenv("DFB_HOST_CHUNKS") ? atoi(getenv("DFB_HOST_CHUNKS")) : 6;
-    if ((rc = enhance_plan(m, st, B, Tf, host_chunks, &group, &tc))) return rc;
+    bool pipelined = false;
+    if ((rc = enhance_plan(m, st, B, Tf, m->host_chunks, &group, &tc, &pipelined))) return rc;
     const float lim = (atten_lim_db > 0.f) ? powf(10.f, -atten_lim_db / 20.f) : 0.f;
     size_t off[16];
     if ((rc = m->aux_arena.reserve(state_floats(m->cfg, st, (int)group, off) * sizeof(float) + 8192))) return rc;
@@ -1842,30 +1914,31 @@ extern "C" int dfb_enhance_host(dfb_model *m, dfb_state *st, const float *h_audi
         if (pad)  // zero tail of the padded rows (enhance.py:233)
             DFB_CUDA(cudaMemset2DAsync(d_in + T, sizeof(float) * Tp, 0, sizeof(float) * (Tp - T), nb, sh));
         ChunkHooks hooks;
-        hooks.before = [&](int64_t x0, int64_t x1) -> int {
+        hooks.before = [&](int64_t x0, int64_t x1, cudaStream_t cs) -> int {
             if (x1 > T) x1 = T;
             if (x0 < x1)
                 DFB_CUDA(cudaMemcpy2DAsync(d_in + x0, sizeof(float) * Tp, hx + x0, sizeof(float) * T, sizeof(float) * (x1 - x0), nb,
                                            cudaMemcpyHostToDevice, sh));
             cudaEvent_t e = new_event();
             DFB_CUDA(cudaEventRecord(e, sh));
-            DFB_CUDA(cudaStreamWaitEvent(sc, e, 0));
+            DFB_CUDA(cudaStreamWaitEvent(cs, e, 0));
             return DFB_OK;
         };
-        hooks.after = [&](int64_t y0, int64_t y1) -> int {
+        hooks.after = [&](int64_t y0, int64_t y1, cudaStream_t cs) -> int {
             cudaEvent_t e = new_event();
-            DFB_CUDA(cudaEventRecord(e, sc));
+            DFB_CUDA(cudaEventRecord(e, cs));
             DFB_CUDA(cudaStreamWaitEvent(sd, e, 0));
             DFB_CUDA(cudaMemcpy2DAsync(hy + y0, sizeof(float) * out_len, d_out + y0, sizeof(float) * out_len, sizeof(float) * (y1 - y0), nb,
                                        cudaMemcpyDeviceToHost, sd));
             return DFB_OK;
         };
         m->aux_arena.reset();
-        rc = enhance_group(m, st, d_in, nb, Tp, T, pad, lim, d_out, out_len, tc, sc, &hooks);
+        rc = enhance_group(m, st, d_in, nb, Tp, T, pad, lim, d_out, out_len, tc, pipelined, sc, &hooks);
     }
     cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sd), e3 = cudaStreamSynchronize(sh);
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
     m->arena.reset();
+    m->arena1.reset();
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(DFB_ERR_CUDA, "enhance_host failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
