@@ -157,10 +157,18 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__
             if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);  // accumulator read: hand the buffer back before the stores
             float *dst = Y + (int64_t)m0 * ldy + n;
             if (accumulate && n < N) {
+                // second K pass: Y += D.  All loads of a half first (independent), then the stores: as separate
+                // load / add / store triples the compiler must assume aliasing and serialises 64 DRAM round trips
+                const bool full = m0 + 64 <= M;
 #pragma unroll
-                for (int j = 0; j < 32; j++) { if (m0 + j < M) *dst += v0[j]; dst += ldy; }
+                for (int j = 0; j < 32; j++) v0[j] += (full || m0 + j < M) ? dst[(int64_t)j * ldy] : 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; j++) { if (m0 + 32 + j < M) *dst += v1[j]; dst += ldy; }
+                for (int j = 0; j < 32; j++) if (full || m0 + j < M) dst[(int64_t)j * ldy] = v0[j];
+                float *dst1 = dst + 32 * ldy;
+#pragma unroll
+                for (int j = 0; j < 32; j++) v1[j] += (full || m0 + 32 + j < M) ? dst1[(int64_t)j * ldy] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (full || m0 + 32 + j < M) dst1[(int64_t)j * ldy] = v1[j];
             } else if (m0 + 64 <= M && n < N) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) { *dst = v0[j] + bn; dst += ldy; }

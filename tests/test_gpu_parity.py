@@ -462,7 +462,7 @@ def test_streaming_equals_one_shot(states, kind):
     got = torch.cat(outs, 1)
     lat = s.latency_frames * hop
     assert got.shape == (2, n * hop + lat)
-    assert got[:, :lat].abs().max() == 0
+    assert lat == 0 or got[:, :lat].abs().max() == 0
     assert rms(got[:, lat:], ref) < 1e-6
     # a reset stream reproduces itself; atten_lim is honoured
     s.reset()
