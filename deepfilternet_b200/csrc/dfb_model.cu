@@ -24,6 +24,7 @@
 
 #include "dfb_common.cuh"
 #include "dfb_dwpw.cuh"
+#include "dfb_ptx.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -628,23 +629,27 @@ k_mask_out(const float *__restrict__ e0, const float *__restrict__ d1, const flo
 // coefs[b,t,f,:] = relu( pw( conv_t(c0) ) + b ); the df_out projection later adds tanh(df_out(c)) on top
 // (deepfilternet3.py:293-295, 328-330).  df_convp = grouped (2) temporal conv C -> 2*O with kernel (ktp,1),
 // 1x1 conv, BN, ReLU.
-// Half a warp owns one frequency bin f and marches along t: lane q holds channel quad q of the 256-byte c0 row
-// (so a warp load is 512 contiguous bytes and every c0 element is read once per chunk), keeps its 4 channels'
-// taps for all (dt, o) in registers for the whole kernel, and accumulates the ktp in-flight output frames in
-// rotating registers.  A finished frame is reduced over the 8 lanes of its channel group with shuffles, the two
-// groups are exchanged, and lanes 0..2*O-1 apply the 1x1 conv + bias + ReLU and store 40 contiguous bytes.
-constexpr int kMaxO2 = 16, kCpWarps = 4, kCpChunk = 128;
+// A warp owns two adjacent frequency bins and marches along t: the 512 contiguous bytes of c0 it needs per frame arrive
+// by one TMA bulk copy into a per-warp ring of kCpSlots slots (armed kCpSlots frames ahead: ~10 KB in flight per warp,
+// 120 KB per SM -- the first version prefetched five frames through registers, ~30 KB per SM, and sat at 0.30 of the HBM
+// roofline with 12 % occupancy), lane q reads channel quad q of its bin from the slot, keeps its 4 channels' taps for
+// all (dt, o) in registers for the whole kernel, and accumulates the ktp in-flight output frames in rotating registers.
+// A finished frame is reduced over the 8 lanes of its channel group with shuffles, the two groups are exchanged, and
+// lanes 0..2*O-1 apply the 1x1 conv + bias + ReLU and store 40 contiguous bytes.
+constexpr int kMaxO2 = 16, kCpWarps = 4, kCpChunk = 128, kCpSlots = 20;
 template <int ORDER, int KTP, int MINB>
 __global__ void __launch_bounds__(32 * kCpWarps, MINB)
 k_df_convp(const float *__restrict__ c0 /*[B,T,Fd,64]*/, const float *__restrict__ w1 /*[ktp][O2][32]*/,
            const float *__restrict__ w2 /*[O2][O2]*/, const float *__restrict__ bias, float *__restrict__ coefs,
            int T, int Fd) {
+    static_assert(kCpSlots % KTP == 0, "a group of KTP frames must not wrap around the ring");
     constexpr int O2 = 2 * ORDER, CG = kCh / 2;
+    extern __shared__ __align__(128) unsigned char cp_smem[];   // [warp][slot][512 B] | [warp][slot] mbarriers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = lane & 15, g = q >> 3, cq = q & 7;
-    const int f_raw = (blockIdx.x * kCpWarps + warp) * 2 + (lane >> 4);
-    const bool f_ok = f_raw < Fd;
-    const int f = f_ok ? f_raw : Fd - 1;
+    const int f0 = (blockIdx.x * kCpWarps + warp) * 2;        // the warp's first bin (Fd is even: both bins exist or none)
+    const bool f_ok = f0 + 1 < Fd;
+    const int f = f0 + (lane >> 4);
     const int b = blockIdx.z;
     const int t_begin = blockIdx.y * kCpChunk, t_end = min(T, t_begin + kCpChunk);
     float4 wv[KTP][ORDER];
@@ -656,26 +661,53 @@ k_df_convp(const float *__restrict__ c0 /*[B,T,Fd,64]*/, const float *__restrict
     __shared__ float s_w2[O2 * O2 + O2];  // 1x1 conv | bias; lane q < O2 applies column q
     for (int i = threadIdx.x; i < O2 * O2; i += blockDim.x) s_w2[i] = w2[i];
     if (threadIdx.x < O2) s_w2[O2 * O2 + threadIdx.x] = bias[threadIdx.x];
+    const uint32_t ring = smem_u32(cp_smem) + (uint32_t)warp * kCpSlots * 512u;
+    const uint32_t bars = smem_u32(cp_smem) + (uint32_t)kCpWarps * kCpSlots * 512u + (uint32_t)warp * kCpSlots * 8u;
+    if (lane == 0) {
+        for (int i = 0; i < kCpSlots; i++) mbar_init_a(bars + 8 * i, 1);
+        fence_barrier_init();
+    }
     __syncthreads();
+    if (!f_ok) return;
     const float *s2c = s_w2 + (q < O2 ? q : 0);
     float acc[KTP][ORDER];
 #pragma unroll
     for (int u = 0; u < KTP; u++)
 #pragma unroll
         for (int o = 0; o < ORDER; o++) acc[u][o] = 0.f;
-    const float *base = c0 + ((int64_t)b * T * Fd + f) * kCh + 4 * q;
+    const float *src0 = c0 + ((int64_t)b * T * Fd + f0) * kCh;   // frame 0 of the warp's two bins (512 contiguous bytes per frame)
     const int64_t fs = (int64_t)Fd * kCh;
     const int tstart = t_begin - (KTP - 1);
-    auto load = [&](int tp) -> float4 {
-        return (tp >= 0 && tp < t_end) ? __ldg(reinterpret_cast<const float4 *>(base + (int64_t)tp * fs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // frame tp lives in slot (tp - tstart) % kCpSlots; frames before the stream start are zeros and never loaded
+    auto arm = [&](int tp) {
+        const uint32_t slot = (uint32_t)((tp - tstart) % kCpSlots);
+        if (tp >= 0 && tp < t_end) {
+            mbar_expect_tx_a(bars + 8 * slot, 512);
+            bulk_load(ring + slot * 512u, src0 + (int64_t)tp * fs, 512, bars + 8 * slot);
+        } else if (tp < 0) {
+            mbar_arrive_a(bars + 8 * slot);   // nothing to load: still complete the phase so that the slot's parity stays in step
+        }
     };
-    float4 xn[KTP];
-#pragma unroll
-    for (int u = 0; u < KTP; u++) xn[u] = load(tstart + u);
+    if (lane == 0)
+        for (int i = 0; i < kCpSlots; i++) arm(tstart + i);
+    __syncwarp();
     for (int tb = tstart; tb < t_end; tb += KTP) {
+        const uint32_t slot0 = (uint32_t)((tb - tstart) % kCpSlots), parity = (uint32_t)(((tb - tstart) / kCpSlots) & 1);
         float4 x[KTP];
 #pragma unroll
-        for (int u = 0; u < KTP; u++) { x[u] = xn[u]; xn[u] = load(tb + KTP + u); }  // prefetch the next group
+        for (int u = 0; u < KTP; u++) {
+            const int tp = tb + u;
+            if (tp >= 0 && tp < t_end) {
+                mbar_wait_a(bars + 8 * (slot0 + u), parity);
+                x[u] = lds128(ring + (slot0 + u) * 512u + lane * 16u);
+            } else {
+                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncwarp();                       // every lane has its values: the slots may be refilled
+        if (lane == 0)
+#pragma unroll
+            for (int u = 0; u < KTP; u++) arm(tb + u + kCpSlots);
 #pragma unroll
         for (int u = 0; u < KTP; u++) {
             const int tp = tb + u;
@@ -708,7 +740,7 @@ k_df_convp(const float *__restrict__ c0 /*[B,T,Fd,64]*/, const float *__restrict
                 for (int k = 0; k < ORDER; k++) out = fmaf(g ? w[k] : v[k], s2c[k * O2], out);
 #pragma unroll
                 for (int k = 0; k < ORDER; k++) out = fmaf(g ? v[k] : w[k], s2c[(ORDER + k) * O2], out);
-                if (q < O2 && f_ok) coefs[(((int64_t)b * T + tp) * Fd + f) * O2 + q] = fmaxf(out, 0.f);
+                if (q < O2) coefs[(((int64_t)b * T + tp) * Fd + f) * O2 + q] = fmaxf(out, 0.f);
             }
         }
     }
@@ -1288,12 +1320,12 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         if (c.df_order != 5 || c.df_pathway_kt != 5)
             return fail(DFB_ERR_UNSUPPORTED, "df_order %d / df_pathway_kernel_size_t %d (built kernels: 5, 5)", c.df_order,
                         c.df_pathway_kt);
+        if (Fd % 2) return fail(DFB_ERR_UNSUPPORTED, "df pathway conv: odd nb_df");
         dim3 grid((unsigned)((Fd + 2 * kCpWarps - 1) / (2 * kCpWarps)), (unsigned)((T + kCpChunk - 1) / kCpChunk), (unsigned)B);
         {
             DFB_PROF("k_df_convp", sl);
-            static const int minb = getenv("DFB_CONVP_MINB") ? atoi(getenv("DFB_CONVP_MINB")) : 2;
-            if (minb == 2) k_df_convp<5, 5, 2><<<grid, 32 * kCpWarps, 0, sl>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
-            else k_df_convp<5, 5, 3><<<grid, 32 * kCpWarps, 0, sl>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
+            const int smem = kCpWarps * kCpSlots * (512 + 8);
+            k_df_convp<5, 5, 3><<<grid, 32 * kCpWarps, smem, sl>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);
             DFB_LAUNCH_CHECK();
         }
         DFB_CUDA(cudaEventRecord(L.ev_convp, sl));
