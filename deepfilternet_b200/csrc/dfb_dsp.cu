@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) k_resample(const float *__restrict__ x, i
 // sequential in t per (stream, band | bin) exactly like the reference loops.
 // grid B, block E + Fd threads (thread j < E: band j; else bin j - E).  Loads are batched kPf
 // frames ahead so the dependent chain is arithmetic only.
-constexpr int kPf = 8;
+constexpr int kPf = 24;   // frames of loads in flight per thread (8: 0.34 ms per 128 x 1002 frames, latency bound at 0.10 of HBM)
 // Ts = frames per stream in the four buffers (the pointers are pre-offset to the first frame to process, Tf = number of
 // frames processed); *_state_out (may alias the inputs) receive the EMA states after the last frame.
 __global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,

@@ -162,18 +162,22 @@ k_gl_bx(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUten
                 const int gl = c / p.Hgp, n = c - gl * p.Hgp + 4 * pc;   // column inside the group
                 const int64_t col = (int64_t)(g0 + gl) * p.Hg + n;
                 if (n < p.Hg) {
+                    // residual rows first, all four in flight (as load / store pairs per row the compiler has to assume that
+                    // res aliases y -- it does for df_out -- and serialises four DRAM round trips per chunk)
+                    float4 rv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int64_t m = mbase + rr + 8 * i;
+                        rv[i] = (p.res && m < p.M) ? *reinterpret_cast<const float4 *>(p.res + m * p.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int r = rr + 8 * i;
                         const int64_t m = mbase + r;
                         if (m >= p.M) continue;
                         float4 x = lds128(stg + r * kGxStageRow + pc * 16);
-                        x.x = gx_act(x.x, p.act) * p.oscale + p.ooffset; x.y = gx_act(x.y, p.act) * p.oscale + p.ooffset;
-                        x.z = gx_act(x.z, p.act) * p.oscale + p.ooffset; x.w = gx_act(x.w, p.act) * p.oscale + p.ooffset;
-                        if (p.res) {
-                            const float4 rv = *reinterpret_cast<const float4 *>(p.res + m * p.ldr + col);
-                            x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
-                        }
+                        x.x = gx_act(x.x, p.act) * p.oscale + p.ooffset + rv[i].x; x.y = gx_act(x.y, p.act) * p.oscale + p.ooffset + rv[i].y;
+                        x.z = gx_act(x.z, p.act) * p.oscale + p.ooffset + rv[i].z; x.w = gx_act(x.w, p.act) * p.oscale + p.ooffset + rv[i].w;
                         if (p.y) *reinterpret_cast<float4 *>(p.y + m * p.ldy + col) = x;
                         if (p.y_hi) {
                             uint32_t h0, l0, h1, l1;

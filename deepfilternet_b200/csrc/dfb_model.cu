@@ -1388,6 +1388,11 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     // DFN3's grouped-linear skip around the DF GRU does not depend on the recurrence: evaluate it here (the ERB
     // branch has the slack) and let the last GRU layer add it as its output residual, instead of a kernel on the
     // DF branch's tail, which is the critical path of the decoder phase
+    // the two decoders' recurrences run concurrently and at most 15 clusters of 8 CTAs are co-resident: one branch uses 32
+    // streams per cluster for batches above 64 (DFB_WIDE_BRANCH=erb|df|both|none selects which, for experiments)
+    static const char *wide_env = getenv("DFB_WIDE_BRANCH");
+    const int wide_df = !wide_env || !strcmp(wide_env, "df") || !strcmp(wide_env, "both");
+    const int wide_erb = wide_env && (!strcmp(wide_env, "erb") || !strcmp(wide_env, "both"));
     const bool early_skip = c.g_df_skip && c.model_kind != 2;
     if (early_skip) {
         if ((rc = gl(s, "df_dec.df_skip.gl", f.emb, emb_dim, &pl_emb, c.g_df_skip, emb_dim, Hd, ACT_NONE, nullptr, 0, f.dfskip, Hd, nullptr)))
@@ -1402,7 +1407,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         const float *res = c.model_kind == 2 ? f.g_a2 : (early_skip ? f.dfskip : nullptr);
         if (early_skip) DFB_CUDA(cudaStreamWaitEvent(s, L.ev_skip, 0));
         if ((rc = run_gru(m, s, "df_dec.df_gru", c.df_gru_layers, Hd, f.g_a2, Hd, res, f.dfc, f.xproj2, f.g_h2, B, T, f.ga2_hi, f.ga2_lo,
-                          f.gh2_hi, f.gh2_lo, 1, gl_tc ? pl_dfc.hi : nullptr, gl_tc ? pl_dfc.lo : nullptr, &pl_dfc.ok, cx ? &ck_df : nullptr))) return rc;
+                          f.gh2_hi, f.gh2_lo, wide_df, gl_tc ? pl_dfc.hi : nullptr, gl_tc ? pl_dfc.lo : nullptr, &pl_dfc.ok, cx ? &ck_df : nullptr))) return rc;
         if (c.g_df_skip && !early_skip) {
             if ((rc = gl(s, "df_dec.df_skip.gl", f.emb, emb_dim, &pl_emb, c.g_df_skip, emb_dim, Hd, ACT_NONE, f.dfc, Hd, f.dfc, Hd, nullptr)))
                 return rc;
@@ -1428,7 +1433,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         const float *res = c.model_kind == 2 ? f.g_a : nullptr;
         pl_gb.ok = false;
         if ((rc = run_gru(m, s, "erb_dec.emb_gru", c.erb_gru_layers, H, f.g_a, H, res, f.g_b, f.xproj, f.g_h, B, T, f.ga_hi, f.ga_lo,
-                          f.gh_hi, f.gh_lo, 0, gl_tc ? pl_gb.hi : nullptr, gl_tc ? pl_gb.lo : nullptr, &pl_gb.ok, cx ? &ck_erb : nullptr))) return rc;
+                          f.gh_hi, f.gh_lo, wide_erb, gl_tc ? pl_gb.hi : nullptr, gl_tc ? pl_gb.lo : nullptr, &pl_gb.ok, cx ? &ck_erb : nullptr))) return rc;
         if ((rc = gl(s, "erb_dec.emb_gru.out.gl", f.g_b, H, &pl_gb, c.g_erb_out, H, ED, ACT_RELU, nullptr, 0, f.dec_emb, ED, nullptr)))
             return rc;
         if (cx && cx->dec_tail && c.conv_kt > 1) {
