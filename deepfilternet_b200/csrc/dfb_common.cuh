@@ -137,6 +137,7 @@ struct ApplyParams {
     // is not written (they belong to the previous window and are only re-synthesised for the overlap-add tail)
     int spec_T, Tv, t_first;
     int mc_T;             // frames per stream in m / coefs (0 = Tf)
+    int frames_per_warp;  // consecutive frames one warp synthesises (set by the launcher)
     // optional stages: post filter (DFN3: on the enhanced spectrum, deepfilternet3.py:448-454; DFN2: on the ERB gains,
     // modules.py:234-245 with beta = 0.02) and mask_only (run_df = False: no deep filter, every bin takes the ERB gain)
     int pf, mask_only;

@@ -372,17 +372,19 @@ __global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
 // it re-synthesises frame t0-1 to obtain the tail of its first frame.
 // Algorithmic HBM bytes per frame (mode 1/2): 3848 R spec + 128 R m + 3840 R coefs + 1920 W audio.
 
-// Valin's post filter on an ERB gain (Mask.pf, modules.py:234-245)
+// Valin's post filter on an ERB gain (Mask.pf, modules.py:234-245).  __sinf on [0, pi/2] is within 2^-21 absolute; the
+// accurate sinf / hypotf (argument-reduction slow paths, 16 inlined copies in the unrolled bin loop) bloated the apply kernel
+// past the instruction cache and cost 30 % even with the filter off.
 __device__ __forceinline__ float pf_gain_mask(float m, float beta) {
-    const float ms = fmaxf(m * sinf(3.14159265358979f * m / 2.f), 1e-12f);
+    const float ms = fmaxf(m * __sinf(3.14159265358979f * m / 2.f), 1e-12f);
     const float q = m / ms;
     return (1.f + beta) * m / (1.f + beta * q * q);
 }
 // ... and on an enhanced bin y of the noisy bin x (deepfilternet3.py:448-454): returns the factor for y
 __device__ __forceinline__ float pf_gain_spec(float2 y, float2 x, float beta) {
     const float eps = 1e-12f;
-    const float mask = fminf(fmaxf(hypotf(y.x, y.y) / (hypotf(x.x, x.y) + eps), eps), 1.f);
-    const float ms = mask * fmaxf(sinf(3.14159265358979f * mask / 2.f), eps);
+    const float mask = fminf(fmaxf(sqrtf(y.x * y.x + y.y * y.y) / (sqrtf(x.x * x.x + x.y * x.y) + eps), eps), 1.f);
+    const float ms = mask * fmaxf(__sinf(3.14159265358979f * mask / 2.f), eps);
     const float q = mask / ms;
     return (1.f + beta) / (1.f + beta * q * q);
 }
@@ -438,9 +440,10 @@ __global__ void __launch_bounds__(32 * kSynWarps) k_apply_synthesis_generic(Appl
 #pragma unroll
     for (int k1 = 0; k1 < kN1; k1++) tw[k1] = lane < kN2 ? tb.tw_a_inv[lane * kN1 + k1] : make_float2(0.f, 0.f);
     __syncthreads();
-    const int t0 = (blockIdx.x * kSynWarps + warp) * kSynChunk;
+    const int syn_chunk = p.frames_per_warp ? p.frames_per_warp : kSynChunk;
+    const int t0 = (blockIdx.x * kSynWarps + warp) * syn_chunk;
     if (t0 >= p.Tf) return;
-    const int t1 = min(t0 + kSynChunk, p.Tf);
+    const int t1 = min(t0 + syn_chunk, p.Tf);
     const float2 *srow0 = p.spec + (int64_t)b * (p.spec_T ? p.spec_T : p.Tf) * kF;
     const int mcT = p.mc_T ? p.mc_T : p.Tf;
     const float *mrow0 = p.m ? p.m + (int64_t)b * mcT * tb.E : nullptr;
@@ -522,9 +525,10 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
     for (int i = tid; i < 241; i += blockDim.x) s_tw960[i] = tb.tw960[i];
     for (int i = tid; i < kN2 * kN1; i += blockDim.x) s_twa[i] = tb.tw_a_inv[i];
     __syncthreads();
-    const int t0 = (blockIdx.x * kSynWarps + warp) * kSynChunk;
+    const int syn_chunk = p.frames_per_warp ? p.frames_per_warp : kSynChunk;
+    const int t0 = (blockIdx.x * kSynWarps + warp) * syn_chunk;
     if (t0 >= p.Tf) return;
-    const int t1 = min(t0 + kSynChunk, p.Tf);
+    const int t1 = min(t0 + syn_chunk, p.Tf);
     const int Tf = p.Tf, L = p.lookahead, back = ORDER - 1 - L;
     const int Tv = p.Tv ? p.Tv : Tf;                       // spectrum rows >= Tv do not exist (end of the stream)
     const float2 *srow0 = p.spec + (int64_t)b * (p.spec_T ? p.spec_T : Tf) * kF;
@@ -897,18 +901,22 @@ int launch_apply_synthesis(dfb_state *st, const ApplyParams &p, int64_t B, cudaS
     if (B <= 0 || p.Tf <= 0) return DFB_OK;
     if (B > 65535) return fail(DFB_ERR_INVALID, "more than 65535 channels per call");
     if (p.mode != 0 && (p.nb_df > 240 || p.order > 8)) return fail(DFB_ERR_UNSUPPORTED, "nb_df > 240 or df_order > 8");
-    int per_cta = kSynWarps * kSynChunk;
+    // frames per warp: 16 amortises the re-synthesis of the frame before a warp's first one; short windows (time chunks)
+    // take 8 so that the grid still fills the device with a few waves
+    ApplyParams q = p;
+    q.frames_per_warp = (B * (int64_t)p.Tf / kSynChunk >= 6000) ? kSynChunk : kSynChunk / 2;
+    int per_cta = kSynWarps * q.frames_per_warp;
     dim3 grid((unsigned)((p.Tf + per_cta - 1) / per_cta), (unsigned)B);
     if (p.lsnr && !(p.mode == 1 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs))
         return fail(DFB_ERR_UNSUPPORTED, "LSNR stage gating is built for the DeepFilterNet3 apply kernel only");
     DFB_PROF("k_apply_synthesis", s);
     static const int minb = getenv("DFB_APPLY_MINB") ? atoi(getenv("DFB_APPLY_MINB")) : 2;  // 2 CTAs/SM without spills measured fastest
     if (p.mode != 0 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs && minb == 3)
-        k_apply_synthesis<5, 3, 3><<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
+        k_apply_synthesis<5, 3, 3><<<grid, 32 * kSynWarps, 0, s>>>(q, st->tb);
     else if (p.mode != 0 && p.order == 5 && p.nb_df == 96 && st->tb.E == 32 && p.m && p.coefs && minb == 2)
-        k_apply_synthesis<5, 3, 2><<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
+        k_apply_synthesis<5, 3, 2><<<grid, 32 * kSynWarps, 0, s>>>(q, st->tb);
     else
-        k_apply_synthesis_generic<<<grid, 32 * kSynWarps, 0, s>>>(p, st->tb);
+        k_apply_synthesis_generic<<<grid, 32 * kSynWarps, 0, s>>>(q, st->tb);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }

@@ -768,7 +768,7 @@ struct dfb_model {
     int gru_tc = 0;  // 1: tensor-core recurrence (BF16 hi/lo split operands) for H = 256
     long long *gru_dbg = nullptr;  // device buffer for dfb_debug_gru_timing
     Arena arena;
-    int dev_chunks = 6, host_chunks = 6, n_lanes = 2;   // chunk pipeline (dfb_model_set_chunking)
+    int dev_chunks = 0, host_chunks = 4, n_lanes = 2;   // chunk pipeline (dfb_model_set_chunking); dev_chunks 0 = auto
     int post_filter = 0, mask_only = 0;       // optional stages (dfb_model_set_options)
     float pf_beta = 0.02f;
     size_t max_workspace = size_t(24) << 30;  // dfb_enhance groups streams so that the arena stays below this
@@ -822,7 +822,7 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
     m->device = device;
     m->cfg = *cfg;
     if (erb_widths) m->erb_widths.assign(erb_widths, erb_widths + cfg->nb_erb);
-    if (const char *e = getenv("DFB_DEVICE_CHUNKS")) m->dev_chunks = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("DFB_DEVICE_CHUNKS")) m->dev_chunks = atoi(e) > 0 ? atoi(e) : 0;
     if (const char *e = getenv("DFB_HOST_CHUNKS")) m->host_chunks = atoi(e) > 0 ? atoi(e) : 1;
     if (const char *e = getenv("DFB_LANES")) m->n_lanes = atoi(e) == 1 ? 1 : 2;
     if (const char *e = getenv("DFB_MAX_WORKSPACE_MB")) {
@@ -1492,10 +1492,10 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
 
 // Chunk pipeline of dfb_enhance / dfb_enhance_host: signals of at least 64 * chunks frames are cut into >= `chunks` time
 // chunks (device-pointer / host-pointer entry point); lanes = 2 overlaps the encoder phase of chunk c + 1 with the decoder
-// phase of chunk c, lanes = 1 runs the chunks back to back.  Defaults 6 / 6 / 2 (DFB_DEVICE_CHUNKS, DFB_HOST_CHUNKS,
-// DFB_LANES at dfb_model_create).
+// phase of chunk c, lanes = 1 runs the chunks back to back.  Defaults auto / 4 / 2 (DFB_DEVICE_CHUNKS, DFB_HOST_CHUNKS,
+// DFB_LANES at dfb_model_create); device_chunks = 0 (auto) is 1 chunk for more than 8 streams, else 3.
 extern "C" int dfb_model_set_chunking(dfb_model *m, int device_chunks, int host_chunks, int lanes) {
-    if (!m || device_chunks < 1 || host_chunks < 1 || lanes < 1 || lanes > 2) return fail(DFB_ERR_INVALID, "bad chunking parameters");
+    if (!m || device_chunks < 0 || host_chunks < 1 || lanes < 1 || lanes > 2) return fail(DFB_ERR_INVALID, "bad chunking parameters");
     m->dev_chunks = device_chunks; m->host_chunks = host_chunks; m->n_lanes = lanes;
     return DFB_OK;
 }
@@ -1890,7 +1890,12 @@ extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, in
     int64_t group = 0;
     int tc = 0, rc;
     bool pipelined = false;
-    if ((rc = enhance_plan(m, st, B, Tf, m->dev_chunks, &group, &tc, &pipelined))) return rc;
+    // measured (profiles/r02_chunk_sweep.txt, 128 x 10 s): cutting a device-resident batch into pipelined chunks costs more
+    // (persistent kernels re-pay their prologues, short grids leave partial waves: 13.6 -> 14.1 ms for 4 chunks) than the
+    // overlap of encoder and decoder phases gains -- except for a few streams, where everything is latency bound
+    // (batch 1: RTF 0.00046 -> 0.00040 with 3 chunks).  0 = that policy.
+    const int dev_chunks = m->dev_chunks > 0 ? m->dev_chunks : (B <= 8 ? 3 : 1);
+    if ((rc = enhance_plan(m, st, B, Tf, dev_chunks, &group, &tc, &pipelined))) return rc;
     const float lim = (atten_lim_db > 0.f) ? powf(10.f, -atten_lim_db / 20.f) : 0.f;
     size_t off[16];
     if ((rc = m->aux_arena.reserve((state_floats(m->cfg, st, (int)group, off) + (pad ? (size_t)group * Tp : 0)) * sizeof(float) + 8192))) return rc;

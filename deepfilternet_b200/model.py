@@ -153,7 +153,7 @@ class DfNet(nn.Module):
         """Cap of the per-call device workspace of enhance(): larger batches are processed in stream groups."""
         check(_lib.lib().dfb_model_set_max_workspace(self._h, int(nbytes)))
 
-    def set_chunking(self, device_chunks: int = 6, host_chunks: int = 6, lanes: int = 2) -> None:
+    def set_chunking(self, device_chunks: int = 0, host_chunks: int = 4, lanes: int = 2) -> None:
         """Chunk pipeline of enhance(): minimum number of time chunks for long signals (device / host entry point) and
         whether consecutive chunks overlap on two lanes (2) or run back to back (1)."""
         check(_lib.lib().dfb_model_set_chunking(self._h, int(device_chunks), int(host_chunks), int(lanes)))
