@@ -86,6 +86,7 @@ def kernel_model(cfg, g: dict) -> dict:
         "k_conv_in[df_conv0]": ("hbm", Fd * 8 + Fd * 256, "bytes"),
         "k_conv_in[erb_conv0]": ("hbm", 4 * E + E * 256, "bytes"),
         "k_df_convp": ("hbm", Fd * 256 + Fd * 4 * O2, "bytes"),
+        "k_df_convp_tc": ("hbm", Fd * 256 + Fd * 4 * O2, "bytes"),
         "k_mask_out": ("hbm", 2 * E * 256 + 4 * E, "bytes"),
     }
 

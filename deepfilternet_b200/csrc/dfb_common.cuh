@@ -186,6 +186,9 @@ int launch_gl_bx(cudaStream_t s, const unsigned short *x_hi, const unsigned shor
                  const float *res, int64_t ldr, float *y, int64_t ldy, unsigned short *y_hi, unsigned short *y_lo, int64_t ldp,
                  int64_t M, int G, int Ig, int Hg, int act, float oscale, float ooffset);
 bool gl_bx_geometry(int G, int Ig, int Hg, int *gpc_out, int *hgp_out, int *stages_out);
+// DF pathway conv (df_convp) on tensor cores (dfb_tc.cu)
+int launch_df_convp_tc(cudaStream_t s, const float *c0, const float *w_sw, const float *w2, const float *bias, float *coefs, int B, int T,
+                       int Fd);
 // fp32 [M][K] -> BF16 hi / lo planes [M][K]
 int launch_to_planes(cudaStream_t s, const float *x, int64_t ldx, int64_t M, int K, unsigned short *hi, unsigned short *lo);
 }  // namespace dfb

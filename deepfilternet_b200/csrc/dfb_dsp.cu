@@ -289,10 +289,12 @@ __global__ void __launch_bounds__(256) k_resample(const float *__restrict__ x, i
 // sequential in t per (stream, band | bin) exactly like the reference loops.
 // grid B, block E + Fd threads (thread j < E: band j; else bin j - E).  Loads are batched kPf
 // frames ahead so the dependent chain is arithmetic only.
-constexpr int kPf = 24;   // frames of loads in flight per thread (8: 0.34 ms per 128 x 1002 frames, latency bound at 0.10 of HBM)
+// kPf = frames of loads in flight per thread: 24 for the enhancement path's shape (E + Fd = 128 threads per stream; with 8
+// the kernel was latency bound at 0.10 of HBM), 4 for the generic libdf.erb_norm / unit_norm shapes (up to 1024 threads)
 // Ts = frames per stream in the four buffers (the pointers are pre-offset to the first frame to process, Tf = number of
 // frames processed); *_state_out (may alias the inputs) receive the EMA states after the last frame.
-__global__ void k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
+template <int kPf>
+__global__ void __launch_bounds__(kPf > 8 ? 128 : 1024) k_feat_norm(const float *erb_in, int E, int64_t erb_stride_t,
                             const float2 *__restrict__ spec_in, int Fd, int64_t spec_stride_t, int Tf,
                             float alpha, const float *erb_state, const float *unit_state,
                             float *feat_erb, float2 *__restrict__ feat_spec, int Ts, float *erb_state_out,
@@ -890,9 +892,14 @@ int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float 
     if (E + Fd > 1024) return fail(DFB_ERR_INVALID, "E + F > 1024 in norm scan");
     int threads = ((E + Fd + 31) / 32) * 32;
     DFB_PROF("k_feat_norm", s);
-    k_feat_norm<<<(unsigned)C, threads, 0, s>>>(d_erb, E, erb_stride, (const float2 *)d_spec, Fd, spec_stride, (int)Tf,
-                                               alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec,
-                                               (int)(Ts > 0 ? Ts : Tf), d_erb_state_out, d_unit_state_out);
+    if (threads <= 128)
+        k_feat_norm<24><<<(unsigned)C, threads, 0, s>>>(d_erb, E, erb_stride, (const float2 *)d_spec, Fd, spec_stride, (int)Tf,
+                                                       alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec,
+                                                       (int)(Ts > 0 ? Ts : Tf), d_erb_state_out, d_unit_state_out);
+    else
+        k_feat_norm<4><<<(unsigned)C, threads, 0, s>>>(d_erb, E, erb_stride, (const float2 *)d_spec, Fd, spec_stride, (int)Tf,
+                                                      alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec,
+                                                      (int)(Ts > 0 ? Ts : Tf), d_erb_state_out, d_unit_state_out);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
 }

@@ -255,6 +255,38 @@ int cached_map_bf16(CUtensorMap *out, const void *base, int64_t rows, int64_t co
     return DFB_OK;
 }
 
+// 2-D fp32 row-major [rows][cols] (row pitch ld floats), box = [box_rows][32 floats = 128 B], 128-byte swizzle
+int cached_map_f32_sw128(CUtensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void *, int64_t, int64_t, int64_t, int>, CUtensorMap> cache;
+    static PFN_encodeTiled_gl enc = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    auto key = std::make_tuple(dev, base, rows, cols, ld, box_rows);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return DFB_OK; }
+    if (!enc) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        enc = (PFN_encodeTiled_gl)fp;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (%d)", (int)r);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+    *out = m;
+    return DFB_OK;
+}
+
 int launch_to_planes(cudaStream_t s, const float *x, int64_t ldx, int64_t M, int K, unsigned short *hi, unsigned short *lo) {
     if (K % 4 || ldx % 4) return fail(DFB_ERR_UNSUPPORTED, "to_planes: K = %d", K);
     int dev = 0, sms = 0;

@@ -1322,7 +1322,11 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
                         c.df_pathway_kt);
         if (Fd % 2) return fail(DFB_ERR_UNSUPPORTED, "df pathway conv: odd nb_df");
         dim3 grid((unsigned)((Fd + 2 * kCpWarps - 1) / (2 * kCpWarps)), (unsigned)((T + kCpChunk - 1) / kCpChunk), (unsigned)B);
-        {
+        static const bool convp_ffma = getenv("DFB_CONVP_FFMA") && atoi(getenv("DFB_CONVP_FFMA"));
+        const float *w_sw = (m->conv_tc && !convp_ffma) ? m->get("df_dec.df_convp.w_sw") : nullptr;
+        if (w_sw) {  // channel contraction on tcgen05 (BF16x3), shifted adds + 1x1 conv in the epilogue
+            if ((rc = launch_df_convp_tc(sl, f.c0, w_sw, w2, bb, d_coefs, B, T, Fd))) return rc;
+        } else {
             DFB_PROF("k_df_convp", sl);
             const int smem = kCpWarps * kCpSlots * (512 + 8);
             k_df_convp<5, 5, 3><<<grid, 32 * kCpWarps, smem, sl>>>(f.c0, w1, w2, bb, d_coefs, T, Fd);

@@ -480,6 +480,144 @@ template int launch_dwpw_tc<DW_S1>(cudaStream_t, DwPwParams, const float *, int)
 template int launch_dwpw_tc<DW_S2>(cudaStream_t, DwPwParams, const float *, int);
 template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int);
 
+// ---------------------------------------------------------- DF pathway conv on tensor cores ----
+// coefs[b,t,f,:] = relu( pw( conv_t(c0) ) + b )  (df_convp, deepfilternet3.py:293-295: grouped (2) temporal conv 64 -> 10
+// with kernel (5,1), 1x1 conv 10 x 10, BN, ReLU).  The FFMA kernel (k_df_convp, dfb_model.cu) is instruction-issue bound
+// (~250 warp instructions per frame and bin pair: 1.4 ms of issue slots per 128 x 10 s, measured 2.2 ms = 0.25 of the HBM
+// roofline, and a deeper load ring did not change it).  Here the channel contraction runs on tcgen05:
+//   Y[t, g*32 + dt*5 + o] = sum_{c in group g} w1[dt][g*5+o][c] * c0[t, f, c]        (one [128 t x 64 c] x [64 c x 64] product)
+//   z[t, g*5 + o]         = sum_dt Y[t - 4 + dt, g*32 + dt*5 + o]                     (shifted adds out of shared memory)
+//   coefs[t, f, :]        = relu(z . w2 + b)
+// One CTA = (stream, bin f, 124 output frames): its 128 time rows of c0[., f, :] (4 frames of history) arrive as two TMA
+// tensor boxes (rows 24.5 KB apart in HBM, 2 x 128 B per row, 128-byte swizzle), are split into BF16 hi / lo operand planes
+// (BF16x3: fp32-level accuracy), 12 tcgen05.mma (M128 N64 K16) leave Y in 64 TMEM columns, the epilogue stages Y in shared
+// memory (row stride 65 floats) and 128 threads (one per time row) do the shifted sums, the 1x1 conv and the 40-byte store.
+constexpr int kCvThreads = 256, kCvOut = 124, kCvYld = 65;
+// shared memory: [0, 32K) A hi | lo planes, [32K, 48K) W hi | lo, [48K, +33280) raw fp32 boxes, later the staged Y tile
+constexpr uint32_t kCvW = 32768, kCvRawOff = 49152, kCvYs = kCvRawOff, kCvTail = kCvYs + 128 * kCvYld * 4;
+
+struct CvParams {
+    const float *w_sw;   // [hi | lo] x [64 n][64 k] BF16, 128B-swizzled rows: n = g*32 + dt*5 + o, k = channel
+    const float *w2;     // [10 in][10 out]
+    const float *bias;   // [10]
+    float *coefs;        // [B,T,Fd,10]
+    int T, Fd;
+};
+
+template <int ORDER, int KTP>
+__global__ void __launch_bounds__(kCvThreads, 2) k_df_convp_tc(const __grid_constant__ CUtensorMap tmC0, CvParams p) {
+    constexpr int O2 = 2 * ORDER;
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    const uint32_t sb = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int f = blockIdx.x, b = blockIdx.z, t0 = blockIdx.y * kCvOut, r0 = t0 - (KTP - 1);
+    const uint32_t s_w2 = sb + kCvTail, bar_raw = s_w2 + 512, bar_mma = bar_raw + 8, s_tmem = bar_mma + 8;
+    if (tid == 0) {
+        mbar_init_a(bar_raw, 1);
+        mbar_init_a(bar_mma, 1);
+        fence_barrier_init();
+        mbar_expect_tx_a(bar_raw, 32768 + 16384);
+        const int row = b * p.T + r0;   // may be negative for the first stream: out-of-bounds rows arrive as zeros
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(sb + kCvRawOff), "l"((uint64_t)&tmC0), "r"(f * 64), "r"(row), "r"(bar_raw) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(sb + kCvRawOff + 16384), "l"((uint64_t)&tmC0), "r"(f * 64 + 32), "r"(row), "r"(bar_raw) : "memory");
+        bulk_load(sb + kCvW, p.w_sw, 16384, bar_raw);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < O2 * O2 + O2; i += kCvThreads)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_w2 + 4 * i), "f"(i < O2 * O2 ? __ldg(p.w2 + i) : __ldg(p.bias + i - O2 * O2)) : "memory");
+    __syncthreads();
+    mbar_wait_a(bar_raw, 0);
+    {   // fp32 rows -> BF16 hi / lo operand planes: thread = (time row, channel half)
+        const int r = tid & 127, half = tid >> 7;
+        const bool zero = r0 + r < 0;   // before the start of the stream (for b > 0 the box holds the previous stream's rows)
+        const uint32_t src = sb + kCvRawOff + (uint32_t)half * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float4 x = lds128(src + (uint32_t)((c ^ (r & 7)) << 4));
+            if (zero) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t h0, l0, h1, l1;
+            bf16x2_split(x.x, x.y, h0, l0);
+            bf16x2_split(x.z, x.w, h1, l1);
+            const int cq = half * 8 + c;
+            const uint32_t off = sb + sw128_off(r, cq >> 1) + (cq & 1) * 8;
+            sts64(off, h0, h1);
+            sts64(off + 16384, l0, l1);
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = lds32(s_tmem);
+    if (warp == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint64_t ah = umma_desc_sw128(sb), al = umma_desc_sw128(sb + 16384);
+        const uint64_t bh = umma_desc_sw128(sb + kCvW), bl = umma_desc_sw128(sb + kCvW + 8192);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            umma_bf16_ss_elect(tmem_u, ah + 2 * k, bh + 2 * k, idesc, k != 0);
+            umma_bf16_ss_elect(tmem_u, al + 2 * k, bh + 2 * k, idesc, 1u);
+            umma_bf16_ss_elect(tmem_u, ah + 2 * k, bl + 2 * k, idesc, 1u);
+        }
+        asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                     "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar_mma) : "memory");
+    }
+    mbar_wait_a(bar_mma, 0);
+    tc_fence_after();
+    {   // Y -> shared memory: warp w holds TMEM lanes [32 (w % 4), +32) = time rows, columns [32 (w / 4), +32) = group w / 4
+        const int q = warp & 3, g = warp >> 2;
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 32, v);
+        const uint32_t dst = sb + kCvYs + (uint32_t)((q * 32 + lane) * kCvYld + g * 32) * 4u;
+#pragma unroll
+        for (int j = 0; j < KTP * ORDER; j++) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 4 * j), "f"(v[j]) : "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 64);
+    if (tid < 128) {
+        const int r = tid, t = r0 + r;
+        if (r >= KTP - 1 && r < KTP - 1 + kCvOut && t < p.T) {
+            float z[O2];
+#pragma unroll
+            for (int g = 0; g < 2; g++)
+#pragma unroll
+                for (int o = 0; o < ORDER; o++) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int dt = 0; dt < KTP; dt++) {
+                        float y;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(sb + kCvYs + (uint32_t)((r - (KTP - 1) + dt) * kCvYld + g * 32 + dt * ORDER + o) * 4u));
+                        a += y;
+                    }
+                    z[g * ORDER + o] = a;
+                }
+            float outv[O2];
+#pragma unroll
+            for (int qo = 0; qo < O2; qo++) {
+                float a;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(s_w2 + 4 * (O2 * O2 + qo)));
+#pragma unroll
+                for (int k = 0; k < O2; k++) {
+                    float w;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(s_w2 + 4 * (k * O2 + qo)));
+                    a = fmaf(z[k], w, a);
+                }
+                outv[qo] = fmaxf(a, 0.f);
+            }
+            float *dst = p.coefs + (((int64_t)b * p.T + t) * p.Fd + f) * O2;   // 40-byte rows: 8-byte aligned
+#pragma unroll
+            for (int qo = 0; qo < O2; qo += 2) *reinterpret_cast<float2 *>(dst + qo) = make_float2(outv[qo], outv[qo + 1]);
+        }
+    }
+}
+
 // ================================================================ tensor-core GRU recurrence ====
 // torch.nn.GRU cell (DeepFilterNet/df/modules.py:684,723), hidden size 256.  A cluster of 8 CTAs owns
 // up to 16 streams for the whole sequence.  CTA `rank` keeps the W_hh rows of its 32 hidden units
@@ -811,6 +949,27 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
     static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
     const bool use32 = force ? force == 32 : (wide && B > 64);
     return use32 ? launch_gru_tc_n<32, 256>(s, p) : launch_gru_tc_n<16, 256>(s, p);
+}
+
+int cached_map_f32_sw128(CUtensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+// c0 [B,T,Fd,64] -> coefs [B,T,Fd,10] (pathway term), tensor-core version; w_sw: host-packed operand image (weights.py)
+int launch_df_convp_tc(cudaStream_t s, const float *c0, const float *w_sw, const float *w2, const float *bias, float *coefs, int B, int T,
+                       int Fd) {
+    if ((int64_t)B * T >= (int64_t(1) << 31) - 256 || B > 65535) return fail(DFB_ERR_UNSUPPORTED, "df pathway conv: batch too large for one launch");
+    CUtensorMap mc;
+    int rc;
+    if ((rc = cached_map_f32_sw128(&mc, c0, (int64_t)B * T, (int64_t)Fd * kCh, (int64_t)Fd * kCh, 128))) return rc;
+    const int smem = 1024 + (int)kCvTail + 512 + 64;
+    static PerDeviceOnce attr_once;
+    if (auto once_guard = attr_once.first())
+        DFB_CUDA(cudaFuncSetAttribute(k_df_convp_tc<5, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CvParams p{w_sw, w2, bias, coefs, T, Fd};
+    dim3 grid((unsigned)Fd, (unsigned)((T + kCvOut - 1) / kCvOut), (unsigned)B);
+    DFB_PROF("k_df_convp_tc", s);
+    k_df_convp_tc<5, 5><<<grid, kCvThreads, smem, s>>>(mc, p);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
 }
 
 // ------------------------------------------------------------------------------- host side ----

@@ -181,6 +181,15 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
     s, b = _bn_fold(sd, f"df_dec.df_convp.{bns[0]}")
     assert w1.shape[0] == 2 * cfg.df_order and w1.shape[1] == C // 2
     out["df_dec.df_convp.w1"] = f32(w1[:, :, :, 0].transpose(2, 0, 1))
+    # tensor-core form (k_df_convp_tc): W2[n = g*32 + dt*O + o][k = channel] = w1[g*O + o][k - 32 g][dt] inside group g, else 0
+    O, ktp = cfg.df_order, w1.shape[2]
+    if C == 64 and ktp * O <= 32:
+        w2x = np.zeros((64, 64), dtype=np.float32)
+        for g_ in range(2):
+            for dt in range(ktp):
+                for o in range(O):
+                    w2x[g_ * 32 + dt * O + o, g_ * 32:(g_ + 1) * 32] = w1[g_ * O + o, :, dt, 0]
+        out["df_dec.df_convp.w_sw"] = umma_sw128_image(w2x)
     out["df_dec.df_convp.w2"] = f32((w2 * s[:, None]).T)
     out["df_dec.df_convp.b"] = f32(b)
     pathway_kt = w1.shape[2]
