@@ -660,9 +660,12 @@ struct GtCfg {
     static constexpr int kPiece = 4 * kLbo;           // one CTA's slice
     static constexpr int kBuf = (HH / 8) * kLbo;      // one buffer (16 KB / 32 KB at 256; 32 KB at 512 x 16)
     static constexpr int kWCols = HH / 2;             // TMEM columns of one W plane: 2 bf16 per 32-bit column
-    static constexpr bool kLoSmem = HH > 256;         // W_lo does not fit next to W_hi and the accumulator
-    static constexpr int kDCol = 256;                 // accumulator columns: after W_hi | W_lo (256) or after W_hi (512)
-    static constexpr int kWloBytes = kLoSmem ? (HH / 8) * 16 * 128 : 16;   // [k core matrix][16 row groups][8 x 16 B]
+    // W_hh lo plane: K elements [0, kLoTmemK) live in tensor memory behind the hi plane, the rest (H = 512: the upper half;
+    // 512 columns cannot hold hi + lo + accumulator) in shared memory as a second A operand (SS form)
+    static constexpr int kLoTmemK = HH > 256 ? 256 : HH;
+    static constexpr bool kLoSmem = kLoTmemK < HH;
+    static constexpr int kDCol = kWCols + kLoTmemK / 2;   // accumulator columns behind W_hi | W_lo[0, kLoTmemK): 256 / 384
+    static constexpr int kWloBytes = kLoSmem ? ((HH - kLoTmemK) / 8) * 16 * 128 : 16;   // [k core matrix][16 row groups][8 x 16 B]
     static constexpr int kWloLbo = 16 * 128;          // stride between K-adjacent core matrices of the smem W_lo operand
 };
 
@@ -673,7 +676,7 @@ struct GruTcSmem {
     float pre[3][kGtU][NS + 1];
     alignas(8) uint64_t bar_h[2];
     uint64_t t_full;
-    uint32_t tmem_base;
+    uint32_t tmem_base, tmem_acc;
 };
 
 struct GruTcParams {
@@ -694,8 +697,14 @@ struct GruTcParams {
 };
 
 
-template <int NS, int HH>
-__global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcParams p) {
+// SHARE (H = 256 only): the CTA takes 256 + 32 tensor-memory columns in two allocations instead of all 512 and is compiled
+// for two CTAs' worth of registers per SM, so that feed-forward kernels with modest shared-memory needs (k_dwpw_bx,
+// k_df_convp_tc, k_apply_synthesis, k_conv_in ...) can run on the SMs a recurrence occupies but hardly uses (sm % 3 in ncu).
+// Two recurrence CTAs never share an SM (the launch still requests more than half of the shared memory): both would need
+// tensor memory the other holds, and with clusters that is a hold-and-wait cycle.
+template <int NS, int HH, int SHARE>
+__global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, (SHARE && NS == 16) ? 2 : 1) k_gru_tc(GruTcParams p) {
+    static_assert(!SHARE || HH == 256, "the shared variant needs W_hh hi | lo in 256 columns");
     using Cfg = GtCfg<NS, HH>;
     constexpr int kGtThreads = Cfg::kThreads;
     constexpr int kGtH = HH, kGtC = Cfg::kC, kGtWCols = Cfg::kWCols, kGtDCol = Cfg::kDCol;
@@ -715,12 +724,21 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
         mbar_init(&sm.t_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
+    if (warp == 0) {
+        if (SHARE) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(256) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_acc)), "r"(32) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            tmem_alloc(&sm.tmem_base, 512);
+        }
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    const uint32_t tmem_d = SHARE ? sm.tmem_acc : tmem + kGtDCol;   // accumulator [128 lanes][NS columns]
     if (p.h0) {  // carried state: every CTA builds the whole operand h_{-1} of its streams in buffer 0
         for (int i = tid; i < nb * (kGtH / 2); i += kGtThreads) {
             const int s = i / (kGtH / 2), gu = (i - s * (kGtH / 2)) * 2;
@@ -753,14 +771,14 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
             }
             const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + cb * 32;
             tmem_st32(ta, vh);
-            if (!Cfg::kLoSmem) {
+            if (cb * 64 < Cfg::kLoTmemK) {
                 tmem_st32(ta + kGtWCols, vl);
             } else {
-                // row rho, elements [64 cb, +64) = 8 core-matrix rows of 16 bytes: core matrix k / 8, row group rho / 8
+                // row rho, elements [64 cb, +64) = 8 core-matrix rows of 16 bytes: core matrix (k - kLoTmemK) / 8, row group rho / 8
                 const uint32_t base = smem_u32(sm.wlo) + (uint32_t)(rho >> 3) * 128u + (uint32_t)(rho & 7) * 16u;
 #pragma unroll
                 for (int j = 0; j < 8; j++)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(cb * 8 + j) * Cfg::kWloLbo),
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(cb * 8 + j - Cfg::kLoTmemK / 8) * Cfg::kWloLbo),
                                  "r"(vl[4 * j]), "r"(vl[4 * j + 1]), "r"(vl[4 * j + 2]), "r"(vl[4 * j + 3]) : "memory");
             }
         }
@@ -776,7 +794,7 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
     if (warp == Cfg::kMmaWarp) {
         // ================================================================= MMA issuer (whole warp, elected lane issues)
         constexpr uint32_t idesc = umma_idesc_bf16(128, NS);
-        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0), tmem_du = __shfl_sync(0xffffffffu, tmem_d, 0);
         const uint64_t bd0 = umma_desc_interleave(smem_u32(sm.h[0]), Cfg::kLbo, Cfg::kSbo);
         const uint64_t bd1 = umma_desc_interleave(smem_u32(sm.h[1]), Cfg::kLbo, Cfg::kSbo);
         const uint64_t wlo_desc = umma_desc_interleave(smem_u32(sm.wlo), Cfg::kWloLbo, 128);
@@ -797,10 +815,10 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
 #pragma unroll
                 for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
                     const uint64_t bdesc = bb + (uint64_t)((ks * 2 * Cfg::kLbo + hb * Cfg::kPlane) >> 4);
-                    if (Cfg::kLoSmem && wa) {   // W_lo from shared memory (SS form): two core matrices per K step
-                        umma_bf16_ss_elect(tmem_u + kGtDCol, wlo_desc + (uint64_t)((ks * 2 * Cfg::kWloLbo) >> 4), bdesc, idesc, 1u);
+                    if (wa && ks * 16 >= Cfg::kLoTmemK) {   // upper part of W_lo from shared memory (SS form): two core matrices per K step
+                        umma_bf16_ss_elect(tmem_du, wlo_desc + (uint64_t)(((ks - Cfg::kLoTmemK / 16) * 2 * Cfg::kWloLbo) >> 4), bdesc, idesc, 1u);
                     } else {
-                        umma_bf16_ts_elect(tmem_u + kGtDCol, tmem_u + wa * kGtWCols + ks * 8, bdesc, idesc,
+                        umma_bf16_ts_elect(tmem_du, tmem_u + wa * kGtWCols + ks * 8, bdesc, idesc,
                                            (combo == 0 && ks == 0) ? 0u : 1u);
                     }
                 }
@@ -845,7 +863,7 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
             if (loader) {  // TMEM lanes 32 g + u hold gate g of unit u; columns = streams
                 const int g = warp & 3, q = warp >> 2;
                 float v[16];
-                tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + kGtDCol + 16 * q, v);
+                tmem_ld16(tmem_d + ((uint32_t)(g * 32) << 16) + 16 * q, v);
 #pragma unroll
                 for (int ss = 0; ss < 16; ss++) sm.pre[g][lane][16 * q + ss] = v[ss];
             }
@@ -905,10 +923,13 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
     tc_fence_before();
     __syncthreads();
     cluster.sync();  // no CTA exits while peers may still address its shared memory
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) {
+        if (SHARE) { tmem_dealloc(tmem, 256); tmem_dealloc(tmem_d, 32); }
+        else tmem_dealloc(tmem, 512);
+    }
 }
 
-template <int NS, int HH>
+template <int NS, int HH, int SHARE = 0>
 static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     using Cfg = GtCfg<NS, HH>;
     static PerDeviceOnce attr_once;
@@ -917,8 +938,8 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     const int need = (int)sizeof(GruTcSmem<NS, HH>) + 1024;
     const int smem = need > 120 * 1024 ? need : 120 * 1024;
     if (auto once_guard = attr_once.first()) {
-        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH, SHARE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(Cfg::kThreads);
@@ -932,22 +953,27 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     cfg.gridDim = dim3((unsigned)(ngroups * Cfg::kC));
     cfg.stream = s;
     DFB_PROF(HH == 256 ? "k_gru_tc" : "k_gru_tc512", s);
-    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH>, p));
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH, SHARE>, p));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return DFB_OK;
 }
 
 // wide != 0: 32 streams per cluster when the batch needs more than 4 clusters of 16 (see GtCfg).  H = 512: clusters of
-// 16 CTAs with 16 streams (the h operand of 32 streams would not fit next to the W_lo plane in shared memory).
+// 16 CTAs with 16 or 32 streams.
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
                   unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg, int wide, int planes_res,
                   const GruWindow *w, int H) {
     GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, planes_res, w ? w->h0 : nullptr, w ? w->hT : nullptr,
                   w ? w->t0 : 0, w ? w->Ts : T, B, T, 0, dbg};
-    if (H == 512) return launch_gru_tc_n<16, 512>(s, p);
-    if (H != 256) return fail(DFB_ERR_UNSUPPORTED, "tensor-core recurrence: hidden size %d", H);
     static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
+    // H = 512: at most 8 clusters of 16 CTAs are co-resident (one per GPC): beyond 128 streams 32 per cluster keep a
+    // launch in one wave
+    if (H == 512) return (force ? force == 32 : B > 128) ? launch_gru_tc_n<32, 512>(s, p) : launch_gru_tc_n<16, 512>(s, p);
+    if (H != 256) return fail(DFB_ERR_UNSUPPORTED, "tensor-core recurrence: hidden size %d", H);
     const bool use32 = force ? force == 32 : (wide && B > 64);
+    // DFB_GRU_SHARE=1: recurrence CTAs leave tensor memory, registers and shared memory for feed-forward CTAs (see k_gru_tc)
+    static const bool share = getenv("DFB_GRU_SHARE") && atoi(getenv("DFB_GRU_SHARE"));
+    if (share) return use32 ? launch_gru_tc_n<32, 256, 1>(s, p) : launch_gru_tc_n<16, 256, 1>(s, p);
     return use32 ? launch_gru_tc_n<32, 256>(s, p) : launch_gru_tc_n<16, 256>(s, p);
 }
 

@@ -1,5 +1,8 @@
 """Condense an `ncu --page raw --csv` export into a per-kernel table (markdown).
-usage: python profiles/summarize_ncu.py gpurun_out/prof_raw.csv > profiles/rNN_ncu_summary.md"""
+usage: python profiles/summarize_ncu.py gpurun_out/prof_raw.csv [--traffic-json out.json --key MODEL:BxS --source TEXT]
+       > profiles/rNN_ncu_summary.md
+--traffic-json additionally writes {key: {bench kernel name: mean DRAM bytes per launch}} (dram__bytes_read.sum +
+dram__bytes_write.sum), which bench.py reports as `roofline.traffic`."""
 import csv
 import sys
 
@@ -47,5 +50,52 @@ def main(path):
         print(f"| {name} | " + " | ".join(vals) + " | " + ", ".join(f"{n} {v:.2f}" for v, n in st[:3]) + " |")
 
 
+def bench_name(kernel: str, grid: str) -> str:
+    """ncu kernel name -> the name the library's event profiler / bench.py uses."""
+    k = kernel.split("<")[0]
+    if k == "k_conv_in":
+        return "k_conv_in[df_conv0]" if "<2>" in kernel else "k_conv_in[erb_conv0]"
+    if k == "k_gemm_bf16x3":
+        return "k_gemm_bf16x3[gru_proj]"
+    if k == "k_gru_tc":
+        return "k_gru_tc512" if "512" in kernel else "k_gru_tc"
+    return k
+
+
+def traffic(path, out_json, key, source):
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr, data = rows[0], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    acc = {}
+    for r in data:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("dfb::", "")
+        try:
+            b = float(r[idx["dram__bytes_read.sum"]]) + float(r[idx["dram__bytes_write.sum"]])
+        except (ValueError, KeyError):
+            continue
+        unit_r = rows[1][idx["dram__bytes_read.sum"]].lower()
+        scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit_r, 1.0)
+        n = bench_name(name, "")
+        s_, c_ = acc.get(n, (0.0, 0))
+        acc[n] = (s_ + b * scale, c_ + 1)
+    try:
+        d = json.load(open(out_json))
+    except Exception:
+        d = {}
+    d[key] = {k: v[0] / v[1] for k, v in acc.items()}
+    d["_source"] = source
+    json.dump(d, open(out_json, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("raw")
+    ap.add_argument("--traffic-json")
+    ap.add_argument("--key", default="DeepFilterNet3:128x10")
+    ap.add_argument("--source", default="ncu --set full --clock-control none, one forward")
+    a = ap.parse_args()
+    main(a.raw)
+    if a.traffic_json:
+        traffic(a.raw, a.traffic_json, a.key, a.source)
