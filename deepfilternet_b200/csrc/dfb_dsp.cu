@@ -145,7 +145,7 @@ __device__ __forceinline__ void warp_fft480_twptr(LoadF load, const float2 *tw_l
 // Frame window: the grid covers frames [t_begin, t_begin + nf) of every stream (time-chunked execution); their rows
 // go to out_t0 ... of spec / erb_db buffers that hold Tbuf frames per stream.  The whole-signal call is
 // (t_begin, nf, out_t0, Tbuf) = (0, Tf, 0, Tf).
-__global__ void __launch_bounds__(32 * kAnaWarps, 3)
+__global__ void __launch_bounds__(32 * kAnaWarps, 4)
 k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restrict__ spec,
            float *__restrict__ erb_db, DspTables tb, const float *__restrict__ init_mem, int t_begin, int nf, int out_t0,
            int Tbuf) {

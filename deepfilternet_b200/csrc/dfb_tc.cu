@@ -492,9 +492,10 @@ template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int)
 // tensor boxes (rows 24.5 KB apart in HBM, 2 x 128 B per row, 128-byte swizzle), are split into BF16 hi / lo operand planes
 // (BF16x3: fp32-level accuracy), 12 tcgen05.mma (M128 N64 K16) leave Y in 64 TMEM columns, the epilogue stages Y in shared
 // memory (row stride 65 floats) and 128 threads (one per time row) do the shifted sums, the 1x1 conv and the 40-byte store.
-constexpr int kCvThreads = 256, kCvOut = 124, kCvYld = 65;
-// shared memory: [0, 32K) A hi | lo planes, [32K, 48K) W hi | lo, [48K, +33280) raw fp32 boxes, later the staged Y tile
-constexpr uint32_t kCvW = 32768, kCvRawOff = 49152, kCvYs = kCvRawOff, kCvTail = kCvYs + 128 * kCvYld * 4;
+constexpr int kCvThreads = 256, kCvOut = 124, kCvYld = 51 /* 2 x 25 used columns + 1 */, kCvBins = 8;
+// shared memory: [0, 32K) A hi | lo planes, [32K, 48K) W hi | lo, [48K, 80K) raw fp32 boxes of the current bin,
+// [80K, +26112) the staged Y tile, then w2 | bias, barriers, the TMEM address
+constexpr uint32_t kCvW = 32768, kCvRawOff = 49152, kCvYs = kCvRawOff + 32768, kCvTail = kCvYs + 128 * kCvYld * 4;
 
 struct CvParams {
     const float *w_sw;   // [hi | lo] x [64 n][64 k] BF16, 128B-swizzled rows: n = g*32 + dt*5 + o, k = channel
@@ -504,25 +505,34 @@ struct CvParams {
     int T, Fd;
 };
 
+// One CTA = (stream, kCvBins consecutive bins, 124 output frames): the weight image, the TMEM allocation and the barrier
+// set-up are paid once per CTA, and the TMA load of the next bin's rows is issued as soon as the current bin's rows have
+// been converted, so it overlaps the MMA and the epilogue (the first version ran one bin per CTA: 0.39 of HBM).
 template <int ORDER, int KTP>
 __global__ void __launch_bounds__(kCvThreads, 2) k_df_convp_tc(const __grid_constant__ CUtensorMap tmC0, CvParams p) {
-    constexpr int O2 = 2 * ORDER;
+    constexpr int O2 = 2 * ORDER, NY = KTP * ORDER;
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     const uint32_t sb = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int f = blockIdx.x, b = blockIdx.z, t0 = blockIdx.y * kCvOut, r0 = t0 - (KTP - 1);
-    const uint32_t s_w2 = sb + kCvTail, bar_raw = s_w2 + 512, bar_mma = bar_raw + 8, s_tmem = bar_mma + 8;
-    if (tid == 0) {
-        mbar_init_a(bar_raw, 1);
-        mbar_init_a(bar_mma, 1);
-        fence_barrier_init();
-        mbar_expect_tx_a(bar_raw, 32768 + 16384);
-        const int row = b * p.T + r0;   // may be negative for the first stream: out-of-bounds rows arrive as zeros
+    const int f_begin = blockIdx.x * kCvBins, f_end = min(f_begin + kCvBins, p.Fd);
+    const int b = blockIdx.z, t0 = blockIdx.y * kCvOut, r0 = t0 - (KTP - 1);
+    const uint32_t s_w2 = sb + kCvTail, bar_raw = s_w2 + 512, bar_mma = bar_raw + 8, bar_w = bar_mma + 8, s_tmem = bar_w + 8;
+    const int row = b * p.T + r0;   // may be negative for the first stream: out-of-bounds rows arrive as zeros
+    auto load_bin = [&](int f) {    // thread 0 only
+        mbar_expect_tx_a(bar_raw, 32768);
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                      ::"r"(sb + kCvRawOff), "l"((uint64_t)&tmC0), "r"(f * 64), "r"(row), "r"(bar_raw) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                      ::"r"(sb + kCvRawOff + 16384), "l"((uint64_t)&tmC0), "r"(f * 64 + 32), "r"(row), "r"(bar_raw) : "memory");
-        bulk_load(sb + kCvW, p.w_sw, 16384, bar_raw);
+    };
+    if (tid == 0) {
+        mbar_init_a(bar_raw, 1);
+        mbar_init_a(bar_mma, 1);
+        mbar_init_a(bar_w, 1);
+        fence_barrier_init();
+        mbar_expect_tx_a(bar_w, 16384);
+        bulk_load(sb + kCvW, p.w_sw, 16384, bar_w);
+        load_bin(f_begin);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(64) : "memory");
@@ -530,92 +540,103 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_df_convp_tc(const __grid_cons
     }
     for (int i = tid; i < O2 * O2 + O2; i += kCvThreads)
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_w2 + 4 * i), "f"(i < O2 * O2 ? __ldg(p.w2 + i) : __ldg(p.bias + i - O2 * O2)) : "memory");
-    __syncthreads();
-    mbar_wait_a(bar_raw, 0);
-    {   // fp32 rows -> BF16 hi / lo operand planes: thread = (time row, channel half)
-        const int r = tid & 127, half = tid >> 7;
-        const bool zero = r0 + r < 0;   // before the start of the stream (for b > 0 the box holds the previous stream's rows)
-        const uint32_t src = sb + kCvRawOff + (uint32_t)half * 16384u + (uint32_t)r * 128u;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            float4 x = lds128(src + (uint32_t)((c ^ (r & 7)) << 4));
-            if (zero) x = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t h0, l0, h1, l1;
-            bf16x2_split(x.x, x.y, h0, l0);
-            bf16x2_split(x.z, x.w, h1, l1);
-            const int cq = half * 8 + c;
-            const uint32_t off = sb + sw128_off(r, cq >> 1) + (cq & 1) * 8;
-            sts64(off, h0, h1);
-            sts64(off + 16384, l0, l1);
-        }
-    }
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = lds32(s_tmem);
-    if (warp == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-        const uint64_t ah = umma_desc_sw128(sb), al = umma_desc_sw128(sb + 16384);
-        const uint64_t bh = umma_desc_sw128(sb + kCvW), bl = umma_desc_sw128(sb + kCvW + 8192);
+    mbar_wait_a(bar_w, 0);
+    const int r = tid & 127, half = tid >> 7;
+    const bool zero = r0 + r < 0;   // before the start of the stream (for b > 0 the box holds the previous stream's rows)
+    for (int f = f_begin, it = 0; f < f_end; f++, it++) {
+        const uint32_t par = (uint32_t)(it & 1);
+        mbar_wait_a(bar_raw, par);
+        {   // fp32 rows -> BF16 hi / lo operand planes: thread = (time row, channel half)
+            const uint32_t src = sb + kCvRawOff + (uint32_t)half * 16384u + (uint32_t)r * 128u;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            umma_bf16_ss_elect(tmem_u, ah + 2 * k, bh + 2 * k, idesc, k != 0);
-            umma_bf16_ss_elect(tmem_u, al + 2 * k, bh + 2 * k, idesc, 1u);
-            umma_bf16_ss_elect(tmem_u, ah + 2 * k, bl + 2 * k, idesc, 1u);
+            for (int c = 0; c < 8; c++) {
+                float4 x = lds128(src + (uint32_t)((c ^ (r & 7)) << 4));
+                if (zero) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t h0, l0, h1, l1;
+                bf16x2_split(x.x, x.y, h0, l0);
+                bf16x2_split(x.z, x.w, h1, l1);
+                const int cq = half * 8 + c;
+                const uint32_t off = sb + sw128_off(r, cq >> 1) + (cq & 1) * 8;
+                sts64(off, h0, h1);
+                sts64(off + 16384, l0, l1);
+            }
         }
-        asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                     "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar_mma) : "memory");
-    }
-    mbar_wait_a(bar_mma, 0);
-    tc_fence_after();
-    {   // Y -> shared memory: warp w holds TMEM lanes [32 (w % 4), +32) = time rows, columns [32 (w / 4), +32) = group w / 4
-        const int q = warp & 3, g = warp >> 2;
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 32, v);
-        const uint32_t dst = sb + kCvYs + (uint32_t)((q * 32 + lane) * kCvYld + g * 32) * 4u;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();     // planes complete (and the raw boxes free; the previous bin's epilogue has left the Y tile)
+        tc_fence_after();
+        if (tid == 0 && f + 1 < f_end) load_bin(f + 1);   // overlaps the MMA and the epilogue below
+        if (warp == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint64_t ah = umma_desc_sw128(sb), al = umma_desc_sw128(sb + 16384);
+            const uint64_t bh = umma_desc_sw128(sb + kCvW), bl = umma_desc_sw128(sb + kCvW + 8192);
 #pragma unroll
-        for (int j = 0; j < KTP * ORDER; j++) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 4 * j), "f"(v[j]) : "memory");
+            for (int k = 0; k < 4; k++) {
+                umma_bf16_ss_elect(tmem_u, ah + 2 * k, bh + 2 * k, idesc, k != 0);
+                umma_bf16_ss_elect(tmem_u, al + 2 * k, bh + 2 * k, idesc, 1u);
+                umma_bf16_ss_elect(tmem_u, ah + 2 * k, bl + 2 * k, idesc, 1u);
+            }
+            asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar_mma) : "memory");
+        }
+        mbar_wait_a(bar_mma, par);
+        tc_fence_after();
+        {   // Y -> shared memory: warp w holds TMEM lanes [32 (w % 4), +32) = time rows, columns [32 (w / 4), +32) = group w / 4
+            const int q = warp & 3, g = warp >> 2;
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 32, v);
+            const uint32_t dst = sb + kCvYs + (uint32_t)((q * 32 + lane) * kCvYld + g * NY) * 4u;
+#pragma unroll
+            for (int j = 0; j < NY; j++) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 4 * j), "f"(v[j]) : "memory");
+        }
+        tc_fence_before();
+        __syncthreads();     // Y staged; the accumulator may be overwritten by the next bin's MMAs
+        if (tid < 128) {
+            const int t = r0 + tid;
+            if (tid >= KTP - 1 && tid < KTP - 1 + kCvOut && t < p.T) {
+                float z[O2];
+#pragma unroll
+                for (int g = 0; g < 2; g++)
+#pragma unroll
+                    for (int o = 0; o < ORDER; o++) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int dt = 0; dt < KTP; dt++) {
+                            float y;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(sb + kCvYs + (uint32_t)((tid - (KTP - 1) + dt) * kCvYld + g * NY + dt * ORDER + o) * 4u));
+                            a += y;
+                        }
+                        z[g * ORDER + o] = a;
+                    }
+                float outv[O2];
+#pragma unroll
+                for (int qo = 0; qo < O2; qo++) {
+                    float a;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(s_w2 + 4 * (O2 * O2 + qo)));
+#pragma unroll
+                    for (int k = 0; k < O2; k++) {
+                        float w;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(s_w2 + 4 * (k * O2 + qo)));
+                        a = fmaf(z[k], w, a);
+                    }
+                    outv[qo] = fmaxf(a, 0.f);
+                }
+                float *dst = p.coefs + (((int64_t)b * p.T + t) * p.Fd + f) * O2;   // 40-byte rows: 8-byte aligned
+#pragma unroll
+                for (int qo = 0; qo < O2; qo += 2) *reinterpret_cast<float2 *>(dst + qo) = make_float2(outv[qo], outv[qo + 1]);
+            }
+        }
+        // the next iteration's conversion writes the operand planes (read by the MMAs that completed above) and its
+        // __syncthreads orders this bin's shifted sums before the next Y tile is staged
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 64);
-    if (tid < 128) {
-        const int r = tid, t = r0 + r;
-        if (r >= KTP - 1 && r < KTP - 1 + kCvOut && t < p.T) {
-            float z[O2];
-#pragma unroll
-            for (int g = 0; g < 2; g++)
-#pragma unroll
-                for (int o = 0; o < ORDER; o++) {
-                    float a = 0.f;
-#pragma unroll
-                    for (int dt = 0; dt < KTP; dt++) {
-                        float y;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(sb + kCvYs + (uint32_t)((r - (KTP - 1) + dt) * kCvYld + g * 32 + dt * ORDER + o) * 4u));
-                        a += y;
-                    }
-                    z[g * ORDER + o] = a;
-                }
-            float outv[O2];
-#pragma unroll
-            for (int qo = 0; qo < O2; qo++) {
-                float a;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(s_w2 + 4 * (O2 * O2 + qo)));
-#pragma unroll
-                for (int k = 0; k < O2; k++) {
-                    float w;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(s_w2 + 4 * (k * O2 + qo)));
-                    a = fmaf(z[k], w, a);
-                }
-                outv[qo] = fmaxf(a, 0.f);
-            }
-            float *dst = p.coefs + (((int64_t)b * p.T + t) * p.Fd + f) * O2;   // 40-byte rows: 8-byte aligned
-#pragma unroll
-            for (int qo = 0; qo < O2; qo += 2) *reinterpret_cast<float2 *>(dst + qo) = make_float2(outv[qo], outv[qo + 1]);
-        }
-    }
 }
 
 // ================================================================ tensor-core GRU recurrence ====
@@ -676,7 +697,7 @@ struct GruTcSmem {
     float pre[3][kGtU][NS + 1];
     alignas(8) uint64_t bar_h[2];
     uint64_t t_full;
-    uint32_t tmem_base, tmem_acc;
+    uint32_t tmem_base;
 };
 
 struct GruTcParams {
@@ -697,14 +718,8 @@ struct GruTcParams {
 };
 
 
-// SHARE (H = 256 only): the CTA takes 256 + 32 tensor-memory columns in two allocations instead of all 512 and is compiled
-// for two CTAs' worth of registers per SM, so that feed-forward kernels with modest shared-memory needs (k_dwpw_bx,
-// k_df_convp_tc, k_apply_synthesis, k_conv_in ...) can run on the SMs a recurrence occupies but hardly uses (sm % 3 in ncu).
-// Two recurrence CTAs never share an SM (the launch still requests more than half of the shared memory): both would need
-// tensor memory the other holds, and with clusters that is a hold-and-wait cycle.
-template <int NS, int HH, int SHARE>
-__global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, (SHARE && NS == 16) ? 2 : 1) k_gru_tc(GruTcParams p) {
-    static_assert(!SHARE || HH == 256, "the shared variant needs W_hh hi | lo in 256 columns");
+template <int NS, int HH>
+__global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcParams p) {
     using Cfg = GtCfg<NS, HH>;
     constexpr int kGtThreads = Cfg::kThreads;
     constexpr int kGtH = HH, kGtC = Cfg::kC, kGtWCols = Cfg::kWCols, kGtDCol = Cfg::kDCol;
@@ -724,21 +739,13 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, (SHARE && NS == 16) ?
         mbar_init(&sm.t_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) {
-        if (SHARE) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(256) : "memory");
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_acc)), "r"(32) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        } else {
-            tmem_alloc(&sm.tmem_base, 512);
-        }
-    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t tmem_d = SHARE ? sm.tmem_acc : tmem + kGtDCol;   // accumulator [128 lanes][NS columns]
+    const uint32_t tmem_d = tmem + kGtDCol;   // accumulator [128 lanes][NS columns]
     if (p.h0) {  // carried state: every CTA builds the whole operand h_{-1} of its streams in buffer 0
         for (int i = tid; i < nb * (kGtH / 2); i += kGtThreads) {
             const int s = i / (kGtH / 2), gu = (i - s * (kGtH / 2)) * 2;
@@ -923,13 +930,10 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, (SHARE && NS == 16) ?
     tc_fence_before();
     __syncthreads();
     cluster.sync();  // no CTA exits while peers may still address its shared memory
-    if (warp == 0) {
-        if (SHARE) { tmem_dealloc(tmem, 256); tmem_dealloc(tmem_d, 32); }
-        else tmem_dealloc(tmem, 512);
-    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int NS, int HH, int SHARE = 0>
+template <int NS, int HH>
 static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     using Cfg = GtCfg<NS, HH>;
     static PerDeviceOnce attr_once;
@@ -938,8 +942,8 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     const int need = (int)sizeof(GruTcSmem<NS, HH>) + 1024;
     const int smem = need > 120 * 1024 ? need : 120 * 1024;
     if (auto once_guard = attr_once.first()) {
-        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH, SHARE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(Cfg::kThreads);
@@ -953,7 +957,7 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     cfg.gridDim = dim3((unsigned)(ngroups * Cfg::kC));
     cfg.stream = s;
     DFB_PROF(HH == 256 ? "k_gru_tc" : "k_gru_tc512", s);
-    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH, SHARE>, p));
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH>, p));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return DFB_OK;
 }
@@ -971,9 +975,6 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
     if (H == 512) return (force ? force == 32 : B > 128) ? launch_gru_tc_n<32, 512>(s, p) : launch_gru_tc_n<16, 512>(s, p);
     if (H != 256) return fail(DFB_ERR_UNSUPPORTED, "tensor-core recurrence: hidden size %d", H);
     const bool use32 = force ? force == 32 : (wide && B > 64);
-    // DFB_GRU_SHARE=1: recurrence CTAs leave tensor memory, registers and shared memory for feed-forward CTAs (see k_gru_tc)
-    static const bool share = getenv("DFB_GRU_SHARE") && atoi(getenv("DFB_GRU_SHARE"));
-    if (share) return use32 ? launch_gru_tc_n<32, 256, 1>(s, p) : launch_gru_tc_n<16, 256, 1>(s, p);
     return use32 ? launch_gru_tc_n<32, 256>(s, p) : launch_gru_tc_n<16, 256>(s, p);
 }
 
@@ -991,7 +992,7 @@ int launch_df_convp_tc(cudaStream_t s, const float *c0, const float *w_sw, const
     if (auto once_guard = attr_once.first())
         DFB_CUDA(cudaFuncSetAttribute(k_df_convp_tc<5, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CvParams p{w_sw, w2, bias, coefs, T, Fd};
-    dim3 grid((unsigned)Fd, (unsigned)((T + kCvOut - 1) / kCvOut), (unsigned)B);
+    dim3 grid((unsigned)((Fd + kCvBins - 1) / kCvBins), (unsigned)((T + kCvOut - 1) / kCvOut), (unsigned)B);
     DFB_PROF("k_df_convp_tc", s);
     k_df_convp_tc<5, 5><<<grid, kCvThreads, smem, s>>>(mc, p);
     DFB_LAUNCH_CHECK();

@@ -132,7 +132,7 @@ class DfNet(nn.Module):
                 _lib.lib().dfb_model_free(h)
             except Exception:
                 pass
-            self._h = None
+            object.__setattr__(self, "_h", None)   # (nn.Module.__setattr__ is unusable during interpreter shutdown)
 
     # -- nn.Module surface ---------------------------------------------------------------
     def state_dict(self, *args, **kwargs):  # reference tensor names
