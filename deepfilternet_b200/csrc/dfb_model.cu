@@ -771,7 +771,7 @@ struct dfb_model {
     int dev_chunks = 0, host_chunks = 4, n_lanes = 2;   // chunk pipeline (dfb_model_set_chunking); dev_chunks 0 = auto
     int post_filter = 0, mask_only = 0;       // optional stages (dfb_model_set_options)
     float pf_beta = 0.02f;
-    size_t max_workspace = size_t(24) << 30;  // dfb_enhance groups streams so that the arena stays below this
+    size_t max_workspace = size_t(64) << 30;  // dfb_enhance chunks / groups the batch so that the arena stays below this
     std::vector<int64_t> erb_widths;          // band table the model was built for (checked against the dfb_state)
     Arena aux_arena;                          // carried stream state + padded input of dfb_enhance
     cudaStream_t stream = nullptr;
@@ -1311,7 +1311,13 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         // DF pathway conv (needs c0 only; its result is consumed by the very last DF-decoder kernel): on the
         // low-priority stream, so its CTAs only take SMs that the critical path -- the encoder convs now, the GRU
         // clusters later -- leaves idle (timeline: on the auxiliary stream it delayed df_fc_emb by 1.8 ms)
-        DFB_CUDA(cudaStreamWaitEvent(sl, L.ev_c0, 0));
+        // ... but only while there ARE idle SMs: with a saturated device (large batches) the least-priority kernel is starved
+        // and finishes seconds-fractions late, and df_out -- hence the apply kernel -- waits for it (timeline at 512 x 10 s:
+        // 13.9 ms on `low`, 4 ms past the last recurrence, per 400-frame chunk).  Then it runs on the DF branch's encoder
+        // stream, behind df_conv1 (whose completion event is already recorded, so df_fc_emb does not wait for it).
+        const bool convp_low = !serial && (int64_t)B * T < 160000;
+        if (!convp_low) sl = sa;
+        else DFB_CUDA(cudaStreamWaitEvent(sl, L.ev_c0, 0));
         const int O2 = 2 * c.df_order;
         const float *w1, *w2, *bb;
         if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||
@@ -1574,7 +1580,7 @@ extern "C" int64_t dfb_enhance_out_len(const dfb_state *st, int64_t T, int pad) 
 }
 
 // enhance(): df/enhance.py:206-250.  Streams are processed in groups so that the workspace stays
-// below the model's workspace cap (24 GB by default; dfb_model_set_max_workspace / DFB_MAX_WORKSPACE_MB); streams
+// below the model's workspace cap (64 GB by default; dfb_model_set_max_workspace / DFB_MAX_WORKSPACE_MB); streams
 // are independent (per-channel state reset, pyDF/src/lib.rs:56-58).
 extern "C" int dfb_model_set_max_workspace(dfb_model *m, int64_t bytes) {
     if (!m || bytes <= 0) return fail(DFB_ERR_INVALID, "bad workspace cap");

@@ -229,7 +229,7 @@ int dfb_model_set_chunking(dfb_model *m, int device_chunks, int host_chunks, int
  * (checkpoint.py:32): no deep-filter stage, every bin takes the ERB gain. */
 int dfb_model_set_options(dfb_model *m, int post_filter, float pf_beta, int mask_only);
 /* Cap (bytes) of the per-call device workspace of dfb_enhance: the batch is processed in time chunks (and, for very
- * large batches, stream groups) that fit below it (default 24 GB, or DFB_MAX_WORKSPACE_MB in the environment at
+ * large batches, stream groups) that fit below it (default 64 GB, or DFB_MAX_WORKSPACE_MB in the environment at
  * dfb_model_create). */
 int dfb_model_set_max_workspace(dfb_model *m, int64_t bytes);
 /* Debug aid: steps > 0 with h_out == NULL arms clock64() phase stamps ([steps][8]) for the following
