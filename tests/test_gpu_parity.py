@@ -372,7 +372,7 @@ def test_stream_groups_with_ragged_last_group(states):
     assert rms(host, full.cpu()) < 1e-6
     for i in (0, 4, 5, 22, 39, 42):
         assert rms(grouped[i:i + 1].cpu(), O.enhance(sd, cfg.as_dict(), audio[i:i + 1].cpu())) < RMS_TOL, i
-    model.set_max_workspace(24 << 30)
+    model.set_max_workspace(64 << 30)
 
 
 @pytest.mark.parametrize("name", ["DeepFilterNet3", "DeepFilterNet2"])
@@ -429,7 +429,7 @@ def test_time_chunked_enhance_equals_one_shot(states, kind):
     many = enhance_device(model, st, audio).clone()
     many_host = enhance(model, st, audio.cpu())
     torch.cuda.synchronize()
-    model.set_max_workspace(24 << 30)
+    model.set_max_workspace(64 << 30)
     for name, x in (("serial6", serial6), ("piped", piped), ("piped2", piped2), ("many", many)):
         assert rms(one.cpu(), x.cpu()) < 1e-6, name
     assert rms(one.cpu(), host) < 1e-6 and rms(one.cpu(), many_host) < 1e-6
