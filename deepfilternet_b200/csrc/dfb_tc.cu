@@ -1003,36 +1003,7 @@ int launch_df_convp_tc(cudaStream_t s, const float *c0, const float *w_sw, const
 }
 
 // ------------------------------------------------------------------------------- host side ----
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
-    return fn;
-}
-
-// 2-D bf16 row-major [rows][cols] (row pitch ld elements), box = [box_rows][64 elements = 128 B], 128-byte swizzle
-static int make_map_bf16(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(DFB_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r);
-    return DFB_OK;
-}
+int cached_map_bf16(CUtensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows);  // dfb_gl.cu
 
 // Y[M,N] = X . W^T + bias with X, W given as BF16 hi/lo planes (X: [M][K] pitch ldx, W: [N][K] pitch K)
 int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64_t ldx, const void *w_hi, const void *w_lo,
@@ -1041,7 +1012,8 @@ int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64
         return fail(DFB_ERR_UNSUPPORTED, "bf16x3 GEMM shape M=%lld N=%d K=%d", (long long)M, N, K);
     CUtensorMap mxh, mxl;
     int rc;
-    if ((rc = make_map_bf16(&mxh, x_hi, M, K, ldx, kBxBM)) || (rc = make_map_bf16(&mxl, x_lo, M, K, ldx, kBxBM))) return rc;
+    // (cached per (base, shape): the arenas hand out the same addresses call after call)
+    if ((rc = cached_map_bf16(&mxh, x_hi, M, K, ldx, kBxBM)) || (rc = cached_map_bf16(&mxl, x_lo, M, K, ldx, kBxBM))) return rc;
     static PerDeviceOnce attr_once;
     const int smem = (int)sizeof(BxSmem) + 1024;
     if (auto once_guard = attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
