@@ -189,3 +189,40 @@ def test_bench_bookkeeping():
     assert set(bench.CONFIGS) == {2, 3, 4, 5} and bench.CONFIGS[2] == ("DeepFilterNet3", 128, 10, 1)
 
 
+
+
+def test_io_wav_roundtrip_and_resample_taps(tmp_path):
+    """df.io mirror, host side: the RIFF reader / writer (PCM16 with the reference's 1 << 15 scaling, float32, 24-bit) and
+    the resampler taps against torchaudio's own `_get_sinc_resample_kernel` (the convolution itself runs on the GPU)."""
+    import math
+    import struct
+    from deepfilternet_b200 import io as dio
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((2, 1000)) * 0.1).astype(np.float32)
+    p = dio.save_audio(str(tmp_path / "a.wav"), torch.from_numpy(x), 48000, suffix="enh")
+    assert p.endswith("a_enh.wav")
+    y, meta = dio.load_audio(p)
+    assert (meta.sample_rate, meta.num_frames, meta.num_channels, meta.bits_per_sample, meta.encoding) == (48000, 1000, 2, 16, "PCM_S")
+    assert np.array_equal(y.numpy(), (x * 32768).astype(np.int16).astype(np.float32) / 32768)
+    p = dio.save_audio(str(tmp_path / "f.wav"), torch.from_numpy((x * 32768).astype(np.int16)), 16000, dtype=torch.float32)
+    y, meta = dio.load_audio(p, frame_offset=10, num_frames=100)
+    assert meta.encoding == "PCM_F" and y.shape == (2, 100)
+    # 24-bit PCM, hand-made
+    v = np.array([0, 1, -1, (1 << 23) - 1, -(1 << 23)], dtype=np.int32)
+    raw = b"".join(struct.pack("<i", int(a))[:3] for a in v)
+    hdr = struct.pack("<4sI4s4sIHHIIHH4sI", b"RIFF", 36 + len(raw), b"WAVE", b"fmt ", 16, 1, 1, 8000, 24000, 3, 24, b"data", len(raw))
+    (tmp_path / "p24.wav").write_bytes(hdr + raw)
+    y, meta = dio.load_audio(str(tmp_path / "p24.wav"))
+    assert meta.bits_per_sample == 24 and np.allclose(y.numpy()[0], v / float(1 << 23))
+    with pytest.raises(RuntimeError):
+        (tmp_path / "bad.wav").write_bytes(b"not a wav file at all")
+        dio.load_audio(str(tmp_path / "bad.wav"))
+    try:
+        from torchaudio.functional.functional import _get_sinc_resample_kernel
+    except Exception:
+        pytest.skip("torchaudio not importable")
+    for o, n, meth in [(44100, 48000, "sinc_fast"), (48000, 16000, "kaiser_best"), (16000, 48000, "kaiser_fast"), (48000, 44100, "sinc_best")]:
+        k, w, og, nw = dio.resample_kernel(o, n, **dio.get_resample_params(meth))
+        kr, wr = _get_sinc_resample_kernel(o, n, math.gcd(o, n), **dio.get_resample_params(meth))
+        assert w == wr and (og, nw) == (o // math.gcd(o, n), n // math.gcd(o, n))
+        assert torch.equal(k, kr[:, 0])
