@@ -84,7 +84,6 @@ def kernel_model(cfg, g: dict) -> dict:
         # fused depthwise -> tcgen05 1x1: rows read (input + pathway) + rows written, 256 B each, over the 7 separable blocks
         "k_dwpw_bx": ("hbm", 256 * rows, "bytes"),
         "k_conv_in[df_conv0]": ("hbm", Fd * 8 + Fd * 256, "bytes"),
-        "k_conv_in_tc[df_conv0]": ("hbm", Fd * 8 + Fd * 256, "bytes"),
         "k_conv_in[erb_conv0]": ("hbm", 4 * E + E * 256, "bytes"),
         "k_df_convp": ("hbm", Fd * 256 + Fd * 4 * O2, "bytes"),
         "k_df_convp_tc": ("hbm", Fd * 256 + Fd * 4 * O2, "bytes"),

@@ -186,9 +186,6 @@ int launch_gl_bx(cudaStream_t s, const unsigned short *x_hi, const unsigned shor
                  const float *res, int64_t ldr, float *y, int64_t ldy, unsigned short *y_hi, unsigned short *y_lo, int64_t ldp,
                  int64_t M, int G, int Ig, int Hg, int act, float oscale, float ooffset);
 bool gl_bx_geometry(int G, int Ig, int Hg, int *gpc_out, int *hgp_out, int *stages_out);
-// df_conv0 (composed 2 -> 64 input conv on the complex features) on tensor cores (dfb_tc.cu)
-int launch_conv_in_tc(cudaStream_t s, const float *x, const float *w_img, const float *bias, float *out, int B, int T, int Fd, int lookahead,
-                      int Tsx, int Tx);
 // DF pathway conv (df_convp) on tensor cores (dfb_tc.cu)
 int launch_df_convp_tc(cudaStream_t s, const float *c0, const float *w_sw, const float *w2, const float *bias, float *coefs, int B, int T,
                        int Fd);

@@ -1295,15 +1295,9 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             if ((rc = need(m, "enc.df_conv0.w", c.inp_kt * 3 * 2 * kCh, &w)) || (rc = need(m, "enc.df_conv0.b", kCh, &bb))) return rc;
             dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
             int smem = (kInFrames + c.inp_kt - 1) * (Fd + 2) * 2 * 4;
-            static const bool c0_ffma = getenv("DFB_CONV0_FFMA") && atoi(getenv("DFB_CONV0_FFMA"));
-            const float *w_bx = (m->conv_tc && !c0_ffma && c.inp_kt == 3 && Fd >= 64 && Fd <= 126) ? m->get("enc.df_conv0.w_bx") : nullptr;
-            if (w_bx) {
-                if ((rc = launch_conv_in_tc(sa, d_feat_spec, w_bx, bb, f.c0, B, T, Fd, c.conv_lookahead, Tsx, Tx))) return rc;
-            } else {
-                DFB_PROF("k_conv_in[df_conv0]", sa);
-                k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead, Tsx, Tx);
-                DFB_LAUNCH_CHECK();
-            }
+            DFB_PROF("k_conv_in[df_conv0]", sa);
+            k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead, Tsx, Tx);
+            DFB_LAUNCH_CHECK();
             DFB_CUDA(cudaEventRecord(L.ev_c0, sa));
         }
         p = mk(f.c0, Fd, (int64_t)Fd * kCh, f.c1, Fd / 2, (int64_t)Fd / 2 * kCh, c.conv_kt);

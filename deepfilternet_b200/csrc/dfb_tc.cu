@@ -480,150 +480,6 @@ template int launch_dwpw_tc<DW_S1>(cudaStream_t, DwPwParams, const float *, int)
 template int launch_dwpw_tc<DW_S2>(cudaStream_t, DwPwParams, const float *, int);
 template int launch_dwpw_tc<DW_T2>(cudaStream_t, DwPwParams, const float *, int);
 
-// ---------------------------------------------------------- df_conv0 on tensor cores ----
-// c0[b,t,f,:] = relu(W . patch(t,f) + b): the grouped 2 -> 64 (3,3) conv on the complex features composed with its 1x1 conv
-// and BN (weights.py: one K = 18 conv; Conv2dNormAct, modules.py:18-72; look-ahead shift deepfilternet3.py:359,409-410).
-// The FFMA kernel (k_conv_in<2>) needs 1152 FMAs per output row and sits at 0.5 of its HBM-write roofline.  Here a CTA
-// owns 128 consecutive (t, f) rows -- 32 KB of contiguous c0 --: the 3 x 3 x 2 patches are gathered from the staged feature
-// frames, padded to K = 32 and written as BF16 hi / lo operand planes (K-major core matrices, no swizzle), 6 tcgen05.mma
-// (M128 N64 K16; BF16x3) produce the tile in 64 TMEM columns, and the epilogue (bias, ReLU, XOR-swizzled staging tile)
-// streams it out with coalesced 256-byte row stores.
-constexpr int kC0Threads = 256;
-constexpr uint32_t kC0W = 16384, kC0Stage = 24576, kC0In = kC0Stage + 32768;
-
-struct C0Params {
-    const float *x;      // feat_spec [B][Tsx][Fd][2]
-    const float *w_img;  // gl_bx_image of W [1][K = 32][N = 64]: BF16 hi plane | lo plane, K-major core matrices
-    const float *bias;   // [64]
-    float *out;          // c0 [B][T][Fd][64]
-    int T, Fd, lookahead, Tsx, Tx;
-};
-
-__global__ void __launch_bounds__(kC0Threads, 3) k_conv_in_tc(C0Params p) {
-    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    const uint32_t sb = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y;
-    const int64_t R0 = (int64_t)blockIdx.x * 128, RT = (int64_t)p.T * p.Fd;   // flat (t, f) rows of this stream
-    const int t_lo = (int)(R0 / p.Fd), t_hi = (int)(min(R0 + 127, RT - 1) / p.Fd);
-    const int nfr = t_hi - t_lo + 3, ld = (p.Fd + 2) * 2;                      // staged frames t_lo - 2 .. t_hi, zero column each side
-    const uint32_t s_in = sb + kC0In, s_bias = s_in + (uint32_t)(5 * ld * 4), bar_w = s_bias + 256, bar_mma = bar_w + 8, s_tmem = bar_mma + 8;
-    if (tid == 0) {
-        mbar_init_a(bar_w, 1);
-        mbar_init_a(bar_mma, 1);
-        fence_barrier_init();
-        mbar_expect_tx_a(bar_w, 8192);
-        bulk_load(sb + kC0W, p.w_img, 8192, bar_w);
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(64) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (tid < 16) sts128(s_bias + tid * 16, __ldg(reinterpret_cast<const float4 *>(p.bias) + tid));
-    // stage the feature frames (time index in the look-ahead shifted sequence; zero before the start / past the end)
-    for (int i = tid; i < nfr * ld; i += kC0Threads) {
-        const int fr = i / ld, j = i - fr * ld;
-        const int f = (j >> 1) - 1, ri = j & 1;
-        const int tp = t_lo - 2 + fr;
-        float v = 0.f;
-        if (f >= 0 && f < p.Fd && tp >= 0 && tp + p.lookahead < p.Tx)
-            v = __ldg(p.x + (((int64_t)b * p.Tsx + tp + p.lookahead) * p.Fd + f) * 2 + ri);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_in + 4 * i), "f"(v) : "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = lds32(s_tmem);
-    {   // patches -> operand planes: thread = (row, K half); k = dt * 6 + df * 2 + ri, 18 of 32 used
-        const int r = tid & 127, kh = tid >> 7;
-        const int64_t R = R0 + r;
-        const bool valid = R < RT;
-        const int t = valid ? (int)(R / p.Fd) : t_lo, f = valid ? (int)(R - (int64_t)t * p.Fd) : 0;
-        const uint32_t row = s_in + (uint32_t)((t - t_lo) * ld + f * 2) * 4u;   // frame t - 2 (dt = 0), column f - 1 (df = 0)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {        // two 16-byte core-matrix rows (8 K elements each) per thread
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int k = kh * 16 + c * 8 + e;
-                v[e] = 0.f;
-                if (k < 18 && valid) {
-                    const int dt = k / 6, rem = k - dt * 6;   // rem = df * 2 + ri: contiguous in the staged row
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[e]) : "r"(row + (uint32_t)(dt * ld + rem) * 4u));
-                }
-            }
-            uint32_t h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) bf16x2_split(v[2 * e], v[2 * e + 1], h[e], l[e]);
-            const uint32_t off = sb + (uint32_t)(kh * 2 + c) * 2048u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off + 8192u), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
-        }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-        mbar_wait_a(bar_w, 0);
-        const uint64_t ah = umma_desc_interleave(sb, 2048, 128), al = umma_desc_interleave(sb + 8192, 2048, 128);
-        const uint64_t bh = umma_desc_interleave(sb + kC0W, 1024, 128), bl = umma_desc_interleave(sb + kC0W + 4096, 1024, 128);
-#pragma unroll
-        for (int k = 0; k < 2; k++) {   // K step 16 = two core matrices: A + 2 * 2048 B, B + 2 * 1024 B
-            umma_bf16_ss_elect(tmem_u, ah + (uint64_t)(k * 4096 >> 4), bh + (uint64_t)(k * 2048 >> 4), idesc, k != 0);
-            umma_bf16_ss_elect(tmem_u, al + (uint64_t)(k * 4096 >> 4), bh + (uint64_t)(k * 2048 >> 4), idesc, 1u);
-            umma_bf16_ss_elect(tmem_u, ah + (uint64_t)(k * 4096 >> 4), bl + (uint64_t)(k * 2048 >> 4), idesc, 1u);
-        }
-        asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                     "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar_mma) : "memory");
-    }
-    mbar_wait_a(bar_mma, 0);
-    tc_fence_after();
-    {   // accumulator -> bias + ReLU -> staging tile (row r, 16-byte chunk j at r * 256 + ((j ^ (r & 15)) << 4))
-        const int q = warp & 3, ch = warp >> 2;
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ch * 32, v);
-        const int r = q * 32 + lane;
-        const uint32_t row = sb + kC0Stage + r * 256;
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-            const float4 bv = lds128(s_bias + (ch * 8 + jj) * 16);
-            sts128(row + (((ch * 8 + jj) ^ (r & 15)) << 4),
-                   make_float4(fmaxf(v[jj * 4] + bv.x, 0.f), fmaxf(v[jj * 4 + 1] + bv.y, 0.f), fmaxf(v[jj * 4 + 2] + bv.z, 0.f),
-                               fmaxf(v[jj * 4 + 3] + bv.w, 0.f)));
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 64);
-    {   // the tile is 128 x 256 contiguous bytes of c0: half a warp per row, 8 rows per thread
-        const int j = tid & 15, slot = tid >> 4;
-        float *dst = p.out + ((int64_t)b * RT + R0) * kCh + j * 4;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int r = 8 * slot + i;
-            if (R0 + r < RT) *reinterpret_cast<float4 *>(dst + (int64_t)r * kCh) = lds128(sb + kC0Stage + r * 256 + ((j ^ (r & 15)) << 4));
-        }
-    }
-}
-
-int launch_conv_in_tc(cudaStream_t s, const float *x, const float *w_img, const float *bias, float *out, int B, int T, int Fd, int lookahead,
-                      int Tsx, int Tx) {
-    if (Fd > 126 || B > 65535) return fail(DFB_ERR_UNSUPPORTED, "df_conv0 tensor-core kernel: nb_df %d", Fd);
-    const int smem = 1024 + (int)kC0In + 5 * (Fd + 2) * 2 * 4 + 256 + 64;
-    static PerDeviceOnce attr_once;
-    if (auto once_guard = attr_once.first()) DFB_CUDA(cudaFuncSetAttribute(k_conv_in_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    C0Params p{x, w_img, bias, out, T, Fd, lookahead, Tsx, Tx};
-    const int64_t rows = (int64_t)T * Fd;
-    dim3 grid((unsigned)((rows + 127) / 128), (unsigned)B);
-    DFB_PROF("k_conv_in_tc[df_conv0]", s);
-    k_conv_in_tc<<<grid, kC0Threads, smem, s>>>(p);
-    DFB_LAUNCH_CHECK();
-    return DFB_OK;
-}
-
 // ---------------------------------------------------------- DF pathway conv on tensor cores ----
 // coefs[b,t,f,:] = relu( pw( conv_t(c0) ) + b )  (df_convp, deepfilternet3.py:293-295: grouped (2) temporal conv 64 -> 10
 // with kernel (5,1), 1x1 conv 10 x 10, BN, ReLU).  The FFMA kernel (k_df_convp, dfb_model.cu) is instruction-issue bound

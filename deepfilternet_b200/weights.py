@@ -155,11 +155,6 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
     pws = pw * s[:, None]                                 # [n][c], BN folded
     weff = np.stack([np.einsum("ctf,nc->tfn", dw[ri * g:(ri + 1) * g, 0], pws[:, ri * g:(ri + 1) * g]) for ri in range(2)], axis=2)
     out["enc.df_conv0.w"] = f32(weff)                     # [kt][3][2][C]
-    if inp_kt == 3 and C == 64:
-        # tensor-core form (k_conv_in_tc): W [1][K = 32][N = 64], k = dt * 6 + df * 2 + ri (18 used), as a grouped-linear image
-        wk = np.zeros((1, 32, C), dtype=np.float32)
-        wk[0, :18] = weff.reshape(18, C)
-        out["enc.df_conv0.w_bx"] = gl_bx_image(wk)
     out["enc.df_conv0.dw"] = f32(dw[:, 0].transpose(1, 2, 0))
     out["enc.df_conv0.pw"] = f32((pw * s[:, None]).T)
     out["enc.df_conv0.pw_nk"] = f32(pw * s[:, None])
