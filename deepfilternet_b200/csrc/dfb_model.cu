@@ -1315,7 +1315,8 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         // and finishes seconds-fractions late, and df_out -- hence the apply kernel -- waits for it (timeline at 512 x 10 s:
         // 13.9 ms on `low`, 4 ms past the last recurrence, per 400-frame chunk).  Then it runs on the DF branch's encoder
         // stream, behind df_conv1 (whose completion event is already recorded, so df_fc_emb does not wait for it).
-        const bool convp_low = !serial && (int64_t)B * T < 160000;
+        static const int convp_env = getenv("DFB_CONVP_LOW") ? atoi(getenv("DFB_CONVP_LOW")) : -1;   // experiments: force either
+        const bool convp_low = !serial && (convp_env >= 0 ? convp_env != 0 : (int64_t)B * T < 160000);
         if (!convp_low) sl = sa;
         else DFB_CUDA(cudaStreamWaitEvent(sl, L.ev_c0, 0));
         const int O2 = 2 * c.df_order;
