@@ -1311,14 +1311,9 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         // DF pathway conv (needs c0 only; its result is consumed by the very last DF-decoder kernel): on the
         // low-priority stream, so its CTAs only take SMs that the critical path -- the encoder convs now, the GRU
         // clusters later -- leaves idle (timeline: on the auxiliary stream it delayed df_fc_emb by 1.8 ms)
-        // ... but only while there ARE idle SMs: with a saturated device (large batches) the least-priority kernel is starved
-        // and finishes seconds-fractions late, and df_out -- hence the apply kernel -- waits for it (timeline at 512 x 10 s:
-        // 13.9 ms on `low`, 4 ms past the last recurrence, per 400-frame chunk).  Then it runs on the DF branch's encoder
-        // stream, behind df_conv1 (whose completion event is already recorded, so df_fc_emb does not wait for it).
-        static const int convp_env = getenv("DFB_CONVP_LOW") ? atoi(getenv("DFB_CONVP_LOW")) : -1;   // experiments: force either
-        const bool convp_low = !serial && (convp_env >= 0 ? convp_env != 0 : (int64_t)B * T < 160000);
-        if (!convp_low) sl = sa;
-        else DFB_CUDA(cudaStreamWaitEvent(sl, L.ev_c0, 0));
+        // (also measured with a saturated device -- 512 x 10 s --: on the DF branch's encoder stream it slows df_fc_emb by
+        // as much as it gains at the tail, 49.4 vs 45.2 ms per step)
+        DFB_CUDA(cudaStreamWaitEvent(sl, L.ev_c0, 0));
         const int O2 = 2 * c.df_order;
         const float *w1, *w2, *bb;
         if ((rc = need(m, "df_dec.df_convp.w1", (int64_t)c.df_pathway_kt * O2 * (kCh / 2), &w1)) ||

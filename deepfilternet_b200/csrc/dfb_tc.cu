@@ -697,7 +697,7 @@ struct GruTcSmem {
     float pre[3][kGtU][NS + 1];
     alignas(8) uint64_t bar_h[2];
     uint64_t t_full;
-    uint32_t tmem_base, tmem_acc;
+    uint32_t tmem_base;
 };
 
 struct GruTcParams {
@@ -718,14 +718,8 @@ struct GruTcParams {
 };
 
 
-// SHARE (H = 256, 16 streams): the CTA takes 256 + 32 tensor-memory columns in two allocations instead of all 512, is
-// compiled for two CTAs' worth of registers per SM and is launched with 115 KB instead of 120+ KB of shared memory, so
-// that feed-forward CTAs with <= 113 KB (k_dwpw_bx, k_df_convp_tc, k_apply_synthesis, k_conv_in, k_analysis) can run on the
-// SMs a recurrence occupies but hardly uses (sm % 3 in ncu).  Two recurrence CTAs still never share an SM (2 x 115 KB does
-// not fit): both would need tensor memory the other holds, and with clusters that is a hold-and-wait cycle.
-template <int NS, int HH, int SHARE>
-__global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, (SHARE && NS == 16) ? 2 : 1) k_gru_tc(GruTcParams p) {
-    static_assert(!SHARE || HH == 256, "the shared variant needs W_hh hi | lo in 256 columns");
+template <int NS, int HH>
+__global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcParams p) {
     using Cfg = GtCfg<NS, HH>;
     constexpr int kGtThreads = Cfg::kThreads;
     constexpr int kGtH = HH, kGtC = Cfg::kC, kGtWCols = Cfg::kWCols, kGtDCol = Cfg::kDCol;
@@ -745,21 +739,13 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, (SHARE && NS == 16) ?
         mbar_init(&sm.t_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) {
-        if (SHARE) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(256) : "memory");
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_acc)), "r"(32) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        } else {
-            tmem_alloc(&sm.tmem_base, 512);
-        }
-    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t tmem_d = SHARE ? sm.tmem_acc : tmem + kGtDCol;   // accumulator [128 lanes][NS columns]
+    const uint32_t tmem_d = tmem + kGtDCol;   // accumulator [128 lanes][NS columns]
     if (p.h0) {  // carried state: every CTA builds the whole operand h_{-1} of its streams in buffer 0
         for (int i = tid; i < nb * (kGtH / 2); i += kGtThreads) {
             const int s = i / (kGtH / 2), gu = (i - s * (kGtH / 2)) * 2;
@@ -944,24 +930,21 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, (SHARE && NS == 16) ?
     tc_fence_before();
     __syncthreads();
     cluster.sync();  // no CTA exits while peers may still address its shared memory
-    if (warp == 0) {
-        if (SHARE) { tmem_dealloc(tmem, 256); tmem_dealloc(tmem_d, 32); }
-        else tmem_dealloc(tmem, 512);
-    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int NS, int HH, int SHARE = 0>
+template <int NS, int HH>
 static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     using Cfg = GtCfg<NS, HH>;
     static PerDeviceOnce attr_once;
-    // the kernel allocates most of the TMEM columns (W_hh lives there), so only one recurrence CTA may be resident
-    // per SM: request more than half of the shared memory to enforce it
+    // the kernel allocates all 512 TMEM columns (W_hh lives there), so only one CTA may be resident per SM: request more
+    // than half of the shared memory to enforce it.  (Tried: 256 + 32 columns, half the registers and 115 KB so that
+    // feed-forward CTAs could share the SMs a recurrence occupies but hardly uses -- no gain at 128 or 512 streams.)
     const int need = (int)sizeof(GruTcSmem<NS, HH>) + 1024;
-    const int floor_kb = SHARE ? 115 : 120;
-    const int smem = need > floor_kb * 1024 ? need : floor_kb * 1024;
+    const int smem = need > 120 * 1024 ? need : 120 * 1024;
     if (auto once_guard = attr_once.first()) {
-        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH, SHARE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(Cfg::kThreads);
@@ -975,7 +958,7 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     cfg.gridDim = dim3((unsigned)(ngroups * Cfg::kC));
     cfg.stream = s;
     DFB_PROF(HH == 256 ? "k_gru_tc" : "k_gru_tc512", s);
-    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH, SHARE>, p));
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH>, p));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return DFB_OK;
 }
@@ -996,9 +979,6 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
     // from 256 streams on a launch needs several waves of the 15 co-resident clusters anyway, and 32 per cluster are faster
     // (512 x 10 s DeepFilterNet2: 48.1 -> 45.3 ms per step)
     const bool use32 = force ? force == 32 : ((wide && B > 64) || B >= 256);
-    // DFB_GRU_SHARE=1 (experiment): recurrence CTAs leave tensor memory, registers and shared memory for feed-forward CTAs
-    static const bool share = getenv("DFB_GRU_SHARE") && atoi(getenv("DFB_GRU_SHARE"));
-    if (share) return use32 ? launch_gru_tc_n<32, 256, 1>(s, p) : launch_gru_tc_n<16, 256, 1>(s, p);
     return use32 ? launch_gru_tc_n<32, 256>(s, p) : launch_gru_tc_n<16, 256>(s, p);
 }
 
