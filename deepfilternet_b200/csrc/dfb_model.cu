@@ -1824,8 +1824,17 @@ static int enhance_group(dfb_model *m, dfb_state *st, const float *d_x, int64_t 
         DFB_CUDA(cudaStreamWaitEvent(m->lanes[1].main, ev_call, 0));
     }
     int chunk = 0, last_lane = 0;
+    // Host path: the first chunk's H2D copy and the last chunk's D2H copy are the only ones nothing overlaps, so both end
+    // chunks are half as long as the others (128 x 10 s in 4 chunks: 250 / 250 / 250 / 252 frames -> 125 / 250 / 250 / 250 / 127).
+    const bool taper = hooks && pipelined && tc < Tf && tc >= 64;
     while (S.d1 < Tf) {
-        const int64_t d1n = S.d1 + tc < Tf ? S.d1 + tc : Tf;
+        int64_t step = tc;
+        if (taper) {
+            const int64_t left = Tf - S.d1;
+            if (chunk == 0) step = tc / 2;
+            else if (left <= tc + tc / 2 && left - tc / 2 >= tc / 4) step = left - tc / 2;   // leaves a half-length last chunk
+        }
+        const int64_t d1n = S.d1 + step < Tf ? S.d1 + step : Tf;
         const int64_t a1n = d1n + g.Lmax < Tf ? d1n + g.Lmax : Tf;
         const int64_t e1n = d1n == Tf ? Tf : d1n - g.lag;
         const int lane = pipelined ? (chunk & 1) : 0;
