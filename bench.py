@@ -65,12 +65,13 @@ def kernel_model(cfg, g: dict) -> dict:
     enc_l, erb_l, df_l = g["enc_gru_layers"], g["erb_gru_layers"], g["df_gru_layers"]
     rec = 2 * 3 * (H * H * (enc_l + erb_l) + Hd * Hd * df_l)        # W_hh h, all layers
     proj = rec                                                       # W_ih x: same shapes (inputs are H wide)
-    gl = 0
+    gl = gl_bytes = 0
     for (i, o, grp) in ((Fd // 2 * 64, ED, g["g_df_fc_emb"]), (emb_in, H, g["g_enc_in"]), (H, ED, g["g_enc_out"]),
                         (emb, H, g["g_erb_in"]), (H, ED, g["g_erb_out"]), (emb, Hd, g["g_df_in"]),
                         (emb, Hd, g["g_df_skip"]), (Hd, Fd * O2, g["g_df_out"])):
         if grp:
             gl += 2 * i * o // grp
+            gl_bytes += 4 * (i + o)                                  # fp32 row in, fp32 row out
     rows = (Fd + Fd // 2) + (E + E // 2) + (E // 2 + E // 4) + (E // 4 + E // 4) + 3 * (E // 4) + (E // 4 + E // 4 + E // 2) \
         + (E // 2 + E // 2 + E)
     return {
@@ -79,7 +80,9 @@ def kernel_model(cfg, g: dict) -> dict:
         "k_apply_synthesis": ("hbm", 8 * cfg.freq_bins + 4 * E + 4 * Fd * O2 + 1920, "bytes"),
         "k_gru_tc": ("tensor", rec, "flops"), "k_gru": ("tensor", rec, "flops"), "k_gru_tc512": ("tensor", rec, "flops"),
         "k_gemm_bf16x3[gru_proj]": ("tensor", proj, "flops"), "k_grouped_linear[gru_proj]": ("tensor", proj, "flops"),
-        "k_grouped_linear": ("tensor", gl, "flops"), "k_gl_bx": ("tensor", gl, "flops"),
+        "k_grouped_linear": ("tensor", gl, "flops"),
+        # grouped linears on tcgen05: 2 * I * O / G flops per row are ~20 flop/B, far under the ridge -> HBM bound
+        "k_gl_bx": ("hbm", gl_bytes, "bytes"),
         "k_dwpw": ("tensor", 2 * 64 * 64 * (Fd // 2 + E // 2 + E // 4 + E // 4 + E // 4 + E // 2 + E), "flops"),
         # fused depthwise -> tcgen05 1x1: rows read (input + pathway) + rows written, 256 B each, over the 7 separable blocks
         "k_dwpw_bx": ("hbm", 256 * rows, "bytes"),

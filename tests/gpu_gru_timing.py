@@ -10,10 +10,15 @@ from tests_common import synth_audio
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 cfg = ModelConfig(model="deepfilternet3", conv_ch=64, conv_lookahead=2, df_lookahead=2, emb_num_layers=3, df_num_layers=2,
                   lin_groups=16, enc_lin_groups=32, df_gru_skip="groupedlinear", df_pathway_kernel_size_t=5)
+if len(sys.argv) > 3 and sys.argv[3] == "ll":   # DeepFilterNet3_ll: H = 512 recurrences (clusters of 16 CTAs)
+    cfg = ModelConfig(model="deepfilternet3", conv_ch=64, conv_lookahead=0, df_lookahead=0, conv_kernel=(2, 3), emb_hidden_dim=512,
+                      df_hidden_dim=512, emb_num_layers=3, df_num_layers=3, lin_groups=16, enc_lin_groups=16,
+                      df_gru_skip="groupedlinear", df_pathway_kernel_size_t=5)
 st = libdf.DF(48000, 960, 480, 32, 2)
 model = DfNet(cfg, random_state_dict(cfg, 0), st)
+model.set_chunking(1, 1, 1)
 SEC = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-audio = synth_audio(B, 48000 * SEC, device="cuda")
+audio = (torch.randn(B, 48000 * SEC, device="cuda") * 0.05).clamp(-1, 1)
 enhance_device(model, st, audio); torch.cuda.synchronize()
 T = (48000 * SEC + 960) // 480
 L = _lib.lib()
