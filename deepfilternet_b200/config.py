@@ -70,6 +70,11 @@ class ModelConfig:
     mask_pf: bool = False
     pf_beta: float = 0.02
     df_n_iter: int = 1
+    # DeepFilterNet v1 only (deepfilternet.py:11-53)
+    conv_k_enc: int = 2
+    conv_k_dec: int = 1
+    gru_groups: int = 1
+    group_shuffle: bool = True
     path: str = field(default="", compare=False)
 
     def as_dict(self) -> dict:
@@ -115,9 +120,9 @@ def load_config(path: str, env: Optional[dict] = None) -> ModelConfig:
         return cast(default)
 
     model = get("model", "deepfilternet3", str, "train").lower()
-    if model not in ("deepfilternet2", "deepfilternet3"):
+    if model not in ("deepfilternet", "deepfilternet2", "deepfilternet3"):
         raise NotImplementedError(
-            f"model '{model}' is outside the B200 hot path (DeepFilterNet2/3/3_ll supported)")
+            f"model '{model}' is outside the B200 hot path (DeepFilterNet/2/3/3_ll supported)")
     c = ModelConfig(model=model, path=path)
     S = "df"
     c.sr = get("sr", 48000, int, S)
@@ -134,6 +139,8 @@ def load_config(path: str, env: Optional[dict] = None) -> ModelConfig:
     S = "deepfilternet"
     c.conv_lookahead = get("conv_lookahead", 0, int, S)
     c.conv_ch = get("conv_ch", 16, int, S)
+    if model == "deepfilternet":
+        return _load_v1(c, get)
     c.conv_kernel = get("conv_kernel", (1, 3), _csv_int, S)
     c.conv_kernel_inp = get("conv_kernel_inp", (3, 3), _csv_int, S)
     c.emb_hidden_dim = get("emb_hidden_dim", 256, int, S)
@@ -171,6 +178,41 @@ def load_config(path: str, env: Optional[dict] = None) -> ModelConfig:
     if c.df_n_iter != 1:
         raise NotImplementedError("df_n_iter != 1")
     check_supported(c)
+    return c
+
+
+def _load_v1(c: "ModelConfig", get) -> "ModelConfig":
+    """ModelParams of DeepFilterNet v1 (deepfilternet.py:11-53).  The kernels build the shipped topology: transposed
+    depthwise decoder convs, grouped GRUs / linears with shuffle, `real_unfold` deep filtering with alpha blending."""
+    S = "deepfilternet"
+    c.conv_k_enc = get("conv_k_enc", 2, int, S)
+    c.conv_k_dec = get("conv_k_dec", 1, int, S)
+    c.emb_hidden_dim = get("emb_hidden_dim", 256, int, S)
+    c.emb_num_layers = get("emb_num_layers", 1, int, S)
+    c.df_hidden_dim = get("df_hidden_dim", 256, int, S)
+    c.df_num_layers = get("df_num_layers", 3, int, S)
+    c.gru_groups = get("gru_groups", 1, int, S)
+    c.lin_groups = get("linear_groups", 1, int, S)
+    c.enc_lin_groups = c.lin_groups
+    c.group_shuffle = get("group_shuffle", True, _bool, S)
+    c.dfop_method = get("dfop_method", "real_unfold", str, S)
+    c.mask_pf = get("mask_pf", False, _bool, S)
+    c.conv_kernel = (c.conv_k_enc, 3)
+    c.convt_kernel = (c.conv_k_dec, 3)
+    k0 = 1 if c.conv_k_enc == 1 and c.conv_lookahead == 0 else max(2, c.conv_k_enc)   # deepfilternet.py:74
+    c.conv_kernel_inp = (k0, 3)
+    bad = []
+    if get("conv_width_factor", 1, int, S) != 1: bad.append("conv_width_factor != 1")
+    if get("conv_dec_mode", "transposed", str, S) != "transposed": bad.append("conv_dec_mode != transposed")
+    if not get("conv_depthwise", True, _bool, S) or not get("convt_depthwise", True, _bool, S): bad.append("dense (non-depthwise) convs")
+    if c.dfop_method not in ("real_unfold", "real_loop", "real_strided", "complex_strided"): bad.append(f"dfop_method={c.dfop_method}")
+    if c.conv_k_enc != 2 or c.conv_k_dec != 2: bad.append("conv_k_enc / conv_k_dec other than 2")
+    if c.conv_lookahead != 2: bad.append("conv_lookahead other than 2")
+    if c.emb_hidden_dim != c.df_hidden_dim: bad.append("emb_hidden_dim != df_hidden_dim")
+    if bad:
+        raise NotImplementedError("DeepFilterNet (v1) variants other than the shipped topology are outside the B200 hot path: " + ", ".join(bad))
+    if c.hop_size * 2 > c.fft_size:
+        raise ValueError("hop_size * 2 <= fft_size required (libDF/src/lib.rs:111)")
     return c
 
 

@@ -146,6 +146,9 @@ struct ApplyParams {
     // lsnr < th_min -> zero gains, no DF; > th_erb -> frame passes unprocessed; > th_df -> gains only; else gains + DF
     const float *lsnr;
     float th_min, th_erb, th_df;
+    // DeepFilterNet v1 (mode 2): alpha [B][mc_T] or null; DF bins <- alpha * deep filter + (1 - alpha) * masked bin
+    // (assign_df, modules.py:470-478)
+    const float *alpha;
     float atten_lim;      // 0 = off
     // carried ISTFT state (pyDF synthesis(reset=False), mode 0 only): channel 0 starts from init_tail,
     // channel c > 0 from the tail left by channel c - 1; the tail after the last frame goes to final_tail

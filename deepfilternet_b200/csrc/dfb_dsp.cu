@@ -421,6 +421,13 @@ __device__ __forceinline__ float2 apply_bin(const ApplyParams &p, const DspTable
             yi += s.x * wi + s.y * wr;
         }
         y = make_float2(yr, yi);
+        if (p.alpha && p.mode == 2) {
+            const float a = p.alpha[(mrow0 - p.m) / tb.E + t];   // same [b][mc_T] indexing as the mask rows
+            float g = mrow0[(int64_t)t * tb.E + band];
+            if (pf2) g = pf_gain_mask(g, 0.02f);
+            y.x = y.x * a + x.x * g * (1.f - a);
+            y.y = y.y * a + x.y * g * (1.f - a);
+        }
     }
     if (p.pf && p.mode == 1) { const float g = pf_gain_spec(y, x, p.pf_beta); y.x *= g; y.y *= g; }
     if (p.atten_lim > 0.f) {
@@ -538,7 +545,8 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
     const float *mrow0 = p.m + (int64_t)b * mcT * 32;
     const bool masked_df = p.mode == 2 && !p.mask_only;
     const bool pf1 = p.pf && p.mode == 1, pf2 = p.pf && p.mode == 2;
-    const bool need_xk = p.atten_lim > 0.f || pf1 || p.mask_only || p.lsnr;   // noisy DF bins are only loaded when something reads them
+    const bool blend = p.alpha != nullptr && masked_df;   // DeepFilterNet v1: alpha blend with the masked bin
+    const bool need_xk = p.atten_lim > 0.f || pf1 || p.mask_only || p.lsnr || blend;   // noisy DF bins are only loaded when something reads them
     // bands of this lane's bins: bk[j] for k = lane + 32 j, bn[j] for 480 - k
     unsigned long long bkp = 0, bnp = 0;  // 8 band indices each, one byte per j
 #pragma unroll
@@ -577,6 +585,7 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
         // ---- loads of this frame, all issued before use
         float mcur = mrow0[(int64_t)t * 32 + lane];
         if (pf2) mcur = pf_gain_mask(mcur, 0.02f);
+        const float al = blend ? p.alpha[(int64_t)b * mcT + t] : 1.f;
         int stage = 3;   // 0 zero gains, 1 unprocessed, 2 gains only, 3 gains + deep filter (tract.rs apply_stages)
         if (p.lsnr) {
             const float l = p.lsnr[(int64_t)b * mcT + t];
@@ -615,6 +624,10 @@ __global__ void __launch_bounds__(32 * kSynWarps, MINB) k_apply_synthesis(ApplyP
                     yi += s.x * w.y + s.y * w.x;
                 }
                 y = make_float2(yr, yi);
+                if (blend) {
+                    const float g = __shfl_sync(0xffffffffu, mcur, BK(j)) * (1.f - al);
+                    y.x = y.x * al + xk[j].x * g; y.y = y.y * al + xk[j].y * g;
+                }
             } else {
                 const float g = __shfl_sync(0xffffffffu, mcur, BK(j));
                 y = make_float2(xk[j].x * g, xk[j].y * g);

@@ -75,8 +75,10 @@ __device__ __forceinline__ float4 dw_prologue(const DwPwParams &p, const DwTaps 
 #pragma unroll
     for (int dt = 0; dt < 3; dt++) {
         if (dt < 3 - p.kt) continue;
-        const int tq = t - (2 - dt);  // causal: taps at t-(kt-1) .. t
-        if (tq < 0) continue;
+        // causal: taps at t-(kt-1) .. t; p.lookahead shifts them forward (DeepFilterNet v1 pads (kt-1-la, la), modules.py:151-154);
+        // DF0 keeps the DeepFilterNet2 / 3 meaning: the feature sequence is shifted first, then padded causally
+        const int tq = (MODE == DW_DF0) ? t - (2 - dt) : t - (2 - dt) + p.lookahead;
+        if (tq < 0 || tq >= p.T) continue;
 #pragma unroll
         for (int df = 0; df < 3; df++) {
             int fi;

@@ -56,7 +56,9 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 k_conv_in(const float *__restrict__ x, const float *__restrict__ w /*[kt][3][CIN][64]*/, const float *__restrict__ bias,
           float *__restrict__ out, int T, int F, int kt, int lookahead, int Tsx /* frames per stream in x */,
-          int Tx /* feature frames that exist; beyond = end of the stream = zero */) {
+          int Tx /* feature frames that exist; beyond = end of the stream = zero */,
+          int tp_min /* 0: the features are shifted by the look-ahead, then padded causally (DeepFilterNet2 / 3, pad_feat);
+                        -lookahead: the conv itself pads (kt-1-la, la) around the unshifted features (DeepFilterNet v1) */) {
     extern __shared__ float s_in[];  // [(kInFrames + kt - 1)][(F + 2) * CIN]
     const int b = blockIdx.y, t0 = blockIdx.x * kInFrames;
     const int rows = kInFrames + kt - 1, ld = (F + 2) * CIN;
@@ -65,7 +67,7 @@ k_conv_in(const float *__restrict__ x, const float *__restrict__ w /*[kt][3][CIN
         int f = j / CIN - 1, ci = j - (f + 1) * CIN;
         int tp = t0 - (kt - 1) + r;  // time index in the look-ahead shifted feature sequence
         float v = 0.f;
-        if (f >= 0 && f < F && tp >= 0 && tp + lookahead < Tx) v = x[(((int64_t)b * Tsx + tp + lookahead) * F + f) * CIN + ci];
+        if (f >= 0 && f < F && tp >= tp_min && tp + lookahead < Tx) v = x[(((int64_t)b * Tsx + tp + lookahead) * F + f) * CIN + ci];
         s_in[i] = v;
     }
     const int cq = threadIdx.x & 15, fl = threadIdx.x >> 4;  // 16 channel quads x 16 f per pass
@@ -625,6 +627,62 @@ k_mask_out(const float *__restrict__ e0, const float *__restrict__ d1, const flo
     }
 }
 
+// ------------------------------------------------- DeepFilterNet v1: gather-sum, pathway 1x1 ----
+// out[m][k] = act( sum_i src_i[m][idx_i[k]] ), optionally also as BF16 hi / lo planes.  DeepFilterNet v1 flattens channel-major
+// into its grouped layers and interleaves ("shuffles") their outputs (deepfilternet.py:135-139,183-185; modules.py:651-654,
+// 807-812) while the device tensors are channel-last: every such re-ordering, and the sum over the GRU layers' outputs
+// (add_outputs, modules.py:655-656), is one pass of this kernel with host-built index tables (weights.py: v1.idx_*).
+struct GatherParams {
+    const float *src[3]; long long ld[3]; const int *idx[3]; int n;
+    float *out; long long ldo;
+    unsigned short *hi, *lo; long long ldp;
+    int K, relu;
+};
+__global__ void __launch_bounds__(256) k_gather_sum(GatherParams p) {
+    const long long m = blockIdx.x;
+    for (int k = threadIdx.x; k < p.K; k += 256) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            if (i < p.n) v += p.src[i][m * p.ld[i] + p.idx[i][k]];
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (p.out) p.out[m * p.ldo + k] = v;
+        if (p.hi) {
+            unsigned short h, l;
+            bf16_split(v, h, l);
+            p.hi[m * p.ldp + k] = h; p.lo[m * p.ldp + k] = l;
+        }
+    }
+}
+
+// coefs[r][k] = tanh(coefs[r][k]) + relu(sum_c c0[r][c] w[c][k] + b[k]),  r = (b, t, f), k < 2 O: the dense 1x1 pathway conv
+// df_convp (deepfilternet.py:210-212) on top of the df_fc_out pre-activations already in `coefs` (deepfilternet.py:224-228)
+template <int O2>
+__global__ void __launch_bounds__(128) k_convp_v1(const float *__restrict__ c0, const float *__restrict__ w /*[64][O2]*/,
+                                                   const float *__restrict__ bias, float *__restrict__ coefs, long long rows) {
+    __shared__ float ws[kCh * O2];
+    __shared__ float bs[O2];
+    for (int i = threadIdx.x; i < kCh * O2; i += 128) ws[i] = w[i];
+    if (threadIdx.x < O2) bs[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (r >= rows) return;
+    float acc[O2];
+#pragma unroll
+    for (int k = 0; k < O2; k++) acc[k] = bs[k];
+    const float4 *x = reinterpret_cast<const float4 *>(c0 + r * kCh);
+#pragma unroll 4
+    for (int q = 0; q < kCh / 4; q++) {
+        const float4 v = x[q];
+#pragma unroll
+        for (int k = 0; k < O2; k++)
+            acc[k] += v.x * ws[(4 * q) * O2 + k] + v.y * ws[(4 * q + 1) * O2 + k] + v.z * ws[(4 * q + 2) * O2 + k] + v.w * ws[(4 * q + 3) * O2 + k];
+    }
+    float *o = coefs + r * O2;
+#pragma unroll
+    for (int k = 0; k < O2; k++) o[k] = tanhf(o[k]) + fmaxf(acc[k], 0.f);
+}
+
 // ------------------------------------------------- DF pathway conv ----
 // coefs[b,t,f,:] = relu( pw( conv_t(c0) ) + b ); the df_out projection later adds tanh(df_out(c)) on top
 // (deepfilternet3.py:293-295, 328-330).  df_convp = grouped (2) temporal conv C -> 2*O with kernel (ktp,1),
@@ -808,7 +866,10 @@ extern "C" int dfb_model_create(dfb_model **out, int device, const dfb_model_con
     if (!out || !cfg || !tensors) return fail(DFB_ERR_INVALID, "null argument");
     *out = nullptr;
     if (cfg->conv_ch != kCh) return fail(DFB_ERR_UNSUPPORTED, "conv_ch = %d (built kernels: 64)", cfg->conv_ch);
-    if (cfg->model_kind != 2 && cfg->model_kind != 3) return fail(DFB_ERR_UNSUPPORTED, "model_kind %d", cfg->model_kind);
+    if (cfg->model_kind < 1 || cfg->model_kind > 3) return fail(DFB_ERR_UNSUPPORTED, "model_kind %d", cfg->model_kind);
+    if (cfg->model_kind == 1 && (cfg->emb_hidden != cfg->df_hidden || cfg->emb_hidden != cfg->nb_erb / 4 * kCh || cfg->conv_kt != 2 ||
+                                 cfg->inp_kt != 2 || cfg->df_order != 5))
+        return fail(DFB_ERR_UNSUPPORTED, "DeepFilterNet v1: only the shipped topology is built (hidden = conv_ch * nb_erb / 4, kt 2, order 5)");
     if (cfg->conv_kt < 1 || cfg->conv_kt > 2 || cfg->inp_kt < 1 || cfg->inp_kt > 3)
         return fail(DFB_ERR_UNSUPPORTED, "conv kernel time taps (%d, %d) unsupported", cfg->conv_kt, cfg->inp_kt);
     if ((cfg->emb_hidden != 256 && cfg->emb_hidden != 512) || (cfg->df_hidden != 256 && cfg->df_hidden != 512))
@@ -1091,8 +1152,38 @@ struct FwdBufs {
     unsigned short *c1_hi, *c1_lo, *embin_hi, *embin_lo, *gb_hi, *gb_lo, *emb_hi, *emb_lo, *dfc_hi, *dfc_lo;
 };
 
+// DeepFilterNet v1 (forward_v1)
+struct FwdBufsV1 {
+    float *e0, *e1, *e2, *e3, *c0, *c1, *c1g, *cemb, *emb, *xproj, *xproj2, *y[3], *embo, *dec_old, *dec, *p3, *p2, *p1, *p0, *d3, *d2, *d1,
+        *z[2], *dfc;
+    unsigned short *emb_hi, *emb_lo, *y_hi[3], *y_lo[3], *embo_hi, *embo_lo, *z_hi[2], *z_lo[2], *dfc_hi, *dfc_lo, *scr_hi, *scr_lo;
+};
+static size_t fwd_plan_v1(const dfb_model_config &c, size_t M, Arena *a, FwdBufsV1 *f) {
+    const int E = c.nb_erb, Fd = c.nb_df, H = c.emb_hidden;
+    size_t bytes = 0;
+    auto take = [&](size_t n) -> float * {
+        bytes += (n * 4 + 255) & ~size_t(255);
+        return a ? a->take<float>(n) : nullptr;
+    };
+    auto take16 = [&](size_t n) { return reinterpret_cast<unsigned short *>(take((n + 1) / 2)); };
+    FwdBufsV1 t{};
+    t.e0 = take(M * E * kCh); t.e1 = take(M * (E / 2) * kCh); t.e2 = take(M * (E / 4) * kCh); t.e3 = take(M * (E / 4) * kCh);
+    t.c0 = take(M * Fd * kCh); t.c1 = take(M * (Fd / 2) * kCh); t.c1g = take(M * (Fd / 2) * kCh);
+    t.cemb = take(M * H); t.emb = take(M * H); t.xproj = take(M * 3 * H); t.xproj2 = take(M * 3 * H);
+    for (int i = 0; i < 3; i++) { t.y[i] = take(M * H); t.y_hi[i] = take16(M * H); t.y_lo[i] = take16(M * H); }
+    for (int i = 0; i < 2; i++) { t.z[i] = take(M * H); t.z_hi[i] = take16(M * H); t.z_lo[i] = take16(M * H); }
+    t.embo = take(M * H); t.dec_old = take(M * H); t.dec = take(M * H); t.dfc = take(M * H);
+    t.p3 = take(M * (E / 4) * kCh); t.p2 = take(M * (E / 4) * kCh); t.p1 = take(M * (E / 2) * kCh); t.p0 = take(M * E * kCh);
+    t.d3 = take(M * (E / 4) * kCh); t.d2 = take(M * (E / 2) * kCh); t.d1 = take(M * E * kCh);
+    t.emb_hi = take16(M * H); t.emb_lo = take16(M * H); t.embo_hi = take16(M * H); t.embo_lo = take16(M * H);
+    t.dfc_hi = take16(M * H); t.dfc_lo = take16(M * H); t.scr_hi = take16(M * H); t.scr_lo = take16(M * H);
+    if (f) *f = t;
+    return bytes + 4096;
+}
+
 // Carves the activations of `M` frames out of `a` (or only counts bytes when a == nullptr).
 static size_t fwd_plan(const dfb_model_config &c, size_t M, Arena *a, FwdBufs *f) {
+    if (c.model_kind == 1 && !a) return fwd_plan_v1(c, M, nullptr, nullptr);
     const int E = c.nb_erb, Fd = c.nb_df, H = c.emb_hidden, Hd = c.df_hidden;
     const int ED = E / 4 * kCh;
     const int emb_in_dim = c.enc_concat ? 2 * ED : ED;
@@ -1165,9 +1256,14 @@ extern "C" int dfb_model_forward(dfb_model *m, const float *d_feat_erb, const fl
 static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
                         float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in, ChunkCtx *cx);
 
+static int forward_v1(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
+                      float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in, ChunkCtx *cx);
+
 static int forward_impl(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
                         float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in, ChunkCtx *cx) {
-    const int rc = forward_body(m, arena, d_feat_erb, d_feat_spec, B, T, d_m, d_coefs, d_lsnr, d_alpha, s_in, cx);
+    const int rc = m->cfg.model_kind == 1
+        ? forward_v1(m, arena, d_feat_erb, d_feat_spec, B, T, d_m, d_coefs, d_lsnr, d_alpha, s_in, cx)
+        : forward_body(m, arena, d_feat_erb, d_feat_spec, B, T, d_m, d_coefs, d_lsnr, d_alpha, s_in, cx);
     // an early return may leave work on the forked internal streams un-joined while the caller goes on to reuse
     // the arena: drain the device before handing the error back (error path only)
     if (rc) cudaDeviceSynchronize();
@@ -1264,7 +1360,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
         dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
         int smem = (kInFrames + c.inp_kt - 1) * (E + 2) * 4;
         DFB_PROF("k_conv_in[erb_conv0]", s);
-        k_conv_in<1><<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead, Tsx, Tx);
+        k_conv_in<1><<<grid, 256, smem, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, c.conv_lookahead, Tsx, Tx, 0);
         DFB_LAUNCH_CHECK();
     }
     const float *pw_sw = nullptr;  // set by blk(): swizzled BF16 hi | lo image of the [C_out][C_in] 1x1 weights (tensor-core path)
@@ -1296,7 +1392,7 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
             dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
             int smem = (kInFrames + c.inp_kt - 1) * (Fd + 2) * 2 * 4;
             DFB_PROF("k_conv_in[df_conv0]", sa);
-            k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead, Tsx, Tx);
+            k_conv_in<2><<<grid, 256, smem, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead, Tsx, Tx, 0);
             DFB_LAUNCH_CHECK();
             DFB_CUDA(cudaEventRecord(L.ev_c0, sa));
         }
@@ -1496,6 +1592,219 @@ static int forward_body(dfb_model *m, Arena &arena, const float *d_feat_erb, con
     return finish();
 }
 
+// ------------------------------------------------------------------ DeepFilterNet v1 ----
+// deepfilternet.py:64-279.  Same kernels as the other models where the layer shapes coincide (input convs, separable conv
+// blocks, GRU recurrence + projections, mask head); what differs is expressed around them:
+//   * convkxf pads (k - 1 - lookahead, lookahead) frames inside the conv (modules.py:151-154): k_conv_in with tp_min =
+//     -lookahead, the depthwise prologue with p.lookahead
+//   * pathway convs are full 1x1 convs (depthwise 1x1 + 1x1 + BN + ReLU): the separable kernel with a one-tap depthwise
+//   * decoder transposed convs have two time taps (reversed on upload)
+//   * GroupedLinear (bias, shuffle) / GroupedGRU (G = 8, shuffle between layers, add_outputs): FFMA grouped linear with bias;
+//     every GroupedGRULayer runs as ONE dense H-wide recurrence with block-diagonal weights (the shuffle of its input folded
+//     into W_ih), the re-orderings and the sum of layer outputs are k_gather_sum passes
+//   * df_fc_out is a dense H -> nb_df * 2 O linear (BF16x3 GEMM), tanh and the 1x1 pathway conv are added by k_convp_v1
+//   * DfOp blends the deep-filtered DF bins with the masked spectrum by alpha (apply kernel)
+// One window = the whole signal (pick_chunk): the in-conv look-ahead makes the zero padding at the END of the signal part of
+// every layer, which a window that stops short of it cannot reproduce.
+static int forward_v1(dfb_model *m, Arena &arena, const float *d_feat_erb, const float *d_feat_spec, int B, int T,
+                      float *d_m, float *d_coefs, float *d_lsnr, float *d_alpha, cudaStream_t s_in, ChunkCtx *cx) {
+    const dfb_model_config &c = m->cfg;
+    if (cx && (cx->Rc != 0 || cx->have_state)) return fail(DFB_ERR_UNSUPPORTED, "DeepFilterNet v1 runs as one window per signal");
+    const int Tsx = cx ? cx->Tsx : T, Tx = cx ? cx->Tx : T;
+    static const bool serial = getenv("DFB_SERIAL") && atoi(getenv("DFB_SERIAL"));
+    dfb_model::Lane &L = m->lanes[cx ? cx->lane : 0];
+    cudaStream_t s = serial ? s_in : L.hi, sa = serial ? s_in : L.aux;
+    if (!serial) {
+        DFB_CUDA(cudaEventRecord(L.ev_in, s_in));
+        DFB_CUDA(cudaStreamWaitEvent(s, L.ev_in, 0));
+    }
+    const int64_t M = (int64_t)B * T;
+    const int E = c.nb_erb, Fd = c.nb_df, H = c.emb_hidden, O2 = 2 * c.df_order, kt = c.conv_kt;
+    int rc;
+    FwdBufsV1 f{};
+    fwd_plan_v1(c, (size_t)M, &arena, &f);
+    if (!f.scr_lo) return fail(DFB_ERR_OOM, "forward workspace exhausted for %lld frames", (long long)M);
+    m->dbg.clear();
+    m->dbg["e0"] = {f.e0, M * E * kCh}; m->dbg["e1"] = {f.e1, M * (E / 2) * kCh}; m->dbg["e2"] = {f.e2, M * (E / 4) * kCh};
+    m->dbg["e3"] = {f.e3, M * (E / 4) * kCh}; m->dbg["c0"] = {f.c0, M * Fd * kCh}; m->dbg["c1"] = {f.c1, M * (Fd / 2) * kCh};
+    m->dbg["cemb"] = {f.cemb, M * H}; m->dbg["emb_in"] = {f.emb, M * H}; m->dbg["emb"] = {f.embo, M * H};
+    m->dbg["dec_emb"] = {f.dec, M * H}; m->dbg["d3"] = {f.d3, M * (E / 4) * kCh}; m->dbg["d2"] = {f.d2, M * (E / 2) * kCh};
+    m->dbg["d1"] = {f.d1, M * E * kCh}; m->dbg["dfc"] = {f.dfc, M * H}; m->dbg["y0"] = {f.y[0], M * H};
+    const bool tc = m->conv_tc != 0;
+    const float *ones, *zeros;
+    if ((rc = need(m, "v1.ones", kCh, &ones)) || (rc = need(m, "v1.zeros", kCh, &zeros))) return rc;
+    auto table = [&](const char *name, int n, const int **out) -> int {
+        const float *t;
+        int r = need(m, name, n, &t);
+        *out = reinterpret_cast<const int *>(t);
+        return r;
+    };
+    const int *idx_c1, *idx_e3, *idx_shuf, *idx_id, *idx_dec, *idx_gshuf;
+    if ((rc = table("v1.idx_c1", Fd / 2 * kCh, &idx_c1)) || (rc = table("v1.idx_e3", H, &idx_e3)) || (rc = table("v1.idx_shuf", H, &idx_shuf)) ||
+        (rc = table("v1.idx_id", H, &idx_id)) || (rc = table("v1.idx_dec", H, &idx_dec)) || (rc = table("v1.idx_gshuf", H, &idx_gshuf)))
+        return rc;
+    auto gather = [&](cudaStream_t st, int n, const float *const *src, const int64_t *ld, const int *const *idx, int K, int relu,
+                      float *out, unsigned short *hi, unsigned short *lo) -> int {
+        GatherParams g{};
+        for (int i = 0; i < n; i++) { g.src[i] = src[i]; g.ld[i] = ld[i]; g.idx[i] = idx[i]; }
+        g.n = n; g.out = out; g.ldo = K; g.hi = hi; g.lo = lo; g.ldp = K; g.K = K; g.relu = relu;
+        DFB_PROF("k_gather_sum", st);
+        k_gather_sum<<<(unsigned)M, 256, 0, st>>>(g);
+        DFB_LAUNCH_CHECK();
+        return DFB_OK;
+    };
+    // separable block `name`: depthwise (kt x 3, look-ahead la) -> 1x1 -> BN -> ReLU, input = in (+ path)
+    auto block = [&](cudaStream_t st, const char *name, int mode, const float *in, int Fin, float *out, int Fout, int bkt, int la,
+                     const float *path) -> int {
+        DwPwParams p{};
+        std::string n(name);
+        int r;
+        if ((r = need(m, (n + ".dw").c_str(), bkt * 3 * kCh, &p.dw)) || (r = need(m, (n + ".pw").c_str(), kCh * kCh, &p.pw)) ||
+            (r = need(m, (n + ".b").c_str(), kCh, &p.bias)))
+            return r;
+        p.in = in; p.Fin = Fin; p.in_fs = (int64_t)Fin * kCh; p.out = out; p.Fout = Fout; p.out_fs = (int64_t)Fout * kCh; p.kt = bkt; p.T = T;
+        p.lookahead = la;
+        if (path) { p.path = path; p.path_fs = p.in_fs; p.ps = ones; p.pb = zeros; }   // the pathway tensor is already >= 0
+        // tensor-core version where it is built: no look-ahead, transposed blocks with one time tap only
+        const float *w_sw = nullptr;
+        if (tc && la == 0 && !(mode == DW_T2 && bkt != 1) && (r = need(m, (n + ".pw_sw").c_str(), kCh * kCh, &w_sw))) return r;
+        if (mode == DW_S1) return run_dwpw<DW_S1>(st, p, B, w_sw);
+        if (mode == DW_S2) return run_dwpw<DW_S2>(st, p, B, w_sw);
+        return run_dwpw<DW_T2>(st, p, B, w_sw);
+    };
+    // ---- encoder, deepfilternet.py:122-141
+    DFB_CUDA(cudaEventRecord(L.ev_fork_enc, s));
+    DFB_CUDA(cudaStreamWaitEvent(sa, L.ev_fork_enc, 0));
+    {
+        const float *w, *bb;
+        if ((rc = need(m, "enc.erb_conv0.w", c.inp_kt * 3 * kCh, &w)) || (rc = need(m, "enc.erb_conv0.b", kCh, &bb))) return rc;
+        dim3 grid((unsigned)((T + kInFrames - 1) / kInFrames), (unsigned)B);
+        const int la = c.conv_lookahead > 0 ? 1 : 0;
+        {
+            DFB_PROF("k_conv_in[erb_conv0]", s);
+            k_conv_in<1><<<grid, 256, (kInFrames + c.inp_kt - 1) * (E + 2) * 4, s>>>(d_feat_erb, w, bb, f.e0, T, E, c.inp_kt, la, Tsx, Tx, -la);
+            DFB_LAUNCH_CHECK();
+        }
+        if ((rc = need(m, "enc.df_conv0.w", c.inp_kt * 3 * 2 * kCh, &w)) || (rc = need(m, "enc.df_conv0.b", kCh, &bb))) return rc;
+        DFB_PROF("k_conv_in[df_conv0]", sa);
+        k_conv_in<2><<<grid, 256, (kInFrames + c.inp_kt - 1) * (Fd + 2) * 2 * 4, sa>>>(d_feat_spec, w, bb, f.c0, T, Fd, c.inp_kt, c.conv_lookahead,
+                                                                                      Tsx, Tx, -c.conv_lookahead);
+        DFB_LAUNCH_CHECK();
+    }
+    if ((rc = block(sa, "enc.df_conv1", DW_S2, f.c0, Fd, f.c1, Fd / 2, kt, 0, nullptr))) return rc;
+    {   // cemb = df_fc_emb(c1 channel-major), pre-shuffle order
+        const float *src[1] = {f.c1}; const int64_t ld[1] = {(int64_t)Fd / 2 * kCh}; const int *ix[1] = {idx_c1};
+        if ((rc = gather(sa, 1, src, ld, ix, Fd / 2 * kCh, 0, f.c1g, nullptr, nullptr))) return rc;
+        const float *w, *bb;
+        const int I = Fd / 2 * kCh;
+        if ((rc = need(m, "enc.df_fc_emb.gl", (int64_t)I * H / c.g_df_fc_emb, &w)) || (rc = need(m, "enc.df_fc_emb.bias", H, &bb))) return rc;
+        if ((rc = run_gl(sa, f.c1g, I, w, bb, nullptr, 0, f.cemb, H, M, c.g_df_fc_emb, I, H, ACT_NONE))) return rc;
+    }
+    DFB_CUDA(cudaEventRecord(L.ev_join_enc, sa));
+    if ((rc = block(s, "enc.erb_conv1", DW_S2, f.e0, E, f.e1, E / 2, kt, c.conv_lookahead > 1 ? 1 : 0, nullptr)) ||
+        (rc = block(s, "enc.erb_conv2", DW_S2, f.e1, E / 2, f.e2, E / 4, kt, c.conv_lookahead > 2 ? 1 : 0, nullptr)) ||
+        (rc = block(s, "enc.erb_conv3", DW_S1, f.e2, E / 4, f.e3, E / 4, kt, 0, nullptr)))
+        return rc;
+    DFB_CUDA(cudaStreamWaitEvent(s, L.ev_join_enc, 0));
+    {   // emb = e3 (channel-major flatten) + shuffle(cemb)
+        const float *src[2] = {f.e3, f.cemb}; const int64_t ld[2] = {H, H}; const int *ix[2] = {idx_e3, idx_shuf};
+        if ((rc = gather(s, 2, src, ld, ix, H, 0, f.emb, f.emb_hi, f.emb_lo))) return rc;
+    }
+    // GroupedGRU: layer l as a dense recurrence, out = sum_l shuffle(y_l) (l < last) + y_last
+    auto ggru = [&](cudaStream_t st, const char *name, int layers, const float *x, unsigned short *x_hi, unsigned short *x_lo, float **y,
+                    unsigned short **y_hi, unsigned short **y_lo, float *xproj, float *hbase, float *out, unsigned short *out_hi,
+                    unsigned short *out_lo) -> int {
+        const float *cur = x;
+        unsigned short *ch = x_hi, *cl = x_lo;
+        for (int l = 0; l < layers; l++) {
+            const std::string nm = std::string(name) + ".g" + std::to_string(l);
+            GruChunk ck{hbase ? hbase + (int64_t)l * B * H : nullptr, false, 0};
+            bool ok = false;
+            int r = run_gru(m, st, nm.c_str(), 1, H, cur, H, nullptr, y[l], xproj, nullptr, B, T, ch, cl, f.scr_hi, f.scr_lo, 0, y_hi[l], y_lo[l], &ok,
+                            hbase ? &ck : nullptr);
+            if (r) return r;
+            cur = y[l]; ch = y_hi[l]; cl = y_lo[l];
+        }
+        const float *src[3]; int64_t ld[3]; const int *ix[3];
+        for (int l = 0; l < layers; l++) { src[l] = y[l]; ld[l] = H; ix[l] = l == layers - 1 ? idx_id : idx_gshuf; }
+        return gather(st, layers, src, ld, ix, H, 0, out, out_hi, out_lo);
+    };
+    if (c.enc_gru_layers > 3 || c.df_gru_layers > 2) return fail(DFB_ERR_UNSUPPORTED, "DeepFilterNet v1: more GRU layers than built (3 / 2)");
+    if ((rc = ggru(s, "enc.emb_gru", c.enc_gru_layers, f.emb, f.emb_hi, f.emb_lo, f.y, f.y_hi, f.y_lo, f.xproj, cx ? cx->h_enc : nullptr, f.embo,
+                   f.embo_hi, f.embo_lo)))
+        return rc;
+    if (d_lsnr) {
+        const float *lw, *lb;
+        if ((rc = need(m, "enc.lsnr.w", H, &lw)) || (rc = need(m, "enc.lsnr.b", 1, &lb))) return rc;
+        if ((rc = run_gl(s, f.embo, H, lw, lb, nullptr, 0, d_lsnr, 1, M, 1, H, 1, ACT_SIGMOID, c.lsnr_scale, c.lsnr_offset))) return rc;
+    }
+    DFB_CUDA(cudaEventRecord(L.ev_fork, s));
+    if (!serial) { s = L.dhi; sa = L.daux; DFB_CUDA(cudaStreamWaitEvent(s, L.ev_fork, 0)); }
+    DFB_CUDA(cudaStreamWaitEvent(sa, L.ev_fork, 0));
+    // ---- DF decoder, deepfilternet.py:219-229 (auxiliary stream)
+    {
+        if ((rc = ggru(sa, "df_dec.df_gru", c.df_gru_layers, f.embo, f.embo_hi, f.embo_lo, f.z, f.z_hi, f.z_lo, f.xproj2, cx ? cx->h_df : nullptr, f.dfc,
+                       f.dfc_hi, f.dfc_lo)))
+            return rc;
+        if (d_alpha) {
+            const float *aw, *ab;
+            if ((rc = need(m, "df_dec.df_fc_a.w", H, &aw)) || (rc = need(m, "df_dec.df_fc_a.b", 1, &ab))) return rc;
+            if ((rc = run_gl(sa, f.dfc, H, aw, ab, nullptr, 0, d_alpha, 1, M, 1, H, 1, ACT_SIGMOID))) return rc;
+        }
+        const float *w_t, *bb, *w_hi, *w_lo;
+        const int N = Fd * O2;
+        if ((rc = need(m, "df_dec.df_fc_out.w_t", (int64_t)H * N, &w_t)) || (rc = need(m, "df_dec.df_fc_out.b", N, &bb))) return rc;
+        rc = DFB_ERR_UNSUPPORTED;
+        if (m->proj_tc && m->get("df_dec.df_fc_out.w_hi")) {
+            if ((rc = need(m, "df_dec.df_fc_out.w_hi", (int64_t)H * N / 2, &w_hi)) || (rc = need(m, "df_dec.df_fc_out.w_lo", (int64_t)H * N / 2, &w_lo))) return rc;
+            rc = launch_gemm_bf16x3(sa, f.dfc_hi, f.dfc_lo, H, w_hi, w_lo, bb, d_coefs, N, M, N, H);
+        }
+        if (rc == DFB_ERR_UNSUPPORTED) rc = run_gl(sa, f.dfc, H, w_t, bb, nullptr, 0, d_coefs, N, M, 1, H, N, ACT_NONE);
+        if (rc) return rc;
+        const float *pw, *pb;
+        if ((rc = need(m, "df_dec.df_convp.w", kCh * O2, &pw)) || (rc = need(m, "df_dec.df_convp.b", O2, &pb))) return rc;
+        const long long rows = (long long)M * Fd;
+        DFB_PROF("k_convp_v1", sa);
+        k_convp_v1<10><<<(unsigned)((rows + 127) / 128), 128, 0, sa>>>(f.c0, pw, pb, d_coefs, rows);
+        DFB_LAUNCH_CHECK();
+    }
+    DFB_CUDA(cudaEventRecord(L.ev_join, sa));
+    // ---- ERB decoder, deepfilternet.py:179-189
+    {
+        const float *w, *bb;
+        if ((rc = need(m, "erb_dec.fc_emb.gl", (int64_t)H * H / c.g_erb_in, &w)) || (rc = need(m, "erb_dec.fc_emb.bias", H, &bb))) return rc;
+        if ((rc = run_gl(s, f.embo, H, w, bb, nullptr, 0, f.dec_old, H, M, c.g_erb_in, H, H, ACT_RELU))) return rc;
+        const float *src[1] = {f.dec_old}; const int64_t ld[1] = {H}; const int *ix[1] = {idx_dec};
+        if ((rc = gather(s, 1, src, ld, ix, H, 0, f.dec, nullptr, nullptr))) return rc;
+        if ((rc = block(s, "erb_dec.conv3p", DW_S1, f.e3, E / 4, f.p3, E / 4, 1, 0, nullptr)) ||
+            (rc = block(s, "erb_dec.conv2p", DW_S1, f.e2, E / 4, f.p2, E / 4, 1, 0, nullptr)) ||
+            (rc = block(s, "erb_dec.conv1p", DW_S1, f.e1, E / 2, f.p1, E / 2, 1, 0, nullptr)) ||
+            (rc = block(s, "erb_dec.conv0p", DW_S1, f.e0, E, f.p0, E, 1, 0, nullptr)))
+            return rc;
+        if ((rc = block(s, "erb_dec.convt3", DW_S1, f.dec, E / 4, f.d3, E / 4, kt, 0, f.p3)) ||
+            (rc = block(s, "erb_dec.convt2", DW_T2, f.d3, E / 4, f.d2, E / 2, kt, 0, f.p2)) ||
+            (rc = block(s, "erb_dec.convt1", DW_T2, f.d2, E / 2, f.d1, E, kt, 0, f.p1)))
+            return rc;
+        if ((rc = need(m, "erb_dec.conv0_out.w", kt * 3 * kCh, &w)) || (rc = need(m, "erb_dec.conv0_out.b", 1, &bb))) return rc;
+        static PerDeviceOnce attr_once;
+        const int smem = (kMaskWarps * 2 * (E + 2) * kMaskLd + kt * 3 * kCh) * 4;
+        if (auto once_guard = attr_once.first()) {
+            DFB_CUDA(cudaFuncSetAttribute(k_mask_out, cudaFuncAttributeMaxDynamicSharedMemorySize, (kMaskWarps * 2 * (64 + 2) * kMaskLd + 2 * 3 * kCh) * 4));
+        }
+        const int per_cta = kMaskWarps * kMaskChunk;
+        dim3 grid((unsigned)((T + per_cta - 1) / per_cta), (unsigned)B);
+        DFB_PROF("k_mask_out", s);
+        k_mask_out<<<grid, 32 * kMaskWarps, smem, s>>>(f.p0, f.d1, ones, zeros, w, bb, d_m, T, E, kt);
+        DFB_LAUNCH_CHECK();
+    }
+    DFB_CUDA(cudaStreamWaitEvent(s, L.ev_join, 0));
+    if (!serial) {
+        DFB_CUDA(cudaEventRecord(L.ev_out, s));
+        DFB_CUDA(cudaStreamWaitEvent(s_in, L.ev_out, 0));
+    }
+    return DFB_OK;
+}
+
 // Chunk pipeline of dfb_enhance / dfb_enhance_host: signals of at least 64 * chunks frames are cut into >= `chunks` time
 // chunks (device-pointer / host-pointer entry point); lanes = 2 overlaps the encoder phase of chunk c + 1 with the decoder
 // phase of chunk c, lanes = 1 runs the chunks back to back.  Defaults auto / 4 / 2 (DFB_DEVICE_CHUNKS, DFB_HOST_CHUNKS,
@@ -1519,7 +1828,7 @@ static int check_state(const dfb_model *m, const dfb_state *st) {
     return DFB_OK;
 }
 
-static int apply_mode(const dfb_model *m) { return m->cfg.model_kind == 2 ? 2 : 1; }
+static int apply_mode(const dfb_model *m) { return m->cfg.model_kind == 3 ? 1 : 2; }   // v1 / v2 filter the masked spectrum
 static void apply_options(const dfb_model *m, dfb::ApplyParams &p) {
     p.pf = m->post_filter; p.pf_beta = m->pf_beta; p.mask_only = m->mask_only;
 }
@@ -1535,14 +1844,23 @@ extern "C" int dfb_model_set_options(dfb_model *m, int post_filter, float pf_bet
     return DFB_OK;
 }
 
+static int apply_impl(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_m, const float *d_coefs, const float *d_alpha,
+                      int64_t B, int64_t T, float *d_spec_e, void *stream);
 extern "C" int dfb_apply(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_m, const float *d_coefs,
                          int64_t B, int64_t T, float *d_spec_e, void *stream) {
+    if (m && m->cfg.model_kind == 1 && !m->mask_only)
+        return fail(DFB_ERR_UNSUPPORTED, "DeepFilterNet v1 blends with df_alpha: use dfb_model_forward_full / dfb_enhance");
+    return apply_impl(m, st, d_spec, d_m, d_coefs, nullptr, B, T, d_spec_e, stream);
+}
+static int apply_impl(dfb_model *m, dfb_state *st, const float *d_spec, const float *d_m, const float *d_coefs, const float *d_alpha,
+                      int64_t B, int64_t T, float *d_spec_e, void *stream) {
     if (!m || !st || !d_spec || !d_m || !d_coefs || !d_spec_e) return fail(DFB_ERR_INVALID, "null argument");
     if (int rcs = check_state(m, st)) return rcs;
     DFB_CUDA(cudaSetDevice(m->device));
     dfb::ApplyParams p{};
     p.spec = (const float2 *)d_spec; p.m = d_m; p.coefs = d_coefs; p.audio = nullptr; p.spec_out = (float2 *)d_spec_e;
     p.Tf = (int)T; p.mode = apply_mode(m); p.nb_df = m->cfg.nb_df; p.order = m->cfg.df_order; p.lookahead = m->cfg.df_lookahead;
+    p.alpha = d_alpha;
     apply_options(m, p);
     return launch_apply_synthesis(st, p, B, (cudaStream_t)stream);
 }
@@ -1557,15 +1875,17 @@ extern "C" int dfb_model_forward_full(dfb_model *m, dfb_state *st, const float *
     const int O2 = 2 * m->cfg.df_order;
     if (B <= 0 || T <= 0) return DFB_OK;
     if (B > 65535) return fail(DFB_ERR_INVALID, "more than 65535 streams per call");
-    size_t extra = ((size_t)M * m->cfg.nb_erb + (size_t)M * m->cfg.nb_df * O2) * 4 + 4096;
+    size_t extra = ((size_t)M * m->cfg.nb_erb + (size_t)M * m->cfg.nb_df * O2 + (size_t)M) * 4 + 8192;
     int rc = m->arena.reserve(fwd_plan(m->cfg, (size_t)M, nullptr, nullptr) + extra);
     if (rc) return rc;
     m->arena.reset();
     float *mm = d_m ? d_m : m->arena.take<float>((size_t)M * m->cfg.nb_erb);
     float *cc = d_coefs ? d_coefs : m->arena.take<float>((size_t)M * m->cfg.nb_df * O2);
-    rc = forward_impl(m, m->arena, d_feat_erb, d_feat_spec, (int)B, (int)T, mm, cc, d_lsnr, d_alpha, (cudaStream_t)stream);
+    float *aa = d_alpha;
+    if (!aa && m->cfg.model_kind == 1) aa = m->arena.take<float>((size_t)M);
+    rc = forward_impl(m, m->arena, d_feat_erb, d_feat_spec, (int)B, (int)T, mm, cc, d_lsnr, aa, (cudaStream_t)stream);
     if (rc) { m->arena.reset(); return rc; }
-    rc = dfb_apply(m, st, d_spec, mm, cc, B, T, d_spec_e, stream);
+    rc = apply_impl(m, st, d_spec, mm, cc, m->cfg.model_kind == 1 ? aa : nullptr, B, T, d_spec_e, stream);
     m->arena.reset();
     return rc;
 }
@@ -1614,7 +1934,7 @@ static ChunkGeom chunk_geom(const dfb_model_config &c) {
     g.Lmax = c.conv_lookahead > c.df_lookahead ? c.conv_lookahead : c.df_lookahead;
     // DeepFilterNet2 filters the MASKED spectrum: frame t needs the masks of frames <= t + df_lookahead, so its audio
     // trails the DNN frames by df_lookahead (deepfilternet2.py:494-503)
-    g.lag = c.model_kind == 2 ? c.df_lookahead : 0;
+    g.lag = c.model_kind != 3 ? c.df_lookahead : 0;
     g.Hf = kHalo + g.Lmax;
     return g;
 }
@@ -1660,7 +1980,7 @@ static int load_tail(cudaStream_t s, float *buf, int T, size_t fe, int n, const 
 static size_t chunk_bytes_per_stream(const dfb_model_config &c, const dfb_state *st, int Tw) {
     const ChunkGeom g = chunk_geom(c);
     const int E = c.nb_erb, Fd = c.nb_df, O2 = 2 * c.df_order, F = st->tb.F;
-    return (size_t)(Tw + g.Lmax) * (2 * F + E + 2 * Fd) * 4 + (size_t)Tw * (E + (size_t)Fd * O2) * 4 + fwd_plan(c, (size_t)Tw, nullptr, nullptr) +
+    return (size_t)(Tw + g.Lmax) * (2 * F + E + 2 * Fd) * 4 + (size_t)Tw * (E + (size_t)Fd * O2 + 2) * 4 + fwd_plan(c, (size_t)Tw, nullptr, nullptr) +
            16384;
 }
 
@@ -1705,7 +2025,8 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
     float *mm = arena.take<float>((size_t)B * (Tw + 1) * E);
     float *cc = arena.take<float>((size_t)B * (Tw + 1) * Fd * O2);
     float *ll = io.lsnr_th ? arena.take<float>((size_t)B * (Tw + 1)) : nullptr;
-    if (!cc) return fail(DFB_ERR_OOM, "chunk workspace exhausted");
+    float *aa = c.model_kind == 1 ? arena.take<float>((size_t)B * (Tw + 1)) : nullptr;   // df_alpha (v1)
+    if (!cc || (c.model_kind == 1 && !aa)) return fail(DFB_ERR_OOM, "chunk workspace exhausted");
     // ---- features: carried history, then the new frames
     if ((rc = load_tail(s, spec, Tsb, (size_t)2 * F, n_hist, S.t_spec, g.Hf, 0, B)) || (rc = load_tail(s, fe, Tsb, E, n_hist, S.t_fe, g.Hf, 0, B)) ||
         (rc = load_tail(s, fs, Tsb, (size_t)2 * Fd, n_hist, S.t_fs, g.Hf, 0, B)))
@@ -1733,7 +2054,7 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
     if (run_dnn) {
     ChunkCtx cx{Rc, Tsb, Tv, S.h_enc, S.h_erb, S.h_df, S.dnn_started, c.conv_kt > 1 ? S.t_dec : nullptr, S.n_dec, lane,
                 have_prev ? P.ev_done : nullptr};
-    if ((rc = forward_impl(m, arena, fe, fs, B, Tw, mm, cc, ll, nullptr, s, &cx))) return rc;
+    if ((rc = forward_impl(m, arena, fe, fs, B, Tw, mm, cc, ll, aa, s, &cx))) return rc;
     S.n_dec = cx.dec_tail_n;
     S.dnn_started = true;
     // the halo rows of m / coefs come from skipped recurrences: restore the last finished frames from the previous chunk
@@ -1754,6 +2075,7 @@ static int run_chunk(dfb_model *m, dfb_state *st, StreamState &S, const ChunkIO 
         p.Tf = (int)(e1n - W0); p.spec_T = Tsb; p.Tv = Tv; p.mc_T = Tw; p.t_first = (int)(S.e1 - W0);
         p.mode = apply_mode(m); p.nb_df = Fd; p.order = c.df_order; p.lookahead = c.df_lookahead;
         p.atten_lim = io.atten_lim;
+        p.alpha = aa;
         apply_options(m, p);
         if (ll) { p.lsnr = ll; p.th_min = io.lsnr_th[0]; p.th_erb = io.lsnr_th[1]; p.th_df = io.lsnr_th[2]; }
         if ((rc = launch_apply_synthesis(st, p, B, s))) return rc;
@@ -1788,6 +2110,7 @@ static int pick_chunk(const dfb_model *m, const dfb_state *st, int64_t B, int64_
         const int64_t t2 = (Tf + min_chunks - 1) / min_chunks;
         if (t2 < tc) tc = t2;
     }
+    if (m->cfg.model_kind == 1) return tw >= Tf ? (int)Tf : 0;   // DeepFilterNet v1: one window per signal (forward_v1)
     if (tc < 1) return 0;
     if (tc < Tf && tc < 32) return 0;   // a chunk this short wastes most of its window on the halo: use stream groups
     return (int)tc;
@@ -2025,6 +2348,8 @@ extern "C" int dfb_stream_create(dfb_stream **out, dfb_model *m, dfb_state *st, 
     if (!out || !m || !st || B <= 0 || B > 65535) return fail(DFB_ERR_INVALID, "bad argument");
     *out = nullptr;
     if (int rcs = check_state(m, st)) return rcs;
+    if (m->cfg.model_kind == 1)
+        return fail(DFB_ERR_UNSUPPORTED, "DeepFilterNet v1 runs as one window per signal (forward_v1): no frame-incremental API");
     DFB_CUDA(cudaSetDevice(m->device));
     dfb_stream *h = new dfb_stream();
     h->m = m; h->st = st; h->B = (int)B;
@@ -2060,7 +2385,7 @@ extern "C" int dfb_stream_reset(dfb_stream *h) {
 extern "C" int dfb_stream_set_lsnr_thresholds(dfb_stream *h, int enable, float min_db_thresh, float max_db_erb_thresh,
                                               float max_db_df_thresh) {
     if (!h) return fail(DFB_ERR_INVALID, "null stream");
-    if (enable && h->m->cfg.model_kind == 2) return fail(DFB_ERR_UNSUPPORTED, "LSNR stage gating: DeepFilterNet3 topologies only");
+    if (enable && h->m->cfg.model_kind != 3) return fail(DFB_ERR_UNSUPPORTED, "LSNR stage gating: DeepFilterNet3 topologies only");
     h->gating = enable != 0;
     h->th[0] = min_db_thresh; h->th[1] = max_db_erb_thresh; h->th[2] = max_db_df_thresh;
     return DFB_OK;

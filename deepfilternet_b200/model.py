@@ -1,4 +1,4 @@
-"""Host-side mirror of the reference's ``DfNet`` (deepfilternet3.py:334-456, deepfilternet2.py:374-505).
+"""Host-side mirror of the reference's ``DfNet`` (deepfilternet3.py:334-456, deepfilternet2.py:374-505, deepfilternet.py:232-279).
 
 ``DfNet`` keeps the reference module's public surface -- ``forward(spec, feat_erb, feat_spec) ->
 (spec_e, m, lsnr, df_coefs | df_alpha)``, ``state_dict()``, ``eval()``, the attributes ``nb_df`` /
@@ -58,7 +58,7 @@ def load_state_dict_file(path: str) -> Dict[str, Tensor]:
 
 
 class DfNet(nn.Module):
-    """B200 drop-in for ``df.deepfilternet3.DfNet`` / ``df.deepfilternet2.DfNet``."""
+    """B200 drop-in for ``df.deepfilternet3.DfNet`` / ``df.deepfilternet2.DfNet`` / ``df.deepfilternet.DfNet``."""
 
     def __init__(self, cfg: ModelConfig, state_dict: Dict[str, Tensor], df_state: Optional[DF] = None,
                  device: Optional[int] = None, run_df: bool = True):
@@ -180,15 +180,16 @@ class DfNet(nn.Module):
         m = torch.empty((b, 1, t, e), device=dev, dtype=torch.float32)
         lsnr = torch.empty((b, t, 1), device=dev, dtype=torch.float32)
         coefs = torch.empty((b, t, fd, 2 * o), device=dev, dtype=torch.float32)
-        alpha = torch.empty((b, t, 1), device=dev, dtype=torch.float32) if self.cfg.model == "deepfilternet2" else None
+        has_alpha = self.cfg.model in ("deepfilternet", "deepfilternet2")   # deepfilternet.py:279, deepfilternet2.py:505
+        alpha = torch.empty((b, t, 1), device=dev, dtype=torch.float32) if has_alpha else None
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             check(_lib.lib().dfb_model_forward_full(
                 self._h, self.df_state.handle, sp.data_ptr(), fe.data_ptr(), fs.data_ptr(), b, t,
                 spec_e.data_ptr(), m.data_ptr(), lsnr.data_ptr(), coefs.data_ptr(),
                 alpha.data_ptr() if alpha is not None else None, stream))
-        if self.cfg.model == "deepfilternet2":
-            last = alpha
+        if has_alpha:
+            last = alpha if self.run_df else torch.zeros_like(alpha)   # deepfilternet.py:277-278
         else:  # DfOutputReshapeMF, deepfilternet3.py:268-275
             last = coefs.view(b, t, fd, o, 2).permute(0, 3, 1, 2, 4)
         outs = (spec_e, m, lsnr, last)

@@ -111,6 +111,8 @@ def gru_layers(sd, prefix: str) -> int:
 
 def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict[str, np.ndarray], dict]:
     """Returns (packed tensors, derived integer config for dfb_model_config)."""
+    if cfg.model == "deepfilternet":
+        return pack_state_dict_v1(sd, cfg)
     C = cfg.conv_ch
     out: Dict[str, np.ndarray] = {}
 
@@ -248,10 +250,264 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict
     return out, derived
 
 
+# ---------------------------------------------------------------------------------- DeepFilterNet v1 ----
+def shuffle_index(n: int, groups: int) -> np.ndarray:
+    """Group shuffle of modules.py:651-654 / :807-812 as a gather: shuffled[r] = x[idx[r]].  x index o = a * G + b is viewed
+    as [n / G][G] and transposed, so r = b * (n / G) + a."""
+    hs = n // groups
+    r = np.arange(n)
+    return ((r % hs) * groups + r // hs).astype(np.int32)
+
+
+def _i32(a) -> np.ndarray:
+    """int32 table in the fp32 container of the C ABI (bit pattern, like the BF16 planes)."""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32)).view(np.float32)
+
+
+def pack_state_dict_v1(sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Tuple[Dict[str, np.ndarray], dict]:
+    """DeepFilterNet v1 (deepfilternet.py:64-279; checkpoint keys with `clc` already renamed to `df`).
+
+    Device activations are channel-last [B,T,F,C]; the reference flattens channel-major ([C][F]) into its grouped linears
+    and GRUs and interleaves (`shuffle`) their outputs.  All of that is expressed with gather tables (v1.idx_*) consumed by
+    k_gather_sum, so every packed weight keeps the reference's index order, except:
+      enc.df_fc_emb.gl     [G][Ig][Hg], input index inside a group i' = f * (C / G) + c (rows gathered from [F][C])
+      <gru>.g{l}.l0.*      GroupedGRULayer l as ONE dense GRU of width H: block-diagonal W_ih / W_hh [3H][H] in torch gate order;
+                           layers l > 0 have the shuffle of their input folded into the columns of W_ih
+      df_dec.df_fc_out.w_t [H][Fd * 2 O] with output column f * 2 O + k (device coefs layout) from reference row k * Fd + f
+    """
+    C, E, Fd, O2 = cfg.conv_ch, cfg.nb_erb, cfg.nb_df, 2 * cfg.df_order
+    G, LG, H = cfg.gru_groups, cfg.lin_groups, cfg.emb_hidden_dim
+    out: Dict[str, np.ndarray] = {}
+
+    def f32(a):
+        return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+    def t64(k):
+        return _np(sd[k]).astype(np.float64)
+
+    def bn(p):
+        if p + ".norm.weight" not in sd:
+            return None, None
+        g_, b_ = t64(p + ".norm.weight"), t64(p + ".norm.bias")
+        scale = g_ / np.sqrt(t64(p + ".norm.running_var") + EPS)
+        return scale, b_ - t64(p + ".norm.running_mean") * scale
+
+    # erb_conv0: dense 1 -> C (k0 x 3) + BN
+    w = t64("enc.erb_conv0.sconv.weight")
+    s, b = bn("enc.erb_conv0")
+    inp_kt = w.shape[2]
+    out["enc.erb_conv0.w"] = f32((w[:, 0] * s[:, None, None]).transpose(1, 2, 0))
+    out["enc.erb_conv0.b"] = f32(b)
+
+    def dwpw(p: str, transposed: bool = False) -> int:
+        dw = t64(p + (".sconvt.weight" if transposed else ".sconv.weight"))   # [C,1,kt,kf] (Conv2d and ConvTranspose2d alike)
+        assert dw.shape[0] == C and dw.shape[1] == 1, (p, dw.shape)
+        if dw.shape[3] == 1:   # pathway convs: depthwise 1 x 1 = per-channel scale, as the centre tap of a 1 x 3 kernel
+            dw = np.concatenate([np.zeros_like(dw), dw, np.zeros_like(dw)], axis=3)
+        taps = dw[:, 0].transpose(1, 2, 0)                  # [kt][3][C]
+        if transposed:
+            # ConvTranspose2d over time with padding kt - 1 behind a (kt - 1)-frame front pad (modules.py:151-154,172-181):
+            # out[t] = sum_j w[j] x[t - j] -- the causal kernel with its time taps reversed
+            taps = taps[::-1]
+        pw = t64(p + ".1x1conv.weight")[:, :, 0, 0]         # [out][in]
+        s, b = bn(p)
+        out[p + ".dw"] = f32(taps)
+        out[p + ".pw"] = f32((pw * s[:, None]).T)
+        out[p + ".pw_nk"] = f32(pw * s[:, None])
+        out[p + ".pw_sw"] = umma_sw128_image(out[p + ".pw_nk"])
+        out[p + ".b"] = f32(b)
+        return dw.shape[2]
+
+    kts = [dwpw(p) for p in ("enc.erb_conv1", "enc.erb_conv2", "enc.erb_conv3", "enc.df_conv1")]
+    assert all(k == cfg.conv_k_enc for k in kts), kts
+    kts = [dwpw("erb_dec.convt3"), dwpw("erb_dec.convt2", True), dwpw("erb_dec.convt1", True)]
+    assert all(k == cfg.conv_k_dec for k in kts), kts
+    for n in (3, 2, 1, 0):
+        assert dwpw(f"erb_dec.conv{n}p") == 1
+    # df_conv0: 2 -> C groups = 2 (k0 x 3), 1x1, BN: composed into the direct 2 -> C conv like DeepFilterNet2 / 3
+    dw = t64("enc.df_conv0.sconv.weight")
+    assert dw.shape == (C, 1, inp_kt, 3), dw.shape
+    pw = t64("enc.df_conv0.1x1conv.weight")[:, :, 0, 0]
+    s, b = bn("enc.df_conv0")
+    g2 = C // 2
+    pws = pw * s[:, None]
+    weff = np.stack([np.einsum("ctf,nc->tfn", dw[ri * g2:(ri + 1) * g2, 0], pws[:, ri * g2:(ri + 1) * g2]) for ri in range(2)], axis=2)
+    out["enc.df_conv0.w"] = f32(weff)
+    out["enc.df_conv0.b"] = f32(b)
+    # conv0_out: C -> 1 (kt x 3) with bias, sigmoid
+    w = t64("erb_dec.conv0_out.sconv.weight")               # [1,C,kt,3]
+    assert w.shape[2] == cfg.conv_k_dec
+    out["erb_dec.conv0_out.w"] = f32(w[0].transpose(1, 2, 0))
+    out["erb_dec.conv0_out.b"] = f32(t64("erb_dec.conv0_out.sconv.bias"))
+    # df_convp: dense 1x1 C -> 2 O + BN + ReLU
+    w = t64("df_dec.df_convp.sconv.weight")
+    assert w.shape == (O2, C, 1, 1), w.shape
+    s, b = bn("df_dec.df_convp")
+    out["df_dec.df_convp.w"] = f32((w[:, :, 0, 0] * s[:, None]).T)   # [C][O2]
+    out["df_dec.df_convp.b"] = f32(b)
+
+    # grouped linears (nn.Linear per group, with bias): [G][Ig][Hg]
+    def glin(dst: str, src: str, in_perm=None):
+        ws = np.stack([t64(f"{src}.layers.{g_}.weight").T for g_ in range(LG)])     # [G][Ig][Hg]
+        if in_perm is not None:
+            ws = ws[:, in_perm, :]
+        out[dst + ".gl"] = f32(ws)
+        out[dst + ".bias"] = f32(np.concatenate([t64(f"{src}.layers.{g_}.bias") for g_ in range(LG)]))
+
+    Fh, cg = Fd // 2, C // LG
+    # group g reads channels [g cg, (g + 1) cg) at all Fh bins; reference index inside the group c * Fh + f, device f * cg + c
+    ip = np.array([(i % cg) * Fh + i // cg for i in range(cg * Fh)])
+    glin("enc.df_fc_emb", "enc.df_fc_emb", ip)
+    glin("erb_dec.fc_emb", "erb_dec.fc_emb.0")
+    ED = C * E // 4
+    assert ED == H, "emb_dim must equal emb_hidden_dim (the grouped GRU keeps the width)"
+    F8 = E // 4
+    # gather tables (out[k] = src[idx[k]])
+    k = np.arange(C * Fh)
+    g_, rem = k // (cg * Fh), k % (cg * Fh)
+    out["v1.idx_c1"] = _i32((rem // cg) * C + g_ * cg + rem % cg)                   # [F][C] rows -> group-contiguous
+    r = np.arange(ED)
+    out["v1.idx_e3"] = _i32((r % F8) * C + r // F8)                                 # reference r = c * F8 + f <- device f * C + c
+    out["v1.idx_shuf"] = _i32(shuffle_index(ED, LG))
+    out["v1.idx_id"] = _i32(r)
+    p_ = np.arange(ED)
+    rr = (p_ % C) * F8 + p_ // C                                                    # device p = f * C + c -> reference r
+    shuf = shuffle_index(ED, LG) if cfg.group_shuffle and LG > 1 else r
+    out["v1.idx_dec"] = _i32(shuf[rr])
+    if G > 1 and cfg.group_shuffle:
+        out["v1.idx_gshuf"] = _i32(shuffle_index(H, G))
+    else:
+        out["v1.idx_gshuf"] = _i32(np.arange(H))
+
+    # grouped GRUs as dense block-diagonal GRUs
+    def ggru(dst: str, src: str) -> int:
+        n = 0
+        while f"{src}.grus.{n}.layers.0.weight_ih_l0" in sd:
+            n += 1
+        hg = H // G
+        for l in range(n):
+            w_ih, w_hh = np.zeros((3 * H, H)), np.zeros((3 * H, H))
+            b_ih, b_hh = np.zeros(3 * H), np.zeros(3 * H)
+            for g_ in range(G):
+                q = f"{src}.grus.{l}.layers.{g_}"
+                wi, wh, bi, bh = t64(q + ".weight_ih_l0"), t64(q + ".weight_hh_l0"), t64(q + ".bias_ih_l0"), t64(q + ".bias_hh_l0")
+                assert wi.shape == (3 * hg, hg), (q, wi.shape)
+                for gate in range(3):
+                    rows = slice(gate * H + g_ * hg, gate * H + (g_ + 1) * hg)
+                    w_ih[rows, g_ * hg:(g_ + 1) * hg] = wi[gate * hg:(gate + 1) * hg]
+                    w_hh[rows, g_ * hg:(g_ + 1) * hg] = wh[gate * hg:(gate + 1) * hg]
+                    b_ih[rows] = bi[gate * hg:(gate + 1) * hg]
+                    b_hh[rows] = bh[gate * hg:(gate + 1) * hg]
+            if l > 0 and G > 1 and cfg.group_shuffle:
+                # x_l[r] = y_{l-1}[idx[r]]  =>  W x_l = W'[:, o] y_{l-1}[o] with W'[:, idx[r]] = W[:, r]
+                idx = shuffle_index(H, G)
+                wp = np.zeros_like(w_ih)
+                wp[:, idx] = w_ih
+                w_ih = wp
+            base = f"{dst}.g{l}.l0"
+            out[base + ".w_ih_t"] = f32(w_ih.T)
+            out[base + ".w_ih"] = f32(w_ih)
+            out[base + ".w_ih_hi"], out[base + ".w_ih_lo"] = bf16_planes(f32(w_ih))
+            out[base + ".w_hh"] = f32(w_hh)
+            out[base + ".b_ih"] = f32(b_ih)
+            out[base + ".b_hh"] = f32(b_hh)
+        return n
+
+    n_enc = ggru("enc.emb_gru", "enc.emb_gru")
+    n_df = ggru("df_dec.df_gru", "df_dec.df_gru")
+    assert n_enc == cfg.emb_num_layers and n_df == cfg.df_num_layers, (n_enc, n_df)
+    out["enc.lsnr.w"] = f32(t64("enc.lsnr_fc.0.weight").reshape(-1))
+    out["enc.lsnr.b"] = f32(t64("enc.lsnr_fc.0.bias").reshape(-1))
+    out["df_dec.df_fc_a.w"] = f32(t64("df_dec.df_fc_a.0.weight").reshape(-1))
+    out["df_dec.df_fc_a.b"] = f32(t64("df_dec.df_fc_a.0.bias").reshape(-1))
+    w = t64("df_dec.df_fc_out.0.weight")                     # [O2 * Fd][H], row k * Fd + f
+    assert w.shape == (O2 * Fd, H)
+    n = np.arange(Fd * O2)
+    src = (n % O2) * Fd + n // O2                            # device column f * O2 + k
+    out["df_dec.df_fc_out.w_t"] = f32(w[src].T)              # [H][Fd * O2]
+    out["df_dec.df_fc_out.b"] = f32(t64("df_dec.df_fc_out.0.bias")[src])
+    out["df_dec.df_fc_out.w_hi"], out["df_dec.df_fc_out.w_lo"] = bf16_planes(f32(w[src]))   # [N][K] B operand of the BF16x3 GEMM
+    out["v1.ones"] = np.ones(C, dtype=np.float32)
+    out["v1.zeros"] = np.zeros(C, dtype=np.float32)
+    derived = dict(
+        model_kind=1, nb_erb=E, nb_df=Fd, df_order=cfg.df_order, df_lookahead=cfg.df_lookahead,
+        conv_lookahead=cfg.conv_lookahead, conv_ch=C, conv_kt=cfg.conv_k_enc, inp_kt=inp_kt,
+        emb_hidden=H, df_hidden=cfg.df_hidden_dim, enc_gru_layers=n_enc, erb_gru_layers=0, df_gru_layers=n_df,
+        df_pathway_kt=1, enc_concat=0, g_df_fc_emb=LG, g_enc_in=G, g_enc_out=0, g_erb_in=LG, g_erb_out=0, g_df_in=G,
+        g_df_skip=0, g_df_out=1,
+        lsnr_scale=float(cfg.lsnr_max - cfg.lsnr_min), lsnr_offset=float(cfg.lsnr_min),
+    )
+    return out, derived
+
+
+def random_state_dict_v1(cfg: ModelConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Random-init DeepFilterNet v1 weights with the shipped checkpoint's tensor names (after the clc -> df rename)."""
+    g = torch.Generator().manual_seed(seed)
+    C, E, Fd, O2 = cfg.conv_ch, cfg.nb_erb, cfg.nb_df, 2 * cfg.df_order
+    G, LG, H = cfg.gru_groups, cfg.lin_groups, cfg.emb_hidden_dim
+    ke, kd, k0 = cfg.conv_k_enc, cfg.conv_k_dec, cfg.conv_kernel_inp[0]
+    sd: Dict[str, torch.Tensor] = {}
+
+    def rnd(*shape, scale=1.0):
+        return (torch.rand(*shape, generator=g) * 2 - 1) * scale
+
+    def bn(p, n):
+        sd[p + ".norm.weight"] = 1.0 + rnd(n, scale=0.3)
+        sd[p + ".norm.bias"] = rnd(n, scale=0.2)
+        sd[p + ".norm.running_mean"] = rnd(n, scale=0.2)
+        sd[p + ".norm.running_var"] = 0.5 + torch.rand(n, generator=g)
+        sd[p + ".norm.num_batches_tracked"] = torch.tensor(1)
+
+    def conv(p, name, shape):
+        fan = shape[1] * shape[2] * shape[3]
+        sd[f"{p}.{name}.weight"] = rnd(*shape, scale=(1.5 / fan) ** 0.5 * 1.7)
+
+    def sep(p, kt, kf=3, transposed=False):
+        conv(p, "sconvt" if transposed else "sconv", (C, 1, kt, kf))
+        conv(p, "1x1conv", (C, C, 1, 1))
+        bn(p, C)
+
+    conv("enc.erb_conv0", "sconv", (C, 1, k0, 3)); bn("enc.erb_conv0", C)
+    for p in ("enc.erb_conv1", "enc.erb_conv2", "enc.erb_conv3", "enc.df_conv1"):
+        sep(p, ke)
+    conv("enc.df_conv0", "sconv", (C, 1, k0, 3)); conv("enc.df_conv0", "1x1conv", (C, C, 1, 1)); bn("enc.df_conv0", C)
+    sep("erb_dec.convt3", kd); sep("erb_dec.convt2", kd, transposed=True); sep("erb_dec.convt1", kd, transposed=True)
+    for n in (3, 2, 1, 0):
+        sep(f"erb_dec.conv{n}p", 1, 1)
+    conv("erb_dec.conv0_out", "sconv", (1, C, kd, 3)); sd["erb_dec.conv0_out.sconv.bias"] = rnd(1, scale=0.1)
+    conv("df_dec.df_convp", "sconv", (O2, C, 1, 1)); bn("df_dec.df_convp", O2)
+
+    def glin(p, i, h):
+        for j in range(LG):
+            sd[f"{p}.layers.{j}.weight"] = rnd(h // LG, i // LG, scale=(3.0 / (i // LG)) ** 0.5)
+            sd[f"{p}.layers.{j}.bias"] = rnd(h // LG, scale=0.1)
+
+    glin("enc.df_fc_emb", C * Fd // 2, C * E // 4)
+    glin("erb_dec.fc_emb.0", H, C * E // 4)
+
+    def ggru(p, layers):
+        hg = H // G
+        for l in range(layers):
+            for j in range(G):
+                k_ = (1.0 / hg) ** 0.5
+                q = f"{p}.grus.{l}.layers.{j}"
+                sd[q + ".weight_ih_l0"] = rnd(3 * hg, hg, scale=k_); sd[q + ".weight_hh_l0"] = rnd(3 * hg, hg, scale=k_)
+                sd[q + ".bias_ih_l0"] = rnd(3 * hg, scale=k_); sd[q + ".bias_hh_l0"] = rnd(3 * hg, scale=k_)
+
+    ggru("enc.emb_gru", cfg.emb_num_layers)
+    ggru("df_dec.df_gru", cfg.df_num_layers)
+    sd["enc.lsnr_fc.0.weight"] = rnd(1, H, scale=0.05); sd["enc.lsnr_fc.0.bias"] = rnd(1, scale=0.1)
+    sd["df_dec.df_fc_out.0.weight"] = rnd(O2 * Fd, H, scale=(3.0 / H) ** 0.5); sd["df_dec.df_fc_out.0.bias"] = rnd(O2 * Fd, scale=0.1)
+    sd["df_dec.df_fc_a.0.weight"] = rnd(1, H, scale=0.05); sd["df_dec.df_fc_a.0.bias"] = rnd(1, scale=0.1)
+    return sd
+
+
 def random_state_dict(cfg: ModelConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
     """Random-init weights with the shipped architecture's tensor names / shapes (for benchmarks
     and parity tests that must not depend on a checkpoint).  BatchNorm statistics are randomised
     too so that folding is exercised."""
+    if cfg.model == "deepfilternet":
+        return random_state_dict_v1(cfg, seed)
     g = torch.Generator().manual_seed(seed)
     C, E, Fd = cfg.conv_ch, cfg.nb_erb, cfg.nb_df
     kt, kti = cfg.conv_kernel[0], cfg.conv_kernel_inp[0]

@@ -578,3 +578,89 @@ def test_streaming_lsnr_stage_gating(states):
     lim = 10 ** (-12 / 20)
     z = run(model, min_db_thresh=1e9, max_db_erb_thresh=2e9, max_db_df_thresh=2e9, atten=12.0)
     assert rms(z, ident * lim) < 1e-6
+
+
+# ------------------------------------------------------------------ DeepFilterNet v1 ----
+def cfg_v1():
+    return ModelConfig(model="deepfilternet", conv_lookahead=2, df_lookahead=1, conv_ch=64, conv_kernel=(2, 3), convt_kernel=(2, 3),
+                       conv_kernel_inp=(2, 3), conv_k_enc=2, conv_k_dec=2, emb_hidden_dim=512, df_hidden_dim=512, emb_num_layers=3,
+                       df_num_layers=2, gru_groups=8, lin_groups=8, enc_lin_groups=8, group_shuffle=True, dfop_method="real_unfold")
+
+
+def test_v1_golden_reference_outputs(golden_dir, model_dir):
+    """DeepFilterNet (v1: convkxf with in-conv look-ahead, GroupedGRU / GroupedLinear with shuffle, DfOp with alpha) against
+    outputs of the reference's own modules (tests/golden/dfnet_DeepFilterNet.npz, made by oracle/gen_golden_v1.py)."""
+    g = np.load(os.path.join(golden_dir, "dfnet_DeepFilterNet.npz"))
+    model, st, suffix, epoch = init_df(os.path.join(model_dir, "DeepFilterNet"), log_level="ERROR")
+    assert suffix == "DeepFilterNet" and epoch == int(g["epoch"]) and model.cfg.model == "deepfilternet"
+    spec_e, m, lsnr, alpha = model(torch.from_numpy(g["spec"]), torch.from_numpy(g["feat_erb"]), torch.from_numpy(g["feat_spec"]))
+    assert rms(m, g["m"]) < TOL_M and np.abs(lsnr.numpy() - g["lsnr"]).max() < TOL_LSNR
+    assert alpha.shape == g["alpha"].shape and np.abs(alpha.numpy() - g["alpha"]).max() < 1e-5
+    assert rms(spec_e, g["spec_e"]) < TOL_SPEC
+    audio = torch.from_numpy(g["audio"])
+    assert rms(enhance(model, st, audio), g["enhanced"]) < RMS_TOL
+    o = enhance(model, st, audio, pad=False)
+    assert o.shape == g["enhanced_nopad"].shape and rms(o, g["enhanced_nopad"]) < RMS_TOL
+    assert rms(enhance(model, st, audio, atten_lim_db=12.0), g["enhanced_atten12"]) < RMS_TOL
+    assert rms(enhance(model, st, torch.from_numpy(g["audio2"])), g["enhanced2"]) < RMS_TOL
+    with pytest.raises(_lib.DfbError, match="one window per signal"):   # no frame-incremental API for v1
+        from deepfilternet_b200 import DfStream
+        DfStream(model, st, 1)
+
+
+def test_v1_si_sdr_known_answer_and_whole_asset(golden_dir, model_dir):
+    """The third known answer of the reference CI (df/scripts/test_df.py:45-55: DeepFilterNet 18.885 dB) on the CUDA path, and
+    every sample of the 10.6 s recording against the oracle."""
+    import dfnet1_oracle as O1
+    import ref_harness as rh
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))["DeepFilterNet"]
+    model, st, _, epoch = init_df(os.path.join(model_dir, "DeepFilterNet"), log_level="ERROR")
+    assert epoch == kat["epoch"]
+    noisy = torch.from_numpy(rh.read_wav(os.path.join(golden_dir, "assets", "noisy_snr0.wav")))
+    clean = rh.read_wav(os.path.join(golden_dir, "assets", "clean_freesound_33711.wav"))
+    out = enhance(model, st, noisy, pad=True)
+    s = rh.si_sdr(clean, out.numpy())
+    assert abs(s - kat["target"]) <= 1e-4 + 1e-4 * abs(kat["target"]), (s, kat["target"])
+    ref = O1.enhance(model.state_dict(), dict(O1.DEFAULTS_DFN1), noisy)
+    assert out.shape == ref.shape and rms(out, ref) < RMS_TOL
+
+
+@pytest.mark.parametrize("precision", ["fp32+gru_tc+proj_tc+conv_tc", "fp32"])
+@pytest.mark.parametrize("B,T", [(3, 24000), (1, 4800), (9, 9600 + 123)])
+def test_v1_random_weights_vs_oracle(states, B, T, precision):
+    """Random weights (BatchNorm statistics included) so that the packing -- folded shuffles, gather tables, block-diagonal
+    GRUs, reversed transposed-conv taps -- is exercised away from the trained checkpoint; both arithmetic modes."""
+    import dfnet1_oracle as O1
+    st, _ = states
+    cfg = cfg_v1()
+    sd = random_state_dict(cfg, seed=7)
+    model = DfNet(cfg, sd, st)
+    model.set_precision(precision)
+    audio = synth_audio(B, T, seed=23)
+    out_o, aux = O1.enhance(sd, dict(O1.DEFAULTS_DFN1), audio, return_all=True)
+    spec_e, m, lsnr, alpha = model(aux["spec"], aux["erb_feat"], aux["spec_feat"])
+    assert rms(m, aux["m"]) < TOL_M and rms(spec_e, aux["spec_e"]) < TOL_SPEC
+    assert np.abs(lsnr.numpy() - aux["lsnr"].numpy()).max() < TOL_LSNR and np.abs(alpha.numpy() - aux["alpha"].numpy()).max() < 1e-5
+    out = enhance(model, st, audio)
+    assert out.shape == audio.shape and rms(out, out_o) < RMS_TOL
+    dev = enhance_device(model, st, audio.cuda())
+    assert rms(dev.cpu(), out_o) < RMS_TOL
+
+
+def test_v1_stream_groups_and_independence(states):
+    """Stream groups under a small workspace cap (one window per signal, so only the batch is split) and batch-position
+    independence."""
+    import dfnet1_oracle as O1
+    st, _ = states
+    cfg = cfg_v1()
+    sd = random_state_dict(cfg, seed=8)
+    model = DfNet(cfg, sd, st)
+    audio = synth_audio(11, 24000, seed=29).cuda()
+    full = enhance_device(model, st, audio)
+    model.set_max_workspace(48 << 20)   # a few streams per group
+    grouped = enhance_device(model, st, audio)
+    model.set_max_workspace(64 << 30)
+    assert rms(full.cpu(), grouped.cpu()) < 1e-7
+    assert rms(full[4:5].cpu(), O1.enhance(sd, dict(O1.DEFAULTS_DFN1), audio[4:5].cpu())) < RMS_TOL
+    single = enhance_device(model, st, audio[10:11].contiguous())
+    assert rms(full[10:11].cpu(), single.cpu()) < 1e-7

@@ -75,8 +75,11 @@ def test_config_parsing(model_dir, tmp_path):
     # df/config.py:119-122: environment variables named like the option win over the ini file
     ce = load_config(os.path.join(model_dir, "DeepFilterNet3", "config.ini"), env={"DF_ORDER": "3"})
     assert ce.df_order == 3
+    c1 = load_config(os.path.join(model_dir, "DeepFilterNet", "config.ini"), env={})
+    assert (c1.model, c1.conv_lookahead, c1.df_lookahead, c1.emb_hidden_dim, c1.gru_groups, c1.lin_groups, tuple(c1.conv_kernel_inp)) == \
+        ("deepfilternet", 2, 1, 512, 8, 8, (2, 3))
     p = tmp_path / "config.ini"
-    p.write_text("[train]\nmodel = deepfilternet\n")
+    p.write_text("[train]\nmodel = deepfilternet\n")   # v1 with the code defaults (conv_ch 16, one decoder time tap, ...): not built
     with pytest.raises(NotImplementedError):
         load_config(str(p), env={})
 
@@ -172,7 +175,9 @@ def test_bench_bookkeeping():
     for f in os.listdir(csrc):
         if f.endswith(".cu"):
             names |= set(re.findall(r'DFB_PROF\("([^"]+)"', open(os.path.join(csrc, f)).read()))
-    default_path = {n for n in names if not n.startswith(("k_gru", "k_dwpw", "k_mask_out", "k_to_planes")) or n in ("k_gru_tc", "k_dwpw_bx")}
+    # (k_gather_sum / k_convp_v1 only run for DeepFilterNet v1, which is not a BASELINE config)
+    default_path = {n for n in names if not n.startswith(("k_gru", "k_dwpw", "k_mask_out", "k_to_planes", "k_gather_sum", "k_convp_v1"))
+                    or n in ("k_gru_tc", "k_dwpw_bx")}
     for model_name in ("DeepFilterNet3", "DeepFilterNet2", "DeepFilterNet3_ll"):
         cfg = bench.model_config(model_name)
         from deepfilternet_b200.weights import pack_state_dict, random_state_dict
@@ -226,3 +231,29 @@ def test_io_wav_roundtrip_and_resample_taps(tmp_path):
         kr, wr = _get_sinc_resample_kernel(o, n, math.gcd(o, n), **dio.get_resample_params(meth))
         assert w == wr and (og, nw) == (o // math.gcd(o, n), n // math.gcd(o, n))
         assert torch.equal(k, kr[:, 0])
+
+
+def test_v1_packing_against_oracle_through_device_graph_emulation():
+    """DeepFilterNet v1: the packed tensors (block-diagonal GRUs with folded shuffles, gather tables, reversed transposed-conv
+    time taps, df_fc_out in the device coefs layout) run through a torch emulation of the DEVICE graph (tests/v1_emulation.py:
+    channel-last tensors, the same kernel sequence as forward_v1) must reproduce the oracle."""
+    import dfnet1_oracle as O1
+    import libdf_oracle as LO
+    import v1_emulation as em
+    cfg = ModelConfig(model="deepfilternet", conv_lookahead=2, df_lookahead=1, conv_ch=64, conv_kernel=(2, 3), convt_kernel=(2, 3),
+                      conv_kernel_inp=(2, 3), conv_k_enc=2, conv_k_dec=2, emb_hidden_dim=512, df_hidden_dim=512, emb_num_layers=3,
+                      df_num_layers=2, gru_groups=8, lin_groups=8, enc_lin_groups=8, group_shuffle=True, dfop_method="real_unfold")
+    sd = random_state_dict(cfg, seed=3)
+    packed, d = pack_state_dict(sd, cfg)
+    assert d["model_kind"] == 1 and d["enc_gru_layers"] == 3 and d["df_gru_layers"] == 2
+    g = torch.Generator().manual_seed(0)
+    B, T = 2, 11
+    fe = torch.randn(B, 1, T, 32, generator=g) * 0.5
+    fs = torch.randn(B, 1, T, 96, 2, generator=g) * 0.5
+    spec = torch.randn(B, 1, T, 481, 2, generator=g)
+    widths = LO.erb_widths(48000, 960, 32, 2)
+    spec_e, m, lsnr, co, alpha = O1.dfnet1_forward(sd, dict(O1.DEFAULTS_DFN1), widths, spec, fe, fs)
+    m2, coefs2, lsnr2, alpha2 = em.forward(packed, d, fe[:, 0], fs[:, 0])
+    co_dev = co.permute(0, 1, 3, 2, 4).reshape(B, T, -1)   # [B,T,O,Fd,2] -> device layout [B,T,Fd * 2 O]
+    assert float((m2 - m[:, 0]).abs().max()) < 1e-5 and float((coefs2 - co_dev).abs().max()) < 1e-5
+    assert float((lsnr2 - lsnr[..., 0]).abs().max()) < 1e-4 and float((alpha2 - alpha[..., 0]).abs().max()) < 1e-5

@@ -201,3 +201,41 @@ def test_oracle_post_filter_and_mask_only_match_reference_modules(name, golden_d
     assert rmsd(O.enhance(sd, c, audio), g[f"{name}_mask_only"]) < 1e-6
     # and they are not no-ops
     assert rmsd(O.enhance(sd, cfg.as_dict(), audio), g[f"{name}_pf"]) > 1e-5
+
+
+def test_v1_oracle_matches_reference_modules(golden_dir, model_dir):
+    """oracle/dfnet1_oracle.py against outputs of the reference's own DeepFilterNet (v1) modules (oracle/gen_golden_v1.py)."""
+    import dfnet1_oracle as O1
+    g = np.load(os.path.join(golden_dir, "dfnet_DeepFilterNet.npz"))
+    cfg = load_config(os.path.join(model_dir, "DeepFilterNet", "config.ini"), env={})
+    assert (cfg.model, cfg.gru_groups, cfg.lin_groups, cfg.conv_k_enc, cfg.conv_k_dec, cfg.df_lookahead) == ("deepfilternet", 8, 8, 2, 2, 1)
+    path, epoch = find_checkpoint(os.path.join(model_dir, "DeepFilterNet", "checkpoints"))
+    assert epoch == int(g["epoch"])
+    sd = load_state_dict_file(path)
+    ocfg = dict(O1.DEFAULTS_DFN1)
+    for k in ("conv_lookahead", "df_lookahead", "df_order", "nb_df", "nb_erb", "emb_num_layers", "df_num_layers", "gru_groups", "lin_groups",
+              "conv_k_enc", "conv_k_dec", "group_shuffle"):
+        assert ocfg[k] == getattr(cfg, k), k
+    st = LO.DF(48000, 960, 480, 32, 2)
+    spec_e, m, lsnr, coefs, alpha = O1.dfnet1_forward(sd, ocfg, st.erb_widths(), torch.from_numpy(g["spec"]), torch.from_numpy(g["feat_erb"]),
+                                                      torch.from_numpy(g["feat_spec"]))
+    assert np.abs(spec_e.numpy() - g["spec_e"]).max() < 1e-6 and np.abs(m.numpy() - g["m"]).max() < 5e-6
+    assert np.abs(lsnr.numpy() - g["lsnr"]).max() < 1e-4 and np.abs(alpha.numpy() - g["alpha"]).max() < 5e-6
+    audio = torch.from_numpy(g["audio"])
+    assert np.abs(O1.enhance(sd, ocfg, audio).numpy() - g["enhanced"]).max() < 1e-6
+    assert np.abs(O1.enhance(sd, ocfg, audio, pad=False).numpy() - g["enhanced_nopad"]).max() < 1e-6
+    assert np.abs(O1.enhance(sd, ocfg, audio, atten_lim_db=12.0).numpy() - g["enhanced_atten12"]).max() < 1e-6
+    assert np.abs(O1.enhance(sd, ocfg, torch.from_numpy(g["audio2"])).numpy() - g["enhanced2"]).max() < 1e-6
+
+
+def test_v1_si_sdr_known_answer(golden_dir, model_dir):
+    """df/scripts/test_df.py:45-55: DeepFilterNet (v1) 18.88543128967285 dB, atol = rtol = 1e-4."""
+    import dfnet1_oracle as O1
+    import ref_harness as rh
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))["DeepFilterNet"]
+    sd = load_state_dict_file(find_checkpoint(os.path.join(model_dir, "DeepFilterNet", "checkpoints"))[0])
+    noisy = torch.from_numpy(rh.read_wav(os.path.join(golden_dir, "assets", "noisy_snr0.wav")))
+    clean = rh.read_wav(os.path.join(golden_dir, "assets", "clean_freesound_33711.wav"))
+    out = O1.enhance(sd, dict(O1.DEFAULTS_DFN1), noisy, pad=True)
+    s = rh.si_sdr(clean, out.numpy())
+    assert abs(s - kat["target"]) <= 1e-4 + 1e-4 * abs(kat["target"]), (s, kat["target"])
