@@ -595,7 +595,7 @@ def test_v1_golden_reference_outputs(golden_dir, model_dir):
     assert suffix == "DeepFilterNet" and epoch == int(g["epoch"]) and model.cfg.model == "deepfilternet"
     spec_e, m, lsnr, alpha = model(torch.from_numpy(g["spec"]), torch.from_numpy(g["feat_erb"]), torch.from_numpy(g["feat_spec"]))
     assert rms(m, g["m"]) < TOL_M and np.abs(lsnr.numpy() - g["lsnr"]).max() < TOL_LSNR
-    assert alpha.shape == g["alpha"].shape and np.abs(alpha.numpy() - g["alpha"]).max() < 1e-5
+    assert alpha.shape == g["alpha"].shape and np.abs(alpha.numpy() - g["alpha"]).max() < 1e-4
     assert rms(spec_e, g["spec_e"]) < TOL_SPEC
     audio = torch.from_numpy(g["audio"])
     assert rms(enhance(model, st, audio), g["enhanced"]) < RMS_TOL
@@ -640,7 +640,7 @@ def test_v1_random_weights_vs_oracle(states, B, T, precision):
     out_o, aux = O1.enhance(sd, dict(O1.DEFAULTS_DFN1), audio, return_all=True)
     spec_e, m, lsnr, alpha = model(aux["spec"], aux["erb_feat"], aux["spec_feat"])
     assert rms(m, aux["m"]) < TOL_M and rms(spec_e, aux["spec_e"]) < TOL_SPEC
-    assert np.abs(lsnr.numpy() - aux["lsnr"].numpy()).max() < TOL_LSNR and np.abs(alpha.numpy() - aux["alpha"].numpy()).max() < 1e-5
+    assert np.abs(lsnr.numpy() - aux["lsnr"].numpy()).max() < TOL_LSNR and np.abs(alpha.numpy() - aux["alpha"].numpy()).max() < 1e-4
     out = enhance(model, st, audio)
     assert out.shape == audio.shape and rms(out, out_o) < RMS_TOL
     dev = enhance_device(model, st, audio.cuda())
