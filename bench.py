@@ -45,9 +45,10 @@ CONFIGS = {
     3: ("DeepFilterNet2", 512, 10, 1),
     4: ("DeepFilterNet3_ll", 256, 10, 4),
     5: ("DeepFilterNet3", 512, 30, 8),
+    6: ("DeepFilterNet", 128, 10, 1),     # SURVEY.md 8f-2 ("next" row): DeepFilterNet v1 at configs[1]'s shape -- not a BASELINE config
 }
 BASELINE_NAME = {2: "BASELINE.json configs[1]", 3: "BASELINE.json configs[2]", 4: "BASELINE.json configs[3] (per-GPU shard)",
-                 5: "BASELINE.json configs[4] (per-GPU shard)"}
+                 5: "BASELINE.json configs[4] (per-GPU shard)", 6: "SURVEY.md 8f-2, DeepFilterNet v1; not a BASELINE config"}
 # Algorithmic DNN flops per frame per stream (SURVEY.md 8d / BASELINE.md 2)
 FLOP_PER_FRAME = {"DeepFilterNet3": 6_614_784, "DeepFilterNet2": 6_956_800, "DeepFilterNet3_ll": 21_846_784}
 DTYPE = "f32 (bf16x3 tensor-core contractions, fp32 accumulate; DSP and gates IEEE fp32)"
@@ -64,6 +65,8 @@ def kernel_model(cfg, g: dict) -> dict:
     emb = H if cfg.model == "deepfilternet2" else ED
     enc_l, erb_l, df_l = g["enc_gru_layers"], g["erb_gru_layers"], g["df_gru_layers"]
     rec = 2 * 3 * (H * H * (enc_l + erb_l) + Hd * Hd * df_l)        # W_hh h, all layers
+    if cfg.model == "deepfilternet":                                 # GroupedGRU: block-diagonal, 1 / G of the dense product
+        rec //= cfg.gru_groups
     proj = rec                                                       # W_ih x: same shapes (inputs are H wide)
     gl = gl_bytes = 0
     for (i, o, grp) in ((Fd // 2 * 64, ED, g["g_df_fc_emb"]), (emb_in, H, g["g_enc_in"]), (H, ED, g["g_enc_out"]),
@@ -91,6 +94,9 @@ def kernel_model(cfg, g: dict) -> dict:
         "k_df_convp": ("hbm", Fd * 256 + Fd * 4 * O2, "bytes"),
         "k_df_convp_tc": ("hbm", Fd * 256 + Fd * 4 * O2, "bytes"),
         "k_mask_out": ("hbm", 2 * E * 256 + 4 * E, "bytes"),
+        # DeepFilterNet v1 only: re-ordering passes (read + write one 2 KB row each, 3 KB for the c1 gather) and the 1x1 pathway conv
+        "k_gather_sum": ("hbm", 2 * 4 * (Fd // 2 * 64) + 4 * 3 * 4 * H + 6 * 4 * H, "bytes"),
+        "k_convp_v1": ("hbm", Fd * 256 + 2 * Fd * 4 * O2, "bytes"),
     }
 
 
@@ -121,6 +127,10 @@ def model_config(name: str):
         return ModelConfig(model="deepfilternet3", conv_lookahead=0, df_lookahead=0, conv_kernel=(2, 3), emb_hidden_dim=512,
                            df_hidden_dim=512, emb_num_layers=3, df_num_layers=3, lin_groups=16, enc_lin_groups=16,
                            df_gru_skip="groupedlinear", **base)
+    if name == "DeepFilterNet":
+        return ModelConfig(model="deepfilternet", conv_lookahead=2, df_lookahead=1, conv_ch=64, conv_kernel=(2, 3), convt_kernel=(2, 3),
+                           conv_kernel_inp=(2, 3), conv_k_enc=2, conv_k_dec=2, emb_hidden_dim=512, df_hidden_dim=512, emb_num_layers=3,
+                           df_num_layers=2, gru_groups=8, lin_groups=8, enc_lin_groups=8, group_shuffle=True, dfop_method="real_unfold")
     raise SystemExit(f"no config for {name}")
 
 
@@ -390,11 +400,15 @@ def measure(ctx: Ctx, cfg_id: int, model_name: str, streams: int, seconds: int, 
     parity = None
     if ctx.rank == 0 and parity_streams > 0:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import dfnet1_oracle
         import dfnet_oracle
         rows = sorted({0, 1, streams // 2, streams - 1})[:parity_streams]
         got_dev = out[rows].cpu()
         got_e2e = host_out[rows]
-        ref = dfnet_oracle.enhance(sd, cfg.as_dict(), audio[rows].cpu())
+        if cfg.model == "deepfilternet":
+            ref = dfnet1_oracle.enhance(sd, dict(dfnet1_oracle.DEFAULTS_DFN1), audio[rows].cpu())
+        else:
+            ref = dfnet_oracle.enhance(sd, cfg.as_dict(), audio[rows].cpu())
         rms_dev = float((got_dev - ref).double().pow(2).mean().sqrt())
         rms_e2e = float((got_e2e - ref).double().pow(2).mean().sqrt())
         parity = {"streams": rows, "rms_vs_oracle_device": rms_dev, "rms_vs_oracle_e2e": rms_e2e, "tol": PARITY_TOL,
@@ -478,7 +492,7 @@ def main():
     ap.add_argument("--model", default=None)
     ap.add_argument("--streams", type=int, default=None, help="streams per GPU")
     ap.add_argument("--seconds", type=int, default=None)
-    ap.add_argument("--extra", default=None, help="comma list of extra configs (default: 3,4,5 at N=1; 4 at N=4; 5 at N=8; 'none')")
+    ap.add_argument("--extra", default=None, help="comma list of extra configs (default: 3,4,5,6 at N=1; 4 at N=4; 5 at N=8; 'none')")
     ap.add_argument("--roofline-kernel", default=None, help="kernel to report (default: the one with most time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -522,7 +536,7 @@ def main():
     head, cfg, sd = measure(ctx, cfg_id, model_name, streams, seconds, a.steps, a.warmup, a.roofline_kernel, clocks=clocks)
     clk = clocks.stop()
     if a.extra is None:
-        extra_ids = {1: [3, 4, 5], 4: [4], 8: [5]}.get(n_gpus, [])
+        extra_ids = {1: [3, 4, 5, 6], 4: [4], 8: [5]}.get(n_gpus, [])
         extra_ids = [i for i in extra_ids if i != cfg_id] if cfg_id == 2 else []
     else:
         extra_ids = [] if a.extra in ("", "none") else [int(x) for x in a.extra.split(",")]

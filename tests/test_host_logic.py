@@ -191,7 +191,12 @@ def test_bench_bookkeeping():
     km = bench.kernel_model(cfg, derived)
     assert km["k_gru_tc"][1] == 2 * 5 * 256 * 768 and km["k_analysis"][1] == 1920 + 3848 + 128
     assert km["k_apply_synthesis"][1] == 3848 + 128 + 3840 + 1920 and km["k_dwpw_bx"][1] == 256 * 352
-    assert set(bench.CONFIGS) == {2, 3, 4, 5} and bench.CONFIGS[2] == ("DeepFilterNet3", 128, 10, 1)
+    assert set(bench.CONFIGS) == {2, 3, 4, 5, 6} and bench.CONFIGS[2] == ("DeepFilterNet3", 128, 10, 1)
+    # DeepFilterNet v1 (cfg 6, not a BASELINE config): the grouped recurrences count 1 / G of the dense product
+    cfg = bench.model_config("DeepFilterNet")
+    _, derived = pack_state_dict(random_state_dict(cfg, seed=0), cfg)
+    km = bench.kernel_model(cfg, derived)
+    assert km["k_gru_tc512"][1] == 2 * 3 * 512 * 512 * 5 // 8 and km["k_gather_sum"][1] > 0 and km["k_convp_v1"][1] > 0
 
 
 
