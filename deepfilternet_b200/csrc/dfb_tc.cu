@@ -941,6 +941,8 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     // than half of the shared memory to enforce it.  (Tried: 256 + 32 columns, half the registers and 115 KB so that
     // feed-forward CTAs could share the SMs a recurrence occupies but hardly uses -- no gain at 128 or 512 streams.)
     const int need = (int)sizeof(GruTcSmem<NS, HH>) + 1024;
+    // (also tried: the whole 227 KB carve-out, so that no feed-forward CTA can sit next to a recurrence CTA and wait in
+    // tcgen05.alloc -- no change at 128 x 10 s with 1 .. 4 device chunks, 512 x 10 s: 45.2 vs 45.3 ms)
     const int smem = need > 120 * 1024 ? need : 120 * 1024;
     if (auto once_guard = attr_once.first()) {
         if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
