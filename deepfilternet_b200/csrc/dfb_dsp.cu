@@ -158,19 +158,37 @@ k_analysis(const float *__restrict__ audio, int64_t T, int Tf, float2 *__restric
     const int b = blockIdx.y, tl0 = blockIdx.x * kAnaWarps, t0 = t_begin + tl0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *x = audio + (int64_t)b * T;
-    // stage samples [(t0-1)*hop, (t0+W)*hop); zeros before the stream start (analysis_mem = 0)
-    const int64_t s0 = (int64_t)(t0 - 1) * kHop;
     const int64_t s_end = (int64_t)Tf * kHop;
-    for (int i = tid; i < (kAnaWarps + 1) * kHop; i += blockDim.x) {
-        int64_t s = s0 + i;
-        float v = 0.f;
-        if (s >= 0 && s < s_end) v = __ldg(x + s);
-        else if (s < 0 && init_mem) v = init_mem[(int64_t)b * kHop + (kHop + s)];  // carried analysis_mem (reset = False)
-        s_stage[i] = v;
+    // stage samples [(t0-1)*hop, (t0+W)*hop); zeros before the stream start (analysis_mem = 0).  All 17 loads of a thread
+    // are issued into registers before the first store: as a load / store loop with the bounds checks inside, the compiler
+    // kept them in program order -- 17 dependent round trips to L2 / HBM per CTA, 85 % of the kernel's stall samples
+    // (ncu source page, profiles/README.md) -- 0.565 -> 0.344 ms for 128 x 10 s.
+    // (Also tried: a CTA looping over 4 / 8 groups of frames with the next group's samples prefetched into registers during
+    // the transforms: 128 registers, 2 CTAs per SM, 0.51 / 0.49 ms.)
+    {
+        constexpr int kPre = ((kAnaWarps + 1) * kHop + 32 * kAnaWarps - 1) / (32 * kAnaWarps);
+        float pre[kPre];
+        const int64_t s0 = (int64_t)(t0 - 1) * kHop;
+#pragma unroll
+        for (int q = 0; q < kPre; q++) {
+            const int i = tid + q * 32 * kAnaWarps;
+            const int64_t sidx = s0 + i;
+            float v = 0.f;
+            if (i < (kAnaWarps + 1) * kHop) {
+                if (sidx >= 0 && sidx < s_end) v = __ldg(x + sidx);
+                else if (sidx < 0 && init_mem) v = init_mem[(int64_t)b * kHop + (kHop + sidx)];  // carried analysis_mem (reset = False)
+            }
+            pre[q] = v;
+        }
+        for (int i = tid; i < kFft; i += blockDim.x) s_win[i] = tb.window[i];
+        for (int i = tid; i < 241; i += blockDim.x) s_tw960[i] = tb.tw960[i];
+        for (int i = tid; i < kN2 * kN1; i += blockDim.x) s_twa[i] = tb.tw_a_fwd[i];
+#pragma unroll
+        for (int q = 0; q < kPre; q++) {
+            const int i = tid + q * 32 * kAnaWarps;
+            if (i < (kAnaWarps + 1) * kHop) s_stage[i] = pre[q];
+        }
     }
-    for (int i = tid; i < kFft; i += blockDim.x) s_win[i] = tb.window[i];
-    for (int i = tid; i < 241; i += blockDim.x) s_tw960[i] = tb.tw960[i];
-    for (int i = tid; i < kN2 * kN1; i += blockDim.x) s_twa[i] = tb.tw_a_fwd[i];
     __syncthreads();
     const int t = t0 + warp;
     if (tl0 + warp >= nf || t >= Tf) return;
@@ -362,6 +380,124 @@ __global__ void __launch_bounds__(kPf > 8 ? 128 : 1024) k_feat_norm(const float 
             }
         }
         if (unit_state_out) unit_state_out[(int64_t)b * Fd + k] = s;
+    }
+}
+
+// Time-segmented version for the enhancement path's shape (E + Fd <= 128 values per stream, long windows): the EMA is a
+// linear recurrence, so a stream's frames are cut into kSeg segments scanned concurrently by kSeg x 128 threads --
+//   pass 1: every (segment, value) thread runs the recurrence over its segment from state 0 (no stores) -> local end state
+//   fold:   state at the start of segment g = alpha^(frames before) * s_in + sum of the earlier local end states, each
+//           decayed by alpha^(frames after it) (evaluated in double: at most kSeg terms per thread)
+//   pass 2: the same loop as k_feat_norm from the segment's true start state, with the reference's operation order, storing
+//           the features (the inputs are re-read from L2)
+// The serial chain per thread drops from Tf to 2 Tf / kSeg steps (128 x 10 s: 0.35 -> 0.1 ms); the results differ from
+// the one-thread scan only through the rounding of the folded start states (~1e-7 relative).
+constexpr int kNormSeg = 8, kNormPf = 8;
+template <bool WRITE>
+__device__ __forceinline__ float norm_scan_erb(const float *src, int64_t stride, float *dst, int E, int ta, int tb, float s, float alpha,
+                                               float one_m_alpha) {
+    float vn[kNormPf];
+#pragma unroll
+    for (int u = 0; u < kNormPf; u++) vn[u] = (ta + u < tb) ? src[(int64_t)(ta + u) * stride] : 0.f;
+    for (int t = ta; t < tb; t += kNormPf) {
+        float v[kNormPf];
+#pragma unroll
+        for (int u = 0; u < kNormPf; u++) {
+            v[u] = vn[u];
+            vn[u] = (t + kNormPf + u < tb) ? src[(int64_t)(t + kNormPf + u) * stride] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kNormPf; u++) {
+            if (t + u < tb) {
+                s = __fadd_rn(__fmul_rn(v[u], one_m_alpha), __fmul_rn(s, alpha));
+                if (WRITE) dst[(int64_t)(t + u) * E] = __fdiv_rn(__fsub_rn(v[u], s), 40.f);
+            }
+        }
+    }
+    return s;
+}
+template <bool WRITE>
+__device__ __forceinline__ float norm_scan_unit(const float2 *src, int64_t stride, float2 *dst, int Fd, int ta, int tb, float s, float alpha,
+                                                float one_m_alpha) {
+    float2 vn[kNormPf];
+#pragma unroll
+    for (int u = 0; u < kNormPf; u++) vn[u] = (ta + u < tb) ? src[(int64_t)(ta + u) * stride] : make_float2(0.f, 0.f);
+    for (int t = ta; t < tb; t += kNormPf) {
+        float2 v[kNormPf];
+        float nrm[kNormPf], sv[kNormPf];
+#pragma unroll
+        for (int u = 0; u < kNormPf; u++) {
+            v[u] = vn[u];
+            vn[u] = (t + kNormPf + u < tb) ? src[(int64_t)(t + kNormPf + u) * stride] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kNormPf; u++) nrm[u] = hypotf(v[u].x, v[u].y);
+#pragma unroll
+        for (int u = 0; u < kNormPf; u++) {
+            if (t + u < tb) s = __fadd_rn(__fmul_rn(nrm[u], one_m_alpha), __fmul_rn(s, alpha));
+            sv[u] = s;
+        }
+        if (WRITE) {
+#pragma unroll
+            for (int u = 0; u < kNormPf; u++) {
+                if (t + u < tb) {
+                    const float d = __fsqrt_rn(sv[u]);
+                    dst[(int64_t)(t + u) * Fd] = make_float2(__fdiv_rn(v[u].x, d), __fdiv_rn(v[u].y, d));
+                }
+            }
+        }
+    }
+    return s;
+}
+__global__ void __launch_bounds__(128 * kNormSeg) k_feat_norm_seg(const float *erb_in, int E, int64_t erb_stride_t,
+                            const float2 *__restrict__ spec_in, int Fd, int64_t spec_stride_t, int Tf,
+                            float alpha, const float *erb_state, const float *unit_state,
+                            float *feat_erb, float2 *__restrict__ feat_spec, int Ts, float *erb_state_out,
+                            float *unit_state_out) {
+    __shared__ float s_loc[kNormSeg][128];
+    const int b = blockIdx.x, j = threadIdx.x & 127, seg = threadIdx.x >> 7;
+    const float one_m_alpha = __fsub_rn(1.f, alpha);
+    const int L = (Tf + kNormSeg - 1) / kNormSeg;
+    const int ta = min(seg * L, Tf), tb = min(ta + L, Tf);
+    const bool is_erb = j < E, is_unit = !is_erb && j < E + Fd;
+    const float *esrc = erb_in + (int64_t)b * Ts * erb_stride_t + j;
+    float *edst = feat_erb + (int64_t)b * Ts * E + j;
+    const int k = j - E;
+    const float2 *usrc = spec_in + (int64_t)b * Ts * spec_stride_t + k;
+    float2 *udst = feat_spec + (int64_t)b * Ts * Fd + k;
+    float loc = 0.f;
+    if (seg + 1 < kNormSeg) {   // the last segment's local end state is never folded
+        if (is_erb) loc = norm_scan_erb<false>(esrc, erb_stride_t, nullptr, E, ta, tb, 0.f, alpha, one_m_alpha);
+        else if (is_unit) loc = norm_scan_unit<false>(usrc, spec_stride_t, nullptr, Fd, ta, tb, 0.f, alpha, one_m_alpha);
+    }
+    s_loc[seg][j] = loc;
+    __syncthreads();
+    if (!is_erb && !is_unit) return;
+    float s0;
+    if (is_erb) {
+        if (erb_state) s0 = erb_state[(int64_t)b * E + j];
+        else s0 = (E == 1) ? -60.f : __fadd_rn(-60.f, __fmul_rn((float)j, __fdiv_rn(-30.f, (float)(E - 1))));
+    } else {
+        if (unit_state) s0 = unit_state[(int64_t)b * Fd + k];
+        else s0 = (Fd == 1) ? 0.001f : __fadd_rn(0.001f, __fmul_rn((float)k, __fdiv_rn(__fsub_rn(0.0001f, 0.001f), (float)(Fd - 1))));
+    }
+    if (seg > 0) {
+        double sd = (double)s0;
+        const double pL = pow((double)alpha, (double)L);
+        for (int g = 0; g < seg; g++) {   // segment g covers min(L, Tf - g L) frames
+            const int lg = min(L, max(Tf - g * L, 0));
+            sd = sd * (lg == L ? pL : pow((double)alpha, (double)lg)) + (double)s_loc[g][j];
+        }
+        s0 = (float)sd;
+    }
+    float s;
+    if (is_erb) s = norm_scan_erb<true>(esrc, erb_stride_t, edst, E, ta, tb, s0, alpha, one_m_alpha);
+    else s = norm_scan_unit<true>(usrc, spec_stride_t, udst, Fd, ta, tb, s0, alpha, one_m_alpha);
+    if (seg == kNormSeg - 1 || tb == Tf) {   // the thread whose segment ends the window owns the carried state
+        if (ta < tb || seg == 0) {
+            if (is_erb && erb_state_out) erb_state_out[(int64_t)b * E + j] = s;
+            if (is_unit && unit_state_out) unit_state_out[(int64_t)b * Fd + k] = s;
+        }
     }
 }
 
@@ -905,7 +1041,12 @@ int launch_feat_norm(const float *d_erb, int E, int64_t erb_stride, const float 
     if (E + Fd > 1024) return fail(DFB_ERR_INVALID, "E + F > 1024 in norm scan");
     int threads = ((E + Fd + 31) / 32) * 32;
     DFB_PROF("k_feat_norm", s);
-    if (threads <= 128)
+    static const bool no_seg = getenv("DFB_NORM_SEG") && !atoi(getenv("DFB_NORM_SEG"));
+    if (threads <= 128 && Tf >= 16 * kNormSeg && !no_seg)
+        k_feat_norm_seg<<<(unsigned)C, 128 * kNormSeg, 0, s>>>(d_erb, E, erb_stride, (const float2 *)d_spec, Fd, spec_stride, (int)Tf,
+                                                            alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec,
+                                                            (int)(Ts > 0 ? Ts : Tf), d_erb_state_out, d_unit_state_out);
+    else if (threads <= 128)
         k_feat_norm<24><<<(unsigned)C, threads, 0, s>>>(d_erb, E, erb_stride, (const float2 *)d_spec, Fd, spec_stride, (int)Tf,
                                                        alpha, d_erb_state, d_unit_state, d_feat_erb, (float2 *)d_feat_spec,
                                                        (int)(Ts > 0 ? Ts : Tf), d_erb_state_out, d_unit_state_out);
