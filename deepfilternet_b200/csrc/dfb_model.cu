@@ -71,18 +71,23 @@ k_conv_in(const float *__restrict__ x, const float *__restrict__ w /*[kt][3][CIN
         s_in[i] = v;
     }
     const int cq = threadIdx.x & 15, fl = threadIdx.x >> 4;  // 16 channel quads x 16 f per pass
-    float4 wr[9 * CIN];
+    // taps of this thread's channel quad as two packed fp32 pairs: the MACs run as FFMA2 (fma.rn.f32x2, one issue slot for two
+    // channels; the scalar version of df_conv0 was issue bound: 69 % of the slots, FMA pipe 49 %)
+    unsigned long long wr[9 * CIN][2];
 #pragma unroll
-    for (int i = 0; i < 9 * CIN; i++)
-        wr[i] = (i >= (3 - kt) * 3 * CIN) ? *reinterpret_cast<const float4 *>(w + (i - (3 - kt) * 3 * CIN) * kCh + cq * 4)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 9 * CIN; i++) {
+        const float4 v = (i >= (3 - kt) * 3 * CIN) ? *reinterpret_cast<const float4 *>(w + (i - (3 - kt) * 3 * CIN) * kCh + cq * 4)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        wr[i][0] = f2_pack(v.x, v.y); wr[i][1] = f2_pack(v.z, v.w);
+    }
     const float4 bv = *reinterpret_cast<const float4 *>(bias + cq * 4);
+    const unsigned long long b01 = f2_pack(bv.x, bv.y), b23 = f2_pack(bv.z, bv.w);
     __syncthreads();
     for (int fr = 0; fr < kInFrames; fr++) {
         int t = t0 + fr;
         if (t >= T) break;
         for (int f = fl; f < F; f += 16) {
-            float4 acc = bv;
+            unsigned long long a01 = b01, a23 = b23;
 #pragma unroll
             for (int dt = 0; dt < 3; dt++) {
                 if (dt < 3 - kt) continue;
@@ -90,10 +95,13 @@ k_conv_in(const float *__restrict__ x, const float *__restrict__ w /*[kt][3][CIN
 #pragma unroll
                 for (int j = 0; j < 3 * CIN; j++) {
                     const float xv = row[j];
-                    const float4 ww = wr[dt * 3 * CIN + j];
-                    acc.x += xv * ww.x; acc.y += xv * ww.y; acc.z += xv * ww.z; acc.w += xv * ww.w;
+                    const unsigned long long xx = f2_pack(xv, xv);
+                    a01 = f2_fma(xx, wr[dt * 3 * CIN + j][0], a01);
+                    a23 = f2_fma(xx, wr[dt * 3 * CIN + j][1], a23);
                 }
             }
+            float4 acc;
+            f2_unpack(a01, acc.x, acc.y); f2_unpack(a23, acc.z, acc.w);
             acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
             *reinterpret_cast<float4 *>(out + (((int64_t)b * T + t) * F + f) * kCh + cq * 4) = acc;
         }
