@@ -1816,7 +1816,7 @@ static int forward_v1(dfb_model *m, Arena &arena, const float *d_feat_erb, const
 // Chunk pipeline of dfb_enhance / dfb_enhance_host: signals of at least 64 * chunks frames are cut into >= `chunks` time
 // chunks (device-pointer / host-pointer entry point); lanes = 2 overlaps the encoder phase of chunk c + 1 with the decoder
 // phase of chunk c, lanes = 1 runs the chunks back to back.  Defaults auto / 4 / 2 (DFB_DEVICE_CHUNKS, DFB_HOST_CHUNKS,
-// DFB_LANES at dfb_model_create); device_chunks = 0 (auto) is 1 chunk for more than 8 streams, else 3.
+// DFB_LANES at dfb_model_create); device_chunks = 0 (auto) is 3 chunks up to 8 streams, 2 up to 256, else 1.
 extern "C" int dfb_model_set_chunking(dfb_model *m, int device_chunks, int host_chunks, int lanes) {
     if (!m || device_chunks < 0 || host_chunks < 1 || lanes < 1 || lanes > 2) return fail(DFB_ERR_INVALID, "bad chunking parameters");
     m->dev_chunks = device_chunks; m->host_chunks = host_chunks; m->n_lanes = lanes;
@@ -2240,7 +2240,9 @@ extern "C" int dfb_enhance(dfb_model *m, dfb_state *st, const float *d_audio, in
     // (persistent kernels re-pay their prologues, short grids leave partial waves: 13.6 -> 14.1 ms for 4 chunks) than the
     // overlap of encoder and decoder phases gains -- except for a few streams, where everything is latency bound
     // (batch 1: RTF 0.00046 -> 0.00040 with 3 chunks).  0 = that policy.
-    const int dev_chunks = m->dev_chunks > 0 ? m->dev_chunks : (B <= 8 ? 3 : 1);
+    // (round 2, after the DSP kernels got shorter: 2 chunks gain 17 % at 32 x 10 s, 1.3 % at 128 x 10 s, 1 % at 256 x 10 s _ll
+    // and lose 1 % at 512 x 10 s)
+    const int dev_chunks = m->dev_chunks > 0 ? m->dev_chunks : (B <= 8 ? 3 : (B <= 256 ? 2 : 1));
     if ((rc = enhance_plan(m, st, B, Tf, dev_chunks, &group, &tc, &pipelined))) return rc;
     const float lim = (atten_lim_db > 0.f) ? powf(10.f, -atten_lim_db / 20.f) : 0.f;
     size_t off[16];

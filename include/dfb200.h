@@ -220,7 +220,7 @@ int dfb_model_set_precision(dfb_model *m, int mode);
 /* Chunk pipeline of dfb_enhance (device_chunks) / dfb_enhance_host (host_chunks): a signal of >= 64 * chunks frames is cut
  * into at least that many time chunks; lanes = 2 overlaps the encoder phase of chunk c + 1 with the decoder phase (the
  * recurrences) of chunk c on a second set of streams and a second workspace, lanes = 1 runs them back to back.
- * Defaults 0 (auto: one chunk for more than 8 streams, else 3) / 4 / 2, from the measured sweep in profiles/.  The output
+ * Defaults 0 (auto: 3 chunks up to 8 streams, 2 up to 256, else 1) / 4 / 2, from the measured sweep in profiles/.  The output
  * does not depend on these settings beyond fp32 reduction order (tests compare them). */
 int dfb_model_set_chunking(dfb_model *m, int device_chunks, int host_chunks, int lanes);
 /* init_df(post_filter=..., mask_only=...) (DeepFilterNet/df/enhance.py:101-187).  post_filter: Valin's post filter -- for
