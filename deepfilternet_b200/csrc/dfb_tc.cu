@@ -6,6 +6,8 @@
 // All three reach fp32-level accuracy on the BF16 tensor pipe by splitting both operands into BF16 hi + lo planes
 // (x = hi + lo to ~2^-17) and issuing hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM.
 #include <cooperative_groups.h>
+#include <map>
+#include <mutex>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -715,10 +717,15 @@ struct GruTcParams {
     int t0, Ts;
     int B, T, Bc;
     long long *dbg;      // optional [T][8] clock64 stamps of CTA 0 (0-3: MMA thread, 4-7: gate thread 0)
+    unsigned char *xbuf; // (XG) exchange scratch in global memory [cluster][2][CTA][kPiece]
 };
 
 
-template <int NS, int HH>
+// XG = 1: the new state travels through L2 instead of SM to SM -- every CTA stores its slice to a global scratch piece and
+// asks the TMA engine for ONE multicast bulk copy of that piece into all CTAs of the cluster (itself included); the
+// per-peer DSMEM copies (15 x 4 KB out and in per CTA and step at H = 512 / 32 streams, ~20 B/cycle on the SM-to-SM
+// network: more than half of the step) become one 4 KB read that the crossbar replicates.
+template <int NS, int HH, int XG>
 __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcParams p) {
     using Cfg = GtCfg<NS, HH>;
     constexpr int kGtThreads = Cfg::kThreads;
@@ -734,8 +741,8 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
     const int H = kGtH, T = p.T;
     for (int i = tid; i < (int)sizeof(sm.h) / 16; i += kGtThreads) reinterpret_cast<uint4 *>(&sm.h[0][0])[i] = make_uint4(0, 0, 0, 0);  // h0 = 0
     if (tid == 0) {
-        mbar_init(&sm.bar_h[0], 2);   // MMA thread's expect_tx arrive + one gate-warp arrive (own slice written)
-        mbar_init(&sm.bar_h[1], 2);
+        mbar_init(&sm.bar_h[0], XG ? 1 : 2);   // MMA thread's expect_tx arrive (+ one gate-warp arrive: own slice written)
+        mbar_init(&sm.bar_h[1], XG ? 1 : 2);
         mbar_init(&sm.t_full, 1);
         fence_barrier_init();
     }
@@ -796,7 +803,7 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
     __syncthreads();
     tc_fence_after();
     cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
-    const uint32_t step_bytes = (uint32_t)((kGtC - 1) * Cfg::kPiece);  // one piece from each of the peers
+    const uint32_t step_bytes = (uint32_t)((kGtC - (XG ? 0 : 1)) * Cfg::kPiece);  // one piece from each of the peers (XG: and the own one)
 
     if (warp == Cfg::kMmaWarp) {
         // ================================================================= MMA issuer (whole warp, elected lane issues)
@@ -889,16 +896,29 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
                 vhi = h0 | (uint32_t)h1 << 16;
                 vlo = l0 | (uint32_t)l1 << 16;
                 if (t + 1 < T) {
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff) = vhi;
-                    *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff + Cfg::kPlane) = vlo;
+                    if (XG) {   // own piece of the scratch buffer (same layout as the shared-memory slice)
+                        unsigned char *xp = p.xbuf + ((size_t)(group * 2 + (cur ^ 1)) * kGtC + rank) * Cfg::kPiece + (hoff - piece0);
+                        *reinterpret_cast<uint32_t *>(xp) = vhi;
+                        *reinterpret_cast<uint32_t *>(xp + Cfg::kPlane) = vlo;
+                    } else {
+                        *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff) = vhi;
+                        *reinterpret_cast<uint32_t *>(sm.h[cur ^ 1] + hoff + Cfg::kPlane) = vlo;
+                    }
                 }
             }
             if (gdbg) p.dbg[t * 8 + 6] = clock64();
             if (t + 1 < T) {
-                fence_proxy_async();  // own slice (generic stores) -> visible to the bulk-copy / tensor-core proxy
+                // own slice (generic stores) -> visible to the bulk-copy / tensor-core proxy
+                if (XG) fence_proxy_async_global(); else fence_proxy_async();
                 if (gdbg) p.dbg[t * 8 + 3] = clock64();
                 asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kGateThreads) : "memory");
-                if (lane == 0) {
+                if (XG) {
+                    if (tid == 0) {
+                        const unsigned char *xp = p.xbuf + ((size_t)(group * 2 + (cur ^ 1)) * kGtC + rank) * Cfg::kPiece;
+                        bulk_load_multicast(smem_u32(sm.h[cur ^ 1]) + piece0, xp, Cfg::kPiece, smem_u32(&sm.bar_h[cur ^ 1]),
+                                            (uint16_t)((1u << kGtC) - 1u));
+                    }
+                } else if (lane == 0) {
                     // gate warp w copies the CTA's slice to peers w, w + #warps, ... (skipping itself); the last gate warp
                     // also signals the local barrier
                     const uint32_t src = smem_u32(sm.h[cur ^ 1]) + piece0;
@@ -933,7 +953,26 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int NS, int HH>
+// exchange scratch of the XG variant: one buffer per (device, stream) -- launches on one stream are serialised, the two
+// decoders' recurrences run on different streams
+static unsigned char *gru_xbuf(cudaStream_t s, size_t bytes) {
+    struct Ent { unsigned char *p = nullptr; size_t cap = 0; };
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, Ent> pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    Ent &e = pool[{dev, s}];
+    if (e.cap < bytes) {
+        if (e.p) { cudaDeviceSynchronize(); cudaFree(e.p); e.p = nullptr; e.cap = 0; }
+        const size_t want = (bytes + (1u << 20)) & ~size_t((1u << 20) - 1);
+        if (cudaMalloc(&e.p, want) != cudaSuccess) { e.p = nullptr; return nullptr; }
+        e.cap = want;
+    }
+    return e.p;
+}
+
+template <int NS, int HH, int XG>
 static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     using Cfg = GtCfg<NS, HH>;
     static PerDeviceOnce attr_once;
@@ -945,8 +984,8 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     // tcgen05.alloc -- no change at 128 x 10 s with 1 .. 4 device chunks, 512 x 10 s: 45.2 vs 45.3 ms)
     const int smem = need > 120 * 1024 ? need : 120 * 1024;
     if (auto once_guard = attr_once.first()) {
-        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (Cfg::kC > 8) DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH, XG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        DFB_CUDA(cudaFuncSetAttribute(k_gru_tc<NS, HH, XG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(Cfg::kThreads);
@@ -959,8 +998,12 @@ static int launch_gru_tc_n(cudaStream_t s, GruTcParams p) {
     const int ngroups = (p.B + NS - 1) / NS;
     cfg.gridDim = dim3((unsigned)(ngroups * Cfg::kC));
     cfg.stream = s;
+    if (XG) {
+        p.xbuf = gru_xbuf(s, (size_t)ngroups * 2 * Cfg::kC * Cfg::kPiece);
+        if (!p.xbuf) return fail(DFB_ERR_OOM, "GRU exchange scratch");
+    }
     DFB_PROF(HH == 256 ? "k_gru_tc" : "k_gru_tc512", s);
-    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH>, p));
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_tc<NS, HH, XG>, p));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return DFB_OK;
 }
@@ -975,13 +1018,23 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
     static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
     // H = 512: at most 8 clusters of 16 CTAs are co-resident (one per GPC): beyond 128 streams 32 per cluster keep a
     // launch in one wave
-    if (H == 512) return (force ? force == 32 : B > 128) ? launch_gru_tc_n<32, 512>(s, p) : launch_gru_tc_n<16, 512>(s, p);
+    // exchange through L2 + multicast (k_gru_tc XG): bit 0: H = 512, bit 1: H = 256 / 32 streams, bit 2: H = 256 / 16 streams.
+    // Measured: H = 512 256 x 10 s 60.8 -> 51.0 ms, 32 x 10 s 12.0 -> 9.5 ms; H = 256 / 32 streams: 512 x 10 s 43.9 -> 41.6 ms;
+    // H = 256 / 16 streams: 128 x 10 s 11.88 -> 11.34 ms, 32 x 10 s 5.57 -> 5.09 ms, batch 1 3.79 -> 3.62 ms.  Default: all.
+    static const int xg = getenv("DFB_GRU_XG") ? atoi(getenv("DFB_GRU_XG")) : 7;
+    if (H == 512) {
+        const bool n32 = force ? force == 32 : B > 128;
+        if (xg & 1) return n32 ? launch_gru_tc_n<32, 512, 1>(s, p) : launch_gru_tc_n<16, 512, 1>(s, p);
+        return n32 ? launch_gru_tc_n<32, 512, 0>(s, p) : launch_gru_tc_n<16, 512, 0>(s, p);
+    }
     if (H != 256) return fail(DFB_ERR_UNSUPPORTED, "tensor-core recurrence: hidden size %d", H);
     // 16 streams per cluster have the shortest step (2600 cycles vs 3830 for 32) but 36 % more cluster time per stream:
     // from 256 streams on a launch needs several waves of the 15 co-resident clusters anyway, and 32 per cluster are faster
     // (512 x 10 s DeepFilterNet2: 48.1 -> 45.3 ms per step)
     const bool use32 = force ? force == 32 : ((wide && B > 64) || B >= 256);
-    return use32 ? launch_gru_tc_n<32, 256>(s, p) : launch_gru_tc_n<16, 256>(s, p);
+    if (use32 && (xg & 2)) return launch_gru_tc_n<32, 256, 1>(s, p);
+    if (!use32 && (xg & 4)) return launch_gru_tc_n<16, 256, 1>(s, p);
+    return use32 ? launch_gru_tc_n<32, 256, 0>(s, p) : launch_gru_tc_n<16, 256, 0>(s, p);
 }
 
 int cached_map_f32_sw128(CUtensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
