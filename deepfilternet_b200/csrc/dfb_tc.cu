@@ -1016,8 +1016,12 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
     GruTcParams p{xproj, whh, bhh, res, hout, hout_hi, hout_lo, planes_res, w ? w->h0 : nullptr, w ? w->hT : nullptr,
                   w ? w->t0 : 0, w ? w->Ts : T, B, T, 0, dbg};
     static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
-    // H = 512: at most 8 clusters of 16 CTAs are co-resident (one per GPC): beyond 128 streams 32 per cluster keep a
-    // launch in one wave
+    // (Tried: a "ping-pong" kernel in which a cluster owns 2 or 3 independent sub-batches of 16 streams -- own state buffers,
+    // accumulator columns, barriers and 8 gate warps each, one MMA warp serving them in turn -- so that one sub-batch's
+    // MMAs fill the other's gate / exchange latency.  Correct (parity tests green), but 48 MMAs of N = 16 take ~800 cycles to
+    // issue (16.7 per instruction, twice their math time), so two sub-batches keep the MMA warp busy 1800 of the 2650-cycle
+    // chain and the chain itself stretches: 3127 cycles per step for 2 x 16 streams vs 3050 for one N = 32 batch, 3947 for
+    // 3 x 16; 128 x 10 s 11.75 vs 11.31 ms.)
     // exchange through L2 + multicast (k_gru_tc XG): bit 0: H = 512, bit 1: H = 256 / 32 streams, bit 2: H = 256 / 16 streams.
     // Measured: H = 512 256 x 10 s 60.8 -> 51.0 ms, 32 x 10 s 12.0 -> 9.5 ms; H = 256 / 32 streams: 512 x 10 s 43.9 -> 41.6 ms;
     // H = 256 / 16 streams: 128 x 10 s 11.88 -> 11.34 ms, 32 x 10 s 5.57 -> 5.09 ms, batch 1 3.79 -> 3.62 ms.  Default: all.
