@@ -1036,6 +1036,10 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
     // from 256 streams on a launch needs several waves of the 15 co-resident clusters anyway, and 32 per cluster are faster
     // (512 x 10 s DeepFilterNet2: 48.1 -> 45.3 ms per step)
     const bool use32 = force ? force == 32 : ((wide && B > 64) || B >= 256);
+    // beyond 15 x 32 streams a launch of 32-stream clusters needs a second wave of the 15 co-resident clusters (512 streams:
+    // 16 clusters -> twice the time); 48 streams per cluster (N = 48, 768 gate threads) keep 512 streams in one wave
+    static const int no48 = getenv("DFB_GRU_NO48") ? atoi(getenv("DFB_GRU_NO48")) : 0;
+    if (use32 && !force && !no48 && B > 15 * 32) return launch_gru_tc_n<48, 256, 1>(s, p);
     if (use32 && (xg & 2)) return launch_gru_tc_n<32, 256, 1>(s, p);
     if (!use32 && (xg & 4)) return launch_gru_tc_n<16, 256, 1>(s, p);
     return use32 ? launch_gru_tc_n<32, 256, 0>(s, p) : launch_gru_tc_n<16, 256, 0>(s, p);
