@@ -554,9 +554,15 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_df_convp_tc(const __grid_cons
         mbar_wait_a(bar_raw, par);
         {   // fp32 rows -> BF16 hi / lo operand planes: thread = (time row, channel half)
             const uint32_t src = sb + kCvRawOff + (uint32_t)half * 16384u + (uint32_t)r * 128u;
+            // all eight loads first: the shared-memory accesses are volatile asm statements, so a load placed after a store
+            // in program order also waits for it -- as one loop every chunk paid the load latency (short-scoreboard was the
+            // top stall of this kernel)
+            float4 xs[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) xs[c] = lds128(src + (uint32_t)((c ^ (r & 7)) << 4));
 #pragma unroll
             for (int c = 0; c < 8; c++) {
-                float4 x = lds128(src + (uint32_t)((c ^ (r & 7)) << 4));
+                float4 x = xs[c];
                 if (zero) x = make_float4(0.f, 0.f, 0.f, 0.f);
                 uint32_t h0, l0, h1, l1;
                 bf16x2_split(x.x, x.y, h0, l0);
