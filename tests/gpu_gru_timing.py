@@ -30,7 +30,7 @@ d = buf[20:T - 20]
 if "gru_tc" in os.environ.get("DFB_PRECISION", "fp32+gru_tc+proj_tc+conv_tc"):
     step = np.diff(d[:, 0])
     print(f"TC GRU B={B}  cycles/step median {np.median(step):.0f}")
-    for a, b_, n in [(0, 1, "mma: wait h"), (1, 2, "mma: issue 48"), (4, 5, "gate: wait t_full"), (5, 6, "gate: ld+gates+write"), (6, 3, "gate: fence"), (3, 7, "gate: bar+copy+gstore")]:
+    for a, b_, n in [(0, 1, "mma: wait h"), (1, 2, "mma: issue 48 (W_hh h)"), (4, 5, "gate: wait t_full"), (5, 6, "gate: ld+gates+write"), (6, 3, "gate: fence"), (3, 7, "gate: bar+copy+gstore")]:
         seg = d[:, b_] - d[:, a]
         print(f"  {n:22s} median {np.median(seg):7.0f}  max {seg.max():7.0f}")
     print(f"  {'mma commit -> gate saw':22s} median {np.median(d[:, 5] - d[:, 2]):7.0f}")
