@@ -82,8 +82,6 @@ def kernel_model(cfg, g: dict) -> dict:
         "k_feat_norm": ("hbm", 2 * (4 * E + 8 * Fd), "bytes"),
         "k_apply_synthesis": ("hbm", 8 * cfg.freq_bins + 4 * E + 4 * Fd * O2 + 1920, "bytes"),
         "k_gru_tc": ("tensor", rec, "flops"), "k_gru": ("tensor", rec, "flops"), "k_gru_tc512": ("tensor", rec, "flops"),
-        # recurrence with the input projection folded into the step: W_hh h + W_ih x per layer
-        "k_gru_fx": ("tensor", rec + proj, "flops"),
         "k_gemm_bf16x3[gru_proj]": ("tensor", proj, "flops"), "k_grouped_linear[gru_proj]": ("tensor", proj, "flops"),
         "k_grouped_linear": ("tensor", gl, "flops"),
         # grouped linears on tcgen05: 2 * I * O / G flops per row are ~20 flop/B, far under the ridge -> HBM bound

@@ -180,12 +180,6 @@ struct GruWindow { const float *h0; float *hT; int t0, Ts; };
 int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const float *bhh, const float *res, float *hout,
                   unsigned short *hout_hi, unsigned short *hout_lo, int B, int T, long long *dbg = nullptr, int wide = 0,
                   int planes_res = 0, const GruWindow *w = nullptr, int H = 256);
-// the same recurrence with the input projection W_ih x_t folded into the step (H = 256, 256 inputs, at most 480 streams):
-// x arrives as BF16 hi / lo planes [B][Ts][256]; hout (fp32) may be null when only the planes are consumed
-int launch_gru_fx(cudaStream_t s, const unsigned short *x_hi, const unsigned short *x_lo, const float *wih, const float *whh,
-                  const float *bih, const float *bhh, const float *res, float *hout, unsigned short *hout_hi,
-                  unsigned short *hout_lo, int B, int T, long long *dbg, int wide, int planes_res, const GruWindow *w);
-bool gru_fx_supported(int B, int H, int in_dim);
 // BF16x3 tcgen05 GEMM on hi/lo planes (dfb_tc.cu)
 int launch_gemm_bf16x3(cudaStream_t s, const void *x_hi, const void *x_lo, int64_t ldx, const void *w_hi, const void *w_lo,
                        const float *bias, float *y, int64_t ldy, int64_t M, int N, int K);

@@ -1084,25 +1084,6 @@ int run_gru(dfb_model *m, cudaStream_t s, const char *name, int layers, int H, c
         if ((rc = need(m, (base + ".w_hh").c_str(), (int64_t)3 * H * H, &w_hh))) return rc;
         if ((rc = need(m, (base + ".b_ih").c_str(), 3 * H, &b_ih))) return rc;
         if ((rc = need(m, (base + ".b_hh").c_str(), 3 * H, &b_hh))) return rc;
-        if (tc_proj && gru_fx_supported(B, H, cur_dim)) {
-            // projection folded into the recurrence (k_gru_fx): no GEMM, no xproj round trip; middle layers only leave
-            // their BF16 planes (the next layer's operand) behind
-            const float *w_ih;
-            if ((rc = need(m, (base + ".w_ih").c_str(), (int64_t)3 * H * cur_dim, &w_ih))) return rc;
-            const bool last = l == layers - 1;
-            float *hs = ck && ck->h ? ck->h + (int64_t)l * B * H : nullptr;
-            GruWindow gw{ck && ck->have_state ? hs : nullptr, hs, t0, T};
-            const bool planes = last ? out_hi != nullptr : true;
-            rc = launch_gru_fx(s, cur_hi, cur_lo, w_ih, w_hh, b_ih, b_hh, last ? res_last : nullptr, last ? y : nullptr,
-                               planes ? (last ? out_hi : pl_hi) : nullptr, planes ? (last ? out_lo : pl_lo) : nullptr, B, Tn,
-                               m->gru_dbg, wide, last ? 1 : 0, &gw);
-            if (rc) return rc;
-            if (last && planes && out_planes_ok) *out_planes_ok = true;
-            cur_hi = pl_hi; cur_lo = pl_lo;
-            cur_in = last ? y : tmp_h;
-            cur_dim = H;
-            continue;
-        }
         if (tc_proj) {
             const float *w_hi, *w_lo;  // bf16 planes packed two per float
             if ((rc = need(m, (base + ".w_ih_hi").c_str(), (int64_t)3 * H * cur_dim / 2, &w_hi)) ||

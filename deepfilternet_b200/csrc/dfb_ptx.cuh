@@ -146,6 +146,42 @@ __device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tme
         : "memory");
 }
 
+// single-thread forms, for code that runs inside an `if (elect_one())` region: the compiler knows that exactly one
+// lane is active there, keeps the operands in uniform registers and moves nothing per instruction
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, e;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "

@@ -816,39 +816,46 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
 
     if (warp == Cfg::kMmaWarp) {
         // ================================================================= MMA issuer (whole warp, elected lane issues)
+        // ONE elected lane runs the whole time loop.  Inside an `if (elect_one())` region the compiler knows that a single lane
+        // is active: the tcgen05.mma operands (tensor-memory addresses, shared-memory descriptors) stay in uniform registers
+        // from step to step.  The earlier form -- all 32 lanes execute every call, each call elects its issuing lane -- made
+        // it move four operands per MMA from vector to uniform registers under the elect predicate: 11-17 SASS instructions
+        // and 16.7 cycles per MMA, against 9.6 cycles of tensor pipe at N = 16 (profiles/r02_mma_rate.txt).
         constexpr uint32_t idesc = umma_idesc_bf16(128, NS);
-        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0), tmem_du = __shfl_sync(0xffffffffu, tmem_d, 0);
-        const uint64_t bd0 = umma_desc_interleave(smem_u32(sm.h[0]), Cfg::kLbo, Cfg::kSbo);
-        const uint64_t bd1 = umma_desc_interleave(smem_u32(sm.h[1]), Cfg::kLbo, Cfg::kSbo);
-        const uint64_t wlo_desc = umma_desc_interleave(smem_u32(sm.wlo), Cfg::kWloLbo, 128);
-        (void)wlo_desc;
-        const bool dbg_on = p.dbg && blockIdx.x == 0 && lane == 0;
-        for (int t = 0; t < T; t++) {
-            const int cur = t & 1;
-            if (dbg_on) p.dbg[t * 8 + 0] = clock64();
-            if (lane == 0 && t + 1 < T) mbar_expect_tx(&sm.bar_h[cur ^ 1], step_bytes);
-            if (t > 0) mbar_wait(&sm.bar_h[cur], (uint32_t)(((t - 1) >> 1) & 1));
-            if (dbg_on) p.dbg[t * 8 + 1] = clock64();
-            fence_proxy_async();
-            tc_fence_after();
-            const uint64_t bb = cur ? bd1 : bd0;
+        if (elect_one()) {
+            const uint32_t tmem_u = tmem, tmem_du = tmem_d;
+            const uint64_t bd0 = umma_desc_interleave(smem_u32(sm.h[0]), Cfg::kLbo, Cfg::kSbo);
+            const uint64_t bd1 = umma_desc_interleave(smem_u32(sm.h[1]), Cfg::kLbo, Cfg::kSbo);
+            const uint64_t wlo_desc = umma_desc_interleave(smem_u32(sm.wlo), Cfg::kWloLbo, 128);
+            (void)wlo_desc;
+            const bool dbg_on = p.dbg && blockIdx.x == 0;
+            for (int t = 0; t < T; t++) {
+                const int cur = t & 1;
+                if (dbg_on) p.dbg[t * 8 + 0] = clock64();
+                if (t + 1 < T) mbar_expect_tx(&sm.bar_h[cur ^ 1], step_bytes);
+                if (t > 0) mbar_wait(&sm.bar_h[cur], (uint32_t)(((t - 1) >> 1) & 1));
+                if (dbg_on) p.dbg[t * 8 + 1] = clock64();
+                fence_proxy_async();
+                tc_fence_after();
+                const uint64_t bb = cur ? bd1 : bd0;
 #pragma unroll
-            for (int combo = 0; combo < 3; combo++) {
-                const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
+                for (int combo = 0; combo < 3; combo++) {
+                    const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
 #pragma unroll
-                for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
-                    const uint64_t bdesc = bb + (uint64_t)((ks * 2 * Cfg::kLbo + hb * Cfg::kPlane) >> 4);
-                    if (wa && ks * 16 >= Cfg::kLoTmemK) {   // upper part of W_lo from shared memory (SS form): two core matrices per K step
-                        umma_bf16_ss_elect(tmem_du, wlo_desc + (uint64_t)(((ks - Cfg::kLoTmemK / 16) * 2 * Cfg::kWloLbo) >> 4), bdesc, idesc, 1u);
-                    } else {
-                        umma_bf16_ts_elect(tmem_du, tmem_u + wa * kGtWCols + ks * 8, bdesc, idesc,
-                                           (combo == 0 && ks == 0) ? 0u : 1u);
+                    for (int ks = 0; ks < kGtH / 16; ks++) {  // K step of 16: 8 TMEM columns of W, two core matrices of h
+                        const uint64_t bdesc = bb + (uint64_t)((ks * 2 * Cfg::kLbo + hb * Cfg::kPlane) >> 4);
+                        if (wa && ks * 16 >= Cfg::kLoTmemK) {   // tail of W_lo from shared memory (SS form): two core matrices per K step
+                            umma_bf16_ss(tmem_du, wlo_desc + (uint64_t)(((ks - Cfg::kLoTmemK / 16) * 2 * Cfg::kWloLbo) >> 4), bdesc, idesc, 1u);
+                        } else {
+                            umma_bf16_ts(tmem_du, tmem_u + wa * kGtWCols + ks * 8, bdesc, idesc, (combo == 0 && ks == 0) ? 0u : 1u);
+                        }
                     }
                 }
+                if (dbg_on) p.dbg[t * 8 + 2] = clock64();
+                umma_commit(&sm.t_full);
             }
-            if (dbg_on) p.dbg[t * 8 + 2] = clock64();
-            umma_commit_elect(&sm.t_full);
         }
+        __syncwarp();
     } else {
         // ================================================================= gate warps (16 NS threads)
         // one item per thread: unit pair up = tid % 16 (units 2 up, 2 up + 1 of this CTA), stream s = tid / 16.
@@ -877,6 +884,16 @@ __global__ void __launch_bounds__(GtCfg<NS, HH>::kThreads, 1) k_gru_tc(GruTcPara
                 xr = *reinterpret_cast<const float2 *>(xp);
                 xz = *reinterpret_cast<const float2 *>(xp + H);
                 xn = *reinterpret_cast<const float2 *>(xp + 2 * H);
+                // xproj streams from HBM (3 KB per frame and stream, used once).  These loads are issued one MMA phase before
+                // the gates need them; since that phase shrank to ~460 cycles (elected-lane issue) a load that misses L2 under
+                // the feed-forward kernels' traffic arrived late (step 2070 cycles alone, 2525 inside the 128-stream pipeline).
+                // Pull the rows of frame t + 3 into L2 now: no registers, and the load above becomes an L2 hit.
+                if (t + 3 < T && (up & 7) == 0) {   // two requests per 128-byte line (16 threads x 8 bytes cover a gate's 32 units)
+                    const float *xq = xp + 3 * (3 * H);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xq));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xq + H));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xq + 2 * H));
+                }
             }
             const bool gdbg = p.dbg && blockIdx.x == 0 && tid == 0;
             if (gdbg) p.dbg[t * 8 + 4] = clock64();
@@ -1052,379 +1069,6 @@ int launch_gru_tc(cudaStream_t s, const float *xproj, const float *whh, const fl
     if (use32 && (xg & 2)) return launch_gru_tc_n<32, 256, 1>(s, p);
     if (!use32 && (xg & 4)) return launch_gru_tc_n<16, 256, 1>(s, p);
     return use32 ? launch_gru_tc_n<32, 256, 0>(s, p) : launch_gru_tc_n<16, 256, 0>(s, p);
-}
-
-// =========================================================== GRU step with the input projection folded in ====
-// k_gru_fx = k_gru_tc<NS, 256, XG = 1> plus W_ih x_t on the tensor core inside the step: the projection GEMM, its
-// [B, T, 3H] fp32 result (3 KB per frame, stream and layer written and read back) and one launch per layer disappear.
-//   * tensor memory: W_hh hi [0,128) | W_hh lo [128,256) | W_ih hi [256,384) | accumulator 2 x NS columns (double
-//     buffered) | the first 192 / 128 K elements of W_ih lo in what is left of the 512 columns.  The rest of W_ih lo
-//     lives in shared memory as an SS-form A operand (4 / 8 of the step's 96 MMAs), like the tail of W_hh lo in the
-//     H = 512 recurrence;
-//   * ONE accumulator for both products: lanes 0-63 = gates r, z (the tensor core sums the x and the h part), lanes
-//     64-95 = W_hn h, lanes 96-127 = W_in x -- the rows the 96-row recurrence left empty.  The x operand has zero rows
-//     64-95, the h operand zero rows 96-127;
-//   * the 48 MMAs of W_ih x_{t+1} are issued right behind the 48 of W_hh h_t and execute while the gate warps work on
-//     step t and the new state travels through L2 -- the tensor pipe was idle there; the step's critical path (h MMAs ->
-//     accumulator -> gates -> exchange) is the old one;
-//   * x_t: a loader warp copies the NS x 512 B hi / lo rows of frame t (BF16 planes written by the producing grouped
-//     linear or by the previous layer's recurrence) into a two-stage operand ring (same core-matrix layout as h) with
-//     asynchronous 16-byte copies that complete on the stage's mbarrier, up to two steps ahead of the MMA warp.
-template <int NS>
-struct GruFxSmem {
-    alignas(1024) unsigned char h[2][GtCfg<NS, 256>::kBuf];
-    alignas(1024) unsigned char x[2][GtCfg<NS, 256>::kBuf];
-    // W_ih lo, K elements [kXLoTmemK, 256): K-major core matrices [k / 8][16 row groups][8 x 16 B]; the first kXLoTmemK live in
-    // the tensor-memory columns behind the accumulators
-    static constexpr int kXLoTmemK = (128 - 2 * NS) / 32 * 64;   // 192 (16 streams) / 128 (32 streams)
-    alignas(128) unsigned char wlo[((256 - kXLoTmemK) / 8) * 16 * 128];
-    float pre[4][kGtU][NS + 1];
-    alignas(8) uint64_t bar_h[2];
-    uint64_t x_full[2], x_empty[2];
-    uint64_t t_full;
-    uint32_t tmem_base;
-};
-
-struct GruFxParams {
-    const unsigned short *x_hi, *x_lo;   // [B][Ts][256] BF16 planes of the layer input
-    const float *wih, *whh;              // [3H][256], [3H][H]
-    const float *bih, *bhh;              // [3H]
-    const float *res;                    // optional [B,Ts,H], added to the OUTPUT only
-    float *hout;                         // optional [B,Ts,H]
-    unsigned short *hout_hi, *hout_lo;   // optional planes of the output
-    int planes_res;
-    const float *h0;
-    float *hT;
-    int t0, Ts, B, T, Bc;
-    long long *dbg;
-    unsigned char *xbuf;
-};
-
-template <int NS>
-__global__ void __launch_bounds__(16 * NS + 64, 1) k_gru_fx(GruFxParams p) {
-    using Cfg = GtCfg<NS, 256>;
-    constexpr int kH = 256, kC = 8, kGateThreads = 16 * NS, kGateWarps = kGateThreads / 32, kThreads = kGateThreads + 64;
-    constexpr int kMmaWarp = kGateWarps, kLoadWarp = kGateWarps + 1;
-    constexpr uint32_t kColWhhLo = 128, kColWih = 256, kColD = 384, kColWihLo = 384 + 2 * NS;   // TMEM columns
-    constexpr int kXLoTmemK = GruFxSmem<NS>::kXLoTmemK;
-    constexpr uint32_t kWloLbo = 16 * 128;
-    static_assert(offsetof(GruFxSmem<NS>, x) == 2 * Cfg::kBuf, "h and x buffers are contiguous");
-    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    GruFxSmem<NS> &sm = *reinterpret_cast<GruFxSmem<NS> *>(((uintptr_t)tc_smem_raw + 1023) & ~uintptr_t(1023));
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
-    const int group = blockIdx.x / kC;
-    const int b0 = group * p.Bc;
-    const int nb = min(p.Bc, p.B - b0);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int T = p.T;
-    // h0 = 0; the x ring's rows of absent streams stay zero
-    for (int i = tid; i < 4 * Cfg::kBuf / 16; i += kThreads) reinterpret_cast<uint4 *>(&sm.h[0][0])[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) {
-        mbar_init(&sm.bar_h[0], 1);
-        mbar_init(&sm.bar_h[1], 1);
-        mbar_init(&sm.x_full[0], 1);
-        mbar_init(&sm.x_full[1], 1);
-        mbar_init(&sm.x_empty[0], 1);
-        mbar_init(&sm.x_empty[1], 1);
-        mbar_init(&sm.t_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = sm.tmem_base;
-    if (p.h0) {  // carried state: every CTA builds the whole operand h_{-1} of its streams in buffer 0
-        for (int i = tid; i < nb * (kH / 2); i += kThreads) {
-            const int s = i / (kH / 2), gu = (i - s * (kH / 2)) * 2;
-            const float2 hv = *reinterpret_cast<const float2 *>(p.h0 + (int64_t)(b0 + s) * kH + gu);
-            unsigned short h0b, l0b, h1b, l1b;
-            bf16_split(hv.x, h0b, l0b);
-            bf16_split(hv.y, h1b, l1b);
-            const uint32_t off = (uint32_t)((gu >> 3) * Cfg::kLbo + (s >> 3) * Cfg::kSbo + (s & 7) * 16 + (gu & 7) * 2);
-            *reinterpret_cast<uint32_t *>(sm.h[0] + off) = h0b | (uint32_t)h1b << 16;
-            *reinterpret_cast<uint32_t *>(sm.h[0] + off + Cfg::kPlane) = l0b | (uint32_t)l1b << 16;
-        }
-        fence_proxy_async();
-    }
-    // ---- weights: tensor-memory lane rho = operand row.  h operand: rows 0-95 = W_hh rows (gate rho / 32, unit rho % 32),
-    //      96-127 zero.  x operand: rows 0-63 = W_ir, W_iz, 64-95 zero, 96-127 = W_in.
-    if (warp < 4) {
-        const int rho = warp * 32 + lane;
-        const int gx = warp == 3 ? 2 : (warp == 2 ? -1 : warp);
-        const float *srch = p.whh + ((int64_t)(warp < 3 ? warp : 0) * kH + rank * kGtU + lane) * kH;
-        const float *srcx = p.wih + ((int64_t)(gx < 0 ? 0 : gx) * kH + rank * kGtU + lane) * kH;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; pass++) {
-            const float *src = pass ? srcx : srch;
-            const bool valid = pass ? gx >= 0 : warp < 3;
-#pragma unroll 1
-            for (int cb = 0; cb < kH / 64; cb++) {  // 32 columns = 64 elements per store
-                uint32_t vh[32], vl[32];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) x = *reinterpret_cast<const float4 *>(src + cb * 64 + i * 2);
-                    unsigned short h0, l0, h1, l1, h2, l2, h3, l3;
-                    bf16_split(x.x, h0, l0); bf16_split(x.y, h1, l1); bf16_split(x.z, h2, l2); bf16_split(x.w, h3, l3);
-                    vh[i] = h0 | (uint32_t)h1 << 16; vh[i + 1] = h2 | (uint32_t)h3 << 16;
-                    vl[i] = l0 | (uint32_t)l1 << 16; vl[i + 1] = l2 | (uint32_t)l3 << 16;
-                }
-                const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + cb * 32;
-                if (pass == 0) {
-                    tmem_st32(ta, vh);
-                    tmem_st32(ta + kColWhhLo, vl);
-                } else {
-                    tmem_st32(ta + kColWih, vh);
-                    if (cb * 64 < kXLoTmemK) {
-                        tmem_st32(ta + kColWihLo, vl);
-                    } else {
-                        // row rho, elements [64 cb, +64) = 8 core-matrix rows of 16 bytes: core matrix (k - kXLoTmemK) / 8, row group rho / 8
-                        const uint32_t base = smem_u32(sm.wlo) + (uint32_t)(rho >> 3) * 128u + (uint32_t)(rho & 7) * 16u;
-#pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(cb * 8 + j - kXLoTmemK / 8) * kWloLbo),
-                                         "r"(vl[4 * j]), "r"(vl[4 * j + 1]), "r"(vl[4 * j + 2]), "r"(vl[4 * j + 3]) : "memory");
-                    }
-                }
-            }
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        fence_proxy_async();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    cluster.sync();  // every CTA's barriers are initialised and its h buffers zeroed before any remote copy
-    const uint32_t step_bytes = (uint32_t)(kC * Cfg::kPiece);  // one piece from every CTA of the cluster (the own one included)
-
-    if (warp == kMmaWarp) {
-        // ================================================================= MMA issuer (whole warp, elected lane issues)
-        constexpr uint32_t idesc = umma_idesc_bf16(128, NS);
-        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-        const uint64_t hd0 = umma_desc_interleave(smem_u32(sm.h[0]), Cfg::kLbo, Cfg::kSbo);
-        const uint64_t hd1 = umma_desc_interleave(smem_u32(sm.h[1]), Cfg::kLbo, Cfg::kSbo);
-        const uint64_t xd0 = umma_desc_interleave(smem_u32(sm.x[0]), Cfg::kLbo, Cfg::kSbo);
-        const uint64_t xd1 = umma_desc_interleave(smem_u32(sm.x[1]), Cfg::kLbo, Cfg::kSbo);
-        const uint64_t wlo_desc = umma_desc_interleave(smem_u32(sm.wlo), kWloLbo, 128);
-        const bool dbg_on = p.dbg && blockIdx.x == 0 && lane == 0;
-        // W_ih x_tau into accumulator buffer tau & 1 (the first MMA overwrites it)
-        auto issue_x = [&](int tau) {
-            const int st = tau & 1;
-            mbar_wait(&sm.x_full[st], (uint32_t)((tau >> 1) & 1));   // the loader has fenced its copies for the tensor core's proxy
-            tc_fence_after();
-            const uint64_t xb = st ? xd1 : xd0;
-            const uint32_t d = tmem_u + kColD + (uint32_t)(st * NS);
-#pragma unroll
-            for (int combo = 0; combo < 3; combo++) {   // hi*hi, lo*hi, hi*lo
-                const int hb = (combo == 2) ? 1 : 0;
-#pragma unroll
-                for (int ks = 0; ks < kH / 16; ks++) {
-                    const uint64_t bdesc = xb + (uint64_t)((ks * 2 * Cfg::kLbo + hb * Cfg::kPlane) >> 4);
-                    if (combo == 1 && ks * 16 < kXLoTmemK)
-                        umma_bf16_ts_elect(d, tmem_u + kColWihLo + ks * 8, bdesc, idesc, 1u);
-                    else if (combo == 1)   // the rest of W_ih lo from shared memory (SS form)
-                        umma_bf16_ss_elect(d, wlo_desc + (uint64_t)(((ks - kXLoTmemK / 16) * 2 * kWloLbo) >> 4), bdesc, idesc, 1u);
-                    else
-                        umma_bf16_ts_elect(d, tmem_u + kColWih + ks * 8, bdesc, idesc, (combo == 0 && ks == 0) ? 0u : 1u);
-                }
-            }
-            umma_commit_elect(&sm.x_empty[st]);   // stage st may be refilled once these MMAs have read it
-        };
-        if (T > 0) issue_x(0);
-        for (int t = 0; t < T; t++) {
-            const int cur = t & 1;
-            if (dbg_on) p.dbg[t * 8 + 0] = clock64();
-            if (lane == 0 && t + 1 < T) mbar_expect_tx(&sm.bar_h[cur ^ 1], step_bytes);
-            if (t > 0) mbar_wait(&sm.bar_h[cur], (uint32_t)(((t - 1) >> 1) & 1));
-            if (dbg_on) p.dbg[t * 8 + 1] = clock64();
-            // no proxy fence here: the state arrives by bulk copy (async proxy) and buffer 0 was fenced in the prologue; a
-            // fence.proxy.async in this warp waited for the loader's copies in flight (h MMA issue 960 -> 1620 cycles)
-            tc_fence_after();
-            const uint64_t bb = cur ? hd1 : hd0;
-            const uint32_t d = tmem_u + kColD + (uint32_t)(cur * NS);
-#pragma unroll
-            for (int combo = 0; combo < 3; combo++) {
-                const int wa = (combo == 1) ? 1 : 0, hb = (combo == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
-#pragma unroll
-                for (int ks = 0; ks < kH / 16; ks++) {
-                    const uint64_t bdesc = bb + (uint64_t)((ks * 2 * Cfg::kLbo + hb * Cfg::kPlane) >> 4);
-                    umma_bf16_ts_elect(d, tmem_u + wa * kColWhhLo + ks * 8, bdesc, idesc, 1u);   // on top of W_ih x_t
-                }
-            }
-            if (dbg_on) p.dbg[t * 8 + 2] = clock64();
-            umma_commit_elect(&sm.t_full);
-            if (t + 1 < T) issue_x(t + 1);
-        }
-    } else if (warp == kLoadWarp) {
-        // ================================================================= x loader: frame tau -> stage tau & 1
-        // lane = (stream within an 8-row group, 16-byte chunk mod 4): one instruction moves 8 rows x 64 contiguous bytes.
-        // Asynchronous 16-byte copies (cp.async, LDGSTS) that complete on the stage's mbarrier: nothing passes through
-        // registers and the warp never waits for memory -- the first version (8 loads into registers, 8 stores, per row
-        // group and plane) exposed one L2 / HBM round trip per batch: 8 batches = 5600 cycles per step at 32 streams, the
-        // whole step waited for it (7800 instead of 3800 cycles).
-        const int sl = lane & 7, kcl = lane >> 3;
-        for (int tau = 0; tau < T; tau++) {
-            const int st = tau & 1;
-            if (tau >= 2) mbar_wait(&sm.x_empty[st], (uint32_t)(((tau >> 1) - 1) & 1));
-            const uint32_t dst0 = smem_u32(sm.x[st]) + (uint32_t)(sl * 16 + kcl * Cfg::kLbo);
-#pragma unroll
-            for (int s8 = 0; s8 < NS / 8; s8++) {
-                const int s = s8 * 8 + sl;
-                if (s < nb) {
-                    const int64_t row = ((int64_t)(b0 + s) * p.Ts + p.t0 + tau) * kH + kcl * 8;
-#pragma unroll
-                    for (int pl = 0; pl < 2; pl++) {
-                        const unsigned short *src = (pl ? p.x_lo : p.x_hi) + row;
-#pragma unroll
-                        for (int kb = 0; kb < 8; kb++)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                                             dst0 + (uint32_t)(kb * 4 * Cfg::kLbo + s8 * Cfg::kSbo + pl * Cfg::kPlane)),
-                                         "l"(src + kb * 32)
-                                         : "memory");
-                    }
-                }
-            }
-            // the stage's copies are all in flight together: wait for them here (one round trip per step, two steps of slack),
-            // make them visible to the tensor core's proxy, then hand the stage to the MMA warp
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.x_full[st]);
-        }
-    } else {
-        // ================================================================= gate warps (16 NS threads)
-        // one item per thread: unit pair up = tid % 16 (units 2 up, 2 up + 1 of this CTA), stream s = tid / 16
-        const int up = tid & 15, s = tid >> 4;
-        const bool active = s < nb;
-        const int gu = rank * kGtU + 2 * up;       // first of the two global hidden units of this thread
-        float hprev0 = 0.f, hprev1 = 0.f;
-        if (p.h0 && active) {
-            const float2 hv = *reinterpret_cast<const float2 *>(p.h0 + (int64_t)(b0 + s) * kH + gu);
-            hprev0 = hv.x; hprev1 = hv.y;
-        }
-        const float2 bir = *reinterpret_cast<const float2 *>(p.bih + gu), biz = *reinterpret_cast<const float2 *>(p.bih + kH + gu),
-                     bin = *reinterpret_cast<const float2 *>(p.bih + 2 * kH + gu);
-        const float2 bhr = *reinterpret_cast<const float2 *>(p.bhh + gu), bhz = *reinterpret_cast<const float2 *>(p.bhh + kH + gu),
-                     bhn = *reinterpret_cast<const float2 *>(p.bhh + 2 * kH + gu);
-        const float2 br = make_float2(bir.x + bhr.x, bir.y + bhr.y), bz = make_float2(biz.x + bhz.x, biz.y + bhz.y);
-        const uint32_t hoff = (uint32_t)((gu >> 3) * Cfg::kLbo + (s >> 3) * Cfg::kSbo + (s & 7) * 16 + (gu & 7) * 2);
-        const uint32_t piece0 = (uint32_t)(rank * Cfg::kPiece);  // this CTA's slice of a buffer
-        // TMEM loaders: warp w reads lane quarter w % 4 (r, z, W_hn h, W_in x), streams [16 (w / 4), +16)
-        const bool loader = (warp >> 2) < NS / 16;
-        for (int t = 0; t < T; t++) {
-            const int cur = t & 1;
-            uint32_t vhi = 0, vlo = 0;
-            const bool gdbg = p.dbg && blockIdx.x == 0 && tid == 0;
-            if (gdbg) p.dbg[t * 8 + 4] = clock64();
-            mbar_wait(&sm.t_full, (uint32_t)(t & 1));
-            if (gdbg) p.dbg[t * 8 + 5] = clock64();
-            tc_fence_after();
-            if (loader) {
-                const int g = warp & 3, q = warp >> 2;
-                float v[16];
-                tmem_ld16(tmem + kColD + (uint32_t)(cur * NS) + ((uint32_t)(g * 32) << 16) + 16 * q, v);
-#pragma unroll
-                for (int ss = 0; ss < 16; ss++) sm.pre[g][lane][16 * q + ss] = v[ss];
-            }
-            tc_fence_before();
-            asm volatile("bar.sync 1, %0;" ::"n"(kGateThreads) : "memory");  // the gate warps only
-            if (active) {
-                const int u0 = 2 * up;
-                const float r0 = gt_sigmoid(sm.pre[0][u0][s] + br.x), r1 = gt_sigmoid(sm.pre[0][u0 + 1][s] + br.y);
-                const float z0 = gt_sigmoid(sm.pre[1][u0][s] + bz.x), z1 = gt_sigmoid(sm.pre[1][u0 + 1][s] + bz.y);
-                const float n0 = gt_tanh(sm.pre[3][u0][s] + bin.x + r0 * (sm.pre[2][u0][s] + bhn.x));
-                const float n1 = gt_tanh(sm.pre[3][u0 + 1][s] + bin.y + r1 * (sm.pre[2][u0 + 1][s] + bhn.y));
-                hprev0 = (1.f - z0) * n0 + z0 * hprev0;
-                hprev1 = (1.f - z1) * n1 + z1 * hprev1;
-                unsigned short h0, l0, h1, l1;
-                bf16_split(hprev0, h0, l0);
-                bf16_split(hprev1, h1, l1);
-                vhi = h0 | (uint32_t)h1 << 16;
-                vlo = l0 | (uint32_t)l1 << 16;
-                if (t + 1 < T) {   // own piece of the exchange scratch (same layout as the shared-memory slice)
-                    unsigned char *xp = p.xbuf + ((size_t)(group * 2 + (cur ^ 1)) * kC + rank) * Cfg::kPiece + (hoff - piece0);
-                    *reinterpret_cast<uint32_t *>(xp) = vhi;
-                    *reinterpret_cast<uint32_t *>(xp + Cfg::kPlane) = vlo;
-                }
-            }
-            if (gdbg) p.dbg[t * 8 + 6] = clock64();
-            if (t + 1 < T) {
-                fence_proxy_async_global();   // own slice (generic stores) -> visible to the bulk copy
-                if (gdbg) p.dbg[t * 8 + 3] = clock64();
-                asm volatile("bar.sync 1, %0;" ::"n"(kGateThreads) : "memory");
-                if (tid == 0) {
-                    const unsigned char *xp = p.xbuf + ((size_t)(group * 2 + (cur ^ 1)) * kC + rank) * Cfg::kPiece;
-                    bulk_load_multicast(smem_u32(sm.h[cur ^ 1]) + piece0, xp, Cfg::kPiece, smem_u32(&sm.bar_h[cur ^ 1]),
-                                        (uint16_t)((1u << kC) - 1u));
-                }
-            } else {
-                asm volatile("bar.sync 1, %0;" ::"n"(kGateThreads) : "memory");
-            }
-            if (active) {  // global result last: nothing on the recurrence's critical path waits for it
-                const int64_t o = ((int64_t)(b0 + s) * p.Ts + p.t0 + t) * kH + gu;
-                float2 ov = make_float2(hprev0, hprev1);
-                if (p.hT && t + 1 == T) *reinterpret_cast<float2 *>(p.hT + (int64_t)(b0 + s) * kH + gu) = ov;
-                if (p.res) { const float2 rv = *reinterpret_cast<const float2 *>(p.res + o); ov.x += rv.x; ov.y += rv.y; }
-                if (p.hout) *reinterpret_cast<float2 *>(p.hout + o) = ov;
-                if (p.hout_hi) {  // residual-free h (the next layer's input) or the layer output
-                    if (p.planes_res && p.res) bf16x2_split(ov.x, ov.y, vhi, vlo);
-                    *reinterpret_cast<uint32_t *>(p.hout_hi + o) = vhi;
-                    *reinterpret_cast<uint32_t *>(p.hout_lo + o) = vlo;
-                }
-            }
-            if (gdbg) p.dbg[t * 8 + 7] = clock64();
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster.sync();  // no CTA exits while peers may still address its shared memory
-    if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-template <int NS>
-static int launch_gru_fx_n(cudaStream_t s, GruFxParams p) {
-    using Cfg = GtCfg<NS, 256>;
-    static PerDeviceOnce attr_once;
-    const int smem = (int)sizeof(GruFxSmem<NS>) + 1024;   // > half of the shared memory: one CTA per SM (all 512 TMEM columns)
-    if (auto once_guard = attr_once.first()) {
-        DFB_CUDA(cudaFuncSetAttribute(k_gru_fx<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(16 * NS + 64);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = Cfg::kC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    p.Bc = NS;
-    const int ngroups = (p.B + NS - 1) / NS;
-    cfg.gridDim = dim3((unsigned)(ngroups * Cfg::kC));
-    cfg.stream = s;
-    p.xbuf = gru_xbuf(s, (size_t)ngroups * 2 * Cfg::kC * Cfg::kPiece);
-    if (!p.xbuf) return fail(DFB_ERR_OOM, "GRU exchange scratch");
-    DFB_PROF("k_gru_fx", s);
-    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_gru_fx<NS>, p));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return DFB_OK;
-}
-
-// DFB_GRU_FX=0 keeps the projection GEMM + k_gru_tc pair (experiments)
-bool gru_fx_supported(int B, int H, int in_dim) {
-    static const int on = getenv("DFB_GRU_FX") ? atoi(getenv("DFB_GRU_FX")) : 1;
-    return on && H == 256 && in_dim == 256 && B <= 15 * 32;   // beyond 480 streams: 48 per cluster (k_gru_tc<48>), no room for x
-}
-
-int launch_gru_fx(cudaStream_t s, const unsigned short *x_hi, const unsigned short *x_lo, const float *wih, const float *whh,
-                  const float *bih, const float *bhh, const float *res, float *hout, unsigned short *hout_hi,
-                  unsigned short *hout_lo, int B, int T, long long *dbg, int wide, int planes_res, const GruWindow *w) {
-    GruFxParams p{x_hi, x_lo, wih, whh, bih, bhh, res, hout, hout_hi, hout_lo, planes_res, w ? w->h0 : nullptr,
-                  w ? w->hT : nullptr, w ? w->t0 : 0, w ? w->Ts : T, B, T, 0, dbg, nullptr};
-    static const int force = getenv("DFB_GRU_NS") ? atoi(getenv("DFB_GRU_NS")) : 0;
-    const bool use32 = force ? force == 32 : ((wide && B > 64) || B >= 256);   // same policy as launch_gru_tc
-    return use32 ? launch_gru_fx_n<32>(s, p) : launch_gru_fx_n<16>(s, p);
 }
 
 int cached_map_f32_sw128(CUtensorMap *out, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
