@@ -20,7 +20,7 @@ echo "launches per forward: $L"
 DFB_DEVICE_CHUNKS=1 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_ -s $((3 * L)) -c $L -f -o gpurun_out/r02_full \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --extra none > gpurun_out/r02_ncu_f.log 2>&1
 ncu -i gpurun_out/r02_full.ncu-rep --page raw --csv > gpurun_out/r02_full_raw.csv 2>/dev/null
-for k in k_gru_fx k_dwpw_bx k_apply_synthesis k_analysis; do
+for k in k_gru_tc k_dwpw_bx k_apply_synthesis k_analysis; do
   ncu -i gpurun_out/r02_full.ncu-rep --page source --csv -k regex:$k > gpurun_out/r02_src_$k.csv 2>/dev/null
 done
 rm -f gpurun_out/r02_full.ncu-rep
