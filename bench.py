@@ -327,6 +327,11 @@ class Ctx:
             self.dist.barrier()
             self.torch.cuda.synchronize()
 
+    def gather_rows(self, vals):
+        """[world][len(vals)]: every rank's figures on every rank (per-GPU report; one all_gather, outside the timed regions)."""
+        from deepfilternet_b200.sharding import gather_rank_rows
+        return gather_rank_rows(vals, device=f"cuda:{self.dev}")
+
     def max_over_ranks(self, vals):
         t = self.torch.tensor(vals, dtype=self.torch.float64, device=f"cuda:{self.dev}")
         if self.world > 1:
@@ -449,6 +454,22 @@ def measure(ctx: Ctx, cfg_id: int, model_name: str, streams: int, seconds: int, 
                 "kernel_frac_of_peak": {k: frac_of(k) for k in sorted(prof, key=lambda k: -prof[k][1])},
                 "end_to_end_tensor_frac": (value * 100 * FLOP_PER_FRAME.get(model_name, 0) / n_gpus) / (tf_sust * 1e12),
                 "end_to_end_hbm_frac_21264B": (value * 100 * 21264 / n_gpus) / (hbm * 1e9)}
+    # per-GPU report: each rank's own device / end-to-end step time and the roofline fraction of ITS dominant
+    # kernel, gathered on every rank; `value` above is the aggregate over ranks at the slowest rank's time
+    knames = sorted(km)
+    own = [ms / steps, e2e_s * 1e3 / steps, (achieved / peak) if peak else float("nan"), avg_launch_s * 1e3,
+           float(knames.index(kname.split("[")[0] if kname not in km else kname)) if (kname in km or kname.split("[")[0] in km) else -1.0,
+           tot_ms / total_prof_ms]
+    rows = ctx.gather_rows(own)
+    per_gpu = None
+    try:
+        num = lambda x: None if x != x else x   # NaN -> null
+        per_gpu = [{"rank": r, "ms_per_step": row[0], "value": streams * seconds / (row[0] / 1e3),
+                    "e2e_ms_per_step": row[1], "e2e_value": streams * seconds / (row[1] / 1e3),
+                    "roofline_kernel": knames[int(row[4])] if row[4] >= 0 else None, "roofline_frac": num(row[2]),
+                    "avg_launch_ms": num(row[3]), "share_of_step": num(row[5])} for r, row in enumerate(rows)]
+    except Exception as e:  # a formatting problem must not take the line down
+        per_gpu = [{"error": f"{type(e).__name__}: {e}"}]
     workload = (f"{model_name}, batch={streams} x {seconds} s 48 kHz synthetic noisy streams per GPU "
                 f"({BASELINE_NAME.get(cfg_id, 'custom')}), pad=True, {frames} frames/stream")
     res = {"cfg": cfg_id, "workload": workload, "model": model_name, "streams_per_gpu": streams, "seconds": seconds,
@@ -457,7 +478,7 @@ def measure(ctx: Ctx, cfg_id: int, model_name: str, streams: int, seconds: int, 
            "gpu_launches": launches,
            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(host_in.numel() * 4),
                    "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": t_e2e * 1e3 / steps},
-           "roofline": roofline, "parity": parity, "workspace_bytes": model.workspace_bytes()}
+           "roofline": roofline, "per_gpu": per_gpu, "parity": parity, "workspace_bytes": model.workspace_bytes()}
     # RTF at batch = 1 (BASELINE.json metric, second half): one stream, device resident and end to end
     a1 = audio[:1].contiguous()
     o1 = torch.empty_like(a1)
@@ -564,7 +585,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": config, "clocks": clk, "gpu_launches": head["gpu_launches"], "e2e": head["e2e"],
             "rtf_batch1": head["rtf_batch1"], "rtf_batch1_e2e": head["rtf_batch1_e2e"], "rtf_note": head["rtf_note"],
-            "roofline": head["roofline"], "parity": head["parity"], "extra": {"configs": extras}}
+            "roofline": head["roofline"], "per_gpu": head["per_gpu"], "parity": head["parity"], "extra": {"configs": extras}}
     if n_gpus == 1 and not a.no_cpu_baseline:
         v, s_step, ns = cpu_reference_run(cfg, sd, seconds, 2, 0, threads, budget_s=25.0)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",

@@ -23,6 +23,18 @@ def shard_sizes(n_streams: int, world_size: int) -> List[int]:
     return [shard_range(n_streams, r, world_size)[1] - shard_range(n_streams, r, world_size)[0] for r in range(world_size)]
 
 
+def gather_rank_rows(vals, device=None) -> List[List[float]]:
+    """Every rank contributes the same number of floats and receives all of them as [world][len(vals)]: one all_gather of
+    a float64 tensor.  bench.py uses it for the per-GPU report (SURVEY.md 8e: "per-GPU roofline report + aggregate");
+    it is not on the data path.  Without an initialised process group the result is the caller's own row."""
+    t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device=device)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [[float(x) for x in t]]
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t)
+    return [[float(x) for x in p.cpu()] for p in parts]
+
+
 def enhance_sharded(enhance_fn: Callable[[torch.Tensor], torch.Tensor], audio: torch.Tensor,
                     rank: Optional[int] = None, world_size: Optional[int] = None, gather_to: Optional[int] = None):
     """Runs `enhance_fn` on this rank's shard of `audio` [B, T] (every rank passes the same global batch, or any

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from deepfilternet_b200.sharding import enhance_sharded, shard_range, shard_sizes
+from deepfilternet_b200.sharding import enhance_sharded, gather_rank_rows, shard_range, shard_sizes
 
 
 def test_shard_range_partitions_exactly():
@@ -20,6 +20,10 @@ def test_shard_range_partitions_exactly():
             assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def test_gather_rank_rows_without_process_group():
+    assert gather_rank_rows([1, 2.5]) == [[1.0, 2.5]]
 
 
 def _free_port():
@@ -49,6 +53,9 @@ def _worker(rank, world, port, n_streams, q):
         ok = ok and out is not None and torch.equal(out, audio * 2.0 + 1.0)
     else:
         ok = ok and out is None
+    # per-GPU report of bench.py: every rank gets every rank's row
+    rows = gather_rank_rows([rank, 10.0 + rank, float("nan")])
+    ok = ok and len(rows) == world and all(rows[r][0] == r and rows[r][1] == 10.0 + r and rows[r][2] != rows[r][2] for r in range(world))
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
