@@ -660,11 +660,11 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_df_convp_tc(const __grid_cons
 // bulk DSMEM copy per peer (cp.async.bulk shared::cta -> shared::cluster) that completes bytes on
 // the peer's mbarrier -- no cluster barrier or fence on the step's critical path.  The fp32 hidden
 // state of a CTA's own units stays in registers; only the MMA operand is BF16.
-// Measured step timeline (clock64, B = 128): 48 MMAs 640 cycles, commit -> gates 110, TMEM load +
-// gates 590, fence + barrier + copy issue 310, DSMEM flight 720  =>  2380 cycles / step
-// (the FFMA kernel k_gru: 4700).  History: issuing the MMAs from inside `if (lane == 0)` cost
-// ~50 cycles per instruction (ptxas wrapped each in an ELECT / R2UR / BRA.U.ANY loop); 4-byte
-// st.async broadcasts (4096 per CTA and step) and W_hh in shared memory were also tried first.
+// Measured step timeline (clock64, 16 streams, XG = 1, profiles/r02_gru_anatomy.txt): 48 MMAs 450 cycles, commit ->
+// gates 135, TMEM load + gates 645, fence 39, barrier + multicast through L2 + global stores 984  =>  2090 cycles / step
+// (round 1, DSMEM exchange: 2380; the FFMA kernel k_gru: 4700).  History of the issue loop: `if (lane == 0)` around each
+// MMA ~50 cycles per instruction (ptxas wrapped each in an ELECT / R2UR / BRA.U.ANY loop); every lane executing every
+// call with a per-call elect 16.7; one elected lane running the whole loop 9.6 (the tensor pipe's rate at N = 16).
 namespace cg = cooperative_groups;
 
 constexpr int kGtU = 32, kGtRows = 3 * kGtU;   // hidden units / W_hh rows per CTA (both hidden sizes)
