@@ -100,6 +100,19 @@ def kernel_model(cfg, g: dict) -> dict:
     }
 
 
+def per_gpu_report(rows, knames, streams: int, seconds: int):
+    """rows[r] = [device ms/step, end-to-end ms/step, roofline fraction, avg launch ms, index into knames (or -1), share of
+    the step] of rank r -> the `per_gpu` list of the JSON line.  Never raises (the line must not depend on it)."""
+    try:
+        num = lambda x: None if x != x else x   # NaN -> null
+        return [{"rank": r, "ms_per_step": row[0], "value": streams * seconds / (row[0] / 1e3),
+                 "e2e_ms_per_step": row[1], "e2e_value": streams * seconds / (row[1] / 1e3),
+                 "roofline_kernel": knames[int(row[4])] if row[4] >= 0 else None, "roofline_frac": num(row[2]),
+                 "avg_launch_ms": num(row[3]), "share_of_step": num(row[5])} for r, row in enumerate(rows)]
+    except Exception as e:
+        return [{"error": f"{type(e).__name__}: {e}"}]
+
+
 def ncu_traffic(model_name: str, streams: int, seconds: int):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) per kernel from the committed
     `ncu --set full` capture of exactly this workload (profiles/r02_ncu_traffic.json), or None."""
@@ -460,16 +473,7 @@ def measure(ctx: Ctx, cfg_id: int, model_name: str, streams: int, seconds: int, 
     own = [ms / steps, e2e_s * 1e3 / steps, (achieved / peak) if peak else float("nan"), avg_launch_s * 1e3,
            float(knames.index(kname.split("[")[0] if kname not in km else kname)) if (kname in km or kname.split("[")[0] in km) else -1.0,
            tot_ms / total_prof_ms]
-    rows = ctx.gather_rows(own)
-    per_gpu = None
-    try:
-        num = lambda x: None if x != x else x   # NaN -> null
-        per_gpu = [{"rank": r, "ms_per_step": row[0], "value": streams * seconds / (row[0] / 1e3),
-                    "e2e_ms_per_step": row[1], "e2e_value": streams * seconds / (row[1] / 1e3),
-                    "roofline_kernel": knames[int(row[4])] if row[4] >= 0 else None, "roofline_frac": num(row[2]),
-                    "avg_launch_ms": num(row[3]), "share_of_step": num(row[5])} for r, row in enumerate(rows)]
-    except Exception as e:  # a formatting problem must not take the line down
-        per_gpu = [{"error": f"{type(e).__name__}: {e}"}]
+    per_gpu = per_gpu_report(ctx.gather_rows(own), knames, streams, seconds)
     workload = (f"{model_name}, batch={streams} x {seconds} s 48 kHz synthetic noisy streams per GPU "
                 f"({BASELINE_NAME.get(cfg_id, 'custom')}), pad=True, {frames} frames/stream")
     res = {"cfg": cfg_id, "workload": workload, "model": model_name, "streams_per_gpu": streams, "seconds": seconds,

@@ -197,6 +197,12 @@ def test_bench_bookkeeping():
     _, derived = pack_state_dict(random_state_dict(cfg, seed=0), cfg)
     km = bench.kernel_model(cfg, derived)
     assert km["k_gru_tc512"][1] == 2 * 3 * 512 * 512 * 5 // 8 and km["k_gather_sum"][1] > 0 and km["k_convp_v1"][1] > 0
+    # per-GPU report: one row per rank, NaN -> null, unknown kernel -> null, malformed rows never raise
+    import json
+    rep = bench.per_gpu_report([[10.0, 12.5, 0.02, 0.8, 1.0, 0.3], [11.0, 13.0, float("nan"), float("nan"), -1.0, 0.4]], ["a", "b"], 128, 10)
+    assert rep[0]["value"] == 128000.0 and rep[0]["roofline_kernel"] == "b" and rep[1]["roofline_kernel"] is None
+    assert rep[1]["roofline_frac"] is None and json.loads(json.dumps(rep))[1]["rank"] == 1
+    assert "error" in bench.per_gpu_report([[1.0]], ["a"], 1, 1)[0]
 
 
 
